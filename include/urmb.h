@@ -1,0 +1,147 @@
+/* include/urmb.h -- C ABI of the B200-native URMAP mapping engine (liburmb.so).
+ *
+ * URMAP has no plugin / FFI interface of its own; the in-process boundary a
+ * drop-in replacement slots under is the one its worker threads use:
+ *
+ *     MapThread      /root/reference/src/map.cpp:11-25    State1::SetUFI, State1::Search, Output1
+ *     UFIMapThread   /root/reference/src/map2.cpp:11-37   State2::SetUFI, State2::Search
+ *     UFIndex::FromFile  /root/reference/src/ufindexio.cpp:60-115
+ *
+ * Each entry point below names the reference interface it replaces.  Plain pointers and
+ * sizes only; no C++ or torch types.  All functions return 0 on success, a negative URMB_E_*
+ * code on failure (never exit()); urmb_last_error() gives the message (the reference instead
+ * terminates the process through Die(), myutils.cpp:915).
+ *
+ * Threading: one urmb_ctx per GPU; a ctx may be driven by one host thread at a time.  A ctx
+ * owns URMB_SLOTS batch slots so that the H2D copy of batch k+1, the kernels of batch k and
+ * the D2H copy of batch k-1 overlap on separate CUDA streams.
+ */
+#ifndef URMB_H
+#define URMB_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URMB_OK 0
+#define URMB_E_ARG (-1)       /* bad argument */
+#define URMB_E_IO (-2)        /* file error / bad UFI magic */
+#define URMB_E_CUDA (-3)      /* CUDA runtime error */
+#define URMB_E_NOMEM (-4)
+#define URMB_E_OVERFLOW (-5)  /* a per-read capacity (hits, HSPs, path runs, runs pool) was exceeded */
+#define URMB_E_UNSUPPORTED (-6) /* read longer than URMB_MAX_READ_LEN, word length > 32, ... */
+#define URMB_E_NODEVICE (-7)  /* no CUDA device: there is NO CPU fallback */
+
+#define URMB_SLOTS 3
+#define URMB_MAX_READ_LEN 256
+
+typedef struct urmb_index_host urmb_index_host; /* parsed UFI file in (pinned) host memory */
+typedef struct urmb_ctx urmb_ctx;               /* per-GPU context */
+
+/* Scoring "method" (State1::SetMethod, state1.cpp:147-183; map.cpp:34-37; map2.cpp:15-21,46-48). */
+typedef struct urmb_params {
+    int32_t method;      /* 6 = default, 7 = -map -veryfast */
+    int32_t pe_method;   /* 4 = default -map2 (Search4), 5 = -map2 -veryfast (Search5) */
+    int32_t band_radius; /* <0: method default (12 / 8; Search5 uses 4) */
+    int32_t minq;        /* statistics only (map2.cpp:75) */
+} urmb_params;
+
+/* A batch of reads: concatenated ASCII bases + n+1 offsets (what FASTQSeqSource::GetNext,
+ * fastqseqsource.cpp:9, hands to State1::Search one read at a time). Labels and qualities
+ * stay on the host. */
+typedef struct urmb_batch {
+    uint32_t n;
+    const uint8_t *seqs;
+    const uint32_t *offs;
+} urmb_batch;
+
+/* Per-read result: exactly the fields State1::SetSAM / State2::SetSAM2 consume
+ * (m_TopHit->{m_DBStartPos,m_Plus,m_Score,m_Path}, m_Mapq; setsam.cpp:75, output2.cpp:71). */
+typedef struct urmb_result {
+    uint32_t db_pos;    /* m_TopHit->m_DBStartPos, 0xFFFFFFFF when there is no top hit */
+    uint32_t path_off;  /* first run of the path in the runs pool */
+    uint16_t path_runs; /* 0 => empty path (gapless hit, CIGAR "<QL>M") */
+    int16_t score;      /* m_TopHit->m_Score */
+    int16_t best;       /* m_BestScore */
+    int16_t second;     /* m_SecondBestScore */
+    uint8_t mapq;       /* m_Mapq */
+    uint8_t flags;      /* bit0 plus strand, bit1 has top hit, bit7 capacity overflow */
+    uint8_t hit_count;
+    uint8_t hsp_count;
+} urmb_result;
+/* path run: u16 = (len << 2) | op, op 0='M' 1='D' 2='I' in the reference's PATH alphabet
+ * (D consumes the read, I consumes the genome; PathToCIGAR, cigar.cpp:22-25, swaps them). */
+
+typedef struct urmb_contig {
+    uint32_t length;
+    uint32_t offset; /* into the concatenated sequence data */
+    const char *label;
+} urmb_contig;
+
+/* Device-resident index description for urmb_index_attach (e.g. buffers that arrived by an
+ * NCCL broadcast). d_blob must hold 5*slot_count+16 bytes, d_seq seq_data_size+URMB_SEQ_PAD
+ * bytes with the padding zero-filled. */
+#define URMB_SEQ_PAD 4096
+#define URMB_BLOB_PAD 16
+typedef struct urmb_index_desc {
+    uint32_t word_length;
+    uint32_t max_ix;
+    uint32_t seq_data_size;
+    uint32_t reserved;
+    uint64_t slot_count;
+    const void *d_blob;
+    const void *d_seq;
+} urmb_index_desc;
+
+/* Kernel timings of the last launch on a slot (CUDA events on the slot's stream). */
+typedef struct urmb_timing {
+    float probe_ms;  /* slot-probe / gather kernel */
+    float search_ms; /* search state-machine kernel (extension + DP + MAPQ) */
+    float h2d_ms;
+    float d2h_ms;
+} urmb_timing;
+
+/* ---- index: replaces UFIndex::FromFile (ufindexio.cpp:51,60-115) ---- */
+int urmb_index_load_host(const char *ufi_path, urmb_index_host **out);
+void urmb_index_free_host(urmb_index_host *h);
+int urmb_index_info(const urmb_index_host *h, urmb_index_desc *desc /* d_* = host pointers */,
+                    uint32_t *n_contigs);
+int urmb_index_contig(const urmb_index_host *h, uint32_t i, urmb_contig *out);
+
+/* ---- context: replaces the per-thread State1 / State2 objects (map.cpp:13, map2.cpp:14) ---- */
+int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out);
+void urmb_ctx_destroy(urmb_ctx *c);
+const char *urmb_last_error(const urmb_ctx *c); /* c may be NULL: last global error */
+
+/* ---- State1::SetUFI / State2::SetUFI (state1.cpp:185, state2.cpp:14) ---- */
+int urmb_index_upload(urmb_ctx *c, const urmb_index_host *h);   /* H2D copy, ctx owns the buffers */
+int urmb_index_attach(urmb_ctx *c, const urmb_index_desc *d);   /* caller-owned device buffers */
+int urmb_index_broadcast(urmb_ctx **ctxs, int n, const urmb_index_host *h); /* one process, n GPUs */
+int urmb_index_device_desc(const urmb_ctx *c, urmb_index_desc *out);
+
+/* ---- mapping: State1::Search (search1.cpp:7) / State2::Search (search2.cpp:59) ---- */
+/* Synchronous convenience calls on slot 0: host buffers in, host buffers out. */
+int urmb_map_se(urmb_ctx *c, const urmb_batch *in, urmb_result *out, uint16_t *runs, uint32_t runs_cap,
+                uint32_t *runs_used);
+int urmb_map_pe(urmb_ctx *c, const urmb_batch *r1, const urmb_batch *r2, urmb_result *out1,
+                urmb_result *out2, uint16_t *runs, uint32_t runs_cap, uint32_t *runs_used);
+
+/* Pipelined calls: stage -> (upload, launch, download are enqueued on the slot's stream) -> wait.
+ * r2 == NULL selects single-end.  After urmb_wait the results of the slot stay valid in pinned
+ * host memory until the slot is staged again. */
+int urmb_submit(urmb_ctx *c, int slot, const urmb_batch *r1, const urmb_batch *r2);
+int urmb_wait(urmb_ctx *c, int slot, const urmb_result **res1, const urmb_result **res2,
+              const uint16_t **runs, uint32_t *runs_used);
+/* Finer-grained steps (bench.py uses them to time the kernels with inputs resident in HBM). */
+int urmb_upload(urmb_ctx *c, int slot, const urmb_batch *r1, const urmb_batch *r2);
+int urmb_launch(urmb_ctx *c, int slot);
+int urmb_download(urmb_ctx *c, int slot);
+int urmb_timing_last(urmb_ctx *c, int slot, urmb_timing *t);
+/* Number of kernels launched by this ctx so far. */
+uint64_t urmb_launch_count(const urmb_ctx *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URMB_H */

@@ -1,0 +1,165 @@
+// tests/emu/emu.cpp -- DEBUGGING HARNESS, NOT PRODUCT CODE (see tests/emu/cuda_runtime.h).
+// Compiles urmap_b200/csrc/urmb_kernels.cu as C++ on top of a lock-step fiber emulation of one warp.
+#include "cuda_runtime.h"
+
+#include "../../urmap_b200/csrc/urmb_kernels.cu"
+
+emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+namespace emu {
+
+struct Lane {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    bool done = false, waiting = false;
+    Kind kind = K_NONE;
+    uint64_t value = 0, result = 0;
+    int arg = 0, site = 0;
+};
+static Lane g_lanes[32];
+static ucontext_t g_sched;
+static int g_cur = 0;
+static const std::function<void()> *g_body = nullptr;
+static uint8_t *g_smem = nullptr;
+static const size_t kStack = 1 << 20;
+
+uint8_t *smem_base() { return g_smem; }
+
+static void lane_entry() {
+    (*g_body)();
+    g_lanes[g_cur].done = true;
+    swapcontext(&g_lanes[g_cur].ctx, &g_sched);
+}
+
+uint64_t collective(Kind kind, uint64_t value, int arg, int site) {
+    Lane &L = g_lanes[g_cur];
+    L.kind = kind;
+    L.value = value;
+    L.arg = arg;
+    L.site = site;
+    L.waiting = true;
+    swapcontext(&L.ctx, &g_sched);
+    return L.result;
+}
+
+static void run_warp(int warp) {
+    for (int l = 0; l < 32; ++l) {
+        Lane &L = g_lanes[l];
+        if (!L.stack) L.stack = (char *)malloc(kStack);
+        getcontext(&L.ctx);
+        L.ctx.uc_stack.ss_sp = L.stack;
+        L.ctx.uc_stack.ss_size = kStack;
+        L.ctx.uc_link = &g_sched;
+        makecontext(&L.ctx, lane_entry, 0);
+        L.done = L.waiting = false;
+    }
+    for (;;) {
+        for (int l = 0; l < 32; ++l) {
+            Lane &L = g_lanes[l];
+            if (L.done || L.waiting) continue;
+            g_cur = l;
+            threadIdx.x = (unsigned)(warp * 32 + l);
+            swapcontext(&g_sched, &L.ctx);
+        }
+        int ndone = 0;
+        for (int l = 0; l < 32; ++l) ndone += g_lanes[l].done;
+        if (ndone == 32) return;
+        if (ndone != 0) {
+            fprintf(stderr, "EMU: %d lanes exited while others wait at a collective (site %d)\n", ndone,
+                    g_lanes[0].done ? -1 : g_lanes[0].site);
+            abort();
+        }
+        const Kind k = g_lanes[0].kind;
+        const int site = g_lanes[0].site;
+        for (int l = 1; l < 32; ++l)
+            if (g_lanes[l].kind != k || g_lanes[l].site != site) {
+                fprintf(stderr, "EMU: warp divergence at a collective: lane0 kind %d line %d, lane%d kind %d line %d\n", k,
+                        site, l, g_lanes[l].kind, g_lanes[l].site);
+                abort();
+            }
+        unsigned bal = 0;
+        for (int l = 0; l < 32; ++l)
+            if (g_lanes[l].value & 1) bal |= 1u << l;
+        for (int l = 0; l < 32; ++l) {
+            Lane &L = g_lanes[l];
+            switch (k) {
+                case K_SHFL: L.result = g_lanes[L.arg & 31].value; break;
+                case K_SHFL_UP: L.result = (l - L.arg >= 0) ? g_lanes[l - L.arg].value : L.value; break;
+                case K_BALLOT: L.result = bal; break;
+                case K_ANY: L.result = bal != 0; break;
+                default: L.result = 0; break;
+            }
+            L.waiting = false;
+        }
+    }
+}
+
+void launch(const std::function<void()> &body, int grid, int block, size_t smem) {
+    g_body = &body;
+    gridDim.x = (unsigned)grid;
+    blockDim.x = (unsigned)block;
+    std::vector<uint8_t> sm(smem + 64, 0xCD);
+    g_smem = sm.data();
+    for (int b = 0; b < grid; ++b) {
+        blockIdx.x = (unsigned)b;
+        for (int w = 0; w < block / 32; ++w) run_warp(w);
+    }
+    g_smem = nullptr;
+}
+
+}  // namespace emu
+
+using namespace urmb;
+
+static DevParams emu_make_params(const urmb_params &p) {  // same table as urmb_api.cu make_params
+    DevParams P;
+    if (p.method == 7) P = DevParams{-4, -6, -2, 35, 35, 12, 75, 8, 6, 5, 8u, 4};
+    else P = DevParams{-3, -5, -1, 20, 60, 9, 100, 1, 1, 1, 12u, 4};
+    P.pe_method = (p.pe_method == 5) ? 5 : 4;
+    if (p.band_radius >= 0) P.R = (uint32_t)p.band_radius;
+    else if (p.pe_method == 5) P.R = 4;
+    return P;
+}
+
+// seqs/offs: n_reads+1 offsets; for paired input read n_units+i is the mate of read i.
+extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t seq_size, uint64_t slot_count,
+                       uint32_t word_len, uint32_t max_ix, const urmb_params *p, const uint8_t *seqs,
+                       const uint32_t *offs, uint32_t n_units, int paired, urmb_result *res, uint16_t *runs,
+                       uint32_t runs_cap, uint32_t *counters /*[4]*/) {
+    DevIndex ix;
+    ix.blob = blob;
+    ix.seq = seq_padded;
+    ix.slot_count = slot_count;
+    ix.magic = (uint64_t)((((unsigned __int128)1) << 64) / slot_count);
+    ix.shift_mask = (word_len >= 32) ? ~0ull : ((1ull << (2 * word_len)) - 1);
+    ix.seq_size = seq_size;
+    ix.word_len = word_len;
+    ix.max_ix = max_ix;
+    DevParams P = emu_make_params(*p);
+    const uint32_t nreads = paired ? 2 * n_units : n_units;
+    uint32_t maxlen = 0;
+    for (uint32_t i = 0; i < nreads; ++i) maxlen = std::max(maxlen, offs[i + 1] - offs[i]);
+    if (maxlen > (uint32_t)kMaxLen) return URMB_E_UNSUPPORTED;
+    const uint32_t qwc = maxlen >= word_len ? maxlen - word_len + 1 : 1;
+    DevBatch b;
+    b.seqs = seqs;
+    b.offs = offs;
+    b.n_reads = nreads;
+    b.n_units = n_units;
+    b.qcap = (qwc + 31) & ~31u;
+    b.seqcap = (std::max(maxlen, 32u) + 31) & ~31u;
+    b.paired = paired;
+    std::vector<uint8_t> tally((size_t)nreads * 2 * b.qcap);
+    std::vector<uint32_t> pos((size_t)nreads * 2 * b.qcap);
+    std::vector<uint64_t> slot((size_t)nreads * 2 * b.qcap);
+    DevProbe pr{tally.data(), pos.data(), slot.data()};
+    memset(counters, 0, 16);
+    DevOut o{res, runs, runs_cap, counters};
+    const int nw = 4;
+    WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch) * nw);
+    memset(ws, 0xEE, sizeof(WarpScratch) * nw);
+    launch_probe(ix, b, pr, nullptr, 1);
+    launch_search(ix, P, b, pr, o, ws, nw, nullptr, 1, nullptr);
+    free(ws);
+    return 0;
+}

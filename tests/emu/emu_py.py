@@ -1,0 +1,51 @@
+"""ctypes wrapper of the debugging emulator (tests/emu/libemu.so). Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Params(C.Structure):
+    _fields_ = [("method", C.c_int32), ("pe_method", C.c_int32), ("band_radius", C.c_int32), ("minq", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(HERE, "libemu.so")
+        src = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_runtime.h"),
+               os.path.join(HERE, "../../urmap_b200/csrc/urmb_kernels.cu")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+            subprocess.check_call([os.path.join(HERE, "build.sh")])
+        _lib = C.CDLL(so)
+        _lib.emu_map.restype = C.c_int
+    return _lib
+
+
+def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, band_radius=-1):
+    """oix: oracle_py.Index (only used as a UFI parser that exposes blob/seq pointers)."""
+    L = lib()
+    seq = np.zeros(oix.seq_size + 4096, dtype=np.uint8)
+    seq[:oix.seq_size] = oix.seq()
+    blob = oix.blob()
+    nreads = 2 * n_units if paired else n_units
+    res = np.zeros(nreads, dtype=res_dtype)
+    cap = 64 * nreads + 1024
+    runs = np.zeros(cap, dtype=np.uint16)
+    counters = np.zeros(4, dtype=np.uint32)
+    p = Params(method, pe_method, band_radius, 10)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint32)
+    vp = C.c_void_p
+    rc = L.emu_map(blob.ctypes.data_as(vp), seq.ctypes.data_as(vp), C.c_uint32(oix.seq_size), C.c_uint64(oix.slot_count),
+                   C.c_uint32(oix.word_length), C.c_uint32(oix.max_ix), C.byref(p), seqs.ctypes.data_as(vp),
+                   offs.ctypes.data_as(vp), C.c_uint32(n_units), C.c_int(1 if paired else 0), res.ctypes.data_as(vp),
+                   runs.ctypes.data_as(vp), C.c_uint32(cap), counters.ctypes.data_as(vp))
+    assert rc == 0, rc
+    return res, runs, counters

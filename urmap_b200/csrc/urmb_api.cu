@@ -1,0 +1,605 @@
+// urmb_api.cu -- C-ABI layer (include/urmb.h): UFI loader, per-GPU context, batch slots, streams.
+//
+// There is deliberately no CPU mapping path here: every urmb_map_* / urmb_submit call runs the CUDA
+// kernels or fails with URMB_E_NODEVICE / URMB_E_CUDA.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "urmb_internal.h"
+
+using namespace urmb;
+
+static std::string g_last_error;
+static std::mutex g_err_mu;
+
+static void set_global_error(const std::string &s) {
+    std::lock_guard<std::mutex> l(g_err_mu);
+    g_last_error = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// UFI file (ufindexio.cpp:15-49 writer / 60-115 reader). All integers little-endian, no padding.
+// ---------------------------------------------------------------------------------------
+struct urmb_index_host {
+    int fd = -1;
+    uint8_t *map = nullptr;
+    size_t map_len = 0;
+    uint32_t word_length = 0, max_ix = 0, seq_data_size = 0;
+    uint64_t slot_count = 0;
+    std::vector<std::string> labels;
+    std::vector<uint32_t> lengths, offsets;
+    const uint8_t *blob = nullptr;
+    const uint8_t *seq = nullptr;
+};
+
+extern "C" int urmb_index_load_host(const char *path, urmb_index_host **out) {
+    if (!path || !out) return URMB_E_ARG;
+    *out = nullptr;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_global_error(std::string("cannot open ") + path); return URMB_E_IO; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size < 40) { close(fd); set_global_error("UFI file too small"); return URMB_E_IO; }
+    uint8_t *m = (uint8_t *)mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { close(fd); set_global_error("mmap failed"); return URMB_E_IO; }
+    urmb_index_host *h = new urmb_index_host;
+    h->fd = fd;
+    h->map = m;
+    h->map_len = (size_t)sb.st_size;
+    size_t o = 0;
+    bool ok = true;
+    auto need = [&](size_t n) { if (o + n > h->map_len) ok = false; return ok; };
+    auto u32 = [&]() -> uint32_t { uint32_t v = 0; if (need(4)) { memcpy(&v, m + o, 4); o += 4; } return v; };
+    auto u64 = [&]() -> uint64_t { uint64_t v = 0; if (need(8)) { memcpy(&v, m + o, 8); o += 8; } return v; };
+    ok = (u32() == 0x55464931u) && ok;  // 'UFI1'
+    h->word_length = u32();
+    h->max_ix = u32();
+    h->seq_data_size = u32();
+    h->slot_count = u64();
+    uint32_t nseq = u32();
+    for (uint32_t i = 0; ok && i < nseq; ++i) {
+        h->lengths.push_back(u32());
+        h->offsets.push_back(u32());
+        uint32_t n = u32();
+        if (!need(n)) break;
+        std::string lab((const char *)m + o, n);
+        h->labels.push_back(std::string(lab.c_str()));  // the reference builds the label from a C string
+        o += n;
+    }
+    ok = ok && (u32() == 0x55464932u);  // 'UFI2'
+    h->blob = m + o;
+    if (ok && need(5 * (size_t)h->slot_count)) o += 5 * (size_t)h->slot_count;
+    ok = ok && (u32() == 0x55464933u);  // 'UFI3'
+    h->seq = m + o;
+    if (ok && need(h->seq_data_size)) o += h->seq_data_size;
+    ok = ok && (u32() == 0x55464935u);  // 'UFI5'
+    if (!ok) {
+        set_global_error(std::string("not a UFI file (bad magic or truncated): ") + path);
+        urmb_index_free_host(h);
+        return URMB_E_IO;
+    }
+    *out = h;
+    return URMB_OK;
+}
+
+extern "C" void urmb_index_free_host(urmb_index_host *h) {
+    if (!h) return;
+    if (h->map) munmap(h->map, h->map_len);
+    if (h->fd >= 0) close(h->fd);
+    delete h;
+}
+
+extern "C" int urmb_index_info(const urmb_index_host *h, urmb_index_desc *d, uint32_t *n_contigs) {
+    if (!h) return URMB_E_ARG;
+    if (d) {
+        d->word_length = h->word_length;
+        d->max_ix = h->max_ix;
+        d->seq_data_size = h->seq_data_size;
+        d->reserved = 0;
+        d->slot_count = h->slot_count;
+        d->d_blob = h->blob;
+        d->d_seq = h->seq;
+    }
+    if (n_contigs) *n_contigs = (uint32_t)h->labels.size();
+    return URMB_OK;
+}
+
+extern "C" int urmb_index_contig(const urmb_index_host *h, uint32_t i, urmb_contig *out) {
+    if (!h || !out || i >= h->labels.size()) return URMB_E_ARG;
+    out->length = h->lengths[i];
+    out->offset = h->offsets[i];
+    out->label = h->labels[i].c_str();
+    return URMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct Slot {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_h2d0 = nullptr, ev_h2d = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_d2h = nullptr;
+    // pinned host staging
+    uint8_t *h_seqs = nullptr; size_t h_seqs_cap = 0;
+    uint32_t *h_offs = nullptr; size_t h_offs_cap = 0;
+    urmb_result *h_res = nullptr; size_t h_res_cap = 0;
+    uint16_t *h_runs = nullptr; size_t h_runs_cap = 0;
+    uint32_t *h_counters = nullptr;
+    // device
+    uint8_t *d_seqs = nullptr; size_t d_seqs_cap = 0;
+    uint32_t *d_offs = nullptr; size_t d_offs_cap = 0;
+    uint8_t *d_tally = nullptr; uint32_t *d_pos = nullptr; uint64_t *d_slot = nullptr; size_t d_probe_cap = 0;
+    urmb_result *d_res = nullptr; size_t d_res_cap = 0;
+    uint16_t *d_runs = nullptr; size_t d_runs_cap = 0;
+    uint32_t *d_counters = nullptr;
+    DevBatch batch{};
+    size_t seq_bytes = 0;
+    bool staged = false, launched = false, downloaded = false;
+};
+
+struct urmb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    urmb_params params{};
+    DevParams P{};
+    DevIndex ix{};
+    bool have_index = false;
+    void *own_blob = nullptr, *own_seq = nullptr;
+    cudaStream_t compute = nullptr;
+    WarpScratch *scratch = nullptr;
+    int n_scratch_warps = 0;
+    Slot slots[URMB_SLOTS];
+    uint64_t launches = 0;
+    std::string err;
+};
+
+static int fail(urmb_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    set_global_error(msg);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, URMB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+static DevParams make_params(const urmb_params &p) {  // State1::SetMethod, state1.cpp:147-183
+    DevParams P;
+    if (p.method == 7) P = DevParams{-4, -6, -2, 35, 35, 12, 75, 8, 6, 5, 8u, 4};
+    else P = DevParams{-3, -5, -1, 20, 60, 9, 100, 1, 1, 1, 12u, 4};
+    P.pe_method = (p.pe_method == 5) ? 5 : 4;
+    if (p.band_radius >= 0) P.R = (uint32_t)p.band_radius;
+    else if (p.pe_method == 5) P.R = 4;   // map2.cpp:17-21
+    return P;
+}
+
+extern "C" const char *urmb_last_error(const urmb_ctx *c) {
+    if (c) return c->err.c_str();
+    return g_last_error.c_str();
+}
+
+extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out) {
+    if (!out) return URMB_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_global_error("no CUDA device available (the mapping engine has no CPU fallback)");
+        return URMB_E_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) { set_global_error("bad device ordinal"); return URMB_E_ARG; }
+    urmb_ctx *c = new urmb_ctx;
+    c->device = device;
+    urmb_params dflt{6, 4, -1, 10};
+    c->params = p ? *p : dflt;
+    if (c->params.method != 7) c->params.method = 6;
+    c->P = make_params(c->params);
+    if (c->P.R > 12) { delete c; set_global_error("band radius > 12 unsupported"); return URMB_E_UNSUPPORTED; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    c->n_scratch_warps = c->sm_count * 24;
+    CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
+    for (auto &s : c->slots) {
+        CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+        for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h}) CK(cudaEventCreate(ev));
+        CK(cudaMalloc(&s.d_counters, 16));
+        CK(cudaHostAlloc(&s.h_counters, 16, cudaHostAllocDefault));
+    }
+    *out = c;
+    return URMB_OK;
+}
+
+static void free_slot(Slot &s) {
+    if (s.copy) cudaStreamDestroy(s.copy);
+    for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h}) if (ev) cudaEventDestroy(ev);
+    cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
+    cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_slot);
+    cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters);
+}
+
+extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->slots) free_slot(s);
+    if (c->compute) cudaStreamDestroy(c->compute);
+    cudaFree(c->scratch);
+    cudaFree(c->own_blob);
+    cudaFree(c->own_seq);
+    delete c;
+}
+
+static int set_index(urmb_ctx *c, const urmb_index_desc *d) {
+    if (d->word_length < 8 || d->word_length > 32) return fail(c, URMB_E_UNSUPPORTED, "word length must be in [8,32]");
+    if (d->max_ix < 1 || d->max_ix > 32) return fail(c, URMB_E_UNSUPPORTED, "max_ix must be in [1,32]");
+    if (d->slot_count < 2 || d->slot_count >= (1ull << 62)) return fail(c, URMB_E_ARG, "bad slot count");
+    c->ix.blob = (const uint8_t *)d->d_blob;
+    c->ix.seq = (const uint8_t *)d->d_seq;
+    c->ix.slot_count = d->slot_count;
+    c->ix.magic = (uint64_t)((((unsigned __int128)1) << 64) / d->slot_count);
+    c->ix.shift_mask = (d->word_length >= 32) ? ~0ull : ((1ull << (2 * d->word_length)) - 1);
+    c->ix.seq_size = d->seq_data_size;
+    c->ix.word_len = d->word_length;
+    c->ix.max_ix = d->max_ix;
+    c->have_index = true;
+    return URMB_OK;
+}
+
+extern "C" int urmb_index_attach(urmb_ctx *c, const urmb_index_desc *d) {
+    if (!c || !d || !d->d_blob || !d->d_seq) return URMB_E_ARG;
+    return set_index(c, d);
+}
+
+extern "C" int urmb_index_device_desc(const urmb_ctx *c, urmb_index_desc *out) {
+    if (!c || !out || !c->have_index) return URMB_E_ARG;
+    out->word_length = c->ix.word_len;
+    out->max_ix = c->ix.max_ix;
+    out->seq_data_size = c->ix.seq_size;
+    out->reserved = 0;
+    out->slot_count = c->ix.slot_count;
+    out->d_blob = c->ix.blob;
+    out->d_seq = c->ix.seq;
+    return URMB_OK;
+}
+
+// Chunked H2D through two pinned staging buffers (the 30 GB human-scale file is never pinned whole).
+static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n) {
+    const size_t CH = 64u << 20;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    CK(cudaHostAlloc(&stage[0], CH, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&stage[1], CH, cudaHostAllocDefault));
+    CK(cudaEventCreate(&ev[0]));
+    CK(cudaEventCreate(&ev[1]));
+    int k = 0;
+    for (size_t o = 0; o < n; o += CH, k ^= 1) {
+        size_t m = std::min(CH, n - o);
+        CK(cudaEventSynchronize(ev[k]));
+        memcpy(stage[k], src + o, m);
+        CK(cudaMemcpyAsync((uint8_t *)dst + o, stage[k], m, cudaMemcpyHostToDevice, c->compute));
+        CK(cudaEventRecord(ev[k], c->compute));
+    }
+    CK(cudaStreamSynchronize(c->compute));
+    cudaFreeHost(stage[0]);
+    cudaFreeHost(stage[1]);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    return URMB_OK;
+}
+
+extern "C" int urmb_index_upload(urmb_ctx *c, const urmb_index_host *h) {
+    if (!c || !h) return URMB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->own_blob);
+    cudaFree(c->own_seq);
+    c->own_blob = c->own_seq = nullptr;
+    const size_t nb = 5 * (size_t)h->slot_count, ns = h->seq_data_size;
+    CK(cudaMalloc(&c->own_blob, nb + URMB_BLOB_PAD));
+    CK(cudaMalloc(&c->own_seq, ns + URMB_SEQ_PAD));
+    CK(cudaMemset((uint8_t *)c->own_blob + nb, 0, URMB_BLOB_PAD));
+    CK(cudaMemset((uint8_t *)c->own_seq + ns, 0, URMB_SEQ_PAD));
+    int rc = upload_region(c, c->own_blob, h->blob, nb);
+    if (rc) return rc;
+    rc = upload_region(c, c->own_seq, h->seq, ns);
+    if (rc) return rc;
+    urmb_index_desc d;
+    urmb_index_info(h, &d, nullptr);
+    d.d_blob = c->own_blob;
+    d.d_seq = c->own_seq;
+    return set_index(c, &d);
+}
+
+// One process, n GPUs: upload to ctx 0, then device-to-device copies (NVLink when peers are enabled).
+// The one-process-per-GPU path (bench.py) instead broadcasts with NCCL and calls urmb_index_attach.
+extern "C" int urmb_index_broadcast(urmb_ctx **ctxs, int n, const urmb_index_host *h) {
+    if (!ctxs || n < 1 || !h) return URMB_E_ARG;
+    int rc = urmb_index_upload(ctxs[0], h);
+    if (rc) return rc;
+    const size_t nb = 5 * (size_t)h->slot_count + URMB_BLOB_PAD, ns = (size_t)h->seq_data_size + URMB_SEQ_PAD;
+    for (int i = 1; i < n; ++i) {
+        urmb_ctx *c = ctxs[i];
+        CK(cudaSetDevice(c->device));
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, c->device, ctxs[0]->device);
+        if (can) cudaDeviceEnablePeerAccess(ctxs[0]->device, 0);
+        cudaGetLastError();
+        cudaFree(c->own_blob);
+        cudaFree(c->own_seq);
+        CK(cudaMalloc(&c->own_blob, nb));
+        CK(cudaMalloc(&c->own_seq, ns));
+        CK(cudaMemcpyPeer(c->own_blob, c->device, ctxs[0]->own_blob, ctxs[0]->device, nb));
+        CK(cudaMemcpyPeer(c->own_seq, c->device, ctxs[0]->own_seq, ctxs[0]->device, ns));
+        urmb_index_desc d;
+        urmb_index_info(h, &d, nullptr);
+        d.d_blob = c->own_blob;
+        d.d_seq = c->own_seq;
+        rc = set_index(c, &d);
+        if (rc) return rc;
+    }
+    return URMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// batches
+// ---------------------------------------------------------------------------------------
+template <class T>
+static int grow_host(urmb_ctx *c, T *&p, size_t &cap, size_t need) {
+    if (need <= cap) return URMB_OK;
+    size_t ncap = std::max(need, cap * 2);
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    CK(cudaHostAlloc(&p, ncap * sizeof(T), cudaHostAllocDefault));
+    cap = ncap;
+    return URMB_OK;
+}
+template <class T>
+static int grow_dev(urmb_ctx *c, T *&p, size_t &cap, size_t need) {
+    if (need <= cap) return URMB_OK;
+    size_t ncap = std::max(need, cap * 2);
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CK(cudaMalloc(&p, ncap * sizeof(T)));
+    cap = ncap;
+    return URMB_OK;
+}
+
+static int check_batch(urmb_ctx *c, const urmb_batch *b) {
+    if (!b || (b->n && (!b->seqs || !b->offs))) return fail(c, URMB_E_ARG, "null batch");
+    return URMB_OK;
+}
+
+extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb_batch *r2) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    if (!c->have_index) return fail(c, URMB_E_ARG, "no index attached");
+    int rc = check_batch(c, r1);
+    if (rc) return rc;
+    if (r2) {
+        rc = check_batch(c, r2);
+        if (rc) return rc;
+        if (r2->n != r1->n) return fail(c, URMB_E_ARG, "mate batches differ in size (map2.cpp:31 dies here)");
+    }
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slots[si];
+    const uint32_t n = r1->n, nreads = r2 ? 2 * n : n;
+    const size_t b1 = n ? r1->offs[n] - r1->offs[0] : 0, b2 = (r2 && n) ? r2->offs[n] - r2->offs[0] : 0;
+    const size_t nbytes = b1 + b2;
+    if (nbytes >= 0xFFFFFFF0ull) return fail(c, URMB_E_UNSUPPORTED, "batch larger than 4 GB of bases");
+    // previous use of this slot must have drained
+    CK(cudaStreamSynchronize(s.copy));
+    if ((rc = grow_host(c, s.h_seqs, s.h_seqs_cap, nbytes + 64))) return rc;
+    if ((rc = grow_host(c, s.h_offs, s.h_offs_cap, (size_t)nreads + 1))) return rc;
+    if ((rc = grow_dev(c, s.d_seqs, s.d_seqs_cap, nbytes + 64))) return rc;
+    if ((rc = grow_dev(c, s.d_offs, s.d_offs_cap, (size_t)nreads + 1))) return rc;
+    uint32_t maxlen = 0;
+    if (n) {
+        memcpy(s.h_seqs, r1->seqs + r1->offs[0], b1);
+        const uint32_t o0 = r1->offs[0];
+        for (uint32_t i = 0; i <= n; ++i) s.h_offs[i] = r1->offs[i] - o0;
+        for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r1->offs[i + 1] - r1->offs[i]);
+        if (r2) {
+            memcpy(s.h_seqs + b1, r2->seqs + r2->offs[0], b2);
+            const uint32_t p0 = r2->offs[0];
+            for (uint32_t i = 0; i <= n; ++i) s.h_offs[n + i] = (uint32_t)b1 + (r2->offs[i] - p0);
+            for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r2->offs[i + 1] - r2->offs[i]);
+        }
+    } else {
+        s.h_offs[0] = 0;
+    }
+    if (maxlen > (uint32_t)kMaxLen)
+        return fail(c, URMB_E_UNSUPPORTED, "read longer than URMB_MAX_READ_LEN (256) in batch");
+    const uint32_t W = c->ix.word_len;
+    const uint32_t qwc = maxlen >= W ? maxlen - W + 1 : 1;
+    DevBatch &b = s.batch;
+    b.seqs = s.d_seqs;
+    b.offs = s.d_offs;
+    b.n_reads = nreads;
+    b.n_units = n;
+    b.qcap = (qwc + 31) & ~31u;
+    b.seqcap = (std::max(maxlen, 32u) + 31) & ~31u;
+    b.paired = r2 ? 1 : 0;
+    s.seq_bytes = nbytes;
+    const size_t probe_need = (size_t)nreads * 2 * b.qcap;
+    if (probe_need > s.d_probe_cap) {
+        cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_slot);
+        s.d_tally = nullptr; s.d_pos = nullptr; s.d_slot = nullptr;
+        s.d_probe_cap = 0;
+        size_t ncap = std::max(probe_need, (size_t)1024);
+        CK(cudaMalloc(&s.d_tally, ncap));
+        CK(cudaMalloc(&s.d_pos, ncap * 4));
+        CK(cudaMalloc(&s.d_slot, ncap * 8));
+        s.d_probe_cap = ncap;
+    }
+    if ((rc = grow_dev(c, s.d_res, s.d_res_cap, (size_t)nreads + 1))) return rc;
+    if ((rc = grow_host(c, s.h_res, s.h_res_cap, (size_t)nreads + 1))) return rc;
+    const size_t runs_need = (size_t)nreads * 8 + 4096;
+    if ((rc = grow_dev(c, s.d_runs, s.d_runs_cap, runs_need))) return rc;
+    if ((rc = grow_host(c, s.h_runs, s.h_runs_cap, s.d_runs_cap))) return rc;
+    CK(cudaEventRecord(s.ev_h2d0, s.copy));
+    CK(cudaMemcpyAsync(s.d_seqs, s.h_seqs, nbytes, cudaMemcpyHostToDevice, s.copy));
+    CK(cudaMemcpyAsync(s.d_offs, s.h_offs, ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, s.copy));
+    CK(cudaEventRecord(s.ev_h2d, s.copy));
+    s.staged = true;
+    s.launched = false;
+    s.downloaded = false;
+    return URMB_OK;
+}
+
+extern "C" int urmb_launch(urmb_ctx *c, int si) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    Slot &s = c->slots[si];
+    if (!s.staged) return fail(c, URMB_E_ARG, "slot not staged");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamWaitEvent(c->compute, s.ev_h2d, 0));
+    CK(cudaMemsetAsync(s.d_counters, 0, 16, c->compute));
+    CK(cudaEventRecord(s.ev_k0, c->compute));
+    if (s.batch.n_reads) {
+        DevProbe pr{s.d_tally, s.d_pos, s.d_slot};
+        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters};
+        int e = launch_probe(c->ix, s.batch, pr, c->compute, c->sm_count);
+        if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
+        CK(cudaEventRecord(s.ev_k1, c->compute));
+        e = launch_search(c->ix, c->P, s.batch, pr, o, c->scratch, c->n_scratch_warps, c->compute, c->sm_count, nullptr);
+        if (e) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)e));
+        c->launches += 2;
+    } else {
+        CK(cudaEventRecord(s.ev_k1, c->compute));
+    }
+    CK(cudaEventRecord(s.ev_k2, c->compute));
+    s.launched = true;
+    s.downloaded = false;
+    return URMB_OK;
+}
+
+extern "C" int urmb_download(urmb_ctx *c, int si) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    Slot &s = c->slots[si];
+    if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamWaitEvent(s.copy, s.ev_k2, 0));
+    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, 16, cudaMemcpyDeviceToHost, s.copy));
+    CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.batch.n_reads * sizeof(urmb_result), cudaMemcpyDeviceToHost, s.copy));
+    // Paths are few and short: copy the whole pool prefix a typical batch uses, the rest on demand in wait.
+    s.downloaded = true;
+    return URMB_OK;
+}
+
+extern "C" int urmb_submit(urmb_ctx *c, int si, const urmb_batch *r1, const urmb_batch *r2) {
+    int rc = urmb_upload(c, si, r1, r2);
+    if (rc) return rc;
+    rc = urmb_launch(c, si);
+    if (rc) return rc;
+    return urmb_download(c, si);
+}
+
+extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const urmb_result **res2, const uint16_t **runs,
+                         uint32_t *runs_used) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    Slot &s = c->slots[si];
+    if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
+    CK(cudaSetDevice(c->device));
+    if (!s.downloaded) {
+        int rc = urmb_download(c, si);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(s.copy));
+    uint32_t used = s.h_counters[0];
+    if (used > s.d_runs_cap) {
+        // The runs pool was too small for this batch: grow it and run the batch again (still on the GPU).
+        int rc;
+        if ((rc = grow_dev(c, s.d_runs, s.d_runs_cap, (size_t)used + 4096))) return rc;
+        if ((rc = grow_host(c, s.h_runs, s.h_runs_cap, s.d_runs_cap))) return rc;
+        if ((rc = urmb_launch(c, si))) return rc;
+        if ((rc = urmb_download(c, si))) return rc;
+        CK(cudaStreamSynchronize(s.copy));
+        used = s.h_counters[0];
+    }
+    if (used) {
+        CK(cudaMemcpyAsync(s.h_runs, s.d_runs, (size_t)used * 2, cudaMemcpyDeviceToHost, s.copy));
+    }
+    CK(cudaEventRecord(s.ev_d2h, s.copy));
+    CK(cudaStreamSynchronize(s.copy));
+    if (res1) *res1 = s.h_res;
+    if (res2) *res2 = s.batch.paired ? s.h_res + s.batch.n_units : nullptr;
+    if (runs) *runs = s.h_runs;
+    if (runs_used) *runs_used = used;
+    if (s.h_counters[1] != 0) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "%u reads exceeded a per-read capacity (hits %d, HSPs %d, path runs %d)",
+                 s.h_counters[1], kHitCap, kHspCap, kRunCap);
+        return fail(c, URMB_E_OVERFLOW, msg);
+    }
+    return URMB_OK;
+}
+
+extern "C" int urmb_timing_last(urmb_ctx *c, int si, urmb_timing *t) {
+    if (!c || !t || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    Slot &s = c->slots[si];
+    memset(t, 0, sizeof *t);
+    if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
+    CK(cudaEventSynchronize(s.ev_k2));
+    cudaEventElapsedTime(&t->probe_ms, s.ev_k0, s.ev_k1);
+    cudaEventElapsedTime(&t->search_ms, s.ev_k1, s.ev_k2);
+    if (cudaEventQuery(s.ev_h2d) == cudaSuccess) cudaEventElapsedTime(&t->h2d_ms, s.ev_h2d0, s.ev_h2d);
+    if (cudaEventQuery(s.ev_d2h) == cudaSuccess && cudaEventQuery(s.ev_k2) == cudaSuccess)
+        cudaEventElapsedTime(&t->d2h_ms, s.ev_k2, s.ev_d2h);
+    cudaGetLastError();
+    return URMB_OK;
+}
+
+extern "C" uint64_t urmb_launch_count(const urmb_ctx *c) { return c ? c->launches : 0; }
+
+static int copy_out(urmb_ctx *c, uint32_t n, const urmb_result *r, urmb_result *out) {
+    if (n && out) memcpy(out, r, (size_t)n * sizeof(urmb_result));
+    return URMB_OK;
+}
+
+extern "C" int urmb_map_se(urmb_ctx *c, const urmb_batch *in, urmb_result *out, uint16_t *runs, uint32_t runs_cap,
+                           uint32_t *runs_used) {
+    int rc = urmb_submit(c, 0, in, nullptr);
+    if (rc) return rc;
+    const urmb_result *r1;
+    const uint16_t *rr;
+    uint32_t used = 0;
+    rc = urmb_wait(c, 0, &r1, nullptr, &rr, &used);
+    if (rc && rc != URMB_E_OVERFLOW) return rc;
+    copy_out(c, in->n, r1, out);
+    if (runs_used) *runs_used = used;
+    if (used > runs_cap) return fail(c, URMB_E_OVERFLOW, "caller's runs buffer too small");
+    if (used && runs) memcpy(runs, rr, (size_t)used * 2);
+    return rc;
+}
+
+extern "C" int urmb_map_pe(urmb_ctx *c, const urmb_batch *r1, const urmb_batch *r2, urmb_result *out1, urmb_result *out2,
+                           uint16_t *runs, uint32_t runs_cap, uint32_t *runs_used) {
+    if (!r2) return URMB_E_ARG;
+    int rc = urmb_submit(c, 0, r1, r2);
+    if (rc) return rc;
+    const urmb_result *a, *b;
+    const uint16_t *rr;
+    uint32_t used = 0;
+    rc = urmb_wait(c, 0, &a, &b, &rr, &used);
+    if (rc && rc != URMB_E_OVERFLOW) return rc;
+    copy_out(c, r1->n, a, out1);
+    copy_out(c, r1->n, b, out2);
+    if (runs_used) *runs_used = used;
+    if (used > runs_cap) return fail(c, URMB_E_OVERFLOW, "caller's runs buffer too small");
+    if (used && runs) memcpy(runs, rr, (size_t)used * 2);
+    return rc;
+}

@@ -1,0 +1,99 @@
+// urmb_internal.h -- structures shared by the CUDA kernels and the C-ABI layer.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/urmb.h"
+
+namespace urmb {
+
+constexpr int kHitCap = 256;    // hits kept per mate (reference grows without bound, state1.cpp:190)
+constexpr int kHspCap = 256;    // HSPs kept per mate
+constexpr int kRunCap = 64;     // RLE runs per stored path
+constexpr int kSeedCap = 512;   // BOTH1 seeds recorded per mate (2*QL, search2m4.cpp:39)
+constexpr int kMaxLen = URMB_MAX_READ_LEN;
+constexpr int kScanSeg = 1024;  // SCAN_DB_SEG_LENGTH, state2.cpp:91
+constexpr int kBigCols = kScanSeg + 2 * kMaxLen + 8;   // widest mate-rescue window (+1 column)
+constexpr int kBigRows = kMaxLen + 1;
+
+struct DevIndex {
+    const uint8_t *blob;   // 5 B/slot AoS exactly as in the UFI file (+URMB_BLOB_PAD)
+    const uint8_t *seq;    // upper-case genome, 1 B/base (+URMB_SEQ_PAD zero bytes)
+    uint64_t slot_count;
+    uint64_t magic;        // floor(2^64 / slot_count) for the Barrett reduction
+    uint64_t shift_mask;   // 2^(2W)-1
+    uint32_t seq_size;
+    uint32_t word_len;
+    uint32_t max_ix;
+};
+
+struct DevParams {  // State1::SetMethod constants, state1.cpp:147-183
+    int MM, GO, GE, MIN_HSP_PCT, TERM3_PCT, XDROP, MAXPEN, XP1, XP3, XP4;
+    uint32_t R;
+    int pe_method;
+};
+
+struct DevBatch {
+    const uint8_t *seqs;   // mate-1 reads then mate-2 reads, concatenated
+    const uint32_t *offs;  // n_reads+1 offsets into seqs
+    uint32_t n_reads;      // SE: n ; PE: 2n (read n+i is the mate of read i)
+    uint32_t n_units;      // reads (SE) or pairs (PE)
+    uint32_t qcap;         // padded max word count per read (multiple of 32)
+    uint32_t seqcap;       // padded max read length (multiple of 32)
+    int paired;
+};
+
+struct DevProbe {   // output of the probe kernel, [n_reads][2 strands][qcap]
+    uint8_t *tally;
+    uint32_t *pos;
+    uint64_t *slot;
+};
+
+struct DevOut {
+    urmb_result *res;      // [n_reads]
+    uint16_t *runs;        // pool
+    uint32_t runs_cap;
+    uint32_t *counters;    // [0] runs used, [1] overflow count, [2] work-queue head, [3] spare
+};
+
+struct MateScratch {
+    uint32_t hit_pos[kHitCap];
+    int16_t hit_score[kHitCap];
+    uint8_t hit_plus[kHitCap];
+    uint8_t hit_nruns[kHitCap];
+    uint16_t hit_runs[kHitCap][kRunCap];
+    uint32_t hsp_dbstart[kHspCap];
+    uint16_t hsp_qstart[kHspCap];
+    uint16_t hsp_len[kHspCap];
+    int16_t hsp_score[kHspCap];
+    uint8_t hsp_flags[kHspCap];   // bit0 plus, bit1 aligned
+    uint8_t pend[2][kMaxLen];     // m_QPosPendingVec_{Plus,Minus} (bytes, state1.h:86)
+    uint8_t todo[2][kMaxLen];     // phase-5 todo lists (search1m6.cpp:170,205)
+    uint32_t seed_db[kSeedCap];
+    uint8_t seed_q[kSeedCap];
+    uint8_t seed_plus[kSeedCap];
+};
+
+struct WarpScratch {
+    MateScratch m[2];
+    uint16_t runs_a[kRunCap + 8];   // reversed runs of the current DP
+    uint16_t runs_l[kRunCap + 8];   // left-flank path
+    uint16_t runs_p[3 * kRunCap + 8]; // assembled path
+    float rowM[kBigCols + 8];
+    float rowD[kBigCols + 8];
+    uint8_t tb[(size_t)kBigRows * kBigCols];   // mate-rescue traceback, 1 B / cell
+};
+
+struct LaunchCfg {
+    int blocks;
+    int warps_per_block;
+    size_t smem_bytes;
+};
+
+// implemented in urmb_kernels.cu
+size_t search_smem_per_warp(const DevBatch &b, const DevParams &P);
+int launch_probe(const DevIndex &ix, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count);
+int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                  WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used);
+int max_search_warps(int sm_count);
+
+}  // namespace urmb

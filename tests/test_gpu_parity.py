@@ -1,0 +1,193 @@
+"""GPU parity tests proper: every call goes through the C-ABI (liburmb.so) and is compared, bit for bit, with
+the oracle restatement and with the golden SAMs of the unmodified reference.  Integer / index work only:
+the bar is exact equality (positions, strand, scores, MAPQ, path runs => CIGAR)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import have_gpu
+from urmap_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("db_pos", "score", "best", "second", "mapq", "flags", "hit_count", "hsp_count")
+
+
+def _paths(res, runs):
+    return [tuple(runs[r["path_off"]:r["path_off"] + r["path_runs"]].tolist()) for r in res]
+
+
+def assert_same(ro, uo, rg, ug):
+    assert len(ro) == len(rg)
+    for f in FIELDS:
+        bad = np.nonzero(ro[f] != rg[f])[0]
+        assert len(bad) == 0, (f, bad[:5], ro[bad[:3]], rg[bad[:3]])
+    assert _paths(ro, uo) == _paths(rg, ug)
+
+
+def canon(res, runs):
+    """Results with path offsets replaced by the path itself (pool layout is not deterministic)."""
+    return [tuple(int(r[f]) for f in FIELDS) + (p,) for r, p in zip(res, _paths(res, runs))]
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    return built_lib
+
+
+@pytest.fixture(scope="module")
+def golden_ctxs(eng, golden_dir):
+    hix = eng.HostIndex(os.path.join(golden_dir, "ref.ufi"))
+    ctxs = {}
+    for key, kw in (("se", {}), ("se_veryfast", {"method": 7}), ("pe", {}), ("pe_veryfast", {"pe_method": 5})):
+        c = eng.Context(0, **kw)
+        c.set_index(hix)
+        ctxs[key] = c
+    yield ctxs
+    for c in ctxs.values():
+        c.close()
+
+
+@pytest.mark.parametrize("key", ["se", "se_veryfast"])
+def test_golden_se(eng, oracle, golden_oix, golden_dir, golden_ctxs, key):
+    b = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "se.fq"))
+    res, runs = golden_ctxs[key].map_se(b.seqs, b.offs)
+    ro, uo = oracle.map_se(golden_oix, b, method=7 if key.endswith("veryfast") else 6)
+    assert_same(ro, uo, res, runs)
+    sam = oracle.sam_header(golden_oix) + oracle.sam_se(golden_oix, b, res, runs)
+    c = synth.compare_sam(os.path.join(golden_dir, key + ".sam"), sam)
+    assert c["identical"] == c["total"] == 580, c["diffs"][:5]
+
+
+@pytest.mark.parametrize("key", ["pe", "pe_veryfast"])
+def test_golden_pe(eng, oracle, golden_oix, golden_dir, golden_ctxs, key):
+    b1 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_1.fq"))
+    b2 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_2.fq"))
+    g1, g2, runs = golden_ctxs[key].map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+    o1, o2, uo = oracle.map_pe(golden_oix, b1, b2, pe_method=5 if key.endswith("veryfast") else 4)
+    assert_same(o1, uo, g1, runs)
+    assert_same(o2, uo, g2, runs)
+    sam = oracle.sam_header(golden_oix) + oracle.sam_pe(golden_oix, b1, b2, g1, g2, runs)
+    c = synth.compare_sam(os.path.join(golden_dir, key + ".sam"), sam)
+    assert c["identical"] == c["total"] == 860, c["diffs"][:5]
+
+
+@pytest.fixture(scope="module")
+def mid_env(eng, oracle, tmp_path_factory):
+    """2 Mb repeat-rich reference indexed by the reference binary (travels in oracle/_ref/)."""
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available to build the index")
+    d = tmp_path_factory.mktemp("mid")
+    g = synth.make_genome(2_000_000, n_contigs=4, seed=77, repeat_frac=0.10, n_runs=[(2, 0.3, 1500)], tandem=20, segdup=4)
+    fa, ufi = str(d / "ref.fa"), str(d / "ref.ufi")
+    g.write_fasta(fa)
+    oracle.run_reference(["-make_ufi", fa, "-output", ufi])
+    return g, oracle.Index(ufi), eng.HostIndex(ufi)
+
+
+@pytest.mark.parametrize("rl,sub,indel,method", [(150, 0.01, 0.001, 6), (150, 0.05, 0.01, 6), (250, 0.02, 0.002, 6),
+                                                 (100, 0.03, 0.003, 7), (150, 0.05, 0.01, 7)])
+def test_random_se(eng, oracle, mid_env, rl, sub, indel, method):
+    g, oix, hix = mid_env
+    reads, _ = synth.sim_se(g, 20000, rl, sub, indel, seed=rl + method)
+    b = oracle.ReadBatch.from_arrays(reads)
+    ctx = eng.Context(0, method=method)
+    ctx.set_index(hix)
+    res, runs = ctx.map_se(b.seqs, b.offs)
+    ro, uo = oracle.map_se(oix, b, method=method, threads=os.cpu_count())
+    assert_same(ro, uo, res, runs)
+    ctx.close()
+
+
+@pytest.mark.parametrize("rl,sub,indel,pe_method", [(150, 0.01, 0.001, 4), (150, 0.05, 0.01, 4), (250, 0.03, 0.003, 4),
+                                                    (150, 0.03, 0.003, 5)])
+def test_random_pe(eng, oracle, mid_env, rl, sub, indel, pe_method):
+    g, oix, hix = mid_env
+    r1, r2, _ = synth.sim_pe(g, 10000, rl, sub, indel, seed=rl + pe_method)
+    r2 = r2.copy()
+    r2[::50, : rl // 2] = r1[::50, : rl // 2]  # damage some mates so that ScanPair (mate rescue) fires
+    b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
+    ctx = eng.Context(0, pe_method=pe_method)
+    ctx.set_index(hix)
+    g1, g2, runs = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+    o1, o2, uo, st = oracle.map_pe(oix, b1, b2, pe_method=pe_method, threads=os.cpu_count(), want_stats=True)
+    if pe_method == 4:
+        assert st["scan_calls"] > 0
+    assert_same(o1, uo, g1, runs)
+    assert_same(o2, uo, g2, runs)
+    ctx.close()
+
+
+def test_ragged_and_edge_reads(eng, oracle, mid_env):
+    """Empty batch, reads shorter than the word length, ragged lengths 1..256, N / lower-case / IUPAC letters."""
+    g, oix, hix = mid_env
+    ctx = eng.Context(0)
+    ctx.set_index(hix)
+    res, runs = ctx.map_se(np.zeros(0, np.uint8), np.zeros(1, np.uint32))
+    assert len(res) == 0
+    rng = np.random.default_rng(3)
+    lens = np.concatenate([[1, 5, 23, 24, 25, 47, 48, 96, 97, 255, 256], rng.integers(24, 257, size=3000)])
+    seqs, offs = [], [0]
+    for i, L in enumerate(lens):
+        p = int(rng.integers(0, len(g.asc) - 300))
+        s = g.asc[p:p + L].copy()
+        if i % 7 == 0 and L > 40:
+            s[rng.integers(0, L, size=3)] = ord("N")
+        if i % 11 == 0:
+            s = np.where((s >= 65) & (s <= 90), s + 32, s).astype(np.uint8)
+        if i % 13 == 0 and L > 30:
+            s[rng.integers(0, L)] = ord("R")
+        if i % 17 == 0 and L > 30:
+            s[rng.integers(0, L)] = ord("u")
+        seqs.append(s)
+        offs.append(offs[-1] + L)
+    b = oracle.ReadBatch(np.concatenate(seqs), np.array(offs, dtype=np.uint32))
+    # reads shorter than W make the reference underflow; both sides report "no hit"
+    res, runs = ctx.map_se(b.seqs, b.offs)
+    ro, uo = oracle.map_se(oix, b, threads=4)
+    assert_same(ro, uo, res, runs)
+    too_long = np.full(300, ord("A"), dtype=np.uint8)
+    with pytest.raises(eng.UrmbError) as e:
+        ctx.map_se(too_long, np.array([0, 300], dtype=np.uint32))
+    assert e.value.code == -6
+    ctx.close()
+
+
+def test_size_independent_properties(eng, oracle, mid_env):
+    """Properties that also hold at BASELINE sizes: idempotence, batch-split invariance, permutation equivariance,
+    and agreement of the pipelined (3-slot) interface with the synchronous one."""
+    g, oix, hix = mid_env
+    ctx = eng.Context(0)
+    ctx.set_index(hix)
+    r1, r2, _ = synth.sim_pe(g, 30000, 150, 0.02, 0.002, seed=5)
+    b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
+    a1, a2, ua = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+    c1, c2, uc = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+    full1, full2 = canon(a1, ua), canon(a2, ua)
+    assert full1 == canon(c1, uc) and full2 == canon(c2, uc)
+    # split into three slots, submitted back to back, waited afterwards
+    n = b1.n
+    cuts = [0, n // 3, 2 * n // 3, n]
+    parts = []
+    for k in range(3):
+        lo, hi = cuts[k], cuts[k + 1]
+        o = (b1.offs[lo:hi + 1] - b1.offs[lo]).astype(np.uint32)
+        parts.append((np.ascontiguousarray(b1.seqs[b1.offs[lo]:b1.offs[hi]]), o,
+                      np.ascontiguousarray(b2.seqs[b2.offs[lo]:b2.offs[hi]]), (b2.offs[lo:hi + 1] - b2.offs[lo]).astype(np.uint32)))
+        ctx.submit(k, *parts[-1])
+    got1, got2 = [], []
+    for k in range(3):
+        x1, x2, ux = ctx.wait(k, cuts[k + 1] - cuts[k], True)
+        got1 += canon(x1, ux)
+        got2 += canon(x2, ux)
+    assert got1 == full1 and got2 == full2
+    # permutation
+    perm = np.random.default_rng(1).permutation(n)
+    p1, p2 = oracle.ReadBatch.from_arrays(r1[perm]), oracle.ReadBatch.from_arrays(r2[perm])
+    q1, q2, uq = ctx.map_pe(p1.seqs, p1.offs, p2.seqs, p2.offs)
+    assert canon(q1, uq) == [full1[i] for i in perm]
+    assert ctx.launch_count() >= 2 * 6
+    ctx.close()

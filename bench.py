@@ -1,0 +1,495 @@
+#!/usr/bin/env python
+"""bench.py -- the headline metric of BASELINE.json on synthetic data:
+reads/s mapped for 2x150 bp paired-end reads against a 3.1 Gb human-scale synthetic reference whose UFI index
+(27 GB hash table + 3.1 GB sequence) is resident in each B200's HBM.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU path (oracle/_ref/urmap) on the host cores
+
+A "step" is one pass of the hot path (probe kernel + search kernel) over one batch of `--pairs-per-step` read
+pairs per GPU.  `value` is measured with the inputs already resident in HBM (CUDA events on the launching
+stream); `e2e` goes through the C-ABI with pinned host buffers, H2D and D2H inside the timed region, three
+batch slots in flight.  Weak scaling: every rank maps its own batches; the only collective is the NCCL
+broadcast of the index at start-up.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.active = False
+        self.proc = None
+        self.th = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        for line in self.proc.stdout:
+            if self.active:
+                self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_json(name):
+    try:
+        return json.load(open(os.path.join(ROOT, name)))
+    except Exception:
+        return {}
+
+
+def build_workload(args, rank, world, device):
+    """Genome + UFI index in HBM on every rank (rank 0 builds on its GPU, NCCL broadcast to the others)."""
+    import torch
+
+    from urmap_b200 import dist as D
+    from urmap_b200 import gpu_synth, index_build
+    meta, seq, blob = None, None, None
+    t0 = time.time()
+    if rank == 0:
+        human = args.genome_len >= 100_000_000
+        seq, names, lens, offsets, sds = gpu_synth.make_seqdata(args.genome_len, device, seed=12345,
+                                                                n_contigs=24 if human else 3, human_ratios=human,
+                                                                repeat_frac=0.10, n_runs=3)
+        slot_count = index_build.slot_count_for(names, lens)
+        torch.cuda.synchronize()
+        log(f"genome {args.genome_len:,} bp in {len(names)} contigs generated in {time.time() - t0:.1f}s; "
+            f"SeqDataSize {sds:,}; SlotCount {slot_count:,}")
+        blob = torch.empty(5 * slot_count + 16, dtype=torch.uint8, device=device)
+        torch.cuda.empty_cache()
+        st = index_build.build_index_device(seq.data_ptr(), sds, slot_count, blob.data_ptr())
+        log(f"UFI built on the GPU: {st}")
+        if st["truncated"]:
+            raise RuntimeError("index builder truncated lists")
+        meta = {"word_length": 24, "max_ix": 32, "seq_data_size": sds, "slot_count": slot_count, "names": names,
+                "lens": lens, "offsets": offsets, "seq_alloc": seq.numel(), "blob_alloc": blob.numel(),
+                "build_seconds": st["seconds"], "indexed": st["indexed"]}
+    t1 = time.time()
+    meta, seq, blob = D.broadcast_index(meta, seq, blob, device)
+    if world > 1:
+        torch.cuda.synchronize()
+        log(f"rank {rank}: index broadcast over NCCL in {time.time() - t1:.2f}s")
+    return meta, seq, blob
+
+
+def make_batches(args, meta, seq, rank, device, nb):
+    """nb distinct batches of read pairs for this rank, as pinned host numpy arrays."""
+    import torch
+
+    from urmap_b200 import gpu_synth
+    B, RL = args.pairs_per_step, args.read_len
+    offs = (np.arange(B + 1, dtype=np.uint32) * RL)
+    out = []
+    for k in range(nb):
+        seed = 1000 * (rank + 1) + k
+        if args.single_end:
+            r1 = gpu_synth.sim_se(seq, meta["lens"], meta["offsets"], B, device, RL, args.sub, args.indel, seed=seed)
+            r2 = None
+        else:
+            r1, r2 = gpu_synth.sim_pe(seq, meta["lens"], meta["offsets"], B, device, RL, args.sub, args.indel, seed=seed)
+        h1 = torch.empty(r1.shape, dtype=torch.uint8, pin_memory=True)
+        h1.copy_(r1)
+        h2 = None
+        if r2 is not None:
+            h2 = torch.empty(r2.shape, dtype=torch.uint8, pin_memory=True)
+            h2.copy_(r2)
+        torch.cuda.synchronize()
+        out.append((h1, h2, h1.numpy().reshape(-1), None if h2 is None else h2.numpy().reshape(-1), offs))
+        del r1, r2
+    torch.cuda.empty_cache()
+    return out
+
+
+def write_ufi_file(path, meta, seq, blob):
+    from urmap_b200 import index_build
+    CH = 1 << 28
+
+    def chunks(t, n):
+        for o in range(0, n, CH):
+            yield t[o:min(n, o + CH)].cpu().numpy().tobytes()
+
+    index_build.write_ufi(path, meta["names"], meta["lens"], meta["offsets"], meta["seq_data_size"], meta["slot_count"],
+                          chunks(blob, 5 * meta["slot_count"]), chunks(seq, meta["seq_data_size"]))
+
+
+def write_fastq_pair(prefix, r1, r2, n, RL):
+    q = b"I" * RL
+
+    def one(path, arr, suffix):
+        with open(path, "wb") as f:
+            buf = []
+            for i in range(n):
+                buf.append(b"@p%d%s\n%s\n+\n%s\n" % (i, suffix, arr[i * RL:(i + 1) * RL].tobytes(), q))
+                if len(buf) >= 50000:
+                    f.write(b"".join(buf))
+                    buf = []
+            f.write(b"".join(buf))
+
+    one(prefix + "_1.fq", r1, b"/1")
+    if r2 is not None:
+        one(prefix + "_2.fq", r2, b"/2")
+
+
+def run_reference_cpu(args, ufi_path, prefix, n_units, paired, threads):
+    """Times the UNMODIFIED reference binary on the host cores: wall(process over the sample) - wall(process over a
+    4-read input), i.e. index load and start-up are excluded the same way for any sample size."""
+    from oracle import oracle_py as O
+    if not os.path.exists(O.REF_BIN):
+        return None
+    tiny = prefix + "_tiny"
+    for sfx in ("_1.fq", "_2.fq"):
+        if os.path.exists(prefix + sfx):
+            with open(prefix + sfx, "rb") as f, open(tiny + sfx, "wb") as g:
+                for _ in range(16):
+                    g.write(f.readline())
+
+    def cmd(p, sam):
+        if paired:
+            c = ["-map2", p + "_1.fq", "-reverse", p + "_2.fq"]
+        else:
+            c = ["-map", p + "_1.fq"]
+        return [O.REF_BIN] + c + ["-ufi", ufi_path, "-samout", sam, "-threads", str(threads)]
+
+    t0 = time.time()
+    subprocess.run(cmd(tiny, prefix + "_tiny.sam"), check=True, capture_output=True)
+    t_load = time.time() - t0
+    t0 = time.time()
+    subprocess.run(cmd(prefix, prefix + "_ref.sam"), check=True, capture_output=True)
+    t_run = time.time() - t0
+    reads = n_units * (2 if paired else 1)
+    dt = max(t_run - t_load, 1e-3)
+    return {"reads": reads, "seconds": dt, "load_seconds": t_load, "reads_per_s": reads / dt, "sam": prefix + "_ref.sam"}
+
+
+def sam_identity(args, meta, ref_sam, ufi_path, batch, n_units, paired, ctx):
+    """% of SAM records identical between the reference binary and the GPU engine on the same sample."""
+    from oracle import oracle_py as O
+    from urmap_b200 import synth
+    _, _, a1, a2, offs = batch
+    RL = args.read_len
+    s1 = np.ascontiguousarray(a1[:n_units * RL])
+    o = np.ascontiguousarray(offs[:n_units + 1])
+    labs1 = [b"p%d/1" % i for i in range(n_units)]
+    oix = O.Index(ufi_path)
+    if paired:
+        s2 = np.ascontiguousarray(a2[:n_units * RL])
+        g1, g2, runs = ctx.map_pe(s1, o, s2, o)
+        labs2 = [b"p%d/2" % i for i in range(n_units)]
+        b1 = O.ReadBatch(s1, o, np.full(len(s1), ord("I"), np.uint8), np.frombuffer(b"".join(labs1), np.uint8),
+                         np.concatenate([[0], np.cumsum([len(x) for x in labs1])]))
+        b2 = O.ReadBatch(s2, o, np.full(len(s2), ord("I"), np.uint8), np.frombuffer(b"".join(labs2), np.uint8),
+                         np.concatenate([[0], np.cumsum([len(x) for x in labs2])]))
+        sam = O.sam_pe(oix, b1, b2, g1.copy(), g2.copy(), runs.copy())
+    else:
+        g1, runs = ctx.map_se(s1, o)
+        b1 = O.ReadBatch(s1, o, np.full(len(s1), ord("I"), np.uint8), np.frombuffer(b"".join(labs1), np.uint8),
+                         np.concatenate([[0], np.cumsum([len(x) for x in labs1])]))
+        sam = O.sam_se(oix, b1, g1.copy(), runs.copy())
+    c = synth.compare_sam(ref_sam, sam)
+    oix.close()
+    return {"records": c["total"], "identical": c["identical"], "pct": 100.0 * c["identical"] / max(1, c["total"]),
+            "formatter": "oracle SAM writer over GPU result structs"}
+
+
+def algorithmic_bytes_per_read(args, ufi_path, batch, n_units, paired):
+    """B_algo = 5*P + 5*H + C from the oracle's work counters on a sample of this workload."""
+    from oracle import oracle_py as O
+    _, _, a1, a2, offs = batch
+    RL = args.read_len
+    o = np.ascontiguousarray(offs[:n_units + 1])
+    oix = O.Index(ufi_path)
+    if paired:
+        *_, st = O.map_pe(oix, O.ReadBatch(np.ascontiguousarray(a1[:n_units * RL]), o),
+                          O.ReadBatch(np.ascontiguousarray(a2[:n_units * RL]), o), threads=os.cpu_count(), want_stats=True)
+    else:
+        *_, st = O.map_se(oix, O.ReadBatch(np.ascontiguousarray(a1[:n_units * RL]), o), threads=os.cpu_count(),
+                          want_stats=True)
+    oix.close()
+    r = max(1, st["reads"])
+    per = {k: st[k] / r for k in ("probes", "row_hops", "compare_bytes", "dp_cells", "extend_calls")}
+    per["bytes"] = 5 * per["probes"] + 5 * per["row_hops"] + per["compare_bytes"]
+    return per
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="urmb", choices=["urmb", "reference"])
+    ap.add_argument("--genome-len", type=int, default=3_100_000_000)
+    ap.add_argument("--pairs-per-step", type=int, default=1_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--sub", type=float, default=0.01)
+    ap.add_argument("--indel", type=float, default=0.001)
+    ap.add_argument("--single-end", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=1_000_000)
+    ap.add_argument("--ref-pairs-per-step", type=int, default=200_000)
+    ap.add_argument("--workdir", default=os.environ.get("URMB_BENCH_DIR", "/dev/shm/urmb_bench"))
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    paired = not args.single_end
+    rpu = 2 if paired else 1
+
+    import torch
+
+    from urmap_b200 import dist as D
+    rank, local_rank, world = D.env_rank()
+    if args.impl == "reference" and rank != 0:
+        return 0
+    if args.impl == "urmb":
+        D.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the mapping engine has no CPU path")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    from urmap_b200 import build as BLD
+    if rank == 0:
+        BLD.build_engine()
+    if args.impl == "urmb":
+        D.barrier()
+    from urmap_b200 import engine
+
+    baseline = load_json("BASELINE.json")
+    peaks = load_json("MEASURED_PEAKS.json")
+    metric = baseline.get("metric", "reads/s mapped, 2x150bp human-scale")
+    workload = ("synthetic %.2f Gb reference (24 contigs, 10%% injected repeats), UFI in HBM, %s %d bp reads, "
+                "%.1f%% subs + %.2f%% indels" % (args.genome_len / 1e9, "paired-end 2x" if paired else "single-end",
+                                                 args.read_len, 100 * args.sub, 100 * args.indel))
+    cfg = {"workload": workload, "pairs_per_step_per_gpu" if paired else "reads_per_step_per_gpu": args.pairs_per_step,
+           "parallelism": f"reads sharded over {world} GPU(s), index replicated by NCCL broadcast, no per-batch collective",
+           "l2_policy": "inputs larger than L2: each batch is >=300 MB of reads and probes a 27 GB table at random",
+           "pe_method": 4, "method": 6}
+
+    meta, seq, blob = build_workload(args, rank, world if args.impl == "urmb" else 1, device)
+    nb = 3
+    batches = make_batches(args, meta, seq, rank, device, nb)
+    os.makedirs(args.workdir, exist_ok=True)
+    ufi_path = os.path.join(args.workdir, "bench.ufi")
+    prefix = os.path.join(args.workdir, "sample")
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        from oracle import oracle_py as O
+        O.build(ref=True)
+        threads = os.cpu_count()
+        n_ref = min(args.pairs_per_step, args.ref_pairs_per_step) * args.steps
+        n_ref = min(n_ref, args.pairs_per_step * nb)
+        t0 = time.time()
+        write_ufi_file(ufi_path, meta, seq, blob)
+        log(f"UFI file written for the reference in {time.time() - t0:.1f}s")
+        a1 = np.concatenate([b[2] for b in batches])
+        a2 = None if not paired else np.concatenate([b[3] for b in batches])
+        write_fastq_pair(prefix, a1, a2, n_ref, args.read_len)
+        del seq, blob
+        torch.cuda.empty_cache()
+        r = run_reference_cpu(args, ufi_path, prefix, n_ref, paired, threads)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/urmap not built"}))
+            return 0
+        sample = (f"{n_ref} {'pairs' if paired else 'reads'} of the same workload in one urmap process "
+                  f"({args.steps} steps x {n_ref // args.steps}); wall minus the wall of a 4-read run (index load)")
+        line = {"impl": "reference", "metric": metric, "value": r["reads_per_s"], "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/fp32",
+                "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": r["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
+                                 "sample": sample},
+                "e2e": {"value": r["reads_per_s"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "index_built_by": "urmb_build_index_device on the GPU (functionally equivalent UFI; setup, not timed)",
+                "load_seconds": r["load_seconds"]}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ urmb arm
+    ctx = engine.Context(local_rank)
+    ctx.attach_index(meta["word_length"], meta["max_ix"], meta["seq_data_size"], meta["slot_count"], blob.data_ptr(),
+                     seq.data_ptr(), keepalive=(seq, blob))
+    B, RL = args.pairs_per_step, args.read_len
+
+    def submit(slot, k):
+        _, _, a1, a2, offs = batches[k % nb]
+        ctx.submit(slot, a1, offs, a2, offs if paired else None)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # warm-up (also sizes every slot's buffers)
+    for w in range(max(args.warmup, 3)):
+        submit(w % 3, w)
+        ctx.wait(w % 3, B, paired)
+    # ---- value: inputs resident in HBM, kernels only, CUDA events on the launching stream
+    for s in range(3):
+        _, _, a1, a2, offs = batches[s % nb]
+        ctx.upload(s, a1, offs, a2, offs if paired else None)
+    D.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
+    sampler.active = True
+    t_wall0 = time.perf_counter()
+    dev_ms, probe_ms, search_ms = 0.0, 0.0, 0.0
+    for k in range(args.steps):
+        ctx.launch(k % 3)
+        tm = ctx.timing(k % 3)   # synchronises on the step's last event
+        probe_ms += tm["probe_ms"]
+        search_ms += tm["search_ms"]
+        dev_ms += tm["probe_ms"] + tm["search_ms"]
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.active = False
+    D.barrier()
+    gpu_launches = ctx.launch_count() - launches0
+    dev_ms_max = D.max_over_ranks(dev_ms, device)
+    total_reads = rpu * B * args.steps * world
+    value = total_reads / (dev_ms_max / 1e3)
+    # ---- e2e: host buffers in, host buffers out, three slots in flight
+    for s in range(3):
+        ctx.download(s)
+        ctx.wait(s, B, paired)
+    D.barrier()
+    torch.cuda.synchronize()
+    sampler.active = True
+    t0 = time.perf_counter()
+    d2h = 0
+    for k in range(args.steps):
+        if k >= 3:
+            r1, r2, runs = ctx.wait(k % 3, B, paired)
+            d2h += r1.nbytes + (r2.nbytes if r2 is not None else 0) + runs.nbytes + 16
+        submit(k % 3, k)
+    for k in range(max(0, args.steps - 3), args.steps):
+        r1, r2, runs = ctx.wait(k % 3, B, paired)
+        d2h += r1.nbytes + (r2.nbytes if r2 is not None else 0) + runs.nbytes + 16
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    sampler.active = False
+    D.barrier()
+    t_e2e_max = D.max_over_ranks(t_e2e, device)
+    e2e_value = total_reads / t_e2e_max
+    h2d_per_step = rpu * B * RL + 4 * (rpu * B + 1)
+    clocks = sampler.summary()
+    sampler.stop()
+
+    # ---- cpu baseline, SAM identity and algorithmic bytes (rank 0, N == 1 only)
+    cpu_baseline, sam_id, algo = None, None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle_py as O
+            O.build(ref=True)
+            t0 = time.time()
+            write_ufi_file(ufi_path, meta, seq, blob)
+            log(f"UFI file for the CPU baseline written in {time.time() - t0:.1f}s")
+            n_cpu = min(args.cpu_sample_pairs, B)
+            write_fastq_pair(prefix, batches[0][2], batches[0][3], n_cpu, RL)
+            threads = os.cpu_count()
+            r = run_reference_cpu(args, ufi_path, prefix, n_cpu, paired, threads)
+            if r is not None:
+                cpu_baseline = {"value": r["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
+                                "sample": f"first {n_cpu} {'pairs' if paired else 'reads'} of batch 0; wall of "
+                                          f"`urmap -map2 -threads {threads}` minus the wall of a 4-read run (index load "
+                                          f"{r['load_seconds']:.1f}s excluded)"}
+                sam_id = sam_identity(args, meta, r["sam"], ufi_path, batches[0], n_cpu, paired, ctx)
+            algo = algorithmic_bytes_per_read(args, ufi_path, batches[0], min(50_000, B), paired)
+        except Exception as e:  # the baseline is reported, never required
+            log(f"cpu baseline failed: {e!r}")
+    if algo is None:
+        # SURVEY.md §8d, measured on the reference at human scale (PE 1 %): P=157, H~50, C=2213
+        algo = {"probes": 157.0, "row_hops": 50.0, "compare_bytes": 2213.0, "bytes": 5 * 157 + 5 * 50 + 2213.0,
+                "source": "SURVEY.md §8d constants"}
+
+    if rank == 0:
+        reads_per_launch = rpu * B
+        peak = peaks.get("hbm_gbs")
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peak else "fallback 6650 GB/s (B200_PROFILING.md)"
+        peak = peak or 6650.0
+        search_avg_s = (search_ms / args.steps) / 1e3
+        probe_avg_s = (probe_ms / args.steps) / 1e3
+        achieved = algo["bytes"] * reads_per_launch / search_avg_s / 1e9
+        qwc = RL - 23
+        probe_bytes = reads_per_launch * 2 * qwc * 5.0
+        line = {
+            "metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (fp32 DP cells, fp64 MAPQ)", "data": "synthetic",
+            "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_per_step,
+                    "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": 1e3 * t_e2e_max / args.steps},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_read": algo["bytes"],
+                         "note": "latency-bound dependent gathers: see DESIGN.md; DP cells/read %.0f" % algo.get("dp_cells", 0)},
+            "roofline_probe": {"kernel": "probe_kernel", "bound": "hbm", "achieved": probe_bytes / probe_avg_s / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": probe_bytes / probe_avg_s / 1e9 / peak,
+                               "note": "5 B per speculative slot probe, 2*(QL-23) probes per read"},
+            "kernel_ms_per_step": {"probe": probe_ms / args.steps, "search": search_ms / args.steps,
+                                   "wall_incl_launch_gaps": 1e3 * t_wall / args.steps},
+            "cpu_baseline": cpu_baseline,
+            "sam_identity_vs_reference": sam_id,
+            "work_per_read": algo,
+            "index": {"slot_count": meta["slot_count"], "seq_data_size": meta["seq_data_size"],
+                      "gpu_build_seconds": meta.get("build_seconds"), "indexed_positions": meta.get("indexed")},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if args.workdir.startswith("/dev/shm") and rank == 0 and not os.environ.get("URMB_KEEP_BENCH_DIR"):
+        shutil.rmtree(args.workdir, ignore_errors=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -73,6 +73,8 @@ def lib():
         L.uo_viterbi.restype = C.c_float
         L.uo_viterbi.argtypes = [C.POINTER(Params), vp, C.c_uint32, vp, C.c_uint32, C.c_int, C.c_int, C.c_char_p]
         L.uo_path_to_cigar.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+        L.uo_index_functional_diff.restype = C.c_uint64
+        L.uo_index_functional_diff.argtypes = [vp, vp, vp]
         L.uo_get_prime.restype = C.c_uint64
         L.uo_get_prime.argtypes = [C.c_uint64]
         _lib = L
@@ -243,6 +245,12 @@ def path_to_cigar(path: str, ql: int):
     buf = C.create_string_buffer(12 * len(path) + 32)
     lib().uo_path_to_cigar(path.encode(), ql, buf)
     return buf.value.decode()
+
+
+def index_functional_diff(a: Index, b: Index):
+    first = C.c_uint64(0)
+    n = lib().uo_index_functional_diff(a.h, b.h, C.addressof(first))
+    return int(n), int(first.value)
 
 
 def get_prime(n: int) -> int:

@@ -1521,6 +1521,37 @@ void uo_path_to_cigar(const char *path, uint32_t QL, char *out) {
     memcpy(out, c.c_str(), c.size() + 1);
 }
 
+// Functional comparison of two indexes over the same genome: for every slot the head class
+// (none / BOTH1 / PLUS1 / list) and the list of positions GetRow_Blob returns must agree; where overflow
+// elements are parked may differ.  Returns the number of differing slots.
+uint64_t uo_index_functional_diff(const uo_index *a, const uo_index *b, uint64_t *first_bad) {
+    if (a->SlotCount != b->SlotCount || a->SeqDataSize != b->SeqDataSize || a->MaxIx != b->MaxIx) return ~0ull;
+    if (memcmp(a->SeqData, b->SeqData, a->SeqDataSize) != 0) return ~0ull;
+    Params P = Params{-3, -5, -1, 20, 60, 9, 100, 1, 1, 1, 12, 4};
+    S1 sa(*a, P, nullptr), sb(*b, P, nullptr);
+    std::vector<uint32> pa(a->MaxIx + 2), pb(b->MaxIx + 2);
+    uint64_t bad = 0;
+    for (uint64 s = 0; s < a->SlotCount; ++s) {
+        const byte *ra = a->Blob + 5 * s, *rb = b->Blob + 5 * s;
+        const bool ma = TallyMine(ra[0]), mb = TallyMine(rb[0]);
+        bool same = (ma == mb);
+        if (same && ma) {
+            const int ca = ra[0] == T_BOTH1 ? 2 : (ra[0] == T_PLUS1 ? 1 : 0);
+            const int cb = rb[0] == T_BOTH1 ? 2 : (rb[0] == T_PLUS1 ? 1 : 0);
+            same = (ca == cb);
+            if (same) {
+                unsigned na = sa.GetRow_Blob(s, ra, pa.data()), nb = sb.GetRow_Blob(s, rb, pb.data());
+                same = (na == nb) && std::equal(pa.begin(), pa.begin() + na, pb.begin());
+            }
+        }
+        if (!same) {
+            if (bad == 0 && first_bad) *first_bad = s;
+            ++bad;
+        }
+    }
+    return bad;
+}
+
 uint64_t uo_get_prime(uint64_t n) {
     // prime.cpp:11 scans primes.h, whose entries are "first prime >= x" for x = 100, then
     // x <- x*100/95 (integer); regenerated here instead of copying the table.

@@ -97,7 +97,9 @@ float uo_viterbi(const uo_params *p, const uint8_t *A, uint32_t LA, const uint8_
                  int left, int right, char *path);
 /* path -> CIGAR incl. the dangling-M polish (cigar.cpp:4,141); out must hold 12*strlen(path)+16 */
 void uo_path_to_cigar(const char *path, uint32_t QL, char *out);
-uint64_t uo_get_prime(uint64_t n);               /* prime.cpp:11 + primes.h */
+uint64_t uo_get_prime(uint64_t n);
+/* number of slots whose observable content (head class + GetRow_Blob list) differs; ~0 if incomparable */
+uint64_t uo_index_functional_diff(const uo_index *a, const uo_index *b, uint64_t *first_bad);               /* prime.cpp:11 + primes.h */
 
 #ifdef __cplusplus
 }

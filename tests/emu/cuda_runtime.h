@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <functional>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #define __global__
@@ -68,6 +70,10 @@ inline void emu_syncwarp(int line) { emu::collective(emu::K_SYNC, 0, 0, line); }
 #define __syncwarp() emu_syncwarp(__LINE__)
 
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
+inline void __syncthreads() {}
+#define __shared__ static
 inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }

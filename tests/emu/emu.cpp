@@ -3,6 +3,7 @@
 #include "cuda_runtime.h"
 
 #include "../../urmap_b200/csrc/urmb_kernels.cu"
+#include "../../urmap_b200/csrc/urmb_build.cu"
 
 emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
@@ -161,5 +162,40 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     launch_probe(ix, b, pr, nullptr, 1);
     launch_search(ix, P, b, pr, o, ws, nw, nullptr, 1, nullptr);
     free(ws);
+    return 0;
+}
+
+// Device index builder under emulation (scan passes done on the host: they use __syncthreads).
+extern "C" int emu_build_index(const uint8_t *seq, uint64_t seq_size, uint64_t slot_count, uint32_t word_len,
+                               uint32_t max_ix, uint8_t *blob /* 5*slot_count+16 */, uint64_t *stats) {
+    BuildArgs a{};
+    a.seq = seq;
+    a.seq_size = seq_size;
+    a.slot_count = slot_count;
+    a.magic = (uint64_t)((((unsigned __int128)1) << 64) / slot_count);
+    a.shift_mask = (word_len >= 32) ? ~0ull : ((1ull << (2 * word_len)) - 1);
+    a.word_len = word_len;
+    a.max_ix = max_ix;
+    a.blob = blob;
+    const uint64_t cwords = (slot_count + 3) / 4 + 1;
+    std::vector<uint32_t> cntP(cwords, 0), cntM(cwords, 0), fill(cwords, 0), base(slot_count, 0),
+        claimed(slot_count / 32 + 2, 0), errors(2, 0);
+    a.cntP = cntP.data(); a.cntM = cntM.data(); a.fill = fill.data(); a.base = base.data();
+    a.claimed = claimed.data(); a.errors = errors.data();
+    const int T = 256;
+    const uint64_t gpos = (seq_size + T - 1) / T, gslot = (slot_count + T - 1) / T;
+    emu::launch([&]() { build_init_kernel(a); }, (int)(((slot_count + 3) / 4 + T - 1) / T), T, 0);
+    emu::launch([&]() { build_count_kernel(a); }, (int)gpos, T, 0);
+    uint64_t run = 0;
+    for (uint64_t s = 0; s < slot_count; ++s) {
+        base[s] = (uint32_t)run;
+        uint32_t n = (cntP[s >> 2] >> ((s & 3) * 8)) & 255u, m = (cntM[s >> 2] >> ((s & 3) * 8)) & 255u;
+        run += (n >= 1 && n <= max_ix && m <= max_ix) ? n : 0;
+    }
+    std::vector<uint32_t> pool(run + 1, 0);
+    a.pool = pool.data();
+    emu::launch([&]() { build_scatter_kernel(a); }, (int)gpos, T, 0);
+    emu::launch([&]() { build_link_kernel(a); }, (int)gslot, T, 0);
+    if (stats) { stats[0] = run; stats[1] = errors[0]; stats[2] = errors[1]; }
     return 0;
 }

@@ -49,3 +49,18 @@ def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, 
                    runs.ctypes.data_as(vp), C.c_uint32(cap), counters.ctypes.data_as(vp))
     assert rc == 0, rc
     return res, runs, counters
+
+
+def emu_build_index(seq: np.ndarray, slot_count: int, word_len: int = 24, max_ix: int = 32):
+    """Runs the device index-builder kernels under emulation; returns (blob uint8[5*slot_count], stats)."""
+    L = lib()
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    pad = np.zeros(len(seq) + 64, dtype=np.uint8)
+    pad[:len(seq)] = seq
+    blob = np.zeros(5 * slot_count + 16, dtype=np.uint8)
+    stats = np.zeros(3, dtype=np.uint64)
+    vp = C.c_void_p
+    rc = L.emu_build_index(pad.ctypes.data_as(vp), C.c_uint64(len(seq)), C.c_uint64(slot_count), C.c_uint32(word_len),
+                           C.c_uint32(max_ix), blob.ctypes.data_as(vp), stats.ctypes.data_as(vp))
+    assert rc == 0
+    return blob[:5 * slot_count], stats

@@ -1,0 +1,369 @@
+// urmb_build.cu -- device-side UFI index construction (the "-make_ufi on GPU" row of SURVEY.md §8f).
+//
+// The reference builder (UFIndex::MakeIndex, ufindex.cpp:83-151) is sequential: k-mers are inserted in genome
+// order and overflow list elements go to the first free never-owned slot after the end of their list
+// (FindFreeSlot, ufindex.cpp:987), so *where* overflow elements land depends on insertion order.  What a
+// mapper can observe, however, is only (a) each owned slot's head tally class (BOTH1 / PLUS1 / list) and
+// (b) the positions of its list in genome order (GetRow_Blob, ufindex.cpp:883); slots that merely store
+// another slot's overflow read as "other" and FREE slots read as FREE, and both are skipped identically
+// (search1m6.cpp:172, getseed.cpp:22).  This builder reproduces (a) and (b) exactly -- same counts
+// (CountSlots / CountSlots_Minus, ufindex.cpp:338,373), same "indexed iff 1<=n<=MaxIx and m<=MaxIx" rule
+// (UpdateSlot, ufindex.cpp:208), same list order, same link encoding incl. long links -- but places overflow
+// elements by parallel claiming, so the blob is functionally equivalent, not byte-identical.  The
+// byte-identical sequential builder lives in the host CLI (urmb_host.cpp).
+//
+// Passes (all thread-per-element, HBM-bound):
+//   init   : every slot := {FREE, 0xFFFFFFFF}
+//   count  : saturating 8-bit counts per slot for plus- and minus-strand k-mers (CAS on packed bytes)
+//   scan   : exclusive prefix sum of list lengths over indexed slots -> pool offsets (two-level)
+//   scatter: positions of indexed k-mers -> pool[base[slot] + ticket]
+//   link   : per indexed slot: sort its <=32 positions, write head, claim overflow slots, write links
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "urmb_internal.h"
+
+namespace urmb {
+
+#ifndef URMB_EMU
+#define URMB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+constexpr uint8_t BT_FREE = 0, BT_END = 127, BT_MY_BIT = 128, BT_PLUS1 = 254, BT_BOTH1 = 255, BT_LONG = 125;
+constexpr uint32_t BT_MAX_NEXT = 124, BT_MAX_LINK = 0xffff;
+
+struct BuildArgs {
+    const uint8_t *seq;     // upper-case genome incl. '-' pads
+    uint64_t seq_size;
+    uint64_t slot_count, magic, shift_mask;
+    uint32_t word_len, max_ix;
+    uint8_t *blob;
+    uint32_t *cntP, *cntM;  // packed 8-bit saturating counters
+    uint32_t *fill;         // packed 8-bit tickets
+    uint32_t *base;         // pool offset per slot
+    uint64_t *blocksum;     // per scan block
+    uint32_t *pool;
+    uint32_t *claimed;      // bitmap
+    uint32_t *errors;       // [0] truncated lists, [1] pool overflow
+};
+
+__device__ __forceinline__ uint32_t bletter(uint32_t c) {  // genome is already upper case (ufindex.cpp:466)
+    uint32_t u = c & 0xDFu, r = 0xFFu;
+    if (u == 'A') r = 0;
+    else if (u == 'C') r = 1;
+    else if (u == 'G') r = 2;
+    else if (u == 'T' || u == 'U') r = 3;
+    return r;
+}
+__device__ __forceinline__ uint64_t bmurmur(uint64_t h) {
+    h ^= (h >> 33); h *= 0xff51afd7ed558ccdULL; h ^= (h >> 33); h *= 0xc4ceb9fe1a85ec53ULL; h ^= (h >> 33);
+    return h;
+}
+__device__ __forceinline__ uint64_t bslot(uint64_t word, const BuildArgs &a) {
+    uint64_t h = bmurmur(word & a.shift_mask);
+    uint64_t q = __umul64hi(h, a.magic);
+    uint64_t r = h - q * a.slot_count;
+    if (r >= a.slot_count) r -= a.slot_count;
+    return r;
+}
+__device__ __forceinline__ uint32_t cnt_get(const uint32_t *c, uint64_t s) { return (c[s >> 2] >> ((s & 3) * 8)) & 255u; }
+
+__device__ __forceinline__ void sat_inc(uint32_t *c, uint64_t s) {
+    uint32_t *w = c + (s >> 2);
+    const uint32_t sh = (uint32_t)(s & 3) * 8;
+    uint32_t old = *w;
+    for (;;) {
+        if (((old >> sh) & 255u) == 255u) return;
+        uint32_t assumed = old;
+        old = atomicCAS(w, assumed, assumed + (1u << sh));
+        if (old == assumed) return;
+    }
+}
+
+// words of the k-mer starting at p on both strands; false if any letter is invalid
+__device__ __forceinline__ bool kmer_words(const BuildArgs &a, uint64_t p, uint64_t &fw, uint64_t &rc) {
+    fw = 0;
+    rc = 0;
+    const uint32_t W = a.word_len;
+    for (uint32_t t = 0; t < W; ++t) {
+        uint32_t l = bletter(a.seq[p + t]);
+        if (l > 3) return false;
+        fw = (fw << 2) | l;
+        rc |= (uint64_t)(3u - l) << (2 * t);
+    }
+    return true;
+}
+
+__global__ void build_init_kernel(BuildArgs a) {
+    // 4 records (20 bytes = 5 words) per thread
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t ngroups = (a.slot_count + 3) / 4;
+    if (g >= ngroups) return;
+    const uint64_t nbytes = 5 * a.slot_count;
+    uint8_t *p = a.blob + g * 20;
+    if (g * 20 + 20 <= nbytes) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(p);
+        w[0] = 0xFFFFFF00u; w[1] = 0xFFFF00FFu; w[2] = 0xFF00FFFFu; w[3] = 0x00FFFFFFu; w[4] = 0xFFFFFFFFu;
+    } else {
+        for (uint64_t i = g * 20; i < nbytes; ++i) a.blob[i] = (i % 5 == 0) ? 0 : 0xFF;
+    }
+}
+
+__global__ void build_count_kernel(BuildArgs a) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p + a.word_len > a.seq_size) return;
+    uint64_t fw, rc;
+    if (!kmer_words(a, p, fw, rc)) return;
+    sat_inc(a.cntP, bslot(fw, a));
+    sat_inc(a.cntM, bslot(rc, a));
+}
+
+__device__ __forceinline__ uint32_t list_len(const BuildArgs &a, uint64_t s) {  // 0 if the slot is not indexed
+    uint32_t n = cnt_get(a.cntP, s), m = cnt_get(a.cntM, s);
+    return (n >= 1 && n <= a.max_ix && m <= a.max_ix) ? n : 0;
+}
+
+constexpr int kScanBlock = 2048;  // slots per scan block, 256 threads x 8
+
+__global__ void build_blocksum_kernel(BuildArgs a) {
+    __shared__ uint32_t red[256];
+    const uint64_t s0 = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * 8;
+    uint32_t sum = 0;
+    for (int k = 0; k < 8; ++k) {
+        uint64_t s = s0 + k;
+        if (s < a.slot_count) sum += list_len(a, s);
+    }
+    red[threadIdx.x] = sum;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.blocksum[blockIdx.x] = red[0];
+}
+
+// single CTA: exclusive scan of blocksum in place
+__global__ void build_scan_blocksums_kernel(BuildArgs a, uint64_t nblocks) {
+    __shared__ uint64_t part[1024];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t b0 = 0; b0 < nblocks; b0 += 1024) {
+        uint64_t i = b0 + threadIdx.x;
+        uint64_t v = (i < nblocks) ? a.blocksum[i] : 0;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            uint64_t t = ((int)threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
+            __syncthreads();
+            part[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblocks) a.blocksum[i] = carry + part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += part[1023];
+        __syncthreads();
+    }
+}
+
+__global__ void build_base_kernel(BuildArgs a) {
+    __shared__ uint32_t part[256];
+    const uint64_t s0 = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * 8;
+    uint32_t len[8], sum = 0;
+    for (int k = 0; k < 8; ++k) {
+        uint64_t s = s0 + k;
+        len[k] = (s < a.slot_count) ? list_len(a, s) : 0;
+        sum += len[k];
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        uint32_t t = ((int)threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint64_t run = a.blocksum[blockIdx.x] + part[threadIdx.x] - sum;
+    for (int k = 0; k < 8; ++k) {
+        uint64_t s = s0 + k;
+        if (s < a.slot_count) a.base[s] = (uint32_t)run;
+        run += len[k];
+    }
+}
+
+__global__ void build_scatter_kernel(BuildArgs a) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p + a.word_len > a.seq_size) return;
+    uint64_t fw, rc;
+    if (!kmer_words(a, p, fw, rc)) return;
+    const uint64_t s = bslot(fw, a);
+    const uint32_t n = list_len(a, s);
+    if (n == 0) return;
+    const uint32_t sh = (uint32_t)(s & 3) * 8;
+    const uint32_t old = atomicAdd(a.fill + (s >> 2), 1u << sh);
+    const uint32_t r = (old >> sh) & 255u;
+    if (r >= n) { atomicAdd(a.errors + 1, 1u); return; }
+    a.pool[(uint64_t)a.base[s] + r] = (uint32_t)p;
+}
+
+__device__ __forceinline__ void put_rec(uint8_t *blob, uint64_t slot, uint8_t tally, uint32_t pos) {
+    uint8_t *p = blob + 5 * slot;
+    p[0] = tally;
+    p[1] = (uint8_t)pos; p[2] = (uint8_t)(pos >> 8); p[3] = (uint8_t)(pos >> 16); p[4] = (uint8_t)(pos >> 24);
+}
+
+// first available (never-owned, FindFreeSlot ufindex.cpp:987-1000) and not yet claimed slot after `from`;
+// returns the step (1..65534) or 0 when none
+__device__ uint32_t claim_after(const BuildArgs &a, uint64_t from, uint64_t &slot_out) {
+    uint64_t t = from;
+    for (uint32_t step = 1; step < BT_MAX_LINK; ++step) {
+        ++t;
+        if (t >= a.slot_count) t = 0;
+        uint32_t n = cnt_get(a.cntP, t);
+        if (n > 0 && n <= a.max_ix) continue;
+        const uint32_t bit = 1u << (t & 31);
+        uint32_t *w = a.claimed + (t >> 5);
+        if (*w & bit) continue;
+        if (atomicOr(w, bit) & bit) continue;
+        slot_out = t;
+        return step;
+    }
+    return 0;
+}
+
+__global__ void build_link_kernel(BuildArgs a) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.slot_count) return;
+    const uint32_t n = list_len(a, s);
+    if (n == 0) return;
+    uint32_t pos[32];
+    const uint64_t b = a.base[s];
+    for (uint32_t i = 0; i < n; ++i) {  // insertion sort: genome order (UpdateSlot is called in genome order)
+        uint32_t v = a.pool[b + i];
+        int j = (int)i - 1;
+        while (j >= 0 && pos[j] > v) { pos[j + 1] = pos[j]; --j; }
+        pos[j + 1] = v;
+    }
+    if (n == 1) {  // ufindex.cpp:217-234
+        put_rec(a.blob, s, (cnt_get(a.cntM, s) == 0) ? BT_BOTH1 : BT_PLUS1, pos[0]);
+        return;
+    }
+    uint64_t cur = s;          // current end of list
+    uint32_t curpos = pos[0];  // position stored at cur
+    bool cur_is_head = true;
+    for (uint32_t r = 1; r < n; ++r) {
+        uint64_t t;
+        uint32_t step = claim_after(a, cur, t);
+        if (step == 0) { atomicAdd(a.errors, 1u); break; }
+        if (step <= BT_MAX_NEXT) {  // ufindex.cpp:303-313
+            put_rec(a.blob, cur, (uint8_t)((cur_is_head ? BT_MY_BIT : 0) | step), curpos);
+            cur = t;
+        } else {  // long link, ufindex.cpp:256-300
+            uint64_t t2;
+            uint32_t step2 = claim_after(a, t, t2);
+            if (step2 == 0) { atomicAdd(a.errors, 1u); break; }
+            put_rec(a.blob, cur, (uint8_t)((cur_is_head ? BT_MY_BIT : 0) | BT_LONG), step | (step2 << 16));
+            put_rec(a.blob, t, BT_LONG, curpos);
+            cur = t2;
+        }
+        curpos = pos[r];
+        cur_is_head = false;
+    }
+    put_rec(a.blob, cur, (uint8_t)((cur_is_head ? BT_MY_BIT : 0) | BT_END), curpos);
+}
+
+static std::string g_build_err;
+
+#define BCK(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e_ = (cudaError_t)(call);                                              \
+        if (e_ != cudaSuccess) {                                                           \
+            g_build_err = std::string(#call) + ": " + cudaGetErrorString(e_);              \
+            goto fail;                                                                     \
+        }                                                                                  \
+    } while (0)
+
+}  // namespace urmb
+
+using namespace urmb;
+
+#ifndef URMB_EMU
+extern "C" const char *urmb_build_last_error() { return g_build_err.c_str(); }
+
+// d_seq: seq_data_size bytes on the current device; d_blob: 5*slot_count+URMB_BLOB_PAD bytes (written).
+// stats[0] = indexed positions, stats[1] = truncated lists (0 expected), stats[2] = seconds.
+extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t slot_count,
+                                       uint32_t word_length, uint32_t max_ix, void *d_blob, uint64_t *stats) {
+    if (!d_seq || !d_blob || slot_count < 2 || word_length < 8 || word_length > 32 || max_ix < 1 || max_ix > 32)
+        return URMB_E_ARG;
+    BuildArgs a{};
+    a.seq = (const uint8_t *)d_seq;
+    a.seq_size = seq_data_size;
+    a.slot_count = slot_count;
+    a.magic = (uint64_t)((((unsigned __int128)1) << 64) / slot_count);
+    a.shift_mask = (word_length >= 32) ? ~0ull : ((1ull << (2 * word_length)) - 1);
+    a.word_len = word_length;
+    a.max_ix = max_ix;
+    a.blob = (uint8_t *)d_blob;
+    const uint64_t cwords = (slot_count + 3) / 4 + 1;
+    const uint64_t nblocks = (slot_count + kScanBlock - 1) / kScanBlock;
+    uint64_t total = 0;
+    uint32_t herr[2] = {0, 0};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0;
+    const int T = 256;
+    const uint64_t gpos = (seq_data_size + T - 1) / T, gslot = (slot_count + T - 1) / T;
+    BCK(cudaEventCreate(&e0));
+    BCK(cudaEventCreate(&e1));
+    BCK(cudaEventRecord(e0));
+    BCK(cudaMalloc(&a.cntP, cwords * 4));
+    BCK(cudaMalloc(&a.cntM, cwords * 4));
+    BCK(cudaMalloc(&a.fill, cwords * 4));
+    BCK(cudaMalloc(&a.base, slot_count * 4));
+    BCK(cudaMalloc(&a.blocksum, (nblocks + 1) * 8));
+    BCK(cudaMalloc(&a.claimed, (slot_count / 32 + 2) * 4));
+    BCK(cudaMalloc(&a.errors, 8));
+    BCK(cudaMemset(a.cntP, 0, cwords * 4));
+    BCK(cudaMemset(a.cntM, 0, cwords * 4));
+    BCK(cudaMemset(a.fill, 0, cwords * 4));
+    BCK(cudaMemset(a.claimed, 0, (slot_count / 32 + 2) * 4));
+    BCK(cudaMemset(a.errors, 0, 8));
+    BCK(cudaMemset(a.blocksum, 0, (nblocks + 1) * 8));
+    BCK(cudaMemset((uint8_t *)d_blob + 5 * slot_count, 0, URMB_BLOB_PAD));
+    build_init_kernel<<<(unsigned)(((slot_count + 3) / 4 + T - 1) / T), T>>>(a);
+    build_count_kernel<<<(unsigned)gpos, T>>>(a);
+    build_blocksum_kernel<<<(unsigned)nblocks, 256>>>(a);
+    build_scan_blocksums_kernel<<<1, 1024>>>(a, nblocks + 1);   // entry [nblocks] (zero) becomes the grand total
+    BCK(cudaGetLastError());
+    BCK(cudaMemcpy(&total, a.blocksum + nblocks, 8, cudaMemcpyDeviceToHost));
+    BCK(cudaMalloc(&a.pool, (total + 1) * 4));
+    build_base_kernel<<<(unsigned)nblocks, 256>>>(a);
+    build_scatter_kernel<<<(unsigned)gpos, T>>>(a);
+    build_link_kernel<<<(unsigned)gslot, T>>>(a);
+    BCK(cudaGetLastError());
+    BCK(cudaMemcpy(herr, a.errors, 8, cudaMemcpyDeviceToHost));
+    BCK(cudaEventRecord(e1));
+    BCK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (stats) {
+        stats[0] = total;
+        stats[1] = herr[0];
+        stats[2] = (uint64_t)(ms * 1000.0f);
+    }
+    cudaFree(a.cntP); cudaFree(a.cntM); cudaFree(a.fill); cudaFree(a.base); cudaFree(a.blocksum);
+    cudaFree(a.claimed); cudaFree(a.errors); cudaFree(a.pool);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (herr[1]) { g_build_err = "pool overflow (internal error)"; return URMB_E_OVERFLOW; }
+    return URMB_OK;
+fail:
+    cudaFree(a.cntP); cudaFree(a.cntM); cudaFree(a.fill); cudaFree(a.base); cudaFree(a.blocksum);
+    cudaFree(a.claimed); cudaFree(a.errors); cudaFree(a.pool);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return URMB_E_CUDA;
+}
+#endif

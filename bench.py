@@ -308,9 +308,10 @@ def main():
     baseline = load_json("BASELINE.json")
     peaks = load_json("MEASURED_PEAKS.json")
     metric = baseline.get("metric", "reads/s mapped, 2x150bp human-scale")
-    workload = ("synthetic %.2f Gb reference (24 contigs, 10%% injected repeats), UFI in HBM, %s %d bp reads, "
-                "%.1f%% subs + %.2f%% indels" % (args.genome_len / 1e9, "paired-end 2x" if paired else "single-end",
-                                                 args.read_len, 100 * args.sub, 100 * args.indel))
+    workload = ("synthetic %.2f Gb reference (%d contigs, 10%% injected repeats), UFI in HBM, %s%d bp reads, "
+                "%.1f%% subs + %.2f%% indels" % (args.genome_len / 1e9, 24 if args.genome_len >= 100_000_000 else 3,
+                                                 "paired-end 2x" if paired else "single-end ", args.read_len,
+                                                 100 * args.sub, 100 * args.indel))
     cfg = {"workload": workload, "pairs_per_step_per_gpu" if paired else "reads_per_step_per_gpu": args.pairs_per_step,
            "parallelism": f"reads sharded over {world} GPU(s), index replicated by NCCL broadcast, no per-batch collective",
            "l2_policy": "inputs larger than L2: each batch is >=300 MB of reads and probes a 27 GB table at random",

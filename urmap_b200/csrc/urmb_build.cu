@@ -366,4 +366,23 @@ fail:
     if (e1) cudaEventDestroy(e1);
     return URMB_E_CUDA;
 }
+
+// Host-buffer convenience used by `urmap_b200 -make_ufi ... -gpu_build`.
+extern "C" int urmb_host_gpu_build(const uint8_t *seq, uint64_t n, uint64_t slots, uint32_t W, uint32_t maxix,
+                                   uint8_t *blob) {
+    void *d_seq = nullptr, *d_blob = nullptr;
+    int rc = URMB_E_CUDA;
+    uint64_t stats[3] = {0, 0, 0};
+    if (cudaMalloc(&d_seq, n + 64) != cudaSuccess) { g_build_err = "cudaMalloc(seq) failed (no CUDA device?)"; return URMB_E_NODEVICE; }
+    if (cudaMalloc(&d_blob, 5 * slots + URMB_BLOB_PAD) != cudaSuccess) { g_build_err = "cudaMalloc(blob) failed"; goto out; }
+    if (cudaMemset((uint8_t *)d_seq + n, 0, 64) != cudaSuccess) goto out;
+    if (cudaMemcpy(d_seq, seq, n, cudaMemcpyHostToDevice) != cudaSuccess) goto out;
+    rc = urmb_build_index_device(d_seq, n, slots, W, maxix, d_blob, stats);
+    if (rc == 0 && stats[1] != 0) { g_build_err = "lists truncated"; rc = URMB_E_OVERFLOW; }
+    if (rc == 0 && cudaMemcpy(blob, d_blob, 5 * slots, cudaMemcpyDeviceToHost) != cudaSuccess) rc = URMB_E_CUDA;
+out:
+    cudaFree(d_seq);
+    cudaFree(d_blob);
+    return rc;
+}
 #endif

@@ -172,6 +172,7 @@ struct Mate {
     const uint8_t *tally;   // shared: [2][qcap]
     const uint32_t *pos;    // shared: [2][qcap]
     const uint64_t *slots;  // global: [2][qcap]
+    uint32_t *alive;        // shared: [2][8] bit q set = the BOTH1 candidate at (strand, q) survives the prefilter
     MateScratch *g;
     uint32_t QL, QWC, qcap;
     int HitCount, HSPCount, Top, MaxPenalty, Best, Second, BestHSP;
@@ -377,9 +378,111 @@ __device__ ExtOut extend_core(const Env &E, const Mate &m, uint32_t SeedPosQ, ui
     return o;
 }
 
+
+// ---- state-independent candidate prefilter ---------------------------------------------------
+// ExtendPen returns -1 WITHOUT touching any state whenever the unconstrained gapless extension (no penalty
+// bound) is neither full-length nor reaches MIN_HSP_SCORE: the penalty bound and the hit-overlap test can only
+// turn more calls into -1 (extendpen.cpp:11-17,45,71).  About 90 % of all candidates are hash-collision
+// artefacts of the key-less table that die within a few bases of the seed, so each LANE tests one candidate
+// against <= 16 bases per side; only candidates that are still alive go through the exact warp-wide path, in
+// the reference's order.  32 independent genome gathers are in flight per warp instead of one.
+__device__ __forceinline__ uint64_t load8_global(const uint8_t *p) {  // 8 bytes at an arbitrary address (padded buffer)
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+    uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    uint64_t lo = ((uint64_t)w1 << 32) | w0;
+    return sh ? ((lo >> sh) | ((uint64_t)w2 << (64 - sh))) : lo;
+}
+__device__ __forceinline__ uint64_t load8_shared(const uint8_t *p) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+    uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    uint64_t lo = ((uint64_t)w1 << 32) | w0;
+    return sh ? ((lo >> sh) | ((uint64_t)w2 << (64 - sh))) : lo;
+}
+
+constexpr int kPrefilterWin = 16;  // bases examined on each side of the seed
+
+// Lane-local. true = must take the exact path; false = ExtendPen would certainly return -1 with no side effect.
+__device__ bool prefilter_alive(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
+    if (SeedPosDB < SeedPosQ) return false;  // extendpen.cpp:11
+    const uint32_t DBLo = SeedPosDB - SeedPosQ;
+    const uint8_t *Qs = mate_seq(m, Plus);
+    const uint8_t *T = E.ix.seq + DBLo;
+    const int QL = (int)m.QL, W = (int)E.ix.word_len, MM = E.P.MM, XD = E.P.XDROP;
+    int Score = W, Best = 0;
+    int End = (int)SeedPosQ + W - 1, Start = (int)SeedPosQ;
+    {   // right scan, extendpen.cpp:29-52 without the penalty bound
+        int p = End + 1;
+        const int lim = min(QL, p + kPrefilterWin);
+        bool term = false;
+        while (p < lim && !term) {
+            uint64_t x = load8_shared(Qs + p) ^ load8_global(T + p);
+            const int n = min(8, lim - p);
+            for (int j = 0; j < n; ++j, ++p) {
+                if (((x >> (8 * j)) & 0xFFu) == 0) {
+                    ++Score;
+                    if (Score > Best) { Best = Score; End = p; }
+                } else {
+                    Score += MM;
+                    if (Best - Score > XD) { term = true; break; }
+                }
+            }
+        }
+        if (!term && p < QL) return true;
+    }
+    {   // left scan, extendpen.cpp:55-78
+        int p = Start - 1;
+        const int lim = max(-1, p - kPrefilterWin);  // exclusive
+        bool term = false;
+        while (p > lim && !term) {
+            const int n = min(8, p - lim);
+            const int lo = p - n + 1;
+            uint64_t x = load8_shared(Qs + lo) ^ load8_global(T + lo);
+            for (int j = n - 1; j >= 0; --j, --p) {
+                if (((x >> (8 * j)) & 0xFFu) == 0) {
+                    ++Score;
+                    if (Score > Best) { Best = Score; Start = p; }
+                } else {
+                    Score += MM;
+                    if (Best - Score > XD) { term = true; break; }
+                }
+            }
+        }
+        if (!term && p >= 0) return true;
+    }
+    if (Start == 0 && End == QL - 1) return true;
+    const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * QL) / 100.0);
+    return Best >= MinHSPScore;
+}
+
+// Prefilter every BOTH1 candidate of a mate (both strands) in parallel and publish the survivors as bitmasks.
+__device__ void build_alive_table(const Env &E, Mate &m) {
+    for (int s = 0; s < 2; ++s) {
+        for (uint32_t q0 = 0; q0 < 256; q0 += 32) {
+            const uint32_t q = q0 + E.lane;
+            bool a = false;
+            if (q < m.QWC && m.tally[s * m.qcap + q] == T_BOTH1) a = prefilter_alive(E, m, q, m.pos[s * m.qcap + q], s == 0);
+            const uint32_t w = __ballot_sync(FULL, a);
+            if (E.lane == 0) m.alive[s * 8 + (q0 >> 5)] = w;
+            if (q0 + 32 >= m.QWC) {
+                for (uint32_t r = (q0 >> 5) + 1 + E.lane; r < 8; r += 32) m.alive[s * 8 + r] = 0;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // State1::ExtendPen, extendpen.cpp:9-95. +score: full-length hit; -2: HSP saved; -1 otherwise.
 __device__ __noinline__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
     if (SeedPosDB < SeedPosQ) return -1;
+    {   // BOTH1 candidate on its own strand that the prefilter proved dead: -1 with no side effect
+        const uint32_t si = Plus ? 0u : 1u;
+        if (SeedPosQ < m.QWC && m.tally[si * m.qcap + SeedPosQ] == T_BOTH1 && m.pos[si * m.qcap + SeedPosQ] == SeedPosDB &&
+            !((m.alive[si * 8 + (SeedPosQ >> 5)] >> (SeedPosQ & 31)) & 1u))
+            return -1;
+    }
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
     if (overlaps_hit(E, m, DBLo)) return -1;
     ExtOut o = extend_core(E, m, SeedPosQ, DBLo, Plus, true);
@@ -788,11 +891,68 @@ __device__ __forceinline__ uint64_t m_slot(const Mate &m, int strand, uint32_t q
     return __ldg(m.slots + strand * m.qcap + q);
 }
 
-// GetRow_Blob for (QPos, strand) followed by ExtendPen of every position (search1m6.cpp:181-199 inner loop).
-__device__ void extend_row(const Env &E, Mate &m, uint32_t QPos, int strand, uint32_t RowLength, uint32_t mypos) {
-    for (uint32_t r = 0; r < RowLength; ++r) {
-        uint32_t SeedPosDB = __shfl_sync(FULL, mypos, r);
-        extend_pen(E, m, QPos, SeedPosDB, strand == 0);
+// Lane-local GetRow_Blob (ufindex.cpp:883-943) limited to what the "rows <= 2 now, longer rows later" logic
+// needs: n = 0 (not mine), 1, 2, or 3 meaning "RowLength > 2"; p0/p1 = the first two positions.
+__device__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tally, uint32_t Pos0, uint32_t &n, uint32_t &p0,
+                          uint32_t &p1) {
+    n = 0; p0 = 0; p1 = 0;
+    uint32_t T = Tally, Pos = Pos0, K = 0;
+    if ((T & T_MY_BIT) == 0) return;
+    uint64_t Slot2 = Slot;
+    const uint64_t SC = E.ix.slot_count;
+    for (;;) {
+        if (K > 0) load_blob(E.ix.blob, Slot2, T, Pos);
+        if (K == 0) p0 = Pos; else if (K == 1) p1 = Pos;
+        ++K;
+        if (K == E.ix.max_ix) { n = K; return; }
+        if (T == T_PLUS1 || T == T_BOTH1) { n = 1; return; }
+        if (T == T_END) { n = K; return; }
+        if (K == 3) { n = 3; return; }
+        if (T == T_LONG_MINE || T == T_LONG_OTHER) {
+            uint32_t StepA = Pos & 0xffffu, StepB = Pos >> 16;
+            uint64_t SlotA = add_mod(Slot2, StepA, SC);
+            Slot2 = add_mod(SlotA, StepB, SC);
+            uint32_t ta, pa;
+            load_blob(E.ix.blob, SlotA, ta, pa);
+            if (K == 1) p0 = pa; else if (K == 2) p1 = pa;
+        } else {
+            Slot2 = add_mod(Slot2, T & T_NEXT_MASK, SC);
+        }
+    }
+}
+
+// One item (QPos) per lane: walk the heads of 32 rows and prefilter their candidates in parallel, then visit the
+// items in lane order exactly like the reference's loop body (search1m6.cpp:181-199, search1pepend.cpp:53-68):
+// rows longer than 2 are deferred through `defer` (returns how many were deferred), the others are extended now.
+template <class Defer>
+__device__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint32_t QPos, Defer defer) {
+    uint32_t n = 0, p0 = 0, p1 = 0;
+    if (valid) row_head3(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), n, p0, p1);
+    if (n > E.ix.max_ix) n = E.ix.max_ix;
+    const bool a0 = valid && n >= 1 && n <= 2 && prefilter_alive(E, m, QPos, p0, s == 0);
+    const bool a1 = valid && n == 2 && prefilter_alive(E, m, QPos, p1, s == 0);
+    uint32_t vmask = __ballot_sync(FULL, valid);
+    const uint32_t m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1), big = __ballot_sync(FULL, n > 2);
+    while (vmask) {
+        const int b = __ffs(vmask) - 1;
+        vmask &= vmask - 1;
+        const uint32_t qb = __shfl_sync(FULL, QPos, b);
+        if (big >> b & 1u) { defer(qb); continue; }
+        if (m0 >> b & 1u) extend_pen(E, m, qb, __shfl_sync(FULL, p0, b), s == 0);
+        if (m1 >> b & 1u) extend_pen(E, m, qb, __shfl_sync(FULL, p1, b), s == 0);
+    }
+}
+
+// A deferred (long) row: full GetRow_Blob, one position per lane, prefilter in parallel, extend survivors in order.
+__device__ void row_long_stage(const Env &E, Mate &m, int s, uint32_t QPos) {
+    uint32_t mypos;
+    const uint32_t RowLength = get_row(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
+    const bool a = ((uint32_t)E.lane < RowLength) && prefilter_alive(E, m, QPos, mypos, s == 0);
+    uint32_t am = __ballot_sync(FULL, a);
+    while (am) {
+        const int r = __ffs(am) - 1;
+        am &= am - 1;
+        extend_pen(E, m, QPos, __shfl_sync(FULL, mypos, r), s == 0);
     }
 }
 
@@ -854,36 +1014,23 @@ __device__ void search_lo(const Env &E, Mate &m) {
     // phase 4: non-BOTH1 owned slots; rows <= 2 now, longer rows deferred
     int nTodo[2] = {0, 0};
     for (int s = 0; s < 2; ++s) {
+        int nt = 0;
         for (uint32_t q0 = 0; q0 < QWC; q0 += 32) {
-            uint32_t q = q0 + E.lane;
-            uint32_t T = (q < QWC) ? m_tally(m, s, q) : 0;
-            uint32_t cand = __ballot_sync(FULL, T != T_FREE && T != T_BOTH1 && (T & T_MY_BIT));
-            while (cand) {
-                int bit = __ffs(cand) - 1;
-                cand &= cand - 1;
-                uint32_t QPos = q0 + bit;
-                uint32_t mypos;
-                uint32_t RowLength = get_row(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
-                if (RowLength > 2) {
-                    if (E.lane == 0) m.g->todo[s][nTodo[s]] = (uint8_t)QPos;
-                    ++nTodo[s];
-                    continue;
-                }
-                extend_row(E, m, QPos, s, RowLength, mypos);
-            }
+            const uint32_t q = q0 + E.lane;
+            const uint32_t T = (q < QWC) ? m_tally(m, s, q) : 0;
+            const bool cand = (T != T_FREE && T != T_BOTH1 && (T & T_MY_BIT));
+            rows_short_stage(E, m, s, cand, q, [&](uint32_t qd) {
+                if (E.lane == 0) m.g->todo[s][nt] = (uint8_t)qd;
+                ++nt;
+            });
         }
+        nTodo[s] = nt;
     }
     __syncwarp();
     if (m.Best >= MinScorePhase3) { m.Mapq = calc_mapq6(m); return; }
     // phase 5
-    for (int s = 0; s < 2; ++s) {
-        for (int t = 0; t < nTodo[s]; ++t) {
-            uint32_t QPos = m.g->todo[s][t];
-            uint32_t mypos;
-            uint32_t RowLength = get_row(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
-            extend_row(E, m, QPos, s, RowLength, mypos);
-        }
-    }
+    for (int s = 0; s < 2; ++s)
+        for (int t = 0; t < nTodo[s]; ++t) row_long_stage(E, m, s, m.g->todo[s][t]);
     if (m.Best >= MinScorePhase4) { m.Mapq = calc_mapq6(m); return; }
     // phase 6
     for (int i = 0; i < m.HSPCount; ++i) align_hsp(E, m, i);
@@ -961,29 +1108,23 @@ __device__ void search_pe_pending(const Env &E, Mate &m) {
     }
     __syncwarp();
     int n2[2] = {0, 0};
-    for (int s = 0; s < 2; ++s) {
-        for (int i = 0; i < m.nPend[s]; ++i) {
-            uint32_t QPos = m.g->pend[s][i];
-            __syncwarp();   // the list is compacted in place below
-            uint32_t mypos;
-            uint32_t RowLength = get_row(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
-            if (RowLength > 2) {
-                if (E.lane == 0) m.g->pend[s][n2[s]] = (uint8_t)QPos;
-                ++n2[s];
-                continue;
-            }
-            extend_row(E, m, QPos, s, RowLength, mypos);
+    for (int s = 0; s < 2; ++s) {   // pending round 1: 32 list entries at a time
+        int nd = 0;
+        for (int i0 = 0; i0 < m.nPend[s]; i0 += 32) {
+            const int i = i0 + E.lane;
+            const bool valid = i < m.nPend[s];
+            const uint32_t QPos = valid ? m.g->pend[s][i] : 0;
+            __syncwarp();   // the list is compacted in place below (nd <= i0 for every write)
+            rows_short_stage(E, m, s, valid, QPos, [&](uint32_t qd) {
+                if (E.lane == 0) m.g->pend[s][nd] = (uint8_t)qd;
+                ++nd;
+            });
+            __syncwarp();
         }
-        __syncwarp();
+        n2[s] = nd;
     }
-    for (int s = 0; s < 2; ++s) {
-        for (int i = 0; i < n2[s]; ++i) {
-            uint32_t QPos = m.g->pend[s][i];
-            uint32_t mypos;
-            uint32_t RowLength = get_row(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
-            extend_row(E, m, QPos, s, RowLength, mypos);
-        }
-    }
+    for (int s = 0; s < 2; ++s)     // pending round 2
+        for (int i = 0; i < n2[s]; ++i) row_long_stage(E, m, s, m.g->pend[s][i]);
     const int B = max(m.Best, m.BestHSP) - 8;
     for (int i = 0; i < m.HSPCount; ++i) {
         if ((int)m.g->hsp_score[i] < B) continue;
@@ -1297,7 +1438,7 @@ __device__ void write_result(const Env &E, const Mate &m, const DevOut &o, uint3
 
 // Load one read into shared memory (bytes, reverse complement, probe results).
 __device__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevProbe &pr, uint32_t r, uint8_t *s_q,
-                          uint8_t *s_rc, uint8_t *s_tally, uint32_t *s_pos, MateScratch *g) {
+                          uint8_t *s_rc, uint8_t *s_tally, uint32_t *s_pos, uint32_t *s_alive, MateScratch *g) {
     const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
     for (uint32_t i = E.lane; i < L; i += 32) {
         uint32_t c = b.seqs[off + i];
@@ -1320,9 +1461,11 @@ __device__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevPro
     m.QWC = (L >= E.ix.word_len) ? L - E.ix.word_len + 1 : 0;
     m.qcap = b.qcap;
     m.overflow = 0;
+    m.alive = s_alive;
+    build_alive_table(E, m);
 }
 
-__global__ void __launch_bounds__(128) search_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
+__global__ void __launch_bounds__(128, 4) search_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
                                                     WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
                                                     uint32_t tb_rows) {
     URMB_DYN_SMEM(smem);
@@ -1339,6 +1482,8 @@ __global__ void __launch_bounds__(128) search_kernel(DevIndex ix, DevParams P, D
     p8 += (size_t)nm * b.seqcap;
     uint8_t *s_tally = p8;
     p8 += (size_t)nm * 2 * b.qcap;
+    uint32_t *s_alive = reinterpret_cast<uint32_t *>(p8);
+    p8 += (size_t)nm * 16 * 4;
     Env E;
     E.ix = ix;
     E.P = P;
@@ -1357,15 +1502,15 @@ __global__ void __launch_bounds__(128) search_kernel(DevIndex ix, DevParams P, D
         if (u >= b.n_units) break;
         if (!b.paired) {
             Mate m;
-            load_mate(E, m, b, pr, u, s_q, s_rc, s_tally, s_pos, &E.ws->m[0]);
+            load_mate(E, m, b, pr, u, s_q, s_rc, s_tally, s_pos, s_alive, &E.ws->m[0]);
             reset_search(E, m);   // State1::Search, search1.cpp:7-24
             search_lo(E, m);
             write_result(E, m, o, u);
         } else {
             Mate F, R;
-            load_mate(E, F, b, pr, u, s_q, s_rc, s_tally, s_pos, &E.ws->m[0]);
+            load_mate(E, F, b, pr, u, s_q, s_rc, s_tally, s_pos, s_alive, &E.ws->m[0]);
             load_mate(E, R, b, pr, b.n_units + u, s_q + b.seqcap, s_rc + b.seqcap, s_tally + 2 * b.qcap,
-                      s_pos + 2 * b.qcap, &E.ws->m[1]);
+                      s_pos + 2 * b.qcap, s_alive + 16, &E.ws->m[1]);
             search_pair(E, F, R);
             write_result(E, F, o, u);
             write_result(E, R, o, b.n_units + u);
@@ -1381,7 +1526,7 @@ static inline uint32_t tb_stride_for(const DevParams &P) { return 4 * P.R + 6; }
 
 size_t search_smem_per_warp(const DevBatch &b, const DevParams &P) {
     const int nm = b.paired ? 2 : 1;
-    size_t s = (size_t)nm * 2 * b.qcap * 4 + (size_t)nm * b.seqcap * 2 + (size_t)nm * 2 * b.qcap;
+    size_t s = (size_t)nm * 2 * b.qcap * 4 + (size_t)nm * b.seqcap * 2 + (size_t)nm * 2 * b.qcap + (size_t)nm * 64;
     s += b.seqcap + 64;
     const uint32_t rows = b.seqcap + 2;
     s += (size_t)rows * tb_stride_for(P) + rows;

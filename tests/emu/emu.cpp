@@ -114,11 +114,12 @@ using namespace urmb;
 
 static DevParams emu_make_params(const urmb_params &p) {  // same table as urmb_api.cu make_params
     DevParams P;
-    if (p.method == 7) P = DevParams{-4, -6, -2, 35, 35, 12, 75, 8, 6, 5, 8u, 4};
-    else P = DevParams{-3, -5, -1, 20, 60, 9, 100, 1, 1, 1, 12u, 4};
+    if (p.method == 7) P = DevParams{-4, -6, -2, 35, 35, 12, 75, 8, 6, 5, 8u, 4, 3u};
+    else P = DevParams{-3, -5, -1, 20, 60, 9, 100, 1, 1, 1, 12u, 4, 3u};
     P.pe_method = (p.pe_method == 5) ? 5 : 4;
     if (p.band_radius >= 0) P.R = (uint32_t)p.band_radius;
     else if (p.pe_method == 5) P.R = 4;
+    if (const char *f = getenv("URMB_FLAGS")) P.flags = (uint32_t)strtoul(f, nullptr, 0);
     return P;
 }
 
@@ -162,6 +163,9 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     launch_probe(ix, b, pr, nullptr, 1);
     launch_search(ix, P, b, pr, o, ws, nw, nullptr, 1, nullptr);
     free(ws);
+    if (getenv("URMB_EMU_STATS"))
+        fprintf(stderr, "EMU stats: prefilter calls %llu alive %llu | extend_pen calls %llu reaching extend_core %llu\n", urmb::g_pf_calls,
+                urmb::g_pf_alive, urmb::g_ext_calls, urmb::g_ext_core);
     return 0;
 }
 

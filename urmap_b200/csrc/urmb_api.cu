@@ -177,11 +177,13 @@ static int fail(urmb_ctx *c, int code, const std::string &msg) {
 
 static DevParams make_params(const urmb_params &p) {  // State1::SetMethod, state1.cpp:147-183
     DevParams P;
-    if (p.method == 7) P = DevParams{-4, -6, -2, 35, 35, 12, 75, 8, 6, 5, 8u, 4};
-    else P = DevParams{-3, -5, -1, 20, 60, 9, 100, 1, 1, 1, 12u, 4};
+    if (p.method == 7) P = DevParams{-4, -6, -2, 35, 35, 12, 75, 8, 6, 5, 8u, 4, 3u};
+    else P = DevParams{-3, -5, -1, 20, 60, 9, 100, 1, 1, 1, 12u, 4, 3u};
     P.pe_method = (p.pe_method == 5) ? 5 : 4;
     if (p.band_radius >= 0) P.R = (uint32_t)p.band_radius;
     else if (p.pe_method == 5) P.R = 4;   // map2.cpp:17-21
+    P.flags = 0x100;   // bit8: automatic (prefilters on for single-end, off for paired-end; measured)
+    if (const char *f = getenv("URMB_FLAGS")) P.flags = (uint32_t)strtoul(f, nullptr, 0);
     return P;
 }
 
@@ -475,7 +477,9 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         int e = launch_probe(c->ix, s.batch, pr, c->compute, c->sm_count);
         if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
         CK(cudaEventRecord(s.ev_k1, c->compute));
-        e = launch_search(c->ix, c->P, s.batch, pr, o, c->scratch, c->n_scratch_warps, c->compute, c->sm_count, nullptr);
+        DevParams P = c->P;
+        if (P.flags & 0x100u) P.flags = s.batch.paired ? 0u : 3u;
+        e = launch_search(c->ix, P, s.batch, pr, o, c->scratch, c->n_scratch_warps, c->compute, c->sm_count, nullptr);
         if (e) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)e));
         c->launches += 2;
     } else {

@@ -94,11 +94,33 @@ __device__ __forceinline__ uint64_t add_mod(uint64_t a, uint64_t b, uint64_t p) 
     return s;
 }
 
+// Index and genome bytes are touched once per candidate at random addresses: keep them out of L1 so that the
+// per-warp search state (local/global scratch) stays resident there.
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t *p) {
+#ifdef URMB_EMU
+    return *p;
+#else
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#endif
+}
+__device__ __forceinline__ uint32_t ldg_stream_u8(const uint8_t *p) {
+#ifdef URMB_EMU
+    return *p;
+#else
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#endif
+}
+
 // 5-byte record at byte offset 5*slot: two aligned 32-bit loads (the table is padded).
+template <bool STREAM = true>
 __device__ __forceinline__ void load_blob(const uint8_t *blob, uint64_t slot, uint32_t &tally, uint32_t &pos) {
     uint64_t a = 5ull * slot;
     const uint32_t *w = reinterpret_cast<const uint32_t *>(blob + (a & ~3ull));
-    uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+    uint32_t w0 = STREAM ? ldg_stream_u32(w) : __ldg(w), w1 = STREAM ? ldg_stream_u32(w + 1) : __ldg(w + 1);
     uint32_t sh = (uint32_t)(a & 3ull) * 8u;   // tally at bit sh, pos at bits sh+8 .. sh+40 (<= 64)
     uint64_t v = (((uint64_t)w1 << 32) | w0) >> sh;
     tally = (uint32_t)v & 0xFFu;
@@ -140,7 +162,7 @@ __global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevBatch b, Dev
                     }
                     if (!bad) {
                         slot = mod_slots(murmur64(word & ix.shift_mask), ix.slot_count, ix.magic);
-                        load_blob(ix.blob, slot, tally, pos);
+                        load_blob<false>(ix.blob, slot, tally, pos);
                     }
                 }
                 pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
@@ -330,7 +352,7 @@ __device__ ExtOut extend_core(const Env &E, const Mate &m, uint32_t SeedPosQ, ui
     uint32_t mymask = 0;
     for (int k = 0; k < nw; ++k) {
         int idx = (k << 5) + E.lane;
-        bool mis = (idx < QL) && (Qs[idx] != __ldg(T + idx));
+        bool mis = (idx < QL) && ((uint32_t)Qs[idx] != ldg_stream_u8(T + idx));
         uint32_t w = __ballot_sync(FULL, mis);
         if (E.lane == k) mymask = w;
     }
@@ -389,7 +411,7 @@ __device__ ExtOut extend_core(const Env &E, const Mate &m, uint32_t SeedPosQ, ui
 __device__ __forceinline__ uint64_t load8_global(const uint8_t *p) {  // 8 bytes at an arbitrary address (padded buffer)
     const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-    uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    uint32_t w0 = ldg_stream_u32(w), w1 = ldg_stream_u32(w + 1), w2 = ldg_stream_u32(w + 2);
     uint64_t lo = ((uint64_t)w1 << 32) | w0;
     return sh ? ((lo >> sh) | ((uint64_t)w2 << (64 - sh))) : lo;
 }
@@ -404,7 +426,20 @@ __device__ __forceinline__ uint64_t load8_shared(const uint8_t *p) {
 constexpr int kPrefilterWin = 16;  // bases examined on each side of the seed
 
 // Lane-local. true = must take the exact path; false = ExtendPen would certainly return -1 with no side effect.
+#ifdef URMB_EMU
+static unsigned long long g_pf_calls = 0, g_pf_alive = 0, g_ext_calls = 0, g_ext_core = 0;
+#define EMU_COUNT(x) (++(x))
+#else
+#define EMU_COUNT(x)
+#endif
+__device__ bool prefilter_alive_impl(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus);
 __device__ bool prefilter_alive(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
+    const bool a = prefilter_alive_impl(E, m, SeedPosQ, SeedPosDB, Plus);
+    EMU_COUNT(g_pf_calls);
+    if (a) EMU_COUNT(g_pf_alive);
+    return a;
+}
+__device__ bool prefilter_alive_impl(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
     if (SeedPosDB < SeedPosQ) return false;  // extendpen.cpp:11
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
     const uint8_t *Qs = mate_seq(m, Plus);
@@ -412,40 +447,53 @@ __device__ bool prefilter_alive(const Env &E, const Mate &m, uint32_t SeedPosQ, 
     const int QL = (int)m.QL, W = (int)E.ix.word_len, MM = E.P.MM, XD = E.P.XDROP;
     int Score = W, Best = 0;
     int End = (int)SeedPosQ + W - 1, Start = (int)SeedPosQ;
+    // all four 8-byte genome chunks (2 per side) are requested before any is consumed: one memory round trip
+    const int pr0 = End + 1, pl0 = Start - 1;
+    const int llo1 = max(0, pl0 - 7), llo2 = max(0, pl0 - 15);
+    uint64_t xr[2], xl[2];
+    {
+        uint64_t tr0 = load8_global(T + pr0), tr1 = load8_global(T + pr0 + 8);
+        uint64_t tl0 = load8_global(T + llo1), tl1 = load8_global(T + llo2);
+        xr[0] = load8_shared(Qs + pr0) ^ tr0;
+        xr[1] = load8_shared(Qs + pr0 + 8) ^ tr1;
+        xl[0] = load8_shared(Qs + llo1) ^ tl0;
+        xl[1] = load8_shared(Qs + llo2) ^ tl1;
+    }
     {   // right scan, extendpen.cpp:29-52 without the penalty bound
-        int p = End + 1;
+        int p = pr0;
         const int lim = min(QL, p + kPrefilterWin);
         bool term = false;
-        while (p < lim && !term) {
-            uint64_t x = load8_shared(Qs + p) ^ load8_global(T + p);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint64_t x = xr[c];
             const int n = min(8, lim - p);
-            for (int j = 0; j < n; ++j, ++p) {
+            for (int j = 0; j < n && !term; ++j, ++p) {
                 if (((x >> (8 * j)) & 0xFFu) == 0) {
                     ++Score;
                     if (Score > Best) { Best = Score; End = p; }
                 } else {
                     Score += MM;
-                    if (Best - Score > XD) { term = true; break; }
+                    if (Best - Score > XD) term = true;
                 }
             }
         }
         if (!term && p < QL) return true;
     }
     {   // left scan, extendpen.cpp:55-78
-        int p = Start - 1;
-        const int lim = max(-1, p - kPrefilterWin);  // exclusive
+        int p = pl0;
         bool term = false;
-        while (p > lim && !term) {
-            const int n = min(8, p - lim);
-            const int lo = p - n + 1;
-            uint64_t x = load8_shared(Qs + lo) ^ load8_global(T + lo);
-            for (int j = n - 1; j >= 0; --j, --p) {
-                if (((x >> (8 * j)) & 0xFFu) == 0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int lo = (c == 0) ? llo1 : llo2;
+            const int hi = (c == 0) ? pl0 : pl0 - 8;     // highest position of this chunk
+            const uint64_t x = xl[c];
+            for (int q = hi; q >= lo && q >= 0 && !term; --q, --p) {
+                if (((x >> (8 * (q - lo))) & 0xFFu) == 0) {
                     ++Score;
-                    if (Score > Best) { Best = Score; Start = p; }
+                    if (Score > Best) { Best = Score; Start = q; }
                 } else {
                     Score += MM;
-                    if (Best - Score > XD) { term = true; break; }
+                    if (Best - Score > XD) term = true;
                 }
             }
         }
@@ -458,6 +506,11 @@ __device__ bool prefilter_alive(const Env &E, const Mate &m, uint32_t SeedPosQ, 
 
 // Prefilter every BOTH1 candidate of a mate (both strands) in parallel and publish the survivors as bitmasks.
 __device__ void build_alive_table(const Env &E, Mate &m) {
+    if (!(E.P.flags & 1u)) {   // switch off: every candidate takes the exact path
+        for (uint32_t r = E.lane; r < 16; r += 32) m.alive[r] = 0xFFFFFFFFu;
+        __syncwarp();
+        return;
+    }
     for (int s = 0; s < 2; ++s) {
         for (uint32_t q0 = 0; q0 < 256; q0 += 32) {
             const uint32_t q = q0 + E.lane;
@@ -476,6 +529,7 @@ __device__ void build_alive_table(const Env &E, Mate &m) {
 
 // State1::ExtendPen, extendpen.cpp:9-95. +score: full-length hit; -2: HSP saved; -1 otherwise.
 __device__ __noinline__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
+    if (E.lane == 0) EMU_COUNT(g_ext_calls);
     if (SeedPosDB < SeedPosQ) return -1;
     {   // BOTH1 candidate on its own strand that the prefilter proved dead: -1 with no side effect
         const uint32_t si = Plus ? 0u : 1u;
@@ -485,6 +539,7 @@ __device__ __noinline__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ,
     }
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
     if (overlaps_hit(E, m, DBLo)) return -1;
+    if (E.lane == 0) EMU_COUNT(g_ext_core);
     ExtOut o = extend_core(E, m, SeedPosQ, DBLo, Plus, true);
     if (o.fail) return -1;
     const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * (int)m.QL) / 100.0);
@@ -514,8 +569,9 @@ __device__ __forceinline__ void range_j(uint32_t LA, uint32_t LB, uint32_t dlo, 
 template <bool BIG>
 struct TBStore {
     uint8_t *base;
-    uint8_t *collb;   // !BIG only
-    uint32_t stride;  // BIG: LB+1 ; !BIG: band width + 2
+    uint8_t *collb;   // !BIG only: column LB, one byte per row
+    uint8_t *rowla;   // !BIG only: row LA (last-row insert chain), one byte per cell (written by many lanes)
+    uint32_t stride;  // BIG: LB+1 bytes ; !BIG: cells per row (even), two cells per byte
     int K;            // !BIG: LA + 1 - dlo
     uint32_t LA, LB;
     __device__ __forceinline__ void put(uint32_t i, uint32_t j, uint8_t v) const {
@@ -526,17 +582,29 @@ struct TBStore {
                 if (i < LA) collb[i] = v;
                 return;
             }
-            uint32_t ie = (i == LA) ? LA - 1 : i;
-            int c = (int)j - (int)ie + K;
-            if (c >= 0 && c < (int)stride) base[(i * stride) + c] = v;
+            if (i == LA) {
+                int c = (int)j - (int)(LA - 1) + K;
+                if (c >= 0 && c < (int)stride) rowla[c] = v;
+                return;
+            }
+            int c = (int)j - (int)i + K;
+            if (c >= 0 && c < (int)stride) {   // a row is only ever written by its own lane: plain read-modify-write
+                uint8_t *b = base + i * (stride >> 1) + (c >> 1);
+                const uint32_t sh = (c & 1) * 4;
+                *b = (uint8_t)((*b & (0xF0u >> sh)) | ((v & 0xFu) << sh));
+            }
         }
     }
     __device__ __forceinline__ uint8_t get(uint32_t i, uint32_t j) const {
         if (BIG) return base[(size_t)i * stride + j];
         if (j == LB) return (i < LA) ? collb[i] : 0;
-        uint32_t ie = (i == LA) ? LA - 1 : i;
-        int c = (int)j - (int)ie + K;
-        return (c >= 0 && c < (int)stride) ? base[(i * stride) + c] : 0;
+        if (i == LA) {
+            int c = (int)j - (int)(LA - 1) + K;
+            return (c >= 0 && c < (int)stride) ? rowla[c] : 0;
+        }
+        int c = (int)j - (int)i + K;
+        if (c < 0 || c >= (int)stride) return 0;
+        return (base[i * (stride >> 1) + (c >> 1)] >> ((c & 1) * 4)) & 0xFu;
     }
 };
 
@@ -570,12 +638,14 @@ __device__ __noinline__ float viterbi_warp(const Env &E, const uint8_t *A, uint3
     if (BIG) {
         tb.base = E.ws->tb;
         tb.collb = nullptr;
+        tb.rowla = nullptr;
         tb.stride = LB + 1;
         tb.K = 0;
     } else {
         tb.base = E.s_tb;
         tb.stride = E.tb_stride;
-        tb.collb = E.s_tb + (size_t)E.tb_rows * E.tb_stride;
+        tb.collb = E.s_tb + (size_t)E.tb_rows * (E.tb_stride >> 1);
+        tb.rowla = tb.collb + E.tb_rows;
         tb.K = (int)LA + 1 - (int)dlo;
     }
     float *rowM = E.ws->rowM, *rowD = E.ws->rowD;
@@ -929,8 +999,9 @@ __device__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint3
     uint32_t n = 0, p0 = 0, p1 = 0;
     if (valid) row_head3(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), n, p0, p1);
     if (n > E.ix.max_ix) n = E.ix.max_ix;
-    const bool a0 = valid && n >= 1 && n <= 2 && prefilter_alive(E, m, QPos, p0, s == 0);
-    const bool a1 = valid && n == 2 && prefilter_alive(E, m, QPos, p1, s == 0);
+    const bool pf = (E.P.flags & 2u) != 0;
+    const bool a0 = valid && n >= 1 && n <= 2 && (!pf || prefilter_alive(E, m, QPos, p0, s == 0));
+    const bool a1 = valid && n == 2 && (!pf || prefilter_alive(E, m, QPos, p1, s == 0));
     uint32_t vmask = __ballot_sync(FULL, valid);
     const uint32_t m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1), big = __ballot_sync(FULL, n > 2);
     while (vmask) {
@@ -947,7 +1018,7 @@ __device__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint3
 __device__ void row_long_stage(const Env &E, Mate &m, int s, uint32_t QPos) {
     uint32_t mypos;
     const uint32_t RowLength = get_row(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
-    const bool a = ((uint32_t)E.lane < RowLength) && prefilter_alive(E, m, QPos, mypos, s == 0);
+    const bool a = ((uint32_t)E.lane < RowLength) && (!(E.P.flags & 2u) || prefilter_alive(E, m, QPos, mypos, s == 0));
     uint32_t am = __ballot_sync(FULL, a);
     while (am) {
         const int r = __ffs(am) - 1;
@@ -1465,9 +1536,9 @@ __device__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevPro
     build_alive_table(E, m);
 }
 
-__global__ void __launch_bounds__(128, 4) search_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
-                                                    WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
-                                                    uint32_t tb_rows) {
+__device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr,
+                                            const DevOut &o, WarpScratch *scratch, uint32_t smem_per_warp,
+                                            uint32_t tb_stride, uint32_t tb_rows) {
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + warp;
@@ -1519,6 +1590,14 @@ __global__ void __launch_bounds__(128, 4) search_kernel(DevIndex ix, DevParams P
     }
 }
 
+// Two register budgets of the same body: MINB = 4 blocks/SM (<=128 regs) or 3 blocks/SM (<=168 regs).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) search_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
+                                                       WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
+                                                       uint32_t tb_rows) {
+    search_body(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
+}
+
 // =====================================================================================
 // host-side launchers
 // =====================================================================================
@@ -1529,7 +1608,7 @@ size_t search_smem_per_warp(const DevBatch &b, const DevParams &P) {
     size_t s = (size_t)nm * 2 * b.qcap * 4 + (size_t)nm * b.seqcap * 2 + (size_t)nm * 2 * b.qcap + (size_t)nm * 64;
     s += b.seqcap + 64;
     const uint32_t rows = b.seqcap + 2;
-    s += (size_t)rows * tb_stride_for(P) + rows;
+    s += (size_t)rows * (tb_stride_for(P) / 2) + rows + tb_stride_for(P);   // nibble rows + column LB + row LA
     return (s + 15) & ~(size_t)15;
 }
 
@@ -1550,13 +1629,16 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     const int wpb = 4;
     const size_t spw = search_smem_per_warp(b, P);
     const size_t smem = spw * wpb;
+    const bool lowreg = !(P.flags & 8u);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(search_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel, wpb * 32, smem);
+    if (lowreg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<4>, wpb * 32, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<3>, wpb * 32, smem);
     if (per_sm < 1) per_sm = 1;
     int blocks = sm_count * per_sm;
     if (blocks * wpb > n_scratch_warps) blocks = n_scratch_warps / wpb;
@@ -1565,8 +1647,13 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     if (blocks < 1) blocks = 1;
     if (warps_used) *warps_used = blocks * wpb;
     const uint32_t rows = b.seqcap + 2;
-    URMB_LAUNCH(search_kernel, blocks, wpb * 32, smem, stream, ix, P, b, pr, o, scratch, (uint32_t)spw,
-                tb_stride_for(P), rows);
+    if (lowreg) {
+        URMB_LAUNCH(search_kernel<4>, blocks, wpb * 32, smem, stream, ix, P, b, pr, o, scratch, (uint32_t)spw,
+                    tb_stride_for(P), rows);
+    } else {
+        URMB_LAUNCH(search_kernel<3>, blocks, wpb * 32, smem, stream, ix, P, b, pr, o, scratch, (uint32_t)spw,
+                    tb_stride_for(P), rows);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -77,6 +77,9 @@ inline void __syncthreads() {}
 inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+inline int __ffsll(long long v) { return v ? __builtin_ctzll((unsigned long long)v) + 1 : 0; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double __dmul_rn(double a, double b) { return a * b; }
 using std::max;
 using std::min;

@@ -119,6 +119,7 @@ static DevParams emu_make_params(const urmb_params &p) {  // same table as urmb_
     P.pe_method = (p.pe_method == 5) ? 5 : 4;
     if (p.band_radius >= 0) P.R = (uint32_t)p.band_radius;
     else if (p.pe_method == 5) P.R = 4;
+    P.flags = 0;
     if (const char *f = getenv("URMB_FLAGS")) P.flags = (uint32_t)strtoul(f, nullptr, 0);
     return P;
 }
@@ -137,6 +138,12 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     ix.seq_size = seq_size;
     ix.word_len = word_len;
     ix.max_ix = max_ix;
+    const size_t nbytes = (size_t)seq_size + 4096, nwords = packed_words(nbytes);
+    std::vector<uint64_t> seq2(nwords);
+    std::vector<uint32_t> seqx(nwords);
+    launch_pack_genome(seq_padded, nbytes, seq2.data(), seqx.data(), nullptr);
+    ix.seq2 = seq2.data();
+    ix.seqx = seqx.data();
     DevParams P = emu_make_params(*p);
     const uint32_t nreads = paired ? 2 * n_units : n_units;
     uint32_t maxlen = 0;
@@ -153,19 +160,16 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     b.paired = paired;
     std::vector<uint8_t> tally((size_t)nreads * 2 * b.qcap);
     std::vector<uint32_t> pos((size_t)nreads * 2 * b.qcap);
-    std::vector<uint64_t> slot((size_t)nreads * 2 * b.qcap);
-    DevProbe pr{tally.data(), pos.data(), slot.data()};
+    std::vector<uint32_t> ext((size_t)nreads * 2 * b.qcap);
+    DevProbe pr{tally.data(), pos.data(), ext.data()};
     memset(counters, 0, 16);
     DevOut o{res, runs, runs_cap, counters};
     const int nw = 4;
     WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch) * nw);
     memset(ws, 0xEE, sizeof(WarpScratch) * nw);
-    launch_probe(ix, b, pr, nullptr, 1);
+    launch_probe(ix, P, b, pr, nullptr, 1);
     launch_search(ix, P, b, pr, o, ws, nw, nullptr, 1, nullptr);
     free(ws);
-    if (getenv("URMB_EMU_STATS"))
-        fprintf(stderr, "EMU stats: prefilter calls %llu alive %llu | extend_pen calls %llu reaching extend_core %llu\n", urmb::g_pf_calls,
-                urmb::g_pf_alive, urmb::g_ext_calls, urmb::g_ext_core);
     return 0;
 }
 

@@ -137,7 +137,7 @@ struct Slot {
     // device
     uint8_t *d_seqs = nullptr; size_t d_seqs_cap = 0;
     uint32_t *d_offs = nullptr; size_t d_offs_cap = 0;
-    uint8_t *d_tally = nullptr; uint32_t *d_pos = nullptr; uint64_t *d_slot = nullptr; size_t d_probe_cap = 0;
+    uint8_t *d_tally = nullptr; uint32_t *d_pos = nullptr; uint32_t *d_ext = nullptr; size_t d_probe_cap = 0;
     urmb_result *d_res = nullptr; size_t d_res_cap = 0;
     uint16_t *d_runs = nullptr; size_t d_runs_cap = 0;
     uint32_t *d_counters = nullptr;
@@ -154,6 +154,8 @@ struct urmb_ctx {
     DevIndex ix{};
     bool have_index = false;
     void *own_blob = nullptr, *own_seq = nullptr;
+    uint64_t *seq2 = nullptr;   // derived 2-bit packing of the genome + exception bits (built on the device)
+    uint32_t *seqx = nullptr;
     cudaStream_t compute = nullptr;
     WarpScratch *scratch = nullptr;
     int n_scratch_warps = 0;
@@ -182,7 +184,7 @@ static DevParams make_params(const urmb_params &p) {  // State1::SetMethod, stat
     P.pe_method = (p.pe_method == 5) ? 5 : 4;
     if (p.band_radius >= 0) P.R = (uint32_t)p.band_radius;
     else if (p.pe_method == 5) P.R = 4;   // map2.cpp:17-21
-    P.flags = 0x100;   // bit8: automatic (prefilters on for single-end, off for paired-end; measured)
+    P.flags = 0;       // bit3: 168-register variant of the search kernel (3 blocks/SM)
     if (const char *f = getenv("URMB_FLAGS")) P.flags = (uint32_t)strtoul(f, nullptr, 0);
     return P;
 }
@@ -230,7 +232,7 @@ static void free_slot(Slot &s) {
     if (s.copy) cudaStreamDestroy(s.copy);
     for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h}) if (ev) cudaEventDestroy(ev);
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
-    cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_slot);
+    cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext);
     cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters);
 }
 
@@ -243,6 +245,8 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     cudaFree(c->scratch);
     cudaFree(c->own_blob);
     cudaFree(c->own_seq);
+    cudaFree(c->seq2);
+    cudaFree(c->seqx);
     delete c;
 }
 
@@ -258,6 +262,21 @@ static int set_index(urmb_ctx *c, const urmb_index_desc *d) {
     c->ix.seq_size = d->seq_data_size;
     c->ix.word_len = d->word_length;
     c->ix.max_ix = d->max_ix;
+    // derived data: 2-bit packed genome + exception bits for the lane-local extension (not part of the UFI format)
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->seq2);
+    cudaFree(c->seqx);
+    c->seq2 = nullptr;
+    c->seqx = nullptr;
+    const size_t nbytes = (size_t)d->seq_data_size + URMB_SEQ_PAD, nwords = packed_words(nbytes);
+    CK(cudaMalloc(&c->seq2, nwords * 8));
+    CK(cudaMalloc(&c->seqx, nwords * 4));
+    int e = launch_pack_genome(c->ix.seq, nbytes, c->seq2, c->seqx, c->compute);
+    if (e) return fail(c, URMB_E_CUDA, std::string("pack launch: ") + cudaGetErrorString((cudaError_t)e));
+    CK(cudaStreamSynchronize(c->compute));
+    c->ix.seq2 = c->seq2;
+    c->ix.seqx = c->seqx;
+    c->launches += 1;
     c->have_index = true;
     return URMB_OK;
 }
@@ -439,13 +458,13 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     s.seq_bytes = nbytes;
     const size_t probe_need = (size_t)nreads * 2 * b.qcap;
     if (probe_need > s.d_probe_cap) {
-        cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_slot);
-        s.d_tally = nullptr; s.d_pos = nullptr; s.d_slot = nullptr;
+        cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext);
+        s.d_tally = nullptr; s.d_pos = nullptr; s.d_ext = nullptr;
         s.d_probe_cap = 0;
         size_t ncap = std::max(probe_need, (size_t)1024);
         CK(cudaMalloc(&s.d_tally, ncap));
         CK(cudaMalloc(&s.d_pos, ncap * 4));
-        CK(cudaMalloc(&s.d_slot, ncap * 8));
+        CK(cudaMalloc(&s.d_ext, ncap * 4));
         s.d_probe_cap = ncap;
     }
     if ((rc = grow_dev(c, s.d_res, s.d_res_cap, (size_t)nreads + 1))) return rc;
@@ -472,13 +491,12 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     CK(cudaMemsetAsync(s.d_counters, 0, 16, c->compute));
     CK(cudaEventRecord(s.ev_k0, c->compute));
     if (s.batch.n_reads) {
-        DevProbe pr{s.d_tally, s.d_pos, s.d_slot};
+        DevProbe pr{s.d_tally, s.d_pos, s.d_ext};
         DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters};
-        int e = launch_probe(c->ix, s.batch, pr, c->compute, c->sm_count);
+        DevParams P = c->P;
+        int e = launch_probe(c->ix, P, s.batch, pr, c->compute, c->sm_count);
         if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
         CK(cudaEventRecord(s.ev_k1, c->compute));
-        DevParams P = c->P;
-        if (P.flags & 0x100u) P.flags = s.batch.paired ? 0u : 3u;
         e = launch_search(c->ix, P, s.batch, pr, o, c->scratch, c->n_scratch_warps, c->compute, c->sm_count, nullptr);
         if (e) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)e));
         c->launches += 2;

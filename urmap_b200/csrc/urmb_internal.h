@@ -9,7 +9,6 @@ namespace urmb {
 constexpr int kHitCap = 256;    // hits kept per mate (reference grows without bound, state1.cpp:190)
 constexpr int kHspCap = 256;    // HSPs kept per mate
 constexpr int kRunCap = 64;     // RLE runs per stored path
-constexpr int kSeedCap = 512;   // BOTH1 seeds recorded per mate (2*QL, search2m4.cpp:39)
 constexpr int kMaxLen = URMB_MAX_READ_LEN;
 constexpr int kScanSeg = 1024;  // SCAN_DB_SEG_LENGTH, state2.cpp:91
 constexpr int kBigCols = kScanSeg + 2 * kMaxLen + 8;   // widest mate-rescue window (+1 column)
@@ -18,6 +17,8 @@ constexpr int kBigRows = kMaxLen + 1;
 struct DevIndex {
     const uint8_t *blob;   // 5 B/slot AoS exactly as in the UFI file (+URMB_BLOB_PAD)
     const uint8_t *seq;    // upper-case genome, 1 B/base (+URMB_SEQ_PAD zero bytes)
+    const uint64_t *seq2;  // derived: genome packed 2 bit/base, base g in word g>>5 at bits 63-2(g&31),62-2(g&31)
+    const uint32_t *seqx;  // derived: bit (g&31) of word g>>5 set when byte g is not one of "ACGT" (exact byte path)
     uint64_t slot_count;
     uint64_t magic;        // floor(2^64 / slot_count) for the Barrett reduction
     uint64_t shift_mask;   // 2^(2W)-1
@@ -43,10 +44,10 @@ struct DevBatch {
     int paired;
 };
 
-struct DevProbe {   // output of the probe kernel, [n_reads][2 strands][qcap]
+struct DevProbe {   // output of the probe+extend kernel, [n_reads][2 strands][qcap]
     uint8_t *tally;
     uint32_t *pos;
-    uint64_t *slot;
+    uint32_t *ext;     // BOTH1 slots: packed state-independent result of the gapless extension (EXT_NONE otherwise)
 };
 
 struct DevOut {
@@ -69,9 +70,6 @@ struct MateScratch {
     uint8_t hsp_flags[kHspCap];   // bit0 plus, bit1 aligned
     uint8_t pend[2][kMaxLen];     // m_QPosPendingVec_{Plus,Minus} (bytes, state1.h:86)
     uint8_t todo[2][kMaxLen];     // phase-5 todo lists (search1m6.cpp:170,205)
-    uint32_t seed_db[kSeedCap];
-    uint8_t seed_q[kSeedCap];
-    uint8_t seed_plus[kSeedCap];
 };
 
 struct WarpScratch {
@@ -92,9 +90,12 @@ struct LaunchCfg {
 
 // implemented in urmb_kernels.cu
 size_t search_smem_per_warp(const DevBatch &b, const DevParams &P);
-int launch_probe(const DevIndex &ix, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count);
+int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count);
 int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
                   WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used);
 int max_search_warps(int sm_count);
+// n_bytes = seq_data_size + URMB_SEQ_PAD; seq2 holds n_bytes/32+2 words, seqx n_bytes/32+2 words
+size_t packed_words(size_t n_bytes);
+int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint32_t *seqx, void *stream);
 
 }  // namespace urmb

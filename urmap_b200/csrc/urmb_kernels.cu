@@ -128,46 +128,300 @@ __device__ __forceinline__ void load_blob(const uint8_t *blob, uint64_t slot, ui
 }
 
 // =====================================================================================
-// probe kernel
+// genome packing (derived data, built once per index on the device)
 // =====================================================================================
-// One warp per read. Letters of both strands are staged in shared memory (1 B/base), then
-// lane = k-mer start: build the 2W-bit word, hash, reduce, gather.
-__global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevBatch b, DevProbe pr) {
+// One thread per 32 bases: 2-bit codes, first base in the most significant bits (so a k-mer is a funnel
+// shift of two words and "next mismatch to the right" is a count-leading-zeros), plus an exception bit
+// for every byte that is not exactly 'A','C','G','T' (N runs, IUPAC codes, the '-' contig padding, the zero
+// padding after the last contig).  Windows that touch an exception bit are compared byte by byte instead.
+__global__ void __launch_bounds__(256) pack_genome_kernel(const uint8_t *seq, size_t n_bytes, size_t n_words,
+                                                          uint64_t *seq2, uint32_t *seqx) {
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
+        uint64_t code = 0;
+        uint32_t exc = 0;
+        for (uint32_t t = 0; t < 32; ++t) {
+            const size_t g = w * 32 + t;
+            const uint32_t c = (g < n_bytes) ? seq[g] : 0u;
+            uint32_t l = 0;
+            if (c == 'A') l = 0;
+            else if (c == 'C') l = 1;
+            else if (c == 'G') l = 2;
+            else if (c == 'T') l = 3;
+            else exc |= 1u << t;
+            code |= (uint64_t)l << (62 - 2 * t);
+        }
+        seq2[w] = code;
+        seqx[w] = exc;
+    }
+}
+
+// =====================================================================================
+// read staging (shared by both kernels)
+// =====================================================================================
+// Per strand, in shared memory: the ASCII bytes (exact byte compare, DP), the 2-bit packing in the genome's
+// bit order (8 words + 1 pad for 256 bases), and one "letter is not ACGTU" bit per base (LSB first).
+constexpr int kPkWords = kMaxLen / 32 + 1;   // u64 words per strand
+constexpr int kBadWords = kMaxLen / 32 + 1;  // u32 words per strand
+struct ReadView {
+    const uint8_t *q, *rc;    // [seqcap] read bytes / RevCompSeq bytes (seqinfo.cpp:9)
+    const uint64_t *pk;       // [2][kPkWords]
+    const uint32_t *bad;      // [2][kBadWords]
+    uint32_t QL;
+    bool slow;                // some byte is not upper-case ACGT: every extension takes the byte path
+    bool hasbad;              // some letter is invalid for hashing (g_CharToLetterNucleo == 0xFF)
+};
+constexpr size_t kReadViewBytes = 2 * kPkWords * 8 + 2 * kBadWords * 4;   // + 2*seqcap bytes
+
+// Warp-cooperative. s_q/s_rc: seqcap bytes each; s_pk: 2*kPkWords u64; s_bad: 2*kBadWords u32.
+__device__ void stage_read(int lane, const uint8_t *src, uint32_t L, uint32_t seqcap, uint8_t *s_q, uint8_t *s_rc,
+                           uint64_t *s_pk, uint32_t *s_bad, ReadView &rv) {
+    bool notacgt = false;
+    for (uint32_t i = lane; i < seqcap; i += 32) {
+        if (i < L) {
+            const uint32_t c = src[i];
+            s_q[i] = (uint8_t)c;
+            s_rc[L - 1 - i] = (uint8_t)compchar_of(c);
+            notacgt |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+        }
+    }
+    for (int i = lane; i < 2 * kPkWords; i += 32) s_pk[i] = 0;
+    for (int i = lane; i < 2 * kBadWords; i += 32) s_bad[i] = 0;
+    __syncwarp();
+    // lane = group of 8 bases (kMaxLen / 8 == 32 groups)
+    uint32_t anybad = 0;
+    for (int s = 0; s < 2; ++s) {
+        const uint8_t *bytes = s ? s_rc : s_q;
+        const uint32_t g = (uint32_t)lane;
+        uint32_t code = 0, bad = 0;
+        for (uint32_t t = 0; t < 8; ++t) {
+            const uint32_t i = 8 * g + t;
+            uint32_t l = (i < L) ? letter_of(bytes[i]) : 0u;
+            if (l & 0x80u) { bad |= 1u << t; l = 0; }
+            code |= (l & 3u) << (14 - 2 * t);
+        }
+        if (8 * g < L) {
+            reinterpret_cast<uint16_t *>(s_pk + s * kPkWords)[4 * (g >> 2) + (3 - (g & 3))] = (uint16_t)code;
+            reinterpret_cast<uint8_t *>(s_bad + s * kBadWords)[g] = (uint8_t)bad;
+        }
+        anybad |= bad;
+    }
+    rv.q = s_q;
+    rv.rc = s_rc;
+    rv.pk = s_pk;
+    rv.bad = s_bad;
+    rv.QL = L;
+    rv.hasbad = __any_sync(FULL, anybad != 0);
+    rv.slow = __any_sync(FULL, notacgt);
+    __syncwarp();
+}
+
+// Slot of the k-mer starting at q on strand s (State1::SetSlotsVec, state1.cpp:396-438): ~0 when a letter is invalid.
+__device__ __forceinline__ uint64_t slot_of(const DevIndex &ix, const ReadView &rv, int s, uint32_t q) {
+    const uint32_t W = ix.word_len;
+    if (rv.hasbad) {
+        const uint32_t *bw = rv.bad + s * kBadWords + (q >> 5);
+        const uint64_t win = (((uint64_t)bw[1] << 32) | bw[0]) >> (q & 31);
+        if (win & ((W >= 32) ? 0xFFFFFFFFull : ((1ull << W) - 1))) return ~0ull;
+    }
+    const uint64_t *pw = rv.pk + s * kPkWords + (q >> 5);
+    const uint32_t off = 2 * (q & 31);
+    const uint64_t hi = off ? ((pw[0] << off) | (pw[1] >> (64 - off))) : pw[0];
+    const uint64_t word = hi >> (64 - 2 * W);
+    return mod_slots(murmur64(word & ix.shift_mask), ix.slot_count, ix.magic);
+}
+
+// =====================================================================================
+// state-independent gapless extension
+// =====================================================================================
+// ExtendPen (extendpen.cpp:9-95) and ExtendScan (extendscan.cpp:51-187) walk right then left from the seed and
+// consult the search state in exactly one place: "Pen > m_MaxPenalty -> return -1".  Pen only grows (by
+// -MISMATCH per visited mismatch), so the bounded walk fails iff the unbounded walk's final penalty exceeds the
+// bound.  The unbounded walk is a pure function of (read strand, seed, genome window): ONE LANE computes it for
+// one candidate -- 32 candidates per warp in flight -- and the order-dependent part of the reference (overlap
+// test, penalty bound, hit / HSP bookkeeping) is replayed afterwards from the packed result in O(1).
+//   packed: Best[0:9] Start[9:17] End[17:25] visited-mismatches[25:32] (saturating; 127 * 3 > any bound)
+constexpr uint32_t EXT_NONE = 0xFFFFFFFFu;   // ExtendPen returns -1 without looking at the genome (or not a candidate)
+__device__ __forceinline__ uint32_t ext_pack(int Best, int Start, int End, int nmis) {
+    return (uint32_t)Best | ((uint32_t)Start << 9) | ((uint32_t)End << 17) | ((uint32_t)min(nmis, 127) << 25);
+}
+__device__ __forceinline__ int ext_best(uint32_t x) { return (int)(x & 511u); }
+__device__ __forceinline__ int ext_start(uint32_t x) { return (int)((x >> 9) & 255u); }
+__device__ __forceinline__ int ext_end(uint32_t x) { return (int)((x >> 17) & 255u); }
+__device__ __forceinline__ int ext_nmis(uint32_t x) { return (int)(x >> 25); }
+
+// Exact byte-by-byte walk (reads with lower-case / IUPAC letters, windows touching N, '-' or the end padding).
+__device__ __noinline__ uint32_t pure_ext_bytes(const uint8_t *Qs, const uint8_t *T, int QL, int W, int MM, int XD,
+                                                uint32_t SeedPosQ, bool LeftCountsPen) {
+    int Score = W, Best = 0, nmis = 0;
+    int End = (int)SeedPosQ + W - 1;
+    for (int p = End + 1; p < QL; ++p) {
+        if ((uint32_t)Qs[p] == ldg_stream_u8(T + p)) {
+            if (++Score > Best) { Best = Score; End = p; }
+        } else {
+            ++nmis;
+            Score += MM;
+            if (Best - Score > XD) break;
+        }
+    }
+    int Start = (int)SeedPosQ;
+    for (int p = Start - 1; p >= 0; --p) {
+        if ((uint32_t)Qs[p] == ldg_stream_u8(T + p)) {
+            if (++Score > Best) { Best = Score; Start = p; }
+        } else {
+            if (LeftCountsPen) ++nmis;
+            Score += MM;
+            if (Best - Score > XD) break;
+        }
+    }
+    return ext_pack(Best, Start, End, nmis);
+}
+
+// Lane-local. Plus selects the read strand; the candidate is (SeedPosQ, SeedPosDB) on diagonal DBLo.
+__device__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus, uint32_t SeedPosQ,
+                             uint32_t SeedPosDB, bool LeftCountsPen) {
+    if (SeedPosDB < SeedPosQ) return EXT_NONE;   // extendpen.cpp:11
+    const uint32_t DBLo = SeedPosDB - SeedPosQ;
+    const int QL = (int)rv.QL, W = (int)ix.word_len, MM = P.MM, XD = P.XDROP;
+    const int nw = (QL + 31) >> 5;   // <= 8
+    uint64_t mm[8];
+    bool slow = rv.slow;
+    if (!slow) {
+        const uint64_t *g = ix.seq2 + (DBLo >> 5);
+        const uint32_t *x = ix.seqx + (DBLo >> 5);
+        const uint32_t sh = 2 * (DBLo & 31);
+        const uint64_t *rp = rv.pk + (Plus ? 0 : kPkWords);
+        uint64_t gw[9];
+        uint32_t exc = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            gw[k] = 0;
+            if (k <= nw) {
+                gw[k] = __ldg(g + k);
+                exc |= __ldg(x + k);
+            }
+        }
+        if (exc) slow = true;
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                mm[k] = 0;
+                if (k < nw) {
+                    const uint64_t a = sh ? ((gw[k] << sh) | (gw[k + 1] >> (64 - sh))) : gw[k];
+                    uint64_t d = a ^ rp[k];
+                    d = (d | (d >> 1)) & 0x5555555555555555ull;
+                    if (k == nw - 1 && (QL & 31)) d &= ~0ull << (64 - 2 * (QL & 31));
+                    mm[k] = d;
+                }
+            }
+        }
+    }
+    if (slow) return pure_ext_bytes(Plus ? rv.q : rv.rc, ix.seq + DBLo, QL, W, MM, XD, SeedPosQ, LeftCountsPen);
+
+    int Score = W, Best = 0, nmis = 0;
+    int End = (int)SeedPosQ + W - 1;
+    {   // right walk, extendpen.cpp:29-52: mismatches in increasing position = decreasing bit index
+        int p = End + 1;
+        bool stop = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < nw && !stop && (k << 5) + 32 > p) {
+                uint64_t w = mm[k];
+                const int b0 = p - (k << 5);
+                if (b0 > 0) w &= ~0ull >> (2 * b0);
+                while (w) {
+                    const int hb = 63 - __clzll((long long)w);
+                    w &= ~(1ull << hb);
+                    const int pos = (k << 5) + ((62 - hb) >> 1);
+                    const int run = pos - p;
+                    if (run > 0) {
+                        Score += run;
+                        if (Score > Best) { Best = Score; End = pos - 1; }
+                    }
+                    ++nmis;
+                    Score += MM;
+                    p = pos + 1;
+                    if (Best - Score > XD) { stop = true; break; }
+                }
+            }
+        }
+        if (!stop) {
+            const int run = QL - p;
+            if (run > 0) {
+                Score += run;
+                if (Score > Best) { Best = Score; End = QL - 1; }
+            }
+        }
+    }
+    int Start = (int)SeedPosQ;
+    {   // left walk, extendpen.cpp:55-78
+        int p = Start - 1;
+        bool stop = false;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            if (k < nw && !stop && p >= 0 && (k << 5) <= p) {
+                uint64_t w = mm[k];
+                const int b1 = p - (k << 5);
+                if (b1 < 31) w &= ~0ull << (62 - 2 * b1);
+                while (w) {
+                    const int lb = __ffsll((long long)w) - 1;
+                    w &= w - 1;
+                    const int pos = (k << 5) + ((62 - lb) >> 1);
+                    const int run = p - pos;
+                    if (run > 0) {
+                        Score += run;
+                        if (Score > Best) { Best = Score; Start = pos + 1; }
+                    }
+                    if (LeftCountsPen) ++nmis;
+                    Score += MM;
+                    p = pos - 1;
+                    if (Best - Score > XD) { stop = true; break; }
+                }
+            }
+        }
+        if (!stop) {
+            const int run = p + 1;
+            if (run > 0) {
+                Score += run;
+                if (Score > Best) { Best = Score; Start = 0; }
+            }
+        }
+    }
+    return ext_pack(Best, Start, End, nmis);
+}
+
+// =====================================================================================
+// probe + extend kernel
+// =====================================================================================
+// One warp per read, lane = k-mer start: hash (SetSlotsVec), gather the 5-byte slot record from the HBM-resident
+// table (GetBlob), and for BOTH1 slots gather the candidate's genome window and run the pure extension above.
+// Every lane's chain is slot sector -> genome sectors; thousands of chains per SM are in flight: HBM-gather bound.
+__global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr) {
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    uint8_t *sl = smem + (size_t)warp * 2 * b.seqcap;  // [2][seqcap] letters fwd / rc
+    uint8_t *sw = smem + (size_t)warp * (2 * b.seqcap + kReadViewBytes);
+    uint64_t *s_pk = reinterpret_cast<uint64_t *>(sw);
+    uint32_t *s_bad = reinterpret_cast<uint32_t *>(sw + 2 * kPkWords * 8);
+    uint8_t *s_q = sw + kReadViewBytes, *s_rc = s_q + b.seqcap;
     const uint32_t W = ix.word_len;
     for (uint32_t r = blockIdx.x * wpb + warp; r < b.n_reads; r += gridDim.x * wpb) {
         const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
-        for (uint32_t i = lane; i < L; i += 32) {
-            uint32_t c = b.seqs[off + i];
-            sl[i] = (uint8_t)letter_of(c);
-            sl[b.seqcap + (L - 1 - i)] = (uint8_t)letter_of(compchar_of(c));
-        }
-        __syncwarp();
+        ReadView rv;
+        stage_read(lane, b.seqs + off, L, b.seqcap, s_q, s_rc, s_pk, s_bad, rv);
         const uint32_t QWC = (L >= W) ? L - W + 1 : 0;
         const size_t base = (size_t)r * 2 * b.qcap;
         for (uint32_t s = 0; s < 2; ++s) {
-            const uint8_t *let = sl + s * b.seqcap;
             for (uint32_t q = lane; q < b.qcap; q += 32) {
-                uint32_t tally = T_FREE, pos = POS_INVALID_WORD;
-                uint64_t slot = ~0ull;
+                uint32_t tally = T_FREE, pos = POS_INVALID_WORD, ext = EXT_NONE;
                 if (q < QWC) {
-                    uint64_t word = 0;
-                    uint32_t bad = 0;
-                    for (uint32_t t = 0; t < W; ++t) {
-                        uint32_t l = let[q + t];
-                        bad |= l & 0x80u;
-                        word = (word << 2) | (l & 3u);
-                    }
-                    if (!bad) {
-                        slot = mod_slots(murmur64(word & ix.shift_mask), ix.slot_count, ix.magic);
+                    const uint64_t slot = slot_of(ix, rv, (int)s, q);
+                    if (slot != ~0ull) {
                         load_blob<false>(ix.blob, slot, tally, pos);
+                        if (tally == T_BOTH1) ext = pure_ext(ix, P, rv, s == 0, q, pos, true);
                     }
                 }
                 pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
                 pr.pos[base + s * b.qcap + q] = pos;
-                pr.slot[base + s * b.qcap + q] = slot;
+                pr.ext[base + s * b.qcap + q] = ext;
             }
         }
         __syncwarp();
@@ -189,12 +443,19 @@ struct Env {
 };
 
 struct Mate {
-    const uint8_t *q;       // shared: read bytes
-    const uint8_t *rc;      // shared: reverse complement bytes
-    const uint8_t *tally;   // shared: [2][qcap]
-    const uint32_t *pos;    // shared: [2][qcap]
-    const uint64_t *slots;  // global: [2][qcap]
-    uint32_t *alive;        // shared: [2][8] bit q set = the BOTH1 candidate at (strand, q) survives the prefilter
+    ReadView rv;            // shared: bytes, packed strands, invalid-letter bits
+    const uint8_t *q;       // = rv.q
+    const uint8_t *rc;      // = rv.rc
+    const uint8_t *tally;   // global (probe output): [2][qcap]
+    const uint32_t *pos;    // global: [2][qcap]
+    const uint32_t *ext;    // global: [2][qcap]
+    // ordered BOTH1 candidate list of the current search (shared, 2*qcap entries): the seed sequence of
+    // GetFirst/NextBoth1Seed (PE) or the phase-1 + phase-2 visit order of Search_Lo (SE)
+    uint32_t *sd_db;        // DBPos
+    uint32_t *sd_ext;       // packed pure extension on the seed's own strand
+    uint16_t *sd_qs;        // QPos | strand << 15 (strand 0 = plus)
+    uint32_t *sd_dead;      // bit i: ExtendPen(seed i, own strand) is known to return <= 0 without side effects
+    int nSeeds;
     MateScratch *g;
     uint32_t QL, QWC, qcap;
     int HitCount, HSPCount, Top, MaxPenalty, Best, Second, BestHSP;
@@ -321,237 +582,91 @@ __device__ int add_hsp_scan(const Env &E, Mate &m, uint32_t qs, uint32_t dbs, bo
     return k;
 }
 
-// ---- gapless x-drop extension ----------------------------------------------------------
-struct ExtOut {
-    int Best, Start, End;
-    bool fail;
-};
-
-// Mismatch bitmask: lane k keeps the word for read positions [32k, 32k+32).
-__device__ __forceinline__ uint32_t mm_word(uint32_t mymask, int k) { return __shfl_sync(FULL, mymask, k); }
-
-__device__ __forceinline__ int mm_next(uint32_t mymask, int p, int nw, int QL) {  // first mismatch >= p, or QL
-    int k = p >> 5;
-    uint32_t w = mm_word(mymask, k) & (0xFFFFFFFFu << (p & 31));
-    while (w == 0 && ++k < nw) w = mm_word(mymask, k);
-    return w ? (k << 5) + __ffs(w) - 1 : QL;
-}
-__device__ __forceinline__ int mm_prev(uint32_t mymask, int p) {  // last mismatch <= p, or -1
-    int k = p >> 5;
-    uint32_t w = mm_word(mymask, k) & (0xFFFFFFFFu >> (31 - (p & 31)));
-    while (w == 0 && --k >= 0) w = mm_word(mymask, k);
-    return w ? (k << 5) + 31 - __clz(w) : -1;
-}
-
-// Common body of ExtendPen (extendpen.cpp:21-79) and ExtendScan (extendscan.cpp:64-133).
-__device__ ExtOut extend_core(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t DBLo, bool Plus,
-                              bool LeftCountsPen) {
-    const uint8_t *Qs = mate_seq(m, Plus);
-    const uint8_t *T = E.ix.seq + DBLo;
-    const int QL = (int)m.QL, nw = (QL + 31) >> 5, W = (int)E.ix.word_len;
-    uint32_t mymask = 0;
-    for (int k = 0; k < nw; ++k) {
-        int idx = (k << 5) + E.lane;
-        bool mis = (idx < QL) && ((uint32_t)Qs[idx] != ldg_stream_u8(T + idx));
-        uint32_t w = __ballot_sync(FULL, mis);
-        if (E.lane == k) mymask = w;
-    }
-    const int MM = E.P.MM, XD = E.P.XDROP, MaxPen = m.MaxPenalty;
-    ExtOut o;
-    o.fail = false;
-    int Pen = 0, Score = W, Best = 0;
-    int End = (int)SeedPosQ + W - 1;
-    int p = End + 1;
-    while (p < QL) {
-        int n = mm_next(mymask, p, nw, QL);
-        int run = n - p;
-        if (run > 0) {
-            Score += run;
-            if (Score > Best) { Best = Score; End = n - 1; }
-        }
-        if (n >= QL) break;
-        Pen -= MM;
-        if (Pen > MaxPen) { o.fail = true; break; }
-        Score += MM;
-        if (Best - Score > XD) break;
-        p = n + 1;
-    }
-    int Start = (int)SeedPosQ;
-    if (!o.fail) {
-        p = Start - 1;
-        while (p >= 0) {
-            int n = mm_prev(mymask, p);
-            int run = p - n;
-            if (run > 0) {
-                Score += run;
-                if (Score > Best) { Best = Score; Start = n + 1; }
-            }
-            if (n < 0) break;
-            if (LeftCountsPen) Pen -= MM;
-            if (Pen > MaxPen) { o.fail = true; break; }
-            Score += MM;
-            if (Best - Score > XD) break;
-            p = n - 1;
-        }
-    }
-    o.Best = Best;
-    o.Start = Start;
-    o.End = End;
-    return o;
-}
-
-
-// ---- state-independent candidate prefilter ---------------------------------------------------
-// ExtendPen returns -1 WITHOUT touching any state whenever the unconstrained gapless extension (no penalty
-// bound) is neither full-length nor reaches MIN_HSP_SCORE: the penalty bound and the hit-overlap test can only
-// turn more calls into -1 (extendpen.cpp:11-17,45,71).  About 90 % of all candidates are hash-collision
-// artefacts of the key-less table that die within a few bases of the seed, so each LANE tests one candidate
-// against <= 16 bases per side; only candidates that are still alive go through the exact warp-wide path, in
-// the reference's order.  32 independent genome gathers are in flight per warp instead of one.
-__device__ __forceinline__ uint64_t load8_global(const uint8_t *p) {  // 8 bytes at an arbitrary address (padded buffer)
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-    uint32_t w0 = ldg_stream_u32(w), w1 = ldg_stream_u32(w + 1), w2 = ldg_stream_u32(w + 2);
-    uint64_t lo = ((uint64_t)w1 << 32) | w0;
-    return sh ? ((lo >> sh) | ((uint64_t)w2 << (64 - sh))) : lo;
-}
-__device__ __forceinline__ uint64_t load8_shared(const uint8_t *p) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-    uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    uint64_t lo = ((uint64_t)w1 << 32) | w0;
-    return sh ? ((lo >> sh) | ((uint64_t)w2 << (64 - sh))) : lo;
-}
-
-constexpr int kPrefilterWin = 16;  // bases examined on each side of the seed
-
-// Lane-local. true = must take the exact path; false = ExtendPen would certainly return -1 with no side effect.
-#ifdef URMB_EMU
-static unsigned long long g_pf_calls = 0, g_pf_alive = 0, g_ext_calls = 0, g_ext_core = 0;
-#define EMU_COUNT(x) (++(x))
-#else
-#define EMU_COUNT(x)
-#endif
-__device__ bool prefilter_alive_impl(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus);
-__device__ bool prefilter_alive(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
-    const bool a = prefilter_alive_impl(E, m, SeedPosQ, SeedPosDB, Plus);
-    EMU_COUNT(g_pf_calls);
-    if (a) EMU_COUNT(g_pf_alive);
-    return a;
-}
-__device__ bool prefilter_alive_impl(const Env &E, const Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
-    if (SeedPosDB < SeedPosQ) return false;  // extendpen.cpp:11
+// ---- order-dependent half of ExtendPen ---------------------------------------------------
+// extendpen.cpp:11-17,45,71,80-94 replayed from the packed pure result. +score: full-length hit; -2: HSP saved;
+// -1 otherwise.  *stored = the hit went into the hit list (then every later call on this diagonal bucket is -1).
+__device__ __noinline__ int extend_apply(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus,
+                                         uint32_t x, bool &stored) {
+    stored = false;
+    if (x == EXT_NONE) return -1;
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
-    const uint8_t *Qs = mate_seq(m, Plus);
-    const uint8_t *T = E.ix.seq + DBLo;
-    const int QL = (int)m.QL, W = (int)E.ix.word_len, MM = E.P.MM, XD = E.P.XDROP;
-    int Score = W, Best = 0;
-    int End = (int)SeedPosQ + W - 1, Start = (int)SeedPosQ;
-    // all four 8-byte genome chunks (2 per side) are requested before any is consumed: one memory round trip
-    const int pr0 = End + 1, pl0 = Start - 1;
-    const int llo1 = max(0, pl0 - 7), llo2 = max(0, pl0 - 15);
-    uint64_t xr[2], xl[2];
-    {
-        uint64_t tr0 = load8_global(T + pr0), tr1 = load8_global(T + pr0 + 8);
-        uint64_t tl0 = load8_global(T + llo1), tl1 = load8_global(T + llo2);
-        xr[0] = load8_shared(Qs + pr0) ^ tr0;
-        xr[1] = load8_shared(Qs + pr0 + 8) ^ tr1;
-        xl[0] = load8_shared(Qs + llo1) ^ tl0;
-        xl[1] = load8_shared(Qs + llo2) ^ tl1;
+    if (overlaps_hit(E, m, DBLo)) return -1;
+    if (ext_nmis(x) * -E.P.MM > m.MaxPenalty) return -1;
+    const int Best = ext_best(x), Start = ext_start(x), End = ext_end(x);
+    if (Start == 0 && End == (int)m.QL - 1) {
+        stored = add_hit(E, m, DBLo, Plus, Best, nullptr, 0) >= 0;
+        return Best;
     }
-    {   // right scan, extendpen.cpp:29-52 without the penalty bound
-        int p = pr0;
-        const int lim = min(QL, p + kPrefilterWin);
-        bool term = false;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const uint64_t x = xr[c];
-            const int n = min(8, lim - p);
-            for (int j = 0; j < n && !term; ++j, ++p) {
-                if (((x >> (8 * j)) & 0xFFu) == 0) {
-                    ++Score;
-                    if (Score > Best) { Best = Score; End = p; }
-                } else {
-                    Score += MM;
-                    if (Best - Score > XD) term = true;
-                }
-            }
-        }
-        if (!term && p < QL) return true;
+    const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * (int)m.QL) / 100.0);
+    if (Best >= MinHSPScore) {
+        add_hsp(E, m, (uint32_t)Start, DBLo + (uint32_t)Start, Plus, (uint32_t)(End - Start + 1), Best);
+        return -2;
     }
-    {   // left scan, extendpen.cpp:55-78
-        int p = pl0;
-        bool term = false;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int lo = (c == 0) ? llo1 : llo2;
-            const int hi = (c == 0) ? pl0 : pl0 - 8;     // highest position of this chunk
-            const uint64_t x = xl[c];
-            for (int q = hi; q >= lo && q >= 0 && !term; --q, --p) {
-                if (((x >> (8 * (q - lo))) & 0xFFu) == 0) {
-                    ++Score;
-                    if (Score > Best) { Best = Score; Start = q; }
-                } else {
-                    Score += MM;
-                    if (Best - Score > XD) term = true;
-                }
-            }
-        }
-        if (!term && p >= 0) return true;
-    }
-    if (Start == 0 && End == QL - 1) return true;
-    const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * QL) / 100.0);
-    return Best >= MinHSPScore;
+    return -1;
 }
 
-// Prefilter every BOTH1 candidate of a mate (both strands) in parallel and publish the survivors as bitmasks.
-__device__ void build_alive_table(const Env &E, Mate &m) {
-    if (!(E.P.flags & 1u)) {   // switch off: every candidate takes the exact path
-        for (uint32_t r = E.lane; r < 16; r += 32) m.alive[r] = 0xFFFFFFFFu;
-        __syncwarp();
-        return;
-    }
-    for (int s = 0; s < 2; ++s) {
-        for (uint32_t q0 = 0; q0 < 256; q0 += 32) {
-            const uint32_t q = q0 + E.lane;
-            bool a = false;
-            if (q < m.QWC && m.tally[s * m.qcap + q] == T_BOTH1) a = prefilter_alive(E, m, q, m.pos[s * m.qcap + q], s == 0);
-            const uint32_t w = __ballot_sync(FULL, a);
-            if (E.lane == 0) m.alive[s * 8 + (q0 >> 5)] = w;
-            if (q0 + 32 >= m.QWC) {
-                for (uint32_t r = (q0 >> 5) + 1 + E.lane; r < 8; r += 32) m.alive[s * 8 + r] = 0;
-                break;
-            }
-        }
+// A call that can only return -1 and change nothing, judged from the pure result and a penalty bound that is
+// >= the bound at the time of the call (m_MaxPenalty never grows while BOTH1 seeds / rows are being extended).
+__device__ __forceinline__ bool ext_is_noop(const Env &E, uint32_t x, int QL, int MaxPenalty) {
+    if (x == EXT_NONE) return true;
+    if (ext_nmis(x) * -E.P.MM > MaxPenalty) return true;
+    if (ext_start(x) == 0 && ext_end(x) == QL - 1) return false;
+    const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * QL) / 100.0);
+    return ext_best(x) < MinHSPScore;
+}
+
+// ExtendPen for a candidate that is not in a seed list (uniform arguments): every lane computes the same pure result.
+__device__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
+    const uint32_t x = pure_ext(E.ix, E.P, m.rv, Plus, SeedPosQ, SeedPosDB, true);
+    bool stored;
+    return extend_apply(E, m, SeedPosQ, SeedPosDB, Plus, x, stored);
+}
+
+// ---- seed lists ----------------------------------------------------------------------------
+__device__ __forceinline__ bool seed_dead(const Mate &m, int i) { return (m.sd_dead[i >> 5] >> (i & 31)) & 1u; }
+
+// After seed appends: mark the seeds whose extension is a no-op from the start.
+__device__ void seeds_init_dead(const Env &E, Mate &m) {
+    __syncwarp();
+    for (int base = 0; base < m.nSeeds; base += 32) {
+        const int i = base + E.lane;
+        const bool d = (i >= m.nSeeds) || ext_is_noop(E, m.sd_ext[i], (int)m.QL, m.MaxPenalty);
+        const uint32_t w = __ballot_sync(FULL, d);
+        if (E.lane == 0) m.sd_dead[base >> 5] = w;
     }
     __syncwarp();
 }
 
-// State1::ExtendPen, extendpen.cpp:9-95. +score: full-length hit; -2: HSP saved; -1 otherwise.
-__device__ __noinline__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
-    if (E.lane == 0) EMU_COUNT(g_ext_calls);
-    if (SeedPosDB < SeedPosQ) return -1;
-    {   // BOTH1 candidate on its own strand that the prefilter proved dead: -1 with no side effect
-        const uint32_t si = Plus ? 0u : 1u;
-        if (SeedPosQ < m.QWC && m.tally[si * m.qcap + SeedPosQ] == T_BOTH1 && m.pos[si * m.qcap + SeedPosQ] == SeedPosDB &&
-            !((m.alive[si * 8 + (SeedPosQ >> 5)] >> (SeedPosQ & 31)) & 1u))
-            return -1;
+// A hit was stored at HitDBLo (and m_MaxPenalty possibly lowered): every seed in the same 64-base bucket now fails
+// OverlapsHit (state1.cpp:230, strand ignored), every seed over the new penalty bound fails the bound.
+__device__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo) {
+    const uint32_t key = HitDBLo >> 6;
+    for (int base = 0; base < m.nSeeds; base += 32) {
+        const int i = base + E.lane;
+        bool d = false;
+        if (i < m.nSeeds) {
+            const uint32_t x = m.sd_ext[i];
+            d = (((m.sd_db[i] - (m.sd_qs[i] & 0x7FFFu)) >> 6) == key) || (ext_nmis(x) * -E.P.MM > m.MaxPenalty);
+        }
+        const uint32_t w = __ballot_sync(FULL, d);
+        if (E.lane == 0 && w) m.sd_dead[base >> 5] |= w;
     }
-    const uint32_t DBLo = SeedPosDB - SeedPosQ;
-    if (overlaps_hit(E, m, DBLo)) return -1;
-    if (E.lane == 0) EMU_COUNT(g_ext_core);
-    ExtOut o = extend_core(E, m, SeedPosQ, DBLo, Plus, true);
-    if (o.fail) return -1;
-    const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * (int)m.QL) / 100.0);
-    if (o.Start == 0 && o.End == (int)m.QL - 1) {
-        add_hit(E, m, DBLo, Plus, o.Best, nullptr, 0);
-        return o.Best;
+    __syncwarp();
+}
+
+// ExtendPen(seed i) on the seed's own strand, through the memo.
+__device__ int apply_seed(const Env &E, Mate &m, int i) {
+    if (seed_dead(m, i)) return -1;
+    const uint32_t qs = m.sd_qs[i], db = m.sd_db[i];
+    bool stored;
+    const int r = extend_apply(E, m, qs & 0x7FFFu, db, (qs >> 15) == 0, m.sd_ext[i], stored);
+    __syncwarp();
+    if (stored) seeds_kill(E, m, db - (qs & 0x7FFFu));
+    else if (r <= 0) {
+        if (E.lane == 0) m.sd_dead[i >> 5] |= 1u << (i & 31);
+        __syncwarp();
     }
-    if (o.Best >= MinHSPScore) {
-        add_hsp(E, m, (uint32_t)o.Start, DBLo + (uint32_t)o.Start, Plus, (uint32_t)(o.End - o.Start + 1), o.Best);
-        return -2;
-    }
-    return -1;
+    return r;
 }
 
 // ---- banded Viterbi --------------------------------------------------------------------
@@ -891,16 +1006,17 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
     return add_hit(E, m, CombinedTLo, Plus, TotalScore, path, np);
 }
 
-// State1::ExtendScan, extendscan.cpp:51-187 (returns hit index or -1)
+// State1::ExtendScan, extendscan.cpp:51-187 (returns hit index or -1). Uniform arguments.
 __device__ __noinline__ int extend_scan(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
     if (SeedPosDB < SeedPosQ) return -1;
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
-    ExtOut o = extend_core(E, m, SeedPosQ, DBLo, Plus, false);
-    if (o.fail) return -1;
+    const uint32_t x = pure_ext(E.ix, E.P, m.rv, Plus, SeedPosQ, SeedPosDB, false);   // left walk adds no penalty (quirk 5)
+    if (ext_nmis(x) * -E.P.MM > m.MaxPenalty) return -1;
+    const int Best = ext_best(x), Start = ext_start(x), End = ext_end(x);
     const int MinHSPScore = (int)E.ix.word_len * 2;
-    if (o.Start == 0 && o.End == (int)m.QL - 1) return add_hit(E, m, DBLo, Plus, o.Best, nullptr, 0);
-    if (o.Best < MinHSPScore) return -1;
-    int k = add_hsp_scan(E, m, (uint32_t)o.Start, DBLo + (uint32_t)o.Start, Plus, (uint32_t)(o.End - o.Start + 1), o.Best);
+    if (Start == 0 && End == (int)m.QL - 1) return add_hit(E, m, DBLo, Plus, Best, nullptr, 0);
+    if (Best < MinHSPScore) return -1;
+    int k = add_hsp_scan(E, m, (uint32_t)Start, DBLo + (uint32_t)Start, Plus, (uint32_t)(End - Start + 1), Best);
     if (k < 0) return -1;
     return align_hsp(E, m, k);
 }
@@ -954,11 +1070,12 @@ __device__ __noinline__ uint32_t get_row(const Env &E, uint64_t Slot, uint32_t T
 }
 
 __device__ __forceinline__ uint32_t m_tally(const Mate &m, int strand /*0 plus,1 minus*/, uint32_t q) {
-    return m.tally[strand * m.qcap + q];
+    return __ldg(m.tally + strand * m.qcap + q);
 }
-__device__ __forceinline__ uint32_t m_pos(const Mate &m, int strand, uint32_t q) { return m.pos[strand * m.qcap + q]; }
-__device__ __forceinline__ uint64_t m_slot(const Mate &m, int strand, uint32_t q) {
-    return __ldg(m.slots + strand * m.qcap + q);
+__device__ __forceinline__ uint32_t m_pos(const Mate &m, int strand, uint32_t q) { return __ldg(m.pos + strand * m.qcap + q); }
+__device__ __forceinline__ uint32_t m_ext(const Mate &m, int strand, uint32_t q) { return __ldg(m.ext + strand * m.qcap + q); }
+__device__ __forceinline__ uint64_t m_slot(const Env &E, const Mate &m, int strand, uint32_t q) {
+    return slot_of(E.ix, m.rv, strand, q);
 }
 
 // Lane-local GetRow_Blob (ufindex.cpp:883-943) limited to what the "rows <= 2 now, longer rows later" logic
@@ -991,39 +1108,45 @@ __device__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tally, uint32_t 
     }
 }
 
-// One item (QPos) per lane: walk the heads of 32 rows and prefilter their candidates in parallel, then visit the
-// items in lane order exactly like the reference's loop body (search1m6.cpp:181-199, search1pepend.cpp:53-68):
-// rows longer than 2 are deferred through `defer` (returns how many were deferred), the others are extended now.
+// One item (QPos) per lane: walk the heads of 32 rows and run the pure extension of their candidates in parallel,
+// then visit the items in lane order exactly like the reference's loop body (search1m6.cpp:181-199,
+// search1pepend.cpp:53-68): rows longer than 2 are deferred through `defer`, the others are extended now.
 template <class Defer>
 __device__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint32_t QPos, Defer defer) {
     uint32_t n = 0, p0 = 0, p1 = 0;
-    if (valid) row_head3(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), n, p0, p1);
+    if (valid) row_head3(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), n, p0, p1);
     if (n > E.ix.max_ix) n = E.ix.max_ix;
-    const bool pf = (E.P.flags & 2u) != 0;
-    const bool a0 = valid && n >= 1 && n <= 2 && (!pf || prefilter_alive(E, m, QPos, p0, s == 0));
-    const bool a1 = valid && n == 2 && (!pf || prefilter_alive(E, m, QPos, p1, s == 0));
-    uint32_t vmask = __ballot_sync(FULL, valid);
+    uint32_t x0 = EXT_NONE, x1 = EXT_NONE;
+    if (valid && n >= 1 && n <= 2) x0 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p0, true);
+    if (valid && n == 2) x1 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p1, true);
+    const bool a0 = !ext_is_noop(E, x0, (int)m.QL, m.MaxPenalty), a1 = !ext_is_noop(E, x1, (int)m.QL, m.MaxPenalty);
+    uint32_t vmask = __ballot_sync(FULL, valid && (n > 2 || a0 || a1));
     const uint32_t m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1), big = __ballot_sync(FULL, n > 2);
+    bool stored;
     while (vmask) {
         const int b = __ffs(vmask) - 1;
         vmask &= vmask - 1;
         const uint32_t qb = __shfl_sync(FULL, QPos, b);
         if (big >> b & 1u) { defer(qb); continue; }
-        if (m0 >> b & 1u) extend_pen(E, m, qb, __shfl_sync(FULL, p0, b), s == 0);
-        if (m1 >> b & 1u) extend_pen(E, m, qb, __shfl_sync(FULL, p1, b), s == 0);
+        const uint32_t pb0 = __shfl_sync(FULL, p0, b), pb1 = __shfl_sync(FULL, p1, b);
+        const uint32_t xb0 = __shfl_sync(FULL, x0, b), xb1 = __shfl_sync(FULL, x1, b);
+        if (m0 >> b & 1u) extend_apply(E, m, qb, pb0, s == 0, xb0, stored);
+        if (m1 >> b & 1u) extend_apply(E, m, qb, pb1, s == 0, xb1, stored);
     }
 }
 
-// A deferred (long) row: full GetRow_Blob, one position per lane, prefilter in parallel, extend survivors in order.
+// A deferred (long) row: full GetRow_Blob, one position per lane, pure extensions in parallel, apply in order.
 __device__ void row_long_stage(const Env &E, Mate &m, int s, uint32_t QPos) {
     uint32_t mypos;
-    const uint32_t RowLength = get_row(E, m_slot(m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
-    const bool a = ((uint32_t)E.lane < RowLength) && (!(E.P.flags & 2u) || prefilter_alive(E, m, QPos, mypos, s == 0));
-    uint32_t am = __ballot_sync(FULL, a);
+    const uint32_t RowLength = get_row(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
+    uint32_t x = EXT_NONE;
+    if ((uint32_t)E.lane < RowLength) x = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, mypos, true);
+    uint32_t am = __ballot_sync(FULL, !ext_is_noop(E, x, (int)m.QL, m.MaxPenalty));
+    bool stored;
     while (am) {
         const int r = __ffs(am) - 1;
         am &= am - 1;
-        extend_pen(E, m, QPos, __shfl_sync(FULL, mypos, r), s == 0);
+        extend_apply(E, m, QPos, __shfl_sync(FULL, mypos, r), s == 0, __shfl_sync(FULL, x, r), stored);
     }
 }
 
@@ -1051,29 +1174,40 @@ __device__ void search_lo(const Env &E, Mate &m) {
     const int MinScorePhase4 = QL + E.P.XP4 * E.P.MM;
     const int TermHSPScorePhase3 = (QL * E.P.TERM3_PCT) / 100;
     m.BestHSP = 0;
-    // phase 1: BOTH1 seeds at stride W
-    for (uint32_t QPos = 0; QPos < QWC; QPos += W) {
-        for (int s = 0; s < 2; ++s) {
-            if (m_tally(m, s, QPos) != T_BOTH1) continue;
-            int Score = extend_pen(E, m, QPos, m_pos(m, s, QPos), s == 0);
-            if (Score >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return; }
+    // phases 1 and 2: BOTH1 seeds at stride W (plus then minus at each QPos), then all remaining QPos.  The visit
+    // order is laid out 32 visits at a time into the seed list together with the probe kernel's pure results;
+    // the order-dependent bookkeeping then runs over the candidates that can still do something.
+    {
+        const uint32_t n1 = (QWC + W - 1) / W;          // phase-1 QPos count
+        const uint32_t nvis = 2 * QWC;
+        m.nSeeds = 0;
+        for (uint32_t v0 = 0; v0 < nvis; v0 += 32) {
+            const uint32_t v = v0 + E.lane;
+            uint32_t q = 0;
+            const int sgn = (int)(v & 1u);
+            if (v < 2 * n1) q = (v >> 1) * W;
+            else {
+                const uint32_t vv = (v - 2 * n1) >> 1;
+                q = (W > 1) ? (vv / (W - 1)) * W + vv % (W - 1) + 1 : QWC;
+            }
+            const bool c = (v < nvis) && (q < QWC) && (m_tally(m, sgn, q) == T_BOTH1);
+            const uint32_t bal = __ballot_sync(FULL, c);
+            if (c) {
+                const int i = m.nSeeds + __popc(bal & ((1u << E.lane) - 1u));
+                m.sd_db[i] = m_pos(m, sgn, q);
+                m.sd_ext[i] = m_ext(m, sgn, q);
+                m.sd_qs[i] = (uint16_t)(q | ((uint32_t)sgn << 15));
+            }
+            m.nSeeds += __popc(bal);
         }
-    }
-    // phase 2: remaining BOTH1 seeds. Lanes scan 32 positions at a time, then visit them in order.
-    for (uint32_t q0 = 0; q0 < QWC; q0 += 32) {
-        uint32_t q = q0 + E.lane;
-        bool okq = (q < QWC) && (q % W != 0);
-        uint32_t bp = __ballot_sync(FULL, okq && m_tally(m, 0, q) == T_BOTH1);
-        uint32_t bm = __ballot_sync(FULL, okq && m_tally(m, 1, q) == T_BOTH1);
-        uint32_t any = bp | bm;
-        while (any) {
-            int bit = __ffs(any) - 1;
-            any &= any - 1;
-            uint32_t QPos = q0 + bit;
-            for (int s = 0; s < 2; ++s) {
-                if (!(((s == 0) ? bp : bm) >> bit & 1u)) continue;
-                int Score = extend_pen(E, m, QPos, m_pos(m, s, QPos), s == 0);
+        seeds_init_dead(E, m);
+        for (int w0 = 0; w0 < m.nSeeds; w0 += 32) {
+            uint32_t live = ~m.sd_dead[w0 >> 5];
+            while (live) {
+                const int bit = __ffs(live) - 1;
+                const int Score = apply_seed(E, m, w0 + bit);
                 if (Score >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return; }
+                live = ~m.sd_dead[w0 >> 5] & ((bit == 31) ? 0u : (0xFFFFFFFFu << (bit + 1)));
             }
         }
     }
@@ -1109,61 +1243,61 @@ __device__ void search_lo(const Env &E, Mate &m) {
 }
 
 // ---- paired-end ------------------------------------------------------------------------
-struct SeedIt {   // iterator state of GetFirst/NextBoth1Seed for one mate
-    uint32_t k;    // UINT_MAX when exhausted
-    uint32_t QPos, DBPos;
-    bool Plus;
-};
-
-__device__ __forceinline__ void pend_push(const Env &E, Mate &m, int s, uint32_t QPos) {
-    if (E.lane == 0) m.g->pend[s][m.nPend[s]] = (uint8_t)QPos;
-    ++m.nPend[s];
-}
-
-// Shared scan loop of GetFirstBoth1Seed (getseed.cpp:9-54) and GetNextBoth1Seed (getseed.cpp:87-137).
-// `first` disables the same-diagonal filter.
-__device__ uint32_t seed_scan(const Env &E, Mate &m, uint32_t kstart, bool first, SeedIt &it) {
+// GetFirstBoth1Seed / GetNextBoth1Seed (getseed.cpp:9-54,56-138) for the whole read at once.
+// The iterator visits v = 2k+strand with QPos = (27k) % QWC and returns a BOTH1 slot unless its diagonal equals
+// the diagonal of the previously RETURNED seed.  A skipped BOTH1 slot has, by construction, the diagonal of the
+// last returned one, so "returned" == "diagonal differs from the previous BOTH1 visit": a run-length dedup that
+// 32 lanes evaluate with one ballot and one shuffle per 32 visits.  Pending lists (state1.h:86-87) in visit order:
+//   plus visit : owned non-BOTH1 slot;
+//   minus visit: owned non-BOTH1 slot, except when the plus slot of the same k was just returned -- then only a
+//                BOTH1 slot on the same diagonal is pushed (getseed.cpp:63-85).
+// The lists are only consumed after the seed loop ran to completion, so building them up front is exact.
+__device__ void build_seeds_pe(const Env &E, Mate &m) {
     const uint32_t QWC = m.QWC;
-    for (uint32_t k = kstart; k < QWC; ++k) {
-        uint32_t QPos = (k * PRIME_STRIDE) % QWC;
-        if (first) it.QPos = QPos;
-        for (int s = 0; s < 2; ++s) {
-            uint32_t T = m_tally(m, s, QPos);
-            uint32_t P = m_pos(m, s, QPos);
-            if (T == T_FREE && P == POS_INVALID_WORD) continue;  // Slot == UINT64_MAX
-            if ((T & T_MY_BIT) == 0) continue;
-            if (T != T_BOTH1) { pend_push(E, m, s, QPos); continue; }
-            if (!first && (P - QPos == it.DBPos - it.QPos)) continue;
-            it.DBPos = P;
-            it.QPos = QPos;
-            it.Plus = (s == 0);
-            return k;
+    m.nSeeds = 0;
+    m.nPend[0] = m.nPend[1] = 0;
+    bool have_prev = false;
+    uint32_t prev_diag = 0;
+    const uint32_t lt = (1u << E.lane) - 1u;
+    for (uint32_t v0 = 0; v0 < 2 * QWC; v0 += 32) {
+        const uint32_t v = v0 + E.lane, k = v >> 1;
+        const int sgn = (int)(v & 1u);
+        const bool valid = k < QWC;
+        const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
+        const uint32_t T = valid ? m_tally(m, sgn, QPos) : 0u;
+        const uint32_t Pz = valid ? m_pos(m, sgn, QPos) : 0u;
+        const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE
+        const bool b1 = mine && T == T_BOTH1;
+        const uint32_t diag = Pz - QPos;
+        const uint32_t b1mask = __ballot_sync(FULL, b1);
+        const uint32_t below = b1mask & lt;
+        const uint32_t pd = __shfl_sync(FULL, diag, below ? 31 - __clz(below) : 0);
+        const bool hasp = below ? true : have_prev;
+        const uint32_t pdiag = below ? pd : prev_diag;
+        const bool ret = b1 && (!hasp || diag != pdiag);
+        const uint32_t retmask = __ballot_sync(FULL, ret);
+        const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
+        const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
+        const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
+        if (ret) {
+            const int i = m.nSeeds + __popc(retmask & lt);
+            m.sd_db[i] = Pz;
+            m.sd_ext[i] = m_ext(m, sgn, QPos);
+            m.sd_qs[i] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
+        }
+        if (pend) {
+            const int i = m.nPend[sgn] + __popc((sgn ? pm : pp) & lt);
+            m.g->pend[sgn][i] = (uint8_t)QPos;
+        }
+        m.nSeeds += __popc(retmask);
+        m.nPend[0] += __popc(pp);
+        m.nPend[1] += __popc(pm);
+        if (b1mask) {
+            have_prev = true;
+            prev_diag = __shfl_sync(FULL, diag, 31 - __clz(b1mask));
         }
     }
-    return 0xFFFFFFFFu;
-}
-
-__device__ void seed_first(const Env &E, Mate &m, SeedIt &it) {
-    it.QPos = 0; it.DBPos = 0; it.Plus = false;
-    it.k = seed_scan(E, m, 0, true, it);
-}
-
-__device__ void seed_next(const Env &E, Mate &m, SeedIt &it) {  // getseed.cpp:56-138
-    const uint32_t QWC = m.QWC;
-    if (it.Plus) {  // minus strand at the same k; a non-BOTH1 owned slot is NOT pushed to pending here
-        uint32_t QPos = (it.k * PRIME_STRIDE) % QWC;
-        uint32_t T = m_tally(m, 1, QPos), P = m_pos(m, 1, QPos);
-        if (!(T == T_FREE && P == POS_INVALID_WORD) && T == T_BOTH1) {
-            if (P - QPos != it.DBPos - it.QPos) {
-                it.DBPos = P;
-                it.QPos = QPos;
-                it.Plus = false;
-                return;
-            } else
-                pend_push(E, m, 1, QPos);
-        }
-    }
-    it.k = seed_scan(E, m, it.k + 1, false, it);
+    seeds_init_dead(E, m);
 }
 
 // State1::SearchPE_Pending, search1pepend.cpp:9-130 (k is always UINT_MAX at the call sites)
@@ -1214,7 +1348,7 @@ __device__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, uint32_t DBSegL
     uint32_t qpos[SCANK];
     for (uint32_t k = 0; k < SCANK; ++k) {
         qpos[k] = (k * PRIME_STRIDE) % m.QWC;
-        qslot[k] = m_slot(m, s, qpos[k]);  // ~0 for invalid words: never equals a real slot
+        qslot[k] = m_slot(E, m, s, qpos[k]);  // ~0 for invalid words: never equals a real slot
     }
     const uint8_t *T = E.ix.seq + DBLo;
     if (DBSegLength < W) return;
@@ -1345,12 +1479,20 @@ __device__ void scan_pair(const Env &E, Mate &F, Mate &R) {
     }
 }
 
+// ExtendPen of seed i of mate m on strand Plus: through the memo when Plus is the seed's own strand, otherwise
+// (search2m4.cpp:94-95,122 extend a stored seed on the strand dictated by the OTHER mate's seed) computed here.
+__device__ int apply_seed_on(const Env &E, Mate &m, int i, bool Plus) {
+    const uint32_t qs = m.sd_qs[i];
+    if (((qs >> 15) == 0) == Plus) return apply_seed(E, m, i);
+    return extend_pen(E, m, qs & 0x7FFFu, m.sd_db[i], Plus);
+}
+
 // State2::ExtendBoth1Pair4/5, search2m4.cpp:189-208, search2m5.cpp:134-156
-__device__ bool extend_both1_pair(const Env &E, Mate &F, Mate &R, uint32_t QPosf, uint32_t DBPosf, bool Plusf,
-                                  uint32_t QPosr, uint32_t DBPosr, int TermPairScore) {
-    int FwdScore = extend_pen(E, F, QPosf, DBPosf, Plusf);
+__device__ bool extend_both1_pair(const Env &E, Mate &F, Mate &R, int fi, int ri, bool Plusf, int TermPairScore,
+                                  int &FwdScore) {
+    FwdScore = apply_seed_on(E, F, fi, Plusf);
     if (FwdScore <= 0) return false;
-    int RevScore = extend_pen(E, R, QPosr, DBPosr, !Plusf);
+    int RevScore = apply_seed_on(E, R, ri, !Plusf);
     if (RevScore <= 0) return false;
     if (FwdScore + RevScore < TermPairScore) return false;
     F.Mapq = 40;
@@ -1358,14 +1500,16 @@ __device__ bool extend_both1_pair(const Env &E, Mate &F, Mate &R, uint32_t QPosf
     return true;
 }
 
-__device__ __forceinline__ void seed_record(const Env &E, Mate &m, int n, const SeedIt &it, int &ovf) {
-    if (n >= kSeedCap) { ovf = 1; return; }
-    if (E.lane == 0) {
-        m.g->seed_db[n] = it.DBPos;
-        m.g->seed_q[n] = (uint8_t)it.QPos;
-        m.g->seed_plus[n] = it.Plus ? 1 : 0;
+// ExtendPen every recorded seed in order (search2m4.cpp:139-153): only seeds that can still do something are visited.
+__device__ void extend_all_seeds(const Env &E, Mate &m) {
+    for (int w0 = 0; w0 < m.nSeeds; w0 += 32) {
+        uint32_t live = ~m.sd_dead[w0 >> 5];
+        while (live) {
+            const int bit = __ffs(live) - 1;
+            apply_seed(E, m, w0 + bit);
+            live = ~m.sd_dead[w0 >> 5] & ((bit == 31) ? 0u : (0xFFFFFFFFu << (bit + 1)));
+        }
     }
-    __syncwarp();
 }
 
 // State2::Search4 / Search5, search2m4.cpp:15-187, search2m5.cpp:9-132
@@ -1376,56 +1520,59 @@ __device__ void search_pair(const Env &E, Mate &F, Mate &R) {
     if (F.QL < W || R.QL < W) { F.Mapq = R.Mapq = 0; return; }
     const int QLf = (int)F.QL, QLr = (int)R.QL, QL2 = (QLf + QLr) / 2;
     const int TermPairScore = QLf + QLr + 5 * E.P.MM;
-    int NB1f = 0, NB1r = 0, ovf = 0;
-    SeedIt itf, itr;
-    seed_first(E, F, itf);
-    seed_first(E, R, itr);
-    do {
-        if (itf.k != 0xFFFFFFFFu) {
-            seed_record(E, F, NB1f, itf, ovf);
-            if (NB1f < kSeedCap) ++NB1f;
-            for (int base = 0; base < NB1r; base += 32) {
-                int i = base + E.lane;
-                uint32_t dbr = (i < NB1r) ? R.g->seed_db[i] : 0;
-                int64_t d = (int64_t)itf.DBPos - (int64_t)dbr;
+    build_seeds_pe(E, F);
+    build_seeds_pe(E, R);
+    // Iteration t of the reference's do-while records F seed t then R seed t (while they last):
+    //   (a) F seed t against R seeds [0, min(t, NR)): ExtendPen(F t) comes first in every ExtendBoth1Pair4 call, so
+    //       once it is known to return <= 0 without side effects the remaining partners are no-ops;
+    //   (b) R seed t against F seeds [0, min(t+1, NF)): partners whose own-strand memo is dead are no-ops.
+    const int NF = F.nSeeds, NR = R.nSeeds;
+    for (int t = 0; t < max(NF, NR); ++t) {
+        if (t < NF && !seed_dead(F, t)) {
+            const int nR = min(t, NR);
+            const uint32_t dbf = F.sd_db[t];
+            const bool Plusf = (F.sd_qs[t] >> 15) == 0;
+            bool gone = false;
+            for (int base = 0; base < nR && !gone; base += 32) {
+                const int i = base + E.lane;
+                int64_t d = (int64_t)dbf - (int64_t)((i < nR) ? R.sd_db[i] : 0u);
                 if (d < 0) d = -d;
-                uint32_t bal = __ballot_sync(FULL, (i < NB1r) && (d + QL2 <= MAX_TL));
+                uint32_t bal = __ballot_sync(FULL, (i < nR) && (d + QL2 <= MAX_TL));
                 while (bal) {
-                    int bit = __ffs(bal) - 1;
+                    const int bit = __ffs(bal) - 1;
                     bal &= bal - 1;
-                    int idx = base + bit;
-                    if (extend_both1_pair(E, F, R, itf.QPos, itf.DBPos, itf.Plus, R.g->seed_q[idx], R.g->seed_db[idx],
-                                          TermPairScore))
-                        return;
+                    int fs;
+                    if (extend_both1_pair(E, F, R, t, base + bit, Plusf, TermPairScore, fs)) return;
+                    if (fs <= 0) { gone = true; break; }
                 }
             }
         }
-        if (itr.k != 0xFFFFFFFFu) {
-            seed_record(E, R, NB1r, itr, ovf);
-            if (NB1r < kSeedCap) ++NB1r;
-            for (int base = 0; base < NB1f; base += 32) {
-                int i = base + E.lane;
-                uint32_t dbf = (i < NB1f) ? F.g->seed_db[i] : 0;
-                int64_t d = (int64_t)dbf - (int64_t)itr.DBPos;
-                if (d < 0) d = -d;
-                uint32_t bal = __ballot_sync(FULL, (i < NB1f) && (d + QL2 <= MAX_TL));
+        if (t < NR) {
+            const int nF = min(t + 1, NF);
+            const uint32_t dbr = R.sd_db[t];
+            const bool Plusr = (R.sd_qs[t] >> 15) == 0;
+            for (int base = 0; base < nF; base += 32) {
+                const int i = base + E.lane;
+                bool ok = false;
+                if (i < nF) {
+                    int64_t d = (int64_t)F.sd_db[i] - (int64_t)dbr;
+                    if (d < 0) d = -d;
+                    const bool own = ((F.sd_qs[i] >> 15) == 0) == !Plusr;
+                    ok = (d + QL2 <= MAX_TL) && !(own && seed_dead(F, i));
+                }
+                uint32_t bal = __ballot_sync(FULL, ok);
                 while (bal) {
-                    int bit = __ffs(bal) - 1;
+                    const int bit = __ffs(bal) - 1;
                     bal &= bal - 1;
-                    int idx = base + bit;
-                    if (extend_both1_pair(E, F, R, F.g->seed_q[idx], F.g->seed_db[idx], !itr.Plus, itr.QPos, itr.DBPos,
-                                          TermPairScore))
-                        return;
+                    int fs;
+                    if (extend_both1_pair(E, F, R, base + bit, t, !Plusr, TermPairScore, fs)) return;
                 }
             }
         }
-        if (itf.k != 0xFFFFFFFFu) seed_next(E, F, itf);
-        if (itr.k != 0xFFFFFFFFu) seed_next(E, R, itr);
-    } while (itf.k != 0xFFFFFFFFu || itr.k != 0xFFFFFFFFu);
-    if (ovf) F.overflow = 1;
+    }
 
-    for (int i = 0; i < NB1f; ++i) extend_pen(E, F, F.g->seed_q[i], F.g->seed_db[i], F.g->seed_plus[i] != 0);
-    for (int i = 0; i < NB1r; ++i) extend_pen(E, R, R.g->seed_q[i], R.g->seed_db[i], R.g->seed_plus[i] != 0);
+    extend_all_seeds(E, F);
+    extend_all_seeds(E, R);
 
     if (E.P.pe_method == 5) {
         search_pe_pending(E, F);
@@ -1507,33 +1654,41 @@ __device__ void write_result(const Env &E, const Mate &m, const DevOut &o, uint3
     }
 }
 
-// Load one read into shared memory (bytes, reverse complement, probe results).
-__device__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevProbe &pr, uint32_t r, uint8_t *s_q,
-                          uint8_t *s_rc, uint8_t *s_tally, uint32_t *s_pos, uint32_t *s_alive, MateScratch *g) {
+// Per-mate shared-memory footprint of the search kernel.
+__host__ __device__ inline size_t mate_smem_bytes(uint32_t qcap, uint32_t seqcap) {
+    //     bytes fwd+rc      packed + bad bits   sd_db + sd_ext          sd_qs              sd_dead
+    return 2 * (size_t)seqcap + kReadViewBytes + 2 * (size_t)qcap * 8 + 2 * (size_t)qcap * 2 + ((2 * (size_t)qcap + 31) / 32) * 4;
+}
+
+// Stage one read: bytes, reverse complement, packed strands in shared memory; probe results stay in global.
+__device__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevProbe &pr, uint32_t r, uint8_t *sm,
+                          MateScratch *g) {
     const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
-    for (uint32_t i = E.lane; i < L; i += 32) {
-        uint32_t c = b.seqs[off + i];
-        s_q[i] = (uint8_t)c;
-        s_rc[L - 1 - i] = (uint8_t)compchar_of(c);  // RevCompSeq, seqinfo.cpp:9
-    }
+    uint64_t *s_pk = reinterpret_cast<uint64_t *>(sm);
+    uint32_t *s_bad = reinterpret_cast<uint32_t *>(sm + 2 * kPkWords * 8);
+    uint8_t *p8 = sm + kReadViewBytes;
+    m.sd_db = reinterpret_cast<uint32_t *>(p8);
+    p8 += 2 * (size_t)b.qcap * 4;
+    m.sd_ext = reinterpret_cast<uint32_t *>(p8);
+    p8 += 2 * (size_t)b.qcap * 4;
+    m.sd_dead = reinterpret_cast<uint32_t *>(p8);
+    p8 += ((2 * (size_t)b.qcap + 31) / 32) * 4;
+    m.sd_qs = reinterpret_cast<uint16_t *>(p8);
+    p8 += 2 * (size_t)b.qcap * 2;
+    uint8_t *s_q = p8, *s_rc = p8 + b.seqcap;
+    stage_read(E.lane, b.seqs + off, L, b.seqcap, s_q, s_rc, s_pk, s_bad, m.rv);
     const size_t base = (size_t)r * 2 * b.qcap;
-    for (uint32_t i = E.lane; i < 2 * b.qcap; i += 32) {
-        s_tally[i] = pr.tally[base + i];
-        s_pos[i] = pr.pos[base + i];
-    }
-    __syncwarp();
     m.q = s_q;
     m.rc = s_rc;
-    m.tally = s_tally;
-    m.pos = s_pos;
-    m.slots = pr.slot + base;
+    m.tally = pr.tally + base;
+    m.pos = pr.pos + base;
+    m.ext = pr.ext + base;
+    m.nSeeds = 0;
     m.g = g;
     m.QL = L;
     m.QWC = (L >= E.ix.word_len) ? L - E.ix.word_len + 1 : 0;
     m.qcap = b.qcap;
     m.overflow = 0;
-    m.alive = s_alive;
-    build_alive_table(E, m);
 }
 
 __device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr,
@@ -1543,18 +1698,10 @@ __device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + warp;
     uint8_t *sw = smem + (size_t)warp * smem_per_warp;
-    // layout: pos[nm][2][qcap] u32 | q[nm][seqcap] | rc[nm][seqcap] | tally[nm][2][qcap] | win | tb
+    // layout: mate 0 | mate 1 (paired) | flank-DP window | flank-DP trace bits
     const int nm = b.paired ? 2 : 1;
-    uint32_t *s_pos = reinterpret_cast<uint32_t *>(sw);
-    uint8_t *p8 = sw + (size_t)nm * 2 * b.qcap * 4;
-    uint8_t *s_q = p8;
-    p8 += (size_t)nm * b.seqcap;
-    uint8_t *s_rc = p8;
-    p8 += (size_t)nm * b.seqcap;
-    uint8_t *s_tally = p8;
-    p8 += (size_t)nm * 2 * b.qcap;
-    uint32_t *s_alive = reinterpret_cast<uint32_t *>(p8);
-    p8 += (size_t)nm * 16 * 4;
+    const size_t msz = (mate_smem_bytes(b.qcap, b.seqcap) + 15) & ~(size_t)15;
+    uint8_t *p8 = sw + (size_t)nm * msz;
     Env E;
     E.ix = ix;
     E.P = P;
@@ -1573,15 +1720,14 @@ __device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams 
         if (u >= b.n_units) break;
         if (!b.paired) {
             Mate m;
-            load_mate(E, m, b, pr, u, s_q, s_rc, s_tally, s_pos, s_alive, &E.ws->m[0]);
+            load_mate(E, m, b, pr, u, sw, &E.ws->m[0]);
             reset_search(E, m);   // State1::Search, search1.cpp:7-24
             search_lo(E, m);
             write_result(E, m, o, u);
         } else {
             Mate F, R;
-            load_mate(E, F, b, pr, u, s_q, s_rc, s_tally, s_pos, s_alive, &E.ws->m[0]);
-            load_mate(E, R, b, pr, b.n_units + u, s_q + b.seqcap, s_rc + b.seqcap, s_tally + 2 * b.qcap,
-                      s_pos + 2 * b.qcap, s_alive + 16, &E.ws->m[1]);
+            load_mate(E, F, b, pr, u, sw, &E.ws->m[0]);
+            load_mate(E, R, b, pr, b.n_units + u, sw + msz, &E.ws->m[1]);
             search_pair(E, F, R);
             write_result(E, F, o, u);
             write_result(E, R, o, b.n_units + u);
@@ -1605,7 +1751,7 @@ static inline uint32_t tb_stride_for(const DevParams &P) { return 4 * P.R + 6; }
 
 size_t search_smem_per_warp(const DevBatch &b, const DevParams &P) {
     const int nm = b.paired ? 2 : 1;
-    size_t s = (size_t)nm * 2 * b.qcap * 4 + (size_t)nm * b.seqcap * 2 + (size_t)nm * 2 * b.qcap + (size_t)nm * 64;
+    size_t s = (size_t)nm * ((mate_smem_bytes(b.qcap, b.seqcap) + 15) & ~(size_t)15);
     s += b.seqcap + 64;
     const uint32_t rows = b.seqcap + 2;
     s += (size_t)rows * (tb_stride_for(P) / 2) + rows + tb_stride_for(P);   // nibble rows + column LB + row LA
@@ -1614,13 +1760,23 @@ size_t search_smem_per_warp(const DevBatch &b, const DevParams &P) {
 
 int max_search_warps(int sm_count) { return sm_count * 32; }
 
-int launch_probe(const DevIndex &ix, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count) {
+size_t packed_words(size_t n_bytes) { return n_bytes / 32 + 2; }
+
+int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint32_t *seqx, void *stream) {
+    const size_t n_words = packed_words(n_bytes);
+    size_t blocks = (n_words + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    URMB_LAUNCH(pack_genome_kernel, (int)blocks, 256, 0, stream, seq, n_bytes, n_words, seq2, seqx);
+    return (int)cudaGetLastError();
+}
+
+int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count) {
     const int threads = 256;
-    const size_t smem = (size_t)(threads / 32) * 2 * b.seqcap;
+    const size_t smem = (size_t)(threads / 32) * (2 * b.seqcap + kReadViewBytes);
     int blocks = (int)((b.n_reads + 7) / 8);
     if (blocks > sm_count * 16) blocks = sm_count * 16;
     if (blocks < 1) blocks = 1;
-    URMB_LAUNCH(probe_kernel, blocks, threads, smem, stream, ix, b, pr);
+    URMB_LAUNCH(probe_kernel, blocks, threads, smem, stream, ix, P, b, pr);
     return (int)cudaGetLastError();
 }
 

@@ -1,11 +1,19 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, a bench line, the ncu launch list and a full capture of the top kernels.
-# Usage (under gpurun): bash tools/gpu_round.sh <tag> [tests|bench|ncu ...]   (default: all three)
+# Usage (under gpurun): bash tools/gpu_round.sh <tag> [tests|smoke|bench|benchq|ncu|ncus|ncup ...]   (default: tests bench ncu)
 TAG=${1:-run}; shift
 WHAT=${*:-tests bench ncu}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/smi.txt 2>&1
+ncu_full() {  # $1 = kernel regex, $2 = output stem
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"$1" -s 3 -c 1 -f -o $OUT/$2 \
+      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --pairs-per-step 250000 > $OUT/ncu_$2.log 2>&1
+  echo "ncu full $2 exit $?"
+  ncu -i $OUT/$2.ncu-rep --page raw --csv > $OUT/$2_raw.csv 2>/dev/null
+  ncu -i $OUT/$2.ncu-rep --page source --csv --print-source cuda,sass > $OUT/$2_src.csv 2>/dev/null
+  python tools/ncu_lines.py $OUT/$2_src.csv 60 > $OUT/$2_hot_lines.txt 2>&1
+}
 for w in $WHAT; do
 case $w in
 tests)
@@ -24,13 +32,10 @@ ncu)
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'probe_kernel|search_kernel' -c 40 --csv \
       --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
   echo "ncu launches exit $?"
-  # one full capture of each hot kernel (skip the warm-up launches)
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'search_kernel' -s 3 -c 1 -f -o $OUT/search_full \
-      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --pairs-per-step 250000 > $OUT/ncu_full_search.log 2>&1
-  echo "ncu full search exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'probe_kernel' -s 3 -c 1 -f -o $OUT/probe_full \
-      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --pairs-per-step 250000 > $OUT/ncu_full_probe.log 2>&1
-  echo "ncu full probe exit $?" ;;
+  ncu_full search_kernel search_full
+  ncu_full probe_kernel probe_full ;;
+ncus) ncu_full search_kernel search_full ;;
+ncup) ncu_full probe_kernel probe_full ;;
 esac
 done
 ls -la $OUT

@@ -47,13 +47,9 @@ constexpr uint32_t BRN = 2;
 
 // g_CharToLetterNucleo semantics (alpha.cpp:1309): A/a=0 C/c=1 G/g=2 T/t/U/u=3 else 0xFF
 __device__ __forceinline__ uint32_t letter_of(uint32_t c) {
-    uint32_t u = c & 0xDFu;
-    uint32_t r = 0xFFu;
-    if (u == 'A') r = 0;
-    else if (u == 'C') r = 1;
-    else if (u == 'G') r = 2;
-    else if (u == 'T' || u == 'U') r = 3;
-    return r;
+    const uint32_t u = c & 0xDFu;
+    const bool ok = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T') | (u == 'U');
+    return ok ? (((u >> 1) ^ (u >> 2)) & 3u) : 0xFFu;   // A 0, C 1, G 2, T/U 3
 }
 
 // g_CharToCompChar semantics (alpha.cpp:3005): IUPAC-aware, case-preserving, 'u' and unknown -> '?'
@@ -89,8 +85,8 @@ __device__ __forceinline__ uint64_t mod_slots(uint64_t h, uint64_t p, uint64_t m
 }
 
 __device__ __forceinline__ uint64_t add_mod(uint64_t a, uint64_t b, uint64_t p) {
-    uint64_t s = a + b;  // a < p < 2^63, b small
-    if (s >= p) s %= p;
+    uint64_t s = a + b;  // a < p < 2^63, b < 2^17: one or two subtractions replace the 64-bit modulo
+    while (s >= p) s -= p;
     return s;
 }
 
@@ -173,37 +169,38 @@ struct ReadView {
 constexpr size_t kReadViewBytes = 2 * kPkWords * 8 + 2 * kBadWords * 4;   // + 2*seqcap bytes
 
 // Warp-cooperative. s_q/s_rc: seqcap bytes each; s_pk: 2*kPkWords u64; s_bad: 2*kBadWords u32.
-__device__ void stage_read(int lane, const uint8_t *src, uint32_t L, uint32_t seqcap, uint8_t *s_q, uint8_t *s_rc,
-                           uint64_t *s_pk, uint32_t *s_bad, ReadView &rv) {
+__device__ __noinline__ void stage_read(int lane, const uint8_t *src, uint32_t L, uint32_t seqcap, uint8_t *s_q,
+                                        uint8_t *s_rc, uint64_t *s_pk, uint32_t *s_bad, ReadView &rv) {
     bool notacgt = false;
-    for (uint32_t i = lane; i < seqcap; i += 32) {
-        if (i < L) {
-            const uint32_t c = src[i];
-            s_q[i] = (uint8_t)c;
-            s_rc[L - 1 - i] = (uint8_t)compchar_of(c);
-            notacgt |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
-        }
+#pragma unroll 1
+    for (uint32_t i = lane; i < L; i += 32) {
+        const uint32_t c = src[i];
+        s_q[i] = (uint8_t)c;
+        s_rc[L - 1 - i] = (uint8_t)compchar_of(c);
+        notacgt |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
     }
     for (int i = lane; i < 2 * kPkWords; i += 32) s_pk[i] = 0;
     for (int i = lane; i < 2 * kBadWords; i += 32) s_bad[i] = 0;
     __syncwarp();
-    // lane = group of 8 bases (kMaxLen / 8 == 32 groups)
+    // lane = group of 8 bases (kMaxLen / 8 == 32 groups), both strands
     uint32_t anybad = 0;
-    for (int s = 0; s < 2; ++s) {
-        const uint8_t *bytes = s ? s_rc : s_q;
-        const uint32_t g = (uint32_t)lane;
-        uint32_t code = 0, bad = 0;
-        for (uint32_t t = 0; t < 8; ++t) {
-            const uint32_t i = 8 * g + t;
-            uint32_t l = (i < L) ? letter_of(bytes[i]) : 0u;
-            if (l & 0x80u) { bad |= 1u << t; l = 0; }
-            code |= (l & 3u) << (14 - 2 * t);
-        }
-        if (8 * g < L) {
+    const uint32_t g = (uint32_t)lane;
+    if (8 * g < L) {
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            const uint8_t *bytes = s ? s_rc : s_q;
+            uint32_t code = 0, bad = 0;
+#pragma unroll 1
+            for (uint32_t t = 0; t < 8; ++t) {
+                const uint32_t i = 8 * g + t;
+                uint32_t l = (i < L) ? letter_of(bytes[i]) : 0u;
+                if (l & 0x80u) { bad |= 1u << t; l = 0; }
+                code = (code << 2) | (l & 3u);
+            }
             reinterpret_cast<uint16_t *>(s_pk + s * kPkWords)[4 * (g >> 2) + (3 - (g & 3))] = (uint16_t)code;
             reinterpret_cast<uint8_t *>(s_bad + s * kBadWords)[g] = (uint8_t)bad;
+            anybad |= bad;
         }
-        anybad |= bad;
     }
     rv.q = s_q;
     rv.rc = s_rc;
@@ -277,12 +274,15 @@ __device__ __noinline__ uint32_t pure_ext_bytes(const uint8_t *Qs, const uint8_t
 }
 
 // Lane-local. Plus selects the read strand; the candidate is (SeedPosQ, SeedPosDB) on diagonal DBLo.
-__device__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus, uint32_t SeedPosQ,
-                             uint32_t SeedPosDB, bool LeftCountsPen) {
+// PenBound: any bound known to be >= m_MaxPenalty at the time the reference would make this call; the walk stops
+// as soon as the penalty exceeds it (the packed result then only says "fails the bound", which is all that is used).
+__device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus,
+                                          uint32_t SeedPosQ, uint32_t SeedPosDB, bool LeftCountsPen, int PenBound) {
     if (SeedPosDB < SeedPosQ) return EXT_NONE;   // extendpen.cpp:11
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
     const int QL = (int)rv.QL, W = (int)ix.word_len, MM = P.MM, XD = P.XDROP;
     const int nw = (QL + 31) >> 5;   // <= 8
+    const int maxmis = min(PenBound / -MM, 126);   // nmis > maxmis  <=>  nmis * -MM > PenBound
     uint64_t mm[8];
     bool slow = rv.slow;
     if (!slow) {
@@ -293,7 +293,7 @@ __device__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadV
         uint64_t gw[9];
         uint32_t exc = 0;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < 9; ++k) {   // all loads are issued before the first one is consumed
             gw[k] = 0;
             if (k <= nw) {
                 gw[k] = __ldg(g + k);
@@ -304,15 +304,15 @@ __device__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadV
         else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                mm[k] = 0;
+                uint64_t d = 0;
                 if (k < nw) {
                     const uint64_t a = sh ? ((gw[k] << sh) | (gw[k + 1] >> (64 - sh))) : gw[k];
-                    uint64_t d = a ^ rp[k];
+                    d = a ^ rp[k];
                     d = (d | (d >> 1)) & 0x5555555555555555ull;
-                    if (k == nw - 1 && (QL & 31)) d &= ~0ull << (64 - 2 * (QL & 31));
-                    mm[k] = d;
                 }
+                mm[k] = d;
             }
+            if (QL & 31) mm[nw - 1] &= ~0ull << (64 - 2 * (QL & 31));
         }
     }
     if (slow) return pure_ext_bytes(Plus ? rv.q : rv.rc, ix.seq + DBLo, QL, W, MM, XD, SeedPosQ, LeftCountsPen);
@@ -322,26 +322,23 @@ __device__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadV
     {   // right walk, extendpen.cpp:29-52: mismatches in increasing position = decreasing bit index
         int p = End + 1;
         bool stop = false;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k < nw && !stop && (k << 5) + 32 > p) {
-                uint64_t w = mm[k];
-                const int b0 = p - (k << 5);
-                if (b0 > 0) w &= ~0ull >> (2 * b0);
-                while (w) {
-                    const int hb = 63 - __clzll((long long)w);
-                    w &= ~(1ull << hb);
-                    const int pos = (k << 5) + ((62 - hb) >> 1);
-                    const int run = pos - p;
-                    if (run > 0) {
-                        Score += run;
-                        if (Score > Best) { Best = Score; End = pos - 1; }
-                    }
-                    ++nmis;
-                    Score += MM;
-                    p = pos + 1;
-                    if (Best - Score > XD) { stop = true; break; }
+        for (int k = p >> 5; k < nw && !stop; ++k) {
+            uint64_t w = mm[k];
+            const int b0 = p - (k << 5);
+            if (b0 > 0) w &= ~0ull >> (2 * b0);
+            while (w) {
+                const int hb = 63 - __clzll((long long)w);
+                w &= ~(1ull << hb);
+                const int pos = (k << 5) + ((62 - hb) >> 1);
+                const int run = pos - p;
+                if (run > 0) {
+                    Score += run;
+                    if (Score > Best) { Best = Score; End = pos - 1; }
                 }
+                ++nmis;
+                Score += MM;
+                p = pos + 1;
+                if (Best - Score > XD || nmis > maxmis) { stop = true; break; }
             }
         }
         if (!stop) {
@@ -352,30 +349,28 @@ __device__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadV
             }
         }
     }
+    if (nmis > maxmis) return ext_pack(0, 1, 0, 127);
     int Start = (int)SeedPosQ;
     {   // left walk, extendpen.cpp:55-78
         int p = Start - 1;
         bool stop = false;
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            if (k < nw && !stop && p >= 0 && (k << 5) <= p) {
-                uint64_t w = mm[k];
-                const int b1 = p - (k << 5);
-                if (b1 < 31) w &= ~0ull << (62 - 2 * b1);
-                while (w) {
-                    const int lb = __ffsll((long long)w) - 1;
-                    w &= w - 1;
-                    const int pos = (k << 5) + ((62 - lb) >> 1);
-                    const int run = p - pos;
-                    if (run > 0) {
-                        Score += run;
-                        if (Score > Best) { Best = Score; Start = pos + 1; }
-                    }
-                    if (LeftCountsPen) ++nmis;
-                    Score += MM;
-                    p = pos - 1;
-                    if (Best - Score > XD) { stop = true; break; }
+        for (int k = p >> 5; k >= 0 && !stop; --k) {   // p == -1 gives k == -1: no iterations
+            uint64_t w = mm[k];
+            const int b1 = p - (k << 5);
+            if (b1 < 31) w &= ~0ull << (62 - 2 * b1);
+            while (w) {
+                const int lb = __ffsll((long long)w) - 1;
+                w &= w - 1;
+                const int pos = (k << 5) + ((62 - lb) >> 1);
+                const int run = p - pos;
+                if (run > 0) {
+                    Score += run;
+                    if (Score > Best) { Best = Score; Start = pos + 1; }
                 }
+                if (LeftCountsPen) ++nmis;
+                Score += MM;
+                p = pos - 1;
+                if (Best - Score > XD || nmis > maxmis) { stop = true; break; }
             }
         }
         if (!stop) {
@@ -386,6 +381,7 @@ __device__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadV
             }
         }
     }
+    if (nmis > maxmis) return ext_pack(0, 1, 0, 127);
     return ext_pack(Best, Start, End, nmis);
 }
 
@@ -416,7 +412,7 @@ __global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevParams P, De
                     const uint64_t slot = slot_of(ix, rv, (int)s, q);
                     if (slot != ~0ull) {
                         load_blob<false>(ix.blob, slot, tally, pos);
-                        if (tally == T_BOTH1) ext = pure_ext(ix, P, rv, s == 0, q, pos, true);
+                        if (tally == T_BOTH1) ext = pure_ext(ix, P, rv, s == 0, q, pos, true, P.MAXPEN);
                     }
                 }
                 pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
@@ -467,7 +463,7 @@ struct Mate {
 __device__ __forceinline__ const uint8_t *mate_seq(const Mate &m, bool Plus) { return Plus ? m.q : m.rc; }
 
 // ---- run-length path helpers -----------------------------------------------------------
-__device__ __forceinline__ void runs_append(uint16_t *runs, int &n, uint32_t op, uint32_t len, int cap, int &ovf,
+__device__ __noinline__ void runs_append(uint16_t *runs, int &n, uint32_t op, uint32_t len, int cap, int &ovf,
                                             int lane) {
     // all lanes track n; lane 0 writes
     if (len == 0) return;
@@ -509,7 +505,7 @@ __device__ int overlaps_hsp(const Env &E, const Mate &m, uint32_t StartPosQ, uin
 }
 
 // State1::AddHitX, state1.cpp:508-551. runs == nullptr / nruns == 0 => empty path.
-__device__ int add_hit(const Env &E, Mate &m, uint32_t StartPosDB, bool Plus, int Score, const uint16_t *runs,
+__device__ __noinline__ int add_hit(const Env &E, Mate &m, uint32_t StartPosDB, bool Plus, int Score, const uint16_t *runs,
                        int nruns) {
     if (Score < 10) return -1;
     if (overlaps_hit(E, m, StartPosDB)) return -1;
@@ -555,7 +551,7 @@ __device__ __forceinline__ void hsp_store(const Env &E, Mate &m, int k, uint32_t
 }
 
 // State1::AddHSPX, state1.cpp:553-591
-__device__ void add_hsp(const Env &E, Mate &m, uint32_t qs, uint32_t dbs, bool Plus, uint32_t len, int Score) {
+__device__ __noinline__ void add_hsp(const Env &E, Mate &m, uint32_t qs, uint32_t dbs, bool Plus, uint32_t len, int Score) {
     if (Score < m.Best - 4) return;
     int k = overlaps_hsp(E, m, qs, dbs);
     if (k >= 0) {
@@ -569,7 +565,7 @@ __device__ void add_hsp(const Env &E, Mate &m, uint32_t qs, uint32_t dbs, bool P
 }
 
 // State1::AddHSPScan, extendscan.cpp:8-49
-__device__ int add_hsp_scan(const Env &E, Mate &m, uint32_t qs, uint32_t dbs, bool Plus, uint32_t len, int Score) {
+__device__ __noinline__ int add_hsp_scan(const Env &E, Mate &m, uint32_t qs, uint32_t dbs, bool Plus, uint32_t len, int Score) {
     int k = overlaps_hsp(E, m, qs, dbs);
     if (k >= 0) {
         if (Score > (int)m.g->hsp_score[k]) hsp_store(E, m, k, qs, dbs, Plus, len, Score);
@@ -597,7 +593,7 @@ __device__ __noinline__ int extend_apply(const Env &E, Mate &m, uint32_t SeedPos
         stored = add_hit(E, m, DBLo, Plus, Best, nullptr, 0) >= 0;
         return Best;
     }
-    const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * (int)m.QL) / 100.0);
+    const int MinHSPScore = (E.P.MIN_HSP_PCT * (int)m.QL) / 100;   // == int(PCT*QL/100.0), extendpen.cpp:22
     if (Best >= MinHSPScore) {
         add_hsp(E, m, (uint32_t)Start, DBLo + (uint32_t)Start, Plus, (uint32_t)(End - Start + 1), Best);
         return -2;
@@ -611,13 +607,13 @@ __device__ __forceinline__ bool ext_is_noop(const Env &E, uint32_t x, int QL, in
     if (x == EXT_NONE) return true;
     if (ext_nmis(x) * -E.P.MM > MaxPenalty) return true;
     if (ext_start(x) == 0 && ext_end(x) == QL - 1) return false;
-    const int MinHSPScore = (int)((double)(E.P.MIN_HSP_PCT * QL) / 100.0);
+    const int MinHSPScore = (E.P.MIN_HSP_PCT * QL) / 100;   // == int(PCT*QL/100.0), extendpen.cpp:22
     return ext_best(x) < MinHSPScore;
 }
 
 // ExtendPen for a candidate that is not in a seed list (uniform arguments): every lane computes the same pure result.
 __device__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
-    const uint32_t x = pure_ext(E.ix, E.P, m.rv, Plus, SeedPosQ, SeedPosDB, true);
+    const uint32_t x = pure_ext(E.ix, E.P, m.rv, Plus, SeedPosQ, SeedPosDB, true, m.MaxPenalty);
     bool stored;
     return extend_apply(E, m, SeedPosQ, SeedPosDB, Plus, x, stored);
 }
@@ -626,7 +622,7 @@ __device__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t See
 __device__ __forceinline__ bool seed_dead(const Mate &m, int i) { return (m.sd_dead[i >> 5] >> (i & 31)) & 1u; }
 
 // After seed appends: mark the seeds whose extension is a no-op from the start.
-__device__ void seeds_init_dead(const Env &E, Mate &m) {
+__device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m) {
     __syncwarp();
     for (int base = 0; base < m.nSeeds; base += 32) {
         const int i = base + E.lane;
@@ -639,7 +635,7 @@ __device__ void seeds_init_dead(const Env &E, Mate &m) {
 
 // A hit was stored at HitDBLo (and m_MaxPenalty possibly lowered): every seed in the same 64-base bucket now fails
 // OverlapsHit (state1.cpp:230, strand ignored), every seed over the new penalty bound fails the bound.
-__device__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo) {
+__device__ __noinline__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo) {
     const uint32_t key = HitDBLo >> 6;
     for (int base = 0; base < m.nSeeds; base += 32) {
         const int i = base + E.lane;
@@ -655,7 +651,7 @@ __device__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo) {
 }
 
 // ExtendPen(seed i) on the seed's own strand, through the memo.
-__device__ int apply_seed(const Env &E, Mate &m, int i) {
+__device__ __noinline__ int apply_seed(const Env &E, Mate &m, int i) {
     if (seed_dead(m, i)) return -1;
     const uint32_t qs = m.sd_qs[i], db = m.sd_db[i];
     bool stored;
@@ -904,7 +900,7 @@ __device__ __noinline__ float viterbi_warp(const Env &E, const uint8_t *A, uint3
 
 // Flank DP dispatch: the shared-memory trace store holds bands up to tb_stride-2 wide (always true for
 // LB = LA + 2R (+1)); a window clipped by the end of the genome can be wider and then uses the HBM store.
-__device__ float flank_viterbi(const Env &E, const uint8_t *A, uint32_t LA, uint32_t TLo, uint32_t LB, bool Left,
+__device__ __noinline__ float flank_viterbi(const Env &E, const uint8_t *A, uint32_t LA, uint32_t TLo, uint32_t LB, bool Left,
                                bool Right, int &n_rev, int &ovf) {
     uint32_t dlo = min(LA, LB), dhi = max(LA, LB);
     if (dlo > E.P.R) dlo -= E.P.R; else dlo = 1;
@@ -1010,7 +1006,7 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
 __device__ __noinline__ int extend_scan(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
     if (SeedPosDB < SeedPosQ) return -1;
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
-    const uint32_t x = pure_ext(E.ix, E.P, m.rv, Plus, SeedPosQ, SeedPosDB, false);   // left walk adds no penalty (quirk 5)
+    const uint32_t x = pure_ext(E.ix, E.P, m.rv, Plus, SeedPosQ, SeedPosDB, false, m.MaxPenalty);   // left walk adds no penalty (quirk 5)
     if (ext_nmis(x) * -E.P.MM > m.MaxPenalty) return -1;
     const int Best = ext_best(x), Start = ext_start(x), End = ext_end(x);
     const int MinHSPScore = (int)E.ix.word_len * 2;
@@ -1022,7 +1018,7 @@ __device__ __noinline__ int extend_scan(const Env &E, Mate &m, uint32_t SeedPosQ
 }
 
 // State1::CalcMAPQ6, search1m6.cpp:9-33 (fp64, same operation order)
-__device__ uint32_t calc_mapq6(const Mate &m) {
+__device__ __noinline__ uint32_t calc_mapq6(const Mate &m) {
     if (m.HitCount == 0) return 0;
     if (m.Best <= 0) return 0;
     double BestPossible = (double)m.QL;
@@ -1080,7 +1076,7 @@ __device__ __forceinline__ uint64_t m_slot(const Env &E, const Mate &m, int stra
 
 // Lane-local GetRow_Blob (ufindex.cpp:883-943) limited to what the "rows <= 2 now, longer rows later" logic
 // needs: n = 0 (not mine), 1, 2, or 3 meaning "RowLength > 2"; p0/p1 = the first two positions.
-__device__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tally, uint32_t Pos0, uint32_t &n, uint32_t &p0,
+__device__ __noinline__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tally, uint32_t Pos0, uint32_t &n, uint32_t &p0,
                           uint32_t &p1) {
     n = 0; p0 = 0; p1 = 0;
     uint32_t T = Tally, Pos = Pos0, K = 0;
@@ -1111,14 +1107,14 @@ __device__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tally, uint32_t 
 // One item (QPos) per lane: walk the heads of 32 rows and run the pure extension of their candidates in parallel,
 // then visit the items in lane order exactly like the reference's loop body (search1m6.cpp:181-199,
 // search1pepend.cpp:53-68): rows longer than 2 are deferred through `defer`, the others are extended now.
-template <class Defer>
-__device__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint32_t QPos, Defer defer) {
+__device__ __noinline__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint32_t QPos, uint8_t *deflist,
+                                              int &ndef) {
     uint32_t n = 0, p0 = 0, p1 = 0;
     if (valid) row_head3(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), n, p0, p1);
     if (n > E.ix.max_ix) n = E.ix.max_ix;
     uint32_t x0 = EXT_NONE, x1 = EXT_NONE;
-    if (valid && n >= 1 && n <= 2) x0 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p0, true);
-    if (valid && n == 2) x1 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p1, true);
+    if (valid && n >= 1 && n <= 2) x0 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p0, true, m.MaxPenalty);
+    if (valid && n == 2) x1 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p1, true, m.MaxPenalty);
     const bool a0 = !ext_is_noop(E, x0, (int)m.QL, m.MaxPenalty), a1 = !ext_is_noop(E, x1, (int)m.QL, m.MaxPenalty);
     uint32_t vmask = __ballot_sync(FULL, valid && (n > 2 || a0 || a1));
     const uint32_t m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1), big = __ballot_sync(FULL, n > 2);
@@ -1127,7 +1123,11 @@ __device__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint3
         const int b = __ffs(vmask) - 1;
         vmask &= vmask - 1;
         const uint32_t qb = __shfl_sync(FULL, QPos, b);
-        if (big >> b & 1u) { defer(qb); continue; }
+        if (big >> b & 1u) {
+            if (E.lane == 0) deflist[ndef] = (uint8_t)qb;
+            ++ndef;
+            continue;
+        }
         const uint32_t pb0 = __shfl_sync(FULL, p0, b), pb1 = __shfl_sync(FULL, p1, b);
         const uint32_t xb0 = __shfl_sync(FULL, x0, b), xb1 = __shfl_sync(FULL, x1, b);
         if (m0 >> b & 1u) extend_apply(E, m, qb, pb0, s == 0, xb0, stored);
@@ -1136,11 +1136,11 @@ __device__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint3
 }
 
 // A deferred (long) row: full GetRow_Blob, one position per lane, pure extensions in parallel, apply in order.
-__device__ void row_long_stage(const Env &E, Mate &m, int s, uint32_t QPos) {
+__device__ __noinline__ void row_long_stage(const Env &E, Mate &m, int s, uint32_t QPos) {
     uint32_t mypos;
     const uint32_t RowLength = get_row(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
     uint32_t x = EXT_NONE;
-    if ((uint32_t)E.lane < RowLength) x = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, mypos, true);
+    if ((uint32_t)E.lane < RowLength) x = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, mypos, true, m.MaxPenalty);
     uint32_t am = __ballot_sync(FULL, !ext_is_noop(E, x, (int)m.QL, m.MaxPenalty));
     bool stored;
     while (am) {
@@ -1163,7 +1163,7 @@ __device__ void reset_search(const Env &E, Mate &m) {
 }
 
 // State1::Search_Lo, search1m6.cpp:35-277
-__device__ void search_lo(const Env &E, Mate &m) {
+__device__ __noinline__ void search_lo(const Env &E, Mate &m) {
     const uint32_t W = E.ix.word_len;
     const int QL = (int)m.QL;
     if (m.QL < W) { m.Mapq = 0; return; }   // reference underflows: report no hit
@@ -1224,10 +1224,7 @@ __device__ void search_lo(const Env &E, Mate &m) {
             const uint32_t q = q0 + E.lane;
             const uint32_t T = (q < QWC) ? m_tally(m, s, q) : 0;
             const bool cand = (T != T_FREE && T != T_BOTH1 && (T & T_MY_BIT));
-            rows_short_stage(E, m, s, cand, q, [&](uint32_t qd) {
-                if (E.lane == 0) m.g->todo[s][nt] = (uint8_t)qd;
-                ++nt;
-            });
+            rows_short_stage(E, m, s, cand, q, m.g->todo[s], nt);
         }
         nTodo[s] = nt;
     }
@@ -1252,7 +1249,7 @@ __device__ void search_lo(const Env &E, Mate &m) {
 //   minus visit: owned non-BOTH1 slot, except when the plus slot of the same k was just returned -- then only a
 //                BOTH1 slot on the same diagonal is pushed (getseed.cpp:63-85).
 // The lists are only consumed after the seed loop ran to completion, so building them up front is exact.
-__device__ void build_seeds_pe(const Env &E, Mate &m) {
+__device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
     const uint32_t QWC = m.QWC;
     m.nSeeds = 0;
     m.nPend[0] = m.nPend[1] = 0;
@@ -1301,7 +1298,7 @@ __device__ void build_seeds_pe(const Env &E, Mate &m) {
 }
 
 // State1::SearchPE_Pending, search1pepend.cpp:9-130 (k is always UINT_MAX at the call sites)
-__device__ void search_pe_pending(const Env &E, Mate &m) {
+__device__ __noinline__ void search_pe_pending(const Env &E, Mate &m) {
     const int QL = (int)m.QL;
     m.MaxPenalty = E.P.MAXPEN;
     const int MinScorePhase1 = QL + E.P.XP1 * E.P.MM;
@@ -1320,10 +1317,7 @@ __device__ void search_pe_pending(const Env &E, Mate &m) {
             const bool valid = i < m.nPend[s];
             const uint32_t QPos = valid ? m.g->pend[s][i] : 0;
             __syncwarp();   // the list is compacted in place below (nd <= i0 for every write)
-            rows_short_stage(E, m, s, valid, QPos, [&](uint32_t qd) {
-                if (E.lane == 0) m.g->pend[s][nd] = (uint8_t)qd;
-                ++nd;
-            });
+            rows_short_stage(E, m, s, valid, QPos, m.g->pend[s], nd);
             __syncwarp();
         }
         n2[s] = nd;
@@ -1340,7 +1334,7 @@ __device__ void search_pe_pending(const Env &E, Mate &m) {
 
 // State1::ScanSlots, scanslots.cpp:7-62.  Lanes hash 32 window positions at a time; matches against
 // the mate's slots at QPos = 0,27,54,81 are then visited in window order.
-__device__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, uint32_t DBSegLength, bool Plus) {
+__device__ __noinline__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, uint32_t DBSegLength, bool Plus) {
     const uint32_t W = E.ix.word_len;
     if (m.QL <= W * 4) return;
     const int s = Plus ? 0 : 1;
@@ -1418,7 +1412,7 @@ struct PairState {
 };
 
 // State2::FindPairs, state2.cpp:20-85 (only what AdjustTopHitsAndMapqs consumes is kept)
-__device__ void find_pairs(const Env &E, const Mate &F, const Mate &R, PairState &ps) {
+__device__ __noinline__ void find_pairs(const Env &E, const Mate &F, const Mate &R, PairState &ps) {
     const int QL2 = (int)((F.QL + R.QL) / 2);
     ps.BestPairScore = -1;
     ps.SecondBestPairScore = -1;
@@ -1461,7 +1455,7 @@ __device__ void find_pairs(const Env &E, const Mate &F, const Mate &R, PairState
 }
 
 // State2::ScanPair, state2.cpp:87-137 (quirk 6: both window extensions use the forward mate's length)
-__device__ void scan_pair(const Env &E, Mate &F, Mate &R) {
+__device__ __noinline__ void scan_pair(const Env &E, Mate &F, Mate &R) {
     const int HitCountF = F.HitCount, HitCountR = R.HitCount;
     const bool DoVitF = ((int)F.Mapq >= 10), DoVitR = ((int)R.Mapq >= 10);
     const uint32_t QLx = F.QL;
@@ -1501,7 +1495,7 @@ __device__ bool extend_both1_pair(const Env &E, Mate &F, Mate &R, int fi, int ri
 }
 
 // ExtendPen every recorded seed in order (search2m4.cpp:139-153): only seeds that can still do something are visited.
-__device__ void extend_all_seeds(const Env &E, Mate &m) {
+__device__ __noinline__ void extend_all_seeds(const Env &E, Mate &m) {
     for (int w0 = 0; w0 < m.nSeeds; w0 += 32) {
         uint32_t live = ~m.sd_dead[w0 >> 5];
         while (live) {
@@ -1513,7 +1507,7 @@ __device__ void extend_all_seeds(const Env &E, Mate &m) {
 }
 
 // State2::Search4 / Search5, search2m4.cpp:15-187, search2m5.cpp:9-132
-__device__ void search_pair(const Env &E, Mate &F, Mate &R) {
+__device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
     reset_search(E, F);
     reset_search(E, R);
     const uint32_t W = E.ix.word_len;
@@ -1617,7 +1611,7 @@ __device__ void search_pair(const Env &E, Mate &F, Mate &R) {
 }
 
 // ---- result write-back -----------------------------------------------------------------
-__device__ void write_result(const Env &E, const Mate &m, const DevOut &o, uint32_t r) {
+__device__ __noinline__ void write_result(const Env &E, const Mate &m, const DevOut &o, uint32_t r) {
     urmb_result res;
     res.db_pos = 0xFFFFFFFFu;
     res.path_off = 0;
@@ -1661,7 +1655,7 @@ __host__ __device__ inline size_t mate_smem_bytes(uint32_t qcap, uint32_t seqcap
 }
 
 // Stage one read: bytes, reverse complement, packed strands in shared memory; probe results stay in global.
-__device__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevProbe &pr, uint32_t r, uint8_t *sm,
+__device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevProbe &pr, uint32_t r, uint8_t *sm,
                           MateScratch *g) {
     const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(sm);

@@ -493,6 +493,15 @@ __device__ bool overlaps_hit(const Env &E, const Mate &m, uint32_t DBStartPos) {
     return false;
 }
 
+// Lane-local form of OverlapsHit for candidate prechecks: the hit list only grows, so a candidate whose bucket is
+// already taken will still get -1 from ExtendPen whenever the reference reaches it (extendpen.cpp:15-17).
+__device__ __forceinline__ bool overlaps_hit_lane(const Mate &m, uint32_t DBStartPos) {
+    const uint32_t key = DBStartPos >> 6;
+    for (int h = 0; h < m.HitCount; ++h)
+        if ((m.g->hit_pos[h] >> 6) == key) return true;
+    return false;
+}
+
 __device__ int overlaps_hsp(const Env &E, const Mate &m, uint32_t StartPosQ, uint32_t StartPosDB) {  // state1.cpp:241
     const int64_t diag = (int64_t)StartPosDB - (int64_t)StartPosQ;
     for (int base = 0; base < m.HSPCount; base += 32) {
@@ -1113,8 +1122,10 @@ __device__ __noinline__ void rows_short_stage(const Env &E, Mate &m, int s, bool
     if (valid) row_head3(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), n, p0, p1);
     if (n > E.ix.max_ix) n = E.ix.max_ix;
     uint32_t x0 = EXT_NONE, x1 = EXT_NONE;
-    if (valid && n >= 1 && n <= 2) x0 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p0, true, m.MaxPenalty);
-    if (valid && n == 2) x1 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p1, true, m.MaxPenalty);
+    if (valid && n >= 1 && n <= 2 && p0 >= QPos && !overlaps_hit_lane(m, p0 - QPos))
+        x0 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p0, true, m.MaxPenalty);
+    if (valid && n == 2 && p1 >= QPos && !overlaps_hit_lane(m, p1 - QPos))
+        x1 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p1, true, m.MaxPenalty);
     const bool a0 = !ext_is_noop(E, x0, (int)m.QL, m.MaxPenalty), a1 = !ext_is_noop(E, x1, (int)m.QL, m.MaxPenalty);
     uint32_t vmask = __ballot_sync(FULL, valid && (n > 2 || a0 || a1));
     const uint32_t m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1), big = __ballot_sync(FULL, n > 2);
@@ -1135,18 +1146,76 @@ __device__ __noinline__ void rows_short_stage(const Env &E, Mate &m, int s, bool
     }
 }
 
-// A deferred (long) row: full GetRow_Blob, one position per lane, pure extensions in parallel, apply in order.
-__device__ __noinline__ void row_long_stage(const Env &E, Mate &m, int s, uint32_t QPos) {
-    uint32_t mypos;
-    const uint32_t RowLength = get_row(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), mypos);
-    uint32_t x = EXT_NONE;
-    if ((uint32_t)E.lane < RowLength) x = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, mypos, true, m.MaxPenalty);
-    uint32_t am = __ballot_sync(FULL, !ext_is_noop(E, x, (int)m.QL, m.MaxPenalty));
-    bool stored;
-    while (am) {
-        const int r = __ffs(am) - 1;
-        am &= am - 1;
-        extend_apply(E, m, QPos, __shfl_sync(FULL, mypos, r), s == 0, __shfl_sync(FULL, x, r), stored);
+// Lane-local GetRow_Blob (ufindex.cpp:883-943): the whole row into out[0..31]; returns the row length.
+__device__ uint32_t row_walk_lane(const Env &E, uint64_t Slot, uint32_t Tally, uint32_t Pos0, uint32_t *out) {
+    uint32_t T = Tally;
+    if ((T & T_MY_BIT) == 0) return 0;
+    uint64_t Slot2 = Slot;
+    uint32_t Pos = Pos0, K = 0;
+    const uint64_t SC = E.ix.slot_count;
+    for (;;) {
+        if (K > 0) load_blob(E.ix.blob, Slot2, T, Pos);
+        out[K] = Pos;
+        ++K;
+        if (K == E.ix.max_ix) return K;
+        if (T == T_PLUS1 || T == T_BOTH1) return 1;
+        if (T == T_END) return K;
+        if (T == T_LONG_MINE || T == T_LONG_OTHER) {
+            const uint32_t StepA = Pos & 0xffffu, StepB = Pos >> 16;
+            const uint64_t SlotA = add_mod(Slot2, StepA, SC);
+            Slot2 = add_mod(SlotA, StepB, SC);
+            uint32_t ta, pa;
+            load_blob(E.ix.blob, SlotA, ta, pa);
+            out[K - 1] = pa;
+        } else {
+            Slot2 = add_mod(Slot2, T & T_NEXT_MASK, SC);
+        }
+    }
+}
+
+// Deferred (long) rows, search1m6.cpp:205-243 / search1pepend.cpp:89-110: the reference walks one row at a time and
+// extends its positions in order.  Here 32 rows are walked at once (one dependent-gather chain per lane), their
+// candidates are laid out row-major in per-warp scratch, the pure extensions run 32 candidates at a time, and the
+// order-dependent bookkeeping visits the survivors in exactly the reference's order.
+__device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, int s, const uint8_t *list, int n) {
+    uint32_t *stage = reinterpret_cast<uint32_t *>(E.ws->rowM);   // [32 rows][32 positions]
+    uint32_t *fpos = reinterpret_cast<uint32_t *>(E.ws->rowD);    // flat candidate positions (<= 1024)
+    uint8_t *fq = E.ws->tb;                                       // flat candidate QPos
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + E.lane;
+        const bool valid = i < n;
+        const uint32_t QPos = valid ? list[i] : 0u;
+        uint32_t len = 0;
+        if (valid) len = row_walk_lane(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), stage + 32 * E.lane);
+        uint32_t off = len;   // exclusive prefix sum over lanes
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, off, d);
+            if (E.lane >= d) off += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, off, 31);
+        off -= len;
+        for (uint32_t k = 0; k < len; ++k) {
+            fpos[off + k] = stage[32 * E.lane + k];
+            fq[off + k] = (uint8_t)QPos;
+        }
+        __syncwarp();
+        for (uint32_t f0 = 0; f0 < total; f0 += 32) {
+            const uint32_t f = f0 + E.lane;
+            uint32_t x = EXT_NONE, q = 0, pz = 0;
+            if (f < total) {
+                q = fq[f];
+                pz = fpos[f];
+                if (pz >= q && !overlaps_hit_lane(m, pz - q)) x = pure_ext(E.ix, E.P, m.rv, s == 0, q, pz, true, m.MaxPenalty);
+            }
+            uint32_t am = __ballot_sync(FULL, !ext_is_noop(E, x, (int)m.QL, m.MaxPenalty));
+            bool stored;
+            while (am) {
+                const int r = __ffs(am) - 1;
+                am &= am - 1;
+                extend_apply(E, m, __shfl_sync(FULL, q, r), __shfl_sync(FULL, pz, r), s == 0, __shfl_sync(FULL, x, r), stored);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1232,7 +1301,7 @@ __device__ __noinline__ void search_lo(const Env &E, Mate &m) {
     if (m.Best >= MinScorePhase3) { m.Mapq = calc_mapq6(m); return; }
     // phase 5
     for (int s = 0; s < 2; ++s)
-        for (int t = 0; t < nTodo[s]; ++t) row_long_stage(E, m, s, m.g->todo[s][t]);
+        rows_long_batch(E, m, s, m.g->todo[s], nTodo[s]);
     if (m.Best >= MinScorePhase4) { m.Mapq = calc_mapq6(m); return; }
     // phase 6
     for (int i = 0; i < m.HSPCount; ++i) align_hsp(E, m, i);
@@ -1323,7 +1392,7 @@ __device__ __noinline__ void search_pe_pending(const Env &E, Mate &m) {
         n2[s] = nd;
     }
     for (int s = 0; s < 2; ++s)     // pending round 2
-        for (int i = 0; i < n2[s]; ++i) row_long_stage(E, m, s, m.g->pend[s][i]);
+        rows_long_batch(E, m, s, m.g->pend[s], n2[s]);
     const int B = max(m.Best, m.BestHSP) - 8;
     for (int i = 0; i < m.HSPCount; ++i) {
         if ((int)m.g->hsp_score[i] < B) continue;

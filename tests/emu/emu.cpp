@@ -128,7 +128,7 @@ static DevParams emu_make_params(const urmb_params &p) {  // same table as urmb_
 extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t seq_size, uint64_t slot_count,
                        uint32_t word_len, uint32_t max_ix, const urmb_params *p, const uint8_t *seqs,
                        const uint32_t *offs, uint32_t n_units, int paired, urmb_result *res, uint16_t *runs,
-                       uint32_t runs_cap, uint32_t *counters /*[4]*/) {
+                       uint32_t runs_cap, uint32_t *counters /*[8]*/) {
     DevIndex ix;
     ix.blob = blob;
     ix.seq = seq_padded;
@@ -162,8 +162,9 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     std::vector<uint32_t> pos((size_t)nreads * 2 * b.qcap);
     std::vector<uint32_t> ext((size_t)nreads * 2 * b.qcap);
     DevProbe pr{tally.data(), pos.data(), ext.data()};
-    memset(counters, 0, 16);
-    DevOut o{res, runs, runs_cap, counters};
+    memset(counters, 0, 32);
+    std::vector<uint32_t> todo(n_units + 1);
+    DevOut o{res, runs, runs_cap, counters, todo.data()};
     const int nw = 4;
     WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch) * nw);
     memset(ws, 0xEE, sizeof(WarpScratch) * nw);

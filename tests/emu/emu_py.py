@@ -38,7 +38,7 @@ def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, 
     res = np.zeros(nreads, dtype=res_dtype)
     cap = 64 * nreads + 1024
     runs = np.zeros(cap, dtype=np.uint16)
-    counters = np.zeros(4, dtype=np.uint32)
+    counters = np.zeros(8, dtype=np.uint32)
     p = Params(method, pe_method, band_radius, 10)
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     offs = np.ascontiguousarray(offs, dtype=np.uint32)

@@ -141,6 +141,7 @@ struct Slot {
     urmb_result *d_res = nullptr; size_t d_res_cap = 0;
     uint16_t *d_runs = nullptr; size_t d_runs_cap = 0;
     uint32_t *d_counters = nullptr;
+    uint32_t *d_todo = nullptr; size_t d_todo_cap = 0;
     DevBatch batch{};
     size_t seq_bytes = 0;
     bool staged = false, launched = false, downloaded = false;
@@ -221,7 +222,7 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     for (auto &s : c->slots) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h}) CK(cudaEventCreate(ev));
-        CK(cudaMalloc(&s.d_counters, 16));
+        CK(cudaMalloc(&s.d_counters, 32));
         CK(cudaHostAlloc(&s.h_counters, 16, cudaHostAllocDefault));
     }
     *out = c;
@@ -233,7 +234,7 @@ static void free_slot(Slot &s) {
     for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h}) if (ev) cudaEventDestroy(ev);
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext);
-    cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters);
+    cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo);
 }
 
 extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
@@ -468,6 +469,7 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
         s.d_probe_cap = ncap;
     }
     if ((rc = grow_dev(c, s.d_res, s.d_res_cap, (size_t)nreads + 1))) return rc;
+    if ((rc = grow_dev(c, s.d_todo, s.d_todo_cap, (size_t)n + 1))) return rc;
     if ((rc = grow_host(c, s.h_res, s.h_res_cap, (size_t)nreads + 1))) return rc;
     const size_t runs_need = (size_t)nreads * 8 + 4096;
     if ((rc = grow_dev(c, s.d_runs, s.d_runs_cap, runs_need))) return rc;
@@ -488,18 +490,18 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     if (!s.staged) return fail(c, URMB_E_ARG, "slot not staged");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(c->compute, s.ev_h2d, 0));
-    CK(cudaMemsetAsync(s.d_counters, 0, 16, c->compute));
+    CK(cudaMemsetAsync(s.d_counters, 0, 32, c->compute));
     CK(cudaEventRecord(s.ev_k0, c->compute));
     if (s.batch.n_reads) {
         DevProbe pr{s.d_tally, s.d_pos, s.d_ext};
-        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters};
+        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo};
         DevParams P = c->P;
         int e = launch_probe(c->ix, P, s.batch, pr, c->compute, c->sm_count);
         if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
         CK(cudaEventRecord(s.ev_k1, c->compute));
         e = launch_search(c->ix, P, s.batch, pr, o, c->scratch, c->n_scratch_warps, c->compute, c->sm_count, nullptr);
-        if (e) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)e));
-        c->launches += 2;
+        if (e < 0) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)-e));
+        c->launches += 1 + (uint64_t)e;
     } else {
         CK(cudaEventRecord(s.ev_k1, c->compute));
     }

@@ -54,7 +54,8 @@ struct DevOut {
     urmb_result *res;      // [n_reads]
     uint16_t *runs;        // pool
     uint32_t runs_cap;
-    uint32_t *counters;    // [0] runs used, [1] overflow count, [2] work-queue head, [3] spare
+    uint32_t *counters;    // [0] runs used, [1] overflow count, [2] work-queue head, [3] todo count, [4] second-pass head
+    uint32_t *todo;        // [n_units] pairs left for the second pass
 };
 
 struct MateScratch {

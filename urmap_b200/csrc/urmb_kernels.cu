@@ -1575,12 +1575,16 @@ __device__ __noinline__ void extend_all_seeds(const Env &E, Mate &m) {
     }
 }
 
-// State2::Search4 / Search5, search2m4.cpp:15-187, search2m5.cpp:9-132
-__device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
+// State2::Search4 / Search5, search2m4.cpp:15-187, search2m5.cpp:9-132.
+// FAST: only the part every pair goes through (seed pairing, extension of all BOTH1 seeds, the 90 % rule); returns
+// false when the pair needs SearchPE_Pending / pair finding / mate rescue, which the second-pass kernel then runs
+// from scratch on the compacted list of such pairs (the first part is cheap to redo and nothing has to be saved).
+template <bool FAST>
+__device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R) {
     reset_search(E, F);
     reset_search(E, R);
     const uint32_t W = E.ix.word_len;
-    if (F.QL < W || R.QL < W) { F.Mapq = R.Mapq = 0; return; }
+    if (F.QL < W || R.QL < W) { F.Mapq = R.Mapq = 0; return true; }
     const int QLf = (int)F.QL, QLr = (int)R.QL, QL2 = (QLf + QLr) / 2;
     const int TermPairScore = QLf + QLr + 5 * E.P.MM;
     build_seeds_pe(E, F);
@@ -1605,7 +1609,7 @@ __device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
                     const int bit = __ffs(bal) - 1;
                     bal &= bal - 1;
                     int fs;
-                    if (extend_both1_pair(E, F, R, t, base + bit, Plusf, TermPairScore, fs)) return;
+                    if (extend_both1_pair(E, F, R, t, base + bit, Plusf, TermPairScore, fs)) return true;
                     if (fs <= 0) { gone = true; break; }
                 }
             }
@@ -1628,7 +1632,7 @@ __device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
                     const int bit = __ffs(bal) - 1;
                     bal &= bal - 1;
                     int fs;
-                    if (extend_both1_pair(E, F, R, base + bit, t, !Plusr, TermPairScore, fs)) return;
+                    if (extend_both1_pair(E, F, R, base + bit, t, !Plusr, TermPairScore, fs)) return true;
                 }
             }
         }
@@ -1638,9 +1642,10 @@ __device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
     extend_all_seeds(E, R);
 
     if (E.P.pe_method == 5) {
+        if (FAST) return false;
         search_pe_pending(E, F);
         search_pe_pending(E, R);
-        return;
+        return true;
     }
     const int TermF = (QLf * 9) / 10, TermR = (QLr * 9) / 10;
     if (F.Best >= TermF && R.Best >= TermR) {
@@ -1649,9 +1654,10 @@ __device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
         if (d + QL2 <= MAX_TL) {
             F.Mapq = 40;
             R.Mapq = 40;
-            return;
+            return true;
         }
     }
+    if (FAST) return false;
     search_pe_pending(E, F);
     search_pe_pending(E, R);
     PairState ps;
@@ -1664,7 +1670,7 @@ __device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
     if (ps.PairCount == 0) {
         F.Mapq /= 2;
         R.Mapq /= 2;
-        return;
+        return true;
     }
     double Fract = (double)ps.BestPairScore / (double)(QLf + QLr);
     double Drop = (double)(ps.BestPairScore - ps.SecondBestPairScore);
@@ -1677,6 +1683,7 @@ __device__ __noinline__ void search_pair(const Env &E, Mate &F, Mate &R) {
         F.Top = ps.BestF;
         R.Top = ps.BestR;
     }
+    return true;
 }
 
 // ---- result write-back -----------------------------------------------------------------
@@ -1754,6 +1761,9 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
     m.overflow = 0;
 }
 
+// MODE 0: every unit, complete search (single-end).  MODE 1 (paired): every pair, fast part only; pairs that need
+// more are appended to o.todo.  MODE 2 (paired): complete search of the pairs listed in o.todo.
+template <int MODE>
 __device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr,
                                             const DevOut &o, WarpScratch *scratch, uint32_t smem_per_warp,
                                             uint32_t tb_stride, uint32_t tb_rows) {
@@ -1775,13 +1785,15 @@ __device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams 
     E.tb_stride = tb_stride;
     E.tb_rows = tb_rows;
     E.lane = lane;
+    const uint32_t n_work = (MODE == 2) ? o.counters[3] : b.n_units;   // MODE 2 runs after MODE 1 on the same stream
 
     for (;;) {
         uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(&o.counters[2], 1u);
+        if (lane == 0) u = atomicAdd(&o.counters[MODE == 2 ? 4 : 2], 1u);
         u = __shfl_sync(FULL, u, 0);
-        if (u >= b.n_units) break;
-        if (!b.paired) {
+        if (u >= n_work) break;
+        if (MODE == 2) u = o.todo[u];
+        if (MODE == 0) {
             Mate m;
             load_mate(E, m, b, pr, u, sw, &E.ws->m[0]);
             reset_search(E, m);   // State1::Search, search1.cpp:7-24
@@ -1791,20 +1803,34 @@ __device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams 
             Mate F, R;
             load_mate(E, F, b, pr, u, sw, &E.ws->m[0]);
             load_mate(E, R, b, pr, b.n_units + u, sw + msz, &E.ws->m[1]);
-            search_pair(E, F, R);
-            write_result(E, F, o, u);
-            write_result(E, R, o, b.n_units + u);
+            const bool done = search_pair<MODE == 1>(E, F, R);
+            if (done) {
+                write_result(E, F, o, u);
+                write_result(E, R, o, b.n_units + u);
+            } else if (lane == 0) {
+                o.todo[atomicAdd(&o.counters[3], 1u)] = u;
+            }
         }
         __syncwarp();
     }
 }
 
-// Two register budgets of the same body: MINB = 4 blocks/SM (<=128 regs) or 3 blocks/SM (<=168 regs).
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) search_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
-                                                       WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
-                                                       uint32_t tb_rows) {
-    search_body(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
+// SE: one kernel.  PE: pair_kernel (MODE 1, small code, every pair) then search_kernel<2> (the rest of the reference's
+// control flow, only for the pairs that need it).
+__global__ void __launch_bounds__(128, 4) search_kernel_se(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
+                                                           WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
+                                                           uint32_t tb_rows) {
+    search_body<0>(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
+}
+__global__ void __launch_bounds__(128, 4) pair_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
+                                                      WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
+                                                      uint32_t tb_rows) {
+    search_body<1>(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
+}
+__global__ void __launch_bounds__(128, 4) search_kernel_pe(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
+                                                           WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
+                                                           uint32_t tb_rows) {
+    search_body<2>(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
 }
 
 // =====================================================================================
@@ -1843,21 +1869,15 @@ int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, cons
     return (int)cudaGetLastError();
 }
 
-int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
-                  WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used) {
+template <class K>
+static int launch_one(K kern, const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                      WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used) {
     const int wpb = 4;
     const size_t spw = search_smem_per_warp(b, P);
     const size_t smem = spw * wpb;
-    const bool lowreg = !(P.flags & 8u);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(search_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int per_sm = 0;
-    if (lowreg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<4>, wpb * 32, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<3>, wpb * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem);
     if (per_sm < 1) per_sm = 1;
     int blocks = sm_count * per_sm;
     if (blocks * wpb > n_scratch_warps) blocks = n_scratch_warps / wpb;
@@ -1866,14 +1886,21 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     if (blocks < 1) blocks = 1;
     if (warps_used) *warps_used = blocks * wpb;
     const uint32_t rows = b.seqcap + 2;
-    if (lowreg) {
-        URMB_LAUNCH(search_kernel<4>, blocks, wpb * 32, smem, stream, ix, P, b, pr, o, scratch, (uint32_t)spw,
-                    tb_stride_for(P), rows);
-    } else {
-        URMB_LAUNCH(search_kernel<3>, blocks, wpb * 32, smem, stream, ix, P, b, pr, o, scratch, (uint32_t)spw,
-                    tb_stride_for(P), rows);
-    }
+    URMB_LAUNCH(kern, blocks, wpb * 32, smem, stream, ix, P, b, pr, o, scratch, (uint32_t)spw, tb_stride_for(P), rows);
     return (int)cudaGetLastError();
+}
+
+// Returns the number of kernels launched (1 single-end, 2 paired-end) or a negative cudaError.
+int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                  WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used) {
+    if (!b.paired) {
+        int e = launch_one(search_kernel_se, ix, P, b, pr, o, scratch, n_scratch_warps, stream, sm_count, warps_used);
+        return e ? -e : 1;
+    }
+    int e = launch_one(pair_kernel, ix, P, b, pr, o, scratch, n_scratch_warps, stream, sm_count, warps_used);
+    if (e) return -e;
+    e = launch_one(search_kernel_pe, ix, P, b, pr, o, scratch, n_scratch_warps, stream, sm_count, warps_used);
+    return e ? -e : 2;
 }
 
 }  // namespace urmb

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <ucontext.h>
 
 #include <algorithm>
@@ -39,7 +40,7 @@ template <class F> inline int cudaFuncSetAttribute(F, int, int) { return 0; }
 template <class F> inline int cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return 0; }
 
 namespace emu {
-enum Kind { K_NONE, K_SHFL, K_SHFL_UP, K_BALLOT, K_ANY, K_SYNC };
+enum Kind { K_NONE, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_BALLOT, K_ANY, K_SYNC };
 uint64_t collective(Kind kind, uint64_t value, int arg, int site);
 uint8_t *smem_base();
 void launch(const std::function<void()> &body, int grid, int block, size_t smem);
@@ -60,11 +61,15 @@ template <class T> inline T emu_shfl(T v, int src, int line) {
 template <class T> inline T emu_shfl_up(T v, unsigned delta, int line) {
     return emu_unbits<T>(emu::collective(emu::K_SHFL_UP, emu_bits(v), (int)delta, line));
 }
+template <class T> inline T emu_shfl_down(T v, unsigned delta, int line) {
+    return emu_unbits<T>(emu::collective(emu::K_SHFL_DOWN, emu_bits(v), (int)delta, line));
+}
 inline unsigned emu_ballot(int pred, int line) { return (unsigned)emu::collective(emu::K_BALLOT, pred ? 1 : 0, 0, line); }
 inline int emu_any(int pred, int line) { return (int)emu::collective(emu::K_ANY, pred ? 1 : 0, 0, line); }
 inline void emu_syncwarp(int line) { emu::collective(emu::K_SYNC, 0, 0, line); }
 #define __shfl_sync(m, v, l) emu_shfl((v), (l), __LINE__)
 #define __shfl_up_sync(m, v, d) emu_shfl_up((v), (d), __LINE__)
+#define __shfl_down_sync(m, v, d) emu_shfl_down((v), (d), __LINE__)
 #define __ballot_sync(m, p) emu_ballot((p), __LINE__)
 #define __any_sync(m, p) emu_any((p), __LINE__)
 #define __syncwarp() emu_syncwarp(__LINE__)

@@ -223,7 +223,7 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h}) CK(cudaEventCreate(ev));
         CK(cudaMalloc(&s.d_counters, 32));
-        CK(cudaHostAlloc(&s.h_counters, 16, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&s.h_counters, 32, cudaHostAllocDefault));
     }
     *out = c;
     return URMB_OK;
@@ -517,7 +517,7 @@ extern "C" int urmb_download(urmb_ctx *c, int si) {
     if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(s.copy, s.ev_k2, 0));
-    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, 16, cudaMemcpyDeviceToHost, s.copy));
+    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, s.copy));
     CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.batch.n_reads * sizeof(urmb_result), cudaMemcpyDeviceToHost, s.copy));
     // Paths are few and short: copy the whole pool prefix a typical batch uses, the rest on demand in wait.
     s.downloaded = true;
@@ -559,6 +559,7 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
     }
     CK(cudaEventRecord(s.ev_d2h, s.copy));
     CK(cudaStreamSynchronize(s.copy));
+    if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u path runs\n", si, s.batch.n_units, s.h_counters[3], used);
     if (res1) *res1 = s.h_res;
     if (res2) *res2 = s.batch.paired ? s.h_res + s.batch.n_units : nullptr;
     if (runs) *runs = s.h_runs;

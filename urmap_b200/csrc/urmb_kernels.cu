@@ -907,16 +907,200 @@ __device__ __noinline__ float viterbi_warp(const Env &E, const uint8_t *A, uint3
     return Score;
 }
 
-// Flank DP dispatch: the shared-memory trace store holds bands up to tb_stride-2 wide (always true for
-// LB = LA + 2R (+1)); a window clipped by the end of the genome can be wider and then uses the HBM store.
+// Flank DP (AlignHSP): State1::Viterbi (viterbi.cpp:11-261) + TraceBackBitMem with the BAND across the lanes.
+// Band coordinate c = j - (dlo + i - LA) in [0, BW), BW = dhi - dlo + 1 <= 64; lane l owns c = 2l and 2l+1.  Going
+// from row i-1 to row i the band slides one column to the right, so for cell (i, j) at coordinate c:
+//     M(i-1, j-1)  is the previous row's value at the SAME coordinate (a register, no shuffle);
+//     D(i-1, j)    is the previous row's value at coordinate c+1 (own register or one shuffle);
+//     the I chain  I0 <- max(I0 + ext, M0 + open) only depends on the previous row, i.e. it is a max-plus prefix
+//                  scan over c: with U_c = I_out(c) - c*ext and V_c = M0(c) + open - c*ext, U_c = max(U_{c-1}, V_c);
+//                  the reference's ">= favours open" tie is V_c >= U_{c-1}.  All finite values are small integers
+//                  and NEG + k == NEG in fp32, so the scan reproduces the sequential floats bit for bit.
+// Rows are sequential (LA <= 126 steps of ~100 instructions) and no lane idles in a wavefront ramp.
+// Trace bits: one byte per lane per row (two nibbles) in shared memory, TB[i][LB] and row LA kept separately,
+// TB[i][Startj-1] = IM (viterbi.cpp:119) answered on the fly.
+__device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB,
+                                           bool Left, bool Right, int &n_rev, int &ovf) {
+    const int lane = E.lane;
+    uint16_t *rev = E.ws->runs_a;
+    n_rev = 0;
+    const float GO = (float)E.P.GO, GE = (float)E.P.GE, MMs = (float)E.P.MM;
+    uint32_t dlo = min(LA, LB), dhi = max(LA, LB);
+    if (dlo > E.P.R) dlo -= E.P.R; else dlo = 1;
+    dhi += E.P.R;
+    if (dhi > LA + LB - 1) dhi = LA + LB - 1;
+    const int BW = (int)(dhi - dlo) + 1;
+    uint8_t *tb = E.s_tb;
+    uint8_t *collb = tb + (size_t)E.tb_rows * 32;
+    uint8_t *rowla = collb + E.tb_rows;
+    const int c0 = 2 * lane, c1 = c0 + 1;
+    float pM0 = NEG_INF, pM1 = NEG_INF, pD0 = NEG_INF, pD1 = NEG_INF;   // previous row at my coordinates
+    float DLB = NEG_INF;                                                 // Drow[LB]
+#pragma unroll 1
+    for (uint32_t i = 0; i < LA; ++i) {
+        const int j0 = (int)dlo + (int)i - (int)LA;
+        const int ja = j0 + c0, jb = ja + 1;
+        const bool ina = c0 < BW && ja >= 0 && ja < (int)LB, inb = c1 < BW && jb >= 0 && jb < (int)LB;
+        const uint32_t a = A[i];
+        const bool free0 = Left && i == 0;
+        const float openA = free0 ? 0.0f : GO, nextA = free0 ? 0.0f : -GE;   // nextA = -extA >= 0
+        const float M0a = (ja == 0) ? ((i == 0) ? 0.0f : NEG_INF) : pM0;
+        const float M0b = (jb == 0) ? ((i == 0) ? 0.0f : NEG_INF) : pM1;
+        float upDb = __shfl_down_sync(FULL, pD0, 1);
+        if (lane == 31) upDb = NEG_INF;
+        const float upDa = pD1;
+        // Drow[LB] (viterbi.cpp:187-200): M0 after the row loop is the previous row's M at column Endj-1
+        {
+            float M0e = NEG_INF;
+            const int e = (int)LB - j0;   // previous-row coordinate of column Endj-1 when the band is clipped at LB
+            if (e >= 0 && e < BW) {
+                const float t0 = __shfl_sync(FULL, pM0, e >> 1), t1 = __shfl_sync(FULL, pM1, e >> 1);
+                M0e = (e & 1) ? t1 : t0;
+            }
+            const float md = M0e + GO;
+            DLB += GE;
+            uint8_t t = 0;
+            if (md >= DLB) { DLB = md; t = TB_MD; }
+            if (lane == 0) collb[i] = t;
+        }
+        // I chain: prefix max of V over the band
+        const float Va = ina ? (M0a + openA) + (float)c0 * nextA : NEG_INF;
+        const float Vb = inb ? (M0b + openA) + (float)c1 * nextA : NEG_INF;
+        float inc = fmaxf(Va, Vb);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float t = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc = fmaxf(inc, t);
+        }
+        float Ua = __shfl_up_sync(FULL, inc, 1);   // U_{c0-1}
+        if (lane == 0) Ua = NEG_INF;
+        const float Ub = fmaxf(Ua, Va);            // U_{c1-1}
+        const float Ia = Ua - (float)(c0 - 1) * nextA, Ib = Ub - (float)(c1 - 1) * nextA;
+        float Ma = NEG_INF, Mb = NEG_INF, Da = NEG_INF, Db = NEG_INF;
+        uint32_t bits = 0;
+        if (ina) {
+            uint32_t t = 0;
+            float xM = M0a;
+            if (upDa > xM) { xM = upDa; t = TB_DM; }
+            if (Ia > xM) { xM = Ia; t = TB_IM; }
+            Ma = xM + ((a == (uint32_t)B[ja]) ? 1.0f : MMs);
+            const bool freeB = (ja == 0) && Left;
+            const float md = M0a + (freeB ? 0.0f : GO);
+            float d = upDa + (freeB ? 0.0f : GE);
+            if (md >= d) { d = md; t |= TB_MD; }
+            Da = d;
+            if (Va >= Ua) t |= TB_MI;
+            bits = t;
+        }
+        if (inb) {
+            uint32_t t = 0;
+            float xM = M0b;
+            if (upDb > xM) { xM = upDb; t = TB_DM; }
+            if (Ib > xM) { xM = Ib; t = TB_IM; }
+            Mb = xM + ((a == (uint32_t)B[jb]) ? 1.0f : MMs);
+            const float md = M0b + GO;   // jb >= 1: never the free column
+            float d = upDb + GE;
+            if (md >= d) { d = md; t |= TB_MD; }
+            Db = d;
+            if (Vb >= Ub) t |= TB_MI;
+            bits |= t << 4;
+        }
+        tb[i * 32 + lane] = (uint8_t)bits;
+        pM0 = Ma; pM1 = Mb; pD0 = Da; pD1 = Db;
+    }
+    // last row of DPI, viterbi.cpp:207-236 (strict >): chain over M(LA-1, j-1), j in [Startj, LB)
+    const int j0f = (int)dlo - 1;   // column of coordinate 0 in row LA-1
+    float I1;
+    {
+        const float gop = Right ? 0.0f : GO, ngex = Right ? 0.0f : -GE;
+        const int ja = j0f + c0, jb = ja + 1;
+        const bool ina = c0 < BW && ja >= 0 && ja < (int)LB, inb = c1 < BW && jb >= 0 && jb < (int)LB;
+        float Mla = __shfl_up_sync(FULL, pM1, 1);   // M at coordinate c0-1
+        if (lane == 0) Mla = NEG_INF;
+        const float Mlb = pM0;
+        const float Va = ina ? (Mla + gop) + (float)c0 * ngex : NEG_INF;
+        const float Vb = inb ? (Mlb + gop) + (float)c1 * ngex : NEG_INF;
+        float inc = fmaxf(Va, Vb);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float t = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc = fmaxf(inc, t);
+        }
+        float Ua = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) Ua = NEG_INF;
+        const float Ub = fmaxf(Ua, Va);
+        rowla[c0] = (ina && Va > Ua) ? TB_MI : 0;
+        rowla[c1] = (inb && Vb > Ub) ? TB_MI : 0;
+        const float tot = __shfl_sync(FULL, inc, 31);
+        I1 = tot - (float)((int)LB - 1 - j0f) * ngex;
+    }
+    __syncwarp();
+    float Score;
+    {
+        const int cf = (int)LB - 1 - j0f;   // coordinate of column LB-1 in the last row
+        const float t0 = __shfl_sync(FULL, pM0, (cf >> 1) & 31), t1 = __shfl_sync(FULL, pM1, (cf >> 1) & 31);
+        Score = (cf >= 0 && cf < BW) ? ((cf & 1) ? t1 : t0) : NEG_INF;
+    }
+    int State = 0;  // 0 M, 1 D, 2 I
+    if (DLB > Score) { Score = DLB; State = 1; }
+    if (I1 > Score) { Score = I1; State = 2; }
+
+    // traceback (uniform across lanes), tracebackbitmem.cpp:22-73
+    auto get = [&](uint32_t i, uint32_t j) -> uint32_t {
+        if (i == LA) {
+            const int c = (int)j - j0f;
+            return (c >= 0 && c < BW) ? rowla[c] : 0u;
+        }
+        if (j == LB) return collb[i];
+        const int jz = (int)dlo + (int)i - (int)LA;
+        const int c = (int)j - jz;
+        if (c == -1) return (jz > 0) ? (uint32_t)TB_IM : 0u;   // TB[i][Startj-1] = IM, viterbi.cpp:119
+        if (c < 0 || c >= BW) return 0u;
+        return ((uint32_t)tb[i * 32 + (c >> 1)] >> ((c & 1) * 4)) & 0xFu;
+    };
+    uint32_t ti = LA, tj = LB;
+    uint32_t curop = (uint32_t)State, curlen = 0;
+#pragma unroll 1
+    for (;;) {
+        if (ti == 0 && tj == 0) break;
+        if ((uint32_t)State == curop) ++curlen;
+        else {
+            runs_append(rev, n_rev, curop, curlen, kRunCap, ovf, lane);
+            curop = (uint32_t)State;
+            curlen = 1;
+        }
+        uint32_t t;
+        if (State == 0) {
+            if (ti == 0 || tj == 0) break;
+            t = get(ti - 1, tj - 1);
+            State = (t & TB_DM) ? 1 : ((t & TB_IM) ? 2 : 0);
+            --ti; --tj;
+        } else if (State == 1) {
+            if (ti == 0) break;
+            t = get(ti - 1, tj);
+            State = (t & TB_MD) ? 0 : 1;
+            --ti;
+        } else {
+            if (tj == 0) break;
+            t = get(ti, tj - 1);
+            State = (t & TB_MI) ? 0 : 2;
+            --tj;
+        }
+    }
+    runs_append(rev, n_rev, curop, curlen, kRunCap, ovf, lane);
+    return Score;
+}
+
+// Flank DP dispatch: bands up to 64 wide (always true for LB = LA + 2R (+1), R <= 12) run with the band across the
+// lanes and trace bits in shared memory; anything else (never seen from AlignHSP) takes the row-block kernel.
 __device__ __noinline__ float flank_viterbi(const Env &E, const uint8_t *A, uint32_t LA, uint32_t TLo, uint32_t LB, bool Left,
                                bool Right, int &n_rev, int &ovf) {
     uint32_t dlo = min(LA, LB), dhi = max(LA, LB);
     if (dlo > E.P.R) dlo -= E.P.R; else dlo = 1;
     dhi += E.P.R;
     if (LA + LB >= 1 && dhi > LA + LB - 1) dhi = LA + LB - 1;
-    const bool fits = (LA + 1 <= E.tb_rows) && (dhi - dlo + 3 <= E.tb_stride) && (LA > 0) && (LB > 0);
-    if (fits) return viterbi_warp<false>(E, A, LA, E.s_win, LB, Left, Right, n_rev, ovf);
+    const bool fits = (LA + 1 <= E.tb_rows) && (dhi - dlo + 1 <= 64) && (LA > 0) && (LB > 0);
+    if (fits) return viterbi_band(E, A, LA, E.s_win, LB, Left, Right, n_rev, ovf);
     return viterbi_warp<true>(E, A, LA, E.ix.seq + TLo, LB, Left, Right, n_rev, ovf);
 }
 
@@ -1843,7 +2027,7 @@ size_t search_smem_per_warp(const DevBatch &b, const DevParams &P) {
     size_t s = (size_t)nm * ((mate_smem_bytes(b.qcap, b.seqcap) + 15) & ~(size_t)15);
     s += b.seqcap + 64;
     const uint32_t rows = b.seqcap + 2;
-    s += (size_t)rows * (tb_stride_for(P) / 2) + rows + tb_stride_for(P);   // nibble rows + column LB + row LA
+    s += (size_t)rows * 32 + rows + 66;   // band trace bytes (2 nibbles per lane per row) + column LB + row LA
     return (s + 15) & ~(size_t)15;
 }
 

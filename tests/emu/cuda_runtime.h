@@ -27,6 +27,7 @@
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __align__(n)
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };

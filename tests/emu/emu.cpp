@@ -163,16 +163,25 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     std::vector<uint32_t> pos((size_t)nreads * 2 * b.qcap);
     std::vector<uint32_t> ext((size_t)nreads * 2 * b.qcap);
     DevProbe pr{tally.data(), pos.data(), ext.data()};
-    memset(counters, 0, 32);
-    std::vector<uint32_t> todo(n_units + 1);
-    DevOut o{res, runs, runs_cap, counters, todo.data()};
+    uint32_t ct[CT_COUNT];
+    memset(ct, 0, sizeof ct);
+    std::vector<uint32_t> todo(n_units + 1), rescue(n_units + 1);
+    DevOut o{res, runs, runs_cap, ct, todo.data(), rescue.data()};
     const int nw = 4;
     WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch) * nw);
     memset(ws, 0xEE, sizeof(WarpScratch) * nw);
+    // a small odd chunk so that several chunks and a ragged last one are exercised
+    uint32_t chunk = 37;
+    if (const char *f = getenv("URMB_CHUNK_PAIRS")) chunk = (uint32_t)strtoul(f, nullptr, 0);
+    MateSave *pool = (MateSave *)malloc(sizeof(MateSave) * 2 * chunk);
+    memset(pool, 0xEE, sizeof(MateSave) * 2 * chunk);
+    SearchRes R{ws, nw, pool, chunk};
     launch_probe(ix, P, b, pr, nullptr, 1);
-    launch_search(ix, P, b, pr, o, ws, nw, nullptr, 1, nullptr);
+    const int nk = launch_search(ix, P, b, pr, o, R, nullptr, 1, nullptr);
     free(ws);
-    return 0;
+    free(pool);
+    memcpy(counters, ct, 32);
+    return nk < 0 ? nk : 0;
 }
 
 // Device index builder under emulation (scan passes done on the host: they use __syncthreads).

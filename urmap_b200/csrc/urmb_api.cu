@@ -142,6 +142,7 @@ struct Slot {
     uint16_t *d_runs = nullptr; size_t d_runs_cap = 0;
     uint32_t *d_counters = nullptr;
     uint32_t *d_todo = nullptr; size_t d_todo_cap = 0;
+    uint32_t *d_rescue = nullptr; size_t d_rescue_cap = 0;
     DevBatch batch{};
     size_t seq_bytes = 0;
     bool staged = false, launched = false, downloaded = false;
@@ -160,6 +161,9 @@ struct urmb_ctx {
     cudaStream_t compute = nullptr;
     WarpScratch *scratch = nullptr;
     int n_scratch_warps = 0;
+    MateSave *pool = nullptr;      // saved mate states of one chunk of the paired-end second pass (2 per pair)
+    size_t pool_pairs = 0;
+    uint32_t chunk_pairs = 262144; // URMB_CHUNK_PAIRS
     Slot slots[URMB_SLOTS];
     uint64_t launches = 0;
     std::string err;
@@ -217,13 +221,14 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
-    c->n_scratch_warps = c->sm_count * 24;
+    c->n_scratch_warps = max_search_warps(c->sm_count);
+    if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
     for (auto &s : c->slots) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h}) CK(cudaEventCreate(ev));
-        CK(cudaMalloc(&s.d_counters, 32));
-        CK(cudaHostAlloc(&s.h_counters, 32, cudaHostAllocDefault));
+        CK(cudaMalloc(&s.d_counters, CT_COUNT * sizeof(uint32_t)));
+        CK(cudaHostAlloc(&s.h_counters, CT_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
     }
     *out = c;
     return URMB_OK;
@@ -234,7 +239,7 @@ static void free_slot(Slot &s) {
     for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h}) if (ev) cudaEventDestroy(ev);
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext);
-    cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo);
+    cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo); cudaFree(s.d_rescue);
 }
 
 extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
@@ -244,6 +249,7 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     for (auto &s : c->slots) free_slot(s);
     if (c->compute) cudaStreamDestroy(c->compute);
     cudaFree(c->scratch);
+    cudaFree(c->pool);
     cudaFree(c->own_blob);
     cudaFree(c->own_seq);
     cudaFree(c->seq2);
@@ -470,6 +476,18 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     }
     if ((rc = grow_dev(c, s.d_res, s.d_res_cap, (size_t)nreads + 1))) return rc;
     if ((rc = grow_dev(c, s.d_todo, s.d_todo_cap, (size_t)n + 1))) return rc;
+    if ((rc = grow_dev(c, s.d_rescue, s.d_rescue_cap, (size_t)n + 1))) return rc;
+    if (r2) {   // pool of saved mate states, shared by the slots (their kernels are serialised on the compute stream)
+        const size_t want = std::min<size_t>(std::max<size_t>(n, 1), c->chunk_pairs);
+        if (want > c->pool_pairs) {
+            CK(cudaStreamSynchronize(c->compute));
+            cudaFree(c->pool);
+            c->pool = nullptr;
+            c->pool_pairs = 0;
+            CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
+            c->pool_pairs = want;
+        }
+    }
     if ((rc = grow_host(c, s.h_res, s.h_res_cap, (size_t)nreads + 1))) return rc;
     const size_t runs_need = (size_t)nreads * 8 + 4096;
     if ((rc = grow_dev(c, s.d_runs, s.d_runs_cap, runs_need))) return rc;
@@ -490,16 +508,17 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     if (!s.staged) return fail(c, URMB_E_ARG, "slot not staged");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(c->compute, s.ev_h2d, 0));
-    CK(cudaMemsetAsync(s.d_counters, 0, 32, c->compute));
+    CK(cudaMemsetAsync(s.d_counters, 0, CT_COUNT * sizeof(uint32_t), c->compute));
     CK(cudaEventRecord(s.ev_k0, c->compute));
     if (s.batch.n_reads) {
         DevProbe pr{s.d_tally, s.d_pos, s.d_ext};
-        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo};
+        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue};
+        SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
         int e = launch_probe(c->ix, P, s.batch, pr, c->compute, c->sm_count);
         if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
         CK(cudaEventRecord(s.ev_k1, c->compute));
-        e = launch_search(c->ix, P, s.batch, pr, o, c->scratch, c->n_scratch_warps, c->compute, c->sm_count, nullptr);
+        e = launch_search(c->ix, P, s.batch, pr, o, R, c->compute, c->sm_count, nullptr);
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)-e));
         c->launches += 1 + (uint64_t)e;
     } else {
@@ -517,7 +536,7 @@ extern "C" int urmb_download(urmb_ctx *c, int si) {
     if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(s.copy, s.ev_k2, 0));
-    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, 32, cudaMemcpyDeviceToHost, s.copy));
+    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, CT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.copy));
     CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.batch.n_reads * sizeof(urmb_result), cudaMemcpyDeviceToHost, s.copy));
     // Paths are few and short: copy the whole pool prefix a typical batch uses, the rest on demand in wait.
     s.downloaded = true;
@@ -559,7 +578,7 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
     }
     CK(cudaEventRecord(s.ev_d2h, s.copy));
     CK(cudaStreamSynchronize(s.copy));
-    if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u path runs\n", si, s.batch.n_units, s.h_counters[3], used);
+    if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u rescued, %u path runs\n", si, s.batch.n_units, s.h_counters[CT_TODO_TOTAL], s.h_counters[CT_RESCUE], used);
     if (res1) *res1 = s.h_res;
     if (res2) *res2 = s.batch.paired ? s.h_res + s.batch.n_units : nullptr;
     if (runs) *runs = s.h_runs;

@@ -50,20 +50,39 @@ struct DevProbe {   // output of the probe+extend kernel, [n_reads][2 strands][q
     uint32_t *ext;     // BOTH1 slots: packed state-independent result of the gapless extension (EXT_NONE otherwise)
 };
 
+// Device counters of one batch slot (u32 each).  CT_RUNS / CT_OVERFLOW / CT_*_TOTAL live for the whole batch; the
+// others are per chunk and are zeroed by the launcher between chunks.
+enum {
+    CT_RUNS = 0,        // path runs used in DevOut::runs
+    CT_OVERFLOW = 1,    // reads that exceeded a per-read capacity
+    CT_RESCUE = 2,      // pairs queued for the mate-rescue kernel (whole batch)
+    CT_RESCUE_HEAD = 3, // work-queue head of the mate-rescue kernel
+    CT_TODO_TOTAL = 4,  // pairs that went through the staged second pass (whole batch, statistics)
+    CT_CHUNK0 = 8,      // first per-chunk counter
+    CT_HEAD = 8,        // work-queue head of the first-pass kernel
+    CT_TODO = 9,        // pairs of this chunk saved for the staged second pass
+    CT_STAGE_A = 10, CT_STAGE_B = 11, CT_STAGE_C = 12, CT_FINISH = 13,   // work-queue heads of the stage kernels
+    CT_COUNT = 16
+};
+
 struct DevOut {
     urmb_result *res;      // [n_reads]
     uint16_t *runs;        // pool
     uint32_t runs_cap;
-    uint32_t *counters;    // [0] runs used, [1] overflow count, [2] work-queue head, [3] todo count, [4] second-pass head
-    uint32_t *todo;        // [n_units] pairs left for the second pass
+    uint32_t *counters;    // [CT_COUNT]
+    uint32_t *todo;        // [chunk pairs] pairs of the current chunk saved for the staged second pass
+    uint32_t *rescue;      // [n_units] pairs that need mate rescue (State2::ScanPair)
 };
+
+constexpr int kRunPool = 2048;  // path runs of all hits of one mate
 
 struct MateScratch {
     uint32_t hit_pos[kHitCap];
     int16_t hit_score[kHitCap];
     uint8_t hit_plus[kHitCap];
     uint8_t hit_nruns[kHitCap];
-    uint16_t hit_runs[kHitCap][kRunCap];
+    uint16_t hit_roff[kHitCap];     // first run of the hit's path in runs_pool
+    uint16_t runs_pool[kRunPool];
     uint32_t hsp_dbstart[kHspCap];
     uint16_t hsp_qstart[kHspCap];
     uint16_t hsp_len[kHspCap];
@@ -71,6 +90,20 @@ struct MateScratch {
     uint8_t hsp_flags[kHspCap];   // bit0 plus, bit1 aligned
     uint8_t pend[2][kMaxLen];     // m_QPosPendingVec_{Plus,Minus} (bytes, state1.h:86)
     uint8_t todo[2][kMaxLen];     // phase-5 todo lists (search1m6.cpp:170,205)
+};
+
+// Per-mate search state that survives between the stage kernels of the paired-end second pass.
+struct MateHdr {
+    int32_t HitCount, HSPCount, Top, MaxPenalty, Best, Second, BestHSP, nRuns;
+    uint32_t Mapq;
+    int32_t nPend[2];
+    int32_t overflow;
+    int32_t done;      // SearchPE_Pending has finished for this mate (Mapq is final)
+    int32_t pad[3];
+};
+struct MateSave {
+    MateHdr h;
+    MateScratch s;
 };
 
 struct WarpScratch {
@@ -90,10 +123,16 @@ struct LaunchCfg {
 };
 
 // implemented in urmb_kernels.cu
-size_t search_smem_per_warp(const DevBatch &b, const DevParams &P);
 int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count);
+// Per-context resources of the search kernels: per-warp scratch and the pool of saved mate states (2 per pair of a chunk).
+struct SearchRes {
+    WarpScratch *scratch;
+    int n_scratch_warps;
+    MateSave *pool;
+    uint32_t pool_pairs;   // chunk size of the paired-end second pass
+};
 int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
-                  WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used);
+                  const SearchRes &R, void *stream, int sm_count, int *warps_used);
 int max_search_warps(int sm_count);
 // n_bytes = seq_data_size + URMB_SEQ_PAD; seq2 holds n_bytes/32+2 words, seqx n_bytes/32+2 words
 size_t packed_words(size_t n_bytes);

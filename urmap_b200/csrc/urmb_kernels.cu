@@ -455,6 +455,7 @@ struct Mate {
     MateScratch *g;
     uint32_t QL, QWC, qcap;
     int HitCount, HSPCount, Top, MaxPenalty, Best, Second, BestHSP;
+    int nRuns;              // used part of g->runs_pool
     uint32_t Mapq;
     int nPend[2];
     int overflow;
@@ -524,13 +525,15 @@ __device__ __noinline__ int add_hit(const Env &E, Mate &m, uint32_t StartPosDB, 
     int idx = m.HitCount;
     if (idx >= kHitCap) { m.overflow = 1; return -1; }
     if (nruns > kRunCap) { m.overflow = 1; nruns = kRunCap; }
+    if (m.nRuns + nruns > kRunPool) { m.overflow = 1; nruns = 0; }
     if (E.lane == 0) {
         m.g->hit_pos[idx] = StartPosDB;
         m.g->hit_score[idx] = (int16_t)Score;
         m.g->hit_plus[idx] = Plus ? 1 : 0;
         m.g->hit_nruns[idx] = (uint8_t)nruns;
+        m.g->hit_roff[idx] = (uint16_t)m.nRuns;
     }
-    for (int i = E.lane; i < nruns; i += 32) m.g->hit_runs[idx][i] = runs[i];
+    for (int i = E.lane; i < nruns; i += 32) m.g->runs_pool[m.nRuns + i] = runs[i];
     __syncwarp();
     if (Score > m.Best) {
         m.Second = m.Best;
@@ -539,10 +542,11 @@ __device__ __noinline__ int add_hit(const Env &E, Mate &m, uint32_t StartPosDB, 
     } else if (Score == m.Best)
         m.Second = Score;
     else {
-        if (Score < m.Best - SECONDARY_HIT_MAX_DELTA) return -1;
+        if (Score < m.Best - SECONDARY_HIT_MAX_DELTA) return -1;   // the record stays uncommitted
         if (Score > m.Second) m.Second = Score;
     }
     ++m.HitCount;
+    m.nRuns += nruns;
     return idx;
 }
 
@@ -1410,6 +1414,7 @@ __device__ void reset_search(const Env &E, Mate &m) {
     m.Best = 0;
     m.Second = 0;
     m.BestHSP = 0;
+    m.nRuns = 0;
     m.Mapq = 0xFFFFFFFFu;
     m.MaxPenalty = E.P.MAXPEN;
     m.nPend[0] = m.nPend[1] = 0;
@@ -1551,17 +1556,25 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
 }
 
 // State1::SearchPE_Pending, search1pepend.cpp:9-130 (k is always UINT_MAX at the call sites)
-__device__ __noinline__ void search_pe_pending(const Env &E, Mate &m) {
+// The function is cut at its two internal borders so that the paired-end second pass can run it as three small
+// kernels (HSP alignment / pending rows / HSP alignment): pend_stage_a returns true when the search is over.
+__device__ __forceinline__ bool pend_done_at_entry(const Env &E, const Mate &m) {   // search1pepend.cpp:27-31
+    return m.Best >= (int)m.QL + E.P.XP1 * E.P.MM;
+}
+__device__ __noinline__ bool pend_stage_a(const Env &E, Mate &m) {
     const int QL = (int)m.QL;
     m.MaxPenalty = E.P.MAXPEN;
     const int MinScorePhase1 = QL + E.P.XP1 * E.P.MM;
     const int TermHSPScorePhase3 = (QL * E.P.TERM3_PCT) / 100;
-    if (m.Best >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return; }
+    if (m.Best >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return true; }
     if (m.BestHSP >= TermHSPScorePhase3) {
         for (int i = 0; i < m.HSPCount; ++i) align_hsp(E, m, i);
-        if (m.Best >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return; }
+        if (m.Best >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return true; }
     }
     __syncwarp();
+    return false;
+}
+__device__ __noinline__ void pend_stage_b(const Env &E, Mate &m) {
     int n2[2] = {0, 0};
     for (int s = 0; s < 2; ++s) {   // pending round 1: 32 list entries at a time
         int nd = 0;
@@ -1577,12 +1590,19 @@ __device__ __noinline__ void search_pe_pending(const Env &E, Mate &m) {
     }
     for (int s = 0; s < 2; ++s)     // pending round 2
         rows_long_batch(E, m, s, m.g->pend[s], n2[s]);
+}
+__device__ __noinline__ void pend_stage_c(const Env &E, Mate &m) {
     const int B = max(m.Best, m.BestHSP) - 8;
     for (int i = 0; i < m.HSPCount; ++i) {
         if ((int)m.g->hsp_score[i] < B) continue;
         align_hsp(E, m, i);
     }
     m.Mapq = calc_mapq6(m);
+}
+__device__ void search_pe_pending(const Env &E, Mate &m) {
+    if (pend_stage_a(E, m)) return;
+    pend_stage_b(E, m);
+    pend_stage_c(E, m);
 }
 
 // State1::ScanSlots, scanslots.cpp:7-62.  Lanes hash 32 window positions at a time; matches against
@@ -1726,6 +1746,26 @@ __device__ __noinline__ void scan_pair(const Env &E, Mate &F, Mate &R) {
     }
 }
 
+// State2::AdjustTopHitsAndMapqs, search2.cpp:8-57
+__device__ __noinline__ void adjust_pair(Mate &F, Mate &R, const PairState &ps) {
+    if (ps.PairCount == 0) {
+        F.Mapq /= 2;
+        R.Mapq /= 2;
+        return;
+    }
+    double Fract = (double)ps.BestPairScore / (double)(F.QL + R.QL);
+    double Drop = (double)(ps.BestPairScore - ps.SecondBestPairScore);
+    if (Drop > 30) Drop = 30;
+    uint32_t mapq = (uint32_t)__dmul_rn(__dmul_rn(Drop, Fract), Fract);
+    if (mapq > 40) mapq = 40;
+    if (mapq > F.Mapq) F.Mapq = mapq;
+    if (mapq > R.Mapq) R.Mapq = mapq;
+    if (ps.BestF >= 0) {
+        F.Top = ps.BestF;
+        R.Top = ps.BestR;
+    }
+}
+
 // ExtendPen of seed i of mate m on strand Plus: through the memo when Plus is the seed's own strand, otherwise
 // (search2m4.cpp:94-95,122 extend a stored seed on the strand dictated by the OTHER mate's seed) computed here.
 __device__ int apply_seed_on(const Env &E, Mate &m, int i, bool Plus) {
@@ -1850,23 +1890,7 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R) {
         scan_pair(E, F, R);
         find_pairs(E, F, R, ps);
     }
-    // State2::AdjustTopHitsAndMapqs, search2.cpp:8-57
-    if (ps.PairCount == 0) {
-        F.Mapq /= 2;
-        R.Mapq /= 2;
-        return true;
-    }
-    double Fract = (double)ps.BestPairScore / (double)(QLf + QLr);
-    double Drop = (double)(ps.BestPairScore - ps.SecondBestPairScore);
-    if (Drop > 30) Drop = 30;
-    uint32_t mapq = (uint32_t)__dmul_rn(__dmul_rn(Drop, Fract), Fract);
-    if (mapq > 40) mapq = 40;
-    if (mapq > F.Mapq) F.Mapq = mapq;
-    if (mapq > R.Mapq) R.Mapq = mapq;
-    if (ps.BestF >= 0) {
-        F.Top = ps.BestF;
-        R.Top = ps.BestR;
-    }
+    adjust_pair(F, R, ps);
     return true;
 }
 
@@ -1891,10 +1915,11 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
         const uint32_t n = m.g->hit_nruns[t];
         if (n) {
             uint32_t off = 0;
-            if (E.lane == 0) off = atomicAdd(&o.counters[0], n);
+            if (E.lane == 0) off = atomicAdd(&o.counters[CT_RUNS], n);
             off = __shfl_sync(FULL, off, 0);
             if (off + n <= o.runs_cap) {
-                for (uint32_t k = E.lane; k < n; k += 32) o.runs[off + k] = m.g->hit_runs[t][k];
+                const uint16_t *src = m.g->runs_pool + m.g->hit_roff[t];
+                for (uint32_t k = E.lane; k < n; k += 32) o.runs[off + k] = src[k];
                 res.path_off = off;
                 res.path_runs = (uint16_t)n;
             } else {
@@ -1904,31 +1929,53 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
     }
     if (E.lane == 0) {
         o.res[r] = res;
-        if (res.flags & 0x80) atomicAdd(&o.counters[1], 1u);
+        if (res.flags & 0x80) atomicAdd(&o.counters[CT_OVERFLOW], 1u);
     }
 }
 
-// Per-mate shared-memory footprint of the search kernel.
-__host__ __device__ inline size_t mate_smem_bytes(uint32_t qcap, uint32_t seqcap) {
-    //     bytes fwd+rc      packed + bad bits   sd_db + sd_ext          sd_qs              sd_dead
-    return 2 * (size_t)seqcap + kReadViewBytes + 2 * (size_t)qcap * 8 + 2 * (size_t)qcap * 2 + ((2 * (size_t)qcap + 31) / 32) * 4;
+// Per-mate shared-memory footprint: read view (+ the seed lists of the first pass).
+__host__ __device__ inline size_t mate_smem_bytes(uint32_t qcap, uint32_t seqcap, bool seeds) {
+    size_t n = 2 * (size_t)seqcap + kReadViewBytes;   // bytes fwd+rc, packed strands, bad bits
+    //            sd_db + sd_ext          sd_qs              sd_dead
+    if (seeds) n += 2 * (size_t)qcap * 8 + 2 * (size_t)qcap * 2 + ((2 * (size_t)qcap + 31) / 32) * 4;
+    return (n + 15) & ~(size_t)15;
+}
+
+// What a kernel keeps per warp in shared memory: nm mate areas | flank-DP window | flank-DP trace bits.
+struct SmemPlan {
+    uint32_t nm;       // mate areas
+    uint32_t seeds;    // mate areas carry seed lists
+    uint32_t dp;       // flank-DP window + trace bits
+};
+__host__ __device__ inline size_t smem_per_warp(const DevBatch &b, const SmemPlan &pl) {
+    size_t s = (size_t)pl.nm * mate_smem_bytes(b.qcap, b.seqcap, pl.seeds != 0);
+    if (pl.dp) {
+        const uint32_t rows = b.seqcap + 2;
+        s += b.seqcap + 64;                      // genome window
+        s += (size_t)rows * 32 + rows + 66;      // band trace bytes (2 nibbles per lane per row) + column LB + row LA
+    }
+    return (s + 15) & ~(size_t)15;
 }
 
 // Stage one read: bytes, reverse complement, packed strands in shared memory; probe results stay in global.
 __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevProbe &pr, uint32_t r, uint8_t *sm,
-                          MateScratch *g) {
+                                       MateScratch *g, bool seeds) {
     const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(sm);
     uint32_t *s_bad = reinterpret_cast<uint32_t *>(sm + 2 * kPkWords * 8);
     uint8_t *p8 = sm + kReadViewBytes;
-    m.sd_db = reinterpret_cast<uint32_t *>(p8);
-    p8 += 2 * (size_t)b.qcap * 4;
-    m.sd_ext = reinterpret_cast<uint32_t *>(p8);
-    p8 += 2 * (size_t)b.qcap * 4;
-    m.sd_dead = reinterpret_cast<uint32_t *>(p8);
-    p8 += ((2 * (size_t)b.qcap + 31) / 32) * 4;
-    m.sd_qs = reinterpret_cast<uint16_t *>(p8);
-    p8 += 2 * (size_t)b.qcap * 2;
+    m.sd_db = m.sd_ext = m.sd_dead = nullptr;
+    m.sd_qs = nullptr;
+    if (seeds) {
+        m.sd_db = reinterpret_cast<uint32_t *>(p8);
+        p8 += 2 * (size_t)b.qcap * 4;
+        m.sd_ext = reinterpret_cast<uint32_t *>(p8);
+        p8 += 2 * (size_t)b.qcap * 4;
+        m.sd_dead = reinterpret_cast<uint32_t *>(p8);
+        p8 += ((2 * (size_t)b.qcap + 31) / 32) * 4;
+        m.sd_qs = reinterpret_cast<uint16_t *>(p8);
+        p8 += 2 * (size_t)b.qcap * 2;
+    }
     uint8_t *s_q = p8, *s_rc = p8 + b.seqcap;
     stage_read(E.lane, b.seqs + off, L, b.seqcap, s_q, s_rc, s_pk, s_bad, m.rv);
     const size_t base = (size_t)r * 2 * b.qcap;
@@ -1945,92 +1992,245 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
     m.overflow = 0;
 }
 
-// MODE 0: every unit, complete search (single-end).  MODE 1 (paired): every pair, fast part only; pairs that need
-// more are appended to o.todo.  MODE 2 (paired): complete search of the pairs listed in o.todo.
-template <int MODE>
-__device__ __forceinline__ void search_body(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr,
-                                            const DevOut &o, WarpScratch *scratch, uint32_t smem_per_warp,
-                                            uint32_t tb_stride, uint32_t tb_rows) {
-    URMB_DYN_SMEM(smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int gw = blockIdx.x * wpb + warp;
-    uint8_t *sw = smem + (size_t)warp * smem_per_warp;
-    // layout: mate 0 | mate 1 (paired) | flank-DP window | flank-DP trace bits
-    const int nm = b.paired ? 2 : 1;
-    const size_t msz = (mate_smem_bytes(b.qcap, b.seqcap) + 15) & ~(size_t)15;
-    uint8_t *p8 = sw + (size_t)nm * msz;
-    Env E;
+// ---- saved mate state (paired-end second pass) -----------------------------------------------------------
+// First pass -> pool: the used part of the per-warp scratch and the scalars.  SearchPE_Pending's entry test
+// (search1pepend.cpp:27-31) is evaluated here so that finished mates never enter a stage kernel.
+__device__ __noinline__ void save_mate(const Env &E, Mate &m, MateSave *dst) {
+    const bool done = pend_done_at_entry(E, m);
+    m.MaxPenalty = E.P.MAXPEN;   // search1pepend.cpp:15
+    if (done) m.Mapq = calc_mapq6(m);
+    const MateScratch *g = m.g;
+    MateScratch *d = &dst->s;
+    for (int i = E.lane; i < m.HitCount; i += 32) {
+        d->hit_pos[i] = g->hit_pos[i];
+        d->hit_score[i] = g->hit_score[i];
+        d->hit_plus[i] = g->hit_plus[i];
+        d->hit_nruns[i] = g->hit_nruns[i];
+        d->hit_roff[i] = g->hit_roff[i];
+    }
+    for (int i = E.lane; i < m.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
+    for (int i = E.lane; i < m.HSPCount; i += 32) {
+        d->hsp_dbstart[i] = g->hsp_dbstart[i];
+        d->hsp_qstart[i] = g->hsp_qstart[i];
+        d->hsp_len[i] = g->hsp_len[i];
+        d->hsp_score[i] = g->hsp_score[i];
+        d->hsp_flags[i] = g->hsp_flags[i];
+    }
+    if (!done)
+        for (int s = 0; s < 2; ++s)
+            for (int i = E.lane; i < m.nPend[s]; i += 32) d->pend[s][i] = g->pend[s][i];
+    if (E.lane == 0) {
+        MateHdr h;
+        h.HitCount = m.HitCount; h.HSPCount = m.HSPCount; h.Top = m.Top; h.MaxPenalty = m.MaxPenalty;
+        h.Best = m.Best; h.Second = m.Second; h.BestHSP = m.BestHSP; h.nRuns = m.nRuns;
+        h.Mapq = m.Mapq; h.nPend[0] = m.nPend[0]; h.nPend[1] = m.nPend[1];
+        h.overflow = m.overflow; h.done = done ? 1 : 0;
+        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        dst->h = h;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void hdr_to_mate(const MateHdr &h, Mate &m) {
+    m.HitCount = h.HitCount; m.HSPCount = h.HSPCount; m.Top = h.Top; m.MaxPenalty = h.MaxPenalty;
+    m.Best = h.Best; m.Second = h.Second; m.BestHSP = h.BestHSP; m.nRuns = h.nRuns;
+    m.Mapq = h.Mapq; m.nPend[0] = h.nPend[0]; m.nPend[1] = h.nPend[1];
+    m.overflow = h.overflow;
+}
+__device__ __forceinline__ void mate_to_hdr(const Env &E, const Mate &m, MateSave *sv, bool done) {
+    __syncwarp();
+    if (E.lane == 0) {
+        MateHdr h;
+        h.HitCount = m.HitCount; h.HSPCount = m.HSPCount; h.Top = m.Top; h.MaxPenalty = m.MaxPenalty;
+        h.Best = m.Best; h.Second = m.Second; h.BestHSP = m.BestHSP; h.nRuns = m.nRuns;
+        h.Mapq = m.Mapq; h.nPend[0] = m.nPend[0]; h.nPend[1] = m.nPend[1];
+        h.overflow = m.overflow; h.done = done ? 1 : 0;
+        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        sv->h = h;
+    }
+}
+
+// A mate of the second pass without its read (pair finishing only touches the hit list).
+__device__ __forceinline__ void bare_mate(const Env &E, Mate &m, const DevBatch &b, uint32_t r, MateSave *sv) {
+    const uint32_t L = b.offs[r + 1] - b.offs[r];
+    m.q = m.rc = nullptr;
+    m.tally = nullptr; m.pos = nullptr; m.ext = nullptr;
+    m.sd_db = m.sd_ext = m.sd_dead = nullptr;
+    m.sd_qs = nullptr;
+    m.nSeeds = 0;
+    m.g = &sv->s;
+    m.QL = L;
+    m.QWC = (L >= E.ix.word_len) ? L - E.ix.word_len + 1 : 0;
+    m.qcap = b.qcap;
+    hdr_to_mate(sv->h, m);
+}
+
+__device__ __forceinline__ void make_env(Env &E, const DevIndex &ix, const DevParams &P, const DevBatch &b,
+                                         WarpScratch *scratch, const SmemPlan &pl, uint8_t *sw, int gw, int lane) {
     E.ix = ix;
     E.P = P;
     E.ws = scratch + gw;
+    uint8_t *p8 = sw + (size_t)pl.nm * mate_smem_bytes(b.qcap, b.seqcap, pl.seeds != 0);
     E.s_win = p8;
-    p8 += b.seqcap + 64;
-    E.s_tb = p8;
-    E.tb_stride = tb_stride;
-    E.tb_rows = tb_rows;
+    E.s_tb = p8 + b.seqcap + 64;
+    E.tb_stride = 4 * P.R + 6;
+    E.tb_rows = pl.dp ? b.seqcap + 2 : 0;
     E.lane = lane;
-    const uint32_t n_work = (MODE == 2) ? o.counters[3] : b.n_units;   // MODE 2 runs after MODE 1 on the same stream
+}
+
+struct KArgs {   // one parameter block for every search kernel
+    DevIndex ix;
+    DevParams P;
+    DevBatch b;
+    DevProbe pr;
+    DevOut o;
+    WarpScratch *scratch;
+    MateSave *pool;
+    uint32_t unit_base, unit_count;   // first-pass kernels: the chunk of units this launch covers
+    uint32_t spw;                     // shared bytes per warp
+};
+
+// MODE 0: single-end, every read, complete search.  MODE 1 (paired, first pass): every pair of the chunk, the part
+// every pair goes through; pairs that need more are saved to the pool.  MODE 2 (paired, mate rescue): complete search
+// of the pairs listed in o.rescue.
+template <int MODE>
+__device__ __forceinline__ void search_body(const KArgs &A) {
+    URMB_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpb + warp;
+    uint8_t *sw = smem + (size_t)warp * A.spw;
+    const DevBatch &b = A.b;
+    const DevOut &o = A.o;
+    const SmemPlan pl{b.paired ? 2u : 1u, 1u, MODE == 1 ? 0u : 1u};
+    const size_t msz = mate_smem_bytes(b.qcap, b.seqcap, true);
+    Env E;
+    make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
+    const uint32_t n_work = (MODE == 2) ? o.counters[CT_RESCUE] : A.unit_count;
 
     for (;;) {
         uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(&o.counters[MODE == 2 ? 4 : 2], 1u);
+        if (lane == 0) u = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
         u = __shfl_sync(FULL, u, 0);
         if (u >= n_work) break;
-        if (MODE == 2) u = o.todo[u];
+        u = (MODE == 2) ? o.rescue[u] : A.unit_base + u;
         if (MODE == 0) {
             Mate m;
-            load_mate(E, m, b, pr, u, sw, &E.ws->m[0]);
+            load_mate(E, m, b, A.pr, u, sw, &E.ws->m[0], true);
             reset_search(E, m);   // State1::Search, search1.cpp:7-24
             search_lo(E, m);
             write_result(E, m, o, u);
         } else {
             Mate F, R;
-            load_mate(E, F, b, pr, u, sw, &E.ws->m[0]);
-            load_mate(E, R, b, pr, b.n_units + u, sw + msz, &E.ws->m[1]);
+            load_mate(E, F, b, A.pr, u, sw, &E.ws->m[0], true);
+            load_mate(E, R, b, A.pr, b.n_units + u, sw + msz, &E.ws->m[1], true);
             const bool done = search_pair<MODE == 1>(E, F, R);
             if (done) {
                 write_result(E, F, o, u);
                 write_result(E, R, o, b.n_units + u);
-            } else if (lane == 0) {
-                o.todo[atomicAdd(&o.counters[3], 1u)] = u;
+            } else {   // MODE 1 only
+                uint32_t t = 0;
+                if (lane == 0) {
+                    t = atomicAdd(&o.counters[CT_TODO], 1u);
+                    o.todo[t] = u;
+                }
+                t = __shfl_sync(FULL, t, 0);
+                save_mate(E, F, A.pool + 2 * (size_t)t);
+                save_mate(E, R, A.pool + 2 * (size_t)t + 1);
             }
         }
         __syncwarp();
     }
 }
 
-// SE: one kernel.  PE: pair_kernel (MODE 1, small code, every pair) then search_kernel<2> (the rest of the reference's
-// control flow, only for the pairs that need it).
-__global__ void __launch_bounds__(128, 4) search_kernel_se(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
-                                                           WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
-                                                           uint32_t tb_rows) {
-    search_body<0>(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
+// Second pass, one warp per saved MATE.  STAGE 0: SearchPE_Pending up to its first HSP alignments
+// (search1pepend.cpp:15-51); STAGE 1: the pending rows (:53-110); STAGE 2: the final HSP alignments and MAPQ (:112-129).
+template <int STAGE>
+__device__ __forceinline__ void stage_body(const KArgs &A) {
+    URMB_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpb + warp;
+    uint8_t *sw = smem + (size_t)warp * A.spw;
+    const DevBatch &b = A.b;
+    const SmemPlan pl{1u, 0u, STAGE == 1 ? 0u : 1u};
+    Env E;
+    make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
+    const uint32_t n_work = 2 * A.o.counters[CT_TODO];
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&A.o.counters[CT_STAGE_A + STAGE], 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_work) break;
+        MateSave *sv = A.pool + k;
+        const MateHdr h = sv->h;
+        if (h.done) continue;
+        const uint32_t u = A.o.todo[k >> 1];
+        const uint32_t r = (k & 1u) ? b.n_units + u : u;
+        if (STAGE == 0) {   // nothing to align: the stage only resets the penalty bound, which save_mate already did
+            const int QL = (int)(b.offs[r + 1] - b.offs[r]);
+            if (h.BestHSP < (QL * A.P.TERM3_PCT) / 100) continue;
+        }
+        Mate m;
+        load_mate(E, m, b, A.pr, r, sw, &sv->s, false);
+        hdr_to_mate(h, m);
+        bool done = false;
+        if (STAGE == 0) done = pend_stage_a(E, m);
+        else if (STAGE == 1) pend_stage_b(E, m);
+        else { pend_stage_c(E, m); done = true; }
+        mate_to_hdr(E, m, sv, done);
+        __syncwarp();
+    }
 }
-__global__ void __launch_bounds__(128, 4) pair_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
-                                                      WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
-                                                      uint32_t tb_rows) {
-    search_body<1>(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
+
+// Second pass, one warp per saved PAIR: State2::FindPairs + AdjustTopHitsAndMapqs (search2m4.cpp:177-186) and the
+// result records; pairs without any pair of hits go to the mate-rescue kernel.
+__device__ __forceinline__ void finish_body(const KArgs &A) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpb + warp;
+    const DevBatch &b = A.b;
+    Env E;
+    E.ix = A.ix;
+    E.P = A.P;
+    E.ws = A.scratch + gw;
+    E.s_win = E.s_tb = nullptr;
+    E.tb_stride = E.tb_rows = 0;
+    E.lane = lane;
+    const uint32_t n_work = A.o.counters[CT_TODO];
+    if (gw == 0 && lane == 0) atomicAdd(&A.o.counters[CT_TODO_TOTAL], n_work);
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&A.o.counters[CT_FINISH], 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= n_work) break;
+        const uint32_t u = A.o.todo[t];
+        Mate F, R;
+        bare_mate(E, F, b, u, A.pool + 2 * (size_t)t);
+        bare_mate(E, R, b, b.n_units + u, A.pool + 2 * (size_t)t + 1);
+        if (A.P.pe_method != 5) {
+            PairState ps;
+            find_pairs(E, F, R, ps);
+            if (ps.PairCount == 0) {   // State2::ScanPair needed (search2m4.cpp:179-183)
+                if (lane == 0) A.o.rescue[atomicAdd(&A.o.counters[CT_RESCUE], 1u)] = u;
+                continue;
+            }
+            adjust_pair(F, R, ps);
+        }
+        write_result(E, F, A.o, u);
+        write_result(E, R, A.o, b.n_units + u);
+        __syncwarp();
+    }
 }
-__global__ void __launch_bounds__(128, 4) search_kernel_pe(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, DevOut o,
-                                                           WarpScratch *scratch, uint32_t smem_per_warp, uint32_t tb_stride,
-                                                           uint32_t tb_rows) {
-    search_body<2>(ix, P, b, pr, o, scratch, smem_per_warp, tb_stride, tb_rows);
-}
+
+__global__ void __launch_bounds__(128, 4) search_kernel_se(const __grid_constant__ KArgs A) { search_body<0>(A); }
+__global__ void __launch_bounds__(128, 4) pair_kernel(const __grid_constant__ KArgs A) { search_body<1>(A); }
+__global__ void __launch_bounds__(128, 4) rescue_kernel(const __grid_constant__ KArgs A) { search_body<2>(A); }
+__global__ void __launch_bounds__(128, 4) align_kernel_a(const __grid_constant__ KArgs A) { stage_body<0>(A); }
+__global__ void __launch_bounds__(128, 4) rows_kernel(const __grid_constant__ KArgs A) { stage_body<1>(A); }
+__global__ void __launch_bounds__(128, 4) align_kernel_c(const __grid_constant__ KArgs A) { stage_body<2>(A); }
+__global__ void __launch_bounds__(128, 4) finish_kernel(const __grid_constant__ KArgs A) { finish_body(A); }
 
 // =====================================================================================
 // host-side launchers
 // =====================================================================================
-static inline uint32_t tb_stride_for(const DevParams &P) { return 4 * P.R + 6; }
-
-size_t search_smem_per_warp(const DevBatch &b, const DevParams &P) {
-    const int nm = b.paired ? 2 : 1;
-    size_t s = (size_t)nm * ((mate_smem_bytes(b.qcap, b.seqcap) + 15) & ~(size_t)15);
-    s += b.seqcap + 64;
-    const uint32_t rows = b.seqcap + 2;
-    s += (size_t)rows * 32 + rows + 66;   // band trace bytes (2 nibbles per lane per row) + column LB + row LA
-    return (s + 15) & ~(size_t)15;
-}
-
 int max_search_warps(int sm_count) { return sm_count * 32; }
 
 size_t packed_words(size_t n_bytes) { return n_bytes / 32 + 2; }
@@ -2053,38 +2253,70 @@ int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, cons
     return (int)cudaGetLastError();
 }
 
+// Persistent grid: SMs x resident blocks (bounded by the per-warp scratch), work claimed by atomicAdd.
 template <class K>
-static int launch_one(K kern, const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
-                      WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used) {
+static int launch_one(K kern, KArgs &A, const SmemPlan &pl, uint32_t max_items, const SearchRes &R, void *stream, int sm_count,
+                      int *warps_used) {
     const int wpb = 4;
-    const size_t spw = search_smem_per_warp(b, P);
-    const size_t smem = spw * wpb;
+    A.spw = (uint32_t)smem_per_warp(A.b, pl);
+    const size_t smem = (size_t)A.spw * wpb;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem);
     if (per_sm < 1) per_sm = 1;
     int blocks = sm_count * per_sm;
-    if (blocks * wpb > n_scratch_warps) blocks = n_scratch_warps / wpb;
-    const int need = (int)((b.n_units + wpb - 1) / wpb);
+    if (blocks * wpb > R.n_scratch_warps) blocks = R.n_scratch_warps / wpb;
+    const int need = (int)((max_items + wpb - 1) / wpb);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     if (warps_used) *warps_used = blocks * wpb;
-    const uint32_t rows = b.seqcap + 2;
-    URMB_LAUNCH(kern, blocks, wpb * 32, smem, stream, ix, P, b, pr, o, scratch, (uint32_t)spw, tb_stride_for(P), rows);
+    URMB_LAUNCH(kern, blocks, wpb * 32, smem, stream, A);
     return (int)cudaGetLastError();
 }
 
-// Returns the number of kernels launched (1 single-end, 2 paired-end) or a negative cudaError.
+// Returns the number of kernels launched or a negative cudaError.
+//   single-end: search_kernel_se.
+//   paired-end: per chunk of R.pool_pairs pairs  pair_kernel -> align_kernel_a -> rows_kernel -> align_kernel_c ->
+//               finish_kernel (each a small kernel over the saved mate states); rescue_kernel once at the end.
 int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
-                  WarpScratch *scratch, int n_scratch_warps, void *stream, int sm_count, int *warps_used) {
+                  const SearchRes &R, void *stream, int sm_count, int *warps_used) {
+    KArgs A;
+    A.ix = ix; A.P = P; A.b = b; A.pr = pr; A.o = o;
+    A.scratch = R.scratch;
+    A.pool = R.pool;
+    A.unit_base = 0;
+    A.unit_count = b.n_units;
+    A.spw = 0;
+    int e;
+#define URMB_TRY(call) do { e = (call); if (e) return -e; } while (0)
     if (!b.paired) {
-        int e = launch_one(search_kernel_se, ix, P, b, pr, o, scratch, n_scratch_warps, stream, sm_count, warps_used);
-        return e ? -e : 1;
+        URMB_TRY(launch_one(search_kernel_se, A, SmemPlan{1, 1, 1}, b.n_units, R, stream, sm_count, warps_used));
+        return 1;
     }
-    int e = launch_one(pair_kernel, ix, P, b, pr, o, scratch, n_scratch_warps, stream, sm_count, warps_used);
-    if (e) return -e;
-    e = launch_one(search_kernel_pe, ix, P, b, pr, o, scratch, n_scratch_warps, stream, sm_count, warps_used);
-    return e ? -e : 2;
+    if (!R.pool || R.pool_pairs == 0) return -1;   // cudaErrorInvalidValue
+    int n = 0;
+    for (uint32_t u0 = 0; u0 < b.n_units; u0 += R.pool_pairs) {
+        const uint32_t cnt = (b.n_units - u0 < R.pool_pairs) ? b.n_units - u0 : R.pool_pairs;
+        A.unit_base = u0;
+        A.unit_count = cnt;
+#ifndef URMB_EMU
+        URMB_TRY((int)cudaMemsetAsync(o.counters + CT_CHUNK0, 0, (CT_COUNT - CT_CHUNK0) * sizeof(uint32_t), (cudaStream_t)stream));
+#else
+        for (int i = CT_CHUNK0; i < CT_COUNT; ++i) o.counters[i] = 0;
+#endif
+        URMB_TRY(launch_one(pair_kernel, A, SmemPlan{2, 1, 0}, cnt, R, stream, sm_count, warps_used));
+        URMB_TRY(launch_one(align_kernel_a, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(rows_kernel, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(align_kernel_c, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(finish_kernel, A, SmemPlan{0, 0, 0}, cnt, R, stream, sm_count, nullptr));
+        n += 5;
+    }
+    if (P.pe_method != 5) {
+        URMB_TRY(launch_one(rescue_kernel, A, SmemPlan{2, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
+        ++n;
+    }
+#undef URMB_TRY
+    return n;
 }
 
 }  // namespace urmb

@@ -388,37 +388,58 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
 // =====================================================================================
 // probe + extend kernel
 // =====================================================================================
-// One warp per read, lane = k-mer start: hash (SetSlotsVec), gather the 5-byte slot record from the HBM-resident
-// table (GetBlob), and for BOTH1 slots gather the candidate's genome window and run the pure extension above.
-// Every lane's chain is slot sector -> genome sectors; thousands of chains per SM are in flight: HBM-gather bound.
+// One warp per read.  Pass 1, lane = k-mer start: hash (SetSlotsVec), gather the 5-byte slot record from the
+// HBM-resident table (GetBlob); BOTH1 slots are appended to a per-warp candidate list in shared memory.  Pass 2,
+// lane = candidate: gather the candidate's packed genome window and run the pure extension above, 32 candidates at a
+// time so that every lane has work.  Every chain is slot sector -> genome sectors; thousands of chains per SM are in
+// flight: HBM-gather bound.
+__host__ __device__ inline size_t probe_smem_per_warp(uint32_t qcap, uint32_t seqcap) {
+    //     read view + bytes                  c_pos                 c_qs
+    return ((kReadViewBytes + 2 * (size_t)seqcap + 2 * (size_t)qcap * 4 + 2 * (size_t)qcap * 2) + 15) & ~(size_t)15;
+}
 __global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr) {
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    uint8_t *sw = smem + (size_t)warp * (2 * b.seqcap + kReadViewBytes);
+    uint8_t *sw = smem + (size_t)warp * probe_smem_per_warp(b.qcap, b.seqcap);
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(sw);
     uint32_t *s_bad = reinterpret_cast<uint32_t *>(sw + 2 * kPkWords * 8);
-    uint8_t *s_q = sw + kReadViewBytes, *s_rc = s_q + b.seqcap;
+    uint32_t *c_pos = reinterpret_cast<uint32_t *>(sw + kReadViewBytes);
+    uint16_t *c_qs = reinterpret_cast<uint16_t *>(c_pos + 2 * b.qcap);
+    uint8_t *s_q = reinterpret_cast<uint8_t *>(c_qs + 2 * b.qcap), *s_rc = s_q + b.seqcap;
     const uint32_t W = ix.word_len;
+    const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t r = blockIdx.x * wpb + warp; r < b.n_reads; r += gridDim.x * wpb) {
         const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
         ReadView rv;
         stage_read(lane, b.seqs + off, L, b.seqcap, s_q, s_rc, s_pk, s_bad, rv);
         const uint32_t QWC = (L >= W) ? L - W + 1 : 0;
         const size_t base = (size_t)r * 2 * b.qcap;
+        uint32_t nc = 0;
         for (uint32_t s = 0; s < 2; ++s) {
             for (uint32_t q = lane; q < b.qcap; q += 32) {
-                uint32_t tally = T_FREE, pos = POS_INVALID_WORD, ext = EXT_NONE;
+                uint32_t tally = T_FREE, pos = POS_INVALID_WORD;
                 if (q < QWC) {
                     const uint64_t slot = slot_of(ix, rv, (int)s, q);
-                    if (slot != ~0ull) {
-                        load_blob<false>(ix.blob, slot, tally, pos);
-                        if (tally == T_BOTH1) ext = pure_ext(ix, P, rv, s == 0, q, pos, true, P.MAXPEN);
-                    }
+                    if (slot != ~0ull) load_blob<false>(ix.blob, slot, tally, pos);
                 }
+                const bool cand = tally == T_BOTH1;
+                const uint32_t bal = __ballot_sync(FULL, cand);
+                if (cand) {
+                    const uint32_t i = nc + __popc(bal & lt);
+                    c_pos[i] = pos;
+                    c_qs[i] = (uint16_t)(q | (s << 15));
+                } else {
+                    pr.ext[base + s * b.qcap + q] = EXT_NONE;
+                }
+                nc += __popc(bal);
                 pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
                 pr.pos[base + s * b.qcap + q] = pos;
-                pr.ext[base + s * b.qcap + q] = ext;
             }
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < nc; i += 32) {
+            const uint32_t qs = c_qs[i], q = qs & 0x7FFFu, s = qs >> 15;
+            pr.ext[base + s * b.qcap + q] = pure_ext(ix, P, rv, s == 0, q, c_pos[i], true, P.MAXPEN);
         }
         __syncwarp();
     }
@@ -1301,37 +1322,85 @@ __device__ __noinline__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tal
     }
 }
 
-// One item (QPos) per lane: walk the heads of 32 rows and run the pure extension of their candidates in parallel,
-// then visit the items in lane order exactly like the reference's loop body (search1m6.cpp:181-199,
-// search1pepend.cpp:53-68): rows longer than 2 are deferred through `defer`, the others are extended now.
-__device__ __noinline__ void rows_short_stage(const Env &E, Mate &m, int s, bool valid, uint32_t QPos, uint8_t *deflist,
+// First round over a list of owned non-BOTH1 slots (search1m6.cpp:181-199, search1pepend.cpp:53-68): rows of length
+// <= 2 are extended now, longer rows are deferred through `deflist`.  Three passes so that every lane has work:
+//   1. the heads of all rows of the list, one dependent-gather chain per lane;
+//   2. the candidates of the short rows laid out flat, 32 pure extensions at a time;
+//   3. the order-dependent bookkeeping, visiting the list in the reference's order.
+// The hit-overlap precheck and the penalty bound of pass 2 use the state at entry: both only ever get stricter, so a
+// candidate dropped here is still a no-op when the reference reaches it, and pass 3 re-applies the current state.
+// `deflist` may alias `list` (it is written in pass 3 only; pass 1 keeps its own copy of the list).
+__device__ __noinline__ void rows_short_round(const Env &E, Mate &m, int s, const uint8_t *list, int n, uint8_t *deflist,
                                               int &ndef) {
-    uint32_t n = 0, p0 = 0, p1 = 0;
-    if (valid) row_head3(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), n, p0, p1);
-    if (n > E.ix.max_ix) n = E.ix.max_ix;
-    uint32_t x0 = EXT_NONE, x1 = EXT_NONE;
-    if (valid && n >= 1 && n <= 2 && p0 >= QPos && !overlaps_hit_lane(m, p0 - QPos))
-        x0 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p0, true, m.MaxPenalty);
-    if (valid && n == 2 && p1 >= QPos && !overlaps_hit_lane(m, p1 - QPos))
-        x1 = pure_ext(E.ix, E.P, m.rv, s == 0, QPos, p1, true, m.MaxPenalty);
-    const bool a0 = !ext_is_noop(E, x0, (int)m.QL, m.MaxPenalty), a1 = !ext_is_noop(E, x1, (int)m.QL, m.MaxPenalty);
-    uint32_t vmask = __ballot_sync(FULL, valid && (n > 2 || a0 || a1));
-    const uint32_t m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1), big = __ballot_sync(FULL, n > 2);
-    bool stored;
-    while (vmask) {
-        const int b = __ffs(vmask) - 1;
-        vmask &= vmask - 1;
-        const uint32_t qb = __shfl_sync(FULL, QPos, b);
-        if (big >> b & 1u) {
-            if (E.lane == 0) deflist[ndef] = (uint8_t)qb;
-            ++ndef;
-            continue;
+    ndef = 0;
+    if (n <= 0) return;
+    uint32_t *hp0 = reinterpret_cast<uint32_t *>(E.ws->rowM);   // [kMaxLen] first position of the row
+    uint32_t *hp1 = hp0 + kMaxLen;                              // [kMaxLen] second position
+    uint32_t *hx0 = hp1 + kMaxLen, *hx1 = hx0 + kMaxLen;        // [kMaxLen] pure extension results
+    uint16_t *flat = reinterpret_cast<uint16_t *>(E.ws->rowD);  // [2 * kMaxLen] entry | which << 15
+    uint8_t *hq = E.ws->tb, *hn = E.ws->tb + kMaxLen;           // [kMaxLen] QPos, row length (3 = longer than 2)
+    const uint32_t lt = (1u << E.lane) - 1u;
+    int total = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {   // pass 1
+        const int i = i0 + E.lane;
+        const bool valid = i < n;
+        const uint32_t QPos = valid ? list[i] : 0u;
+        uint32_t rn = 0, p0 = 0, p1 = 0;
+        if (valid) row_head3(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), rn, p0, p1);
+        if (rn > E.ix.max_ix) rn = E.ix.max_ix;
+        const bool c0 = valid && rn >= 1 && rn <= 2 && p0 >= QPos && !overlaps_hit_lane(m, p0 - QPos);
+        const bool c1 = valid && rn == 2 && p1 >= QPos && !overlaps_hit_lane(m, p1 - QPos);
+        const uint32_t b0 = __ballot_sync(FULL, c0), b1 = __ballot_sync(FULL, c1);
+        if (valid) {
+            hq[i] = (uint8_t)QPos;
+            hn[i] = (uint8_t)rn;
+            hp0[i] = p0;
+            hp1[i] = p1;
+            hx0[i] = EXT_NONE;
+            hx1[i] = EXT_NONE;
         }
-        const uint32_t pb0 = __shfl_sync(FULL, p0, b), pb1 = __shfl_sync(FULL, p1, b);
-        const uint32_t xb0 = __shfl_sync(FULL, x0, b), xb1 = __shfl_sync(FULL, x1, b);
-        if (m0 >> b & 1u) extend_apply(E, m, qb, pb0, s == 0, xb0, stored);
-        if (m1 >> b & 1u) extend_apply(E, m, qb, pb1, s == 0, xb1, stored);
+        if (c0) flat[total + __popc(b0 & lt)] = (uint16_t)i;
+        total += __popc(b0);
+        if (c1) flat[total + __popc(b1 & lt)] = (uint16_t)(i | 0x8000);
+        total += __popc(b1);
     }
+    __syncwarp();
+    for (int f0 = 0; f0 < total; f0 += 32) {   // pass 2
+        const int f = f0 + E.lane;
+        if (f < total) {
+            const uint32_t e = flat[f], i = e & 0x7FFFu;
+            const uint32_t pz = (e & 0x8000u) ? hp1[i] : hp0[i];
+            const uint32_t x = pure_ext(E.ix, E.P, m.rv, s == 0, hq[i], pz, true, m.MaxPenalty);
+            if (e & 0x8000u) hx1[i] = x; else hx0[i] = x;
+        }
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < n; i0 += 32) {   // pass 3
+        const int i = i0 + E.lane;
+        const bool valid = i < n;
+        const uint32_t QPos = valid ? hq[i] : 0u, rn = valid ? hn[i] : 0u;
+        const uint32_t p0 = valid ? hp0[i] : 0u, p1 = valid ? hp1[i] : 0u;
+        const uint32_t x0 = valid ? hx0[i] : EXT_NONE, x1 = valid ? hx1[i] : EXT_NONE;
+        const bool a0 = !ext_is_noop(E, x0, (int)m.QL, m.MaxPenalty), a1 = !ext_is_noop(E, x1, (int)m.QL, m.MaxPenalty);
+        uint32_t vmask = __ballot_sync(FULL, valid && (rn > 2 || a0 || a1));
+        const uint32_t m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1), big = __ballot_sync(FULL, rn > 2);
+        bool stored;
+        while (vmask) {
+            const int b = __ffs(vmask) - 1;
+            vmask &= vmask - 1;
+            const uint32_t qb = __shfl_sync(FULL, QPos, b);
+            if (big >> b & 1u) {
+                if (E.lane == 0) deflist[ndef] = (uint8_t)qb;
+                ++ndef;
+                continue;
+            }
+            const uint32_t pb0 = __shfl_sync(FULL, p0, b), pb1 = __shfl_sync(FULL, p1, b);
+            const uint32_t xb0 = __shfl_sync(FULL, x0, b), xb1 = __shfl_sync(FULL, x1, b);
+            if (m0 >> b & 1u) extend_apply(E, m, qb, pb0, s == 0, xb0, stored);
+            if (m1 >> b & 1u) extend_apply(E, m, qb, pb1, s == 0, xb1, stored);
+        }
+    }
+    __syncwarp();
 }
 
 // Lane-local GetRow_Blob (ufindex.cpp:883-943): the whole row into out[0..31]; returns the row length.
@@ -1477,13 +1546,20 @@ __device__ __noinline__ void search_lo(const Env &E, Mate &m) {
     // phase 4: non-BOTH1 owned slots; rows <= 2 now, longer rows deferred
     int nTodo[2] = {0, 0};
     for (int s = 0; s < 2; ++s) {
-        int nt = 0;
+        // the owned non-BOTH1 slots of this strand in QPos order (search1m6.cpp:170-203), then rows <= 2 / deferral
+        uint8_t *lst = m.g->todo[s];
+        int nl = 0;
         for (uint32_t q0 = 0; q0 < QWC; q0 += 32) {
             const uint32_t q = q0 + E.lane;
             const uint32_t T = (q < QWC) ? m_tally(m, s, q) : 0;
             const bool cand = (T != T_FREE && T != T_BOTH1 && (T & T_MY_BIT));
-            rows_short_stage(E, m, s, cand, q, m.g->todo[s], nt);
+            const uint32_t bal = __ballot_sync(FULL, cand);
+            if (cand) lst[nl + __popc(bal & ((1u << E.lane) - 1u))] = (uint8_t)q;
+            nl += __popc(bal);
         }
+        __syncwarp();
+        int nt = 0;
+        rows_short_round(E, m, s, lst, nl, lst, nt);
         nTodo[s] = nt;
     }
     __syncwarp();
@@ -1576,16 +1652,9 @@ __device__ __noinline__ bool pend_stage_a(const Env &E, Mate &m) {
 }
 __device__ __noinline__ void pend_stage_b(const Env &E, Mate &m) {
     int n2[2] = {0, 0};
-    for (int s = 0; s < 2; ++s) {   // pending round 1: 32 list entries at a time
+    for (int s = 0; s < 2; ++s) {   // pending round 1; the list is compacted in place into the deferred rows
         int nd = 0;
-        for (int i0 = 0; i0 < m.nPend[s]; i0 += 32) {
-            const int i = i0 + E.lane;
-            const bool valid = i < m.nPend[s];
-            const uint32_t QPos = valid ? m.g->pend[s][i] : 0;
-            __syncwarp();   // the list is compacted in place below (nd <= i0 for every write)
-            rows_short_stage(E, m, s, valid, QPos, m.g->pend[s], nd);
-            __syncwarp();
-        }
+        rows_short_round(E, m, s, m.g->pend[s], m.nPend[s], m.g->pend[s], nd);
         n2[s] = nd;
     }
     for (int s = 0; s < 2; ++s)     // pending round 2
@@ -2220,12 +2289,22 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
     }
 }
 
+// Resident blocks per SM each kernel is compiled for (register budget = 65536 / (128 * blocks)).
+#ifndef URMB_LB_PAIR
+#define URMB_LB_PAIR 5
+#endif
+#ifndef URMB_LB_ROWS
+#define URMB_LB_ROWS 6
+#endif
+#ifndef URMB_LB_ALIGN
+#define URMB_LB_ALIGN 5
+#endif
 __global__ void __launch_bounds__(128, 4) search_kernel_se(const __grid_constant__ KArgs A) { search_body<0>(A); }
-__global__ void __launch_bounds__(128, 4) pair_kernel(const __grid_constant__ KArgs A) { search_body<1>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_PAIR) pair_kernel(const __grid_constant__ KArgs A) { search_body<1>(A); }
 __global__ void __launch_bounds__(128, 4) rescue_kernel(const __grid_constant__ KArgs A) { search_body<2>(A); }
-__global__ void __launch_bounds__(128, 4) align_kernel_a(const __grid_constant__ KArgs A) { stage_body<0>(A); }
-__global__ void __launch_bounds__(128, 4) rows_kernel(const __grid_constant__ KArgs A) { stage_body<1>(A); }
-__global__ void __launch_bounds__(128, 4) align_kernel_c(const __grid_constant__ KArgs A) { stage_body<2>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_a(const __grid_constant__ KArgs A) { stage_body<0>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_kernel(const __grid_constant__ KArgs A) { stage_body<1>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_c(const __grid_constant__ KArgs A) { stage_body<2>(A); }
 __global__ void __launch_bounds__(128, 4) finish_kernel(const __grid_constant__ KArgs A) { finish_body(A); }
 
 // =====================================================================================
@@ -2245,7 +2324,8 @@ int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint3
 
 int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count) {
     const int threads = 256;
-    const size_t smem = (size_t)(threads / 32) * (2 * b.seqcap + kReadViewBytes);
+    const size_t smem = (size_t)(threads / 32) * probe_smem_per_warp(b.qcap, b.seqcap);
+    cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int blocks = (int)((b.n_reads + 7) / 8);
     if (blocks > sm_count * 16) blocks = sm_count * 16;
     if (blocks < 1) blocks = 1;

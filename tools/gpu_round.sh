@@ -29,7 +29,7 @@ benchq)
   cat $OUT/benchq.json ;;
 ncu)
   # launch list of the same command (short): per-launch durations, cold-cache and serialised
-  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'probe_kernel|search_kernel|pair_kernel|align_kernel|rows_kernel|finish_kernel|rescue_kernel' -c 200 --csv \
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'probe_kernel|seed_kernel|pair_kernel|align_kernel|rows_kernel|finish_kernel|rescue_kernel' -c 200 --csv \
       --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
   echo "ncu launches exit $?"
   ncu_full rows_kernel rows_full

@@ -7,8 +7,8 @@ cp urmap_b200/liburmb.so $OUT/liburmb_saved.so
 for so in urmap_b200/variants/liburmb_*.so; do
   name=$(basename $so .so); name=${name#liburmb_}
   cp $so urmap_b200/liburmb.so
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'probe_kernel|search_kernel|pair_kernel|align_kernel|rows_kernel|finish_kernel|rescue_kernel' \
-      --csv --log-file $OUT/launches_$name.csv python tools/perf_sweep.py --pairs $PAIRS --flags 0 --reps 3 > $OUT/sweep_$name.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'probe_kernel|seed_kernel|pair_kernel|align_kernel|rows_kernel|finish_kernel|rescue_kernel' \
+      --csv --log-file $OUT/launches_$name.csv python tools/perf_sweep.py --pairs $PAIRS --flags 0 --reps 3 $SWEEP_EXTRA > $OUT/sweep_$name.log 2>&1
   echo "== $name"; tail -1 $OUT/sweep_$name.log
   python tools/launch_summary.py $OUT/launches_$name.csv
 done

@@ -477,8 +477,10 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     if ((rc = grow_dev(c, s.d_res, s.d_res_cap, (size_t)nreads + 1))) return rc;
     if ((rc = grow_dev(c, s.d_todo, s.d_todo_cap, (size_t)n + 1))) return rc;
     if ((rc = grow_dev(c, s.d_rescue, s.d_rescue_cap, (size_t)n + 1))) return rc;
-    if (r2) {   // pool of saved mate states, shared by the slots (their kernels are serialised on the compute stream)
-        const size_t want = std::min<size_t>(std::max<size_t>(n, 1), c->chunk_pairs);
+    {   // pool of saved mate states (2 per pair, 1 per single-end read), shared by the slots: their kernels are
+        // serialised on the compute stream
+        const size_t units = r2 ? n : ((size_t)n + 1) / 2;
+        const size_t want = std::min<size_t>(std::max<size_t>(units, 1), c->chunk_pairs);
         if (want > c->pool_pairs) {
             CK(cudaStreamSynchronize(c->compute));
             cudaFree(c->pool);

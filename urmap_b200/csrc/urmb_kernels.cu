@@ -1,18 +1,23 @@
 // urmb_kernels.cu -- hand-written sm_100a kernels of the URMAP mapping hot path.
 //
-//   probe_kernel   : SetSlotsVec (state1.cpp:396) + GetBlob (ufindex.h:184) for every k-mer of every
-//                    read on both strands: hash, Barrett-reduce, gather the 5-byte slot record from the
-//                    HBM-resident UFI table.  Pure function of (read, index); HBM-gather bound.
-//   search_kernel  : one warp per read (SE, Search_Lo search1m6.cpp:35) or per pair (PE, Search4/5
-//                    search2m4.cpp:15 / search2m5.cpp:9).  The order-dependent state machine is replayed
-//                    exactly; the primitives inside it are warp-cooperative:
-//                      extend  (ExtendPen extendpen.cpp:9, ExtendScan extendscan.cpp:51): 32 bases per
-//                              ballot into a mismatch bitmask, then replay over set bits only;
-//                      row walk (GetRow_Blob ufindex.cpp:883): positions held one per lane;
-//                      viterbi (State1::Viterbi viterbi.cpp:11 + TraceBackBitMem): 32-row blocks, lane =
-//                              row, anti-diagonal wavefront over columns with shuffles, fp32 arithmetic
-//                              identical to the reference, trace bits in shared memory (flank DP) or in
-//                              a per-warp HBM scratch (mate-rescue DP).
+//   probe_kernel   : SetSlotsVec (state1.cpp:396) + GetBlob (ufindex.h:184) for every k-mer of every read on both
+//                    strands (hash, Barrett-reduce, gather the 5-byte slot record from the HBM-resident UFI table),
+//                    then the state-independent half of ExtendPen for every BOTH1 candidate.  HBM-gather bound.
+//   search kernels : one warp per read / pair / saved mate.  The reference's order-dependent state machine
+//                    (SE Search_Lo search1m6.cpp:35; PE Search4/5 search2m4.cpp:15 / search2m5.cpp:9) is replayed
+//                    exactly, but it is cut at its phase borders into SMALL kernels that hand the per-mate state
+//                    over through a pool in HBM -- one 160 KB kernel spent half its cycles on instruction fetch:
+//                      PE: pair_kernel (seed pairing, every pair) -> align_kernel_a -> rows_kernel -> align_kernel_c
+//                          (SearchPE_Pending, search1pepend.cpp:9, per saved mate) -> finish_kernel (FindPairs,
+//                          AdjustTopHitsAndMapqs) per chunk; rescue_kernel (ScanPair) once per batch;
+//                      SE: seed_kernel_se (phases 1-2) -> align_kernel_se3 -> rows_kernel_se -> align_kernel_se6.
+//                    The primitives inside are warp-cooperative:
+//                      extend  (ExtendPen extendpen.cpp:9, ExtendScan extendscan.cpp:51): one candidate per lane on
+//                              the 2-bit packed genome, XOR -> mismatch bitmask -> walk over set bits only;
+//                      row walk (GetRow_Blob ufindex.cpp:883): one dependent-gather chain per lane;
+//                      viterbi (State1::Viterbi viterbi.cpp:11 + TraceBackBitMem): flank DP with the band across
+//                              the lanes (max-plus prefix scan for the insert chain), mate-rescue DP as 32-row
+//                              blocks with an anti-diagonal wavefront; fp32 arithmetic identical to the reference.
 // No tensor cores: nothing here is a dense contraction.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -1489,61 +1494,69 @@ __device__ void reset_search(const Env &E, Mate &m) {
     m.nPend[0] = m.nPend[1] = 0;
 }
 
-// State1::Search_Lo, search1m6.cpp:35-277
-__device__ __noinline__ void search_lo(const Env &E, Mate &m) {
+// State1::Search_Lo, search1m6.cpp:35-277, cut at its phase borders so that the single-end search runs as small
+// kernels (seeds / HSP alignment / rows / HSP alignment).  Each piece returns true when the search is over.
+// Phases 1 and 2 (search1m6.cpp:48-131): BOTH1 seeds at stride W (plus then minus at each QPos), then all remaining
+// QPos.  The visit order is laid out 32 visits at a time into the seed list together with the probe kernel's pure
+// results; the order-dependent bookkeeping then runs over the candidates that can still do something.
+__device__ __noinline__ bool se_phase12(const Env &E, Mate &m) {
     const uint32_t W = E.ix.word_len;
     const int QL = (int)m.QL;
-    if (m.QL < W) { m.Mapq = 0; return; }   // reference underflows: report no hit
+    if (m.QL < W) { m.Mapq = 0; return true; }   // reference underflows: report no hit
     const uint32_t QWC = m.QWC;
     m.MaxPenalty = E.P.MAXPEN;
     const int MinScorePhase1 = QL + E.P.XP1 * E.P.MM;
-    const int MinScorePhase3 = QL + E.P.XP3 * E.P.MM;
-    const int MinScorePhase4 = QL + E.P.XP4 * E.P.MM;
-    const int TermHSPScorePhase3 = (QL * E.P.TERM3_PCT) / 100;
     m.BestHSP = 0;
-    // phases 1 and 2: BOTH1 seeds at stride W (plus then minus at each QPos), then all remaining QPos.  The visit
-    // order is laid out 32 visits at a time into the seed list together with the probe kernel's pure results;
-    // the order-dependent bookkeeping then runs over the candidates that can still do something.
-    {
-        const uint32_t n1 = (QWC + W - 1) / W;          // phase-1 QPos count
-        const uint32_t nvis = 2 * QWC;
-        m.nSeeds = 0;
-        for (uint32_t v0 = 0; v0 < nvis; v0 += 32) {
-            const uint32_t v = v0 + E.lane;
-            uint32_t q = 0;
-            const int sgn = (int)(v & 1u);
-            if (v < 2 * n1) q = (v >> 1) * W;
-            else {
-                const uint32_t vv = (v - 2 * n1) >> 1;
-                q = (W > 1) ? (vv / (W - 1)) * W + vv % (W - 1) + 1 : QWC;
-            }
-            const bool c = (v < nvis) && (q < QWC) && (m_tally(m, sgn, q) == T_BOTH1);
-            const uint32_t bal = __ballot_sync(FULL, c);
-            if (c) {
-                const int i = m.nSeeds + __popc(bal & ((1u << E.lane) - 1u));
-                m.sd_db[i] = m_pos(m, sgn, q);
-                m.sd_ext[i] = m_ext(m, sgn, q);
-                m.sd_qs[i] = (uint16_t)(q | ((uint32_t)sgn << 15));
-            }
-            m.nSeeds += __popc(bal);
+    const uint32_t n1 = (QWC + W - 1) / W;          // phase-1 QPos count
+    const uint32_t nvis = 2 * QWC;
+    m.nSeeds = 0;
+    for (uint32_t v0 = 0; v0 < nvis; v0 += 32) {
+        const uint32_t v = v0 + E.lane;
+        uint32_t q = 0;
+        const int sgn = (int)(v & 1u);
+        if (v < 2 * n1) q = (v >> 1) * W;
+        else {
+            const uint32_t vv = (v - 2 * n1) >> 1;
+            q = (W > 1) ? (vv / (W - 1)) * W + vv % (W - 1) + 1 : QWC;
         }
-        seeds_init_dead(E, m);
-        for (int w0 = 0; w0 < m.nSeeds; w0 += 32) {
-            uint32_t live = ~m.sd_dead[w0 >> 5];
-            while (live) {
-                const int bit = __ffs(live) - 1;
-                const int Score = apply_seed(E, m, w0 + bit);
-                if (Score >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return; }
-                live = ~m.sd_dead[w0 >> 5] & ((bit == 31) ? 0u : (0xFFFFFFFFu << (bit + 1)));
-            }
+        const bool c = (v < nvis) && (q < QWC) && (m_tally(m, sgn, q) == T_BOTH1);
+        const uint32_t bal = __ballot_sync(FULL, c);
+        if (c) {
+            const int i = m.nSeeds + __popc(bal & ((1u << E.lane) - 1u));
+            m.sd_db[i] = m_pos(m, sgn, q);
+            m.sd_ext[i] = m_ext(m, sgn, q);
+            m.sd_qs[i] = (uint16_t)(q | ((uint32_t)sgn << 15));
+        }
+        m.nSeeds += __popc(bal);
+    }
+    seeds_init_dead(E, m);
+    for (int w0 = 0; w0 < m.nSeeds; w0 += 32) {
+        uint32_t live = ~m.sd_dead[w0 >> 5];
+        while (live) {
+            const int bit = __ffs(live) - 1;
+            const int Score = apply_seed(E, m, w0 + bit);
+            if (Score >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return true; }
+            live = ~m.sd_dead[w0 >> 5] & ((bit == 31) ? 0u : (0xFFFFFFFFu << (bit + 1)));
         }
     }
-    // phase 3
-    if (m.BestHSP > TermHSPScorePhase3) {
+    return false;
+}
+__device__ __forceinline__ bool se_phase3_needed(const DevParams &P, int QL, int BestHSP) {
+    return BestHSP > (QL * P.TERM3_PCT) / 100;
+}
+// Phase 3 (search1m6.cpp:133-147)
+__device__ __noinline__ bool se_phase3(const Env &E, Mate &m) {
+    const int QL = (int)m.QL;
+    if (se_phase3_needed(E.P, QL, m.BestHSP)) {
         for (int i = 0; i < m.HSPCount; ++i) align_hsp(E, m, i);
-        if (m.Best >= MinScorePhase1) { m.Mapq = calc_mapq6(m); return; }
+        if (m.Best >= QL + E.P.XP1 * E.P.MM) { m.Mapq = calc_mapq6(m); return true; }
     }
-    // phase 4: non-BOTH1 owned slots; rows <= 2 now, longer rows deferred
+    return false;
+}
+// Phases 4 and 5 (search1m6.cpp:149-245): non-BOTH1 owned slots; rows <= 2 now, longer rows deferred
+__device__ __noinline__ bool se_phase45(const Env &E, Mate &m) {
+    const int QL = (int)m.QL;
+    const uint32_t QWC = m.QWC;
     int nTodo[2] = {0, 0};
     for (int s = 0; s < 2; ++s) {
         // the owned non-BOTH1 slots of this strand in QPos order (search1m6.cpp:170-203), then rows <= 2 / deferral
@@ -1563,12 +1576,14 @@ __device__ __noinline__ void search_lo(const Env &E, Mate &m) {
         nTodo[s] = nt;
     }
     __syncwarp();
-    if (m.Best >= MinScorePhase3) { m.Mapq = calc_mapq6(m); return; }
-    // phase 5
+    if (m.Best >= QL + E.P.XP3 * E.P.MM) { m.Mapq = calc_mapq6(m); return true; }
     for (int s = 0; s < 2; ++s)
         rows_long_batch(E, m, s, m.g->todo[s], nTodo[s]);
-    if (m.Best >= MinScorePhase4) { m.Mapq = calc_mapq6(m); return; }
-    // phase 6
+    if (m.Best >= QL + E.P.XP4 * E.P.MM) { m.Mapq = calc_mapq6(m); return true; }
+    return false;
+}
+// Phase 6 (search1m6.cpp:247-276)
+__device__ __noinline__ void se_phase6(const Env &E, Mate &m) {
     for (int i = 0; i < m.HSPCount; ++i) align_hsp(E, m, i);
     m.Mapq = calc_mapq6(m);
 }
@@ -2064,10 +2079,14 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
 // ---- saved mate state (paired-end second pass) -----------------------------------------------------------
 // First pass -> pool: the used part of the per-warp scratch and the scalars.  SearchPE_Pending's entry test
 // (search1pepend.cpp:27-31) is evaluated here so that finished mates never enter a stage kernel.
+template <bool PE>
 __device__ __noinline__ void save_mate(const Env &E, Mate &m, MateSave *dst) {
-    const bool done = pend_done_at_entry(E, m);
-    m.MaxPenalty = E.P.MAXPEN;   // search1pepend.cpp:15
-    if (done) m.Mapq = calc_mapq6(m);
+    bool done = false;
+    if (PE) {
+        done = pend_done_at_entry(E, m);
+        m.MaxPenalty = E.P.MAXPEN;   // search1pepend.cpp:15
+        if (done) m.Mapq = calc_mapq6(m);
+    }
     const MateScratch *g = m.g;
     MateScratch *d = &dst->s;
     for (int i = E.lane; i < m.HitCount; i += 32) {
@@ -2159,7 +2178,8 @@ struct KArgs {   // one parameter block for every search kernel
     uint32_t spw;                     // shared bytes per warp
 };
 
-// MODE 0: single-end, every read, complete search.  MODE 1 (paired, first pass): every pair of the chunk, the part
+// MODE 0 (single-end, first pass): every read of the chunk, phases 1-2; reads that need more are saved to the pool.
+// MODE 1 (paired, first pass): every pair of the chunk, the part
 // every pair goes through; pairs that need more are saved to the pool.  MODE 2 (paired, mate rescue): complete search
 // of the pairs listed in o.rescue.
 template <int MODE>
@@ -2170,7 +2190,7 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
     uint8_t *sw = smem + (size_t)warp * A.spw;
     const DevBatch &b = A.b;
     const DevOut &o = A.o;
-    const SmemPlan pl{b.paired ? 2u : 1u, 1u, MODE == 1 ? 0u : 1u};
+    const SmemPlan pl{b.paired ? 2u : 1u, 1u, MODE == 2 ? 1u : 0u};
     const size_t msz = mate_smem_bytes(b.qcap, b.seqcap, true);
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
@@ -2186,8 +2206,16 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
             Mate m;
             load_mate(E, m, b, A.pr, u, sw, &E.ws->m[0], true);
             reset_search(E, m);   // State1::Search, search1.cpp:7-24
-            search_lo(E, m);
-            write_result(E, m, o, u);
+            if (se_phase12(E, m)) write_result(E, m, o, u);
+            else {
+                uint32_t t = 0;
+                if (lane == 0) {
+                    t = atomicAdd(&o.counters[CT_TODO], 1u);
+                    o.todo[t] = u;
+                }
+                t = __shfl_sync(FULL, t, 0);
+                save_mate<false>(E, m, A.pool + t);
+            }
         } else {
             Mate F, R;
             load_mate(E, F, b, A.pr, u, sw, &E.ws->m[0], true);
@@ -2203,8 +2231,8 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
                     o.todo[t] = u;
                 }
                 t = __shfl_sync(FULL, t, 0);
-                save_mate(E, F, A.pool + 2 * (size_t)t);
-                save_mate(E, R, A.pool + 2 * (size_t)t + 1);
+                save_mate<true>(E, F, A.pool + 2 * (size_t)t);
+                save_mate<true>(E, R, A.pool + 2 * (size_t)t + 1);
             }
         }
         __syncwarp();
@@ -2213,39 +2241,51 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
 
 // Second pass, one warp per saved MATE.  STAGE 0: SearchPE_Pending up to its first HSP alignments
 // (search1pepend.cpp:15-51); STAGE 1: the pending rows (:53-110); STAGE 2: the final HSP alignments and MAPQ (:112-129).
+// STAGE 3-5: the same for the single-end search (one saved state per read): phase 3, phases 4-5, phase 6 + result.
 template <int STAGE>
 __device__ __forceinline__ void stage_body(const KArgs &A) {
+    constexpr bool SE = STAGE >= 3;
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + warp;
     uint8_t *sw = smem + (size_t)warp * A.spw;
     const DevBatch &b = A.b;
-    const SmemPlan pl{1u, 0u, STAGE == 1 ? 0u : 1u};
+    const SmemPlan pl{1u, 0u, (STAGE == 1 || STAGE == 4) ? 0u : 1u};
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
-    const uint32_t n_work = 2 * A.o.counters[CT_TODO];
+    const uint32_t n_work = (SE ? 1u : 2u) * A.o.counters[CT_TODO];
     for (;;) {
         uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&A.o.counters[CT_STAGE_A + STAGE], 1u);
+        if (lane == 0) k = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
         k = __shfl_sync(FULL, k, 0);
         if (k >= n_work) break;
         MateSave *sv = A.pool + k;
         const MateHdr h = sv->h;
-        if (h.done) continue;
-        const uint32_t u = A.o.todo[k >> 1];
-        const uint32_t r = (k & 1u) ? b.n_units + u : u;
-        if (STAGE == 0) {   // nothing to align: the stage only resets the penalty bound, which save_mate already did
+        const uint32_t u = A.o.todo[SE ? k : k >> 1];
+        const uint32_t r = (!SE && (k & 1u)) ? b.n_units + u : u;
+        if (h.done && STAGE != 5) continue;
+        if (STAGE == 0 || STAGE == 3) {   // nothing to align (save_mate already reset the paired-end penalty bound)
             const int QL = (int)(b.offs[r + 1] - b.offs[r]);
-            if (h.BestHSP < (QL * A.P.TERM3_PCT) / 100) continue;
+            if (STAGE == 0 && h.BestHSP < (QL * A.P.TERM3_PCT) / 100) continue;
+            if (STAGE == 3 && !se_phase3_needed(A.P, QL, h.BestHSP)) continue;
         }
         Mate m;
+        if (STAGE == 5 && h.done) {   // finished in an earlier stage: only the result record is left
+            bare_mate(E, m, b, r, sv);
+            write_result(E, m, A.o, u);
+            continue;
+        }
         load_mate(E, m, b, A.pr, r, sw, &sv->s, false);
         hdr_to_mate(h, m);
         bool done = false;
         if (STAGE == 0) done = pend_stage_a(E, m);
         else if (STAGE == 1) pend_stage_b(E, m);
-        else { pend_stage_c(E, m); done = true; }
-        mate_to_hdr(E, m, sv, done);
+        else if (STAGE == 2) { pend_stage_c(E, m); done = true; }
+        else if (STAGE == 3) done = se_phase3(E, m);
+        else if (STAGE == 4) done = se_phase45(E, m);
+        else { se_phase6(E, m); done = true; }
+        if (STAGE == 5) write_result(E, m, A.o, u);
+        else mate_to_hdr(E, m, sv, done);
         __syncwarp();
     }
 }
@@ -2299,7 +2339,10 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
 #ifndef URMB_LB_ALIGN
 #define URMB_LB_ALIGN 5
 #endif
-__global__ void __launch_bounds__(128, 4) search_kernel_se(const __grid_constant__ KArgs A) { search_body<0>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_PAIR) seed_kernel_se(const __grid_constant__ KArgs A) { search_body<0>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se3(const __grid_constant__ KArgs A) { stage_body<3>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_kernel_se(const __grid_constant__ KArgs A) { stage_body<4>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se6(const __grid_constant__ KArgs A) { stage_body<5>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_PAIR) pair_kernel(const __grid_constant__ KArgs A) { search_body<1>(A); }
 __global__ void __launch_bounds__(128, 4) rescue_kernel(const __grid_constant__ KArgs A) { search_body<2>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_a(const __grid_constant__ KArgs A) { stage_body<0>(A); }
@@ -2355,7 +2398,7 @@ static int launch_one(K kern, KArgs &A, const SmemPlan &pl, uint32_t max_items, 
 }
 
 // Returns the number of kernels launched or a negative cudaError.
-//   single-end: search_kernel_se.
+//   single-end: per chunk  seed_kernel_se -> align_kernel_se3 -> rows_kernel_se -> align_kernel_se6.
 //   paired-end: per chunk of R.pool_pairs pairs  pair_kernel -> align_kernel_a -> rows_kernel -> align_kernel_c ->
 //               finish_kernel (each a small kernel over the saved mate states); rescue_kernel once at the end.
 int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
@@ -2369,12 +2412,27 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     A.spw = 0;
     int e;
 #define URMB_TRY(call) do { e = (call); if (e) return -e; } while (0)
-    if (!b.paired) {
-        URMB_TRY(launch_one(search_kernel_se, A, SmemPlan{1, 1, 1}, b.n_units, R, stream, sm_count, warps_used));
-        return 1;
-    }
     if (!R.pool || R.pool_pairs == 0) return -1;   // cudaErrorInvalidValue
     int n = 0;
+    if (!b.paired) {
+        const uint32_t chunk = 2 * R.pool_pairs;   // one saved state per read
+        for (uint32_t u0 = 0; u0 < b.n_units; u0 += chunk) {
+            const uint32_t cnt = (b.n_units - u0 < chunk) ? b.n_units - u0 : chunk;
+            A.unit_base = u0;
+            A.unit_count = cnt;
+#ifndef URMB_EMU
+            URMB_TRY((int)cudaMemsetAsync(o.counters + CT_CHUNK0, 0, (CT_COUNT - CT_CHUNK0) * sizeof(uint32_t), (cudaStream_t)stream));
+#else
+            for (int i = CT_CHUNK0; i < CT_COUNT; ++i) o.counters[i] = 0;
+#endif
+            URMB_TRY(launch_one(seed_kernel_se, A, SmemPlan{1, 1, 0}, cnt, R, stream, sm_count, warps_used));
+            URMB_TRY(launch_one(align_kernel_se3, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
+            URMB_TRY(launch_one(rows_kernel_se, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
+            URMB_TRY(launch_one(align_kernel_se6, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
+            n += 4;
+        }
+        return n;
+    }
     for (uint32_t u0 = 0; u0 < b.n_units; u0 += R.pool_pairs) {
         const uint32_t cnt = (b.n_units - u0 < R.pool_pairs) ? b.n_units - u0 : R.pool_pairs;
         A.unit_base = u0;

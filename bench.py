@@ -7,9 +7,9 @@ reads/s mapped for 2x150 bp paired-end reads against a 3.1 Gb human-scale synthe
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's own CPU path (oracle/_ref/urmap) on the host cores
 
-A "step" is one pass of the hot path (probe kernel + search kernel) over one batch of `--pairs-per-step` read
-pairs per GPU.  `value` is measured with the inputs already resident in HBM (CUDA events on the launching
-stream); `e2e` goes through the C-ABI with pinned host buffers, H2D and D2H inside the timed region, three
+A "step" is one pass of the hot path (probe kernel + search kernels) over one batch of `--pairs-per-step` read
+pairs per GPU.  `value` is measured with the inputs already resident in HBM: K steps issued back to back, device time
+between two CUDA events that bracket them; `e2e` goes through the C-ABI with pinned host buffers, H2D and D2H inside the timed region, three
 batch slots in flight.  Weak scaling: every rank maps its own batches; the only collective is the NCCL
 broadcast of the index at start-up.
 """
@@ -286,8 +286,11 @@ def algorithmic_bytes_per_read(args, ufi_path, batch, n_units, paired):
                           want_stats=True)
     oix.close()
     r = max(1, st["reads"])
-    per = {k: st[k] / r for k in ("probes", "row_hops", "compare_bytes", "dp_cells", "extend_calls")}
+    per = {k: st[k] / r for k in ("probes", "row_hops", "compare_bytes", "compare_bytes_rows", "dp_cells", "extend_calls")}
     per["bytes"] = 5 * per["probes"] + 5 * per["row_hops"] + per["compare_bytes"]
+    # attribution to the two gather kernels: slot probes + seed extensions vs list hops + row-candidate extensions
+    per["bytes_rows"] = 5 * per["row_hops"] + per["compare_bytes_rows"]
+    per["bytes_probe"] = per["bytes"] - per["bytes_rows"]
     return per
 
 
@@ -416,18 +419,29 @@ def main():
     launches0 = ctx.launch_count()
     sampler.active = True
     t_wall0 = time.perf_counter()
-    dev_ms, probe_ms, search_ms = 0.0, 0.0, 0.0
+    # K steps issued back to back; the device time between two context-wide CUDA events brackets exactly these K steps
+    # (the mate-rescue kernel of step k runs on a side stream and overlaps step k+1; the end mark waits for the last one)
+    ctx.mark(0)
     for k in range(args.steps):
         ctx.launch(k % 3)
-        tm = ctx.timing(k % 3)   # synchronises on the step's last event
-        probe_ms += tm["probe_ms"]
-        search_ms += tm["search_ms"]
-        dev_ms += tm["probe_ms"] + tm["search_ms"]
+    ctx.mark(1)
+    dev_ms = ctx.mark_elapsed()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     sampler.active = False
     D.barrier()
     gpu_launches = ctx.launch_count() - launches0
+    # per-kernel-class launch durations (CUDA events around every launch) of the last steps still held by the slots
+    nlast = min(3, args.steps)
+    kms = {}
+    klaunch = {}
+    for k in range(args.steps - nlast, args.steps):
+        tm = ctx.timing(k % 3)
+        for name, v in tm["kernel_ms"].items():
+            kms[name] = kms.get(name, 0.0) + v / nlast
+            klaunch[name] = klaunch.get(name, 0) + tm["kernel_launches"][name]
+    probe_ms = kms.get("probe", 0.0) * args.steps
+    search_ms = sum(v for n_, v in kms.items() if n_ != "probe") * args.steps
     dev_ms_max = D.max_over_ranks(dev_ms, device)
     total_reads = rpu * B * args.steps * world
     value = total_reads / (dev_ms_max / 1e3)
@@ -492,19 +506,39 @@ def main():
             log(f"cpu baseline failed: {e!r}")
     if algo is None:
         # SURVEY.md §8d, measured on the reference at human scale (PE 1 %): P=157, H~50, C=2213
-        algo = {"probes": 157.0, "row_hops": 50.0, "compare_bytes": 2213.0, "bytes": 5 * 157 + 5 * 50 + 2213.0,
-                "source": "SURVEY.md §8d constants"}
+        algo = {"probes": 157.0, "row_hops": 50.0, "compare_bytes": 2213.0, "compare_bytes_rows": 1100.0,
+                "bytes": 5 * 157 + 5 * 50 + 2213.0, "bytes_rows": 5 * 50 + 1100.0, "bytes_probe": 5 * 157 + 1113.0,
+                "source": "SURVEY.md §8d constants (rows share estimated)"}
 
     if rank == 0:
-        reads_per_launch = rpu * B
+        reads_per_step = rpu * B
         peak = peaks.get("hbm_gbs")
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peak else "fallback 6650 GB/s (B200_PROFILING.md)"
         peak = peak or 6650.0
-        search_avg_s = (search_ms / args.steps) / 1e3
-        probe_avg_s = (probe_ms / args.steps) / 1e3
-        achieved = algo["bytes"] * reads_per_launch / search_avg_s / 1e9
-        qwc = RL - 23
-        probe_bytes = reads_per_launch * 2 * qwc * 5.0
+        traffic = load_json(os.path.join("profiles", "ncu_traffic.json"))   # dram bytes per pair from ncu --set full
+        # the two HBM-gather kernels; the dominant one (by measured time) is reported as `roofline`
+        gather = {
+            "probe": ("probe_kernel", algo["bytes_probe"],
+                      "5 B x slot probes + compared bases of BOTH1 seed extensions (reference control flow)"),
+            "rows": ("rows_kernel", algo["bytes_rows"],
+                     "5 B x list hops + compared bases of row-candidate extensions (reference control flow)"),
+        }
+
+        def roof(cls):
+            name, bytes_per_read, what = gather[cls]
+            launches = max(1, klaunch.get(cls, 0) // nlast)           # launches per step
+            avg_s = kms.get(cls, 0.0) / 1e3 / launches                # average launch duration
+            reads_per_launch = reads_per_step / launches
+            ach = bytes_per_read * reads_per_launch / max(avg_s, 1e-9) / 1e9
+            tr = traffic.get(name)
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": (tr["dram_bytes_per_pair"] * (reads_per_launch / rpu)) if tr else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_read": bytes_per_read, "algorithmic_bytes": what,
+                    "launches_per_step": launches, "avg_launch_ms": 1e3 * avg_s,
+                    "share_of_step": kms.get(cls, 0.0) / max(sum(kms.values()), 1e-9)}
+
+        dominant = "rows" if kms.get("rows", 0.0) >= kms.get("probe", 0.0) else "probe"
+        other = "probe" if dominant == "rows" else "rows"
         line = {
             "metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -514,15 +548,10 @@ def main():
                     "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": 1e3 * t_e2e_max / args.steps},
             "gpu_launches": gpu_launches,
             "clocks": clocks,
-            "roofline": {"kernel": "search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_read": algo["bytes"],
-                         "note": "latency-bound dependent gathers: see DESIGN.md; DP cells/read %.0f" % algo.get("dp_cells", 0)},
-            "roofline_probe": {"kernel": "probe_kernel", "bound": "hbm", "achieved": probe_bytes / probe_avg_s / 1e9,
-                               "peak": peak, "unit": "GB/s", "frac": probe_bytes / probe_avg_s / 1e9 / peak,
-                               "note": "5 B per speculative slot probe, 2*(QL-23) probes per read"},
-            "kernel_ms_per_step": {"probe": probe_ms / args.steps, "search": search_ms / args.steps,
-                                   "wall_incl_launch_gaps": 1e3 * t_wall / args.steps},
+            "roofline": roof(dominant),
+            "roofline_" + other: roof(other),
+            "kernel_ms_per_step": dict(kms, wall_incl_launch_gaps=1e3 * t_wall / args.steps,
+                                       note="summed launch durations per kernel class; rescue overlaps the next step"),
             "cpu_baseline": cpu_baseline,
             "sam_identity_vs_reference": sam_id,
             "work_per_read": algo,

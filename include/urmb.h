@@ -94,12 +94,17 @@ typedef struct urmb_index_desc {
     const void *d_seq;
 } urmb_index_desc;
 
-/* Kernel timings of the last launch on a slot (CUDA events on the slot's stream). */
+/* Kernel timings of the last launch on a slot (CUDA events on the launching streams). */
+#define URMB_KCLASSES 7 /* 0 probe, 1 seed pairing (PE) / seeds (SE), 2 first HSP alignment, 3 rows, 4 final HSP
+                           alignment, 5 pair finishing, 6 mate rescue */
 typedef struct urmb_timing {
     float probe_ms;  /* slot-probe / gather kernel */
-    float search_ms; /* search state-machine kernel (extension + DP + MAPQ) */
+    float search_ms; /* all search kernels on the compute stream (seed pairing, alignment, rows, finishing) */
     float h2d_ms;
     float d2h_ms;
+    float rescue_ms; /* mate-rescue kernel: runs on a side stream and overlaps the next batch */
+    float kernel_ms[URMB_KCLASSES];      /* summed launch durations per kernel class */
+    uint32_t kernel_launches[URMB_KCLASSES];
 } urmb_timing;
 
 /* ---- index: replaces UFIndex::FromFile (ufindexio.cpp:51,60-115) ---- */
@@ -140,6 +145,11 @@ int urmb_download(urmb_ctx *c, int slot);
 int urmb_timing_last(urmb_ctx *c, int slot, urmb_timing *t);
 /* Number of kernels launched by this ctx so far. */
 uint64_t urmb_launch_count(const urmb_ctx *c);
+/* Context-wide time marks for timing several launches issued back to back: a mark is a CUDA event recorded after all
+ * work submitted so far on both the compute and the rescue stream.  urmb_mark_elapsed synchronises on mark 1 and
+ * returns the device time between mark 0 and mark 1. */
+int urmb_mark(urmb_ctx *c, int which /* 0 | 1 */);
+int urmb_mark_elapsed(urmb_ctx *c, float *ms);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ RESULT_DTYPE = np.dtype([
 assert RESULT_DTYPE.itemsize == 20
 
 STATS_FIELDS = ["reads", "probes", "row_calls", "row_hops", "extend_calls", "compare_bytes", "slot_hashes",
-                "dp_calls", "dp_cells", "scan_calls", "tb_poison_reads"]
+                "dp_calls", "dp_cells", "scan_calls", "tb_poison_reads", "compare_bytes_rows"]
 
 
 class Params(C.Structure):

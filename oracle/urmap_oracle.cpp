@@ -488,6 +488,18 @@ struct S1 {
         return k;
     }
 
+    // ExtendPen of a position that came out of GetRow_Blob (statistics only: the compared bytes are also counted
+    // separately so that bench.py can attribute algorithmic bytes to the probe and the row kernels).
+    bool InRows = false;
+    int ExtendPenRow(uint32 SeedPosQ, uint32 SeedPosDB, bool Plus) {
+        InRows = true;
+        const uint64 c0 = st ? st->compare_bytes : 0;
+        int r = ExtendPen(SeedPosQ, SeedPosDB, Plus);
+        if (st) st->compare_bytes_rows += st->compare_bytes - c0;
+        InRows = false;
+        return r;
+    }
+
     // State1::ExtendPen, extendpen.cpp:9-95.  +score: new full-length hit; -2: HSP; -1 otherwise.
     int ExtendPen(uint32 SeedPosQ, uint32 SeedPosDB, bool Plus) {
         if (st) st->extend_calls++;
@@ -720,7 +732,7 @@ struct S1 {
                 if (T == T_FREE || T == T_BOTH1 || TallyOther(T)) continue;
                 unsigned RowLength = GetRow_Blob(Sv[QPos], Bv + 5 * QPos, PosVec.data());
                 if (RowLength > 2) { Todo.push_back(QPos); continue; }
-                for (unsigned r = 0; r < RowLength; ++r) ExtendPen(QPos, PosVec[r], Plus);
+                for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], Plus);
             }
         }
         if (BestScore >= MinScorePhase3) { Mapq = CalcMAPQ6(); return; }
@@ -730,7 +742,7 @@ struct S1 {
             const uint64 *Sv = (Plus ? SlotsP : SlotsM).data();
             for (uint32 QPos : (Plus ? TodoP : TodoM)) {
                 unsigned RowLength = GetRow_Blob(Sv[QPos], Bv + 5 * QPos, PosVec.data());
-                for (unsigned r = 0; r < RowLength; ++r) ExtendPen(QPos, PosVec[r], Plus);
+                for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], Plus);
             }
         }
         if (BestScore >= MinScorePhase4) { Mapq = CalcMAPQ6(); return; }
@@ -857,23 +869,23 @@ struct S1 {
             unsigned QPos = PendP[i];
             unsigned RowLength = GetRow_Blob(SlotsP[QPos], BlobP.data() + 5 * QPos, PosVec.data());
             if (RowLength > 2) { PendP[nP2++] = (byte)QPos; continue; }
-            for (unsigned r = 0; r < RowLength; ++r) ExtendPen(QPos, PosVec[r], true);
+            for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], true);
         }
         for (unsigned i = 0; i < nPendM; ++i) {
             unsigned QPos = PendM[i];
             unsigned RowLength = GetRow_Blob(SlotsM[QPos], BlobM.data() + 5 * QPos, PosVec.data());
             if (RowLength > 2) { PendM[nM2++] = (byte)QPos; continue; }
-            for (unsigned r = 0; r < RowLength; ++r) ExtendPen(QPos, PosVec[r], false);
+            for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], false);
         }
         for (unsigned i = 0; i < nP2; ++i) {
             unsigned QPos = PendP[i];
             unsigned RowLength = GetRow_Blob(SlotsP[QPos], BlobP.data() + 5 * QPos, PosVec.data());
-            for (unsigned r = 0; r < RowLength; ++r) ExtendPen(QPos, PosVec[r], true);
+            for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], true);
         }
         for (unsigned i = 0; i < nM2; ++i) {
             unsigned QPos = PendM[i];
             unsigned RowLength = GetRow_Blob(SlotsM[QPos], BlobM.data() + 5 * QPos, PosVec.data());
-            for (unsigned r = 0; r < RowLength; ++r) ExtendPen(QPos, PosVec[r], false);
+            for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], false);
         }
         int B = std::max(BestScore, BestHSPScore) - 8;
         for (unsigned i = 0; i < HSPCount; ++i) {
@@ -1147,6 +1159,7 @@ void AddStats(uo_stats *dst, const uo_stats &s) {
     dst->compare_bytes += s.compare_bytes; dst->slot_hashes += s.slot_hashes;
     dst->dp_calls += s.dp_calls; dst->dp_cells += s.dp_cells; dst->scan_calls += s.scan_calls;
     dst->tb_poison_reads += s.tb_poison_reads;
+    dst->compare_bytes_rows += s.compare_bytes_rows;
 }
 
 // ---- CIGAR (cigar.cpp:4-41, 141-199; state1.cpp:717-734) --------------------------------

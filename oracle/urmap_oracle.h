@@ -53,6 +53,7 @@ typedef struct uo_stats {
     uint64_t dp_cells;      /* inner-loop trip count of viterbi.cpp:122   */
     uint64_t scan_calls;
     uint64_t tb_poison_reads; /* traceback reads of cells the current call never wrote */
+    uint64_t compare_bytes_rows; /* part of C spent on positions that came out of GetRow_Blob */
 } uo_stats;
 
 uo_index *uo_index_open(const char *ufi_path);   /* mmap, ufindexio.cpp:60-115 */

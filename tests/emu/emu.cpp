@@ -141,10 +141,11 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     ix.max_ix = max_ix;
     const size_t nbytes = (size_t)seq_size + 4096, nwords = packed_words(nbytes);
     std::vector<uint64_t> seq2(nwords);
-    std::vector<uint32_t> seqx(nwords);
-    launch_pack_genome(seq_padded, nbytes, seq2.data(), seqx.data(), nullptr);
+    std::vector<uint32_t> seqx(nwords), seqc(coarse_words(nbytes), 0);
+    launch_pack_genome(seq_padded, nbytes, seq2.data(), seqx.data(), seqc.data(), nullptr);
     ix.seq2 = seq2.data();
     ix.seqx = seqx.data();
+    ix.seqc = seqc.data();
     DevParams P = emu_make_params(*p);
     const uint32_t nreads = paired ? 2 * n_units : n_units;
     uint32_t maxlen = 0;
@@ -177,7 +178,8 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     memset(pool, 0xEE, sizeof(MateSave) * 2 * chunk);
     SearchRes R{ws, nw, pool, chunk};
     launch_probe(ix, P, b, pr, nullptr, 1);
-    const int nk = launch_search(ix, P, b, pr, o, R, nullptr, 1, nullptr);
+    int nk = launch_search(ix, P, b, pr, o, R, nullptr, 1, nullptr, nullptr);
+    if (nk >= 0) nk = launch_rescue(ix, P, b, pr, o, R, nullptr, 1, nullptr);
     free(ws);
     free(pool);
     memcpy(counters, ct, 32);

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <vector>
 #include <string>
 #include <vector>
 
@@ -128,6 +129,10 @@ extern "C" int urmb_index_contig(const urmb_index_host *h, uint32_t i, urmb_cont
 struct Slot {
     cudaStream_t copy = nullptr;
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_d2h = nullptr;
+    cudaEvent_t ev_rescue = nullptr;          // end of the mate-rescue kernel (rescue stream)
+    std::vector<cudaEvent_t> kev;             // begin/end events of every kernel of the last launch
+    std::vector<int> kclass;                  // kernel class of kev[2i], kev[2i+1]
+    size_t nkev = 0;
     // pinned host staging
     uint8_t *h_seqs = nullptr; size_t h_seqs_cap = 0;
     uint32_t *h_offs = nullptr; size_t h_offs_cap = 0;
@@ -158,9 +163,16 @@ struct urmb_ctx {
     void *own_blob = nullptr, *own_seq = nullptr;
     uint64_t *seq2 = nullptr;   // derived 2-bit packing of the genome + exception bits (built on the device)
     uint32_t *seqx = nullptr;
+    uint32_t *seqc = nullptr;
     cudaStream_t compute = nullptr;
+    cudaStream_t rescue = nullptr;            // low-priority side stream of the mate-rescue kernel
+    cudaEvent_t ev_mark[2] = {nullptr, nullptr};
+    cudaEvent_t ev_rescue_tail = nullptr;     // last event recorded on the rescue stream
+    bool rescue_used = false;
     WarpScratch *scratch = nullptr;
     int n_scratch_warps = 0;
+    WarpScratch *rescue_scratch = nullptr;
+    int n_rescue_warps = 0;
     MateSave *pool = nullptr;      // saved mate states of one chunk of the paired-end second pass (2 per pair)
     size_t pool_pairs = 0;
     uint32_t chunk_pairs = 262144; // URMB_CHUNK_PAIRS
@@ -220,13 +232,21 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->compute, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->rescue, cudaStreamNonBlocking, prio_lo));
+    for (auto &ev : c->ev_mark) CK(cudaEventCreate(&ev));
+    CK(cudaEventCreateWithFlags(&c->ev_rescue_tail, cudaEventDisableTiming));
     c->n_scratch_warps = max_search_warps(c->sm_count);
+    c->n_rescue_warps = c->sm_count * 8;   // two blocks per SM: the kernel is a long tail of few, long work items
+    if (const char *f = getenv("URMB_RESCUE_WARPS_PER_SM")) c->n_rescue_warps = c->sm_count * std::max(4, atoi(f));
+    CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps));
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
     for (auto &s : c->slots) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
-        for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h}) CK(cudaEventCreate(ev));
+        for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h, &s.ev_rescue}) CK(cudaEventCreate(ev));
         CK(cudaMalloc(&s.d_counters, CT_COUNT * sizeof(uint32_t)));
         CK(cudaHostAlloc(&s.h_counters, CT_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
     }
@@ -236,7 +256,8 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
 
 static void free_slot(Slot &s) {
     if (s.copy) cudaStreamDestroy(s.copy);
-    for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h, s.ev_rescue}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : s.kev) cudaEventDestroy(ev);
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext);
     cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo); cudaFree(s.d_rescue);
@@ -248,12 +269,17 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &s : c->slots) free_slot(s);
     if (c->compute) cudaStreamDestroy(c->compute);
+    if (c->rescue) cudaStreamDestroy(c->rescue);
+    for (auto ev : c->ev_mark) if (ev) cudaEventDestroy(ev);
+    if (c->ev_rescue_tail) cudaEventDestroy(c->ev_rescue_tail);
+    cudaFree(c->rescue_scratch);
     cudaFree(c->scratch);
     cudaFree(c->pool);
     cudaFree(c->own_blob);
     cudaFree(c->own_seq);
     cudaFree(c->seq2);
     cudaFree(c->seqx);
+    cudaFree(c->seqc);
     delete c;
 }
 
@@ -273,16 +299,21 @@ static int set_index(urmb_ctx *c, const urmb_index_desc *d) {
     CK(cudaSetDevice(c->device));
     cudaFree(c->seq2);
     cudaFree(c->seqx);
+    cudaFree(c->seqc);
     c->seq2 = nullptr;
     c->seqx = nullptr;
+    c->seqc = nullptr;
     const size_t nbytes = (size_t)d->seq_data_size + URMB_SEQ_PAD, nwords = packed_words(nbytes);
     CK(cudaMalloc(&c->seq2, nwords * 8));
     CK(cudaMalloc(&c->seqx, nwords * 4));
-    int e = launch_pack_genome(c->ix.seq, nbytes, c->seq2, c->seqx, c->compute);
+    CK(cudaMalloc(&c->seqc, coarse_words(nbytes) * 4));
+    CK(cudaMemsetAsync(c->seqc, 0, coarse_words(nbytes) * 4, c->compute));
+    int e = launch_pack_genome(c->ix.seq, nbytes, c->seq2, c->seqx, c->seqc, c->compute);
     if (e) return fail(c, URMB_E_CUDA, std::string("pack launch: ") + cudaGetErrorString((cudaError_t)e));
     CK(cudaStreamSynchronize(c->compute));
     c->ix.seq2 = c->seq2;
     c->ix.seqx = c->seqx;
+    c->ix.seqc = c->seqc;
     c->launches += 1;
     c->have_index = true;
     return URMB_OK;
@@ -504,31 +535,94 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     return URMB_OK;
 }
 
+struct TraceCtx {
+    Slot *s;
+    cudaStream_t stream;
+    cudaError_t err;
+};
+static void trace_mark(void *user, int klass, int phase) {
+    TraceCtx *t = (TraceCtx *)user;
+    Slot &s = *t->s;
+    const size_t i = 2 * s.nkev + (size_t)phase;
+    while (s.kev.size() <= i) {
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreate(&ev);
+        if (e != cudaSuccess) { t->err = e; return; }
+        s.kev.push_back(ev);
+    }
+    cudaError_t e = cudaEventRecord(s.kev[i], t->stream);
+    if (e != cudaSuccess) t->err = e;
+    if (phase == 0) {
+        if (s.kclass.size() <= s.nkev) s.kclass.resize(s.nkev + 1);
+        s.kclass[s.nkev] = klass;
+    } else {
+        ++s.nkev;
+    }
+}
+
 extern "C" int urmb_launch(urmb_ctx *c, int si) {
     if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
     Slot &s = c->slots[si];
     if (!s.staged) return fail(c, URMB_E_ARG, "slot not staged");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(c->compute, s.ev_h2d, 0));
+    if (s.launched) CK(cudaStreamWaitEvent(c->compute, s.ev_rescue, 0));   // an earlier launch of this very slot
     CK(cudaMemsetAsync(s.d_counters, 0, CT_COUNT * sizeof(uint32_t), c->compute));
     CK(cudaEventRecord(s.ev_k0, c->compute));
+    s.nkev = 0;
+    bool rescued = false;
     if (s.batch.n_reads) {
         DevProbe pr{s.d_tally, s.d_pos, s.d_ext};
         DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue};
         SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
+        TraceCtx tc{&s, c->compute, cudaSuccess};
+        LaunchTrace tr{trace_mark, &tc};
+        trace_mark(&tc, 0, 0);
         int e = launch_probe(c->ix, P, s.batch, pr, c->compute, c->sm_count);
+        trace_mark(&tc, 0, 1);
         if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
         CK(cudaEventRecord(s.ev_k1, c->compute));
-        e = launch_search(c->ix, P, s.batch, pr, o, R, c->compute, c->sm_count, nullptr);
+        e = launch_search(c->ix, P, s.batch, pr, o, R, c->compute, c->sm_count, nullptr, &tr);
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)-e));
         c->launches += 1 + (uint64_t)e;
+        CK(cudaEventRecord(s.ev_k2, c->compute));
+        // Mate rescue: few, long work items.  It runs on the low-priority side stream so that its tail overlaps the
+        // kernels of the next batch instead of idling the GPU.
+        SearchRes RR{c->rescue_scratch, c->n_rescue_warps, nullptr, 0};
+        CK(cudaStreamWaitEvent(c->rescue, s.ev_k2, 0));
+        tc.stream = c->rescue;
+        e = launch_rescue(c->ix, P, s.batch, pr, o, RR, c->rescue, c->sm_count, &tr);
+        if (e < 0) return fail(c, URMB_E_CUDA, std::string("rescue launch: ") + cudaGetErrorString((cudaError_t)-e));
+        if (tc.err != cudaSuccess) return fail(c, URMB_E_CUDA, std::string("event record: ") + cudaGetErrorString(tc.err));
+        c->launches += (uint64_t)e;
+        rescued = e > 0;
     } else {
         CK(cudaEventRecord(s.ev_k1, c->compute));
+        CK(cudaEventRecord(s.ev_k2, c->compute));
     }
-    CK(cudaEventRecord(s.ev_k2, c->compute));
+    if (!rescued) CK(cudaStreamWaitEvent(c->rescue, s.ev_k2, 0));
+    CK(cudaEventRecord(s.ev_rescue, c->rescue));
+    CK(cudaEventRecord(c->ev_rescue_tail, c->rescue));
+    c->rescue_used = true;
     s.launched = true;
     s.downloaded = false;
+    return URMB_OK;
+}
+
+extern "C" int urmb_mark(urmb_ctx *c, int which) {
+    if (!c || which < 0 || which > 1) return URMB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (c->rescue_used) CK(cudaStreamWaitEvent(c->compute, c->ev_rescue_tail, 0));
+    CK(cudaEventRecord(c->ev_mark[which], c->compute));
+    return URMB_OK;
+}
+
+extern "C" int urmb_mark_elapsed(urmb_ctx *c, float *ms) {
+    if (!c || !ms) return URMB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->ev_mark[1]));
+    CK(cudaEventElapsedTime(ms, c->ev_mark[0], c->ev_mark[1]));
     return URMB_OK;
 }
 
@@ -538,6 +632,7 @@ extern "C" int urmb_download(urmb_ctx *c, int si) {
     if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(s.copy, s.ev_k2, 0));
+    CK(cudaStreamWaitEvent(s.copy, s.ev_rescue, 0));
     CK(cudaMemcpyAsync(s.h_counters, s.d_counters, CT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.copy));
     CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.batch.n_reads * sizeof(urmb_result), cudaMemcpyDeviceToHost, s.copy));
     // Paths are few and short: copy the whole pool prefix a typical batch uses, the rest on demand in wait.
@@ -600,8 +695,19 @@ extern "C" int urmb_timing_last(urmb_ctx *c, int si, urmb_timing *t) {
     memset(t, 0, sizeof *t);
     if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
     CK(cudaEventSynchronize(s.ev_k2));
+    CK(cudaEventSynchronize(s.ev_rescue));
     cudaEventElapsedTime(&t->probe_ms, s.ev_k0, s.ev_k1);
     cudaEventElapsedTime(&t->search_ms, s.ev_k1, s.ev_k2);
+    for (size_t i = 0; i < s.nkev; ++i) {
+        float ms = 0.f;
+        const int k = s.kclass[i];
+        if (k < 0 || k >= URMB_KCLASSES) continue;
+        if (cudaEventElapsedTime(&ms, s.kev[2 * i], s.kev[2 * i + 1]) == cudaSuccess) {
+            t->kernel_ms[k] += ms;
+            t->kernel_launches[k] += 1;
+        }
+    }
+    t->rescue_ms = t->kernel_ms[6];
     if (cudaEventQuery(s.ev_h2d) == cudaSuccess) cudaEventElapsedTime(&t->h2d_ms, s.ev_h2d0, s.ev_h2d);
     if (cudaEventQuery(s.ev_d2h) == cudaSuccess && cudaEventQuery(s.ev_k2) == cudaSuccess)
         cudaEventElapsedTime(&t->d2h_ms, s.ev_k2, s.ev_d2h);

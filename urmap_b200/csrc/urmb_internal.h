@@ -19,6 +19,8 @@ struct DevIndex {
     const uint8_t *seq;    // upper-case genome, 1 B/base (+URMB_SEQ_PAD zero bytes)
     const uint64_t *seq2;  // derived: genome packed 2 bit/base, base g in word g>>5 at bits 63-2(g&31),62-2(g&31)
     const uint32_t *seqx;  // derived: bit (g&31) of word g>>5 set when byte g is not one of "ACGT" (exact byte path)
+    const uint32_t *seqc;  // derived: bit b set when any byte of [1024 b, 1024 (b+1)) is not one of "ACGT" (tiny, cache
+                           // resident: windows whose coarse bits are clear never load seqx)
     uint64_t slot_count;
     uint64_t magic;        // floor(2^64 / slot_count) for the Barrett reduction
     uint64_t shift_mask;   // 2^(2W)-1
@@ -131,11 +133,23 @@ struct SearchRes {
     MateSave *pool;
     uint32_t pool_pairs;   // chunk size of the paired-end second pass
 };
+// Optional hook called before (phase 0) and after (phase 1) every kernel launch of launch_search / launch_rescue with
+// the kernel class (URMB_KCLASSES numbering): the API layer records CUDA events there.
+struct LaunchTrace {
+    void (*mark)(void *user, int klass, int phase);
+    void *user;
+};
 int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
-                  const SearchRes &R, void *stream, int sm_count, int *warps_used);
+                  const SearchRes &R, void *stream, int sm_count, int *warps_used, const LaunchTrace *tr);
+// Paired-end mate rescue (State2::ScanPair) of the pairs queued by launch_search; may run on another stream (it only
+// touches the batch's own buffers and R.scratch).  Returns the number of kernels launched or a negative cudaError.
+int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                  const SearchRes &R, void *stream, int sm_count, const LaunchTrace *tr);
 int max_search_warps(int sm_count);
 // n_bytes = seq_data_size + URMB_SEQ_PAD; seq2 holds n_bytes/32+2 words, seqx n_bytes/32+2 words
 size_t packed_words(size_t n_bytes);
-int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint32_t *seqx, void *stream);
+// seqc holds coarse_words(n_bytes) words and must be zero-filled before the launch
+size_t coarse_words(size_t n_bytes);
+int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint32_t *seqx, uint32_t *seqc, void *stream);
 
 }  // namespace urmb

@@ -135,8 +135,9 @@ __device__ __forceinline__ void load_blob(const uint8_t *blob, uint64_t slot, ui
 // shift of two words and "next mismatch to the right" is a count-leading-zeros), plus an exception bit
 // for every byte that is not exactly 'A','C','G','T' (N runs, IUPAC codes, the '-' contig padding, the zero
 // padding after the last contig).  Windows that touch an exception bit are compared byte by byte instead.
+constexpr int kCoarseShift = 10;   // one coarse exception bit per 1024 bases
 __global__ void __launch_bounds__(256) pack_genome_kernel(const uint8_t *seq, size_t n_bytes, size_t n_words,
-                                                          uint64_t *seq2, uint32_t *seqx) {
+                                                          uint64_t *seq2, uint32_t *seqx, uint32_t *seqc) {
     for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
         uint64_t code = 0;
         uint32_t exc = 0;
@@ -153,6 +154,10 @@ __global__ void __launch_bounds__(256) pack_genome_kernel(const uint8_t *seq, si
         }
         seq2[w] = code;
         seqx[w] = exc;
+        if (exc) {
+            const size_t cb = (w * 32) >> kCoarseShift;
+            atomicOr(&seqc[cb >> 5], 1u << (cb & 31));
+        }
     }
 }
 
@@ -292,18 +297,21 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
     bool slow = rv.slow;
     if (!slow) {
         const uint64_t *g = ix.seq2 + (DBLo >> 5);
-        const uint32_t *x = ix.seqx + (DBLo >> 5);
         const uint32_t sh = 2 * (DBLo & 31);
         const uint64_t *rp = rv.pk + (Plus ? 0 : kPkWords);
         uint64_t gw[9];
-        uint32_t exc = 0;
+        // coarse exception bits of the (at most two) 1024-base blocks under words [DBLo>>5, (DBLo>>5)+nw]
+        const uint32_t cb0 = DBLo >> kCoarseShift, cb1 = (((DBLo >> 5) + (uint32_t)nw) << 5) >> kCoarseShift;
+        uint32_t exc = ((__ldg(ix.seqc + (cb0 >> 5)) >> (cb0 & 31)) | (__ldg(ix.seqc + (cb1 >> 5)) >> (cb1 & 31))) & 1u;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {   // all loads are issued before the first one is consumed
             gw[k] = 0;
-            if (k <= nw) {
-                gw[k] = __ldg(g + k);
-                exc |= __ldg(x + k);
-            }
+            if (k <= nw) gw[k] = __ldg(g + k);
+        }
+        if (exc) {   // rare: look at the fine bits
+            const uint32_t *x = ix.seqx + (DBLo >> 5);
+            exc = 0;
+            for (int k = 0; k <= nw; ++k) exc |= __ldg(x + k);
         }
         if (exc) slow = true;
         else {
@@ -2356,12 +2364,13 @@ __global__ void __launch_bounds__(128, 4) finish_kernel(const __grid_constant__ 
 int max_search_warps(int sm_count) { return sm_count * 32; }
 
 size_t packed_words(size_t n_bytes) { return n_bytes / 32 + 2; }
+size_t coarse_words(size_t n_bytes) { return ((packed_words(n_bytes) * 32) >> kCoarseShift) / 32 + 2; }
 
-int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint32_t *seqx, void *stream) {
+int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint32_t *seqx, uint32_t *seqc, void *stream) {
     const size_t n_words = packed_words(n_bytes);
     size_t blocks = (n_words + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    URMB_LAUNCH(pack_genome_kernel, (int)blocks, 256, 0, stream, seq, n_bytes, n_words, seq2, seqx);
+    URMB_LAUNCH(pack_genome_kernel, (int)blocks, 256, 0, stream, seq, n_bytes, n_words, seq2, seqx, seqc);
     return (int)cudaGetLastError();
 }
 
@@ -2378,8 +2387,8 @@ int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, cons
 
 // Persistent grid: SMs x resident blocks (bounded by the per-warp scratch), work claimed by atomicAdd.
 template <class K>
-static int launch_one(K kern, KArgs &A, const SmemPlan &pl, uint32_t max_items, const SearchRes &R, void *stream, int sm_count,
-                      int *warps_used) {
+static int launch_one(K kern, int klass, const LaunchTrace *tr, KArgs &A, const SmemPlan &pl, uint32_t max_items,
+                      const SearchRes &R, void *stream, int sm_count, int *warps_used) {
     const int wpb = 4;
     A.spw = (uint32_t)smem_per_warp(A.b, pl);
     const size_t smem = (size_t)A.spw * wpb;
@@ -2393,16 +2402,14 @@ static int launch_one(K kern, KArgs &A, const SmemPlan &pl, uint32_t max_items, 
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     if (warps_used) *warps_used = blocks * wpb;
+    if (tr) tr->mark(tr->user, klass, 0);
     URMB_LAUNCH(kern, blocks, wpb * 32, smem, stream, A);
+    if (tr) tr->mark(tr->user, klass, 1);
     return (int)cudaGetLastError();
 }
 
-// Returns the number of kernels launched or a negative cudaError.
-//   single-end: per chunk  seed_kernel_se -> align_kernel_se3 -> rows_kernel_se -> align_kernel_se6.
-//   paired-end: per chunk of R.pool_pairs pairs  pair_kernel -> align_kernel_a -> rows_kernel -> align_kernel_c ->
-//               finish_kernel (each a small kernel over the saved mate states); rescue_kernel once at the end.
-int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
-                  const SearchRes &R, void *stream, int sm_count, int *warps_used) {
+static KArgs make_kargs(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                        const SearchRes &R) {
     KArgs A;
     A.ix = ix; A.P = P; A.b = b; A.pr = pr; A.o = o;
     A.scratch = R.scratch;
@@ -2410,6 +2417,16 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     A.unit_base = 0;
     A.unit_count = b.n_units;
     A.spw = 0;
+    return A;
+}
+
+// Returns the number of kernels launched or a negative cudaError.
+//   single-end: per chunk  seed_kernel_se -> align_kernel_se3 -> rows_kernel_se -> align_kernel_se6.
+//   paired-end: per chunk of R.pool_pairs pairs  pair_kernel -> align_kernel_a -> rows_kernel -> align_kernel_c ->
+//               finish_kernel (each a small kernel over the saved mate states); launch_rescue does the rest.
+int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                  const SearchRes &R, void *stream, int sm_count, int *warps_used, const LaunchTrace *tr) {
+    KArgs A = make_kargs(ix, P, b, pr, o, R);
     int e;
 #define URMB_TRY(call) do { e = (call); if (e) return -e; } while (0)
     if (!R.pool || R.pool_pairs == 0) return -1;   // cudaErrorInvalidValue
@@ -2425,10 +2442,10 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
 #else
             for (int i = CT_CHUNK0; i < CT_COUNT; ++i) o.counters[i] = 0;
 #endif
-            URMB_TRY(launch_one(seed_kernel_se, A, SmemPlan{1, 1, 0}, cnt, R, stream, sm_count, warps_used));
-            URMB_TRY(launch_one(align_kernel_se3, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
-            URMB_TRY(launch_one(rows_kernel_se, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
-            URMB_TRY(launch_one(align_kernel_se6, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
+            URMB_TRY(launch_one(seed_kernel_se, 1, tr, A, SmemPlan{1, 1, 0}, cnt, R, stream, sm_count, warps_used));
+            URMB_TRY(launch_one(align_kernel_se3, 2, tr, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
+            URMB_TRY(launch_one(rows_kernel_se, 3, tr, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
+            URMB_TRY(launch_one(align_kernel_se6, 4, tr, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
             n += 4;
         }
         return n;
@@ -2442,19 +2459,24 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
 #else
         for (int i = CT_CHUNK0; i < CT_COUNT; ++i) o.counters[i] = 0;
 #endif
-        URMB_TRY(launch_one(pair_kernel, A, SmemPlan{2, 1, 0}, cnt, R, stream, sm_count, warps_used));
-        URMB_TRY(launch_one(align_kernel_a, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
-        URMB_TRY(launch_one(rows_kernel, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
-        URMB_TRY(launch_one(align_kernel_c, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
-        URMB_TRY(launch_one(finish_kernel, A, SmemPlan{0, 0, 0}, cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(pair_kernel, 1, tr, A, SmemPlan{2, 1, 0}, cnt, R, stream, sm_count, warps_used));
+        URMB_TRY(launch_one(align_kernel_a, 2, tr, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(rows_kernel, 3, tr, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(align_kernel_c, 4, tr, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(finish_kernel, 5, tr, A, SmemPlan{0, 0, 0}, cnt, R, stream, sm_count, nullptr));
         n += 5;
     }
-    if (P.pe_method != 5) {
-        URMB_TRY(launch_one(rescue_kernel, A, SmemPlan{2, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
-        ++n;
-    }
-#undef URMB_TRY
     return n;
+}
+
+int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                  const SearchRes &R, void *stream, int sm_count, const LaunchTrace *tr) {
+    if (!b.paired || P.pe_method == 5) return 0;
+    KArgs A = make_kargs(ix, P, b, pr, o, R);
+    int e;
+    URMB_TRY(launch_one(rescue_kernel, 6, tr, A, SmemPlan{2, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
+    return 1;
+#undef URMB_TRY
 }
 
 }  // namespace urmb

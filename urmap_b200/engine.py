@@ -55,14 +55,18 @@ class Contig(C.Structure):
 
 
 class Timing(C.Structure):
-    _fields_ = [("probe_ms", C.c_float), ("search_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
+    _fields_ = [("probe_ms", C.c_float), ("search_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("rescue_ms", C.c_float), ("kernel_ms", C.c_float * 7), ("kernel_launches", C.c_uint32 * 7)]
+
+
+KERNEL_CLASSES = ("probe", "pair", "align_a", "rows", "align_c", "finish", "rescue")
 
 
 EXPORTS = [
     "urmb_index_load_host", "urmb_index_free_host", "urmb_index_info", "urmb_index_contig", "urmb_ctx_create",
     "urmb_ctx_destroy", "urmb_last_error", "urmb_index_upload", "urmb_index_attach", "urmb_index_broadcast",
     "urmb_index_device_desc", "urmb_map_se", "urmb_map_pe", "urmb_submit", "urmb_wait", "urmb_upload",
-    "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count",
+    "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
 ]
 
 _lib = None
@@ -99,6 +103,8 @@ def lib():
         L.urmb_timing_last.argtypes = [vp, C.c_int, C.POINTER(Timing)]
         L.urmb_launch_count.restype = C.c_uint64
         L.urmb_launch_count.argtypes = [vp]
+        L.urmb_mark.argtypes = [vp, C.c_int]
+        L.urmb_mark_elapsed.argtypes = [vp, C.POINTER(C.c_float)]
         for nm in EXPORTS:
             if nm not in ("urmb_last_error", "urmb_launch_count", "urmb_index_free_host", "urmb_ctx_destroy"):
                 getattr(L, nm).restype = C.c_int
@@ -235,7 +241,20 @@ class Context:
     def timing(self, slot):
         t = Timing()
         _check(lib().urmb_timing_last(self.c, slot, C.byref(t)), self.c)
-        return {"probe_ms": t.probe_ms, "search_ms": t.search_ms, "h2d_ms": t.h2d_ms, "d2h_ms": t.d2h_ms}
+        return {"probe_ms": t.probe_ms, "search_ms": t.search_ms, "h2d_ms": t.h2d_ms, "d2h_ms": t.d2h_ms,
+                "rescue_ms": t.rescue_ms,
+                "kernel_ms": {k: float(t.kernel_ms[i]) for i, k in enumerate(KERNEL_CLASSES)},
+                "kernel_launches": {k: int(t.kernel_launches[i]) for i, k in enumerate(KERNEL_CLASSES)}}
+
+    def mark(self, which):
+        """Context-wide time mark (0 = start, 1 = end) after all work submitted so far."""
+        _check(lib().urmb_mark(self.c, which), self.c)
+
+    def mark_elapsed(self):
+        """Device milliseconds between mark 0 and mark 1 (synchronises)."""
+        ms = C.c_float()
+        _check(lib().urmb_mark_elapsed(self.c, C.byref(ms)), self.c)
+        return float(ms.value)
 
     def launch_count(self):
         return int(lib().urmb_launch_count(self.c))

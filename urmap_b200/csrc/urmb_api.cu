@@ -239,8 +239,10 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     for (auto &ev : c->ev_mark) CK(cudaEventCreate(&ev));
     CK(cudaEventCreateWithFlags(&c->ev_rescue_tail, cudaEventDisableTiming));
     c->n_scratch_warps = max_search_warps(c->sm_count);
-    c->n_rescue_warps = c->sm_count * 8;   // two blocks per SM: the kernel is a long tail of few, long work items
-    if (const char *f = getenv("URMB_RESCUE_WARPS_PER_SM")) c->n_rescue_warps = c->sm_count * std::max(4, atoi(f));
+    // The rescue kernel is a queue of few, long work items that runs beside the next batch: a small persistent grid
+    // (one block on every second SM) takes few registers away from the main kernels and still drains the queue in time.
+    c->n_rescue_warps = c->sm_count * 2;
+    if (const char *f = getenv("URMB_RESCUE_WARPS")) c->n_rescue_warps = std::max(4, atoi(f) & ~3);
     CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps));
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));

@@ -116,6 +116,15 @@ __device__ __forceinline__ uint32_t ldg_stream_u8(const uint8_t *p) {
 #endif
 }
 
+// L2 prefetch of the 128-byte line holding p: the next work item's rows are requested while the current one is processed.
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+#ifndef URMB_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // 5-byte record at byte offset 5*slot: two aligned 32-bit loads (the table is padded).
 template <bool STREAM = true>
 __device__ __forceinline__ void load_blob(const uint8_t *blob, uint64_t slot, uint32_t &tally, uint32_t &pos) {
@@ -2174,6 +2183,17 @@ __device__ __forceinline__ void make_env(Env &E, const DevIndex &ix, const DevPa
     E.lane = lane;
 }
 
+// Probe output rows of read r (tally 2*qcap B, pos and ext 8*qcap B each), one 128-byte line per lane.
+__device__ __forceinline__ void prefetch_probe_rows(const DevBatch &b, const DevProbe &pr, uint32_t r, int lane, bool want_ext) {
+    const size_t base = (size_t)r * 2 * b.qcap;
+    const uint32_t lt = (2 * b.qcap + 127) >> 7, lp = (8 * b.qcap + 127) >> 7;   // lines of tally / pos (= ext)
+    for (uint32_t l = (uint32_t)lane; l < lt + (want_ext ? 2 : 1) * lp; l += 32) {
+        if (l < lt) prefetch_l2(pr.tally + base + ((size_t)l << 7));
+        else if (l < lt + lp) prefetch_l2(reinterpret_cast<const uint8_t *>(pr.pos + base) + ((size_t)(l - lt) << 7));
+        else prefetch_l2(reinterpret_cast<const uint8_t *>(pr.ext + base) + ((size_t)(l - lt - lp) << 7));
+    }
+}
+
 struct KArgs {   // one parameter block for every search kernel
     DevIndex ix;
     DevParams P;
@@ -2204,11 +2224,19 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
     const uint32_t n_work = (MODE == 2) ? o.counters[CT_RESCUE] : A.unit_count;
 
+    // work items are claimed one ahead so that the next item's probe rows are on their way while this one is processed
+    uint32_t nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
+    nxt = __shfl_sync(FULL, nxt, 0);
     for (;;) {
-        uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
-        u = __shfl_sync(FULL, u, 0);
+        uint32_t u = nxt;
         if (u >= n_work) break;
+        if (lane == 0) nxt = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
+        nxt = __shfl_sync(FULL, nxt, 0);
+        if (MODE != 2 && nxt < n_work) {
+            prefetch_probe_rows(b, A.pr, A.unit_base + nxt, lane, true);
+            if (MODE == 1) prefetch_probe_rows(b, A.pr, b.n_units + A.unit_base + nxt, lane, true);
+        }
         u = (MODE == 2) ? o.rescue[u] : A.unit_base + u;
         if (MODE == 0) {
             Mate m;
@@ -2262,11 +2290,25 @@ __device__ __forceinline__ void stage_body(const KArgs &A) {
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
     const uint32_t n_work = (SE ? 1u : 2u) * A.o.counters[CT_TODO];
+    uint32_t nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
+    nxt = __shfl_sync(FULL, nxt, 0);
     for (;;) {
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
-        k = __shfl_sync(FULL, k, 0);
+        const uint32_t k = nxt;
         if (k >= n_work) break;
+        if (lane == 0) nxt = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
+        nxt = __shfl_sync(FULL, nxt, 0);
+        if (nxt < n_work) {   // next item: saved header + first hit / HSP lines; the rows stage also reads the probe rows
+            const MateSave *nv = A.pool + nxt;
+            if (lane == 0) prefetch_l2(&nv->h);
+            else if (lane == 1) prefetch_l2(nv->s.hit_pos);
+            else if (lane == 2) prefetch_l2(nv->s.hsp_dbstart);
+            else if (lane == 3) prefetch_l2(nv->s.hsp_qstart);
+            if (STAGE == 1 || STAGE == 4) {
+                const uint32_t un = A.o.todo[SE ? nxt : nxt >> 1];
+                prefetch_probe_rows(b, A.pr, (!SE && (nxt & 1u)) ? b.n_units + un : un, lane, false);
+            }
+        }
         MateSave *sv = A.pool + k;
         const MateHdr h = sv->h;
         const uint32_t u = A.o.todo[SE ? k : k >> 1];

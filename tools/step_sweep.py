@@ -37,7 +37,8 @@ for k in range(3):
 ref = None
 for val in (args.values.split(",") if args.values else [""]):
     if val:
-        os.environ[args.var] = val
+        for kv, v in zip(args.var.split("+"), val.split("+")):   # several variables: A+B with values a+b
+            os.environ[kv] = v
     ctx = engine.Context(0)
     ctx.attach_index(24, 32, sds, slots, blob.data_ptr(), seq.data_ptr())
     for s in range(3):

@@ -169,6 +169,7 @@ struct urmb_ctx {
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
     cudaEvent_t ev_rescue_tail = nullptr;     // last event recorded on the rescue stream
     bool rescue_used = false;
+    bool rescue_inline = false;               // URMB_RESCUE_INLINE: run the rescue kernel on the compute stream
     WarpScratch *scratch = nullptr;
     int n_scratch_warps = 0;
     WarpScratch *rescue_scratch = nullptr;
@@ -240,9 +241,10 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     CK(cudaEventCreateWithFlags(&c->ev_rescue_tail, cudaEventDisableTiming));
     c->n_scratch_warps = max_search_warps(c->sm_count);
     // The rescue kernel is a queue of few, long work items that runs beside the next batch: a small persistent grid
-    // (one block on every second SM) takes few registers away from the main kernels and still drains the queue in time.
-    c->n_rescue_warps = c->sm_count * 2;
+    // (one block per SM) takes few registers away from the main kernels and still drains the queue in time.
+    c->n_rescue_warps = c->sm_count * 4;
     if (const char *f = getenv("URMB_RESCUE_WARPS")) c->n_rescue_warps = std::max(4, atoi(f) & ~3);
+    if (const char *f = getenv("URMB_RESCUE_INLINE")) c->rescue_inline = atoi(f) != 0;
     CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps));
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
@@ -592,9 +594,11 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         // Mate rescue: few, long work items.  It runs on the low-priority side stream so that its tail overlaps the
         // kernels of the next batch instead of idling the GPU.
         SearchRes RR{c->rescue_scratch, c->n_rescue_warps, nullptr, 0};
-        CK(cudaStreamWaitEvent(c->rescue, s.ev_k2, 0));
-        tc.stream = c->rescue;
-        e = launch_rescue(c->ix, P, s.batch, pr, o, RR, c->rescue, c->sm_count, &tr);
+        cudaStream_t rs = c->rescue_inline ? c->compute : c->rescue;
+        CK(cudaStreamWaitEvent(rs, s.ev_k2, 0));
+        tc.stream = rs;
+        e = launch_rescue(c->ix, P, s.batch, pr, o, c->rescue_inline ? R : RR, rs, c->sm_count, &tr);
+        if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, c->compute));
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("rescue launch: ") + cudaGetErrorString((cudaError_t)-e));
         if (tc.err != cudaSuccess) return fail(c, URMB_E_CUDA, std::string("event record: ") + cudaGetErrorString(tc.err));
         c->launches += (uint64_t)e;

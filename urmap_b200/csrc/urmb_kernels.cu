@@ -116,15 +116,6 @@ __device__ __forceinline__ uint32_t ldg_stream_u8(const uint8_t *p) {
 #endif
 }
 
-// L2 prefetch of the 128-byte line holding p: the next work item's rows are requested while the current one is processed.
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-#ifndef URMB_EMU
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
 // 5-byte record at byte offset 5*slot: two aligned 32-bit loads (the table is padded).
 template <bool STREAM = true>
 __device__ __forceinline__ void load_blob(const uint8_t *blob, uint64_t slot, uint32_t &tally, uint32_t &pos) {
@@ -311,7 +302,8 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
         uint64_t gw[9];
         // coarse exception bits of the (at most two) 1024-base blocks under words [DBLo>>5, (DBLo>>5)+nw]
         const uint32_t cb0 = DBLo >> kCoarseShift, cb1 = (((DBLo >> 5) + (uint32_t)nw) << 5) >> kCoarseShift;
-        uint32_t exc = ((__ldg(ix.seqc + (cb0 >> 5)) >> (cb0 & 31)) | (__ldg(ix.seqc + (cb1 >> 5)) >> (cb1 & 31))) & 1u;
+        uint32_t exc = 1u;
+        if (!(P.flags & 32u)) exc = ((__ldg(ix.seqc + (cb0 >> 5)) >> (cb0 & 31)) | (__ldg(ix.seqc + (cb1 >> 5)) >> (cb1 & 31))) & 1u;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {   // all loads are issued before the first one is consumed
             gw[k] = 0;
@@ -1622,43 +1614,63 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
     bool have_prev = false;
     uint32_t prev_diag = 0;
     const uint32_t lt = (1u << E.lane) - 1u;
-    for (uint32_t v0 = 0; v0 < 2 * QWC; v0 += 32) {
-        const uint32_t v = v0 + E.lane, k = v >> 1;
-        const int sgn = (int)(v & 1u);
-        const bool valid = k < QWC;
-        const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
-        const uint32_t T = valid ? m_tally(m, sgn, QPos) : 0u;
-        const uint32_t Pz = valid ? m_pos(m, sgn, QPos) : 0u;
-        const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE
-        const bool b1 = mine && T == T_BOTH1;
-        const uint32_t diag = Pz - QPos;
-        const uint32_t b1mask = __ballot_sync(FULL, b1);
-        const uint32_t below = b1mask & lt;
-        const uint32_t pd = __shfl_sync(FULL, diag, below ? 31 - __clz(below) : 0);
-        const bool hasp = below ? true : have_prev;
-        const uint32_t pdiag = below ? pd : prev_diag;
-        const bool ret = b1 && (!hasp || diag != pdiag);
-        const uint32_t retmask = __ballot_sync(FULL, ret);
-        const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
-        const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
-        const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
-        if (ret) {
-            const int i = m.nSeeds + __popc(retmask & lt);
-            m.sd_db[i] = Pz;
-            m.sd_ext[i] = m_ext(m, sgn, QPos);
-            m.sd_qs[i] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
+    // The probe rows live in HBM: the loads of eight 32-visit rounds are issued together, then the rounds are replayed
+    // in order (the iterator state only flows from one round to the next through have_prev / prev_diag).
+    constexpr int kRounds = 8;
+    for (uint32_t vb = 0; vb < 2 * QWC; vb += 32 * kRounds) {
+        uint32_t Tt[kRounds], Pp[kRounds];
+        uint16_t Qq[kRounds];
+#pragma unroll
+        for (int it = 0; it < kRounds; ++it) {
+            const uint32_t v = vb + 32 * it + E.lane, k = v >> 1;
+            const int sgn = (int)(v & 1u);
+            const bool valid = k < QWC;
+            const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
+            Qq[it] = (uint16_t)QPos;
+            Tt[it] = valid ? m_tally(m, sgn, QPos) : 0u;
+            Pp[it] = valid ? m_pos(m, sgn, QPos) : 0u;
         }
-        if (pend) {
-            const int i = m.nPend[sgn] + __popc((sgn ? pm : pp) & lt);
-            m.g->pend[sgn][i] = (uint8_t)QPos;
+#pragma unroll
+        for (int it = 0; it < kRounds; ++it) {
+            if (vb + 32 * it >= 2 * QWC) break;
+            const int sgn = E.lane & 1;
+            const uint32_t QPos = Qq[it], T = Tt[it], Pz = Pp[it];
+            const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE
+            const bool b1 = mine && T == T_BOTH1;
+            const uint32_t diag = Pz - QPos;
+            const uint32_t b1mask = __ballot_sync(FULL, b1);
+            const uint32_t below = b1mask & lt;
+            const uint32_t pd = __shfl_sync(FULL, diag, below ? 31 - __clz(below) : 0);
+            const bool hasp = below ? true : have_prev;
+            const uint32_t pdiag = below ? pd : prev_diag;
+            const bool ret = b1 && (!hasp || diag != pdiag);
+            const uint32_t retmask = __ballot_sync(FULL, ret);
+            const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
+            const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
+            const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
+            if (ret) {
+                const int i = m.nSeeds + __popc(retmask & lt);
+                m.sd_db[i] = Pz;
+                m.sd_qs[i] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
+            }
+            if (pend) {
+                const int i = m.nPend[sgn] + __popc((sgn ? pm : pp) & lt);
+                m.g->pend[sgn][i] = (uint8_t)QPos;
+            }
+            m.nSeeds += __popc(retmask);
+            m.nPend[0] += __popc(pp);
+            m.nPend[1] += __popc(pm);
+            if (b1mask) {
+                have_prev = true;
+                prev_diag = __shfl_sync(FULL, diag, 31 - __clz(b1mask));
+            }
         }
-        m.nSeeds += __popc(retmask);
-        m.nPend[0] += __popc(pp);
-        m.nPend[1] += __popc(pm);
-        if (b1mask) {
-            have_prev = true;
-            prev_diag = __shfl_sync(FULL, diag, 31 - __clz(b1mask));
-        }
+    }
+    __syncwarp();
+    // the probe kernel's pure extension results of the returned seeds, all loads in flight at once
+    for (int i = E.lane; i < m.nSeeds; i += 32) {
+        const uint32_t qs = m.sd_qs[i];
+        m.sd_ext[i] = m_ext(m, (int)(qs >> 15), qs & 0x7FFFu);
     }
     seeds_init_dead(E, m);
 }
@@ -2183,17 +2195,6 @@ __device__ __forceinline__ void make_env(Env &E, const DevIndex &ix, const DevPa
     E.lane = lane;
 }
 
-// Probe output rows of read r (tally 2*qcap B, pos and ext 8*qcap B each), one 128-byte line per lane.
-__device__ __forceinline__ void prefetch_probe_rows(const DevBatch &b, const DevProbe &pr, uint32_t r, int lane, bool want_ext) {
-    const size_t base = (size_t)r * 2 * b.qcap;
-    const uint32_t lt = (2 * b.qcap + 127) >> 7, lp = (8 * b.qcap + 127) >> 7;   // lines of tally / pos (= ext)
-    for (uint32_t l = (uint32_t)lane; l < lt + (want_ext ? 2 : 1) * lp; l += 32) {
-        if (l < lt) prefetch_l2(pr.tally + base + ((size_t)l << 7));
-        else if (l < lt + lp) prefetch_l2(reinterpret_cast<const uint8_t *>(pr.pos + base) + ((size_t)(l - lt) << 7));
-        else prefetch_l2(reinterpret_cast<const uint8_t *>(pr.ext + base) + ((size_t)(l - lt - lp) << 7));
-    }
-}
-
 struct KArgs {   // one parameter block for every search kernel
     DevIndex ix;
     DevParams P;
@@ -2224,19 +2225,11 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
     const uint32_t n_work = (MODE == 2) ? o.counters[CT_RESCUE] : A.unit_count;
 
-    // work items are claimed one ahead so that the next item's probe rows are on their way while this one is processed
-    uint32_t nxt = 0;
-    if (lane == 0) nxt = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
-    nxt = __shfl_sync(FULL, nxt, 0);
     for (;;) {
-        uint32_t u = nxt;
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
+        u = __shfl_sync(FULL, u, 0);
         if (u >= n_work) break;
-        if (lane == 0) nxt = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
-        nxt = __shfl_sync(FULL, nxt, 0);
-        if (MODE != 2 && nxt < n_work) {
-            prefetch_probe_rows(b, A.pr, A.unit_base + nxt, lane, true);
-            if (MODE == 1) prefetch_probe_rows(b, A.pr, b.n_units + A.unit_base + nxt, lane, true);
-        }
         u = (MODE == 2) ? o.rescue[u] : A.unit_base + u;
         if (MODE == 0) {
             Mate m;
@@ -2290,25 +2283,11 @@ __device__ __forceinline__ void stage_body(const KArgs &A) {
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
     const uint32_t n_work = (SE ? 1u : 2u) * A.o.counters[CT_TODO];
-    uint32_t nxt = 0;
-    if (lane == 0) nxt = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
-    nxt = __shfl_sync(FULL, nxt, 0);
     for (;;) {
-        const uint32_t k = nxt;
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
+        k = __shfl_sync(FULL, k, 0);
         if (k >= n_work) break;
-        if (lane == 0) nxt = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
-        nxt = __shfl_sync(FULL, nxt, 0);
-        if (nxt < n_work) {   // next item: saved header + first hit / HSP lines; the rows stage also reads the probe rows
-            const MateSave *nv = A.pool + nxt;
-            if (lane == 0) prefetch_l2(&nv->h);
-            else if (lane == 1) prefetch_l2(nv->s.hit_pos);
-            else if (lane == 2) prefetch_l2(nv->s.hsp_dbstart);
-            else if (lane == 3) prefetch_l2(nv->s.hsp_qstart);
-            if (STAGE == 1 || STAGE == 4) {
-                const uint32_t un = A.o.todo[SE ? nxt : nxt >> 1];
-                prefetch_probe_rows(b, A.pr, (!SE && (nxt & 1u)) ? b.n_units + un : un, lane, false);
-            }
-        }
         MateSave *sv = A.pool + k;
         const MateHdr h = sv->h;
         const uint32_t u = A.o.todo[SE ? k : k >> 1];

@@ -1614,63 +1614,43 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
     bool have_prev = false;
     uint32_t prev_diag = 0;
     const uint32_t lt = (1u << E.lane) - 1u;
-    // The probe rows live in HBM: the loads of eight 32-visit rounds are issued together, then the rounds are replayed
-    // in order (the iterator state only flows from one round to the next through have_prev / prev_diag).
-    constexpr int kRounds = 8;
-    for (uint32_t vb = 0; vb < 2 * QWC; vb += 32 * kRounds) {
-        uint32_t Tt[kRounds], Pp[kRounds];
-        uint16_t Qq[kRounds];
-#pragma unroll
-        for (int it = 0; it < kRounds; ++it) {
-            const uint32_t v = vb + 32 * it + E.lane, k = v >> 1;
-            const int sgn = (int)(v & 1u);
-            const bool valid = k < QWC;
-            const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
-            Qq[it] = (uint16_t)QPos;
-            Tt[it] = valid ? m_tally(m, sgn, QPos) : 0u;
-            Pp[it] = valid ? m_pos(m, sgn, QPos) : 0u;
+    for (uint32_t v0 = 0; v0 < 2 * QWC; v0 += 32) {
+        const uint32_t v = v0 + E.lane, k = v >> 1;
+        const int sgn = (int)(v & 1u);
+        const bool valid = k < QWC;
+        const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
+        const uint32_t T = valid ? m_tally(m, sgn, QPos) : 0u;
+        const uint32_t Pz = valid ? m_pos(m, sgn, QPos) : 0u;
+        const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE
+        const bool b1 = mine && T == T_BOTH1;
+        const uint32_t diag = Pz - QPos;
+        const uint32_t b1mask = __ballot_sync(FULL, b1);
+        const uint32_t below = b1mask & lt;
+        const uint32_t pd = __shfl_sync(FULL, diag, below ? 31 - __clz(below) : 0);
+        const bool hasp = below ? true : have_prev;
+        const uint32_t pdiag = below ? pd : prev_diag;
+        const bool ret = b1 && (!hasp || diag != pdiag);
+        const uint32_t retmask = __ballot_sync(FULL, ret);
+        const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
+        const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
+        const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
+        if (ret) {
+            const int i = m.nSeeds + __popc(retmask & lt);
+            m.sd_db[i] = Pz;
+            m.sd_ext[i] = m_ext(m, sgn, QPos);
+            m.sd_qs[i] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
         }
-#pragma unroll
-        for (int it = 0; it < kRounds; ++it) {
-            if (vb + 32 * it >= 2 * QWC) break;
-            const int sgn = E.lane & 1;
-            const uint32_t QPos = Qq[it], T = Tt[it], Pz = Pp[it];
-            const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE
-            const bool b1 = mine && T == T_BOTH1;
-            const uint32_t diag = Pz - QPos;
-            const uint32_t b1mask = __ballot_sync(FULL, b1);
-            const uint32_t below = b1mask & lt;
-            const uint32_t pd = __shfl_sync(FULL, diag, below ? 31 - __clz(below) : 0);
-            const bool hasp = below ? true : have_prev;
-            const uint32_t pdiag = below ? pd : prev_diag;
-            const bool ret = b1 && (!hasp || diag != pdiag);
-            const uint32_t retmask = __ballot_sync(FULL, ret);
-            const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
-            const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
-            const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
-            if (ret) {
-                const int i = m.nSeeds + __popc(retmask & lt);
-                m.sd_db[i] = Pz;
-                m.sd_qs[i] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
-            }
-            if (pend) {
-                const int i = m.nPend[sgn] + __popc((sgn ? pm : pp) & lt);
-                m.g->pend[sgn][i] = (uint8_t)QPos;
-            }
-            m.nSeeds += __popc(retmask);
-            m.nPend[0] += __popc(pp);
-            m.nPend[1] += __popc(pm);
-            if (b1mask) {
-                have_prev = true;
-                prev_diag = __shfl_sync(FULL, diag, 31 - __clz(b1mask));
-            }
+        if (pend) {
+            const int i = m.nPend[sgn] + __popc((sgn ? pm : pp) & lt);
+            m.g->pend[sgn][i] = (uint8_t)QPos;
         }
-    }
-    __syncwarp();
-    // the probe kernel's pure extension results of the returned seeds, all loads in flight at once
-    for (int i = E.lane; i < m.nSeeds; i += 32) {
-        const uint32_t qs = m.sd_qs[i];
-        m.sd_ext[i] = m_ext(m, (int)(qs >> 15), qs & 0x7FFFu);
+        m.nSeeds += __popc(retmask);
+        m.nPend[0] += __popc(pp);
+        m.nPend[1] += __popc(pm);
+        if (b1mask) {
+            have_prev = true;
+            prev_diag = __shfl_sync(FULL, diag, 31 - __clz(b1mask));
+        }
     }
     seeds_init_dead(E, m);
 }

@@ -163,7 +163,8 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     std::vector<uint8_t> tally((size_t)nreads * 2 * b.qcap);
     std::vector<uint32_t> pos((size_t)nreads * 2 * b.qcap);
     std::vector<uint32_t> ext((size_t)nreads * 2 * b.qcap);
-    DevProbe pr{tally.data(), pos.data(), ext.data()};
+    std::vector<uint8_t> view((size_t)nreads * view_stride_for(b.seqcap) + 64, 0xCD);
+    DevProbe pr{tally.data(), pos.data(), ext.data(), view.data(), view_stride_for(b.seqcap)};
     uint32_t ct[CT_COUNT];
     memset(ct, 0, sizeof ct);
     std::vector<uint32_t> todo(n_units + 1), rescue(n_units + 1);

@@ -143,6 +143,7 @@ struct Slot {
     uint8_t *d_seqs = nullptr; size_t d_seqs_cap = 0;
     uint32_t *d_offs = nullptr; size_t d_offs_cap = 0;
     uint8_t *d_tally = nullptr; uint32_t *d_pos = nullptr; uint32_t *d_ext = nullptr; size_t d_probe_cap = 0;
+    uint8_t *d_view = nullptr; size_t d_view_cap = 0;
     urmb_result *d_res = nullptr; size_t d_res_cap = 0;
     uint16_t *d_runs = nullptr; size_t d_runs_cap = 0;
     uint32_t *d_counters = nullptr;
@@ -263,7 +264,7 @@ static void free_slot(Slot &s) {
     for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h, s.ev_rescue}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s.kev) cudaEventDestroy(ev);
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
-    cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext);
+    cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext); cudaFree(s.d_view);
     cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo); cudaFree(s.d_rescue);
 }
 
@@ -509,6 +510,7 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
         CK(cudaMalloc(&s.d_ext, ncap * 4));
         s.d_probe_cap = ncap;
     }
+    if ((rc = grow_dev(c, s.d_view, s.d_view_cap, (size_t)nreads * view_stride_for(b.seqcap) + 64))) return rc;
     if ((rc = grow_dev(c, s.d_res, s.d_res_cap, (size_t)nreads + 1))) return rc;
     if ((rc = grow_dev(c, s.d_todo, s.d_todo_cap, (size_t)n + 1))) return rc;
     if ((rc = grow_dev(c, s.d_rescue, s.d_rescue_cap, (size_t)n + 1))) return rc;
@@ -576,7 +578,7 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     s.nkev = 0;
     bool rescued = false;
     if (s.batch.n_reads) {
-        DevProbe pr{s.d_tally, s.d_pos, s.d_ext};
+        DevProbe pr{s.d_tally, s.d_pos, s.d_ext, s.d_view, view_stride_for(s.batch.seqcap)};
         DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue};
         SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;

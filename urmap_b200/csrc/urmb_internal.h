@@ -50,7 +50,11 @@ struct DevProbe {   // output of the probe+extend kernel, [n_reads][2 strands][q
     uint8_t *tally;
     uint32_t *pos;
     uint32_t *ext;     // BOTH1 slots: packed state-independent result of the gapless extension (EXT_NONE otherwise)
+    uint8_t *view;     // [n_reads][view_stride] staged read: packed strands, invalid-letter bits, flags, reverse complement
+    uint32_t view_stride;
 };
+constexpr uint32_t kViewHdr = 224;   // packed strands (144) + bad bits (72) + flags (4) + pad; then seqcap bytes of rc
+inline uint32_t view_stride_for(uint32_t seqcap) { return kViewHdr + seqcap; }
 
 // Device counters of one batch slot (u32 each).  CT_RUNS / CT_OVERFLOW / CT_*_TOTAL live for the whole batch; the
 // others are per chunk and are zeroed by the launcher between chunks.

@@ -426,6 +426,14 @@ __global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevParams P, De
         const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
         ReadView rv;
         stage_read(lane, b.seqs + off, L, b.seqcap, s_q, s_rc, s_pk, s_bad, rv);
+        {   // the staged read is kept for the search kernels (they would otherwise redo stage_read up to four times)
+            uint32_t *vw = reinterpret_cast<uint32_t *>(pr.view + (size_t)r * pr.view_stride);
+            const uint32_t *src32 = reinterpret_cast<const uint32_t *>(sw);
+            for (uint32_t i = lane; i < kReadViewBytes / 4; i += 32) vw[i] = src32[i];
+            if (lane == 0) vw[kReadViewBytes / 4] = (rv.slow ? 1u : 0u) | (rv.hasbad ? 2u : 0u);
+            const uint32_t *rc32 = reinterpret_cast<const uint32_t *>(s_rc);
+            for (uint32_t i = lane; i < b.seqcap / 4; i += 32) vw[kViewHdr / 4 + i] = rc32[i];
+        }
         const uint32_t QWC = (L >= W) ? L - W + 1 : 0;
         const size_t base = (size_t)r * 2 * b.qcap;
         uint32_t nc = 0;
@@ -2070,7 +2078,24 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
         p8 += 2 * (size_t)b.qcap * 2;
     }
     uint8_t *s_q = p8, *s_rc = p8 + b.seqcap;
-    stage_read(E.lane, b.seqs + off, L, b.seqcap, s_q, s_rc, s_pk, s_bad, m.rv);
+    {   // the probe kernel's staged read: packed strands + bad bits + flags + reverse complement; forward bytes as given
+        const uint32_t *vw = reinterpret_cast<const uint32_t *>(pr.view + (size_t)r * pr.view_stride);
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(sm);
+        for (uint32_t i = E.lane; i < kReadViewBytes / 4; i += 32) dst32[i] = __ldg(vw + i);
+        const uint32_t fl = __ldg(vw + kReadViewBytes / 4);
+        uint32_t *rc32 = reinterpret_cast<uint32_t *>(s_rc);
+        for (uint32_t i = E.lane; i < b.seqcap / 4; i += 32) rc32[i] = __ldg(vw + kViewHdr / 4 + i);
+        const uint8_t *src = b.seqs + off;
+        for (uint32_t i = E.lane; i < L; i += 32) s_q[i] = src[i];
+        m.rv.q = s_q;
+        m.rv.rc = s_rc;
+        m.rv.pk = s_pk;
+        m.rv.bad = s_bad;
+        m.rv.QL = L;
+        m.rv.slow = (fl & 1u) != 0;
+        m.rv.hasbad = (fl & 2u) != 0;
+        __syncwarp();
+    }
     const size_t base = (size_t)r * 2 * b.qcap;
     m.q = s_q;
     m.rc = s_rc;

@@ -87,6 +87,10 @@ inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long
 inline int __ffsll(long long v) { return v ? __builtin_ctzll((unsigned long long)v) + 1 : 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double __dmul_rn(double a, double b) { return a * b; }
+inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift) {
+    shift &= 31;
+    return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
+}
 using std::max;
 using std::min;
 inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }

@@ -291,24 +291,30 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
     if (SeedPosDB < SeedPosQ) return EXT_NONE;   // extendpen.cpp:11
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
     const int QL = (int)rv.QL, W = (int)ix.word_len, MM = P.MM, XD = P.XDROP;
-    const int nw = (QL + 31) >> 5;   // <= 8
+    const int nw = (QL + 31) >> 5;   // <= 8 packed 64-bit words
+    const int nh = (QL + 15) >> 4;   // <= 16 half-words of 16 bases
     const int maxmis = min(PenBound / -MM, 126);   // nmis > maxmis  <=>  nmis * -MM > PenBound
-    uint64_t mm[8];
+    // Mismatch flags, 16 bases per 32-bit word: base t of half-word h (read position 16 h + t) at bit 30 - 2 t.
+    uint32_t mm[16];
     bool slow = rv.slow;
     if (!slow) {
         const uint64_t *g = ix.seq2 + (DBLo >> 5);
         const uint32_t sh = 2 * (DBLo & 31);
-        const uint64_t *rp = rv.pk + (Plus ? 0 : kPkWords);
-        uint64_t gw[9];
+        const uint32_t *rp = reinterpret_cast<const uint32_t *>(rv.pk + (Plus ? 0 : kPkWords));
         // coarse exception bits of the (at most two) 1024-base blocks under words [DBLo>>5, (DBLo>>5)+nw]
         const uint32_t cb0 = DBLo >> kCoarseShift, cb1 = (((DBLo >> 5) + (uint32_t)nw) << 5) >> kCoarseShift;
         uint32_t exc = 1u;
         if (!(P.flags & 32u)) exc = ((__ldg(ix.seqc + (cb0 >> 5)) >> (cb0 & 31)) | (__ldg(ix.seqc + (cb1 >> 5)) >> (cb1 & 31))) & 1u;
+        // the genome window as a stream of 32-bit pieces in base order: S[2k] = high half of word k, S[2k+1] = low half
+        uint32_t S[19];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {   // all loads are issued before the first one is consumed
-            gw[k] = 0;
-            if (k <= nw) gw[k] = __ldg(g + k);
+            uint64_t v = 0;
+            if (k <= nw) v = __ldg(g + k);
+            S[2 * k] = (uint32_t)(v >> 32);
+            S[2 * k + 1] = (uint32_t)v;
         }
+        S[18] = 0;
         if (exc) {   // rare: look at the fine bits
             const uint32_t *x = ix.seqx + (DBLo >> 5);
             exc = 0;
@@ -316,44 +322,53 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
         }
         if (exc) slow = true;
         else {
+            const bool odd = sh >= 32;        // the window starts in the low half of word 0
+            const uint32_t s = sh & 31u;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint64_t d = 0;
-                if (k < nw) {
-                    const uint64_t a = sh ? ((gw[k] << sh) | (gw[k + 1] >> (64 - sh))) : gw[k];
-                    d = a ^ rp[k];
-                    d = (d | (d >> 1)) & 0x5555555555555555ull;
+            for (int j = 0; j < 16; ++j) {
+                uint32_t d = 0;
+                if (j < nh) {
+                    const uint32_t lo = odd ? S[j + 1] : S[j], hi = odd ? S[j + 2] : S[j + 1];
+                    const uint32_t a = __funnelshift_l(hi, lo, s);   // (lo << s) | (hi >> (32 - s)), s in [0, 31]
+                    d = a ^ rp[j ^ 1];                               // packed read: 64-bit words, high half first
+                    d = (d | (d >> 1)) & 0x55555555u;
                 }
-                mm[k] = d;
+                mm[j] = d;
             }
-            if (QL & 31) mm[nw - 1] &= ~0ull << (64 - 2 * (QL & 31));
+            if (QL & 15) mm[nh - 1] &= 0xFFFFFFFFu << (32 - 2 * (QL & 15));
         }
     }
     if (slow) return pure_ext_bytes(Plus ? rv.q : rv.rc, ix.seq + DBLo, QL, W, MM, XD, SeedPosQ, LeftCountsPen);
 
+    // Both walks are single loops whose iterations either step to the next half-word or consume one mismatch, so that
+    // lanes with many mismatches (bogus candidates) and lanes that cross many clean words (true candidates) take a
+    // similar number of trips.
     int Score = W, Best = 0, nmis = 0;
     int End = (int)SeedPosQ + W - 1;
     {   // right walk, extendpen.cpp:29-52: mismatches in increasing position = decreasing bit index
         int p = End + 1;
+        int h = p >> 4;
+        uint32_t w = 0;
+        if (h < nh) w = mm[h] & (0xFFFFFFFFu >> (2 * (p & 15)));
         bool stop = false;
-        for (int k = p >> 5; k < nw && !stop; ++k) {
-            uint64_t w = mm[k];
-            const int b0 = p - (k << 5);
-            if (b0 > 0) w &= ~0ull >> (2 * b0);
-            while (w) {
-                const int hb = 63 - __clzll((long long)w);
-                w &= ~(1ull << hb);
-                const int pos = (k << 5) + ((62 - hb) >> 1);
-                const int run = pos - p;
-                if (run > 0) {
-                    Score += run;
-                    if (Score > Best) { Best = Score; End = pos - 1; }
-                }
-                ++nmis;
-                Score += MM;
-                p = pos + 1;
-                if (Best - Score > XD || nmis > maxmis) { stop = true; break; }
+        for (;;) {
+            if (w == 0) {
+                if (++h >= nh) break;
+                w = mm[h];
+                continue;
             }
+            const int hb = 31 - __clz(w);
+            w ^= 1u << hb;
+            const int pos = (h << 4) + ((30 - hb) >> 1);
+            const int run = pos - p;
+            if (run > 0) {
+                Score += run;
+                if (Score > Best) { Best = Score; End = pos - 1; }
+            }
+            ++nmis;
+            Score += MM;
+            p = pos + 1;
+            if (Best - Score > XD || nmis > maxmis) { stop = true; break; }
         }
         if (!stop) {
             const int run = QL - p;
@@ -367,25 +382,28 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
     int Start = (int)SeedPosQ;
     {   // left walk, extendpen.cpp:55-78
         int p = Start - 1;
+        int h = p >> 4;   // -1 when the seed starts the read
+        uint32_t w = 0;
+        if (h >= 0) w = mm[h] & (0xFFFFFFFFu << (30 - 2 * (p & 15)));
         bool stop = false;
-        for (int k = p >> 5; k >= 0 && !stop; --k) {   // p == -1 gives k == -1: no iterations
-            uint64_t w = mm[k];
-            const int b1 = p - (k << 5);
-            if (b1 < 31) w &= ~0ull << (62 - 2 * b1);
-            while (w) {
-                const int lb = __ffsll((long long)w) - 1;
-                w &= w - 1;
-                const int pos = (k << 5) + ((62 - lb) >> 1);
-                const int run = p - pos;
-                if (run > 0) {
-                    Score += run;
-                    if (Score > Best) { Best = Score; Start = pos + 1; }
-                }
-                if (LeftCountsPen) ++nmis;
-                Score += MM;
-                p = pos - 1;
-                if (Best - Score > XD || nmis > maxmis) { stop = true; break; }
+        for (;;) {
+            if (w == 0) {
+                if (--h < 0) break;
+                w = mm[h];
+                continue;
             }
+            const int lb = __ffs(w) - 1;
+            w &= w - 1;
+            const int pos = (h << 4) + ((30 - lb) >> 1);
+            const int run = p - pos;
+            if (run > 0) {
+                Score += run;
+                if (Score > Best) { Best = Score; Start = pos + 1; }
+            }
+            if (LeftCountsPen) ++nmis;
+            Score += MM;
+            p = pos - 1;
+            if (Best - Score > XD || nmis > maxmis) { stop = true; break; }
         }
         if (!stop) {
             const int run = p + 1;

@@ -151,6 +151,15 @@ uint64_t urmb_launch_count(const urmb_ctx *c);
 int urmb_mark(urmb_ctx *c, int which /* 0 | 1 */);
 int urmb_mark_elapsed(urmb_ctx *c, float *ms);
 
+/* ---- index construction on the device (replaces UFIndex::MakeIndex, ufindex.cpp:83-151, as far
+ * as the mapping path can tell: the same lists in every slot, free-slot placement not byte-identical to the reference;
+ * the byte-identical builder is `urmap_b200 -make_ufi` on the host) ----
+ * d_seq: seq_data_size bytes of upper-case sequence data on the current device; d_blob: 5*slot_count+URMB_BLOB_PAD
+ * bytes (written).  stats[0] = indexed positions, stats[1] = truncated lists (0 expected), stats[2] = microseconds. */
+int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t slot_count, uint32_t word_length,
+                            uint32_t max_ix, void *d_blob, uint64_t *stats);
+const char *urmb_build_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

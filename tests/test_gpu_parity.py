@@ -191,3 +191,111 @@ def test_size_independent_properties(eng, oracle, mid_env):
     assert canon(q1, uq) == [full1[i] for i in perm]
     assert ctx.launch_count() >= 2 * 6
     ctx.close()
+
+
+def _ctx_with_env(eng, hix, env, **kw):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        c = eng.Context(0, **kw)   # tuning variables are read at context creation
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    c.set_index(hix)
+    return c
+
+
+def test_chunk_size_invariance(eng, oracle, mid_env):
+    """The staged search hands per-mate state over between small kernels chunk by chunk: results must not depend on the
+    chunk size, on where the chunk borders fall, or on which stream the mate-rescue kernel runs (SE and PE)."""
+    g, oix, hix = mid_env
+    r1, r2, _ = synth.sim_pe(g, 6000, 150, 0.03, 0.003, seed=9)
+    b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
+    o1, o2, uo = oracle.map_pe(oix, b1, b2, threads=os.cpu_count())
+    s1, us = oracle.map_se(oix, b1, threads=os.cpu_count())
+    for env in ({"URMB_CHUNK_PAIRS": "1"}, {"URMB_CHUNK_PAIRS": "997"}, {"URMB_CHUNK_PAIRS": "5000", "URMB_RESCUE_INLINE": "1"},
+                {"URMB_RESCUE_WARPS": "4"}):
+        ctx = _ctx_with_env(eng, hix, env)
+        if env.get("URMB_CHUNK_PAIRS") == "1":   # one pair per chunk: a small prefix is enough
+            n = 150
+            sb1 = oracle.ReadBatch(b1.seqs[:b1.offs[n]], b1.offs[:n + 1])
+            sb2 = oracle.ReadBatch(b2.seqs[:b2.offs[n]], b2.offs[:n + 1])
+            g1, g2, ug = ctx.map_pe(sb1.seqs, sb1.offs, sb2.seqs, sb2.offs)
+            assert canon(g1, ug) == canon(o1[:n], uo) and canon(g2, ug) == canon(o2[:n], uo)
+            x1, ux = ctx.map_se(sb1.seqs, sb1.offs)
+            assert canon(x1, ux) == canon(s1[:n], us)
+        else:
+            g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+            assert_same(np.concatenate([o1, o2]), uo, np.concatenate([g1, g2]), ug)
+            x1, ux = ctx.map_se(b1.seqs, b1.offs)
+            assert_same(s1, us, x1, ux)
+        ctx.close()
+
+
+def test_human_scale_properties(eng):
+    """BASELINE.json's full-size index (3.1 Gb reference, 27 GB table, built on the GPU) with properties that need no
+    oracle: reads map back to where they were drawn from, results are idempotent, independent of the chunk size and of
+    how a batch is split over the three pipeline slots.  (bench.py additionally compares 2 M SAM records with the
+    reference binary at this size.)"""
+    import torch
+    from urmap_b200 import gpu_synth, index_build
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs 60 GB of free HBM")
+    dev = torch.device("cuda", 0)
+    seq, names, lens, offsets, sds = gpu_synth.make_seqdata(3_100_000_000, dev, n_contigs=24, human_ratios=True)
+    slots = index_build.slot_count_for(names, lens)
+    assert slots == 5392814809   # first prime >= FASTA bytes / 0.6 (SURVEY.md §8)
+    blob = torch.empty(5 * slots + 16, dtype=torch.uint8, device=dev)
+    st = index_build.build_index_device(seq.data_ptr(), sds, slots, blob.data_ptr())
+    assert st["truncated"] == 0 and st["indexed"] > 2_900_000_000
+    n, RL = 200_000, 150
+    r1, r2, t1, t2, plus1 = gpu_synth.sim_pe(seq, lens, offsets, n, dev, RL, 0.01, 0.001, seed=4242, return_truth=True)
+    a1, a2 = r1.cpu().numpy().reshape(-1), r2.cpu().numpy().reshape(-1)
+    t1, t2, plus1 = t1.cpu().numpy(), t2.cpu().numpy(), plus1.cpu().numpy()
+    offs = (np.arange(n + 1, dtype=np.uint32) * RL)
+    desc = (24, 32, sds, slots, blob.data_ptr(), seq.data_ptr())
+
+    def run(env, split=None):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            ctx = eng.Context(0)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        ctx.attach_index(*desc, keepalive=(seq, blob))
+        if split is None:
+            x1, x2, ux = ctx.map_pe(a1, offs, a2, offs)
+            out = canon(x1, ux), canon(x2, ux), x1.copy(), x2.copy()
+        else:
+            cuts = [0, split, 2 * split, n]
+            for k in range(3):
+                lo, hi = cuts[k], cuts[k + 1]
+                o = (np.arange(hi - lo + 1, dtype=np.uint32) * RL)
+                ctx.submit(k, a1[lo * RL:hi * RL], o, a2[lo * RL:hi * RL], o)
+            c1, c2 = [], []
+            for k in range(3):
+                x1, x2, ux = ctx.wait(k, cuts[k + 1] - cuts[k], True)
+                c1 += canon(x1, ux)
+                c2 += canon(x2, ux)
+            out = c1, c2, None, None
+        ctx.close()
+        return out
+
+    f1, f2, x1, x2 = run({})
+    # truth: confidently mapped mates sit where they were drawn from (alignment start within the read's own indels)
+    for x, t, plus in ((x1, t1, plus1), (x2, t2, ~plus1)):
+        conf = x["mapq"] >= 20
+        assert conf.mean() > 0.8, float(conf.mean())
+        ok = (np.abs(x["db_pos"].astype(np.int64) - t) <= 12) & (((x["flags"] & 1) != 0) == plus)
+        assert ok[conf].mean() > 0.999, float(ok[conf].mean())
+    g1, g2, _, _ = run({"URMB_CHUNK_PAIRS": "30011"})
+    assert g1 == f1 and g2 == f2
+    h1, h2, _, _ = run({}, split=70_001)
+    assert h1 == f1 and h2 == f2
+    del blob, seq
+    torch.cuda.empty_cache()

@@ -67,6 +67,7 @@ EXPORTS = [
     "urmb_ctx_destroy", "urmb_last_error", "urmb_index_upload", "urmb_index_attach", "urmb_index_broadcast",
     "urmb_index_device_desc", "urmb_map_se", "urmb_map_pe", "urmb_submit", "urmb_wait", "urmb_upload",
     "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
+    "urmb_build_index_device", "urmb_build_last_error",
 ]
 
 _lib = None
@@ -106,7 +107,8 @@ def lib():
         L.urmb_mark.argtypes = [vp, C.c_int]
         L.urmb_mark_elapsed.argtypes = [vp, C.POINTER(C.c_float)]
         for nm in EXPORTS:
-            if nm not in ("urmb_last_error", "urmb_launch_count", "urmb_index_free_host", "urmb_ctx_destroy"):
+            if nm not in ("urmb_last_error", "urmb_launch_count", "urmb_index_free_host", "urmb_ctx_destroy",
+                          "urmb_build_last_error"):
                 getattr(L, nm).restype = C.c_int
         _lib = L
     return _lib

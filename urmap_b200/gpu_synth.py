@@ -131,8 +131,10 @@ def _mutate(frag, sub, indel, read_len, gen):
 
 
 def sim_pe(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, seed=778, pad=40, ins_mean=400,
-           ins_sd=50, ins_lo=200, ins_hi=800, chunk=1 << 18):
-    """FR pairs (which mate is forward is randomised). Returns (r1, r2) uint8 tensors [n, read_len] on device."""
+           ins_sd=50, ins_lo=200, ins_hi=800, chunk=1 << 18, return_truth=False):
+    """FR pairs (which mate is forward is randomised). Returns (r1, r2) uint8 tensors [n, read_len] on device; with
+    return_truth also (pos1, pos2, plus1): the sequence-data offset each mate was drawn from (start of its alignment
+    on the plus strand, up to the read's own indels) and whether mate 1 is the forward one."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     L = read_len + pad
@@ -142,6 +144,7 @@ def sim_pe(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, s
     comp = _comp_lut(device)
     ar = torch.arange(L, device=device)[None, :]
     o1, o2 = [], []
+    t1, t2, tf = [], [], []
     for c0 in range(0, n, chunk):
         m = min(chunk, n - c0)
         ci = torch.multinomial(w / w.sum(), m, replacement=True, generator=gen)
@@ -157,6 +160,13 @@ def sim_pe(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, s
         flip = torch.rand(m, device=device, generator=gen) < 0.5
         o1.append(torch.where(flip[:, None], b, a))
         o2.append(torch.where(flip[:, None], a, b))
+        if return_truth:
+            pa, pb = g0, g0 + ins - read_len
+            t1.append(torch.where(flip, pb, pa))
+            t2.append(torch.where(flip, pa, pb))
+            tf.append(~flip)
+    if return_truth:
+        return (torch.cat(o1).contiguous(), torch.cat(o2).contiguous(), torch.cat(t1), torch.cat(t2), torch.cat(tf))
     return torch.cat(o1).contiguous(), torch.cat(o2).contiguous()
 
 

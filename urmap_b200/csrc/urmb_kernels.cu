@@ -286,6 +286,53 @@ __device__ __noinline__ uint32_t pure_ext_bytes(const uint8_t *Qs, const uint8_t
 // Lane-local. Plus selects the read strand; the candidate is (SeedPosQ, SeedPosDB) on diagonal DBLo.
 // PenBound: any bound known to be >= m_MaxPenalty at the time the reference would make this call; the walk stops
 // as soon as the penalty exceeds it (the packed result then only says "fails the bound", which is all that is used).
+// The mismatch flags of a candidate window, 16 bases per 32-bit word: base t of half-word h (read position 16 h + t) at
+// bit 30 - 2 t.  NH = compiled number of half-words (10 covers reads up to 160 bases with half the code of 16: the
+// search kernels are instruction-fetch sensitive).  Returns false when the window touches a non-ACGT genome byte.
+template <int NH>
+__device__ __forceinline__ bool ext_flags(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus, uint32_t DBLo,
+                                          int nw, int nh, int QL, uint32_t *mm) {
+    constexpr int NW = NH / 2 + 1;   // 64-bit genome words that can be touched
+    const uint64_t *g = ix.seq2 + (DBLo >> 5);
+    const uint32_t sh = 2 * (DBLo & 31);
+    const uint32_t *rp = reinterpret_cast<const uint32_t *>(rv.pk + (Plus ? 0 : kPkWords));
+    // coarse exception bits of the (at most two) 1024-base blocks under words [DBLo>>5, (DBLo>>5)+nw]
+    const uint32_t cb0 = DBLo >> kCoarseShift, cb1 = (((DBLo >> 5) + (uint32_t)nw) << 5) >> kCoarseShift;
+    uint32_t exc = 1u;
+    if (!(P.flags & 32u)) exc = ((__ldg(ix.seqc + (cb0 >> 5)) >> (cb0 & 31)) | (__ldg(ix.seqc + (cb1 >> 5)) >> (cb1 & 31))) & 1u;
+    // the genome window as a stream of 32-bit pieces in base order: S[2k] = high half of word k, S[2k+1] = low half
+    uint32_t S[2 * NW + 1];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {   // all loads are issued before the first one is consumed
+        uint64_t v = 0;
+        if (k <= nw) v = __ldg(g + k);
+        S[2 * k] = (uint32_t)(v >> 32);
+        S[2 * k + 1] = (uint32_t)v;
+    }
+    S[2 * NW] = 0;
+    if (exc) {   // rare: look at the fine bits
+        const uint32_t *x = ix.seqx + (DBLo >> 5);
+        exc = 0;
+        for (int k = 0; k <= nw; ++k) exc |= __ldg(x + k);
+        if (exc) return false;
+    }
+    const bool odd = sh >= 32;        // the window starts in the low half of word 0
+    const uint32_t s = sh & 31u;
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+        uint32_t d = 0;
+        if (j < nh) {
+            const uint32_t lo = odd ? S[j + 1] : S[j], hi = odd ? S[j + 2] : S[j + 1];
+            const uint32_t a = __funnelshift_l(hi, lo, s);   // (lo << s) | (hi >> (32 - s)), s in [0, 31]
+            d = a ^ rp[j ^ 1];                               // packed read: 64-bit words, high half first
+            d = (d | (d >> 1)) & 0x55555555u;
+        }
+        mm[j] = d;
+    }
+    if (QL & 15) mm[nh - 1] &= 0xFFFFFFFFu << (32 - 2 * (QL & 15));
+    return true;
+}
+
 __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus,
                                           uint32_t SeedPosQ, uint32_t SeedPosDB, bool LeftCountsPen, int PenBound) {
     if (SeedPosDB < SeedPosQ) return EXT_NONE;   // extendpen.cpp:11
@@ -294,50 +341,9 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
     const int nw = (QL + 31) >> 5;   // <= 8 packed 64-bit words
     const int nh = (QL + 15) >> 4;   // <= 16 half-words of 16 bases
     const int maxmis = min(PenBound / -MM, 126);   // nmis > maxmis  <=>  nmis * -MM > PenBound
-    // Mismatch flags, 16 bases per 32-bit word: base t of half-word h (read position 16 h + t) at bit 30 - 2 t.
     uint32_t mm[16];
     bool slow = rv.slow;
-    if (!slow) {
-        const uint64_t *g = ix.seq2 + (DBLo >> 5);
-        const uint32_t sh = 2 * (DBLo & 31);
-        const uint32_t *rp = reinterpret_cast<const uint32_t *>(rv.pk + (Plus ? 0 : kPkWords));
-        // coarse exception bits of the (at most two) 1024-base blocks under words [DBLo>>5, (DBLo>>5)+nw]
-        const uint32_t cb0 = DBLo >> kCoarseShift, cb1 = (((DBLo >> 5) + (uint32_t)nw) << 5) >> kCoarseShift;
-        uint32_t exc = 1u;
-        if (!(P.flags & 32u)) exc = ((__ldg(ix.seqc + (cb0 >> 5)) >> (cb0 & 31)) | (__ldg(ix.seqc + (cb1 >> 5)) >> (cb1 & 31))) & 1u;
-        // the genome window as a stream of 32-bit pieces in base order: S[2k] = high half of word k, S[2k+1] = low half
-        uint32_t S[19];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {   // all loads are issued before the first one is consumed
-            uint64_t v = 0;
-            if (k <= nw) v = __ldg(g + k);
-            S[2 * k] = (uint32_t)(v >> 32);
-            S[2 * k + 1] = (uint32_t)v;
-        }
-        S[18] = 0;
-        if (exc) {   // rare: look at the fine bits
-            const uint32_t *x = ix.seqx + (DBLo >> 5);
-            exc = 0;
-            for (int k = 0; k <= nw; ++k) exc |= __ldg(x + k);
-        }
-        if (exc) slow = true;
-        else {
-            const bool odd = sh >= 32;        // the window starts in the low half of word 0
-            const uint32_t s = sh & 31u;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                uint32_t d = 0;
-                if (j < nh) {
-                    const uint32_t lo = odd ? S[j + 1] : S[j], hi = odd ? S[j + 2] : S[j + 1];
-                    const uint32_t a = __funnelshift_l(hi, lo, s);   // (lo << s) | (hi >> (32 - s)), s in [0, 31]
-                    d = a ^ rp[j ^ 1];                               // packed read: 64-bit words, high half first
-                    d = (d | (d >> 1)) & 0x55555555u;
-                }
-                mm[j] = d;
-            }
-            if (QL & 15) mm[nh - 1] &= 0xFFFFFFFFu << (32 - 2 * (QL & 15));
-        }
-    }
+    if (!slow) slow = (nh <= 10) ? !ext_flags<10>(ix, P, rv, Plus, DBLo, nw, nh, QL, mm) : !ext_flags<16>(ix, P, rv, Plus, DBLo, nw, nh, QL, mm);
     if (slow) return pure_ext_bytes(Plus ? rv.q : rv.rc, ix.seq + DBLo, QL, W, MM, XD, SeedPosQ, LeftCountsPen);
 
     // Both walks are single loops whose iterations either step to the next half-word or consume one mismatch, so that

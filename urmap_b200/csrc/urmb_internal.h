@@ -67,7 +67,7 @@ enum {
     CT_CHUNK0 = 8,      // first per-chunk counter
     CT_HEAD = 8,        // work-queue head of the first-pass kernel
     CT_TODO = 9,        // pairs of this chunk saved for the staged second pass
-    CT_STAGE_A = 10, CT_STAGE_B = 11, CT_STAGE_C = 12, CT_FINISH = 13,   // work-queue heads of the stage kernels
+    CT_STAGE_A = 10, CT_STAGE_B = 11, CT_STAGE_C = 12, CT_FINISH = 13, CT_STAGE_B2 = 14,   // work-queue heads of the stage kernels
     CT_COUNT = 16
 };
 

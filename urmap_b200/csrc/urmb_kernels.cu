@@ -237,6 +237,15 @@ __device__ __forceinline__ uint64_t slot_of(const DevIndex &ix, const ReadView &
     return mod_slots(murmur64(word & ix.shift_mask), ix.slot_count, ix.magic);
 }
 
+// Out-of-line versions for the search kernels, which are instruction-fetch sensitive (one shared copy instead of an
+// inlined one per call site); the probe kernel keeps the inlined forms in its hot loop.
+__device__ __noinline__ void load_blob_s(const uint8_t *blob, uint64_t slot, uint32_t &tally, uint32_t &pos) {
+    load_blob<true>(blob, slot, tally, pos);
+}
+__device__ __noinline__ uint64_t slot_of_s(const DevIndex &ix, const ReadView &rv, int s, uint32_t q) {
+    return slot_of(ix, rv, s, q);
+}
+
 // =====================================================================================
 // state-independent gapless extension
 // =====================================================================================
@@ -1310,7 +1319,7 @@ __device__ __noinline__ uint32_t get_row(const Env &E, uint64_t Slot, uint32_t T
     uint32_t K = 0;
     const uint64_t SC = E.ix.slot_count;
     for (;;) {
-        if (K > 0) load_blob(E.ix.blob, Slot2, T, Pos);
+        if (K > 0) load_blob_s(E.ix.blob, Slot2, T, Pos);
         if ((uint32_t)E.lane == K) mypos = Pos;
         ++K;
         if (K == E.ix.max_ix) return K;
@@ -1321,7 +1330,7 @@ __device__ __noinline__ uint32_t get_row(const Env &E, uint64_t Slot, uint32_t T
             uint64_t SlotA = add_mod(Slot2, StepA, SC);
             Slot2 = add_mod(SlotA, StepB, SC);
             uint32_t ta, pa;
-            load_blob(E.ix.blob, SlotA, ta, pa);
+            load_blob_s(E.ix.blob, SlotA, ta, pa);
             if ((uint32_t)E.lane == K - 1) mypos = pa;
         } else {
             Slot2 = add_mod(Slot2, T & T_NEXT_MASK, SC);
@@ -1335,7 +1344,7 @@ __device__ __forceinline__ uint32_t m_tally(const Mate &m, int strand /*0 plus,1
 __device__ __forceinline__ uint32_t m_pos(const Mate &m, int strand, uint32_t q) { return __ldg(m.pos + strand * m.qcap + q); }
 __device__ __forceinline__ uint32_t m_ext(const Mate &m, int strand, uint32_t q) { return __ldg(m.ext + strand * m.qcap + q); }
 __device__ __forceinline__ uint64_t m_slot(const Env &E, const Mate &m, int strand, uint32_t q) {
-    return slot_of(E.ix, m.rv, strand, q);
+    return slot_of_s(E.ix, m.rv, strand, q);
 }
 
 // Lane-local GetRow_Blob (ufindex.cpp:883-943) limited to what the "rows <= 2 now, longer rows later" logic
@@ -1348,7 +1357,7 @@ __device__ __noinline__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tal
     uint64_t Slot2 = Slot;
     const uint64_t SC = E.ix.slot_count;
     for (;;) {
-        if (K > 0) load_blob(E.ix.blob, Slot2, T, Pos);
+        if (K > 0) load_blob_s(E.ix.blob, Slot2, T, Pos);
         if (K == 0) p0 = Pos; else if (K == 1) p1 = Pos;
         ++K;
         if (K == E.ix.max_ix) { n = K; return; }
@@ -1360,7 +1369,7 @@ __device__ __noinline__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tal
             uint64_t SlotA = add_mod(Slot2, StepA, SC);
             Slot2 = add_mod(SlotA, StepB, SC);
             uint32_t ta, pa;
-            load_blob(E.ix.blob, SlotA, ta, pa);
+            load_blob_s(E.ix.blob, SlotA, ta, pa);
             if (K == 1) p0 = pa; else if (K == 2) p1 = pa;
         } else {
             Slot2 = add_mod(Slot2, T & T_NEXT_MASK, SC);
@@ -1457,7 +1466,7 @@ __device__ uint32_t row_walk_lane(const Env &E, uint64_t Slot, uint32_t Tally, u
     uint32_t Pos = Pos0, K = 0;
     const uint64_t SC = E.ix.slot_count;
     for (;;) {
-        if (K > 0) load_blob(E.ix.blob, Slot2, T, Pos);
+        if (K > 0) load_blob_s(E.ix.blob, Slot2, T, Pos);
         out[K] = Pos;
         ++K;
         if (K == E.ix.max_ix) return K;
@@ -1468,7 +1477,7 @@ __device__ uint32_t row_walk_lane(const Env &E, uint64_t Slot, uint32_t Tally, u
             const uint64_t SlotA = add_mod(Slot2, StepA, SC);
             Slot2 = add_mod(SlotA, StepB, SC);
             uint32_t ta, pa;
-            load_blob(E.ix.blob, SlotA, ta, pa);
+            load_blob_s(E.ix.blob, SlotA, ta, pa);
             out[K - 1] = pa;
         } else {
             Slot2 = add_mod(Slot2, T & T_NEXT_MASK, SC);
@@ -1706,15 +1715,21 @@ __device__ __noinline__ bool pend_stage_a(const Env &E, Mate &m) {
     __syncwarp();
     return false;
 }
-__device__ __noinline__ void pend_stage_b(const Env &E, Mate &m) {
-    int n2[2] = {0, 0};
-    for (int s = 0; s < 2; ++s) {   // pending round 1; the list is compacted in place into the deferred rows
+// Pending round 1 (rows <= 2 extended, longer rows deferred: the lists are compacted in place and nPend becomes the
+// number of deferred rows) and pending round 2 (the deferred rows): two kernels in the staged search.
+__device__ __noinline__ void pend_stage_b1(const Env &E, Mate &m) {
+    for (int s = 0; s < 2; ++s) {
         int nd = 0;
         rows_short_round(E, m, s, m.g->pend[s], m.nPend[s], m.g->pend[s], nd);
-        n2[s] = nd;
+        m.nPend[s] = nd;
     }
-    for (int s = 0; s < 2; ++s)     // pending round 2
-        rows_long_batch(E, m, s, m.g->pend[s], n2[s]);
+}
+__device__ __noinline__ void pend_stage_b2(const Env &E, Mate &m) {
+    for (int s = 0; s < 2; ++s) rows_long_batch(E, m, s, m.g->pend[s], m.nPend[s]);
+}
+__device__ void pend_stage_b(const Env &E, Mate &m) {
+    pend_stage_b1(E, m);
+    pend_stage_b2(E, m);
 }
 __device__ __noinline__ void pend_stage_c(const Env &E, Mate &m) {
     const int B = max(m.Best, m.BestHSP) - 8;
@@ -2300,21 +2315,22 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
 // Second pass, one warp per saved MATE.  STAGE 0: SearchPE_Pending up to its first HSP alignments
 // (search1pepend.cpp:15-51); STAGE 1: the pending rows (:53-110); STAGE 2: the final HSP alignments and MAPQ (:112-129).
 // STAGE 3-5: the same for the single-end search (one saved state per read): phase 3, phases 4-5, phase 6 + result.
+// STAGE 6: paired-end pending round 2 (the deferred long rows), STAGE 1 then only does round 1.
 template <int STAGE>
 __device__ __forceinline__ void stage_body(const KArgs &A) {
-    constexpr bool SE = STAGE >= 3;
+    constexpr bool SE = STAGE >= 3 && STAGE <= 5;
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + warp;
     uint8_t *sw = smem + (size_t)warp * A.spw;
     const DevBatch &b = A.b;
-    const SmemPlan pl{1u, 0u, (STAGE == 1 || STAGE == 4) ? 0u : 1u};
+    const SmemPlan pl{1u, 0u, (STAGE == 1 || STAGE == 4 || STAGE == 6) ? 0u : 1u};
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
     const uint32_t n_work = (SE ? 1u : 2u) * A.o.counters[CT_TODO];
     for (;;) {
         uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&A.o.counters[CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
+        if (lane == 0) k = atomicAdd(&A.o.counters[STAGE == 6 ? CT_STAGE_B2 : CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
         k = __shfl_sync(FULL, k, 0);
         if (k >= n_work) break;
         MateSave *sv = A.pool + k;
@@ -2322,6 +2338,7 @@ __device__ __forceinline__ void stage_body(const KArgs &A) {
         const uint32_t u = A.o.todo[SE ? k : k >> 1];
         const uint32_t r = (!SE && (k & 1u)) ? b.n_units + u : u;
         if (h.done && STAGE != 5) continue;
+        if (STAGE == 6 && h.nPend[0] + h.nPend[1] == 0) continue;   // no deferred rows
         if (STAGE == 0 || STAGE == 3) {   // nothing to align (save_mate already reset the paired-end penalty bound)
             const int QL = (int)(b.offs[r + 1] - b.offs[r]);
             if (STAGE == 0 && h.BestHSP < (QL * A.P.TERM3_PCT) / 100) continue;
@@ -2337,7 +2354,8 @@ __device__ __forceinline__ void stage_body(const KArgs &A) {
         hdr_to_mate(h, m);
         bool done = false;
         if (STAGE == 0) done = pend_stage_a(E, m);
-        else if (STAGE == 1) pend_stage_b(E, m);
+        else if (STAGE == 1) pend_stage_b1(E, m);
+        else if (STAGE == 6) pend_stage_b2(E, m);
         else if (STAGE == 2) { pend_stage_c(E, m); done = true; }
         else if (STAGE == 3) done = se_phase3(E, m);
         else if (STAGE == 4) done = se_phase45(E, m);
@@ -2405,6 +2423,7 @@ __global__ void __launch_bounds__(128, URMB_LB_PAIR) pair_kernel(const __grid_co
 __global__ void __launch_bounds__(128, 4) rescue_kernel(const __grid_constant__ KArgs A) { search_body<2>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_a(const __grid_constant__ KArgs A) { stage_body<0>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_kernel(const __grid_constant__ KArgs A) { stage_body<1>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_long_kernel(const __grid_constant__ KArgs A) { stage_body<6>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_c(const __grid_constant__ KArgs A) { stage_body<2>(A); }
 __global__ void __launch_bounds__(128, 4) finish_kernel(const __grid_constant__ KArgs A) { finish_body(A); }
 
@@ -2512,9 +2531,10 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
         URMB_TRY(launch_one(pair_kernel, 1, tr, A, SmemPlan{2, 1, 0}, cnt, R, stream, sm_count, warps_used));
         URMB_TRY(launch_one(align_kernel_a, 2, tr, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
         URMB_TRY(launch_one(rows_kernel, 3, tr, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(rows_long_kernel, 3, tr, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
         URMB_TRY(launch_one(align_kernel_c, 4, tr, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
         URMB_TRY(launch_one(finish_kernel, 5, tr, A, SmemPlan{0, 0, 0}, cnt, R, stream, sm_count, nullptr));
-        n += 5;
+        n += 6;
     }
     return n;
 }

@@ -166,17 +166,30 @@ def write_ufi_file(path, meta, seq, blob):
 
 
 def write_fastq_pair(prefix, r1, r2, n, RL):
-    q = b"I" * RL
-
+    """@p<i>/1|2, bases, '+', constant quality 'I' -- written as one 2-D byte array per label width."""
     def one(path, arr, suffix):
         with open(path, "wb") as f:
-            buf = []
-            for i in range(n):
-                buf.append(b"@p%d%s\n%s\n+\n%s\n" % (i, suffix, arr[i * RL:(i + 1) * RL].tobytes(), q))
-                if len(buf) >= 50000:
-                    f.write(b"".join(buf))
-                    buf = []
-            f.write(b"".join(buf))
+            lo = 0
+            width = 1
+            while lo < n:
+                hi = min(n, 10 ** width)
+                m = hi - lo
+                idx = np.arange(lo, hi, dtype=np.int64)
+                rec = np.empty((m, 2 + width + len(suffix) + 1 + RL + 3 + RL + 1), np.uint8)
+                c = 0
+                rec[:, 0] = ord("@"); rec[:, 1] = ord("p"); c = 2
+                for k in range(width):
+                    rec[:, c + k] = (idx // 10 ** (width - 1 - k)) % 10 + ord("0")
+                c += width
+                rec[:, c:c + len(suffix)] = np.frombuffer(suffix, np.uint8); c += len(suffix)
+                rec[:, c] = 10; c += 1
+                rec[:, c:c + RL] = arr[lo * RL:hi * RL].reshape(m, RL); c += RL
+                rec[:, c:c + 3] = np.frombuffer(b"\n+\n", np.uint8); c += 3
+                rec[:, c:c + RL] = ord("I"); c += RL
+                rec[:, c] = 10
+                f.write(rec.tobytes())
+                lo = hi
+                width += 1
 
     one(prefix + "_1.fq", r1, b"/1")
     if r2 is not None:
@@ -223,6 +236,49 @@ def run_reference_cpu(args, ufi_path, prefix, n_units, paired, threads):
     reads = n_units * (2 if paired else 1)
     dt = max(t_run - t_load, 1e-3)
     return {"reads": reads, "seconds": dt, "load_seconds": t_load, "reads_per_s": reads / dt, "sam": prefix + "_ref.sam"}
+
+
+def run_cli(args, ufi_path, prefix, cli_prefix, n_units, n_ref, paired, threads, ref_sam):
+    """The drop-in itself: `urmap_b200 -map2 ... -samout` (FASTQ files in, SAM file out) over n_units pairs whose first
+    n_ref are the sample the reference was timed on; timed the same way (wall minus the wall of a 4-read run, which
+    takes out index load and context set-up) and its SAM file compared with the reference's record by record."""
+    from urmap_b200 import synth
+    exe = os.path.join(ROOT, "urmap_b200", "bin", "urmap_b200")
+    if not os.path.exists(exe):
+        return None
+    tiny = prefix + "_tiny"
+
+    def cmd(p, sam):
+        c = ["-map2", p + "_1.fq", "-reverse", p + "_2.fq"] if paired else ["-map", p + "_1.fq"]
+        return [exe] + c + ["-ufi", ufi_path, "-samout", sam, "-threads", str(threads)]
+
+    def run(c):
+        t0 = time.time()
+        p = subprocess.run(c, capture_output=True, env=dict(os.environ, URMB_PROFILE="1"))
+        if p.returncode != 0:
+            raise RuntimeError(f"urmap_b200 exited {p.returncode}: {p.stderr.decode(errors='replace')[-300:]!r}")
+        return time.time() - t0, p.stderr.decode(errors="replace")
+
+    t_load, _ = run(cmd(tiny, prefix + "_tiny_cli.sam"))
+    t_run, err = run(cmd(cli_prefix, cli_prefix + "_cli.sam"))
+    reads = n_units * (2 if paired else 1)
+    dt = max(t_run - t_load, 1e-3)
+    out = {"value": reads / dt, "unit": "reads/s", "reads": reads, "seconds": dt, "load_seconds": t_load,
+           "host_threads": threads,
+           "what": "urmap_b200 CLI, FASTQ files -> SAM file in /dev/shm, wall minus the wall of a 4-read run"}
+    for ln in err.splitlines():
+        if "Seconds in mapper" in ln:
+            out["seconds_in_mapper_reported"] = float(ln.split()[0])
+        if ln.startswith("[urmb host]"):
+            out["host_profile"] = ln[len("[urmb host] "):]
+    if ref_sam and os.path.exists(ref_sam):
+        hr, rr = synth.parse_sam(ref_sam)
+        hc, rc = synth.parse_sam(cli_prefix + "_cli.sam")
+        same = sum(1 for k, v in rr.items() if rc.get(k) == v)
+        nopg = lambda h: [x for x in h if not x.startswith(b"@PG")]
+        out["sam_vs_reference"] = {"records": len(rr), "identical": same, "header_equal": nopg(hr) == nopg(hc),
+                                   "pct": 100.0 * same / max(1, len(rr)), "cli_records": len(rc)}
+    return out
 
 
 def run_port_cpu(args, ufi_path, a1, a2, n_units, paired, threads):
@@ -406,6 +462,17 @@ def main():
         _, _, a1, a2, offs = batches[k % nb]
         ctx.submit(slot, a1, offs, a2, offs if paired else None)
 
+    # measured denominators of the two rooflines: random sector gathers over the 27 GB blob, int32 ALU rate
+    micro = None
+    if rank == 0:
+        try:
+            torch.cuda.synchronize()
+            micro = {"gather_4B": engine.peak_gather(blob.data_ptr(), 5 * meta["slot_count"] // 32 * 32, 4),
+                     "gather_16B": engine.peak_gather(blob.data_ptr(), 5 * meta["slot_count"] // 32 * 32, 16),
+                     "alu": engine.peak_alu()}
+            log(f"micro-benchmarks: {micro}")
+        except Exception as e:
+            log(f"micro-benchmarks failed: {e!r}")
     sampler = ClockSampler(local_rank)
     sampler.start()
     # warm-up (also sizes every slot's buffers)
@@ -475,7 +542,7 @@ def main():
     sampler.stop()
 
     # ---- cpu baseline, SAM identity and algorithmic bytes (rank 0, N == 1 only)
-    cpu_baseline, sam_id, algo = None, None, None
+    cpu_baseline, sam_id, algo, cli = None, None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import oracle_py as O
@@ -503,6 +570,13 @@ def main():
                                           f"`urmap -map2 -threads {threads}` minus the wall of a 4-read run (index load "
                                           f"{r['load_seconds']:.1f}s excluded)"}
                 sam_id = sam_identity(args, meta, r["sam"], ufi_path, batches[0], n_cpu, paired, ctx)
+                try:
+                    n_cli = B * nb
+                    write_fastq_pair(prefix + "_all", np.concatenate([b[2] for b in batches]),
+                                     None if not paired else np.concatenate([b[3] for b in batches]), n_cli, RL)
+                    cli = run_cli(args, ufi_path, prefix, prefix + "_all", n_cli, n_cpu, paired, threads, r["sam"])
+                except Exception as e:
+                    log(f"cli leg failed: {e!r}")
             algo = algorithmic_bytes_per_read(args, ufi_path, batches[0], min(50_000, B), paired)
         except Exception as e:  # the baseline is reported, never required
             log(f"cpu baseline failed: {e!r}")
@@ -539,6 +613,27 @@ def main():
                     "launches_per_step": launches, "avg_launch_ms": 1e3 * avg_s,
                     "share_of_step": kms.get(cls, 0.0) / max(sum(kms.values()), 1e-9)}
 
+        # SURVEY.md §8d's second views: the probe kernel against the measured random-gather rate (its 2 x QWordCount slot
+        # probes per read alone: candidate-window loads come on top, so the fraction is a lower bound), and the DP work of
+        # the alignment kernels against the measured int32 ALU rate (16 ALU ops per cell)
+        roof_gather, roof_alu = None, None
+        if micro:
+            qwc = max(1, RL - meta["word_length"] + 1)
+            acc = 2.0 * qwc * reads_per_step / max(kms.get("probe", 0.0) / 1e3, 1e-9) / 1e9
+            pk = micro["gather_4B"]["gaccess_per_s"]
+            roof_gather = {"kernel": "probe_kernel", "bound": "hbm random sector gather", "achieved": acc, "peak": pk,
+                           "unit": "G accesses/s", "frac": acc / pk, "accesses_per_read": 2 * qwc,
+                           "peak_source": "urmb_peak_gather: random 4-byte reads at 32-byte-aligned addresses over the blob",
+                           "peak_16B_gaccess_per_s": micro["gather_16B"]["gaccess_per_s"]}
+            align_ms = sum(kms.get(k, 0.0) for k in ("align_a", "align_c", "rescue"))
+            cells = algo["dp_cells"] * reads_per_step if "dp_cells" in algo else None
+            if cells:
+                ach = 16.0 * cells / max(align_ms / 1e3, 1e-9) / 1e12
+                roof_alu = {"kernels": "align_kernel_a + align_kernel_c + rescue_kernel", "bound": "int32 alu",
+                            "achieved": ach, "peak": micro["alu"]["tops_per_s"], "unit": "Tops/s",
+                            "frac": ach / micro["alu"]["tops_per_s"], "dp_cells_per_s": cells / (align_ms / 1e3),
+                            "ops_per_cell": 16, "kernel_ms": align_ms,
+                            "peak_source": "urmb_peak_alu: independent LOP3/IADD chains on all SMs"}
         dominant = "rows" if kms.get("rows", 0.0) >= kms.get("probe", 0.0) else "probe"
         other = "probe" if dominant == "rows" else "rows"
         line = {
@@ -552,10 +647,14 @@ def main():
             "clocks": clocks,
             "roofline": roof(dominant),
             "roofline_" + other: roof(other),
+            "roofline_probe_gather": roof_gather,
+            "roofline_dp_alu": roof_alu,
+            "micro": micro,
             "kernel_ms_per_step": dict(kms, wall_incl_launch_gaps=1e3 * t_wall / args.steps,
                                        note="summed launch durations per kernel class; rescue overlaps the next step"),
             "cpu_baseline": cpu_baseline,
             "sam_identity_vs_reference": sam_id,
+            "cli": cli,
             "work_per_read": algo,
             "index": {"slot_count": meta["slot_count"], "seq_data_size": meta["seq_data_size"],
                       "gpu_build_seconds": meta.get("build_seconds"), "indexed_positions": meta.get("indexed")},

@@ -160,6 +160,15 @@ int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t 
                             uint32_t max_ix, void *d_blob, uint64_t *stats);
 const char *urmb_build_last_error(void);
 
+/* ---- measured roofline denominators ("a 32-byte random-gather micro-benchmark on the 27 GB blob" and
+ * "measured int32 ALU op/s from a micro-benchmark on the same box").  No reference counterpart; bench.py calls them.
+ * urmb_peak_gather: n_access random reads of access_bytes (4 | 8 | 16) at 32-byte-aligned addresses uniform over
+ * d_buf[0, n_bytes) (32-byte aligned device pointer, current device); *ms = device time of the best of two timed passes.
+ * urmb_peak_alu: independent LOP3/IADD3/SHF chains, ops_per_thread per thread on SMs x 8 blocks x 256 threads;
+ * *total_ops = 32-bit integer operations executed in *ms. */
+int urmb_peak_gather(const void *d_buf, uint64_t n_bytes, uint32_t access_bytes, uint64_t n_access, float *ms);
+int urmb_peak_alu(uint64_t ops_per_thread, float *ms, double *total_ops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,3 +93,88 @@ def test_cli_gz_input_and_gpu_built_index(cli, golden_dir, tmp_path):
     assert r.returncode == 0, r.stderr
     c = synth.compare_sam(os.path.join(golden_dir, "se.sam"), str(out))
     assert c["identical"] == c["total"] == 580 and c["header_equal"]
+
+
+# ---- the block FASTQ reader (FASTQSeqSource::GetNextLo, fastqseqsource.cpp:9-116; linereader.cpp:54-99) on the CPU ----
+def _fastq_records(path):
+    """Plain restatement: CR bytes dropped everywhere, last line may lack LF, empty lines only at the end."""
+    op = gzip.open if str(path).endswith(".gz") else open
+    data = op(path, "rb").read().replace(b"\r", b"")
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    while lines and lines[-1] == b"":
+        lines.pop()
+    assert len(lines) % 4 == 0
+    return [(lines[i][1:], lines[i + 1], lines[i + 3]) for i in range(0, len(lines), 4)]
+
+
+def _dump(cli, fq, out, extra=()):
+    r = run([cli, "-fastq_dump", str(fq), "-output", str(out)] + list(extra))
+    assert r.returncode == 0, r.stderr
+    return [tuple(l.split(b"\t")) for l in open(out, "rb").read().split(b"\n")[:-1]]
+
+
+@pytest.mark.parametrize("variant", ["lf", "crlf", "no_final_lf", "trailing_blank", "gz", "ragged", "one"])
+def test_fastq_reader_matches_plain_parse(cli, golden_dir, tmp_path, variant):
+    src = open(os.path.join(golden_dir, "se.fq"), "rb").read()
+    fq = tmp_path / "in.fq"
+    if variant == "crlf":
+        src = src.replace(b"\n", b"\r\n")
+    elif variant == "no_final_lf":
+        src = src.rstrip(b"\n")
+    elif variant == "trailing_blank":
+        src = src + b"\n\n\n"
+    elif variant == "ragged":   # reads of every length 0..150, labels with blanks
+        recs = _fastq_records(os.path.join(golden_dir, "se.fq"))
+        src = b"".join(b"@%s extra words\n%s\n+anything\n%s\n" % (l, s[:i % 151], q[:i % 151]) for i, (l, s, q) in enumerate(recs))
+    elif variant == "one":
+        src = b"@only\nACGT\n+\nIIII"
+    if variant == "gz":
+        fq = tmp_path / "in.fq.gz"
+        with gzip.open(fq, "wb") as g:
+            g.write(src)
+    else:
+        fq.write_bytes(src)
+    want = _fastq_records(fq)
+    for extra in (["-batch", "1", "-threads", "1"], ["-batch", "7", "-threads", "3"], ["-batch", "97", "-threads", "8"],
+                  ["-batch", "100000", "-threads", "5"]):
+        if variant in ("ragged", "lf") or extra[1] != "1":
+            assert _dump(cli, fq, tmp_path / "d.txt", extra) == want, (variant, extra)
+
+
+def test_fastq_reader_pairs_and_errors(cli, golden_dir, tmp_path):
+    g1, g2 = os.path.join(golden_dir, "pe_1.fq"), os.path.join(golden_dir, "pe_2.fq")
+    got = _dump(cli, g1, tmp_path / "d.txt", ["-reverse", g2, "-batch", "33", "-threads", "4"])
+    r1, r2 = _fastq_records(g1), _fastq_records(g2)
+    assert got == [x for pair in zip(r1, r2) for x in pair]
+    # mate files of different length (map2.cpp:31)
+    short = tmp_path / "short.fq"
+    short.write_bytes(b"".join(b"@%s\n%s\n+\n%s\n" % r for r in r2[:-3]))
+    r = run([cli, "-fastq_dump", g1, "-reverse", str(short), "-output", str(tmp_path / "x"), "-batch", "50"])
+    assert r.returncode == 1 and "Premature end of file in FASTQ2" in r.stderr
+    good = b"@a\nACGT\n+\nIIII\n"
+    for bad, msg in ((good + b"b\nACGT\n+\nIIII\n", "expected '@'"),
+                     (good + b"@b\nACGT\n+\nIII\n", "4 bases, 3 quals"),
+                     (good + b"@b\nAC-T\n+\nIIII\n", "Invalid sequence letter '-'"),
+                     (good + b"@b\nAC\x01T\n+\nIIII\n", "Non-printing byte 0x01"),
+                     (good + b"\n" + good, "Empty line nr 5"),
+                     (good + b"@b\nACGT\n+\n", "Unexpected end-of-file")):
+        f = tmp_path / "bad.fq"
+        f.write_bytes(bad)
+        for extra in (["-batch", "1"], ["-batch", "100", "-threads", "3"]):
+            r = run([cli, "-fastq_dump", str(f), "-output", str(tmp_path / "x")] + extra)
+            assert r.returncode == 1 and msg in r.stderr and "---Fatal error---" in r.stderr, (bad, extra, r.stderr)
+
+
+def test_ufi_info_matches_reference(cli, oracle, golden_dir):
+    """-ufi_info (ufistats.cpp:148-172): the same four lines (the reference prefixes its progress clock)."""
+    ufi = os.path.join(golden_dir, "ref.ufi")
+    r = run([cli, "-ufi_info", ufi])
+    assert r.returncode == 0
+    mine = [l.strip() for l in r.stderr.splitlines() if l.strip()]
+    assert mine == ["Word length  24", "MaxIx  32", "SeqData  150064 (150.1kb)", "Slots  257171 (257.2kb)"]
+    if os.path.exists(oracle.REF_BIN):
+        ref = subprocess.run([oracle.REF_BIN, "-ufi_info", ufi], capture_output=True, text=True).stderr
+        for l in mine:
+            assert l in ref

@@ -36,6 +36,10 @@ ncu)
   ncu_full align_kernel_c align_full
   ncu_full pair_kernel pair_full
   ncu_full probe_kernel probe_full ;;
+ncul)
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'probe_kernel|seed_kernel|pair_kernel|align_kernel|rows_kernel|finish_kernel|rescue_kernel' -c 200 --csv \
+      --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
+  echo "ncu launches exit $?" ;;
 ncus) ncu_full rows_kernel rows_full ;;
 ncua) ncu_full align_kernel_c align_full ;;
 ncur) ncu_full rescue_kernel rescue_full ;;

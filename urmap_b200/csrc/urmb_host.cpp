@@ -15,18 +15,24 @@
 //   CIGAR                       cigar.cpp:4-41,141-199, state1.cpp:717-734
 //   end-of-run summary          state1.cpp:593-632
 #include <ctype.h>
+#include <errno.h>
+#include <fcntl.h>
 #include <omp.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -82,7 +88,7 @@ static double now_s() {
 // options
 // ------------------------------------------------------------------------------------------------
 struct Opts {
-    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots;
+    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots, ufi_info, fastq_dump;
     unsigned threads = 0, wordlength = 24, maxix = 32, minq = 10, gpus = 1, batch = 262144;
     double load_factor = 0.6;
     bool veryfast = false, quiet = false, gpu_build = false, version = false;
@@ -108,6 +114,8 @@ static Opts ParseCmdLine(int argc, char **argv) {
         else if (name == "map") o.map = val();
         else if (name == "map2") o.map2 = val();
         else if (name == "reverse") o.reverse = val();
+        else if (name == "ufi_info") o.ufi_info = val();
+        else if (name == "fastq_dump") o.fastq_dump = val();
         else if (name == "ufi") o.ufi = val();
         else if (name == "samout") o.samout = val();
         else if (name == "output") o.output = val();
@@ -126,7 +134,8 @@ static Opts ParseCmdLine(int argc, char **argv) {
         else if (name == "version") o.version = true;
         else bad("Unknown option " + name);
     }
-    int ncmd = (!o.make_ufi.empty()) + (!o.map.empty()) + (!o.map2.empty()) + (o.version ? 1 : 0);
+    int ncmd = (!o.make_ufi.empty()) + (!o.map.empty()) + (!o.map2.empty()) + (o.version ? 1 : 0) + (!o.ufi_info.empty()) +
+               (!o.fastq_dump.empty());
     if (ncmd == 0) bad("No command specified");       // getcmd.cpp:6-11
     if (ncmd > 1) bad("Two commands specified");
     return o;
@@ -195,57 +204,379 @@ class LineReader {
 };
 
 // ------------------------------------------------------------------------------------------------
-// FASTQ batches
+// worker pool: Run(fn) executes fn(t, n) on n persistent threads (t = 0 runs on the caller)
 // ------------------------------------------------------------------------------------------------
+class Pool {
+   public:
+    explicit Pool(int n) : n_(std::max(1, n)) {
+        for (int t = 1; t < n_; ++t) th_.emplace_back([this, t]() { Loop(t); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return n_; }
+    template <class F>
+    void Run(F &&fn) {
+        std::function<void(int, int)> f = std::forward<F>(fn);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f;
+            left_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        f(0, n_);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this]() { return left_ == 0; });
+        fn_ = nullptr;
+    }
+
+   private:
+    void Loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)> *f;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&]() { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                f = fn_;
+            }
+            (*f)(t, n_);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--left_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)> *fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int left_ = 0;
+    bool stop_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// FASTQ batches.  The reference parses a byte at a time under a global lock (seqsource.cpp:37-49,
+// linereader.cpp:54-99); here a batch is carved out of a large window of the (decompressed) file: newline positions are
+// found by all threads in parallel, records are validated and their bases copied into one contiguous buffer (what the
+// C ABI takes) in parallel, labels and qualities stay where they are (the window) and are read again by the SAM writer.
+// ------------------------------------------------------------------------------------------------
+struct RawBuf {   // recycled byte buffer (no zero-fill, no shrink)
+    char *p = nullptr;
+    size_t cap = 0;
+    ~RawBuf() { free(p); }
+    void need(size_t n, size_t keep = 0) {
+        if (n <= cap) return;
+        size_t ncap = std::max(n, cap + cap / 2);
+        char *q = (char *)malloc(ncap);
+        if (!q) Die("Out of memory (%zu bytes)", ncap);
+        if (keep) memcpy(q, p, keep);
+        free(p);
+        p = q;
+        cap = ncap;
+    }
+};
+
 struct HostBatch {
-    std::vector<uint8_t> seqs, quals, labels;
-    std::vector<uint32_t> offs{0}, loffs{0};
     uint32_t n = 0;
-    void clear() { seqs.clear(); quals.clear(); labels.clear(); offs.assign(1, 0); loffs.assign(1, 0); n = 0; }
+    RawBuf seqs;                       // bases of all reads, concatenated
+    std::vector<uint32_t> offs;        // n + 1 offsets into seqs
+    std::vector<uint32_t> lab, lablen, qual;   // per read: label / quality offsets into text
+    const char *text = nullptr;        // the window the offsets refer to: own.p or a view into the mapped file
+    RawBuf own;                        // window bytes when they had to be materialised (gz input, CR stripping)
+    const uint8_t *Seq(uint32_t i) const { return (const uint8_t *)seqs.p + offs[i]; }
+    unsigned Len(uint32_t i) const { return offs[i + 1] - offs[i]; }
+    const uint8_t *Label(uint32_t i) const { return (const uint8_t *)text + lab[i]; }
+    const uint8_t *Qual(uint32_t i) const { return (const uint8_t *)text + qual[i]; }
 };
 
 class FastqReader {  // FASTQSeqSource::GetNextLo, fastqseqsource.cpp:9-116
    public:
-    explicit FastqReader(const std::string &path) : lr_(path) {}
-    // appends up to max_reads records; returns number read
-    uint32_t Fill(HostBatch &b, uint32_t max_reads) {
-        uint32_t got = 0;
-        const char *p;
-        size_t n;
-        while (got < max_reads) {
-            if (!lr_.ReadLine(p, n)) break;
-            if (n == 0) {  // empty lines are only allowed at EOF
-                unsigned ln = lr_.line_nr();
-                while (lr_.ReadLine(p, n))
-                    if (n != 0) Die("Empty line nr %u in FASTQ file '%s'", ln, lr_.path().c_str());
-                break;
+    FastqReader(const std::string &path, Pool &pool) : path_(path), pool_(pool) {
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) Die("Cannot open %s", path.c_str());
+        unsigned char magic[2] = {0, 0};
+        size_t got = fread(magic, 1, 2, f);
+        struct stat sb;
+        const bool regular = fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode);
+        fclose(f);
+        if (regular && !(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) && sb.st_size > 0) {
+            int fd = open(path.c_str(), O_RDONLY);
+            if (fd < 0) Die("Cannot open %s", path.c_str());
+            void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            close(fd);
+            if (m != MAP_FAILED) {
+                madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+                map_ = (const char *)m;
+                map_len_ = (size_t)sb.st_size;
             }
-            if (p[0] != '@') Die("Bad line %u in FASTQ file '%s': expected '@'", lr_.line_nr(), lr_.path().c_str());
-            b.labels.insert(b.labels.end(), p + 1, p + n);
-            b.loffs.push_back((uint32_t)b.labels.size());
-            if (!lr_.ReadLine(p, n)) Die("Unexpected end-of-file in FASTQ file %s", lr_.path().c_str());
-            const size_t L = n;
-            for (size_t i = 0; i < L; ++i) {
-                unsigned char c = (unsigned char)p[i];
-                if (!isalpha(c)) {
-                    if (isprint(c)) Die("Invalid sequence letter '%c' in FASTQ, line %u file %s", c, lr_.line_nr(), lr_.path().c_str());
-                    Die("Non-printing byte 0x%02x in FASTQ sequence line %u file %s", c, lr_.line_nr(), lr_.path().c_str());
-                }
-            }
-            b.seqs.insert(b.seqs.end(), p, p + L);
-            b.offs.push_back((uint32_t)b.seqs.size());
-            lr_.ReadLine(p, n);  // '+' line, contents ignored
-            if (!lr_.ReadLine(p, n)) Die("Unexpected end-of-file in FASTQ file %s", lr_.path().c_str());
-            if (n != L) Die("Bad FASTQ record: %u bases, %u quals line %u file %s", (unsigned)L, (unsigned)n, lr_.line_nr(), lr_.path().c_str());
-            b.quals.insert(b.quals.end(), p, p + n);
-            ++b.n;
-            ++got;
         }
-        return got;
+        if (!map_) {   // compressed, a pipe, or empty: stream through zlib (reads plain data transparently too)
+            gz_ = gzopen(path.c_str(), "rb");
+            if (!gz_) Die("Cannot open %s", path.c_str());
+            gzbuffer(gz_, 1 << 20);
+        }
+    }
+    ~FastqReader() {
+        if (gz_) gzclose(gz_);
+        if (map_) munmap((void *)map_, map_len_);
+    }
+
+    // Fills b with up to max_reads records; returns the number read (0 at end of file).
+    uint32_t Fill(HostBatch &b, uint32_t max_reads) {
+        b.n = 0;
+        b.offs.assign(1, 0);
+        if (finished_ || max_reads == 0) return 0;
+        size_t want = std::max<size_t>((size_t)(max_reads * est_rec_ * 1.05) + 4096, 1 << 16);
+        const char *w = nullptr;
+        size_t wn = 0;
+        bool eof = false, stripped = false;
+        for (;;) {   // grow the window until it holds 4 * max_reads lines or the rest of the file
+            Window(b, want, w, wn, eof, stripped);
+            if (ScanLines(w, wn, eof) /* saw '\r' */ && !stripped) {
+                // CR bytes are dropped wherever they are (linereader.cpp:75): rare, so strip them from a private copy
+                stripped = true;
+                continue;
+            }
+            if (nl_.size() >= 4 * (size_t)max_reads || eof) break;
+            want = want + want / 2 + (1 << 20);
+        }
+        size_t lines = nl_.size();
+        if (eof)   // empty lines are allowed at the end of the file only
+            while (lines > 0 && LineLen(lines - 1) == 0) --lines;
+        uint32_t nrec = (uint32_t)std::min<size_t>(lines / 4, max_reads);
+        // an empty line where a record should start: fine if nothing but empty lines follows, fatal otherwise
+        const uint32_t cand = (uint32_t)std::min<size_t>((lines + 3) / 4, max_reads);
+        const uint32_t first_empty = FirstEmptyLabel(cand);
+        if (first_empty < cand) {
+            const unsigned ln = line_base_ + 4 * first_empty + 1;
+            if (!RestIsEmpty(w, wn, LineStart(4 * (size_t)first_empty), eof))
+                Die("Empty line nr %u in FASTQ file '%s'", ln, path_.c_str());
+            nrec = first_empty;
+            finished_ = true;
+        } else if (eof && lines % 4 != 0 && lines / 4 < max_reads) {
+            // a truncated last record: the reference dies when it runs out of lines inside a record
+            CheckLabelLines(w, (uint32_t)(lines / 4) + 1, lines);
+            Die("Unexpected end-of-file in FASTQ file %s", path_.c_str());
+        }
+        Parse(b, w, nrec);
+        const size_t used = nrec ? (size_t)nl_[4 * (size_t)nrec - 1] + 1 : 0;
+        Consume(b, w, std::min(used, wn), wn);
+        line_base_ += 4 * nrec;
+        if (nrec) est_rec_ = std::max(16.0, (double)used / nrec);
+        if (nrec < max_reads && (eof || finished_)) finished_ = true;
+        return nrec;
     }
 
    private:
-    LineReader lr_;
+    // ---- window management: [w, w + wn) are the next unread bytes of the decompressed file
+    void Window(HostBatch &b, size_t want, const char *&w, size_t &wn, bool &eof, bool strip_cr) {
+        if (map_ && !strip_cr && !seen_cr_) {
+            w = map_ + map_pos_;
+            wn = std::min(want, map_len_ - map_pos_);
+            eof = map_pos_ + wn == map_len_;
+            b.text = w;
+            return;
+        }
+        // materialised window in b.own: carry-over of the previous batch first, then fresh bytes
+        RawBuf &o = b.own;
+        if (carry_n_) {
+            o.need(std::max(want, carry_n_));
+            memcpy(o.p, carry_.p, carry_n_);
+            own_n_ = carry_n_;
+            carry_n_ = 0;
+        }
+        o.need(want + 1, own_n_);
+        while (own_n_ < want && !src_eof_) {
+            size_t got;
+            if (map_) {   // CR stripping of a mapped file
+                got = std::min(want - own_n_, map_len_ - map_pos_);
+                memcpy(o.p + own_n_, map_ + map_pos_, got);
+                map_pos_ += got;
+                if (map_pos_ == map_len_) src_eof_ = true;
+            } else {
+                int r = gzread(gz_, o.p + own_n_, (unsigned)std::min<size_t>(want - own_n_, 1u << 30));
+                if (r < 0) Die("Read error in %s", path_.c_str());
+                got = (size_t)r;
+                if (r == 0) src_eof_ = true;
+            }
+            if (strip_cr || seen_cr_) {
+                char *e = std::remove(o.p + own_n_, o.p + own_n_ + got, '\r');
+                got = (size_t)(e - (o.p + own_n_));
+            }
+            own_n_ += got;
+        }
+        if (strip_cr && !seen_cr_) {   // first CR seen: also clean what was already in the window
+            seen_cr_ = true;
+            own_n_ = (size_t)(std::remove(o.p, o.p + own_n_, '\r') - o.p);
+        }
+        w = o.p;
+        wn = own_n_;
+        eof = src_eof_;
+        b.text = w;
+    }
+    void Consume(HostBatch &b, const char *w, size_t used, size_t wn) {
+        if (map_ && !seen_cr_) { map_pos_ += used; return; }
+        carry_n_ = wn - used;   // unread tail of the materialised window goes to the next batch
+        if (carry_n_) {
+            carry_.need(carry_n_);
+            memcpy(carry_.p, w + used, carry_n_);
+        }
+        own_n_ = 0;
+    }
+
+    // ---- newline index of the window; returns true when a CR byte was seen
+    bool ScanLines(const char *w, size_t wn, bool eof) {
+        const int T = pool_.size();
+        if ((int)parts_.size() < T) parts_.resize(T);
+        std::vector<char> cr(T, 0);
+        pool_.Run([&](int t, int nt) {
+            std::vector<uint32_t> &v = parts_[t];
+            v.clear();
+            const size_t lo = wn * t / nt, hi = wn * (t + 1) / nt;
+            const char *p = w + lo, *e = w + hi;
+            if (memchr(p, '\r', hi - lo)) cr[t] = 1;
+            while (p < e) {
+                const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+                if (!q) break;
+                v.push_back((uint32_t)(q - w));
+                p = q + 1;
+            }
+        });
+        for (int t = 0; t < T; ++t) if (cr[t]) return true;
+        size_t total = 0;
+        std::vector<size_t> base(T + 1, 0);
+        for (int t = 0; t < T; ++t) { base[t] = total; total += parts_[t].size(); }
+        const bool virt = eof && wn > 0 && w[wn - 1] != '\n';   // last line of the file may lack its LF
+        nl_.resize(total + (virt ? 1 : 0));
+        pool_.Run([&](int t, int) {
+            if (!parts_[t].empty()) memcpy(nl_.data() + base[t], parts_[t].data(), parts_[t].size() * sizeof(uint32_t));
+        });
+        if (virt) nl_[total] = (uint32_t)wn;
+        return false;
+    }
+    size_t LineStart(size_t line) const { return line ? (size_t)nl_[line - 1] + 1 : 0; }
+    size_t LineLen(size_t line) const { return (size_t)nl_[line] - LineStart(line); }
+    uint32_t FirstEmptyLabel(uint32_t nrec) {
+        std::vector<uint32_t> first(pool_.size(), nrec);
+        pool_.Run([&](int t, int nt) {
+            const uint32_t lo = (uint32_t)((uint64_t)nrec * t / nt), hi = (uint32_t)((uint64_t)nrec * (t + 1) / nt);
+            for (uint32_t r = lo; r < hi; ++r)
+                if (LineLen(4 * (size_t)r) == 0) { first[t] = r; break; }
+        });
+        return *std::min_element(first.begin(), first.end());
+    }
+    bool RestIsEmpty(const char *w, size_t wn, size_t from, bool eof) {
+        for (size_t i = from; i < wn; ++i) if (w[i] != '\n' && w[i] != '\r') return false;
+        if (eof) return true;
+        if (map_) {   // bytes of the file behind the window
+            const size_t start = (w >= map_ && w < map_ + map_len_) ? (size_t)(w - map_) + wn : map_pos_;
+            for (size_t i = start; i < map_len_; ++i) if (map_[i] != '\n' && map_[i] != '\r') return false;
+            return true;
+        }
+        std::vector<char> tmp(1 << 20);
+        for (;;) {
+            int r = gzread(gz_, tmp.data(), (unsigned)tmp.size());
+            if (r < 0) Die("Read error in %s", path_.c_str());
+            if (r == 0) return true;
+            for (int i = 0; i < r; ++i) if (tmp[i] != '\n' && tmp[i] != '\r') return false;
+        }
+    }
+    void CheckLabelLines(const char *w, uint32_t nrec, size_t lines) {
+        for (uint32_t r = 0; r < nrec && 4 * (size_t)r < lines; ++r)
+            if (LineLen(4 * (size_t)r) && w[LineStart(4 * (size_t)r)] != '@')
+                Die("Bad line %u in FASTQ file '%s': expected '@'", line_base_ + 4 * r + 1, path_.c_str());
+    }
+
+    // ---- records [0, nrec) of the window -> b
+    void Parse(HostBatch &b, const char *w, uint32_t nrec) {
+        b.n = nrec;
+        b.offs.resize((size_t)nrec + 1);
+        b.lab.resize(nrec);
+        b.lablen.resize(nrec);
+        b.qual.resize(nrec);
+        const int T = pool_.size();
+        std::vector<uint64_t> sum(T + 1, 0);
+        struct Bad { uint32_t rec = UINT32_MAX; int kind = 0; unsigned a = 0, b = 0; };
+        std::vector<Bad> bad(T);
+        // pass 1: line geometry (no byte of the records is touched but the '@')
+        pool_.Run([&](int t, int nt) {
+            const uint32_t lo = (uint32_t)((uint64_t)nrec * t / nt), hi = (uint32_t)((uint64_t)nrec * (t + 1) / nt);
+            uint64_t s = 0;
+            for (uint32_t r = lo; r < hi; ++r) {
+                const size_t l0 = 4 * (size_t)r;
+                const size_t s0 = LineStart(l0), n0 = (size_t)nl_[l0] - s0;
+                const size_t s1 = (size_t)nl_[l0] + 1, n1 = (size_t)nl_[l0 + 1] - s1;
+                const size_t s3 = (size_t)nl_[l0 + 2] + 1, n3 = (size_t)nl_[l0 + 3] - s3;
+                if (w[s0] != '@') { if (bad[t].rec == UINT32_MAX) bad[t] = Bad{r, 1, 0, 0}; }
+                else if (n3 != n1) { if (bad[t].rec == UINT32_MAX) bad[t] = Bad{r, 2, (unsigned)n1, (unsigned)n3}; }
+                b.lab[r] = (uint32_t)(s0 + 1);
+                b.lablen[r] = (uint32_t)(n0 - 1);
+                b.qual[r] = (uint32_t)s3;
+                b.offs[r + 1] = (uint32_t)n1;   // length for now
+                s += n1;
+            }
+            sum[t + 1] = s;
+        });
+        for (int t = 0; t < T; ++t) sum[t + 1] += sum[t];
+        if (sum[T] >= 0xFFFFFFF0ull) Die("FASTQ batch larger than 4 GB of bases; use a smaller -batch");
+        b.seqs.need(sum[T] + 64);
+        // pass 2: offsets, base validation and copy
+        pool_.Run([&](int t, int nt) {
+            const uint32_t lo = (uint32_t)((uint64_t)nrec * t / nt), hi = (uint32_t)((uint64_t)nrec * (t + 1) / nt);
+            uint32_t off = (uint32_t)sum[t];
+            for (uint32_t r = lo; r < hi; ++r) {
+                const uint32_t L = b.offs[r + 1];
+                const char *src = w + (size_t)nl_[4 * (size_t)r] + 1;
+                char *dst = b.seqs.p + off;
+                unsigned badc = 0;
+                for (uint32_t i = 0; i < L; ++i) {
+                    const unsigned char c = (unsigned char)src[i];
+                    badc |= (unsigned)(((unsigned char)((c | 0x20) - 'a')) > 25);
+                    dst[i] = (char)c;
+                }
+                if (badc && bad[t].rec == UINT32_MAX) bad[t] = Bad{r, 3, 0, 0};
+                off += L;
+                b.offs[r + 1] = off;
+            }
+        });
+        b.offs[0] = 0;
+        Bad first;
+        for (int t = 0; t < T; ++t) if (bad[t].rec < first.rec) first = bad[t];
+        if (first.rec != UINT32_MAX) {
+            const unsigned ln = line_base_ + 4 * first.rec;
+            if (first.kind == 1) Die("Bad line %u in FASTQ file '%s': expected '@'", ln + 1, path_.c_str());
+            if (first.kind == 2)
+                Die("Bad FASTQ record: %u bases, %u quals line %u file %s", first.a, first.b, ln + 4, path_.c_str());
+            const uint8_t *s = b.Seq(first.rec);
+            for (unsigned i = 0; i < b.Len(first.rec); ++i)
+                if (!isalpha(s[i])) {
+                    if (isprint(s[i])) Die("Invalid sequence letter '%c' in FASTQ, line %u file %s", s[i], ln + 2, path_.c_str());
+                    Die("Non-printing byte 0x%02x in FASTQ sequence line %u file %s", s[i], ln + 2, path_.c_str());
+                }
+        }
+    }
+
+    std::string path_;
+    Pool &pool_;
+    gzFile gz_ = nullptr;
+    const char *map_ = nullptr;
+    size_t map_len_ = 0, map_pos_ = 0;
+    RawBuf carry_;
+    size_t carry_n_ = 0, own_n_ = 0;
+    bool src_eof_ = false, seen_cr_ = false, finished_ = false;
+    std::vector<std::vector<uint32_t>> parts_;
+    std::vector<uint32_t> nl_;
+    double est_rec_ = 400.0;
+    unsigned line_base_ = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -292,12 +623,42 @@ struct Contigs {
     }
 };
 
-static inline void put_u(std::string &o, uint32_t v) { char t[16]; int n = snprintf(t, sizeof t, "%u", v); o.append(t, n); }
-static inline void put_i(std::string &o, int v) { char t[16]; int n = snprintf(t, sizeof t, "%d", v); o.append(t, n); }
+// Append-only text buffer of one formatter thread (capacity is kept from batch to batch).
+struct OutBuf {
+    char *p = nullptr;
+    size_t n = 0, cap = 0;
+    ~OutBuf() { free(p); }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    const char *data() const { return p; }
+    inline char *room(size_t k) {   // pointer to k writable bytes at the end (not yet counted)
+        if (n + k > cap) {
+            cap = std::max(n + k, cap + cap / 2 + 4096);
+            p = (char *)realloc(p, cap);
+            if (!p) Die("Out of memory (%zu bytes of SAM text)", cap);
+        }
+        return p + n;
+    }
+    inline void push_back(char c) { *room(1) = c; ++n; }
+    inline void append(const char *s, size_t k) { memcpy(room(k), s, k); n += k; }
+    inline OutBuf &operator+=(const std::string &s) { append(s.data(), s.size()); return *this; }
+    inline OutBuf &operator+=(const char *s) { append(s, strlen(s)); return *this; }
+};
+
+static inline void put_u(OutBuf &o, uint32_t v) {
+    char t[12];
+    int k = 12;
+    do { t[--k] = (char)('0' + v % 10); v /= 10; } while (v);
+    o.append(t + k, 12 - k);
+}
+static inline void put_i(OutBuf &o, int v) {
+    if (v < 0) { o.push_back('-'); put_u(o, (uint32_t)(-(int64_t)v)); }
+    else put_u(o, (uint32_t)v);
+}
 
 // PathToCIGAR (cigar.cpp:4-41, D<->I swapped) + CIGAROpsFixDanglingMs (cigar.cpp:141-199).  The reference's
 // second fix-up block cannot fire once the first has (it would need a length that is both <= 2 and > 4).
-static void RunsToCigar(const uint16_t *runs, unsigned nruns, unsigned QL, std::string &o) {
+static void RunsToCigar(const uint16_t *runs, unsigned nruns, unsigned QL, OutBuf &o) {
     if (nruns == 0) { put_u(o, QL); o.push_back('M'); return; }
     char ops[512];
     unsigned lens[512];
@@ -316,13 +677,16 @@ static void RunsToCigar(const uint16_t *runs, unsigned nruns, unsigned QL, std::
     for (unsigned i = first; i < last; ++i) { put_u(o, lens[i]); o.push_back(ops[i]); }
 }
 
-static void AppendQName(std::string &o, const uint8_t *Label, unsigned n) {  // setsam.cpp:32-44
+static void AppendQName(OutBuf &o, const uint8_t *Label, unsigned n) {  // setsam.cpp:32-44
     if (n > 2 && Label[n - 2] == '/' && (Label[n - 1] == '1' || Label[n - 1] == '2')) n -= 2;
-    for (unsigned i = 0; i < n; ++i) {
-        char c = (char)Label[i];
+    char *d = o.room(n);
+    unsigned k = 0;
+    for (; k < n; ++k) {
+        char c = (char)Label[k];
         if (c == ' ' || c == '\t') break;
-        o.push_back(c);
+        d[k] = c;
     }
+    o.n += k;
 }
 
 struct Mapped { int idx; uint32_t coord; };
@@ -339,7 +703,7 @@ static Mapped SetMappedPos(const Contigs &C, const urmb_result &r, unsigned QL) 
     return m;
 }
 
-static void SamUnmapped(std::string &o, uint32_t aFlags, const uint8_t *Label, unsigned LabelLen, const uint8_t *Seq,
+static void SamUnmapped(OutBuf &o, uint32_t aFlags, const uint8_t *Label, unsigned LabelLen, const uint8_t *Seq,
                         const uint8_t *Qual, unsigned QL) {  // setsam.cpp:12-73
     uint32_t Flags = 0x04;
     if (aFlags & 0x01) Flags |= 0x01;
@@ -355,7 +719,7 @@ static void SamUnmapped(std::string &o, uint32_t aFlags, const uint8_t *Label, u
     o.push_back('\n');
 }
 
-static void SamRecord(const Contigs &C, std::string &o, uint32_t Flags, const Mapped &self, const urmb_result &r,
+static void SamRecord(const Contigs &C, OutBuf &o, uint32_t Flags, const Mapped &self, const urmb_result &r,
                       const uint16_t *runs, int MateIdx, uint32_t MatePos, int TLEN, const uint8_t *Label,
                       unsigned LabelLen, const uint8_t *Seq, const uint8_t *Qual, unsigned QL) {  // setsam.cpp:75-207
     if (self.idx < 0) { SamUnmapped(o, Flags, Label, LabelLen, Seq, Qual, QL); return; }
@@ -381,10 +745,18 @@ static void SamRecord(const Contigs &C, std::string &o, uint32_t Flags, const Ma
     put_i(o, TLEN);
     o.push_back('\t');
     if (Plus) o.append((const char *)Seq, QL);
-    else for (unsigned i = 0; i < QL; ++i) o.push_back((char)g_CompChar[Seq[QL - 1 - i]]);
+    else {
+        char *d = o.room(QL);
+        for (unsigned i = 0; i < QL; ++i) d[i] = (char)g_CompChar[Seq[QL - 1 - i]];
+        o.n += QL;
+    }
     o.push_back('\t');
     if (Plus) o.append((const char *)Qual, QL);
-    else for (unsigned i = 1; i <= QL; ++i) o.push_back((char)Qual[QL - i]);
+    else {
+        char *d = o.room(QL);
+        for (unsigned i = 0; i < QL; ++i) d[i] = (char)Qual[QL - 1 - i];
+        o.n += QL;
+    }
     o.push_back('\n');
 }
 
@@ -406,21 +778,20 @@ static inline void UpdateHitStats(HitCounters &hc, bool has_top, unsigned mapq, 
 
 // formats reads [lo,hi) of a finished batch
 static void FormatSE(const Contigs &C, const HostBatch &b, const urmb_result *res, const uint16_t *runs, uint32_t lo,
-                     uint32_t hi, unsigned minq, std::string &o, HitCounters &hc) {
+                     uint32_t hi, unsigned minq, OutBuf &o, HitCounters &hc) {
     for (uint32_t i = lo; i < hi; ++i) {  // State1::Output1: SetSAM(0, "*", UINT32_MAX, 0)
-        const unsigned QL = b.offs[i + 1] - b.offs[i];
+        const unsigned QL = b.Len(i);
         Mapped m = SetMappedPos(C, res[i], QL);
-        SamRecord(C, o, 0, m, res[i], runs, -1, UINT32_MAX, 0, b.labels.data() + b.loffs[i], b.loffs[i + 1] - b.loffs[i],
-                  b.seqs.data() + b.offs[i], b.quals.data() + b.offs[i], QL);
+        SamRecord(C, o, 0, m, res[i], runs, -1, UINT32_MAX, 0, b.Label(i), b.lablen[i], b.Seq(i), b.Qual(i), QL);
         UpdateHitStats(hc, m.idx >= 0, m.idx >= 0 ? res[i].mapq : 0, minq);
     }
 }
 
 static void FormatPE(const Contigs &C, const HostBatch &b1, const HostBatch &b2, const urmb_result *r1,
-                     const urmb_result *r2, const uint16_t *runs, uint32_t lo, uint32_t hi, unsigned minq, std::string &o,
+                     const urmb_result *r2, const uint16_t *runs, uint32_t lo, uint32_t hi, unsigned minq, OutBuf &o,
                      HitCounters &hc) {
     for (uint32_t i = lo; i < hi; ++i) {  // State2::SetSAM2, output2.cpp:71-132
-        const unsigned L1 = b1.offs[i + 1] - b1.offs[i], L2 = b2.offs[i + 1] - b2.offs[i];
+        const unsigned L1 = b1.Len(i), L2 = b2.Len(i);
         Mapped m1 = SetMappedPos(C, r1[i], L1), m2 = SetMappedPos(C, r2[i], L2);
         const bool Mapped1 = m1.idx >= 0, Mapped2 = m2.idx >= 0;
         const bool Plus1 = Mapped1 && (r1[i].flags & 1), Plus2 = Mapped2 && (r2[i].flags & 1);
@@ -444,10 +815,10 @@ static void FormatPE(const Contigs &C, const HostBatch &b1, const HostBatch &b2,
         uint32_t Flags1 = GetPairedFlags(true, RevComp1, RevComp2, !Mapped2);
         uint32_t Flags2 = GetPairedFlags(false, RevComp2, RevComp1, !Mapped1);
         if (CorrectlyPaired) { Flags1 |= 0x02; Flags2 |= 0x02; }
-        SamRecord(C, o, Flags1, m1, r1[i], runs, m2.idx, m2.coord, TLEN1, b1.labels.data() + b1.loffs[i],
-                  b1.loffs[i + 1] - b1.loffs[i], b1.seqs.data() + b1.offs[i], b1.quals.data() + b1.offs[i], L1);
-        SamRecord(C, o, Flags2, m2, r2[i], runs, m1.idx, m1.coord, TLEN2, b2.labels.data() + b2.loffs[i],
-                  b2.loffs[i + 1] - b2.loffs[i], b2.seqs.data() + b2.offs[i], b2.quals.data() + b2.offs[i], L2);
+        SamRecord(C, o, Flags1, m1, r1[i], runs, m2.idx, m2.coord, TLEN1, b1.Label(i), b1.lablen[i], b1.Seq(i),
+                  b1.Qual(i), L1);
+        SamRecord(C, o, Flags2, m2, r2[i], runs, m1.idx, m1.coord, TLEN2, b2.Label(i), b2.lablen[i], b2.Seq(i),
+                  b2.Qual(i), L2);
         UpdateHitStats(hc, Mapped1, Mapped1 ? r1[i].mapq : 0, minq);
         UpdateHitStats(hc, Mapped2, Mapped2 ? r2[i].mapq : 0, minq);
     }
@@ -470,6 +841,24 @@ struct InFlight {
     std::unique_ptr<HostBatch> b1, b2;
     int gpu = 0, slot = 0;
 };
+
+static void WriteAll(int fd, const char *p, size_t n, const std::string &path) {
+    while (n) {
+        ssize_t w = write(fd, p, n);
+        if (w < 0) { if (errno == EINTR) continue; Die("Write error on %s: %s", path.c_str(), strerror(errno)); }
+        p += w;
+        n -= (size_t)w;
+    }
+}
+static void PWriteAll(int fd, const char *p, size_t n, off_t off, const std::string &path) {
+    while (n) {
+        ssize_t w = pwrite(fd, p, n, off);
+        if (w < 0) { if (errno == EINTR) continue; Die("Write error on %s: %s", path.c_str(), strerror(errno)); }
+        p += w;
+        n -= (size_t)w;
+        off += w;
+    }
+}
 
 static int CmdMap(const Opts &o, bool paired) {
     if (o.ufi.empty()) Die("-ufi required");
@@ -502,43 +891,58 @@ static int CmdMap(const Opts &o, bool paired) {
     const double t_loaded = now_s();
     Progress("Index %s loaded into %d GPU(s) in %.1f s\n", o.ufi.c_str(), ngpu, t_loaded - t_start);
 
-    FILE *fsam = nullptr;
+    // SAM file: header by write(2); record text of a batch by one pwrite per formatter thread when the file can seek
+    int fd_sam = -1;
+    off_t sam_off = 0;
+    bool sam_seek = false;
     if (!o.samout.empty()) {
-        fsam = fopen(o.samout.c_str(), "wb");
-        if (!fsam) Die("Cannot create %s", o.samout.c_str());
-        setvbuf(fsam, nullptr, _IOFBF, 16 << 20);
-        for (uint32_t i = 0; i < ncontig; ++i) fprintf(fsam, "@SQ\tSN:%s\tLN:%u\n", C.labels[i].c_str(), C.lengths[i]);
-        fprintf(fsam, "@PG\tID:urmap\tPN:urmap\tVN:%s\tCL:", URMB_VERSION "-b200");  // state1.cpp:736-752
-        for (auto &a : g_argv) fprintf(fsam, "%s ", a.c_str());
-        fprintf(fsam, "\n");
+        fd_sam = open(o.samout.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd_sam < 0) Die("Cannot create %s", o.samout.c_str());
+        std::string h;
+        for (uint32_t i = 0; i < ncontig; ++i) h += "@SQ\tSN:" + C.labels[i] + "\tLN:" + std::to_string(C.lengths[i]) + "\n";
+        h += "@PG\tID:urmap\tPN:urmap\tVN:" URMB_VERSION "-b200\tCL:";  // state1.cpp:736-752
+        for (auto &a : g_argv) h += a + " ";
+        h += "\n";
+        WriteAll(fd_sam, h.data(), h.size(), o.samout);
+        struct stat sb;
+        sam_seek = fstat(fd_sam, &sb) == 0 && S_ISREG(sb.st_mode) && lseek(fd_sam, 0, SEEK_CUR) == (off_t)h.size();
+        sam_off = (off_t)h.size();
     }
-    int nthreads = o.set_threads ? (int)o.threads : std::min(omp_get_num_procs(), 32);
+    int nthreads = o.set_threads ? (int)o.threads : std::min((int)std::thread::hardware_concurrency(), 32);
     if (nthreads < 1) nthreads = 1;
-    omp_set_num_threads(nthreads);
+    Pool rpool(nthreads), fpool(nthreads);
 
-    FastqReader rd1(paired ? o.map2 : o.map);
+    FastqReader rd1(paired ? o.map2 : o.map, rpool);
     std::unique_ptr<FastqReader> rd2;
-    if (paired) rd2.reset(new FastqReader(o.reverse));
+    if (paired) rd2.reset(new FastqReader(o.reverse, rpool));
 
-    // reader thread(s) -> bounded queue of batches
+    // reader thread -> bounded queue of parsed batches; finished batches are recycled (their buffers stay allocated)
+    typedef std::pair<std::unique_ptr<HostBatch>, std::unique_ptr<HostBatch>> Item;
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<std::pair<std::unique_ptr<HostBatch>, std::unique_ptr<HostBatch>>> q;
+    std::deque<Item> q;
+    std::vector<std::unique_ptr<HostBatch>> spare;
     bool done = false;
-    const size_t qcap = 4;
+    const size_t qcap = 3;
+    double t_read = 0, t_qwait = 0, t_submit = 0, t_gpuwait = 0, t_format = 0, t_write = 0;
+    auto fresh = [&]() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (spare.empty()) return std::unique_ptr<HostBatch>(new HostBatch);
+        std::unique_ptr<HostBatch> b = std::move(spare.back());
+        spare.pop_back();
+        return b;
+    };
     std::thread reader([&]() {
         for (;;) {
-            std::unique_ptr<HostBatch> a(new HostBatch), b;
-            uint32_t n1 = 0, n2 = 0;
+            std::unique_ptr<HostBatch> a = fresh(), b;
+            const double t0 = now_s();
+            uint32_t n1 = rd1.Fill(*a, o.batch), n2 = 0;
             if (paired) {
-                b.reset(new HostBatch);
-                std::thread t2([&]() { n2 = rd2->Fill(*b, o.batch); });
-                n1 = rd1.Fill(*a, o.batch);
-                t2.join();
+                b = fresh();
+                n2 = rd2->Fill(*b, o.batch);
                 if (n1 != n2) Die("Premature end of file in FASTQ%c", n1 > n2 ? '2' : '1');  // map2.cpp:31
-            } else {
-                n1 = rd1.Fill(*a, o.batch);
             }
+            t_read += now_s() - t0;
             std::unique_lock<std::mutex> lk(mu);
             if (n1 == 0) { done = true; cv.notify_all(); return; }
             cv.wait(lk, [&]() { return q.size() < qcap; });
@@ -549,35 +953,54 @@ static int CmdMap(const Opts &o, bool paired) {
 
     HitCounters total;
     std::deque<InFlight> fly;
-    std::vector<std::string> outs(nthreads);
+    std::vector<OutBuf> outs(nthreads);
     std::vector<HitCounters> hcs(nthreads);
+    std::vector<off_t> woff(nthreads + 1);
     auto finish = [&](InFlight &f) {
         const urmb_result *r1, *r2;
         const uint16_t *runs;
         uint32_t used;
+        double t0 = now_s();
         if (urmb_wait(ctxs[f.gpu], f.slot, &r1, &r2, &runs, &used) != 0) Die("GPU %d: %s", f.gpu, urmb_last_error(ctxs[f.gpu]));
+        double t1 = now_s();
+        t_gpuwait += t1 - t0;
         const uint32_t n = f.b1->n;
-        for (auto &s : outs) s.clear();
-        for (auto &h : hcs) h = HitCounters();
-#pragma omp parallel num_threads(nthreads)
-        {
-            int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        fpool.Run([&](int t, int nt) {
+            outs[t].clear();
+            hcs[t] = HitCounters();
             uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
             if (paired) FormatPE(C, *f.b1, *f.b2, r1, r2, runs, lo, hi, o.minq, outs[t], hcs[t]);
             else FormatSE(C, *f.b1, r1, runs, lo, hi, o.minq, outs[t], hcs[t]);
-        }
+        });
+        double t2 = now_s();
+        t_format += t2 - t1;
+        woff[0] = sam_off;
         for (int t = 0; t < nthreads; ++t) {
-            if (fsam) fwrite(outs[t].data(), 1, outs[t].size(), fsam);
+            woff[t + 1] = woff[t] + (off_t)outs[t].size();
             total.query += hcs[t].query; total.accept += hcs[t].accept; total.reject += hcs[t].reject; total.nohit += hcs[t].nohit;
         }
+        if (fd_sam >= 0) {
+            if (sam_seek) {
+                if (ftruncate(fd_sam, woff[nthreads]) != 0) sam_seek = false;   // extend once, then fill in parallel
+            }
+            if (sam_seek) fpool.Run([&](int t, int) { PWriteAll(fd_sam, outs[t].data(), outs[t].size(), woff[t], o.samout); });
+            else for (int t = 0; t < nthreads; ++t) WriteAll(fd_sam, outs[t].data(), outs[t].size(), o.samout);
+            sam_off = woff[nthreads];
+        }
+        t_write += now_s() - t2;
+        std::lock_guard<std::mutex> lk(mu);
+        spare.push_back(std::move(f.b1));
+        if (f.b2) spare.push_back(std::move(f.b2));
     };
     uint64_t k = 0;
     const size_t max_fly = (size_t)ngpu * URMB_SLOTS;
     for (;;) {
-        std::pair<std::unique_ptr<HostBatch>, std::unique_ptr<HostBatch>> item;
+        Item item;
         {
+            const double t0 = now_s();
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&]() { return !q.empty() || done; });
+            t_qwait += now_s() - t0;
             if (q.empty()) break;
             item = std::move(q.front());
             q.pop_front();
@@ -589,17 +1012,23 @@ static int CmdMap(const Opts &o, bool paired) {
         f.slot = (int)((k / ngpu) % URMB_SLOTS);
         f.b1 = std::move(item.first);
         f.b2 = std::move(item.second);
-        urmb_batch u1{f.b1->n, f.b1->seqs.data(), f.b1->offs.data()}, u2{0, nullptr, nullptr};
-        if (paired) u2 = urmb_batch{f.b2->n, f.b2->seqs.data(), f.b2->offs.data()};
+        urmb_batch u1{f.b1->n, (const uint8_t *)f.b1->seqs.p, f.b1->offs.data()}, u2{0, nullptr, nullptr};
+        if (paired) u2 = urmb_batch{f.b2->n, (const uint8_t *)f.b2->seqs.p, f.b2->offs.data()};
+        const double t0 = now_s();
         if (urmb_submit(ctxs[f.gpu], f.slot, &u1, paired ? &u2 : nullptr) != 0) Die("GPU %d: %s", f.gpu, urmb_last_error(ctxs[f.gpu]));
+        t_submit += now_s() - t0;
         fly.push_back(std::move(f));
         ++k;
     }
     while (!fly.empty()) { finish(fly.front()); fly.pop_front(); }
     reader.join();
-    if (fsam) fclose(fsam);
+    if (fd_sam >= 0 && close(fd_sam) != 0) Die("Write error on %s: %s", o.samout.c_str(), strerror(errno));
     const double t_end = now_s();
     const double secs = t_end - t_loaded;
+    if (getenv("URMB_PROFILE"))
+        fprintf(stderr, "[urmb host] %llu batches; reader %.3fs (own thread); main thread: queue wait %.3fs, submit %.3fs, "
+                "gpu wait %.3fs, format %.3fs, write %.3fs; total %.3fs\n", (unsigned long long)k, t_read, t_qwait, t_submit,
+                t_gpuwait, t_format, t_write, secs);
     auto pct = [&](uint64_t x) { return total.query ? 100.0 * x / total.query : 0.0; };
     Progress("\n%16.1f  Seconds to load index\n%16.1f  Seconds in mapper\n", t_loaded - t_start, secs);  // state1.cpp:593-632
     Progress("%16s  Reads (%llu)\n", Commas(total.query).c_str(), (unsigned long long)total.query);
@@ -860,6 +1289,72 @@ static int CmdMakeUfi(const Opts &o) {  // cmd_make_ufi, ufindexio.cpp:117-179
     return 0;
 }
 
+// cmd_ufi_info, ufistats.cpp:148-172: the four header fields, same text
+static std::string MemBytesToStr(double Bytes) {  // myutils.cpp:1220-1235
+    char t[64];
+    if (Bytes < 1e4) snprintf(t, sizeof t, "%.1fb", Bytes);
+    else if (Bytes < 1e6) snprintf(t, sizeof t, "%.1fkb", Bytes / 1e3);
+    else if (Bytes < 10e6) snprintf(t, sizeof t, "%.1fMb", Bytes / 1e6);
+    else if (Bytes < 1e9) snprintf(t, sizeof t, "%.0fMb", Bytes / 1e6);
+    else if (Bytes < 100e9) snprintf(t, sizeof t, "%.1fGb", Bytes / 1e9);
+    else snprintf(t, sizeof t, "%.0fGb", Bytes / 1e9);
+    return t;
+}
+
+static int CmdUfiInfo(const Opts &o) {
+    FILE *f = fopen(o.ufi_info.c_str(), "rb");
+    if (!f) Die("Cannot open %s", o.ufi_info.c_str());
+    uint32_t h[4];
+    uint64_t SlotCount;
+    if (fread(h, 4, 4, f) != 4 || fread(&SlotCount, 8, 1, f) != 1) Die("Error reading %s", o.ufi_info.c_str());
+    fclose(f);
+    if (h[0] != ((uint32_t)'U' << 24 | (uint32_t)'F' << 16 | (uint32_t)'I' << 8 | (uint32_t)'1')) Die("%s is not a UFI file (bad magic)", o.ufi_info.c_str());  // UFI_MAGIC1, ufindex.h
+    Progress(" Word length  %u\n", h[1]);
+    Progress("       MaxIx  %u\n", h[2]);
+    Progress("     SeqData  %u (%s)\n", h[3], MemBytesToStr((double)h[3]).c_str());
+    Progress("       Slots  %llu (%s)\n", (unsigned long long)SlotCount, MemBytesToStr((double)SlotCount).c_str());
+    return 0;
+}
+
+// Diagnostic (no reference counterpart): the records the block FASTQ reader hands to the mapper, one per line as
+// label <TAB> bases <TAB> qualities; with -reverse the mates alternate.  Lets the CPU tests pin the reader.
+static int CmdFastqDump(const Opts &o) {
+    if (o.output.empty()) Die("-output required");
+    int nthreads = o.set_threads ? (int)std::max(1u, o.threads) : 4;
+    Pool pool(nthreads);
+    FastqReader rd1(o.fastq_dump, pool);
+    std::unique_ptr<FastqReader> rd2;
+    if (!o.reverse.empty()) rd2.reset(new FastqReader(o.reverse, pool));
+    FILE *f = fopen(o.output.c_str(), "wb");
+    if (!f) Die("Cannot create %s", o.output.c_str());
+    HostBatch a, b;
+    double t_fill = 0;
+    uint64_t nrec = 0;
+    const bool discard = o.output == "/dev/null";
+    for (;;) {
+        const double t0 = now_s();
+        uint32_t n1 = rd1.Fill(a, o.batch), n2 = rd2 ? rd2->Fill(b, o.batch) : 0;
+        t_fill += now_s() - t0;
+        nrec += n1 + n2;
+        if (discard && n1) continue;
+        if (rd2 && n1 != n2) Die("Premature end of file in FASTQ%c", n1 > n2 ? '2' : '1');
+        if (n1 == 0) break;
+        for (uint32_t i = 0; i < n1; ++i)
+            for (const HostBatch *h : {(const HostBatch *)&a, rd2 ? (const HostBatch *)&b : (const HostBatch *)nullptr}) {
+                if (!h) continue;
+                fwrite(h->Label(i), 1, h->lablen[i], f);
+                fputc('\t', f);
+                fwrite(h->Seq(i), 1, h->Len(i), f);
+                fputc('\t', f);
+                fwrite(h->Qual(i), 1, h->Len(i), f);
+                fputc('\n', f);
+            }
+    }
+    fclose(f);
+    if (getenv("URMB_PROFILE")) fprintf(stderr, "[urmb host] %llu records parsed in %.3f s (%d threads)\n", (unsigned long long)nrec, t_fill, nthreads);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     InitAlpha();
     Opts o = ParseCmdLine(argc, argv);
@@ -867,6 +1362,8 @@ int main(int argc, char **argv) {
     if (!o.log.empty()) g_log = fopen(o.log.c_str(), "w");
     if (o.version) { printf("urmap_b200 v%s (B200-native drop-in for urmap -map/-map2)\n", URMB_VERSION); return 0; }
     if (!o.make_ufi.empty()) return CmdMakeUfi(o);
+    if (!o.ufi_info.empty()) return CmdUfiInfo(o);
+    if (!o.fastq_dump.empty()) return CmdFastqDump(o);
     if (!o.map.empty()) return CmdMap(o, false);
     return CmdMap(o, true);
 }

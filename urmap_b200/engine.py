@@ -67,7 +67,7 @@ EXPORTS = [
     "urmb_ctx_destroy", "urmb_last_error", "urmb_index_upload", "urmb_index_attach", "urmb_index_broadcast",
     "urmb_index_device_desc", "urmb_map_se", "urmb_map_pe", "urmb_submit", "urmb_wait", "urmb_upload",
     "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
-    "urmb_build_index_device", "urmb_build_last_error",
+    "urmb_build_index_device", "urmb_build_last_error", "urmb_peak_gather", "urmb_peak_alu",
 ]
 
 _lib = None
@@ -106,6 +106,8 @@ def lib():
         L.urmb_launch_count.argtypes = [vp]
         L.urmb_mark.argtypes = [vp, C.c_int]
         L.urmb_mark_elapsed.argtypes = [vp, C.POINTER(C.c_float)]
+        L.urmb_peak_gather.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_float)]
+        L.urmb_peak_alu.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_double)]
         for nm in EXPORTS:
             if nm not in ("urmb_last_error", "urmb_launch_count", "urmb_index_free_host", "urmb_ctx_destroy",
                           "urmb_build_last_error"):
@@ -119,6 +121,24 @@ def _check(rc, ctx=None, allow=()):
         msg = lib().urmb_last_error(ctx).decode(errors="replace") if True else ""
         raise UrmbError(rc, msg)
     return rc
+
+
+def peak_gather(d_ptr: int, n_bytes: int, access_bytes: int = 8, n_access: int = 1 << 28) -> dict:
+    """Random sector-aligned reads over a device buffer (current device): the measured denominator of the gather
+    roofline.  Returns accesses/s and GB/s counted at 32 B (one sector) per access."""
+    ms = C.c_float(0)
+    _check(lib().urmb_peak_gather(C.c_void_p(d_ptr), n_bytes, access_bytes, n_access, C.byref(ms)))
+    s = ms.value / 1e3
+    return {"access_bytes": access_bytes, "accesses": n_access, "ms": ms.value, "gaccess_per_s": n_access / s / 1e9,
+            "sector_gbs": 32.0 * n_access / s / 1e9}
+
+
+def peak_alu(ops_per_thread: int = 1 << 22) -> dict:
+    """Measured 32-bit integer ALU rate (independent LOP3/IADD chains on every SM): the DP / extension denominator."""
+    ms = C.c_float(0)
+    ops = C.c_double(0)
+    _check(lib().urmb_peak_alu(ops_per_thread, C.byref(ms), C.byref(ops)))
+    return {"ms": ms.value, "ops": ops.value, "tops_per_s": ops.value / (ms.value / 1e3) / 1e12}
 
 
 class HostIndex:

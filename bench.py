@@ -263,14 +263,14 @@ def run_cli(args, ufi_path, prefix, cli_prefix, n_units, n_ref, paired, threads,
     t_run, err = run(cmd(cli_prefix, cli_prefix + "_cli.sam"))
     reads = n_units * (2 if paired else 1)
     dt = max(t_run - t_load, 1e-3)
-    out = {"value": reads / dt, "unit": "reads/s", "reads": reads, "seconds": dt, "load_seconds": t_load,
+    out = {"value": reads / dt, "unit": "reads/s", "reads": reads, "seconds": dt, "load_seconds": t_load, "wall_seconds": t_run,
            "host_threads": threads,
            "what": "urmap_b200 CLI, FASTQ files -> SAM file in /dev/shm, wall minus the wall of a 4-read run"}
     for ln in err.splitlines():
         if "Seconds in mapper" in ln:
             out["seconds_in_mapper_reported"] = float(ln.split()[0])
         if ln.startswith("[urmb host]"):
-            out["host_profile"] = ln[len("[urmb host] "):]
+            out.setdefault("host_profile", []).append(ln[len("[urmb host] "):])
     if ref_sam and os.path.exists(ref_sam):
         hr, rr = synth.parse_sam(ref_sam)
         hc, rc = synth.parse_sam(cli_prefix + "_cli.sam")

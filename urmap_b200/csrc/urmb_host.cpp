@@ -850,16 +850,55 @@ static void WriteAll(int fd, const char *p, size_t n, const std::string &path) {
         n -= (size_t)w;
     }
 }
-static void PWriteAll(int fd, const char *p, size_t n, off_t off, const std::string &path) {
-    while (n) {
-        ssize_t w = pwrite(fd, p, n, off);
-        if (w < 0) { if (errno == EINTR) continue; Die("Write error on %s: %s", path.c_str(), strerror(errno)); }
-        p += w;
-        n -= (size_t)w;
-        off += w;
-    }
-}
 
+// Bounded hand-over between two pipeline stages; Close() ends the consumer's loop once the queue has drained.
+template <class T>
+class Channel {
+   public:
+    explicit Channel(size_t cap) : cap_(cap) {}
+    void Push(T v) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return q_.size() < cap_; });
+        q_.push_back(std::move(v));
+        cv_.notify_all();
+    }
+    bool Pop(T &v) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = std::move(q_.front());
+        q_.pop_front();
+        cv_.notify_all();
+        return true;
+    }
+    void Close() {
+        std::lock_guard<std::mutex> lk(mu_);
+        closed_ = true;
+        cv_.notify_all();
+    }
+
+   private:
+    size_t cap_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+    bool closed_ = false;
+};
+
+// Results of one finished batch, copied out of the slot's pinned buffers so that the slot can take the next batch
+// while this one is being formatted.
+struct FormatJob {
+    std::unique_ptr<HostBatch> b1, b2;
+    std::vector<urmb_result> res;   // mate 1 results, then mate 2
+    std::vector<uint16_t> runs;
+};
+struct TextSet {   // SAM text of one batch, one piece per formatter thread, in record order
+    std::vector<OutBuf> parts;
+};
+
+// The host pipeline, one thread per stage, every stage internally parallel or cheap:
+//   reader (block FASTQ parse, rpool) -> main (urmb_submit / urmb_wait: the only thread that talks to the C ABI)
+//   -> formatter (SAM text, fpool) -> writer (write(2) in record order)
 static int CmdMap(const Opts &o, bool paired) {
     if (o.ufi.empty()) Die("-ufi required");
     if (paired && o.reverse.empty()) Die("-reverse required");  // map2.cpp:42
@@ -891,10 +930,7 @@ static int CmdMap(const Opts &o, bool paired) {
     const double t_loaded = now_s();
     Progress("Index %s loaded into %d GPU(s) in %.1f s\n", o.ufi.c_str(), ngpu, t_loaded - t_start);
 
-    // SAM file: header by write(2); record text of a batch by one pwrite per formatter thread when the file can seek
     int fd_sam = -1;
-    off_t sam_off = 0;
-    bool sam_seek = false;
     if (!o.samout.empty()) {
         fd_sam = open(o.samout.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
         if (fd_sam < 0) Die("Cannot create %s", o.samout.c_str());
@@ -904,9 +940,6 @@ static int CmdMap(const Opts &o, bool paired) {
         for (auto &a : g_argv) h += a + " ";
         h += "\n";
         WriteAll(fd_sam, h.data(), h.size(), o.samout);
-        struct stat sb;
-        sam_seek = fstat(fd_sam, &sb) == 0 && S_ISREG(sb.st_mode) && lseek(fd_sam, 0, SEEK_CUR) == (off_t)h.size();
-        sam_off = (off_t)h.size();
     }
     int nthreads = o.set_threads ? (int)o.threads : std::min((int)std::thread::hardware_concurrency(), 32);
     if (nthreads < 1) nthreads = 1;
@@ -916,15 +949,15 @@ static int CmdMap(const Opts &o, bool paired) {
     std::unique_ptr<FastqReader> rd2;
     if (paired) rd2.reset(new FastqReader(o.reverse, rpool));
 
-    // reader thread -> bounded queue of parsed batches; finished batches are recycled (their buffers stay allocated)
     typedef std::pair<std::unique_ptr<HostBatch>, std::unique_ptr<HostBatch>> Item;
-    std::mutex mu;
-    std::condition_variable cv;
-    std::deque<Item> q;
+    Channel<Item> parsed(3);
+    Channel<std::unique_ptr<FormatJob>> to_format(2);
+    Channel<std::unique_ptr<TextSet>> to_write(2);
+    std::mutex mu;   // guards the spare lists
     std::vector<std::unique_ptr<HostBatch>> spare;
-    bool done = false;
-    const size_t qcap = 3;
-    double t_read = 0, t_qwait = 0, t_submit = 0, t_gpuwait = 0, t_format = 0, t_write = 0;
+    std::vector<std::unique_ptr<FormatJob>> spare_jobs;
+    std::vector<std::unique_ptr<TextSet>> spare_text;
+    double t_read = 0, t_qwait = 0, t_submit = 0, t_gpuwait = 0, t_copy = 0, t_format = 0, t_write = 0;
     auto fresh = [&]() {
         std::lock_guard<std::mutex> lk(mu);
         if (spare.empty()) return std::unique_ptr<HostBatch>(new HostBatch);
@@ -943,20 +976,62 @@ static int CmdMap(const Opts &o, bool paired) {
                 if (n1 != n2) Die("Premature end of file in FASTQ%c", n1 > n2 ? '2' : '1');  // map2.cpp:31
             }
             t_read += now_s() - t0;
-            std::unique_lock<std::mutex> lk(mu);
-            if (n1 == 0) { done = true; cv.notify_all(); return; }
-            cv.wait(lk, [&]() { return q.size() < qcap; });
-            q.emplace_back(std::move(a), std::move(b));
-            cv.notify_all();
+            if (n1 == 0) { parsed.Close(); return; }
+            parsed.Push(Item(std::move(a), std::move(b)));
         }
     });
 
     HitCounters total;
+    std::thread formatter([&]() {
+        std::vector<HitCounters> hcs(nthreads);
+        std::unique_ptr<FormatJob> job;
+        while (to_format.Pop(job)) {
+            std::unique_ptr<TextSet> ts;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!spare_text.empty()) { ts = std::move(spare_text.back()); spare_text.pop_back(); }
+            }
+            if (!ts) { ts.reset(new TextSet); ts->parts.resize(nthreads); }
+            const double t0 = now_s();
+            const uint32_t n = job->b1->n;
+            const urmb_result *r1 = job->res.data(), *r2 = r1 + n;
+            const uint16_t *runs = job->runs.data();
+            fpool.Run([&](int t, int nt) {
+                OutBuf &out = ts->parts[t];
+                out.clear();
+                hcs[t] = HitCounters();
+                uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
+                if (paired) FormatPE(C, *job->b1, *job->b2, r1, r2, runs, lo, hi, o.minq, out, hcs[t]);
+                else FormatSE(C, *job->b1, r1, runs, lo, hi, o.minq, out, hcs[t]);
+            });
+            for (int t = 0; t < nthreads; ++t) {
+                total.query += hcs[t].query; total.accept += hcs[t].accept; total.reject += hcs[t].reject; total.nohit += hcs[t].nohit;
+            }
+            t_format += now_s() - t0;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                spare.push_back(std::move(job->b1));
+                if (job->b2) spare.push_back(std::move(job->b2));
+                spare_jobs.push_back(std::move(job));
+            }
+            to_write.Push(std::move(ts));
+        }
+        to_write.Close();
+    });
+    std::thread writer([&]() {
+        std::unique_ptr<TextSet> ts;
+        while (to_write.Pop(ts)) {
+            const double t0 = now_s();
+            if (fd_sam >= 0)
+                for (auto &part : ts->parts) WriteAll(fd_sam, part.data(), part.size(), o.samout);
+            t_write += now_s() - t0;
+            std::lock_guard<std::mutex> lk(mu);
+            spare_text.push_back(std::move(ts));
+        }
+    });
+
     std::deque<InFlight> fly;
-    std::vector<OutBuf> outs(nthreads);
-    std::vector<HitCounters> hcs(nthreads);
-    std::vector<off_t> woff(nthreads + 1);
-    auto finish = [&](InFlight &f) {
+    auto retire = [&](InFlight &f) {
         const urmb_result *r1, *r2;
         const uint16_t *runs;
         uint32_t used;
@@ -964,49 +1039,32 @@ static int CmdMap(const Opts &o, bool paired) {
         if (urmb_wait(ctxs[f.gpu], f.slot, &r1, &r2, &runs, &used) != 0) Die("GPU %d: %s", f.gpu, urmb_last_error(ctxs[f.gpu]));
         double t1 = now_s();
         t_gpuwait += t1 - t0;
+        std::unique_ptr<FormatJob> job;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!spare_jobs.empty()) { job = std::move(spare_jobs.back()); spare_jobs.pop_back(); }
+        }
+        if (!job) job.reset(new FormatJob);
         const uint32_t n = f.b1->n;
-        fpool.Run([&](int t, int nt) {
-            outs[t].clear();
-            hcs[t] = HitCounters();
-            uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
-            if (paired) FormatPE(C, *f.b1, *f.b2, r1, r2, runs, lo, hi, o.minq, outs[t], hcs[t]);
-            else FormatSE(C, *f.b1, r1, runs, lo, hi, o.minq, outs[t], hcs[t]);
-        });
-        double t2 = now_s();
-        t_format += t2 - t1;
-        woff[0] = sam_off;
-        for (int t = 0; t < nthreads; ++t) {
-            woff[t + 1] = woff[t] + (off_t)outs[t].size();
-            total.query += hcs[t].query; total.accept += hcs[t].accept; total.reject += hcs[t].reject; total.nohit += hcs[t].nohit;
-        }
-        if (fd_sam >= 0) {
-            if (sam_seek) {
-                if (ftruncate(fd_sam, woff[nthreads]) != 0) sam_seek = false;   // extend once, then fill in parallel
-            }
-            if (sam_seek) fpool.Run([&](int t, int) { PWriteAll(fd_sam, outs[t].data(), outs[t].size(), woff[t], o.samout); });
-            else for (int t = 0; t < nthreads; ++t) WriteAll(fd_sam, outs[t].data(), outs[t].size(), o.samout);
-            sam_off = woff[nthreads];
-        }
-        t_write += now_s() - t2;
-        std::lock_guard<std::mutex> lk(mu);
-        spare.push_back(std::move(f.b1));
-        if (f.b2) spare.push_back(std::move(f.b2));
+        job->res.resize((size_t)n * (paired ? 2 : 1));
+        memcpy(job->res.data(), r1, (size_t)n * sizeof(urmb_result));
+        if (paired) memcpy(job->res.data() + n, r2, (size_t)n * sizeof(urmb_result));
+        job->runs.resize(used);
+        if (used) memcpy(job->runs.data(), runs, (size_t)used * sizeof(uint16_t));
+        job->b1 = std::move(f.b1);
+        job->b2 = std::move(f.b2);
+        t_copy += now_s() - t1;
+        to_format.Push(std::move(job));
     };
     uint64_t k = 0;
     const size_t max_fly = (size_t)ngpu * URMB_SLOTS;
     for (;;) {
         Item item;
-        {
-            const double t0 = now_s();
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&]() { return !q.empty() || done; });
-            t_qwait += now_s() - t0;
-            if (q.empty()) break;
-            item = std::move(q.front());
-            q.pop_front();
-            cv.notify_all();
-        }
-        if (fly.size() == max_fly) { finish(fly.front()); fly.pop_front(); }
+        const double tq = now_s();
+        const bool more = parsed.Pop(item);
+        t_qwait += now_s() - tq;
+        if (!more) break;
+        if (fly.size() == max_fly) { retire(fly.front()); fly.pop_front(); }
         InFlight f;
         f.gpu = (int)(k % ngpu);
         f.slot = (int)((k / ngpu) % URMB_SLOTS);
@@ -1020,15 +1078,19 @@ static int CmdMap(const Opts &o, bool paired) {
         fly.push_back(std::move(f));
         ++k;
     }
-    while (!fly.empty()) { finish(fly.front()); fly.pop_front(); }
+    while (!fly.empty()) { retire(fly.front()); fly.pop_front(); }
+    to_format.Close();
     reader.join();
+    formatter.join();
+    writer.join();
     if (fd_sam >= 0 && close(fd_sam) != 0) Die("Write error on %s: %s", o.samout.c_str(), strerror(errno));
     const double t_end = now_s();
     const double secs = t_end - t_loaded;
-    if (getenv("URMB_PROFILE"))
-        fprintf(stderr, "[urmb host] %llu batches; reader %.3fs (own thread); main thread: queue wait %.3fs, submit %.3fs, "
-                "gpu wait %.3fs, format %.3fs, write %.3fs; total %.3fs\n", (unsigned long long)k, t_read, t_qwait, t_submit,
-                t_gpuwait, t_format, t_write, secs);
+    const bool profile = getenv("URMB_PROFILE") != nullptr;
+    if (profile)
+        fprintf(stderr, "[urmb host] %llu batches; load %.3fs; stage busy times: reader %.3fs, main (queue wait %.3fs, submit "
+                "%.3fs, gpu wait %.3fs, result copy %.3fs), formatter %.3fs, writer %.3fs; mapper total %.3fs\n",
+                (unsigned long long)k, t_loaded - t_start, t_read, t_qwait, t_submit, t_gpuwait, t_copy, t_format, t_write, secs);
     auto pct = [&](uint64_t x) { return total.query ? 100.0 * x / total.query : 0.0; };
     Progress("\n%16.1f  Seconds to load index\n%16.1f  Seconds in mapper\n", t_loaded - t_start, secs);  // state1.cpp:593-632
     Progress("%16s  Reads (%llu)\n", Commas(total.query).c_str(), (unsigned long long)total.query);
@@ -1038,6 +1100,7 @@ static int CmdMap(const Opts &o, bool paired) {
     Progress("%16s  Unmapped (%.1f%%)\n\n", Commas(total.nohit).c_str(), pct(total.nohit));
     for (auto c : ctxs) urmb_ctx_destroy(c);
     urmb_index_free_host(hix);
+    if (profile) fprintf(stderr, "[urmb host] teardown %.3fs\n", now_s() - t_end);
     return 0;
 }
 

@@ -252,9 +252,9 @@ def run_cli(args, ufi_path, prefix, cli_prefix, n_units, n_ref, paired, threads,
         c = ["-map2", p + "_1.fq", "-reverse", p + "_2.fq"] if paired else ["-map", p + "_1.fq"]
         return [exe] + c + ["-ufi", ufi_path, "-samout", sam, "-threads", str(threads)]
 
-    def run(c):
+    def run(c, **env):
         t0 = time.time()
-        p = subprocess.run(c, capture_output=True, env=dict(os.environ, URMB_PROFILE="1"))
+        p = subprocess.run(c, capture_output=True, env=dict(os.environ, URMB_PROFILE="1", **env))
         if p.returncode != 0:
             raise RuntimeError(f"urmap_b200 exited {p.returncode}: {p.stderr.decode(errors='replace')[-300:]!r}")
         return time.time() - t0, p.stderr.decode(errors="replace")
@@ -271,6 +271,14 @@ def run_cli(args, ufi_path, prefix, cli_prefix, n_units, n_ref, paired, threads,
             out["seconds_in_mapper_reported"] = float(ln.split()[0])
         if ln.startswith("[urmb host]"):
             out.setdefault("host_profile", []).append(ln[len("[urmb host] "):])
+    # the same run with the output medium taken out (SAM text to /dev/null) and with plain write(2) instead of the mapping
+    for key, sam, env in (("to_dev_null", "/dev/null", {}), ("write2", cli_prefix + "_cli2.sam", {"URMB_NO_MMAP_OUT": "1"})):
+        try:
+            t2, err2 = run(cmd(cli_prefix, sam), **env)
+            out[key] = {"value": reads / max(t2 - t_load, 1e-3), "unit": "reads/s", "wall_seconds": t2,
+                        "host_profile": [ln[len("[urmb host] "):] for ln in err2.splitlines() if ln.startswith("[urmb host]")]}
+        except Exception as e:
+            out[key] = {"error": repr(e)}
     if ref_sam and os.path.exists(ref_sam):
         hr, rr = synth.parse_sam(ref_sam)
         hc, rc = synth.parse_sam(cli_prefix + "_cli.sam")

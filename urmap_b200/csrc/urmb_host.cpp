@@ -27,6 +27,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -88,7 +91,7 @@ static double now_s() {
 // options
 // ------------------------------------------------------------------------------------------------
 struct Opts {
-    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots, ufi_info, fastq_dump;
+    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots, ufi_info, fastq_dump, sam_bench;
     unsigned threads = 0, wordlength = 24, maxix = 32, minq = 10, gpus = 1, batch = 262144;
     double load_factor = 0.6;
     bool veryfast = false, quiet = false, gpu_build = false, version = false;
@@ -116,6 +119,7 @@ static Opts ParseCmdLine(int argc, char **argv) {
         else if (name == "reverse") o.reverse = val();
         else if (name == "ufi_info") o.ufi_info = val();
         else if (name == "fastq_dump") o.fastq_dump = val();
+        else if (name == "sam_bench") o.sam_bench = val();
         else if (name == "ufi") o.ufi = val();
         else if (name == "samout") o.samout = val();
         else if (name == "output") o.output = val();
@@ -135,7 +139,7 @@ static Opts ParseCmdLine(int argc, char **argv) {
         else bad("Unknown option " + name);
     }
     int ncmd = (!o.make_ufi.empty()) + (!o.map.empty()) + (!o.map2.empty()) + (o.version ? 1 : 0) + (!o.ufi_info.empty()) +
-               (!o.fastq_dump.empty());
+               (!o.fastq_dump.empty()) + (!o.sam_bench.empty());
     if (ncmd == 0) bad("No command specified");       // getcmd.cpp:6-11
     if (ncmd > 1) bad("Two commands specified");
     return o;
@@ -433,23 +437,65 @@ class FastqReader {  // FASTQSeqSource::GetNextLo, fastqseqsource.cpp:9-116
         own_n_ = 0;
     }
 
+    // newline offsets of w[lo, hi) appended to v, 64 bytes per step (SSE2 compares, one bit per byte); true if a CR was seen
+    static bool ScanRange(const char *w, size_t lo, size_t hi, std::vector<uint32_t> &v) {
+        size_t i = lo;
+        bool cr = false;
+#if defined(__SSE2__)
+        const __m128i nl = _mm_set1_epi8('\n'), crv = _mm_set1_epi8('\r');
+        v.reserve(v.size() + (hi - lo) / 48 + 16);
+        for (; i + 64 <= hi; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(w + i)), b = _mm_loadu_si128((const __m128i *)(w + i + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(w + i + 32)), d = _mm_loadu_si128((const __m128i *)(w + i + 48));
+            uint64_t m = (uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(a, nl)) |
+                         ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(b, nl)) << 16) |
+                         ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(c, nl)) << 32) |
+                         ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(d, nl)) << 48);
+            const __m128i anycr = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(a, crv), _mm_cmpeq_epi8(b, crv)),
+                                               _mm_or_si128(_mm_cmpeq_epi8(c, crv), _mm_cmpeq_epi8(d, crv)));
+            if (_mm_movemask_epi8(anycr)) cr = true;
+            while (m) {
+                v.push_back((uint32_t)(i + (size_t)__builtin_ctzll(m)));
+                m &= m - 1;
+            }
+        }
+#endif
+        for (; i < hi; ++i) {
+            if (w[i] == '\n') v.push_back((uint32_t)i);
+            else if (w[i] == '\r') cr = true;
+        }
+        return cr;
+    }
+
+    // every byte a letter (fastqseqsource.cpp:60-70 rejects anything else)
+    static bool AllAlpha(const char *p, size_t n) {
+        size_t i = 0;
+        unsigned bad = 0;
+#if defined(__SSE2__)
+        const __m128i lower = _mm_set1_epi8(0x20), a = _mm_set1_epi8('a'), lim = _mm_set1_epi8(25);
+        __m128i acc = _mm_setzero_si128();
+        for (; i + 16 <= n; i += 16) {
+            const __m128i x = _mm_sub_epi8(_mm_or_si128(_mm_loadu_si128((const __m128i *)(p + i)), lower), a);
+            acc = _mm_or_si128(acc, _mm_subs_epu8(x, lim));   // non-zero where x > 25 (unsigned)
+        }
+        bad = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(acc, _mm_setzero_si128())) ^ 0xFFFFu;
+#endif
+        for (; i < n; ++i) bad |= (unsigned)(((unsigned char)(((unsigned char)p[i] | 0x20) - 'a')) > 25);
+        return bad == 0;
+    }
+
     // ---- newline index of the window; returns true when a CR byte was seen
     bool ScanLines(const char *w, size_t wn, bool eof) {
         const int T = pool_.size();
         if ((int)parts_.size() < T) parts_.resize(T);
         std::vector<char> cr(T, 0);
         pool_.Run([&](int t, int nt) {
-            std::vector<uint32_t> &v = parts_[t];
+            std::vector<uint32_t> v;   // local header: the threads' vector objects would share cache lines
+            v.swap(parts_[t]);
             v.clear();
             const size_t lo = wn * t / nt, hi = wn * (t + 1) / nt;
-            const char *p = w + lo, *e = w + hi;
-            if (memchr(p, '\r', hi - lo)) cr[t] = 1;
-            while (p < e) {
-                const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
-                if (!q) break;
-                v.push_back((uint32_t)(q - w));
-                p = q + 1;
-            }
+            if (ScanRange(w, lo, hi, v)) cr[t] = 1;
+            v.swap(parts_[t]);
         });
         for (int t = 0; t < T; ++t) if (cr[t]) return true;
         size_t total = 0;
@@ -537,12 +583,8 @@ class FastqReader {  // FASTQSeqSource::GetNextLo, fastqseqsource.cpp:9-116
                 const uint32_t L = b.offs[r + 1];
                 const char *src = w + (size_t)nl_[4 * (size_t)r] + 1;
                 char *dst = b.seqs.p + off;
-                unsigned badc = 0;
-                for (uint32_t i = 0; i < L; ++i) {
-                    const unsigned char c = (unsigned char)src[i];
-                    badc |= (unsigned)(((unsigned char)((c | 0x20) - 'a')) > 25);
-                    dst[i] = (char)c;
-                }
+                memcpy(dst, src, L);
+                const bool badc = !AllAlpha(src, L);
                 if (badc && bad[t].rec == UINT32_MAX) bad[t] = Bad{r, 3, 0, 0};
                 off += L;
                 b.offs[r + 1] = off;
@@ -624,13 +666,22 @@ struct Contigs {
 };
 
 // Append-only text buffer of one formatter thread (capacity is kept from batch to batch).
-struct OutBuf {
+struct alignas(128) OutBuf {   // one per formatter thread: own cache lines, the counters are written per byte
     char *p = nullptr;
     size_t n = 0, cap = 0;
     ~OutBuf() { free(p); }
     void clear() { n = 0; }
     size_t size() const { return n; }
     const char *data() const { return p; }
+    void reserve(size_t want) {   // one allocation up front: growing a large block under many threads is what costs
+        if (want <= cap) return;
+        char *q = (char *)malloc(want);
+        if (!q) Die("Out of memory (%zu bytes of SAM text)", want);
+        if (n) memcpy(q, p, n);
+        free(p);
+        p = q;
+        cap = want;
+    }
     inline char *room(size_t k) {   // pointer to k writable bytes at the end (not yet counted)
         if (n + k > cap) {
             cap = std::max(n + k, cap + cap / 2 + 4096);
@@ -767,13 +818,21 @@ static uint32_t GetPairedFlags(bool First, bool RevComp, bool MateRevComp, bool 
     return Flags;
 }
 
-struct HitCounters { uint64_t query = 0, accept = 0, reject = 0, nohit = 0; };
+struct alignas(128) HitCounters { uint64_t query = 0, accept = 0, reject = 0, nohit = 0; };
 
 static inline void UpdateHitStats(HitCounters &hc, bool has_top, unsigned mapq, unsigned minq) {  // output1.cpp:20-30
     ++hc.query;
     if (!has_top) ++hc.nohit;
     else if (mapq >= minq) ++hc.accept;
     else ++hc.reject;
+}
+
+// upper estimate of the SAM text of reads [lo,hi): both copies of bases and qualities, the label, and the fixed columns
+static size_t SamTextEstimate(const HostBatch &b, uint32_t lo, uint32_t hi) {
+    if (hi <= lo) return 0;
+    const size_t bases = b.offs[hi] - b.offs[lo];
+    const size_t labels = (size_t)(b.lab[hi - 1] + b.lablen[hi - 1]) - b.lab[lo];   // spans the records' whole text: generous
+    return 2 * bases + std::min(labels, (size_t)(hi - lo) * 256) + (size_t)(hi - lo) * 96;
 }
 
 // formats reads [lo,hi) of a finished batch
@@ -896,6 +955,67 @@ struct TextSet {   // SAM text of one batch, one piece per formatter thread, in 
     std::vector<OutBuf> parts;
 };
 
+// SAM output.  A regular file is extended and filled through a shared mapping by several threads (write(2) serialises
+// on the inode and was the slowest stage of the pipeline); anything else (pipe, device) gets plain sequential writes.
+class SamSink {
+   public:
+    SamSink(const std::string &path, int nthreads) : path_(path), pool_(std::max(1, std::min(nthreads, 8))) {
+        if (path.empty()) return;
+        fd_ = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd_ < 0) Die("Cannot create %s", path.c_str());
+        struct stat sb;
+        map_ = fstat(fd_, &sb) == 0 && S_ISREG(sb.st_mode) && !getenv("URMB_NO_MMAP_OUT");
+        page_ = (size_t)sysconf(_SC_PAGESIZE);
+    }
+    ~SamSink() { Close(); }
+    bool active() const { return fd_ >= 0; }
+    void Header(const std::string &h) {
+        if (fd_ < 0) return;
+        WriteAll(fd_, h.data(), h.size(), path_);
+        off_ += (off_t)h.size();
+    }
+    void Append(const std::vector<OutBuf> &parts) {   // the parts in order
+        if (fd_ < 0) return;
+        const size_t np = parts.size();
+        woff_.assign(np + 1, 0);
+        for (size_t i = 0; i < np; ++i) woff_[i + 1] = woff_[i] + parts[i].size();
+        const size_t len = woff_[np], lead = (size_t)off_ % page_;
+        char *m = nullptr;
+        if (map_ && len) {
+            if (ftruncate(fd_, off_ + (off_t)len) == 0) {
+                void *q = mmap(nullptr, len + lead, PROT_READ | PROT_WRITE, MAP_SHARED, fd_, off_ - (off_t)lead);
+                if (q != MAP_FAILED) m = (char *)q;
+            }
+            if (!m) {   // not mappable after all: position the descriptor and stay with write(2)
+                map_ = false;
+                if (ftruncate(fd_, off_) != 0 || lseek(fd_, off_, SEEK_SET) < 0) Die("Write error on %s: %s", path_.c_str(), strerror(errno));
+            }
+        }
+        if (m) {
+            pool_.Run([&](int t, int nt) {
+                for (size_t i = (size_t)t; i < np; i += (size_t)nt) memcpy(m + lead + woff_[i], parts[i].data(), parts[i].size());
+            });
+            munmap(m, len + lead);
+        } else {
+            for (auto &part : parts) WriteAll(fd_, part.data(), part.size(), path_);
+        }
+        off_ += (off_t)len;
+    }
+    void Close() {
+        if (fd_ >= 0 && close(fd_) != 0) Die("Write error on %s: %s", path_.c_str(), strerror(errno));
+        fd_ = -1;
+    }
+
+   private:
+    std::string path_;
+    Pool pool_;
+    int fd_ = -1;
+    off_t off_ = 0;
+    bool map_ = false;
+    size_t page_ = 4096;
+    std::vector<size_t> woff_;
+};
+
 // The host pipeline, one thread per stage, every stage internally parallel or cheap:
 //   reader (block FASTQ parse, rpool) -> main (urmb_submit / urmb_wait: the only thread that talks to the C ABI)
 //   -> formatter (SAM text, fpool) -> writer (write(2) in record order)
@@ -930,19 +1050,17 @@ static int CmdMap(const Opts &o, bool paired) {
     const double t_loaded = now_s();
     Progress("Index %s loaded into %d GPU(s) in %.1f s\n", o.ufi.c_str(), ngpu, t_loaded - t_start);
 
-    int fd_sam = -1;
-    if (!o.samout.empty()) {
-        fd_sam = open(o.samout.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
-        if (fd_sam < 0) Die("Cannot create %s", o.samout.c_str());
+    int nthreads = o.set_threads ? (int)o.threads : std::min((int)std::thread::hardware_concurrency(), 32);
+    if (nthreads < 1) nthreads = 1;
+    SamSink sink(o.samout, nthreads);
+    if (sink.active()) {
         std::string h;
         for (uint32_t i = 0; i < ncontig; ++i) h += "@SQ\tSN:" + C.labels[i] + "\tLN:" + std::to_string(C.lengths[i]) + "\n";
         h += "@PG\tID:urmap\tPN:urmap\tVN:" URMB_VERSION "-b200\tCL:";  // state1.cpp:736-752
         for (auto &a : g_argv) h += a + " ";
         h += "\n";
-        WriteAll(fd_sam, h.data(), h.size(), o.samout);
+        sink.Header(h);
     }
-    int nthreads = o.set_threads ? (int)o.threads : std::min((int)std::thread::hardware_concurrency(), 32);
-    if (nthreads < 1) nthreads = 1;
     Pool rpool(nthreads), fpool(nthreads);
 
     FastqReader rd1(paired ? o.map2 : o.map, rpool);
@@ -1001,6 +1119,7 @@ static int CmdMap(const Opts &o, bool paired) {
                 out.clear();
                 hcs[t] = HitCounters();
                 uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
+                out.reserve(SamTextEstimate(*job->b1, lo, hi) + (paired ? SamTextEstimate(*job->b2, lo, hi) : 0));
                 if (paired) FormatPE(C, *job->b1, *job->b2, r1, r2, runs, lo, hi, o.minq, out, hcs[t]);
                 else FormatSE(C, *job->b1, r1, runs, lo, hi, o.minq, out, hcs[t]);
             });
@@ -1022,8 +1141,7 @@ static int CmdMap(const Opts &o, bool paired) {
         std::unique_ptr<TextSet> ts;
         while (to_write.Pop(ts)) {
             const double t0 = now_s();
-            if (fd_sam >= 0)
-                for (auto &part : ts->parts) WriteAll(fd_sam, part.data(), part.size(), o.samout);
+            sink.Append(ts->parts);
             t_write += now_s() - t0;
             std::lock_guard<std::mutex> lk(mu);
             spare_text.push_back(std::move(ts));
@@ -1083,7 +1201,7 @@ static int CmdMap(const Opts &o, bool paired) {
     reader.join();
     formatter.join();
     writer.join();
-    if (fd_sam >= 0 && close(fd_sam) != 0) Die("Write error on %s: %s", o.samout.c_str(), strerror(errno));
+    sink.Close();
     const double t_end = now_s();
     const double secs = t_end - t_loaded;
     const bool profile = getenv("URMB_PROFILE") != nullptr;
@@ -1418,6 +1536,75 @@ static int CmdFastqDump(const Opts &o) {
     return 0;
 }
 
+// Diagnostic (no reference counterpart): host-only timing of the FASTQ reader and the SAM formatter over made-up
+// results (every read mapped gapless, alternating strands), to size the host stages without a GPU.
+static int CmdSamBench(const Opts &o) {
+    int nthreads = o.set_threads ? (int)std::max(1u, o.threads) : (int)std::thread::hardware_concurrency();
+    Pool pool(nthreads);
+    FastqReader rd1(o.sam_bench, pool);
+    std::unique_ptr<FastqReader> rd2;
+    if (!o.reverse.empty()) rd2.reset(new FastqReader(o.reverse, pool));
+    Contigs C;
+    C.labels = {"chr1", "chr2"};
+    C.lengths = {2000000000u, 1000000000u};
+    C.offsets = {0u, 2000000032u};
+    std::vector<OutBuf> outs(nthreads);
+    std::vector<HitCounters> hcs(nthreads);
+    std::vector<urmb_result> res;
+    HostBatch a, b;
+    double t_fill = 0, t_fmt = 0, t_wr = 0;
+    uint64_t nrec = 0, bytes = 0;
+    const int reps = getenv("URMB_BENCH_REPS") ? atoi(getenv("URMB_BENCH_REPS")) : 1;
+    SamSink sink(o.output, nthreads);
+    for (;;) {
+        double t0 = now_s();
+        uint32_t n1 = rd1.Fill(a, o.batch), n2 = rd2 ? rd2->Fill(b, o.batch) : 0;
+        double t1 = now_s();
+        t_fill += t1 - t0;
+        if (n1 == 0) break;
+        res.resize((size_t)n1 * 2);
+        for (uint32_t i = 0; i < 2 * n1; ++i) {
+            urmb_result r;
+            memset(&r, 0, sizeof r);
+            r.db_pos = (uint32_t)((nrec + i) * 977 % 1900000000u) + (i >= n1 ? 300 : 0);
+            r.flags = (uint8_t)(2 | ((i ^ (i >= n1)) & 1));
+            r.mapq = 40;
+            res[i] = r;
+        }
+        t1 = now_s();
+        for (int rep = 1; rep < reps; ++rep) {
+            const double r0 = now_s();
+            pool.Run([&](int t, int nt) {
+                outs[t].clear();
+                uint32_t lo = (uint32_t)((uint64_t)n1 * t / nt), hi = (uint32_t)((uint64_t)n1 * (t + 1) / nt);
+                outs[t].reserve(SamTextEstimate(a, lo, hi) + (rd2 ? SamTextEstimate(b, lo, hi) : 0));
+                if (rd2) FormatPE(C, a, b, res.data(), res.data() + n1, nullptr, lo, hi, 10, outs[t], hcs[t]);
+                else FormatSE(C, a, res.data(), nullptr, lo, hi, 10, outs[t], hcs[t]);
+            });
+            fprintf(stderr, "  rep %d: %.3fs\n", rep, now_s() - r0);
+        }
+        t1 = now_s();
+        pool.Run([&](int t, int nt) {
+            outs[t].clear();
+            uint32_t lo = (uint32_t)((uint64_t)n1 * t / nt), hi = (uint32_t)((uint64_t)n1 * (t + 1) / nt);
+            outs[t].reserve(SamTextEstimate(a, lo, hi) + (rd2 ? SamTextEstimate(b, lo, hi) : 0));
+            if (rd2) FormatPE(C, a, b, res.data(), res.data() + n1, nullptr, lo, hi, 10, outs[t], hcs[t]);
+            else FormatSE(C, a, res.data(), nullptr, lo, hi, 10, outs[t], hcs[t]);
+        });
+        double t2 = now_s();
+        t_fmt += t2 - t1;
+        for (auto &x : outs) bytes += x.size();
+        sink.Append(outs);
+        t_wr += now_s() - t2;
+        nrec += n1 + n2;
+        (void)n2;
+    }
+    sink.Close();
+    fprintf(stderr, "[urmb host] %llu records, %d threads: read %.3fs, format %.3fs (%.1f MB of SAM), write %.3fs\n",
+            (unsigned long long)nrec, nthreads, t_fill, t_fmt, bytes / 1e6, t_wr);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     InitAlpha();
     Opts o = ParseCmdLine(argc, argv);
@@ -1427,6 +1614,7 @@ int main(int argc, char **argv) {
     if (!o.make_ufi.empty()) return CmdMakeUfi(o);
     if (!o.ufi_info.empty()) return CmdUfiInfo(o);
     if (!o.fastq_dump.empty()) return CmdFastqDump(o);
+    if (!o.sam_bench.empty()) return CmdSamBench(o);
     if (!o.map.empty()) return CmdMap(o, false);
     return CmdMap(o, true);
 }

@@ -160,6 +160,13 @@ int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t 
                             uint32_t max_ix, void *d_blob, uint64_t *stats);
 const char *urmb_build_last_error(void);
 
+/* ---- page-locked host memory for read batches.  When the `seqs` pointers of a batch handed to urmb_submit / urmb_upload
+ * lie in page-locked memory (from urmb_host_alloc, cudaHostAlloc / cudaHostRegister, a pinned torch tensor ...) the bases
+ * are copied to the device straight from there, without the staging copy; such a batch must then stay unchanged until
+ * urmb_wait has returned for that slot.  Pageable batches are staged as before and may be reused right after the call. */
+int urmb_host_alloc(size_t bytes, void **out);
+void urmb_host_free(void *p);
+
 /* ---- measured roofline denominators ("a 32-byte random-gather micro-benchmark on the 27 GB blob" and
  * "measured int32 ALU op/s from a micro-benchmark on the same box").  No reference counterpart; bench.py calls them.
  * urmb_peak_gather: n_access random reads of access_bytes (4 | 8 | 16) at 32-byte-aligned addresses uniform over

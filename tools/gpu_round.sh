@@ -36,6 +36,9 @@ ncu)
   ncu_full align_kernel_c align_full
   ncu_full pair_kernel pair_full
   ncu_full probe_kernel probe_full ;;
+benchse)
+  timeout 900 python bench.py --single-end --pairs-per-step 2000000 --steps 5 --warmup 3 --cpu-sample-pairs 500000 > $OUT/bench_se.json 2> $OUT/bench_se.log; echo "benchse exit $?"
+  cat $OUT/bench_se.json ;;
 ncul)
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'probe_kernel|seed_kernel|pair_kernel|align_kernel|rows_kernel|finish_kernel|rescue_kernel' -c 200 --csv \
       --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1

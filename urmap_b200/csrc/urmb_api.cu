@@ -444,6 +444,15 @@ static int grow_dev(urmb_ctx *c, T *&p, size_t &cap, size_t need) {
     return URMB_OK;
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. urmb_host_alloc or a pinned torch tensor) can be read
+// by the copy engine directly; anything else goes through the slot's pinned staging buffer.
+static bool is_pinned_host(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static int check_batch(urmb_ctx *c, const urmb_batch *b) {
     if (!b || (b->n && (!b->seqs || !b->offs))) return fail(c, URMB_E_ARG, "null batch");
     return URMB_OK;
@@ -467,18 +476,19 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     if (nbytes >= 0xFFFFFFF0ull) return fail(c, URMB_E_UNSUPPORTED, "batch larger than 4 GB of bases");
     // previous use of this slot must have drained
     CK(cudaStreamSynchronize(s.copy));
-    if ((rc = grow_host(c, s.h_seqs, s.h_seqs_cap, nbytes + 64))) return rc;
+    const bool direct = n > 0 && !getenv("URMB_NO_DIRECT_H2D") && is_pinned_host(r1->seqs) && (!r2 || is_pinned_host(r2->seqs));
+    if (!direct && (rc = grow_host(c, s.h_seqs, s.h_seqs_cap, nbytes + 64))) return rc;
     if ((rc = grow_host(c, s.h_offs, s.h_offs_cap, (size_t)nreads + 1))) return rc;
     if ((rc = grow_dev(c, s.d_seqs, s.d_seqs_cap, nbytes + 64))) return rc;
     if ((rc = grow_dev(c, s.d_offs, s.d_offs_cap, (size_t)nreads + 1))) return rc;
     uint32_t maxlen = 0;
     if (n) {
-        memcpy(s.h_seqs, r1->seqs + r1->offs[0], b1);
+        if (!direct) memcpy(s.h_seqs, r1->seqs + r1->offs[0], b1);
         const uint32_t o0 = r1->offs[0];
         for (uint32_t i = 0; i <= n; ++i) s.h_offs[i] = r1->offs[i] - o0;
         for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r1->offs[i + 1] - r1->offs[i]);
         if (r2) {
-            memcpy(s.h_seqs + b1, r2->seqs + r2->offs[0], b2);
+            if (!direct) memcpy(s.h_seqs + b1, r2->seqs + r2->offs[0], b2);
             const uint32_t p0 = r2->offs[0];
             for (uint32_t i = 0; i <= n; ++i) s.h_offs[n + i] = (uint32_t)b1 + (r2->offs[i] - p0);
             for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r2->offs[i + 1] - r2->offs[i]);
@@ -532,7 +542,12 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     if ((rc = grow_dev(c, s.d_runs, s.d_runs_cap, runs_need))) return rc;
     if ((rc = grow_host(c, s.h_runs, s.h_runs_cap, s.d_runs_cap))) return rc;
     CK(cudaEventRecord(s.ev_h2d0, s.copy));
-    CK(cudaMemcpyAsync(s.d_seqs, s.h_seqs, nbytes, cudaMemcpyHostToDevice, s.copy));
+    if (direct) {   // the caller's pinned bases go to the device as they are; they must stay valid until urmb_wait
+        CK(cudaMemcpyAsync(s.d_seqs, r1->seqs + r1->offs[0], b1, cudaMemcpyHostToDevice, s.copy));
+        if (r2) CK(cudaMemcpyAsync(s.d_seqs + b1, r2->seqs + r2->offs[0], b2, cudaMemcpyHostToDevice, s.copy));
+    } else {
+        CK(cudaMemcpyAsync(s.d_seqs, s.h_seqs, nbytes, cudaMemcpyHostToDevice, s.copy));
+    }
     CK(cudaMemcpyAsync(s.d_offs, s.h_offs, ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, s.copy));
     CK(cudaEventRecord(s.ev_h2d, s.copy));
     s.staged = true;
@@ -646,6 +661,22 @@ extern "C" int urmb_download(urmb_ctx *c, int si) {
     // Paths are few and short: copy the whole pool prefix a typical batch uses, the rest on demand in wait.
     s.downloaded = true;
     return URMB_OK;
+}
+
+extern "C" int urmb_host_alloc(size_t bytes, void **out) {
+    if (!out) return URMB_E_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        set_global_error(std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? URMB_E_NODEVICE : URMB_E_CUDA;
+    }
+    return URMB_OK;
+}
+
+extern "C" void urmb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int urmb_submit(urmb_ctx *c, int si, const urmb_batch *r1, const urmb_batch *r2) {

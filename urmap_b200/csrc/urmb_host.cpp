@@ -289,9 +289,37 @@ struct RawBuf {   // recycled byte buffer (no zero-fill, no shrink)
     }
 };
 
+struct PinnedBuf {   // bases of a batch in page-locked memory: urmb_submit then copies them to the device without staging
+    char *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    ~PinnedBuf() { release(); }
+    void release() {
+        if (pinned) urmb_host_free(p); else free(p);
+        p = nullptr;
+        cap = 0;
+    }
+    void need(size_t n) {   // contents are not kept
+        if (n <= cap) return;
+        release();
+        const size_t ncap = ((n + n / 8) | ((1u << 20) - 1)) + 1;
+        void *q = nullptr;
+        static bool can_pin = true;   // false once the driver said no (host-only diagnostics without a GPU)
+        if (can_pin && urmb_host_alloc(ncap, &q) == 0) pinned = true;
+        else {
+            can_pin = false;
+            pinned = false;
+            q = malloc(ncap);
+            if (!q) Die("Out of memory (%zu bytes)", ncap);
+        }
+        p = (char *)q;
+        cap = ncap;
+    }
+};
+
 struct HostBatch {
     uint32_t n = 0;
-    RawBuf seqs;                       // bases of all reads, concatenated
+    PinnedBuf seqs;                    // bases of all reads, concatenated
     std::vector<uint32_t> offs;        // n + 1 offsets into seqs
     std::vector<uint32_t> lab, lablen, qual;   // per read: label / quality offsets into text
     const char *text = nullptr;        // the window the offsets refer to: own.p or a view into the mapped file

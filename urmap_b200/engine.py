@@ -68,6 +68,7 @@ EXPORTS = [
     "urmb_index_device_desc", "urmb_map_se", "urmb_map_pe", "urmb_submit", "urmb_wait", "urmb_upload",
     "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
     "urmb_build_index_device", "urmb_build_last_error", "urmb_peak_gather", "urmb_peak_alu",
+    "urmb_host_alloc", "urmb_host_free",
 ]
 
 _lib = None
@@ -108,9 +109,12 @@ def lib():
         L.urmb_mark_elapsed.argtypes = [vp, C.POINTER(C.c_float)]
         L.urmb_peak_gather.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_float)]
         L.urmb_peak_alu.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_double)]
+        L.urmb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        L.urmb_host_free.argtypes = [vp]
+        L.urmb_host_free.restype = None
         for nm in EXPORTS:
             if nm not in ("urmb_last_error", "urmb_launch_count", "urmb_index_free_host", "urmb_ctx_destroy",
-                          "urmb_build_last_error"):
+                          "urmb_build_last_error", "urmb_host_free"):
                 getattr(L, nm).restype = C.c_int
         _lib = L
     return _lib

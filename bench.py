@@ -584,7 +584,7 @@ def main():
             if r is not None:
                 cpu_baseline = {"value": r["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
                                 "sample": f"first {n_cpu} {'pairs' if paired else 'reads'} of batch 0; wall of "
-                                          f"`urmap -map2 -threads {threads}` minus the wall of a 4-read run (index load "
+                                          f"`urmap {'-map2' if paired else '-map'} -threads {threads}` minus the wall of a 4-read run (index load "
                                           f"{r['load_seconds']:.1f}s excluded)"}
                 sam_id = sam_identity(args, meta, r["sam"], ufi_path, batches[0], n_cpu, paired, ctx)
                 try:

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <vector>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "urmb_internal.h"
@@ -342,8 +343,13 @@ extern "C" int urmb_index_device_desc(const urmb_ctx *c, urmb_index_desc *out) {
 }
 
 // Chunked H2D through two pinned staging buffers (the 30 GB human-scale file is never pinned whole).
+// Host (mapped file) -> device through two page-locked staging buffers; the staging copy, which also takes the page
+// faults of the mapping, is what bounds the load, so several threads share each chunk.
 static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n) {
-    const size_t CH = 64u << 20;
+    const size_t CH = 128u << 20;
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt);
+    if (getenv("URMB_LOAD_THREADS")) nt = (unsigned)std::max(1, atoi(getenv("URMB_LOAD_THREADS")));
     uint8_t *stage[2] = {nullptr, nullptr};
     cudaEvent_t ev[2];
     CK(cudaHostAlloc(&stage[0], CH, cudaHostAllocDefault));
@@ -351,10 +357,18 @@ static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n) {
     CK(cudaEventCreate(&ev[0]));
     CK(cudaEventCreate(&ev[1]));
     int k = 0;
+    std::vector<std::thread> th;
     for (size_t o = 0; o < n; o += CH, k ^= 1) {
-        size_t m = std::min(CH, n - o);
+        const size_t m = std::min(CH, n - o);
         CK(cudaEventSynchronize(ev[k]));
-        memcpy(stage[k], src + o, m);
+        const size_t piece = ((m + nt - 1) / nt + 4095) & ~(size_t)4095;
+        th.clear();
+        for (unsigned t = 1; t < nt; ++t) {
+            const size_t lo = std::min(m, t * piece), hi = std::min(m, (t + 1) * piece);
+            if (hi > lo) th.emplace_back([=]() { memcpy(stage[k] + lo, src + o + lo, hi - lo); });
+        }
+        memcpy(stage[k], src + o, std::min(m, piece));
+        for (auto &x : th) x.join();
         CK(cudaMemcpyAsync((uint8_t *)dst + o, stage[k], m, cudaMemcpyHostToDevice, c->compute));
         CK(cudaEventRecord(ev[k], c->compute));
     }

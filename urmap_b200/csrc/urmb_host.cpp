@@ -1074,7 +1074,20 @@ static int CmdMap(const Opts &o, bool paired) {
     std::vector<urmb_ctx *> ctxs(ngpu, nullptr);
     for (int g = 0; g < ngpu; ++g)
         if (urmb_ctx_create(g, &p, &ctxs[g]) != 0) Die("GPU %d: %s", g, urmb_last_error(nullptr));
+    // page-locked batch buffers are slow to allocate (~0.4 s for the ones in circulation): get them while the index loads
+    std::mutex mu;   // guards the spare lists
+    std::vector<std::unique_ptr<HostBatch>> spare;
+    std::thread prealloc([&]() {
+        const int want = (paired ? 2 : 1) * (6 + ngpu * URMB_SLOTS);
+        for (int i = 0; i < want; ++i) {
+            std::unique_ptr<HostBatch> b(new HostBatch);
+            b->seqs.need((size_t)o.batch * 152 + 64);
+            std::lock_guard<std::mutex> lk(mu);
+            spare.push_back(std::move(b));
+        }
+    });
     if (urmb_index_broadcast(ctxs.data(), ngpu, hix) != 0) Die("index upload: %s", urmb_last_error(ctxs[0]));
+    prealloc.join();
     const double t_loaded = now_s();
     Progress("Index %s loaded into %d GPU(s) in %.1f s\n", o.ufi.c_str(), ngpu, t_loaded - t_start);
 
@@ -1099,8 +1112,6 @@ static int CmdMap(const Opts &o, bool paired) {
     Channel<Item> parsed(3);
     Channel<std::unique_ptr<FormatJob>> to_format(2);
     Channel<std::unique_ptr<TextSet>> to_write(2);
-    std::mutex mu;   // guards the spare lists
-    std::vector<std::unique_ptr<HostBatch>> spare;
     std::vector<std::unique_ptr<FormatJob>> spare_jobs;
     std::vector<std::unique_ptr<TextSet>> spare_text;
     double t_read = 0, t_qwait = 0, t_submit = 0, t_gpuwait = 0, t_copy = 0, t_format = 0, t_write = 0;
@@ -1244,6 +1255,9 @@ static int CmdMap(const Opts &o, bool paired) {
     Progress("%16s  Mapped Q>=%u (%.1f%%)\n", Commas(total.accept).c_str(), o.minq, pct(total.accept));
     Progress("%16s  Mapped Q< %u (%.1f%%)\n", Commas(total.reject).c_str(), o.minq, pct(total.reject));
     Progress("%16s  Unmapped (%.1f%%)\n\n", Commas(total.nohit).c_str(), pct(total.nohit));
+    if (g_log) fclose(g_log);
+    fflush(nullptr);
+    if (!getenv("URMB_TEARDOWN")) _exit(0);   // the output is complete: leave the 70 GB of mappings and device memory to the OS
     for (auto c : ctxs) urmb_ctx_destroy(c);
     urmb_index_free_host(hix);
     if (profile) fprintf(stderr, "[urmb host] teardown %.3fs\n", now_s() - t_end);

@@ -1603,11 +1603,12 @@ __device__ __noinline__ bool se_phase3(const Env &E, Mate &m) {
     }
     return false;
 }
-// Phases 4 and 5 (search1m6.cpp:149-245): non-BOTH1 owned slots; rows <= 2 now, longer rows deferred
-__device__ __noinline__ bool se_phase45(const Env &E, Mate &m) {
+// Phases 4 and 5 (search1m6.cpp:149-245): non-BOTH1 owned slots; rows <= 2 now, longer rows deferred.  Two pieces so
+// that the staged search can run them as two kernels: the deferred lists stay in m.g->todo, their lengths in m.nPend
+// (the paired-end pending counters, unused by the single-end search).
+__device__ __noinline__ bool se_phase4(const Env &E, Mate &m) {
     const int QL = (int)m.QL;
     const uint32_t QWC = m.QWC;
-    int nTodo[2] = {0, 0};
     for (int s = 0; s < 2; ++s) {
         // the owned non-BOTH1 slots of this strand in QPos order (search1m6.cpp:170-203), then rows <= 2 / deferral
         uint8_t *lst = m.g->todo[s];
@@ -1623,14 +1624,22 @@ __device__ __noinline__ bool se_phase45(const Env &E, Mate &m) {
         __syncwarp();
         int nt = 0;
         rows_short_round(E, m, s, lst, nl, lst, nt);
-        nTodo[s] = nt;
+        m.nPend[s] = nt;
     }
     __syncwarp();
     if (m.Best >= QL + E.P.XP3 * E.P.MM) { m.Mapq = calc_mapq6(m); return true; }
-    for (int s = 0; s < 2; ++s)
-        rows_long_batch(E, m, s, m.g->todo[s], nTodo[s]);
-    if (m.Best >= QL + E.P.XP4 * E.P.MM) { m.Mapq = calc_mapq6(m); return true; }
     return false;
+}
+__device__ __forceinline__ bool se_phase5_done(const DevParams &P, int QL, int Best) { return Best >= QL + P.XP4 * P.MM; }
+__device__ __noinline__ bool se_phase5(const Env &E, Mate &m) {
+    for (int s = 0; s < 2; ++s)
+        rows_long_batch(E, m, s, m.g->todo[s], m.nPend[s]);
+    if (se_phase5_done(E.P, (int)m.QL, m.Best)) { m.Mapq = calc_mapq6(m); return true; }
+    return false;
+}
+__device__ bool se_phase45(const Env &E, Mate &m) {
+    if (se_phase4(E, m)) return true;
+    return se_phase5(E, m);
 }
 // Phase 6 (search1m6.cpp:247-276)
 __device__ __noinline__ void se_phase6(const Env &E, Mate &m) {
@@ -2316,21 +2325,22 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
 // (search1pepend.cpp:15-51); STAGE 1: the pending rows (:53-110); STAGE 2: the final HSP alignments and MAPQ (:112-129).
 // STAGE 3-5: the same for the single-end search (one saved state per read): phase 3, phases 4-5, phase 6 + result.
 // STAGE 6: paired-end pending round 2 (the deferred long rows), STAGE 1 then only does round 1.
+// STAGE 7: single-end phase 5 (the deferred long rows), STAGE 4 then only does phase 4.
 template <int STAGE>
 __device__ __forceinline__ void stage_body(const KArgs &A) {
-    constexpr bool SE = STAGE >= 3 && STAGE <= 5;
+    constexpr bool SE = (STAGE >= 3 && STAGE <= 5) || STAGE == 7;
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int gw = blockIdx.x * wpb + warp;
     uint8_t *sw = smem + (size_t)warp * A.spw;
     const DevBatch &b = A.b;
-    const SmemPlan pl{1u, 0u, (STAGE == 1 || STAGE == 4 || STAGE == 6) ? 0u : 1u};
+    const SmemPlan pl{1u, 0u, (STAGE == 1 || STAGE == 4 || STAGE == 6 || STAGE == 7) ? 0u : 1u};
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
     const uint32_t n_work = (SE ? 1u : 2u) * A.o.counters[CT_TODO];
     for (;;) {
         uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&A.o.counters[STAGE == 6 ? CT_STAGE_B2 : CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
+        if (lane == 0) k = atomicAdd(&A.o.counters[(STAGE == 6 || STAGE == 7) ? CT_STAGE_B2 : CT_STAGE_A + (SE ? STAGE - 3 : STAGE)], 1u);
         k = __shfl_sync(FULL, k, 0);
         if (k >= n_work) break;
         MateSave *sv = A.pool + k;
@@ -2339,6 +2349,8 @@ __device__ __forceinline__ void stage_body(const KArgs &A) {
         const uint32_t r = (!SE && (k & 1u)) ? b.n_units + u : u;
         if (h.done && STAGE != 5) continue;
         if (STAGE == 6 && h.nPend[0] + h.nPend[1] == 0) continue;   // no deferred rows
+        if (STAGE == 7 && h.nPend[0] + h.nPend[1] == 0 &&
+            !se_phase5_done(A.P, (int)(b.offs[r + 1] - b.offs[r]), h.Best)) continue;   // phase 5 would do nothing
         if (STAGE == 0 || STAGE == 3) {   // nothing to align (save_mate already reset the paired-end penalty bound)
             const int QL = (int)(b.offs[r + 1] - b.offs[r]);
             if (STAGE == 0 && h.BestHSP < (QL * A.P.TERM3_PCT) / 100) continue;
@@ -2358,7 +2370,8 @@ __device__ __forceinline__ void stage_body(const KArgs &A) {
         else if (STAGE == 6) pend_stage_b2(E, m);
         else if (STAGE == 2) { pend_stage_c(E, m); done = true; }
         else if (STAGE == 3) done = se_phase3(E, m);
-        else if (STAGE == 4) done = se_phase45(E, m);
+        else if (STAGE == 4) done = se_phase4(E, m);
+        else if (STAGE == 7) done = se_phase5(E, m);
         else { se_phase6(E, m); done = true; }
         if (STAGE == 5) write_result(E, m, A.o, u);
         else mate_to_hdr(E, m, sv, done);
@@ -2418,6 +2431,7 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
 __global__ void __launch_bounds__(128, URMB_LB_PAIR) seed_kernel_se(const __grid_constant__ KArgs A) { search_body<0>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se3(const __grid_constant__ KArgs A) { stage_body<3>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_kernel_se(const __grid_constant__ KArgs A) { stage_body<4>(A); }
+__global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_long_kernel_se(const __grid_constant__ KArgs A) { stage_body<7>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se6(const __grid_constant__ KArgs A) { stage_body<5>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_PAIR) pair_kernel(const __grid_constant__ KArgs A) { search_body<1>(A); }
 __global__ void __launch_bounds__(128, 4) rescue_kernel(const __grid_constant__ KArgs A) { search_body<2>(A); }
@@ -2490,7 +2504,7 @@ static KArgs make_kargs(const DevIndex &ix, const DevParams &P, const DevBatch &
 }
 
 // Returns the number of kernels launched or a negative cudaError.
-//   single-end: per chunk  seed_kernel_se -> align_kernel_se3 -> rows_kernel_se -> align_kernel_se6.
+//   single-end: per chunk  seed_kernel_se -> align_kernel_se3 -> rows_kernel_se -> rows_long_kernel_se -> align_kernel_se6.
 //   paired-end: per chunk of R.pool_pairs pairs  pair_kernel -> align_kernel_a -> rows_kernel -> align_kernel_c ->
 //               finish_kernel (each a small kernel over the saved mate states); launch_rescue does the rest.
 int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
@@ -2514,8 +2528,9 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
             URMB_TRY(launch_one(seed_kernel_se, 1, tr, A, SmemPlan{1, 1, 0}, cnt, R, stream, sm_count, warps_used));
             URMB_TRY(launch_one(align_kernel_se3, 2, tr, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
             URMB_TRY(launch_one(rows_kernel_se, 3, tr, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
+            URMB_TRY(launch_one(rows_long_kernel_se, 3, tr, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
             URMB_TRY(launch_one(align_kernel_se6, 4, tr, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
-            n += 4;
+            n += 5;
         }
         return n;
     }

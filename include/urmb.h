@@ -160,6 +160,11 @@ int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t 
                             uint32_t max_ix, void *d_blob, uint64_t *stats);
 const char *urmb_build_last_error(void);
 
+/* Optional: size all slots for batches of n_units reads (pairs when paired != 0) of up to max_read_len bases ahead of
+ * the first urmb_submit.  It touches the slots only and may run on another thread while urmb_index_upload /
+ * urmb_index_broadcast of the same context is still copying; word_length is the index's (UFI header). */
+int urmb_reserve(urmb_ctx *c, uint32_t n_units, uint32_t max_read_len, int paired, uint32_t word_length);
+
 /* ---- page-locked host memory for read batches.  When the `seqs` pointers of a batch handed to urmb_submit / urmb_upload
  * lie in page-locked memory (from urmb_host_alloc, cudaHostAlloc / cudaHostRegister, a pinned torch tensor ...) the bases
  * are copied to the device straight from there, without the staging copy; such a batch must then stay unchanged until

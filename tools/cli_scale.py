@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=10_000_000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--batches", default="", help="comma list of -batch values to try with the SAM text sent to /dev/null")
     ap.add_argument("--workdir", default="/dev/shm/urmb_cli_scale")
     a = ap.parse_args()
     # everything lives in RAM (tmpfs): 30 GB UFI + 0.63 GB FASTQ and 1.6 GB of SAM per million pairs, plus the readers'
@@ -85,9 +86,9 @@ def main():
     out = {"pairs": a.pairs, "reads": 2 * a.pairs, "host_threads": threads, "gpus": a.gpus,
            "workload": "3.1 Gb synthetic reference (24 contigs, 10% repeats), 2x150 bp, 1% subs + 0.1% indels"}
 
-    def cli(sam, **env):
+    def cli(sam, batch=None, **env):
         c = [exe, "-map2", prefix + "_1.fq", "-reverse", prefix + "_2.fq", "-ufi", ufi, "-samout", sam, "-threads",
-             str(threads), "-gpus", str(a.gpus)]
+             str(threads), "-gpus", str(a.gpus)] + (["-batch", str(batch)] if batch else [])
         t0 = time.time()
         p = subprocess.run(c, capture_output=True, env=dict(os.environ, URMB_PROFILE="1", **env))
         wall = time.time() - t0
@@ -102,6 +103,9 @@ def main():
 
     out["urmap_b200"] = cli(os.path.join(a.workdir, "urmb.sam"))
     out["urmap_b200_to_dev_null"] = cli("/dev/null")
+    for bsz in [int(x) for x in a.batches.split(",") if x]:
+        out[f"to_dev_null_batch_{bsz}"] = cli("/dev/null", batch=bsz)
+        out[f"to_file_batch_{bsz}"] = cli(os.path.join(a.workdir, "urmb2.sam"), batch=bsz)
     if not a.no_reference and os.path.exists(O.REF_BIN):
         c = [O.REF_BIN, "-map2", prefix + "_1.fq", "-reverse", prefix + "_2.fq", "-ufi", ufi, "-samout",
              os.path.join(a.workdir, "ref.sam"), "-threads", str(threads)]

@@ -472,6 +472,54 @@ static int check_batch(urmb_ctx *c, const urmb_batch *b) {
     return URMB_OK;
 }
 
+// Sizes every slot (and the pool of saved mate states) for batches of n_units reads / pairs of up to max_read_len bases,
+// so that the first batches do not pay for the allocations.  Touches only the slots and the pool: the CLI calls it from
+// a helper thread while urmb_index_broadcast is still copying the index.
+extern "C" int urmb_reserve(urmb_ctx *c, uint32_t n_units, uint32_t max_read_len, int paired, uint32_t word_length) {
+    if (!c || n_units == 0 || max_read_len == 0 || max_read_len > (uint32_t)kMaxLen || word_length < 8 || word_length > 32)
+        return URMB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const size_t n = n_units, nreads = paired ? 2 * n : n;
+    const size_t nbytes = nreads * max_read_len;
+    if (nbytes >= 0xFFFFFFF0ull) return fail(c, URMB_E_UNSUPPORTED, "batch larger than 4 GB of bases");
+    const uint32_t qwc = max_read_len >= word_length ? max_read_len - word_length + 1 : 1;
+    const uint32_t qcap = (qwc + 31) & ~31u, seqcap = (std::max(max_read_len, 32u) + 31) & ~31u;
+    int rc;
+    for (auto &s : c->slots) {
+        if ((rc = grow_host(c, s.h_offs, s.h_offs_cap, nreads + 1))) return rc;
+        if ((rc = grow_dev(c, s.d_seqs, s.d_seqs_cap, nbytes + 64))) return rc;
+        if ((rc = grow_dev(c, s.d_offs, s.d_offs_cap, nreads + 1))) return rc;
+        const size_t probe_need = nreads * 2 * qcap;
+        if (probe_need > s.d_probe_cap) {
+            cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext);
+            s.d_tally = nullptr; s.d_pos = nullptr; s.d_ext = nullptr;
+            s.d_probe_cap = 0;
+            CK(cudaMalloc(&s.d_tally, probe_need));
+            CK(cudaMalloc(&s.d_pos, probe_need * 4));
+            CK(cudaMalloc(&s.d_ext, probe_need * 4));
+            s.d_probe_cap = probe_need;
+        }
+        if ((rc = grow_dev(c, s.d_view, s.d_view_cap, nreads * view_stride_for(seqcap) + 64))) return rc;
+        if ((rc = grow_dev(c, s.d_res, s.d_res_cap, nreads + 1))) return rc;
+        if ((rc = grow_dev(c, s.d_todo, s.d_todo_cap, n + 1))) return rc;
+        if ((rc = grow_dev(c, s.d_rescue, s.d_rescue_cap, n + 1))) return rc;
+        if ((rc = grow_host(c, s.h_res, s.h_res_cap, nreads + 1))) return rc;
+        if ((rc = grow_dev(c, s.d_runs, s.d_runs_cap, nreads * 8 + 4096))) return rc;
+        if ((rc = grow_host(c, s.h_runs, s.h_runs_cap, s.d_runs_cap))) return rc;
+    }
+    const size_t units = paired ? n : (n + 1) / 2;
+    const size_t want = std::min<size_t>(std::max<size_t>(units, 1), c->chunk_pairs);
+    if (want > c->pool_pairs) {
+        CK(cudaStreamSynchronize(c->compute));
+        cudaFree(c->pool);
+        c->pool = nullptr;
+        c->pool_pairs = 0;
+        CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
+        c->pool_pairs = want;
+    }
+    return URMB_OK;
+}
+
 extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb_batch *r2) {
     if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
     if (!c->have_index) return fail(c, URMB_E_ARG, "no index attached");

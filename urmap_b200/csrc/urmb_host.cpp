@@ -1078,6 +1078,8 @@ static int CmdMap(const Opts &o, bool paired) {
     std::mutex mu;   // guards the spare lists
     std::vector<std::unique_ptr<HostBatch>> spare;
     std::thread prealloc([&]() {
+        for (int g = 0; g < ngpu; ++g)   // slot buffers for reads of up to 160 bases; longer reads grow them later
+            if (urmb_reserve(ctxs[g], o.batch, 160, paired ? 1 : 0, d.word_length) != 0) Die("GPU %d: %s", g, urmb_last_error(ctxs[g]));
         const int want = (paired ? 2 : 1) * (6 + ngpu * URMB_SLOTS);
         for (int i = 0; i < want; ++i) {
             std::unique_ptr<HostBatch> b(new HostBatch);

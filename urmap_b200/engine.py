@@ -68,7 +68,7 @@ EXPORTS = [
     "urmb_index_device_desc", "urmb_map_se", "urmb_map_pe", "urmb_submit", "urmb_wait", "urmb_upload",
     "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
     "urmb_build_index_device", "urmb_build_last_error", "urmb_peak_gather", "urmb_peak_alu",
-    "urmb_host_alloc", "urmb_host_free",
+    "urmb_host_alloc", "urmb_host_free", "urmb_reserve",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def lib():
         L.urmb_mark_elapsed.argtypes = [vp, C.POINTER(C.c_float)]
         L.urmb_peak_gather.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_float)]
         L.urmb_peak_alu.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_double)]
+        L.urmb_reserve.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
         L.urmb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
         L.urmb_host_free.argtypes = [vp]
         L.urmb_host_free.restype = None

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=10_000_000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--write-threads", default="", help="comma list of URMB_WRITE_THREADS values to try (SAM file in /dev/shm)")
     ap.add_argument("--batches", default="", help="comma list of -batch values to try with the SAM text sent to /dev/null")
     ap.add_argument("--workdir", default="/dev/shm/urmb_cli_scale")
     a = ap.parse_args()
@@ -103,6 +104,8 @@ def main():
 
     out["urmap_b200"] = cli(os.path.join(a.workdir, "urmb.sam"))
     out["urmap_b200_to_dev_null"] = cli("/dev/null")
+    for wt in [int(x) for x in a.write_threads.split(",") if x]:
+        out[f"to_file_write_threads_{wt}"] = cli(os.path.join(a.workdir, "urmb2.sam"), URMB_WRITE_THREADS=str(wt))
     for bsz in [int(x) for x in a.batches.split(",") if x]:
         out[f"to_dev_null_batch_{bsz}"] = cli("/dev/null", batch=bsz)
         out[f"to_file_batch_{bsz}"] = cli(os.path.join(a.workdir, "urmb2.sam"), batch=bsz)

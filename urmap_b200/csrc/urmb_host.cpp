@@ -987,7 +987,8 @@ struct TextSet {   // SAM text of one batch, one piece per formatter thread, in 
 // on the inode and was the slowest stage of the pipeline); anything else (pipe, device) gets plain sequential writes.
 class SamSink {
    public:
-    SamSink(const std::string &path, int nthreads) : path_(path), pool_(std::max(1, std::min(nthreads, 8))) {
+    SamSink(const std::string &path, int nthreads)
+        : path_(path), pool_(getenv("URMB_WRITE_THREADS") ? std::max(1, atoi(getenv("URMB_WRITE_THREADS"))) : std::max(1, std::min(nthreads, 8))) {
         if (path.empty()) return;
         fd_ = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
         if (fd_ < 0) Die("Cannot create %s", path.c_str());

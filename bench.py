@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 
+_OUT = sys.stdout
+
+
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
@@ -370,6 +373,11 @@ def algorithmic_bytes_per_read(args, ufi_path, batch, n_units, paired):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version there) get stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -466,7 +474,7 @@ def main():
                 "e2e": {"value": r["reads_per_s"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "index_built_by": "urmb_build_index_device on the GPU (functionally equivalent UFI; setup, not timed)",
                 "load_seconds": r["load_seconds"]}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
         return 0
 
     # ------------------------------------------------------------------ urmb arm
@@ -676,7 +684,7 @@ def main():
             "index": {"slot_count": meta["slot_count"], "seq_data_size": meta["seq_data_size"],
                       "gpu_build_seconds": meta.get("build_seconds"), "indexed_positions": meta.get("indexed")},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     ctx.close()
     if args.workdir.startswith("/dev/shm") and rank == 0 and not os.environ.get("URMB_KEEP_BENCH_DIR"):
         shutil.rmtree(args.workdir, ignore_errors=True)

@@ -45,6 +45,7 @@ typedef struct urmb_params {
     int32_t pe_method;   /* 4 = default -map2 (Search4), 5 = -map2 -veryfast (Search5) */
     int32_t band_radius; /* <0: method default (12 / 8; Search5 uses 4) */
     int32_t minq;        /* statistics only (map2.cpp:75) */
+    int32_t want_second; /* != 0: paired-end searches also report State2's second pair (urmb_second_hits; -tabbedout) */
 } urmb_params;
 
 /* A batch of reads: concatenated ASCII bases + n+1 offsets (what FASTQSeqSource::GetNext,
@@ -70,6 +71,14 @@ typedef struct urmb_result {
     uint8_t hit_count;
     uint8_t hsp_count;
 } urmb_result;
+/* Second pair of a paired-end search: m_UD_Fwd/Rev.m_SecondHit as AdjustTopHitsAndMapqs leaves them (search2.cpp:49-56),
+ * which is what State2::OutputTab2 prints (outputtab2.cpp:85-119).  flags bit1 clear = no second hit. */
+typedef struct urmb_second {
+    uint32_t db_pos; /* m_SecondHit->m_DBStartPos */
+    int16_t score;   /* m_SecondHit->m_Score */
+    uint8_t flags;   /* bit0 plus strand, bit1 has second hit */
+    uint8_t pad;
+} urmb_second;
 /* path run: u16 = (len << 2) | op, op 0='M' 1='D' 2='I' in the reference's PATH alphabet
  * (D consumes the read, I consumes the genome; PathToCIGAR, cigar.cpp:22-25, swaps them). */
 
@@ -138,6 +147,8 @@ int urmb_map_pe(urmb_ctx *c, const urmb_batch *r1, const urmb_batch *r2, urmb_re
 int urmb_submit(urmb_ctx *c, int slot, const urmb_batch *r1, const urmb_batch *r2);
 int urmb_wait(urmb_ctx *c, int slot, const urmb_result **res1, const urmb_result **res2,
               const uint16_t **runs, uint32_t *runs_used);
+/* After urmb_wait on a paired-end slot of a context created with want_second: the second hits of mate 1 / mate 2. */
+int urmb_second_hits(urmb_ctx *c, int slot, const urmb_second **s1, const urmb_second **s2);
 /* Finer-grained steps (bench.py uses them to time the kernels with inputs resident in HBM). */
 int urmb_upload(urmb_ctx *c, int slot, const urmb_batch *r1, const urmb_batch *r2);
 int urmb_launch(urmb_ctx *c, int slot);

@@ -78,6 +78,7 @@ struct DevOut {
     uint32_t *counters;    // [CT_COUNT]
     uint32_t *todo;        // [chunk pairs] pairs of the current chunk saved for the staged second pass
     uint32_t *rescue;      // [n_units] pairs that need mate rescue (State2::ScanPair)
+    urmb_second *second;   // [n_reads] or null: State2's second pair (m_SecondHit, search2.cpp:49-56), zero-filled per launch
 };
 
 constexpr int kRunPool = 2048;  // path runs of all hits of one mate

@@ -1830,6 +1830,7 @@ __device__ __noinline__ void scan_mate(const Env &E, Mate &m, uint32_t DBPos, ui
 struct PairState {
     int BestPairScore, SecondBestPairScore;
     int BestF, BestR;   // hit indexes of the best pair (-1: none)
+    int SecF, SecR;     // hit indexes of m_SecondPairIndex (-1: UINT_MAX)
     int PairCount;
 };
 
@@ -1839,6 +1840,7 @@ __device__ __noinline__ void find_pairs(const Env &E, const Mate &F, const Mate 
     ps.BestPairScore = -1;
     ps.SecondBestPairScore = -1;
     ps.BestF = ps.BestR = -1;
+    ps.SecF = ps.SecR = -1;
     ps.PairCount = 0;
     for (int hf = 0; hf < F.HitCount; ++hf) {
         const int ScoreF = F.g->hit_score[hf];
@@ -1861,15 +1863,22 @@ __device__ __noinline__ void find_pairs(const Env &E, const Mate &F, const Mate 
                 int bit = __ffs(bal) - 1;
                 bal &= bal - 1;
                 int Total = ScoreF + __shfl_sync(FULL, ScoreR, bit);
-                if (Total > ps.BestPairScore) {
+                if (Total > ps.BestPairScore) {   // state2.cpp:61-67
+                    ps.SecF = ps.BestF;
+                    ps.SecR = ps.BestR;
                     ps.SecondBestPairScore = ps.BestPairScore;
                     ps.BestPairScore = Total;
                     ps.BestF = hf;
                     ps.BestR = base + bit;
-                } else if (Total == ps.BestPairScore)
+                } else if (Total == ps.BestPairScore) {   // :68-72
+                    ps.SecF = hf;
+                    ps.SecR = base + bit;
                     ps.SecondBestPairScore = ps.BestPairScore;
-                else if (Total > ps.SecondBestPairScore)
+                } else if (Total > ps.SecondBestPairScore) {   // :73-77: the second INDEX becomes the best pair's
+                    ps.SecF = ps.BestF;
+                    ps.SecR = ps.BestR;
                     ps.SecondBestPairScore = Total;
+                }
                 ++ps.PairCount;
             }
         }
@@ -1917,6 +1926,24 @@ __device__ __noinline__ void adjust_pair(Mate &F, Mate &R, const PairState &ps) 
 
 // ExtendPen of seed i of mate m on strand Plus: through the memo when Plus is the seed's own strand, otherwise
 // (search2m4.cpp:94-95,122 extend a stored seed on the strand dictated by the OTHER mate's seed) computed here.
+// m_SecondHit of both mates (search2.cpp:49-56) for -tabbedout; the array is zero-filled before every launch, so pairs
+// that never reach AdjustTopHitsAndMapqs with a second pair keep "no second hit".
+__device__ __forceinline__ void write_second(const Env &E, const Mate &F, const Mate &R, const PairState &ps, urmb_second *out,
+                                             uint32_t u, uint32_t n_units) {
+    if (!out || ps.PairCount == 0 || ps.SecF < 0 || E.lane != 0) return;
+    urmb_second a, b;
+    a.db_pos = F.g->hit_pos[ps.SecF];
+    a.score = F.g->hit_score[ps.SecF];
+    a.flags = (uint8_t)(2u | (F.g->hit_plus[ps.SecF] ? 1u : 0u));
+    a.pad = 0;
+    b.db_pos = R.g->hit_pos[ps.SecR];
+    b.score = R.g->hit_score[ps.SecR];
+    b.flags = (uint8_t)(2u | (R.g->hit_plus[ps.SecR] ? 1u : 0u));
+    b.pad = 0;
+    out[u] = a;
+    out[n_units + u] = b;
+}
+
 __device__ int apply_seed_on(const Env &E, Mate &m, int i, bool Plus) {
     const uint32_t qs = m.sd_qs[i];
     if (((qs >> 15) == 0) == Plus) return apply_seed(E, m, i);
@@ -1953,7 +1980,7 @@ __device__ __noinline__ void extend_all_seeds(const Env &E, Mate &m) {
 // false when the pair needs SearchPE_Pending / pair finding / mate rescue, which the second-pass kernel then runs
 // from scratch on the compacted list of such pairs (the first part is cheap to redo and nothing has to be saved).
 template <bool FAST>
-__device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R) {
+__device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairState *ps_out = nullptr) {
     reset_search(E, F);
     reset_search(E, R);
     const uint32_t W = E.ix.word_len;
@@ -2040,6 +2067,7 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R) {
         find_pairs(E, F, R, ps);
     }
     adjust_pair(F, R, ps);
+    if (ps_out) *ps_out = ps;
     return true;
 }
 
@@ -2302,8 +2330,12 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
             Mate F, R;
             load_mate(E, F, b, A.pr, u, sw, &E.ws->m[0], true);
             load_mate(E, R, b, A.pr, b.n_units + u, sw + msz, &E.ws->m[1], true);
-            const bool done = search_pair<MODE == 1>(E, F, R);
+            PairState ps;
+            ps.PairCount = 0;
+            ps.SecF = ps.SecR = -1;
+            const bool done = search_pair<MODE == 1>(E, F, R, MODE == 2 ? &ps : nullptr);
             if (done) {
+                if (MODE == 2) write_second(E, F, R, ps, o.second, u, b.n_units);
                 write_result(E, F, o, u);
                 write_result(E, R, o, b.n_units + u);
             } else {   // MODE 1 only
@@ -2411,6 +2443,7 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
                 continue;
             }
             adjust_pair(F, R, ps);
+            write_second(E, F, R, ps, A.o.second, u, b.n_units);
         }
         write_result(E, F, A.o, u);
         write_result(E, R, A.o, b.n_units + u);

@@ -219,7 +219,9 @@ def run_reference_cpu(args, ufi_path, prefix, n_units, paired, threads):
             c = ["-map", p + "_1.fq"]
         return [O.REF_BIN] + c + ["-ufi", ufi_path, "-samout", sam, "-threads", str(threads)]
 
-    env = dict(os.environ, OMP_STACKSIZE="64M")
+    # torchrun exports OMP_NUM_THREADS=1 to its workers and the reference caps -threads at omp_get_max_threads()
+    # (myutils.cpp:129-147): give the baseline every host thread explicitly
+    env = dict(os.environ, OMP_STACKSIZE="64M", OMP_NUM_THREADS=str(threads))
 
     def run(c, what):
         # The reference has no error channel but its exit status, and its multi-threaded mapper occasionally dies with

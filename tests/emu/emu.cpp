@@ -125,6 +125,10 @@ static DevParams emu_make_params(const urmb_params &p) {  // same table as urmb_
     return P;
 }
 
+// Optional output of State2's second pair (-tabbedout): set before emu_map, n_reads entries, zero-filled here.
+static urmb_second *g_emu_second = nullptr;
+extern "C" void emu_set_second(urmb_second *p) { g_emu_second = p; }
+
 // seqs/offs: n_reads+1 offsets; for paired input read n_units+i is the mate of read i.
 extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t seq_size, uint64_t slot_count,
                        uint32_t word_len, uint32_t max_ix, const urmb_params *p, const uint8_t *seqs,
@@ -168,7 +172,8 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     uint32_t ct[CT_COUNT];
     memset(ct, 0, sizeof ct);
     std::vector<uint32_t> todo(n_units + 1), rescue(n_units + 1);
-    DevOut o{res, runs, runs_cap, ct, todo.data(), rescue.data()};
+    if (g_emu_second) memset(g_emu_second, 0, sizeof(urmb_second) * nreads);
+    DevOut o{res, runs, runs_cap, ct, todo.data(), rescue.data(), paired ? g_emu_second : nullptr};
     const int nw = 4;
     WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch) * nw);
     memset(ws, 0xEE, sizeof(WarpScratch) * nw);

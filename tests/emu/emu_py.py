@@ -9,7 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 class Params(C.Structure):
-    _fields_ = [("method", C.c_int32), ("pe_method", C.c_int32), ("band_radius", C.c_int32), ("minq", C.c_int32)]
+    _fields_ = [("method", C.c_int32), ("pe_method", C.c_int32), ("band_radius", C.c_int32), ("minq", C.c_int32),
+                ("want_second", C.c_int32)]
+
+
+SECOND_DTYPE = np.dtype([("db_pos", "<u4"), ("score", "<i2"), ("flags", "u1"), ("pad", "u1")])
 
 
 _lib = None
@@ -28,7 +32,7 @@ def lib():
     return _lib
 
 
-def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, band_radius=-1):
+def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, band_radius=-1, second=None):
     """oix: oracle_py.Index (only used as a UFI parser that exposes blob/seq pointers)."""
     L = lib()
     seq = np.zeros(oix.seq_size + 4096, dtype=np.uint8)
@@ -39,7 +43,8 @@ def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, 
     cap = 64 * nreads + 1024
     runs = np.zeros(cap, dtype=np.uint16)
     counters = np.zeros(8, dtype=np.uint32)
-    p = Params(method, pe_method, band_radius, 10)
+    p = Params(method, pe_method, band_radius, 10, 0)
+    L.emu_set_second(second.ctypes.data_as(C.c_void_p) if second is not None else None)
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     offs = np.ascontiguousarray(offs, dtype=np.uint32)
     vp = C.c_void_p

@@ -178,3 +178,50 @@ def test_ufi_info_matches_reference(cli, oracle, golden_dir):
         ref = subprocess.run([oracle.REF_BIN, "-ufi_info", ufi], capture_output=True, text=True).stderr
         for l in mine:
             assert l in ref
+
+
+# ---- -tabbedout (State2::OutputTab2, outputtab2.cpp:85-119): written by the formatter stage next to the SAM file ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,extra", [("pe.tab", []), ("pe_veryfast.tab", ["-veryfast"])])
+def test_cli_tabbedout_matches_golden(cli, golden_dir, tmp_path, name, extra):
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    out, sam = tmp_path / name, tmp_path / "o.sam"
+    r = run([cli, "-map2", os.path.join(golden_dir, "pe_1.fq"), "-reverse", os.path.join(golden_dir, "pe_2.fq"), "-ufi",
+             os.path.join(golden_dir, "ref.ufi"), "-samout", str(sam), "-tabbedout", str(out), "-threads", "3", "-batch", "61"] + extra)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, name), "rb").read()
+    # the SAM file is the one written without -tabbedout
+    c = synth.compare_sam(os.path.join(golden_dir, name.replace(".tab", ".sam")), str(sam))
+    assert c["identical"] == c["total"] == 860
+
+
+@pytest.mark.gpu
+def test_cli_tabbedout_repeat_rich_vs_reference(cli, oracle, tmp_path):
+    """Many second pairs: 2 Mb repeat-rich genome, 6 000 pairs (some mates damaged); the reference binary writes the
+    expected file at test time (-threads 1 keeps its output in input order)."""
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available")
+    g = synth.make_genome(2_000_000, n_contigs=4, seed=78, repeat_frac=0.15, n_runs=[(2, 0.3, 1500)], tandem=20, segdup=6)
+    fa, ufi = str(tmp_path / "ref.fa"), str(tmp_path / "ref.ufi")
+    g.write_fasta(fa)
+    oracle.run_reference(["-make_ufi", fa, "-output", ufi])
+    r1, r2, names = synth.sim_pe(g, 6000, 150, 0.02, 0.002, seed=5)
+    r2 = r2.copy()
+    r2[::40, :75] = r1[::40, :75]
+    for path, arr, sfx in ((tmp_path / "r_1.fq", r1, b"/1"), (tmp_path / "r_2.fq", r2, b"/2")):
+        with open(path, "wb") as f:
+            for i in range(len(names)):
+                s = arr[i].tobytes()
+                f.write(b"@" + names[i] + b".%d" % i + sfx + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    args = ["-map2", str(tmp_path / "r_1.fq"), "-reverse", str(tmp_path / "r_2.fq"), "-ufi", ufi]
+    oracle.run_reference(args + ["-samout", str(tmp_path / "ref.sam"), "-tabbedout", str(tmp_path / "ref.tab"), "-threads", "1"])
+    r = run([cli] + args + ["-samout", str(tmp_path / "o.sam"), "-tabbedout", str(tmp_path / "o.tab"), "-batch", "1000"])
+    assert r.returncode == 0, r.stderr
+    want = open(tmp_path / "ref.tab", "rb").read().split(b"\n")
+    got = open(tmp_path / "o.tab", "rb").read().split(b"\n")
+    assert sum(1 for l in want if l and l.split(b"\t")[3] != b"*") > 100   # the case is exercised
+    diff = [(a, b) for a, b in zip(want, got) if a != b]
+    assert len(want) == len(got) and not diff, diff[:5]

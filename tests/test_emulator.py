@@ -60,3 +60,77 @@ def test_emulated_pe(oracle, golden_oix, golden_dir, pe_method):
                                   band_radius=br)
     assert cnt[1] == 0
     _same(np.concatenate([r1, r2]), uo, re_, ue)
+
+
+def _tab_lines(contigs, labels, L1, L2, r1, r2, s1, s2):
+    """State2::OutputTab2 (outputtab2.cpp:6-119) restated in Python over result records (test helper)."""
+    def chrpos(pos):
+        for lab, length, off in contigs:   # UFIndex::PosToCoord, ufindex.cpp:701-727
+            if off <= pos < off + length:
+                return lab, pos - off
+        return "", 0xFFFFFFFF
+
+    def pos1(h, fwd):
+        lab, c = chrpos(h[1])
+        return "%s:%u(%s)/%s" % (lab, (c + 1) & 0xFFFFFFFF, "+" if h[2] else "-", "1" if fwd else "2")
+
+    def pairpos(h1, h2):
+        if not h1[0] and not h2[0]:
+            return "*"
+        if h1[0] and not h2[0]:
+            return pos1(h1, True)
+        if h2[0] and not h1[0]:
+            return pos1(h2, False)
+        (l1, c1), (l2, c2) = chrpos(h1[1]), chrpos(h2[1])
+        if l1 == l2 and h1[2] != h2[2]:
+            return "%s:%u-%u" % (l1, (c1 + 1) & 0xFFFFFFFF, (c2 + 1) & 0xFFFFFFFF)
+        return pos1(h1, True) + "," + pos1(h2, False)
+
+    def tl(h1, h2, a, b):
+        v = (h2[1] + b - h1[1]) if h1[1] <= h2[1] else (h1[1] + a - h2[1])
+        return 0 if v < 0 or v > 1000 else v
+
+    out = []
+    for i, lab in enumerate(labels):
+        t1 = (bool(r1[i]["flags"] & 2), int(r1[i]["db_pos"]), bool(r1[i]["flags"] & 1), int(r1[i]["score"]))
+        t2 = (bool(r2[i]["flags"] & 2), int(r2[i]["db_pos"]), bool(r2[i]["flags"] & 1), int(r2[i]["score"]))
+        u1 = (bool(s1[i]["flags"] & 2), int(s1[i]["db_pos"]), bool(s1[i]["flags"] & 1), int(s1[i]["score"]))
+        u2 = (bool(s2[i]["flags"] & 2), int(s2[i]["db_pos"]), bool(s2[i]["flags"] & 1), int(s2[i]["score"]))
+        f = [lab, pairpos(t1, t2), "%u,%u" % (r1[i]["mapq"], r2[i]["mapq"]), pairpos(u1, u2) if u1[0] else "*"]
+        if t1[0] and t2[0] and u1[0] and u2[0]:
+            a, b = tl(t1, t2, L1[i], L2[i]), tl(u1, u2, L1[i], L2[i])
+            x, y = t1[3] + t2[3], u1[3] + u2[3]
+            f.append(("TL=%u;" % a if a == b else "TL/%u,%u;" % (a, b)) + ("Score=%d;" % x if x == y else "Score/%d,%d;" % (x, y)))
+        out.append("\t".join(f))
+    return out
+
+
+def test_emulated_second_pair_matches_reference_tabbedout(oracle, golden_oix, golden_dir, built_lib):
+    """The second pair the kernels export (urmb_second, -tabbedout) against the reference's own tabbed output
+    (tests/golden/pe.tab, written by the reference binary): all pairs with a second pair plus some without."""
+    import emu_py
+    from urmap_b200 import engine
+    want = open(os.path.join(golden_dir, "pe.tab")).read().split("\n")[:-1]
+    with_second = [i for i, l in enumerate(want) if l.split("\t")[3] != "*"]
+    assert len(with_second) >= 9
+    sel = sorted(set(with_second) | set(range(0, 12)) | set(range(392, 400)))
+    b1 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_1.fq"))
+    b2 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_2.fq"))
+
+    def take(b):
+        s = np.concatenate([b.seqs[b.offs[i]:b.offs[i + 1]] for i in sel])
+        o = np.concatenate([[0], np.cumsum([b.offs[i + 1] - b.offs[i] for i in sel])]).astype(np.uint32)
+        return s, o
+
+    s1, o1 = take(b1)
+    s2, o2 = take(b2)
+    seqs = np.concatenate([s1, s2])
+    offs = np.concatenate([o1, o2[1:] + o1[-1]]).astype(np.uint32)
+    n = len(sel)
+    second = np.zeros(2 * n, dtype=emu_py.SECOND_DTYPE)
+    res, _, cnt = emu_py.emu_map(golden_oix, oracle.RESULT_DTYPE, seqs, offs, n, True, second=second)
+    assert cnt[1] == 0
+    hix = engine.HostIndex(os.path.join(golden_dir, "ref.ufi"))
+    labels = [want[i].split("\t")[0] for i in sel]
+    got = _tab_lines(hix.contigs, labels, np.diff(o1), np.diff(o2), res[:n], res[n:], second[:n], second[n:])
+    assert got == [want[i] for i in sel]

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=10_000_000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--tabbedout", action="store_true", help="also write and compare -tabbedout files")
     ap.add_argument("--write-threads", default="", help="comma list of URMB_WRITE_THREADS values to try (SAM file in /dev/shm)")
     ap.add_argument("--batches", default="", help="comma list of -batch values to try with the SAM text sent to /dev/null")
     ap.add_argument("--workdir", default="/dev/shm/urmb_cli_scale")
@@ -87,9 +88,9 @@ def main():
     out = {"pairs": a.pairs, "reads": 2 * a.pairs, "host_threads": threads, "gpus": a.gpus,
            "workload": "3.1 Gb synthetic reference (24 contigs, 10% repeats), 2x150 bp, 1% subs + 0.1% indels"}
 
-    def cli(sam, batch=None, **env):
+    def cli(sam, batch=None, tab=None, **env):
         c = [exe, "-map2", prefix + "_1.fq", "-reverse", prefix + "_2.fq", "-ufi", ufi, "-samout", sam, "-threads",
-             str(threads), "-gpus", str(a.gpus)] + (["-batch", str(batch)] if batch else [])
+             str(threads), "-gpus", str(a.gpus)] + (["-batch", str(batch)] if batch else []) + (["-tabbedout", tab] if tab else [])
         t0 = time.time()
         p = subprocess.run(c, capture_output=True, env=dict(os.environ, URMB_PROFILE="1", **env))
         wall = time.time() - t0
@@ -103,6 +104,8 @@ def main():
                 "host_profile": prof, "summary": [ln.strip() for ln in err.splitlines() if "Mapped Q" in ln or "Unmapped" in ln]}
 
     out["urmap_b200"] = cli(os.path.join(a.workdir, "urmb.sam"))
+    if a.tabbedout:
+        out["urmap_b200_with_tabbedout"] = cli(os.path.join(a.workdir, "urmb.sam"), tab=os.path.join(a.workdir, "urmb.tab"))
     out["urmap_b200_to_dev_null"] = cli("/dev/null")
     for wt in [int(x) for x in a.write_threads.split(",") if x]:
         out[f"to_file_write_threads_{wt}"] = cli(os.path.join(a.workdir, "urmb2.sam"), URMB_WRITE_THREADS=str(wt))
@@ -111,10 +114,11 @@ def main():
         out[f"to_file_batch_{bsz}"] = cli(os.path.join(a.workdir, "urmb2.sam"), batch=bsz)
     if not a.no_reference and os.path.exists(O.REF_BIN):
         c = [O.REF_BIN, "-map2", prefix + "_1.fq", "-reverse", prefix + "_2.fq", "-ufi", ufi, "-samout",
-             os.path.join(a.workdir, "ref.sam"), "-threads", str(threads)]
+             os.path.join(a.workdir, "ref.sam"), "-threads", str(threads)] + (
+                 ["-tabbedout", os.path.join(a.workdir, "ref.tab")] if a.tabbedout else [])
         for attempt in range(3):
             t0 = time.time()
-            p = subprocess.run(c, capture_output=True, env=dict(os.environ, OMP_STACKSIZE="64M"))
+            p = subprocess.run(c, capture_output=True, env=dict(os.environ, OMP_STACKSIZE="64M", OMP_NUM_THREADS=str(threads)))
             wall = time.time() - t0
             if p.returncode == 0:
                 break
@@ -131,6 +135,10 @@ def main():
             d = subprocess.run([samdiff, os.path.join(a.workdir, "ref.sam"), os.path.join(a.workdir, "urmb.sam")],
                                capture_output=True, text=True)
             out["sam_identity_vs_reference"] = json.loads(d.stdout) if d.returncode == 0 else {"error": d.stderr[-300:]}
+            if a.tabbedout:
+                d = subprocess.run([samdiff, os.path.join(a.workdir, "ref.tab"), os.path.join(a.workdir, "urmb.tab")],
+                                   capture_output=True, text=True)
+                out["tabbedout_identity_vs_reference"] = json.loads(d.stdout) if d.returncode == 0 else {"error": d.stderr[-300:]}
     print(json.dumps(out))
     shutil.rmtree(a.workdir, ignore_errors=True)
 

@@ -138,6 +138,8 @@ struct Slot {
     uint8_t *h_seqs = nullptr; size_t h_seqs_cap = 0;
     uint32_t *h_offs = nullptr; size_t h_offs_cap = 0;
     urmb_result *h_res = nullptr; size_t h_res_cap = 0;
+    urmb_second *d_second = nullptr; size_t d_second_cap = 0;   // only with params.want_second
+    urmb_second *h_second = nullptr; size_t h_second_cap = 0;
     uint16_t *h_runs = nullptr; size_t h_runs_cap = 0;
     uint32_t *h_counters = nullptr;
     // device
@@ -226,7 +228,7 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     if (device < 0 || device >= ndev) { set_global_error("bad device ordinal"); return URMB_E_ARG; }
     urmb_ctx *c = new urmb_ctx;
     c->device = device;
-    urmb_params dflt{6, 4, -1, 10};
+    urmb_params dflt{6, 4, -1, 10, 0};
     c->params = p ? *p : dflt;
     if (c->params.method != 7) c->params.method = 6;
     c->P = make_params(c->params);
@@ -266,6 +268,7 @@ static void free_slot(Slot &s) {
     for (cudaEvent_t ev : s.kev) cudaEventDestroy(ev);
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext); cudaFree(s.d_view);
+    cudaFree(s.d_second); cudaFreeHost(s.h_second);
     cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo); cudaFree(s.d_rescue);
 }
 
@@ -600,6 +603,10 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
         }
     }
     if ((rc = grow_host(c, s.h_res, s.h_res_cap, (size_t)nreads + 1))) return rc;
+    if (c->params.want_second && r2) {
+        if ((rc = grow_dev(c, s.d_second, s.d_second_cap, (size_t)nreads + 1))) return rc;
+        if ((rc = grow_host(c, s.h_second, s.h_second_cap, (size_t)nreads + 1))) return rc;
+    }
     const size_t runs_need = (size_t)nreads * 8 + 4096;
     if ((rc = grow_dev(c, s.d_runs, s.d_runs_cap, runs_need))) return rc;
     if ((rc = grow_host(c, s.h_runs, s.h_runs_cap, s.d_runs_cap))) return rc;
@@ -656,7 +663,9 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     bool rescued = false;
     if (s.batch.n_reads) {
         DevProbe pr{s.d_tally, s.d_pos, s.d_ext, s.d_view, view_stride_for(s.batch.seqcap)};
-        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue};
+        urmb_second *second = (c->params.want_second && s.batch.paired) ? s.d_second : nullptr;
+        if (second) CK(cudaMemsetAsync(second, 0, (size_t)s.batch.n_reads * sizeof(urmb_second), c->compute));
+        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue, second};
         SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
         TraceCtx tc{&s, c->compute, cudaSuccess};
@@ -720,6 +729,8 @@ extern "C" int urmb_download(urmb_ctx *c, int si) {
     CK(cudaStreamWaitEvent(s.copy, s.ev_rescue, 0));
     CK(cudaMemcpyAsync(s.h_counters, s.d_counters, CT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.copy));
     CK(cudaMemcpyAsync(s.h_res, s.d_res, (size_t)s.batch.n_reads * sizeof(urmb_result), cudaMemcpyDeviceToHost, s.copy));
+    if (c->params.want_second && s.batch.paired && s.batch.n_reads)
+        CK(cudaMemcpyAsync(s.h_second, s.d_second, (size_t)s.batch.n_reads * sizeof(urmb_second), cudaMemcpyDeviceToHost, s.copy));
     // Paths are few and short: copy the whole pool prefix a typical batch uses, the rest on demand in wait.
     s.downloaded = true;
     return URMB_OK;
@@ -787,6 +798,16 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
                  s.h_counters[1], kHitCap, kHspCap, kRunCap);
         return fail(c, URMB_E_OVERFLOW, msg);
     }
+    return URMB_OK;
+}
+
+extern "C" int urmb_second_hits(urmb_ctx *c, int si, const urmb_second **s1, const urmb_second **s2) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    Slot &s = c->slots[si];
+    if (!c->params.want_second) return fail(c, URMB_E_ARG, "context created without want_second");
+    if (!s.launched || !s.downloaded || !s.batch.paired) return fail(c, URMB_E_ARG, "no finished paired-end batch in this slot");
+    if (s1) *s1 = s.h_second;
+    if (s2) *s2 = s.h_second + s.batch.n_units;
     return URMB_OK;
 }
 

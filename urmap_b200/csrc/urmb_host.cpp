@@ -4,7 +4,8 @@
 //
 //   urmap_b200 -make_ufi ref.fa -output ref.ufi [-wordlength 24] [-maxix 32] [-slots N] [-load_factor 0.6] [-veryfast] [-gpu_build]
 //   urmap_b200 -map reads.fq[.gz] -ufi ref.ufi -samout out.sam [-threads N] [-veryfast] [-gpus G] [-batch N]
-//   urmap_b200 -map2 R1.fq -reverse R2.fq -ufi ref.ufi -samout out.sam [-threads N] [-veryfast] [-minq 10]
+//   urmap_b200 -map2 R1.fq -reverse R2.fq -ufi ref.ufi -samout out.sam [-tabbedout out.tab] [-threads N] [-veryfast] [-minq 10]
+//   urmap_b200 -ufi_info ref.ufi
 //
 // Reference behaviour restated here (file:line under /root/reference/src):
 //   option spellings / errors   cmdline.cpp:148-269, myopts.h, getcmd.cpp:6-26, myutils.cpp:915-960
@@ -91,7 +92,7 @@ static double now_s() {
 // options
 // ------------------------------------------------------------------------------------------------
 struct Opts {
-    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots, ufi_info, fastq_dump, sam_bench;
+    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots, ufi_info, fastq_dump, sam_bench, tabbedout;
     unsigned threads = 0, wordlength = 24, maxix = 32, minq = 10, gpus = 1, batch = 262144;
     double load_factor = 0.6;
     bool veryfast = false, quiet = false, gpu_build = false, version = false;
@@ -122,6 +123,7 @@ static Opts ParseCmdLine(int argc, char **argv) {
         else if (name == "sam_bench") o.sam_bench = val();
         else if (name == "ufi") o.ufi = val();
         else if (name == "samout") o.samout = val();
+        else if (name == "tabbedout") o.tabbedout = val();
         else if (name == "output") o.output = val();
         else if (name == "log") o.log = val();
         else if (name == "slots") o.slots = val();
@@ -911,6 +913,89 @@ static void FormatPE(const Contigs &C, const HostBatch &b1, const HostBatch &b2,
     }
 }
 
+// State2::OutputTab2 (outputtab2.cpp:6-119): pair label, top pair, MAPQs, second pair, TL/score info.  A "hit" here is
+// (has, DBStartPos, Plus, Score); positions go through UFIndex::PosToCoord (ufindex.cpp:701-727): a position in the
+// padding between contigs leaves the label empty and prints coordinate 0 (UINT32_MAX + 1).
+struct TabHit { bool has; uint32_t pos; bool plus; int score; };
+
+static void TabChrPos(const Contigs &C, const TabHit &h, const char *&lab, size_t &lablen, uint32_t &coord) {
+    int idx;
+    uint32_t L;
+    coord = C.PosToCoordL(h.pos, idx, L);
+    if (idx >= 0) { lab = C.labels[idx].data(); lablen = C.labels[idx].size(); }
+    else { lab = ""; lablen = 0; }
+}
+
+static void TabPairPos1(const Contigs &C, OutBuf &o, const TabHit &h, bool Fwd) {  // GetPairPosStr1
+    const char *lab; size_t n; uint32_t coord;
+    TabChrPos(C, h, lab, n, coord);
+    o.append(lab, n);
+    o.push_back(':');
+    put_u(o, coord + 1);
+    o.push_back('(');
+    o.push_back(h.plus ? '+' : '-');
+    o += ")/";
+    o.push_back(Fwd ? '1' : '2');
+}
+
+static void TabPairPos(const Contigs &C, OutBuf &o, const TabHit &h1, const TabHit &h2) {  // GetPairPosStr
+    if (!h1.has && !h2.has) { o.push_back('*'); return; }
+    if (h1.has && !h2.has) { TabPairPos1(C, o, h1, true); return; }
+    if (!h1.has && h2.has) { TabPairPos1(C, o, h2, false); return; }
+    const char *l1, *l2; size_t n1, n2; uint32_t c1, c2;
+    TabChrPos(C, h1, l1, n1, c1);
+    TabChrPos(C, h2, l2, n2, c2);
+    if (n1 == n2 && memcmp(l1, l2, n1) == 0 && h1.plus != h2.plus) {
+        o.append(l1, n1);
+        o.push_back(':');
+        put_u(o, c1 + 1);
+        o.push_back('-');
+        put_u(o, c2 + 1);
+        return;
+    }
+    TabPairPos1(C, o, h1, true);
+    o.push_back(',');
+    TabPairPos1(C, o, h2, false);
+}
+
+static unsigned TabTemplateLength(const TabHit &h1, const TabHit &h2, unsigned L1, unsigned L2) {  // output2.cpp:49-69
+    int iTL = h1.pos <= h2.pos ? int(h2.pos + L2) - int(h1.pos) : int(h1.pos + L1) - int(h2.pos);
+    if (iTL < 0 || iTL > 1000) iTL = 0;
+    return (unsigned)iTL;
+}
+
+static void FormatTab2(const Contigs &C, const HostBatch &b1, const HostBatch &b2, const urmb_result *r1, const urmb_result *r2,
+                       const urmb_second *s1, const urmb_second *s2, uint32_t lo, uint32_t hi, OutBuf &o) {
+    for (uint32_t i = lo; i < hi; ++i) {
+        const TabHit t1{(r1[i].flags & 2) != 0, r1[i].db_pos, (r1[i].flags & 1) != 0, r1[i].score};
+        const TabHit t2{(r2[i].flags & 2) != 0, r2[i].db_pos, (r2[i].flags & 1) != 0, r2[i].score};
+        const TabHit u1{(s1[i].flags & 2) != 0, s1[i].db_pos, (s1[i].flags & 1) != 0, s1[i].score};
+        const TabHit u2{(s2[i].flags & 2) != 0, s2[i].db_pos, (s2[i].flags & 1) != 0, s2[i].score};
+        AppendQName(o, b1.Label(i), b1.lablen[i]);   // State1::GetPairLabel, state1.cpp:762-778
+        o.push_back('\t');
+        TabPairPos(C, o, t1, t2);
+        o.push_back('\t');
+        put_u(o, r1[i].mapq);
+        o.push_back(',');
+        put_u(o, r2[i].mapq);
+        o.push_back('\t');
+        if (u1.has) TabPairPos(C, o, u1, u2); else o.push_back('*');
+        if (t1.has && t2.has && u1.has && u2.has) {   // State2::GetInfoStr
+            o.push_back('\t');
+            const unsigned L1 = b1.Len(i), L2 = b2.Len(i);
+            const unsigned TopTL = TabTemplateLength(t1, t2, L1, L2), SecondTL = TabTemplateLength(u1, u2, L1, L2);
+            if (TopTL == SecondTL) { o += "TL="; put_u(o, TopTL); }
+            else { o += "TL/"; put_u(o, TopTL); o.push_back(','); put_u(o, SecondTL); }
+            o.push_back(';');
+            const int TopScore = t1.score + t2.score, SecondScore = u1.score + u2.score;
+            if (TopScore == SecondScore) { o += "Score="; put_i(o, TopScore); }
+            else { o += "Score/"; put_i(o, TopScore); o.push_back(','); put_i(o, SecondScore); }
+            o.push_back(';');
+        }
+        o.push_back('\n');
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // -map / -map2
 // ------------------------------------------------------------------------------------------------
@@ -978,9 +1063,10 @@ struct FormatJob {
     std::unique_ptr<HostBatch> b1, b2;
     std::vector<urmb_result> res;   // mate 1 results, then mate 2
     std::vector<uint16_t> runs;
+    std::vector<urmb_second> second;   // -tabbedout: second pair of mate 1, then mate 2
 };
-struct TextSet {   // SAM text of one batch, one piece per formatter thread, in record order
-    std::vector<OutBuf> parts;
+struct TextSet {   // SAM text of one batch, one piece per formatter thread, in record order (+ the -tabbedout text)
+    std::vector<OutBuf> parts, tab;
 };
 
 // SAM output.  A regular file is extended and filled through a shared mapping by several threads (write(2) serialises
@@ -1066,11 +1152,13 @@ static int CmdMap(const Opts &o, bool paired) {
         C.offsets.push_back(c.offset);
     }
     if (o.veryfast && d.max_ix > 3) fprintf(stderr, "\nWARNING: index not optimal for -veryfast\n\n");  // map.cpp:49
-    urmb_params p;
+    urmb_params p{};
     p.method = (!paired && o.veryfast) ? 7 : 6;       // map.cpp:34-37; map2 always uses method 6 (map2.cpp:15)
     p.pe_method = (paired && o.veryfast) ? 5 : 4;     // map2.cpp:46-48
     p.band_radius = -1;
     p.minq = (int)o.minq;
+    const bool want_tab = paired && !o.tabbedout.empty();   // outputtab2.cpp: only State2 writes it
+    p.want_second = want_tab ? 1 : 0;
     const int ngpu = (int)std::max(1u, o.gpus);
     std::vector<urmb_ctx *> ctxs(ngpu, nullptr);
     for (int g = 0; g < ngpu; ++g)
@@ -1096,6 +1184,8 @@ static int CmdMap(const Opts &o, bool paired) {
 
     int nthreads = o.set_threads ? (int)o.threads : std::min((int)std::thread::hardware_concurrency(), 32);
     if (nthreads < 1) nthreads = 1;
+    SamSink tabsink(paired ? o.tabbedout : std::string(), nthreads);
+    if (!paired && !o.tabbedout.empty()) { FILE *f = fopen(o.tabbedout.c_str(), "w"); if (f) fclose(f); }   // created, stays empty
     SamSink sink(o.samout, nthreads);
     if (sink.active()) {
         std::string h;
@@ -1151,7 +1241,7 @@ static int CmdMap(const Opts &o, bool paired) {
                 std::lock_guard<std::mutex> lk(mu);
                 if (!spare_text.empty()) { ts = std::move(spare_text.back()); spare_text.pop_back(); }
             }
-            if (!ts) { ts.reset(new TextSet); ts->parts.resize(nthreads); }
+            if (!ts) { ts.reset(new TextSet); ts->parts.resize(nthreads); ts->tab.resize(want_tab ? nthreads : 0); }
             const double t0 = now_s();
             const uint32_t n = job->b1->n;
             const urmb_result *r1 = job->res.data(), *r2 = r1 + n;
@@ -1164,6 +1254,10 @@ static int CmdMap(const Opts &o, bool paired) {
                 out.reserve(SamTextEstimate(*job->b1, lo, hi) + (paired ? SamTextEstimate(*job->b2, lo, hi) : 0));
                 if (paired) FormatPE(C, *job->b1, *job->b2, r1, r2, runs, lo, hi, o.minq, out, hcs[t]);
                 else FormatSE(C, *job->b1, r1, runs, lo, hi, o.minq, out, hcs[t]);
+                if (want_tab) {
+                    ts->tab[t].clear();
+                    FormatTab2(C, *job->b1, *job->b2, r1, r2, job->second.data(), job->second.data() + n, lo, hi, ts->tab[t]);
+                }
             });
             for (int t = 0; t < nthreads; ++t) {
                 total.query += hcs[t].query; total.accept += hcs[t].accept; total.reject += hcs[t].reject; total.nohit += hcs[t].nohit;
@@ -1184,6 +1278,7 @@ static int CmdMap(const Opts &o, bool paired) {
         while (to_write.Pop(ts)) {
             const double t0 = now_s();
             sink.Append(ts->parts);
+            if (want_tab) tabsink.Append(ts->tab);
             t_write += now_s() - t0;
             std::lock_guard<std::mutex> lk(mu);
             spare_text.push_back(std::move(ts));
@@ -1211,6 +1306,13 @@ static int CmdMap(const Opts &o, bool paired) {
         if (paired) memcpy(job->res.data() + n, r2, (size_t)n * sizeof(urmb_result));
         job->runs.resize(used);
         if (used) memcpy(job->runs.data(), runs, (size_t)used * sizeof(uint16_t));
+        if (want_tab) {
+            const urmb_second *s1, *s2;
+            if (urmb_second_hits(ctxs[f.gpu], f.slot, &s1, &s2) != 0) Die("GPU %d: %s", f.gpu, urmb_last_error(ctxs[f.gpu]));
+            job->second.resize((size_t)n * 2);
+            memcpy(job->second.data(), s1, (size_t)n * sizeof(urmb_second));
+            memcpy(job->second.data() + n, s2, (size_t)n * sizeof(urmb_second));
+        }
         job->b1 = std::move(f.b1);
         job->b2 = std::move(f.b2);
         t_copy += now_s() - t1;
@@ -1244,6 +1346,7 @@ static int CmdMap(const Opts &o, bool paired) {
     formatter.join();
     writer.join();
     sink.Close();
+    tabsink.Close();
     const double t_end = now_s();
     const double secs = t_end - t_loaded;
     const bool profile = getenv("URMB_PROFILE") != nullptr;

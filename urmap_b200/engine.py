@@ -38,7 +38,11 @@ class UrmbError(RuntimeError):
 
 
 class Params(C.Structure):
-    _fields_ = [("method", C.c_int32), ("pe_method", C.c_int32), ("band_radius", C.c_int32), ("minq", C.c_int32)]
+    _fields_ = [("method", C.c_int32), ("pe_method", C.c_int32), ("band_radius", C.c_int32), ("minq", C.c_int32),
+                ("want_second", C.c_int32)]
+
+
+SECOND_DTYPE = np.dtype([("db_pos", "<u4"), ("score", "<i2"), ("flags", "u1"), ("pad", "u1")])
 
 
 class Batch(C.Structure):
@@ -68,7 +72,7 @@ EXPORTS = [
     "urmb_index_device_desc", "urmb_map_se", "urmb_map_pe", "urmb_submit", "urmb_wait", "urmb_upload",
     "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
     "urmb_build_index_device", "urmb_build_last_error", "urmb_peak_gather", "urmb_peak_alu",
-    "urmb_host_alloc", "urmb_host_free", "urmb_reserve",
+    "urmb_host_alloc", "urmb_host_free", "urmb_reserve", "urmb_second_hits",
 ]
 
 _lib = None
@@ -110,6 +114,7 @@ def lib():
         L.urmb_peak_gather.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_float)]
         L.urmb_peak_alu.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_double)]
         L.urmb_reserve.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
+        L.urmb_second_hits.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
         L.urmb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
         L.urmb_host_free.argtypes = [vp]
         L.urmb_host_free.restype = None
@@ -190,9 +195,10 @@ def _as_batch(seqs: np.ndarray, offs: np.ndarray) -> Batch:
 class Context:
     """One GPU's mapping context (replaces the per-thread State1 / State2 of map.cpp:13, map2.cpp:14)."""
 
-    def __init__(self, device: int = 0, method: int = 6, pe_method: int = 4, band_radius: int = -1, minq: int = 10):
+    def __init__(self, device: int = 0, method: int = 6, pe_method: int = 4, band_radius: int = -1, minq: int = 10,
+                 want_second: bool = False):
         self.c = C.c_void_p()
-        p = Params(method, pe_method, band_radius, minq)
+        p = Params(method, pe_method, band_radius, minq, 1 if want_second else 0)
         _check(lib().urmb_ctx_create(device, C.byref(p), C.byref(self.c)))
         self.device = device
         self._keep = []
@@ -264,6 +270,13 @@ class Context:
         r1 = view(p1.value, n, RESULT_DTYPE)
         r2 = view(p2.value, n, RESULT_DTYPE) if paired else None
         return r1, r2, view(pr.value, used.value, np.uint16)
+
+    def second_hits(self, slot, n):
+        """State2's second pair per mate (contexts created with want_second; after wait() on a paired-end slot)."""
+        p1, p2 = C.c_void_p(), C.c_void_p()
+        _check(lib().urmb_second_hits(self.c, slot, C.byref(p1), C.byref(p2)), self.c)
+        mk = lambda p: np.frombuffer((C.c_uint8 * (n * SECOND_DTYPE.itemsize)).from_address(p.value), dtype=SECOND_DTYPE, count=n)
+        return mk(p1), mk(p2)
 
     def timing(self, slot):
         t = Timing()

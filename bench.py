@@ -116,7 +116,7 @@ def build_workload(args, rank, world, device):
         st = index_build.build_index_device(seq.data_ptr(), sds, slot_count, blob.data_ptr())
         log(f"UFI built on the GPU: {st}")
         if st["truncated"]:
-            raise RuntimeError("index builder truncated lists")
+            raise RuntimeError("index needs long links / truncated lists: use the sequential builder")
         meta = {"word_length": 24, "max_ix": 32, "seq_data_size": sds, "slot_count": slot_count, "names": names,
                 "lens": lens, "offsets": offsets, "seq_alloc": seq.numel(), "blob_alloc": blob.numel(),
                 "build_seconds": st["seconds"], "indexed": st["indexed"]}
@@ -474,7 +474,7 @@ def main():
                 "cpu_baseline": {"value": r["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": kind,
                                  "sample": sample},
                 "e2e": {"value": r["reads_per_s"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "index_built_by": "urmb_build_index_device on the GPU (functionally equivalent UFI; setup, not timed)",
+                "index_built_by": "urmb_build_index_device on the GPU (byte-identical UFI; setup, not timed)",
                 "load_seconds": r["load_seconds"]}
         print(json.dumps(line), file=_OUT, flush=True)
         return 0

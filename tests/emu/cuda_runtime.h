@@ -77,6 +77,7 @@ inline void emu_syncwarp(int line) { emu::collective(emu::K_SYNC, 0, 0, line); }
 
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+inline unsigned atomicSub(unsigned *p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
 inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
 inline void __syncthreads() {}
 #define __shared__ static

@@ -206,9 +206,10 @@ extern "C" int emu_build_index(const uint8_t *seq, uint64_t seq_size, uint64_t s
     a.blob = blob;
     const uint64_t cwords = (slot_count + 3) / 4 + 1;
     std::vector<uint32_t> cntP(cwords, 0), cntM(cwords, 0), fill(cwords, 0), base(slot_count, 0),
-        claimed(slot_count / 32 + 2, 0), errors(2, 0);
+        errors(2, 0);
+    std::vector<uint8_t> qzero(slot_count / 8 + 16, 0);
     a.cntP = cntP.data(); a.cntM = cntM.data(); a.fill = fill.data(); a.base = base.data();
-    a.claimed = claimed.data(); a.errors = errors.data();
+    a.qzero = qzero.data(); a.errors = errors.data();
     const int T = 256;
     const uint64_t gpos = (seq_size + T - 1) / T, gslot = (slot_count + T - 1) / T;
     emu::launch([&]() { build_init_kernel(a); }, (int)(((slot_count + 3) / 4 + T - 1) / T), T, 0);
@@ -222,7 +223,18 @@ extern "C" int emu_build_index(const uint8_t *seq, uint64_t seq_size, uint64_t s
     std::vector<uint32_t> pool(run + 1, 0);
     a.pool = pool.data();
     emu::launch([&]() { build_scatter_kernel(a); }, (int)gpos, T, 0);
-    emu::launch([&]() { build_link_kernel(a); }, (int)gslot, T, 0);
+    emu::launch([&]() { build_heads_kernel(a); }, (int)gslot, T, 0);
+    {   // the carry scan (build_carry_*_kernel use __syncthreads) restated sequentially: two rounds over the ring
+        int64_t q = 0;
+        for (int round = 0; round < 2; ++round)
+            for (uint64_t s = 0; s < slot_count; ++s) {
+                const MaxPlus m = mp_slot(a, s);
+                const int64_t t = q + m.B;
+                q = m.A > t ? m.A : t;
+                if (round == 1 && q == 0) qzero[s >> 3] |= (uint8_t)(1u << (s & 7));
+            }
+    }
+    emu::launch([&]() { build_segment_kernel(a); }, (int)gslot, T, 0);
     if (stats) { stats[0] = run; stats[1] = errors[0]; stats[2] = errors[1]; }
     return 0;
 }

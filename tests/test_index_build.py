@@ -1,5 +1,6 @@
-"""The device index builder (urmb_build.cu) must produce a UFI that is functionally identical to the reference's:
-same head class and same GetRow_Blob list for every slot (placement of overflow elements may differ)."""
+"""The device index builder (urmb_build.cu) must produce the reference's UFI blob byte for byte (segments cut by a max-plus
+carry scan, the reference's insertions replayed in genome order inside each segment); where a table needs long links or
+truncated lists (load factors well above 0.6) it must say so instead of writing a different table."""
 import os
 import struct
 import sys
@@ -32,10 +33,34 @@ def test_emulated_builder_matches_reference(oracle, golden_oix, golden_dir, tmp_
     assert stats[1] == 0 and stats[2] == 0
     out = str(tmp_path / "emu.ufi")
     _swap_blob(os.path.join(golden_dir, "ref.ufi"), blob, golden_oix.slot_count, out)
+    assert np.array_equal(blob, np.asarray(golden_oix.blob()[:5 * golden_oix.slot_count]))   # byte-identical
     mine = oracle.Index(out)
     assert oracle.index_functional_diff(golden_oix, mine)[0] == 0
     if os.path.exists(oracle.REF_BIN):  # the reference's own validator accepts it (ufistats.cpp:141)
         oracle.run_reference(["-ufi_validate", out])
+
+
+@pytest.mark.parametrize("extra,exact", [([], True), (["-veryfast"], True), (["-maxix", "5", "-wordlength", "20"], True),
+                                         (["-load_factor", "0.9"], False)])
+def test_emulated_builder_options(oracle, tmp_path, extra, exact):
+    """Repeat-rich 400 kb genome under the reference's index options: byte-identical at the usual load factors; at load
+    factor 0.9 the reference needs long links and the builder reports the segments it cannot reproduce."""
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available")
+    import emu_py
+    from urmap_b200 import synth
+    g = synth.make_genome(400_000, n_contigs=3, seed=31, repeat_frac=0.15, n_runs=[(1, 0.3, 900)], tandem=15, segdup=4)
+    fa, ufi = str(tmp_path / "r.fa"), str(tmp_path / "r.ufi")
+    g.write_fasta(fa)
+    oracle.run_reference(["-make_ufi", fa, "-output", ufi] + extra)
+    ref = oracle.Index(ufi)
+    blob, stats = emu_py.emu_build_index(ref.seq(), ref.slot_count, ref.word_length, ref.max_ix)
+    want = np.asarray(ref.blob()[:5 * ref.slot_count])
+    if exact:
+        assert stats[1] == 0 and np.array_equal(blob, want)
+    else:
+        tl = want[0::5]
+        assert int(((tl == 125) | (tl == 253)).sum()) > 0 and stats[1] > 0
 
 
 @pytest.mark.gpu
@@ -57,7 +82,10 @@ def test_gpu_builder_matches_reference(oracle, built_lib, tmp_path):
     st = index_build.build_index_device(seq.data_ptr(), ref.seq_size, ref.slot_count, blob.data_ptr())
     assert st["truncated"] == 0
     out = str(tmp_path / "gpu.ufi")
-    _swap_blob(ufi, blob[:5 * ref.slot_count].cpu().numpy(), ref.slot_count, out)
+    mine_blob = blob[:5 * ref.slot_count].cpu().numpy()
+    assert np.array_equal(mine_blob, np.asarray(ref.blob()[:5 * ref.slot_count]))   # byte-identical to the reference
+    _swap_blob(ufi, mine_blob, ref.slot_count, out)
+    assert open(out, "rb").read() == open(ufi, "rb").read()
     mine = oracle.Index(out)
     assert oracle.index_functional_diff(ref, mine)[0] == 0
     oracle.run_reference(["-ufi_validate", out])

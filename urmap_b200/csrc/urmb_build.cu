@@ -17,7 +17,9 @@
 //   count  : saturating 8-bit counts per slot for plus- and minus-strand k-mers (CAS on packed bytes)
 //   scan   : exclusive prefix sum of list lengths over indexed slots -> pool offsets (two-level)
 //   scatter: positions of indexed k-mers -> pool[base[slot] + ticket]
-//   link   : per indexed slot: sort its <=32 positions, write head, claim overflow slots, write links
+//   heads  : per indexed slot: sort its <=32 positions (genome order), write the head record
+//   carry  : q(s) by a two-level max-plus scan -> bitmap of segment borders (q(s) == 0)
+//   segment: one thread per segment replays UpdateSlot (ufindex.cpp:194-322) for its overflow elements in genome order
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -47,8 +49,10 @@ struct BuildArgs {
     uint32_t *base;         // pool offset per slot
     uint64_t *blocksum;     // per scan block
     uint32_t *pool;
-    uint32_t *claimed;      // bitmap
-    uint32_t *errors;       // [0] truncated lists, [1] pool overflow
+    uint8_t *qzero;         // bit s: q(s) == 0, nothing is carried from slot s to slot s+1 (segment border)
+    int64_t *blockA, *blockB;   // per scan block: composite f(q) = max(A, q + B) of its slots
+    int64_t *blockQ;        // q entering each scan block
+    uint32_t *errors;       // [0] segments that need the sequential builder (long link / truncation), [1] pool overflow
 };
 
 __device__ __forceinline__ uint32_t bletter(uint32_t c) {  // genome is already upper case (ufindex.cpp:466)
@@ -216,64 +220,188 @@ __device__ __forceinline__ void put_rec(uint8_t *blob, uint64_t slot, uint8_t ta
     p[1] = (uint8_t)pos; p[2] = (uint8_t)(pos >> 8); p[3] = (uint8_t)(pos >> 16); p[4] = (uint8_t)(pos >> 24);
 }
 
-// first available (never-owned, FindFreeSlot ufindex.cpp:987-1000) and not yet claimed slot after `from`;
-// returns the step (1..65534) or 0 when none
-__device__ uint32_t claim_after(const BuildArgs &a, uint64_t from, uint64_t &slot_out) {
-    uint64_t t = from;
-    for (uint32_t step = 1; step < BT_MAX_LINK; ++step) {
-        ++t;
-        if (t >= a.slot_count) t = 0;
-        uint32_t n = cnt_get(a.cntP, t);
-        if (n > 0 && n <= a.max_ix) continue;
-        const uint32_t bit = 1u << (t & 31);
-        uint32_t *w = a.claimed + (t >> 5);
-        if (*w & bit) continue;
-        if (atomicOr(w, bit) & bit) continue;
-        slot_out = t;
-        return step;
-    }
-    return 0;
+__device__ __forceinline__ uint32_t get_tally(const uint8_t *blob, uint64_t slot) { return blob[5 * slot]; }
+__device__ __forceinline__ uint32_t get_pos(const uint8_t *blob, uint64_t slot) {
+    const uint8_t *p = blob + 5 * slot;
+    return (uint32_t)p[1] | ((uint32_t)p[2] << 8) | ((uint32_t)p[3] << 16) | ((uint32_t)p[4] << 24);
+}
+__device__ __forceinline__ bool in_U(const BuildArgs &a, uint64_t s) {   // FindFreeSlot's "will never be owned"
+    const uint32_t n = cnt_get(a.cntP, s);
+    return !(n > 0 && n <= a.max_ix);
+}
+__device__ __forceinline__ uint32_t arrivals(const BuildArgs &a, uint64_t s) {
+    const uint32_t n = list_len(a, s);
+    return n >= 2 ? n - 1 : 0;
 }
 
-__global__ void build_link_kernel(BuildArgs a) {
+// heads: sort the slot's positions into genome order (UpdateSlot is called in genome order) and write the head record
+// (ufindex.cpp:217-234); the ticket byte is turned into "elements still to insert".
+__global__ void build_heads_kernel(BuildArgs a) {
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.slot_count) return;
     const uint32_t n = list_len(a, s);
     if (n == 0) return;
     uint32_t pos[32];
     const uint64_t b = a.base[s];
-    for (uint32_t i = 0; i < n; ++i) {  // insertion sort: genome order (UpdateSlot is called in genome order)
+    for (uint32_t i = 0; i < n; ++i) {
         uint32_t v = a.pool[b + i];
         int j = (int)i - 1;
         while (j >= 0 && pos[j] > v) { pos[j + 1] = pos[j]; --j; }
         pos[j + 1] = v;
     }
-    if (n == 1) {  // ufindex.cpp:217-234
-        put_rec(a.blob, s, (cnt_get(a.cntM, s) == 0) ? BT_BOTH1 : BT_PLUS1, pos[0]);
-        return;
+    for (uint32_t i = 0; i < n; ++i) a.pool[b + i] = pos[i];
+    put_rec(a.blob, s, (n == 1 && cnt_get(a.cntM, s) == 0) ? BT_BOTH1 : BT_PLUS1, pos[0]);
+    atomicSub(a.fill + (s >> 2), 1u << ((uint32_t)(s & 3) * 8));
+}
+
+// carry, level 1: composite of one scan block.  f_s(q) = max(0, q - u(s)) + a(s) = max(a(s), q + a(s) - u(s)).
+constexpr int64_t kNegInf = -(1ll << 60);
+struct MaxPlus { int64_t A, B; };
+__device__ __forceinline__ MaxPlus mp_then(const MaxPlus &f, const MaxPlus &g) {   // apply f, then g
+    MaxPlus r;
+    const int64_t t = f.A + g.B;
+    r.A = g.A > t ? g.A : t;
+    r.B = f.B + g.B;
+    return r;
+}
+__device__ __forceinline__ MaxPlus mp_slot(const BuildArgs &a, uint64_t s) {
+    const int64_t ar = arrivals(a, s), u = in_U(a, s) ? 1 : 0;
+    return MaxPlus{ar, ar - u};
+}
+#ifndef URMB_EMU
+__global__ void build_carry_block_kernel(BuildArgs a) {
+    __shared__ MaxPlus red[256];
+    const uint64_t s0 = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * 8;
+    MaxPlus f{kNegInf, 0};
+    for (int k = 0; k < 8; ++k)
+        if (s0 + k < a.slot_count) f = mp_then(f, mp_slot(a, s0 + k));
+    red[threadIdx.x] = f;
+    __syncthreads();
+    for (int st = 1; st < 256; st <<= 1) {   // ordered tree: thread i (multiple of 2*st) absorbs its right neighbour
+        if ((threadIdx.x & (2 * st - 1)) == 0) red[threadIdx.x] = mp_then(red[threadIdx.x], red[threadIdx.x + st]);
+        __syncthreads();
     }
-    uint64_t cur = s;          // current end of list
-    uint32_t curpos = pos[0];  // position stored at cur
-    bool cur_is_head = true;
-    for (uint32_t r = 1; r < n; ++r) {
-        uint64_t t;
-        uint32_t step = claim_after(a, cur, t);
-        if (step == 0) { atomicAdd(a.errors, 1u); break; }
-        if (step <= BT_MAX_NEXT) {  // ufindex.cpp:303-313
-            put_rec(a.blob, cur, (uint8_t)((cur_is_head ? BT_MY_BIT : 0) | step), curpos);
-            cur = t;
-        } else {  // long link, ufindex.cpp:256-300
-            uint64_t t2;
-            uint32_t step2 = claim_after(a, t, t2);
-            if (step2 == 0) { atomicAdd(a.errors, 1u); break; }
-            put_rec(a.blob, cur, (uint8_t)((cur_is_head ? BT_MY_BIT : 0) | BT_LONG), step | (step2 << 16));
-            put_rec(a.blob, t, BT_LONG, curpos);
-            cur = t2;
+    if (threadIdx.x == 0) { a.blockA[blockIdx.x] = red[0].A; a.blockB[blockIdx.x] = red[0].B; }
+}
+// carry, level 2 (one CTA): q entering every scan block.  Each thread composes a contiguous range of block composites,
+// thread 0 chains the 1024 range composites -- twice, because the table is a ring: the second round starts from the
+// carry that leaves the last block -- and every thread then walks its range again with its entry value.
+__global__ void __launch_bounds__(1024) build_carry_top_kernel(BuildArgs a, uint64_t nblocks) {
+    __shared__ MaxPlus part[1024];
+    __shared__ int64_t entry[1024];
+    const uint64_t per = (nblocks + 1023) / 1024;
+    const uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per < nblocks ? lo + per : nblocks;
+    MaxPlus f{kNegInf, 0};
+    for (uint64_t b = lo; b < hi; ++b) f = mp_then(f, MaxPlus{a.blockA[b], a.blockB[b]});
+    part[threadIdx.x] = f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t q = 0;
+        for (int round = 0; round < 2; ++round)
+            for (int t = 0; t < 1024; ++t) {
+                entry[t] = q;
+                const int64_t v = q + part[t].B;
+                q = part[t].A > v ? part[t].A : v;
+            }
+    }
+    __syncthreads();
+    int64_t q = entry[threadIdx.x];
+    for (uint64_t b = lo; b < hi; ++b) {
+        a.blockQ[b] = q;
+        const int64_t v = q + a.blockB[b];
+        q = a.blockA[b] > v ? a.blockA[b] : v;
+    }
+}
+// carry, level 3: q at every slot -> border bitmap (one byte per thread: its 8 slots)
+__global__ void build_carry_apply_kernel(BuildArgs a) {
+    __shared__ MaxPlus sc[256];
+    const uint64_t s0 = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * 8;
+    MaxPlus f{kNegInf, 0};
+    for (int k = 0; k < 8; ++k)
+        if (s0 + k < a.slot_count) f = mp_then(f, mp_slot(a, s0 + k));
+    sc[threadIdx.x] = f;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {   // inclusive scan of the composites, left to right
+        MaxPlus t = sc[threadIdx.x];
+        if ((int)threadIdx.x >= off) t = mp_then(sc[threadIdx.x - off], t);
+        __syncthreads();
+        sc[threadIdx.x] = t;
+        __syncthreads();
+    }
+    int64_t q = a.blockQ[blockIdx.x];
+    if (threadIdx.x > 0) {
+        const MaxPlus p = sc[threadIdx.x - 1];
+        const int64_t t = q + p.B;
+        q = p.A > t ? p.A : t;
+    }
+    uint32_t bits = 0;
+    for (int k = 0; k < 8; ++k) {
+        const uint64_t s = s0 + k;
+        if (s >= a.slot_count) break;
+        const MaxPlus m = mp_slot(a, s);
+        const int64_t t = q + m.B;
+        q = m.A > t ? m.A : t;
+        if (q == 0) bits |= 1u << k;
+    }
+    if (s0 < a.slot_count) a.qzero[s0 >> 3] = (uint8_t)bits;
+}
+#endif
+
+__device__ __forceinline__ bool q_is_zero(const BuildArgs &a, uint64_t s) { return (a.qzero[s >> 3] >> (s & 7)) & 1u; }
+__device__ __forceinline__ uint64_t next_slot(const BuildArgs &a, uint64_t s) { return s + 1 == a.slot_count ? 0 : s + 1; }
+
+// segment: thread s owns the segment that starts at s when s has overflow elements and nothing is carried into s.
+// It replays UFIndex::UpdateSlot (ufindex.cpp:194-322) for the overflow elements of every list whose head lies in
+// the segment, in genome order, with FindEndOfList (ufindex.cpp:945-985) and FindFreeSlot (:987-1000) on the blob.
+__global__ void build_segment_kernel(BuildArgs a) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.slot_count) return;
+    if (arrivals(a, s) == 0) return;
+    if (!q_is_zero(a, s == 0 ? a.slot_count - 1 : s - 1)) return;
+    // extent: up to and including the first slot e with q(e) == 0 (a whole ring of carried elements cannot happen:
+    // then no slot would start a segment)
+    uint64_t len = 1;
+    for (uint64_t t = s; !q_is_zero(a, t); t = next_slot(a, t)) ++len;
+    for (;;) {
+        // the list with the smallest next genome position
+        uint64_t best = 0, t = s;
+        uint32_t bestpos = 0xFFFFFFFFu;
+        bool any = false;
+        for (uint64_t i = 0; i < len; ++i, t = next_slot(a, t)) {
+            const uint32_t n = list_len(a, t);
+            if (n < 2) continue;
+            const uint32_t left = (a.fill[t >> 2] >> ((uint32_t)(t & 3) * 8)) & 255u;
+            if (left == 0) continue;
+            const uint32_t p = a.pool[(uint64_t)a.base[t] + (n - left)];
+            if (!any || p < bestpos) { any = true; best = t; bestpos = p; }
         }
-        curpos = pos[r];
-        cur_is_head = false;
+        if (!any) return;
+        atomicSub(a.fill + (best >> 2), 1u << ((uint32_t)(best & 3) * 8));
+        // FindEndOfList
+        uint64_t eol = best;
+        for (;;) {
+            const uint32_t T = get_tally(a.blob, eol);
+            if (T == BT_PLUS1 || T == BT_BOTH1 || T == BT_END) break;
+            if (T == 253 || T == BT_LONG) { atomicAdd(a.errors, 1u); return; }   // long link: not reproduced here
+            eol += T & 127u;
+            if (eol >= a.slot_count) eol -= a.slot_count;
+        }
+        // FindFreeSlot, bounded by the segment (beyond it the one-slot-per-element count would be violated)
+        uint64_t fs = eol;
+        uint32_t step = 0;
+        bool border = q_is_zero(a, eol);   // nothing may be carried out of the segment's last slot
+        for (;;) {
+            if (border) { atomicAdd(a.errors, 1u); return; }
+            fs = next_slot(a, fs);
+            ++step;
+            if (in_U(a, fs) && get_tally(a.blob, fs) == BT_FREE) break;
+            border = q_is_zero(a, fs);
+        }
+        if (step > BT_MAX_NEXT) { atomicAdd(a.errors, 1u); return; }   // would be a long link (two U-slots)
+        // ufindex.cpp:303-313
+        a.blob[5 * eol] = (uint8_t)((get_tally(a.blob, eol) & BT_MY_BIT) | step);
+        put_rec(a.blob, fs, BT_END, bestpos);
     }
-    put_rec(a.blob, cur, (uint8_t)((cur_is_head ? BT_MY_BIT : 0) | BT_END), curpos);
 }
 
 static std::string g_build_err;
@@ -295,7 +423,8 @@ using namespace urmb;
 extern "C" const char *urmb_build_last_error() { return g_build_err.c_str(); }
 
 // d_seq: seq_data_size bytes on the current device; d_blob: 5*slot_count+URMB_BLOB_PAD bytes (written).
-// stats[0] = indexed positions, stats[1] = truncated lists (0 expected), stats[2] = seconds.
+// stats[0] = indexed positions, stats[1] = segments that need the sequential builder (long links / truncated lists: the
+// blob is then NOT valid; 0 at the reference's load factor), stats[2] = microseconds.
 extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t slot_count,
                                        uint32_t word_length, uint32_t max_ix, void *d_blob, uint64_t *stats) {
     if (!d_seq || !d_blob || slot_count < 2 || word_length < 8 || word_length > 32 || max_ix < 1 || max_ix > 32)
@@ -325,12 +454,15 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
     BCK(cudaMalloc(&a.fill, cwords * 4));
     BCK(cudaMalloc(&a.base, slot_count * 4));
     BCK(cudaMalloc(&a.blocksum, (nblocks + 1) * 8));
-    BCK(cudaMalloc(&a.claimed, (slot_count / 32 + 2) * 4));
+    BCK(cudaMalloc(&a.qzero, slot_count / 8 + 16));
+    BCK(cudaMalloc(&a.blockA, (nblocks + 1) * 8));
+    BCK(cudaMalloc(&a.blockB, (nblocks + 1) * 8));
+    BCK(cudaMalloc(&a.blockQ, (nblocks + 1) * 8));
     BCK(cudaMalloc(&a.errors, 8));
     BCK(cudaMemset(a.cntP, 0, cwords * 4));
     BCK(cudaMemset(a.cntM, 0, cwords * 4));
     BCK(cudaMemset(a.fill, 0, cwords * 4));
-    BCK(cudaMemset(a.claimed, 0, (slot_count / 32 + 2) * 4));
+    BCK(cudaMemset(a.qzero, 0, slot_count / 8 + 16));
     BCK(cudaMemset(a.errors, 0, 8));
     BCK(cudaMemset(a.blocksum, 0, (nblocks + 1) * 8));
     BCK(cudaMemset((uint8_t *)d_blob + 5 * slot_count, 0, URMB_BLOB_PAD));
@@ -343,7 +475,11 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
     BCK(cudaMalloc(&a.pool, (total + 1) * 4));
     build_base_kernel<<<(unsigned)nblocks, 256>>>(a);
     build_scatter_kernel<<<(unsigned)gpos, T>>>(a);
-    build_link_kernel<<<(unsigned)gslot, T>>>(a);
+    build_heads_kernel<<<(unsigned)gslot, T>>>(a);
+    build_carry_block_kernel<<<(unsigned)nblocks, 256>>>(a);
+    build_carry_top_kernel<<<1, 1024>>>(a, nblocks);
+    build_carry_apply_kernel<<<(unsigned)nblocks, 256>>>(a);
+    build_segment_kernel<<<(unsigned)gslot, T>>>(a);
     BCK(cudaGetLastError());
     BCK(cudaMemcpy(herr, a.errors, 8, cudaMemcpyDeviceToHost));
     BCK(cudaEventRecord(e1));
@@ -355,13 +491,13 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
         stats[2] = (uint64_t)(ms * 1000.0f);
     }
     cudaFree(a.cntP); cudaFree(a.cntM); cudaFree(a.fill); cudaFree(a.base); cudaFree(a.blocksum);
-    cudaFree(a.claimed); cudaFree(a.errors); cudaFree(a.pool);
+    cudaFree(a.qzero); cudaFree(a.blockA); cudaFree(a.blockB); cudaFree(a.blockQ); cudaFree(a.errors); cudaFree(a.pool);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (herr[1]) { g_build_err = "pool overflow (internal error)"; return URMB_E_OVERFLOW; }
     return URMB_OK;
 fail:
     cudaFree(a.cntP); cudaFree(a.cntM); cudaFree(a.fill); cudaFree(a.base); cudaFree(a.blocksum);
-    cudaFree(a.claimed); cudaFree(a.errors); cudaFree(a.pool);
+    cudaFree(a.qzero); cudaFree(a.blockA); cudaFree(a.blockB); cudaFree(a.blockQ); cudaFree(a.errors); cudaFree(a.pool);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return URMB_E_CUDA;
@@ -378,7 +514,10 @@ extern "C" int urmb_host_gpu_build(const uint8_t *seq, uint64_t n, uint64_t slot
     if (cudaMemset((uint8_t *)d_seq + n, 0, 64) != cudaSuccess) goto out;
     if (cudaMemcpy(d_seq, seq, n, cudaMemcpyHostToDevice) != cudaSuccess) goto out;
     rc = urmb_build_index_device(d_seq, n, slots, W, maxix, d_blob, stats);
-    if (rc == 0 && stats[1] != 0) { g_build_err = "lists truncated"; rc = URMB_E_OVERFLOW; }
+    if (rc == 0 && stats[1] != 0) {
+        g_build_err = std::to_string(stats[1]) + " segment(s) need long links or list truncation";
+        rc = URMB_E_OVERFLOW;
+    }
     if (rc == 0 && cudaMemcpy(blob, d_blob, 5 * slots, cudaMemcpyDeviceToHost) != cudaSuccess) rc = URMB_E_CUDA;
 out:
     cudaFree(d_seq);

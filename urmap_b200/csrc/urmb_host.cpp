@@ -1607,9 +1607,17 @@ static int CmdMakeUfi(const Opts &o) {  // cmd_make_ufi, ufindexio.cpp:117-179
     t0 = now_s();
     if (o.gpu_build) {
         B.Blob.resize(5 * B.SlotCount);
-        if (urmb_host_gpu_build(B.Seq.data(), B.Seq.size(), B.SlotCount, B.W, B.MaxIx, B.Blob.data()) != 0)
+        const int rc = urmb_host_gpu_build(B.Seq.data(), B.Seq.size(), B.SlotCount, B.W, B.MaxIx, B.Blob.data());
+        if (rc == URMB_E_OVERFLOW) {   // long links / truncated lists (load factors well above 0.6): exact on the host only
+            Progress("GPU index build: %s; building on the host instead\n", urmb_build_last_error());
+            std::vector<uint8_t>().swap(B.Blob);
+            B.MakeIndex();
+            Progress("Index built in %.1f s\n%u slots truncated\n", now_s() - t0, B.Truncated);
+        } else if (rc != 0) {
             Die("GPU index build failed: %s", urmb_build_last_error());
-        Progress("Index built on the GPU (functionally equivalent layout) in %.1f s\n", now_s() - t0);
+        } else {
+            Progress("Index built on the GPU (byte-identical to the sequential builder) in %.1f s\n", now_s() - t0);
+        }
     } else {
         B.MakeIndex();
         Progress("Index built in %.1f s\n%u slots truncated\n", now_s() - t0, B.Truncated);

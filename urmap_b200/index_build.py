@@ -55,7 +55,8 @@ def slot_count_for(names, lens, load_factor=0.6):
 
 
 def build_index_device(d_seq_ptr: int, seq_data_size: int, slot_count: int, d_blob_ptr: int, word_length=24, max_ix=32):
-    """Runs the builder kernels on the current CUDA device. Returns dict(indexed, truncated, seconds)."""
+    """Runs the builder kernels on the current CUDA device. Returns dict(indexed, truncated, seconds); the blob is
+    byte-identical to the reference's when `truncated` (segments that need long links / truncated lists) is 0."""
     L = engine.lib()
     L.urmb_build_index_device.restype = C.c_int
     L.urmb_build_index_device.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,

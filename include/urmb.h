@@ -165,12 +165,13 @@ int urmb_mark_elapsed(urmb_ctx *c, float *ms);
 /* ---- index construction on the device (replaces UFIndex::MakeIndex, ufindex.cpp:83-151).
  * The blob is BYTE-IDENTICAL to the reference's: the order-dependent placement of overflow list elements
  * (UpdateSlot / FindFreeSlot, ufindex.cpp:194-322, 987-1000) is reproduced by cutting the table into independent
- * segments with a max-plus carry scan and replaying the reference's insertions inside each segment in genome order
- * (urmb_build.cu).  Long links and truncated lists (probe distance > 124; load factors well above the default 0.6) are
- * not reproduced: stats[1] then counts the segments that need them, the blob is not valid and the caller must use the
- * sequential builder (`urmap_b200 -make_ufi` does that by itself).
+ * segments with a max-plus carry scan and replaying the reference's insertions inside each segment in genome order;
+ * segments in which an element needs a long link (probe distance > 124) are replayed once more, merged with the
+ * segments they spill into (urmb_build.cu).  Only lists that the reference would TRUNCATE (no free slot within 65534)
+ * are not reproduced: stats[1] counts them, the blob is then not valid and the caller must use the sequential builder
+ * (`urmap_b200 -make_ufi -gpu_build` does that by itself).
  * d_seq: seq_data_size bytes of upper-case sequence data on the current device; d_blob: 5*slot_count+URMB_BLOB_PAD
- * bytes (written).  stats[0] = indexed positions, stats[1] = segments needing the sequential builder, stats[2] = us. */
+ * bytes (written).  stats[0] = indexed positions, stats[1] = lists that would be truncated, stats[2] = microseconds. */
 int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t slot_count, uint32_t word_length,
                             uint32_t max_ix, void *d_blob, uint64_t *stats);
 const char *urmb_build_last_error(void);

@@ -206,10 +206,12 @@ extern "C" int emu_build_index(const uint8_t *seq, uint64_t seq_size, uint64_t s
     a.blob = blob;
     const uint64_t cwords = (slot_count + 3) / 4 + 1;
     std::vector<uint32_t> cntP(cwords, 0), cntM(cwords, 0), fill(cwords, 0), base(slot_count, 0),
-        errors(2, 0);
+        errors(4, 0);
+    std::vector<uint64_t> flagged(1u << 16, 0);
     std::vector<uint8_t> qzero(slot_count / 8 + 16, 0);
     a.cntP = cntP.data(); a.cntM = cntM.data(); a.fill = fill.data(); a.base = base.data();
     a.qzero = qzero.data(); a.errors = errors.data();
+    a.flagged = flagged.data(); a.flagged_cap = (uint32_t)flagged.size();
     const int T = 256;
     const uint64_t gpos = (seq_size + T - 1) / T, gslot = (slot_count + T - 1) / T;
     emu::launch([&]() { build_init_kernel(a); }, (int)(((slot_count + 3) / 4 + T - 1) / T), T, 0);
@@ -235,6 +237,8 @@ extern "C" int emu_build_index(const uint8_t *seq, uint64_t seq_size, uint64_t s
             }
     }
     emu::launch([&]() { build_segment_kernel(a); }, (int)gslot, T, 0);
-    if (stats) { stats[0] = run; stats[1] = errors[0]; stats[2] = errors[1]; }
+    emu::launch([&]() { build_repair_kernel(a); }, 1, 32, 0);
+    if (stats) { stats[0] = run; stats[1] = errors[2]; stats[2] = errors[1]; }
+    if (getenv("URMB_BUILD_DEBUG")) fprintf(stderr, "[emu build] %u segment(s) repaired\n", errors[0]);
     return 0;
 }

@@ -20,6 +20,7 @@
 //   heads  : per indexed slot: sort its <=32 positions (genome order), write the head record
 //   carry  : q(s) by a two-level max-plus scan -> bitmap of segment borders (q(s) == 0)
 //   segment: one thread per segment replays UpdateSlot (ufindex.cpp:194-322) for its overflow elements in genome order
+//   repair : segments that need a long link, replayed with the segments they spill into
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -52,7 +53,9 @@ struct BuildArgs {
     uint8_t *qzero;         // bit s: q(s) == 0, nothing is carried from slot s to slot s+1 (segment border)
     int64_t *blockA, *blockB;   // per scan block: composite f(q) = max(A, q + B) of its slots
     int64_t *blockQ;        // q entering each scan block
-    uint32_t *errors;       // [0] segments that need the sequential builder (long link / truncation), [1] pool overflow
+    uint32_t *errors;       // [0] segments handed to the repair pass, [1] pool overflow, [2] truncated lists / repair gave up
+    uint64_t *flagged;      // start slots of the segments handed to the repair pass
+    uint32_t flagged_cap;
 };
 
 __device__ __forceinline__ uint32_t bletter(uint32_t c) {  // genome is already upper case (ufindex.cpp:466)
@@ -350,6 +353,12 @@ __global__ void build_carry_apply_kernel(BuildArgs a) {
 __device__ __forceinline__ bool q_is_zero(const BuildArgs &a, uint64_t s) { return (a.qzero[s >> 3] >> (s & 7)) & 1u; }
 __device__ __forceinline__ uint64_t next_slot(const BuildArgs &a, uint64_t s) { return s + 1 == a.slot_count ? 0 : s + 1; }
 
+__device__ __forceinline__ void flag_segment(const BuildArgs &a, uint64_t s) {
+    const uint32_t i = atomicAdd(a.errors, 1u);
+    if (i < a.flagged_cap) a.flagged[i] = s;
+    else atomicAdd(a.errors + 2, 1u);
+}
+
 // segment: thread s owns the segment that starts at s when s has overflow elements and nothing is carried into s.
 // It replays UFIndex::UpdateSlot (ufindex.cpp:194-322) for the overflow elements of every list whose head lies in
 // the segment, in genome order, with FindEndOfList (ufindex.cpp:945-985) and FindFreeSlot (:987-1000) on the blob.
@@ -382,7 +391,7 @@ __global__ void build_segment_kernel(BuildArgs a) {
         for (;;) {
             const uint32_t T = get_tally(a.blob, eol);
             if (T == BT_PLUS1 || T == BT_BOTH1 || T == BT_END) break;
-            if (T == 253 || T == BT_LONG) { atomicAdd(a.errors, 1u); return; }   // long link: not reproduced here
+            if (T == 253 || T == BT_LONG) { flag_segment(a, s); return; }   // long link: the repair pass handles it
             eol += T & 127u;
             if (eol >= a.slot_count) eol -= a.slot_count;
         }
@@ -391,16 +400,122 @@ __global__ void build_segment_kernel(BuildArgs a) {
         uint32_t step = 0;
         bool border = q_is_zero(a, eol);   // nothing may be carried out of the segment's last slot
         for (;;) {
-            if (border) { atomicAdd(a.errors, 1u); return; }
+            if (border) { flag_segment(a, s); return; }
             fs = next_slot(a, fs);
             ++step;
             if (in_U(a, fs) && get_tally(a.blob, fs) == BT_FREE) break;
             border = q_is_zero(a, fs);
         }
-        if (step > BT_MAX_NEXT) { atomicAdd(a.errors, 1u); return; }   // would be a long link (two U-slots)
+        if (step > BT_MAX_NEXT) { flag_segment(a, s); return; }   // a long link takes two U-slots: repair pass
         // ufindex.cpp:303-313
         a.blob[5 * eol] = (uint8_t)((get_tally(a.blob, eol) & BT_MY_BIT) | step);
         put_rec(a.blob, fs, BT_END, bestpos);
+    }
+}
+
+// repair: the few segments in which an element needs a LONG LINK (probe distance > 124: two U-slots, ufindex.cpp:256-300).
+// The extra slot breaks the one-slot-per-element count, so such a segment may spill over its border.  One thread takes
+// the flagged segments in slot order: the region (whole segments, starting with the flagged one) is reset to its heads
+// and replayed with the complete UpdateSlot; whenever a probe would leave the region, the next segment is added and the
+// region is replayed again.  Lists that would have to be truncated (no free slot within 65534) are counted in errors[2].
+__device__ uint64_t segment_end(const BuildArgs &a, uint64_t t) {
+    while (!q_is_zero(a, t)) t = next_slot(a, t);
+    return t;
+}
+__device__ __forceinline__ void set_left(const BuildArgs &a, uint64_t t, uint32_t v) {
+    uint32_t *w = a.fill + (t >> 2);
+    const uint32_t sh = (uint32_t)(t & 3) * 8;
+    *w = (*w & ~(255u << sh)) | (v << sh);
+}
+// FindFreeSlot from `from`; returns the step or 0 (none within 65534) and sets `left_region` when the walk would pass `end`
+__device__ uint32_t repair_find_free(const BuildArgs &a, uint64_t from, uint64_t end, uint64_t &slot_out, bool &left_region) {
+    uint64_t t = from;
+    for (uint32_t step = 1; step < BT_MAX_LINK; ++step) {
+        if (t == end) { left_region = true; return 0; }
+        t = next_slot(a, t);
+        if (in_U(a, t) && get_tally(a.blob, t) == BT_FREE) { slot_out = t; return step; }
+    }
+    return 0;
+}
+__global__ void build_repair_kernel(BuildArgs a) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t nf = a.errors[0];
+    if (nf > a.flagged_cap) nf = a.flagged_cap;
+    for (uint32_t i = 1; i < nf; ++i) {   // slot order
+        const uint64_t v = a.flagged[i];
+        int j = (int)i - 1;
+        while (j >= 0 && a.flagged[j] > v) { a.flagged[j + 1] = a.flagged[j]; --j; }
+        a.flagged[j + 1] = v;
+    }
+    uint64_t done_from = 0, done_to = 0;
+    bool have_done = false;
+    for (uint32_t f = 0; f < nf; ++f) {
+        const uint64_t s = a.flagged[f];
+        if (have_done && done_from <= done_to && s >= done_from && s <= done_to) continue;   // inside a repaired region
+        uint64_t end = segment_end(a, s);
+        for (;;) {   // (re)play the region [s .. end]
+            for (uint64_t t = s;; t = next_slot(a, t)) {   // reset to the state after the heads pass
+                const uint32_t n = list_len(a, t);
+                if (in_U(a, t)) put_rec(a.blob, t, BT_FREE, 0xFFFFFFFFu);
+                else if (n > 0) {
+                    put_rec(a.blob, t, (n == 1 && cnt_get(a.cntM, t) == 0) ? BT_BOTH1 : BT_PLUS1, a.pool[a.base[t]]);
+                    set_left(a, t, n - 1);
+                }
+                if (t == end) break;
+            }
+            bool grow = false, give_up = false;
+            for (;;) {
+                uint64_t best = 0;
+                uint32_t bestpos = 0xFFFFFFFFu;
+                bool any = false;
+                for (uint64_t t = s;; t = next_slot(a, t)) {
+                    const uint32_t n = list_len(a, t);
+                    if (n >= 2) {
+                        const uint32_t left = (a.fill[t >> 2] >> ((uint32_t)(t & 3) * 8)) & 255u;
+                        if (left) {
+                            const uint32_t p = a.pool[(uint64_t)a.base[t] + (n - left)];
+                            if (!any || p < bestpos) { any = true; best = t; bestpos = p; }
+                        }
+                    }
+                    if (t == end) break;
+                }
+                if (!any) break;
+                uint64_t eol = best;   // FindEndOfList, ufindex.cpp:945-985
+                for (;;) {
+                    const uint32_t T = get_tally(a.blob, eol);
+                    if (T == BT_PLUS1 || T == BT_BOTH1 || T == BT_END) break;
+                    if (T == 253 || T == BT_LONG) {
+                        const uint32_t P = get_pos(a.blob, eol);
+                        eol = (eol + (P & 0xffffu)) % a.slot_count;
+                        eol = (eol + (P >> 16)) % a.slot_count;
+                    } else
+                        eol = (eol + (T & 127u)) % a.slot_count;
+                }
+                uint64_t fs = 0, fs2 = 0;
+                const uint32_t step = repair_find_free(a, eol, end, fs, grow);
+                if (grow) break;
+                if (step == 0) { give_up = true; break; }
+                if (step > BT_MAX_NEXT) {   // ufindex.cpp:256-300
+                    const uint32_t step2 = repair_find_free(a, fs, end, fs2, grow);
+                    if (grow) break;
+                    if (step2 == 0) { give_up = true; break; }
+                    const uint32_t eolpos = get_pos(a.blob, eol);
+                    put_rec(a.blob, eol, (uint8_t)((get_tally(a.blob, eol) & BT_MY_BIT) | BT_LONG), step | (step2 << 16));
+                    put_rec(a.blob, fs, BT_LONG, eolpos);
+                    put_rec(a.blob, fs2, BT_END, bestpos);
+                } else {   // ufindex.cpp:303-313
+                    a.blob[5 * eol] = (uint8_t)((get_tally(a.blob, eol) & BT_MY_BIT) | step);
+                    put_rec(a.blob, fs, BT_END, bestpos);
+                }
+                set_left(a, best, ((a.fill[best >> 2] >> ((uint32_t)(best & 3) * 8)) & 255u) - 1);
+            }
+            if (give_up) { atomicAdd(a.errors + 2, 1u); break; }   // TruncateSlot (ufindex.cpp:153-192) is not reproduced
+            if (!grow) break;
+            end = segment_end(a, next_slot(a, end));   // the region swallows the next segment and is replayed
+        }
+        done_from = s;
+        done_to = end;
+        have_done = true;
     }
 }
 
@@ -423,8 +538,8 @@ using namespace urmb;
 extern "C" const char *urmb_build_last_error() { return g_build_err.c_str(); }
 
 // d_seq: seq_data_size bytes on the current device; d_blob: 5*slot_count+URMB_BLOB_PAD bytes (written).
-// stats[0] = indexed positions, stats[1] = segments that need the sequential builder (long links / truncated lists: the
-// blob is then NOT valid; 0 at the reference's load factor), stats[2] = microseconds.
+// stats[0] = indexed positions, stats[1] = lists the reference would truncate (the blob is then NOT valid),
+// stats[2] = microseconds.
 extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t slot_count,
                                        uint32_t word_length, uint32_t max_ix, void *d_blob, uint64_t *stats) {
     if (!d_seq || !d_blob || slot_count < 2 || word_length < 8 || word_length > 32 || max_ix < 1 || max_ix > 32)
@@ -441,7 +556,7 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
     const uint64_t cwords = (slot_count + 3) / 4 + 1;
     const uint64_t nblocks = (slot_count + kScanBlock - 1) / kScanBlock;
     uint64_t total = 0;
-    uint32_t herr[2] = {0, 0};
+    uint32_t herr[4] = {0, 0, 0, 0};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     float ms = 0;
     const int T = 256;
@@ -458,12 +573,14 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
     BCK(cudaMalloc(&a.blockA, (nblocks + 1) * 8));
     BCK(cudaMalloc(&a.blockB, (nblocks + 1) * 8));
     BCK(cudaMalloc(&a.blockQ, (nblocks + 1) * 8));
-    BCK(cudaMalloc(&a.errors, 8));
+    BCK(cudaMalloc(&a.errors, 16));
+    a.flagged_cap = 1u << 16;
+    BCK(cudaMalloc(&a.flagged, (size_t)a.flagged_cap * 8));
     BCK(cudaMemset(a.cntP, 0, cwords * 4));
     BCK(cudaMemset(a.cntM, 0, cwords * 4));
     BCK(cudaMemset(a.fill, 0, cwords * 4));
     BCK(cudaMemset(a.qzero, 0, slot_count / 8 + 16));
-    BCK(cudaMemset(a.errors, 0, 8));
+    BCK(cudaMemset(a.errors, 0, 16));
     BCK(cudaMemset(a.blocksum, 0, (nblocks + 1) * 8));
     BCK(cudaMemset((uint8_t *)d_blob + 5 * slot_count, 0, URMB_BLOB_PAD));
     build_init_kernel<<<(unsigned)(((slot_count + 3) / 4 + T - 1) / T), T>>>(a);
@@ -480,24 +597,25 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
     build_carry_top_kernel<<<1, 1024>>>(a, nblocks);
     build_carry_apply_kernel<<<(unsigned)nblocks, 256>>>(a);
     build_segment_kernel<<<(unsigned)gslot, T>>>(a);
+    build_repair_kernel<<<1, 32>>>(a);
     BCK(cudaGetLastError());
-    BCK(cudaMemcpy(herr, a.errors, 8, cudaMemcpyDeviceToHost));
+    BCK(cudaMemcpy(herr, a.errors, 16, cudaMemcpyDeviceToHost));
     BCK(cudaEventRecord(e1));
     BCK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1);
     if (stats) {
         stats[0] = total;
-        stats[1] = herr[0];
+        stats[1] = herr[2];
         stats[2] = (uint64_t)(ms * 1000.0f);
     }
     cudaFree(a.cntP); cudaFree(a.cntM); cudaFree(a.fill); cudaFree(a.base); cudaFree(a.blocksum);
-    cudaFree(a.qzero); cudaFree(a.blockA); cudaFree(a.blockB); cudaFree(a.blockQ); cudaFree(a.errors); cudaFree(a.pool);
+    cudaFree(a.qzero); cudaFree(a.blockA); cudaFree(a.blockB); cudaFree(a.blockQ); cudaFree(a.errors); cudaFree(a.flagged); cudaFree(a.pool);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (herr[1]) { g_build_err = "pool overflow (internal error)"; return URMB_E_OVERFLOW; }
     return URMB_OK;
 fail:
     cudaFree(a.cntP); cudaFree(a.cntM); cudaFree(a.fill); cudaFree(a.base); cudaFree(a.blocksum);
-    cudaFree(a.qzero); cudaFree(a.blockA); cudaFree(a.blockB); cudaFree(a.blockQ); cudaFree(a.errors); cudaFree(a.pool);
+    cudaFree(a.qzero); cudaFree(a.blockA); cudaFree(a.blockB); cudaFree(a.blockQ); cudaFree(a.errors); cudaFree(a.flagged); cudaFree(a.pool);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return URMB_E_CUDA;
@@ -515,7 +633,7 @@ extern "C" int urmb_host_gpu_build(const uint8_t *seq, uint64_t n, uint64_t slot
     if (cudaMemcpy(d_seq, seq, n, cudaMemcpyHostToDevice) != cudaSuccess) goto out;
     rc = urmb_build_index_device(d_seq, n, slots, W, maxix, d_blob, stats);
     if (rc == 0 && stats[1] != 0) {
-        g_build_err = std::to_string(stats[1]) + " segment(s) need long links or list truncation";
+        g_build_err = std::to_string(stats[1]) + " list(s) would have to be truncated";
         rc = URMB_E_OVERFLOW;
     }
     if (rc == 0 && cudaMemcpy(blob, d_blob, 5 * slots, cudaMemcpyDeviceToHost) != cudaSuccess) rc = URMB_E_CUDA;

@@ -521,10 +521,15 @@ struct Mate {
     const uint8_t *tally;   // global (probe output): [2][qcap]
     const uint32_t *pos;    // global: [2][qcap]
     const uint32_t *ext;    // global: [2][qcap]
+    // first-pass kernels: the probe rows of this read staged in shared memory by load_mate ([2][qcap] each), so
+    // that the seed lists are built without a round trip to HBM per 32 visits
+    const uint8_t *s_tally;
+    const uint32_t *s_pos;
+    const uint32_t *s_ext;
     // ordered BOTH1 candidate list of the current search (shared, 2*qcap entries): the seed sequence of
-    // GetFirst/NextBoth1Seed (PE) or the phase-1 + phase-2 visit order of Search_Lo (SE)
-    uint32_t *sd_db;        // DBPos
-    uint32_t *sd_ext;       // packed pure extension on the seed's own strand
+    // GetFirst/NextBoth1Seed (PE) or the phase-1 + phase-2 visit order of Search_Lo (SE).  A seed is its
+    // (QPos, strand); DBPos and the packed pure extension on the seed's own strand are read from the staged rows
+    // (sd_db, sd_ext below)
     uint16_t *sd_qs;        // QPos | strand << 15 (strand 0 = plus)
     uint32_t *sd_dead;      // bit i: ExtendPen(seed i, own strand) is known to return <= 0 without side effects
     int nSeeds;
@@ -538,6 +543,12 @@ struct Mate {
 };
 
 __device__ __forceinline__ const uint8_t *mate_seq(const Mate &m, bool Plus) { return Plus ? m.q : m.rc; }
+__device__ __forceinline__ uint32_t sd_row(const Mate &m, int i) {
+    const uint32_t qs = m.sd_qs[i];
+    return (qs >> 15) * m.qcap + (qs & 0x7FFFu);
+}
+__device__ __forceinline__ uint32_t sd_db(const Mate &m, int i) { return m.s_pos[sd_row(m, i)]; }    // DBPos of seed i
+__device__ __forceinline__ uint32_t sd_ext(const Mate &m, int i) { return m.s_ext[sd_row(m, i)]; }   // its pure extension
 
 // ---- run-length path helpers -----------------------------------------------------------
 __device__ __noinline__ void runs_append(uint16_t *runs, int &n, uint32_t op, uint32_t len, int cap, int &ovf,
@@ -715,7 +726,7 @@ __device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m) {
     __syncwarp();
     for (int base = 0; base < m.nSeeds; base += 32) {
         const int i = base + E.lane;
-        const bool d = (i >= m.nSeeds) || ext_is_noop(E, m.sd_ext[i], (int)m.QL, m.MaxPenalty);
+        const bool d = (i >= m.nSeeds) || ext_is_noop(E, sd_ext(m, i), (int)m.QL, m.MaxPenalty);
         const uint32_t w = __ballot_sync(FULL, d);
         if (E.lane == 0) m.sd_dead[base >> 5] = w;
     }
@@ -730,8 +741,9 @@ __device__ __noinline__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo)
         const int i = base + E.lane;
         bool d = false;
         if (i < m.nSeeds) {
-            const uint32_t x = m.sd_ext[i];
-            d = (((m.sd_db[i] - (m.sd_qs[i] & 0x7FFFu)) >> 6) == key) || (ext_nmis(x) * -E.P.MM > m.MaxPenalty);
+            const uint32_t qs = m.sd_qs[i], row = (qs >> 15) * m.qcap + (qs & 0x7FFFu);
+            const uint32_t x = m.s_ext[row];
+            d = (((m.s_pos[row] - (qs & 0x7FFFu)) >> 6) == key) || (ext_nmis(x) * -E.P.MM > m.MaxPenalty);
         }
         const uint32_t w = __ballot_sync(FULL, d);
         if (E.lane == 0 && w) m.sd_dead[base >> 5] |= w;
@@ -742,9 +754,9 @@ __device__ __noinline__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo)
 // ExtendPen(seed i) on the seed's own strand, through the memo.
 __device__ __noinline__ int apply_seed(const Env &E, Mate &m, int i) {
     if (seed_dead(m, i)) return -1;
-    const uint32_t qs = m.sd_qs[i], db = m.sd_db[i];
+    const uint32_t qs = m.sd_qs[i], row = (qs >> 15) * m.qcap + (qs & 0x7FFFu), db = m.s_pos[row];
     bool stored;
-    const int r = extend_apply(E, m, qs & 0x7FFFu, db, (qs >> 15) == 0, m.sd_ext[i], stored);
+    const int r = extend_apply(E, m, qs & 0x7FFFu, db, (qs >> 15) == 0, m.s_ext[row], stored);
     __syncwarp();
     if (stored) seeds_kill(E, m, db - (qs & 0x7FFFu));
     else if (r <= 0) {
@@ -1377,29 +1389,36 @@ __device__ __noinline__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tal
     }
 }
 
-// First round over a list of owned non-BOTH1 slots (search1m6.cpp:181-199, search1pepend.cpp:53-68): rows of length
-// <= 2 are extended now, longer rows are deferred through `deflist`.  Three passes so that every lane has work:
-//   1. the heads of all rows of the list, one dependent-gather chain per lane;
+// First round over the lists of owned non-BOTH1 slots of both strands (search1m6.cpp:181-199,
+// search1pepend.cpp:53-68): rows of length <= 2 are extended now, longer rows are deferred through `def0` / `def1`.
+// Three passes so that every lane has work:
+//   1. the heads of all rows of both lists, one dependent-gather chain per lane;
 //   2. the candidates of the short rows laid out flat, 32 pure extensions at a time;
-//   3. the order-dependent bookkeeping, visiting the list in the reference's order.
-// The hit-overlap precheck and the penalty bound of pass 2 use the state at entry: both only ever get stricter, so a
-// candidate dropped here is still a no-op when the reference reaches it, and pass 3 re-applies the current state.
-// `deflist` may alias `list` (it is written in pass 3 only; pass 1 keeps its own copy of the list).
-__device__ __noinline__ void rows_short_round(const Env &E, Mate &m, int s, const uint8_t *list, int n, uint8_t *deflist,
-                                              int &ndef) {
-    ndef = 0;
+//   3. the order-dependent bookkeeping, visiting the plus list and then the minus list in the reference's order.
+// The hit-overlap precheck and the penalty bound of passes 1 and 2 use the state at entry: both only ever get
+// stricter, so a candidate dropped here is still a no-op when the reference reaches it, and pass 3 re-applies the
+// current state (extend_apply).  Taking the minus list through passes 1 and 2 together with the plus list halves the
+// number of dependent-gather rounds per mate; a caller that wants the strands one after the other passes one empty list.
+// `def0` / `def1` may alias `list0` / `list1` (written in pass 3 only; pass 1 keeps its own copy of the lists).
+__device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8_t *list0, int n0, const uint8_t *list1, int n1,
+                                              uint8_t *def0, int &nd0, uint8_t *def1, int &nd1) {
+    nd0 = nd1 = 0;
+    const int n = n0 + n1;
     if (n <= 0) return;
-    uint32_t *hp0 = reinterpret_cast<uint32_t *>(E.ws->rowM);   // [kMaxLen] first position of the row
-    uint32_t *hp1 = hp0 + kMaxLen;                              // [kMaxLen] second position
-    uint32_t *hx0 = hp1 + kMaxLen, *hx1 = hx0 + kMaxLen;        // [kMaxLen] pure extension results
-    uint16_t *flat = reinterpret_cast<uint16_t *>(E.ws->rowD);  // [2 * kMaxLen] entry | which << 15
-    uint8_t *hq = E.ws->tb, *hn = E.ws->tb + kMaxLen;           // [kMaxLen] QPos, row length (3 = longer than 2)
+    constexpr int CAP = 2 * kMaxLen;
+    uint32_t *hp0 = reinterpret_cast<uint32_t *>(E.ws->rowM);   // [CAP] first position of the row
+    uint32_t *hp1 = hp0 + CAP;                                  // [CAP] second position
+    uint32_t *hx0 = reinterpret_cast<uint32_t *>(E.ws->rowD);   // [CAP] pure extension results
+    uint32_t *hx1 = hx0 + CAP;
+    uint8_t *hq = E.ws->tb, *hn = E.ws->tb + CAP;               // [CAP] QPos, row length (3 = longer than 2)
+    uint16_t *flat = reinterpret_cast<uint16_t *>(E.ws->tb + 2 * CAP);   // [2 * CAP] entry | which << 15
     const uint32_t lt = (1u << E.lane) - 1u;
     int total = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {   // pass 1
         const int i = i0 + E.lane;
         const bool valid = i < n;
-        const uint32_t QPos = valid ? list[i] : 0u;
+        const int s = (i < n0) ? 0 : 1;
+        const uint32_t QPos = valid ? (s ? list1[i - n0] : list0[i]) : 0u;
         uint32_t rn = 0, p0 = 0, p1 = 0;
         if (valid) row_head3(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), rn, p0, p1);
         if (rn > E.ix.max_ix) rn = E.ix.max_ix;
@@ -1425,12 +1444,12 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, int s, cons
         if (f < total) {
             const uint32_t e = flat[f], i = e & 0x7FFFu;
             const uint32_t pz = (e & 0x8000u) ? hp1[i] : hp0[i];
-            const uint32_t x = pure_ext(E.ix, E.P, m.rv, s == 0, hq[i], pz, true, m.MaxPenalty);
+            const uint32_t x = pure_ext(E.ix, E.P, m.rv, (int)i < n0, hq[i], pz, true, m.MaxPenalty);
             if (e & 0x8000u) hx1[i] = x; else hx0[i] = x;
         }
     }
     __syncwarp();
-    for (int i0 = 0; i0 < n; i0 += 32) {   // pass 3
+    for (int i0 = 0; i0 < n; i0 += 32) {   // pass 3; a block of 32 entries may straddle the two lists
         const int i = i0 + E.lane;
         const bool valid = i < n;
         const uint32_t QPos = valid ? hq[i] : 0u, rn = valid ? hn[i] : 0u;
@@ -1444,15 +1463,21 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, int s, cons
             const int b = __ffs(vmask) - 1;
             vmask &= vmask - 1;
             const uint32_t qb = __shfl_sync(FULL, QPos, b);
+            const bool plus = i0 + b < n0;
             if (big >> b & 1u) {
-                if (E.lane == 0) deflist[ndef] = (uint8_t)qb;
-                ++ndef;
+                if (plus) {
+                    if (E.lane == 0) def0[nd0] = (uint8_t)qb;
+                    ++nd0;
+                } else {
+                    if (E.lane == 0) def1[nd1] = (uint8_t)qb;
+                    ++nd1;
+                }
                 continue;
             }
             const uint32_t pb0 = __shfl_sync(FULL, p0, b), pb1 = __shfl_sync(FULL, p1, b);
             const uint32_t xb0 = __shfl_sync(FULL, x0, b), xb1 = __shfl_sync(FULL, x1, b);
-            if (m0 >> b & 1u) extend_apply(E, m, qb, pb0, s == 0, xb0, stored);
-            if (m1 >> b & 1u) extend_apply(E, m, qb, pb1, s == 0, xb1, stored);
+            if (m0 >> b & 1u) extend_apply(E, m, qb, pb0, plus, xb0, stored);
+            if (m1 >> b & 1u) extend_apply(E, m, qb, pb1, plus, xb1, stored);
         }
     }
     __syncwarp();
@@ -1489,14 +1514,16 @@ __device__ uint32_t row_walk_lane(const Env &E, uint64_t Slot, uint32_t Tally, u
 // extends its positions in order.  Here 32 rows are walked at once (one dependent-gather chain per lane), their
 // candidates are laid out row-major in per-warp scratch, the pure extensions run 32 candidates at a time, and the
 // order-dependent bookkeeping visits the survivors in exactly the reference's order.
-__device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, int s, const uint8_t *list, int n) {
+__device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_t *list0, int n0, const uint8_t *list1, int n1) {
     uint32_t *stage = reinterpret_cast<uint32_t *>(E.ws->rowM);   // [32 rows][32 positions]
     uint32_t *fpos = reinterpret_cast<uint32_t *>(E.ws->rowD);    // flat candidate positions (<= 1024)
     uint8_t *fq = E.ws->tb;                                       // flat candidate QPos
+    const int n = n0 + n1;   // the plus list, then the minus list (one may be empty)
     for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + E.lane;
         const bool valid = i < n;
-        const uint32_t QPos = valid ? list[i] : 0u;
+        const int s = (i < n0) ? 0 : 1;
+        const uint32_t QPos = valid ? (s ? list1[i - n0] : list0[i]) : 0u;
         uint32_t len = 0;
         if (valid) len = row_walk_lane(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), stage + 32 * E.lane);
         uint32_t off = len;   // exclusive prefix sum over lanes
@@ -1506,6 +1533,9 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, int s, const
         }
         const uint32_t total = __shfl_sync(FULL, off, 31);
         off -= len;
+        // candidates of the plus rows come first: [0, nplus) is the plus strand
+        const int lp = min(max(n0 - i0, 0), 32);   // lanes [0, lp) hold plus rows
+        const uint32_t nplus = (lp >= 32) ? total : __shfl_sync(FULL, off, lp);
         for (uint32_t k = 0; k < len; ++k) {
             fpos[off + k] = stage[32 * E.lane + k];
             fq[off + k] = (uint8_t)QPos;
@@ -1517,14 +1547,15 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, int s, const
             if (f < total) {
                 q = fq[f];
                 pz = fpos[f];
-                if (pz >= q && !overlaps_hit_lane(m, pz - q)) x = pure_ext(E.ix, E.P, m.rv, s == 0, q, pz, true, m.MaxPenalty);
+                if (pz >= q && !overlaps_hit_lane(m, pz - q)) x = pure_ext(E.ix, E.P, m.rv, f < nplus, q, pz, true, m.MaxPenalty);
             }
             uint32_t am = __ballot_sync(FULL, !ext_is_noop(E, x, (int)m.QL, m.MaxPenalty));
             bool stored;
             while (am) {
                 const int r = __ffs(am) - 1;
                 am &= am - 1;
-                extend_apply(E, m, __shfl_sync(FULL, q, r), __shfl_sync(FULL, pz, r), s == 0, __shfl_sync(FULL, x, r), stored);
+                extend_apply(E, m, __shfl_sync(FULL, q, r), __shfl_sync(FULL, pz, r), f0 + (uint32_t)r < nplus,
+                             __shfl_sync(FULL, x, r), stored);
             }
         }
         __syncwarp();
@@ -1569,14 +1600,9 @@ __device__ __noinline__ bool se_phase12(const Env &E, Mate &m) {
             const uint32_t vv = (v - 2 * n1) >> 1;
             q = (W > 1) ? (vv / (W - 1)) * W + vv % (W - 1) + 1 : QWC;
         }
-        const bool c = (v < nvis) && (q < QWC) && (m_tally(m, sgn, q) == T_BOTH1);
+        const bool c = (v < nvis) && (q < QWC) && (m.s_tally[sgn * m.qcap + q] == T_BOTH1);
         const uint32_t bal = __ballot_sync(FULL, c);
-        if (c) {
-            const int i = m.nSeeds + __popc(bal & ((1u << E.lane) - 1u));
-            m.sd_db[i] = m_pos(m, sgn, q);
-            m.sd_ext[i] = m_ext(m, sgn, q);
-            m.sd_qs[i] = (uint16_t)(q | ((uint32_t)sgn << 15));
-        }
+        if (c) m.sd_qs[m.nSeeds + __popc(bal & ((1u << E.lane) - 1u))] = (uint16_t)(q | ((uint32_t)sgn << 15));
         m.nSeeds += __popc(bal);
     }
     seeds_init_dead(E, m);
@@ -1609,6 +1635,7 @@ __device__ __noinline__ bool se_phase3(const Env &E, Mate &m) {
 __device__ __noinline__ bool se_phase4(const Env &E, Mate &m) {
     const int QL = (int)m.QL;
     const uint32_t QWC = m.QWC;
+    int nls[2];
     for (int s = 0; s < 2; ++s) {
         // the owned non-BOTH1 slots of this strand in QPos order (search1m6.cpp:170-203), then rows <= 2 / deferral
         uint8_t *lst = m.g->todo[s];
@@ -1621,19 +1648,31 @@ __device__ __noinline__ bool se_phase4(const Env &E, Mate &m) {
             if (cand) lst[nl + __popc(bal & ((1u << E.lane) - 1u))] = (uint8_t)q;
             nl += __popc(bal);
         }
-        __syncwarp();
-        int nt = 0;
-        rows_short_round(E, m, s, lst, nl, lst, nt);
-        m.nPend[s] = nt;
+        nls[s] = nl;
     }
+    __syncwarp();
+    int nt0 = 0, nt1 = 0;
+    if (E.P.flags & 64u) {
+        int z;
+        rows_short_round(E, m, m.g->todo[0], nls[0], nullptr, 0, m.g->todo[0], nt0, nullptr, z);
+        rows_short_round(E, m, nullptr, 0, m.g->todo[1], nls[1], nullptr, z, m.g->todo[1], nt1);
+    } else {
+        rows_short_round(E, m, m.g->todo[0], nls[0], m.g->todo[1], nls[1], m.g->todo[0], nt0, m.g->todo[1], nt1);
+    }
+    m.nPend[0] = nt0;
+    m.nPend[1] = nt1;
     __syncwarp();
     if (m.Best >= QL + E.P.XP3 * E.P.MM) { m.Mapq = calc_mapq6(m); return true; }
     return false;
 }
 __device__ __forceinline__ bool se_phase5_done(const DevParams &P, int QL, int Best) { return Best >= QL + P.XP4 * P.MM; }
 __device__ __noinline__ bool se_phase5(const Env &E, Mate &m) {
-    for (int s = 0; s < 2; ++s)
-        rows_long_batch(E, m, s, m.g->todo[s], m.nPend[s]);
+    if (E.P.flags & 64u) {
+        rows_long_batch(E, m, m.g->todo[0], m.nPend[0], nullptr, 0);
+        rows_long_batch(E, m, nullptr, 0, m.g->todo[1], m.nPend[1]);
+    } else {
+        rows_long_batch(E, m, m.g->todo[0], m.nPend[0], m.g->todo[1], m.nPend[1]);
+    }
     if (se_phase5_done(E.P, (int)m.QL, m.Best)) { m.Mapq = calc_mapq6(m); return true; }
     return false;
 }
@@ -1669,8 +1708,8 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
         const int sgn = (int)(v & 1u);
         const bool valid = k < QWC;
         const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
-        const uint32_t T = valid ? m_tally(m, sgn, QPos) : 0u;
-        const uint32_t Pz = valid ? m_pos(m, sgn, QPos) : 0u;
+        const uint32_t T = valid ? m.s_tally[sgn * m.qcap + QPos] : 0u;
+        const uint32_t Pz = valid ? m.s_pos[sgn * m.qcap + QPos] : 0u;
         const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE
         const bool b1 = mine && T == T_BOTH1;
         const uint32_t diag = Pz - QPos;
@@ -1684,12 +1723,7 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
         const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
         const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
         const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
-        if (ret) {
-            const int i = m.nSeeds + __popc(retmask & lt);
-            m.sd_db[i] = Pz;
-            m.sd_ext[i] = m_ext(m, sgn, QPos);
-            m.sd_qs[i] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
-        }
+        if (ret) m.sd_qs[m.nSeeds + __popc(retmask & lt)] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
         if (pend) {
             const int i = m.nPend[sgn] + __popc((sgn ? pm : pp) & lt);
             m.g->pend[sgn][i] = (uint8_t)QPos;
@@ -1727,14 +1761,24 @@ __device__ __noinline__ bool pend_stage_a(const Env &E, Mate &m) {
 // Pending round 1 (rows <= 2 extended, longer rows deferred: the lists are compacted in place and nPend becomes the
 // number of deferred rows) and pending round 2 (the deferred rows): two kernels in the staged search.
 __device__ __noinline__ void pend_stage_b1(const Env &E, Mate &m) {
-    for (int s = 0; s < 2; ++s) {
-        int nd = 0;
-        rows_short_round(E, m, s, m.g->pend[s], m.nPend[s], m.g->pend[s], nd);
-        m.nPend[s] = nd;
+    int nd0 = 0, nd1 = 0;
+    if (E.P.flags & 64u) {   // URMB_FLAGS bit 6: the strands one after the other
+        int z;
+        rows_short_round(E, m, m.g->pend[0], m.nPend[0], nullptr, 0, m.g->pend[0], nd0, nullptr, z);
+        rows_short_round(E, m, nullptr, 0, m.g->pend[1], m.nPend[1], nullptr, z, m.g->pend[1], nd1);
+    } else {
+        rows_short_round(E, m, m.g->pend[0], m.nPend[0], m.g->pend[1], m.nPend[1], m.g->pend[0], nd0, m.g->pend[1], nd1);
     }
+    m.nPend[0] = nd0;
+    m.nPend[1] = nd1;
 }
 __device__ __noinline__ void pend_stage_b2(const Env &E, Mate &m) {
-    for (int s = 0; s < 2; ++s) rows_long_batch(E, m, s, m.g->pend[s], m.nPend[s]);
+    if (E.P.flags & 64u) {
+        rows_long_batch(E, m, m.g->pend[0], m.nPend[0], nullptr, 0);
+        rows_long_batch(E, m, nullptr, 0, m.g->pend[1], m.nPend[1]);
+    } else {
+        rows_long_batch(E, m, m.g->pend[0], m.nPend[0], m.g->pend[1], m.nPend[1]);
+    }
 }
 __device__ void pend_stage_b(const Env &E, Mate &m) {
     pend_stage_b1(E, m);
@@ -1947,7 +1991,7 @@ __device__ __forceinline__ void write_second(const Env &E, const Mate &F, const 
 __device__ int apply_seed_on(const Env &E, Mate &m, int i, bool Plus) {
     const uint32_t qs = m.sd_qs[i];
     if (((qs >> 15) == 0) == Plus) return apply_seed(E, m, i);
-    return extend_pen(E, m, qs & 0x7FFFu, m.sd_db[i], Plus);
+    return extend_pen(E, m, qs & 0x7FFFu, sd_db(m, i), Plus);
 }
 
 // State2::ExtendBoth1Pair4/5, search2m4.cpp:189-208, search2m5.cpp:134-156
@@ -1997,12 +2041,12 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairSta
     for (int t = 0; t < max(NF, NR); ++t) {
         if (t < NF && !seed_dead(F, t)) {
             const int nR = min(t, NR);
-            const uint32_t dbf = F.sd_db[t];
+            const uint32_t dbf = sd_db(F, t);
             const bool Plusf = (F.sd_qs[t] >> 15) == 0;
             bool gone = false;
             for (int base = 0; base < nR && !gone; base += 32) {
                 const int i = base + E.lane;
-                int64_t d = (int64_t)dbf - (int64_t)((i < nR) ? R.sd_db[i] : 0u);
+                int64_t d = (int64_t)dbf - (int64_t)((i < nR) ? sd_db(R, i) : 0u);
                 if (d < 0) d = -d;
                 uint32_t bal = __ballot_sync(FULL, (i < nR) && (d + QL2 <= MAX_TL));
                 while (bal) {
@@ -2016,13 +2060,13 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairSta
         }
         if (t < NR) {
             const int nF = min(t + 1, NF);
-            const uint32_t dbr = R.sd_db[t];
+            const uint32_t dbr = sd_db(R, t);
             const bool Plusr = (R.sd_qs[t] >> 15) == 0;
             for (int base = 0; base < nF; base += 32) {
                 const int i = base + E.lane;
                 bool ok = false;
                 if (i < nF) {
-                    int64_t d = (int64_t)F.sd_db[i] - (int64_t)dbr;
+                    int64_t d = (int64_t)sd_db(F, i) - (int64_t)dbr;
                     if (d < 0) d = -d;
                     const bool own = ((F.sd_qs[i] >> 15) == 0) == !Plusr;
                     ok = (d + QL2 <= MAX_TL) && !(own && seed_dead(F, i));
@@ -2113,8 +2157,8 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
 // Per-mate shared-memory footprint: read view (+ the seed lists of the first pass).
 __host__ __device__ inline size_t mate_smem_bytes(uint32_t qcap, uint32_t seqcap, bool seeds) {
     size_t n = 2 * (size_t)seqcap + kReadViewBytes;   // bytes fwd+rc, packed strands, bad bits
-    //            sd_db + sd_ext          sd_qs              sd_dead
-    if (seeds) n += 2 * (size_t)qcap * 8 + 2 * (size_t)qcap * 2 + ((2 * (size_t)qcap + 31) / 32) * 4;
+    //            s_pos + s_ext           sd_qs              sd_dead                              s_tally
+    if (seeds) n += 2 * (size_t)qcap * 8 + 2 * (size_t)qcap * 2 + ((2 * (size_t)qcap + 31) / 32) * 4 + 2 * (size_t)qcap;
     return (n + 15) & ~(size_t)15;
 }
 
@@ -2141,17 +2185,35 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(sm);
     uint32_t *s_bad = reinterpret_cast<uint32_t *>(sm + 2 * kPkWords * 8);
     uint8_t *p8 = sm + kReadViewBytes;
-    m.sd_db = m.sd_ext = m.sd_dead = nullptr;
+    const size_t base = (size_t)r * 2 * b.qcap;
+    m.sd_dead = nullptr;
     m.sd_qs = nullptr;
+    m.s_tally = nullptr;
+    m.s_pos = m.s_ext = nullptr;
     if (seeds) {
-        m.sd_db = reinterpret_cast<uint32_t *>(p8);
+        // the probe rows of the read ([2][qcap] tally / pos / ext): 8-byte loads, all in flight together with the
+        // loads of the read view below (every address is a multiple of 8: qcap is a multiple of 32)
+        uint64_t *d_pos = reinterpret_cast<uint64_t *>(p8);
         p8 += 2 * (size_t)b.qcap * 4;
-        m.sd_ext = reinterpret_cast<uint32_t *>(p8);
+        uint64_t *d_ext = reinterpret_cast<uint64_t *>(p8);
         p8 += 2 * (size_t)b.qcap * 4;
         m.sd_dead = reinterpret_cast<uint32_t *>(p8);
         p8 += ((2 * (size_t)b.qcap + 31) / 32) * 4;
         m.sd_qs = reinterpret_cast<uint16_t *>(p8);
         p8 += 2 * (size_t)b.qcap * 2;
+        uint64_t *d_tally = reinterpret_cast<uint64_t *>(p8);
+        p8 += 2 * (size_t)b.qcap;
+        const uint64_t *g_pos = reinterpret_cast<const uint64_t *>(pr.pos + base);
+        const uint64_t *g_ext = reinterpret_cast<const uint64_t *>(pr.ext + base);
+        const uint64_t *g_tally = reinterpret_cast<const uint64_t *>(pr.tally + base);
+        for (uint32_t i = E.lane; i < b.qcap; i += 32) {
+            d_pos[i] = __ldg(g_pos + i);
+            d_ext[i] = __ldg(g_ext + i);
+        }
+        for (uint32_t i = E.lane; i < b.qcap / 4; i += 32) d_tally[i] = __ldg(g_tally + i);
+        m.s_pos = reinterpret_cast<const uint32_t *>(d_pos);
+        m.s_ext = reinterpret_cast<const uint32_t *>(d_ext);
+        m.s_tally = reinterpret_cast<const uint8_t *>(d_tally);
     }
     uint8_t *s_q = p8, *s_rc = p8 + b.seqcap;
     {   // the probe kernel's staged read: packed strands + bad bits + flags + reverse complement; forward bytes as given
@@ -2172,7 +2234,6 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
         m.rv.hasbad = (fl & 2u) != 0;
         __syncwarp();
     }
-    const size_t base = (size_t)r * 2 * b.qcap;
     m.q = s_q;
     m.rc = s_rc;
     m.tally = pr.tally + base;
@@ -2253,8 +2314,10 @@ __device__ __forceinline__ void bare_mate(const Env &E, Mate &m, const DevBatch 
     const uint32_t L = b.offs[r + 1] - b.offs[r];
     m.q = m.rc = nullptr;
     m.tally = nullptr; m.pos = nullptr; m.ext = nullptr;
-    m.sd_db = m.sd_ext = m.sd_dead = nullptr;
+    m.sd_dead = nullptr;
     m.sd_qs = nullptr;
+    m.s_tally = nullptr;
+    m.s_pos = m.s_ext = nullptr;
     m.nSeeds = 0;
     m.g = &sv->s;
     m.QL = L;

@@ -45,7 +45,7 @@ def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, 
     counters = np.zeros(8, dtype=np.uint32)
     p = Params(method, pe_method, band_radius, 10, 0)
     L.emu_set_second(second.ctypes.data_as(C.c_void_p) if second is not None else None)
-    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    seqs = np.concatenate([np.asarray(seqs, dtype=np.uint8), np.zeros(64, dtype=np.uint8)])   # padded like the device buffer
     offs = np.ascontiguousarray(offs, dtype=np.uint32)
     vp = C.c_void_p
     rc = L.emu_map(blob.ctypes.data_as(vp), seq.ctypes.data_as(vp), C.c_uint32(oix.seq_size), C.c_uint64(oix.slot_count),

@@ -1,5 +1,5 @@
 """Aggregate an `ncu -i X.ncu-rep --page source --csv --print-source cuda,sass` dump by CUDA source line.
-Usage: python tools/ncu_lines.py dump.csv [top_n]"""
+Usage: python tools/ncu_lines.py dump.csv [top_n] [samples]   (third argument: rank by stall samples instead of instructions)"""
 import csv
 import sys
 
@@ -19,5 +19,6 @@ for r in rows:
     tot += inst
     tots += s
 print(f"total warp instructions {tot}  stall samples {tots}")
-for inst, s, ln, src in sorted(lines, reverse=True)[:top]:
+by_samples = len(sys.argv) > 3 and sys.argv[3] == "samples"
+for inst, s, ln, src in sorted(lines, key=lambda t: (t[1], t[0]) if by_samples else t, reverse=True)[:top]:
     print(f"{100 * inst / max(tot, 1):5.1f}% inst {100 * s / max(tots, 1):5.1f}% samples  L{ln}: {src}")

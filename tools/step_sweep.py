@@ -57,6 +57,6 @@ for val in (args.values.split(",") if args.values else [""]):
     if ref is None:
         ref = sig
     n = B * (1 if args.se else 2)
-    print(f"{args.var}={val or '-'}: {ms:.2f} ms/step -> {n / ms / 1e3:.2f} M reads/s  same_results={sig == ref}  "
+    print(f"{args.var}={val or '-'}: {ms:.2f} ms/step -> {n / ms / 1e3:.2f} M reads/s  same_results={sig == ref} sig={sig}  "
           + " ".join(f"{k}={v:.1f}" for k, v in tm["kernel_ms"].items()), flush=True)
     ctx.close()

@@ -521,15 +521,10 @@ struct Mate {
     const uint8_t *tally;   // global (probe output): [2][qcap]
     const uint32_t *pos;    // global: [2][qcap]
     const uint32_t *ext;    // global: [2][qcap]
-    // first-pass kernels: the probe rows of this read staged in shared memory by load_mate ([2][qcap] each), so
-    // that the seed lists are built without a round trip to HBM per 32 visits
-    const uint8_t *s_tally;
-    const uint32_t *s_pos;
-    const uint32_t *s_ext;
     // ordered BOTH1 candidate list of the current search (shared, 2*qcap entries): the seed sequence of
-    // GetFirst/NextBoth1Seed (PE) or the phase-1 + phase-2 visit order of Search_Lo (SE).  A seed is its
-    // (QPos, strand); DBPos and the packed pure extension on the seed's own strand are read from the staged rows
-    // (sd_db, sd_ext below)
+    // GetFirst/NextBoth1Seed (PE) or the phase-1 + phase-2 visit order of Search_Lo (SE)
+    uint32_t *sd_db;        // DBPos
+    uint32_t *sd_ext;       // packed pure extension on the seed's own strand
     uint16_t *sd_qs;        // QPos | strand << 15 (strand 0 = plus)
     uint32_t *sd_dead;      // bit i: ExtendPen(seed i, own strand) is known to return <= 0 without side effects
     int nSeeds;
@@ -543,12 +538,6 @@ struct Mate {
 };
 
 __device__ __forceinline__ const uint8_t *mate_seq(const Mate &m, bool Plus) { return Plus ? m.q : m.rc; }
-__device__ __forceinline__ uint32_t sd_row(const Mate &m, int i) {
-    const uint32_t qs = m.sd_qs[i];
-    return (qs >> 15) * m.qcap + (qs & 0x7FFFu);
-}
-__device__ __forceinline__ uint32_t sd_db(const Mate &m, int i) { return m.s_pos[sd_row(m, i)]; }    // DBPos of seed i
-__device__ __forceinline__ uint32_t sd_ext(const Mate &m, int i) { return m.s_ext[sd_row(m, i)]; }   // its pure extension
 
 // ---- run-length path helpers -----------------------------------------------------------
 __device__ __noinline__ void runs_append(uint16_t *runs, int &n, uint32_t op, uint32_t len, int cap, int &ovf,
@@ -721,12 +710,22 @@ __device__ int extend_pen(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t See
 // ---- seed lists ----------------------------------------------------------------------------
 __device__ __forceinline__ bool seed_dead(const Mate &m, int i) { return (m.sd_dead[i >> 5] >> (i & 31)) & 1u; }
 
-// After seed appends: mark the seeds whose extension is a no-op from the start.
-__device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m) {
+// After seed appends: fetch the packed pure extensions of the seeds from the probe rows (one gather round for 32
+// seeds, instead of a dependent load inside every round of the list builders) and mark the seeds whose extension is
+// a no-op from the start.
+__device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m, bool fetch_db) {
     __syncwarp();
     for (int base = 0; base < m.nSeeds; base += 32) {
         const int i = base + E.lane;
-        const bool d = (i >= m.nSeeds) || ext_is_noop(E, sd_ext(m, i), (int)m.QL, m.MaxPenalty);
+        uint32_t x = EXT_NONE;
+        if (i < m.nSeeds) {
+            const uint32_t qs = m.sd_qs[i];
+            const uint32_t row = (qs >> 15) * m.qcap + (qs & 0x7FFFu);
+            x = __ldg(m.ext + row);
+            if (fetch_db) m.sd_db[i] = __ldg(m.pos + row);   // the single-end builder only looked at the tallies
+            m.sd_ext[i] = x;
+        }
+        const bool d = (i >= m.nSeeds) || ext_is_noop(E, x, (int)m.QL, m.MaxPenalty);
         const uint32_t w = __ballot_sync(FULL, d);
         if (E.lane == 0) m.sd_dead[base >> 5] = w;
     }
@@ -741,9 +740,8 @@ __device__ __noinline__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo)
         const int i = base + E.lane;
         bool d = false;
         if (i < m.nSeeds) {
-            const uint32_t qs = m.sd_qs[i], row = (qs >> 15) * m.qcap + (qs & 0x7FFFu);
-            const uint32_t x = m.s_ext[row];
-            d = (((m.s_pos[row] - (qs & 0x7FFFu)) >> 6) == key) || (ext_nmis(x) * -E.P.MM > m.MaxPenalty);
+            const uint32_t x = m.sd_ext[i];
+            d = (((m.sd_db[i] - (m.sd_qs[i] & 0x7FFFu)) >> 6) == key) || (ext_nmis(x) * -E.P.MM > m.MaxPenalty);
         }
         const uint32_t w = __ballot_sync(FULL, d);
         if (E.lane == 0 && w) m.sd_dead[base >> 5] |= w;
@@ -754,9 +752,9 @@ __device__ __noinline__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo)
 // ExtendPen(seed i) on the seed's own strand, through the memo.
 __device__ __noinline__ int apply_seed(const Env &E, Mate &m, int i) {
     if (seed_dead(m, i)) return -1;
-    const uint32_t qs = m.sd_qs[i], row = (qs >> 15) * m.qcap + (qs & 0x7FFFu), db = m.s_pos[row];
+    const uint32_t qs = m.sd_qs[i], db = m.sd_db[i];
     bool stored;
-    const int r = extend_apply(E, m, qs & 0x7FFFu, db, (qs >> 15) == 0, m.s_ext[row], stored);
+    const int r = extend_apply(E, m, qs & 0x7FFFu, db, (qs >> 15) == 0, m.sd_ext[i], stored);
     __syncwarp();
     if (stored) seeds_kill(E, m, db - (qs & 0x7FFFu));
     else if (r <= 0) {
@@ -1398,7 +1396,7 @@ __device__ __noinline__ void row_head3(const Env &E, uint64_t Slot, uint32_t Tal
 // The hit-overlap precheck and the penalty bound of passes 1 and 2 use the state at entry: both only ever get
 // stricter, so a candidate dropped here is still a no-op when the reference reaches it, and pass 3 re-applies the
 // current state (extend_apply).  Taking the minus list through passes 1 and 2 together with the plus list halves the
-// number of dependent-gather rounds per mate; a caller that wants the strands one after the other passes one empty list.
+// number of dependent-gather rounds per mate; either list may be empty.
 // `def0` / `def1` may alias `list0` / `list1` (written in pass 3 only; pass 1 keeps its own copy of the lists).
 __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8_t *list0, int n0, const uint8_t *list1, int n1,
                                               uint8_t *def0, int &nd0, uint8_t *def1, int &nd1) {
@@ -1600,12 +1598,12 @@ __device__ __noinline__ bool se_phase12(const Env &E, Mate &m) {
             const uint32_t vv = (v - 2 * n1) >> 1;
             q = (W > 1) ? (vv / (W - 1)) * W + vv % (W - 1) + 1 : QWC;
         }
-        const bool c = (v < nvis) && (q < QWC) && (m.s_tally[sgn * m.qcap + q] == T_BOTH1);
+        const bool c = (v < nvis) && (q < QWC) && (m_tally(m, sgn, q) == T_BOTH1);
         const uint32_t bal = __ballot_sync(FULL, c);
         if (c) m.sd_qs[m.nSeeds + __popc(bal & ((1u << E.lane) - 1u))] = (uint16_t)(q | ((uint32_t)sgn << 15));
         m.nSeeds += __popc(bal);
     }
-    seeds_init_dead(E, m);
+    seeds_init_dead(E, m, true);
     for (int w0 = 0; w0 < m.nSeeds; w0 += 32) {
         uint32_t live = ~m.sd_dead[w0 >> 5];
         while (live) {
@@ -1652,13 +1650,7 @@ __device__ __noinline__ bool se_phase4(const Env &E, Mate &m) {
     }
     __syncwarp();
     int nt0 = 0, nt1 = 0;
-    if (E.P.flags & 64u) {
-        int z;
-        rows_short_round(E, m, m.g->todo[0], nls[0], nullptr, 0, m.g->todo[0], nt0, nullptr, z);
-        rows_short_round(E, m, nullptr, 0, m.g->todo[1], nls[1], nullptr, z, m.g->todo[1], nt1);
-    } else {
-        rows_short_round(E, m, m.g->todo[0], nls[0], m.g->todo[1], nls[1], m.g->todo[0], nt0, m.g->todo[1], nt1);
-    }
+    rows_short_round(E, m, m.g->todo[0], nls[0], m.g->todo[1], nls[1], m.g->todo[0], nt0, m.g->todo[1], nt1);
     m.nPend[0] = nt0;
     m.nPend[1] = nt1;
     __syncwarp();
@@ -1667,12 +1659,7 @@ __device__ __noinline__ bool se_phase4(const Env &E, Mate &m) {
 }
 __device__ __forceinline__ bool se_phase5_done(const DevParams &P, int QL, int Best) { return Best >= QL + P.XP4 * P.MM; }
 __device__ __noinline__ bool se_phase5(const Env &E, Mate &m) {
-    if (E.P.flags & 64u) {
-        rows_long_batch(E, m, m.g->todo[0], m.nPend[0], nullptr, 0);
-        rows_long_batch(E, m, nullptr, 0, m.g->todo[1], m.nPend[1]);
-    } else {
-        rows_long_batch(E, m, m.g->todo[0], m.nPend[0], m.g->todo[1], m.nPend[1]);
-    }
+    rows_long_batch(E, m, m.g->todo[0], m.nPend[0], m.g->todo[1], m.nPend[1]);
     if (se_phase5_done(E.P, (int)m.QL, m.Best)) { m.Mapq = calc_mapq6(m); return true; }
     return false;
 }
@@ -1708,8 +1695,8 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
         const int sgn = (int)(v & 1u);
         const bool valid = k < QWC;
         const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
-        const uint32_t T = valid ? m.s_tally[sgn * m.qcap + QPos] : 0u;
-        const uint32_t Pz = valid ? m.s_pos[sgn * m.qcap + QPos] : 0u;
+        const uint32_t T = valid ? m_tally(m, sgn, QPos) : 0u;
+        const uint32_t Pz = valid ? m_pos(m, sgn, QPos) : 0u;
         const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE
         const bool b1 = mine && T == T_BOTH1;
         const uint32_t diag = Pz - QPos;
@@ -1723,7 +1710,11 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
         const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
         const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
         const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
-        if (ret) m.sd_qs[m.nSeeds + __popc(retmask & lt)] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
+        if (ret) {
+            const int i = m.nSeeds + __popc(retmask & lt);
+            m.sd_db[i] = Pz;
+            m.sd_qs[i] = (uint16_t)(QPos | ((uint32_t)sgn << 15));
+        }
         if (pend) {
             const int i = m.nPend[sgn] + __popc((sgn ? pm : pp) & lt);
             m.g->pend[sgn][i] = (uint8_t)QPos;
@@ -1736,7 +1727,7 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
             prev_diag = __shfl_sync(FULL, diag, 31 - __clz(b1mask));
         }
     }
-    seeds_init_dead(E, m);
+    seeds_init_dead(E, m, false);
 }
 
 // State1::SearchPE_Pending, search1pepend.cpp:9-130 (k is always UINT_MAX at the call sites)
@@ -1762,23 +1753,12 @@ __device__ __noinline__ bool pend_stage_a(const Env &E, Mate &m) {
 // number of deferred rows) and pending round 2 (the deferred rows): two kernels in the staged search.
 __device__ __noinline__ void pend_stage_b1(const Env &E, Mate &m) {
     int nd0 = 0, nd1 = 0;
-    if (E.P.flags & 64u) {   // URMB_FLAGS bit 6: the strands one after the other
-        int z;
-        rows_short_round(E, m, m.g->pend[0], m.nPend[0], nullptr, 0, m.g->pend[0], nd0, nullptr, z);
-        rows_short_round(E, m, nullptr, 0, m.g->pend[1], m.nPend[1], nullptr, z, m.g->pend[1], nd1);
-    } else {
-        rows_short_round(E, m, m.g->pend[0], m.nPend[0], m.g->pend[1], m.nPend[1], m.g->pend[0], nd0, m.g->pend[1], nd1);
-    }
+    rows_short_round(E, m, m.g->pend[0], m.nPend[0], m.g->pend[1], m.nPend[1], m.g->pend[0], nd0, m.g->pend[1], nd1);
     m.nPend[0] = nd0;
     m.nPend[1] = nd1;
 }
 __device__ __noinline__ void pend_stage_b2(const Env &E, Mate &m) {
-    if (E.P.flags & 64u) {
-        rows_long_batch(E, m, m.g->pend[0], m.nPend[0], nullptr, 0);
-        rows_long_batch(E, m, nullptr, 0, m.g->pend[1], m.nPend[1]);
-    } else {
-        rows_long_batch(E, m, m.g->pend[0], m.nPend[0], m.g->pend[1], m.nPend[1]);
-    }
+    rows_long_batch(E, m, m.g->pend[0], m.nPend[0], m.g->pend[1], m.nPend[1]);
 }
 __device__ void pend_stage_b(const Env &E, Mate &m) {
     pend_stage_b1(E, m);
@@ -1991,7 +1971,7 @@ __device__ __forceinline__ void write_second(const Env &E, const Mate &F, const 
 __device__ int apply_seed_on(const Env &E, Mate &m, int i, bool Plus) {
     const uint32_t qs = m.sd_qs[i];
     if (((qs >> 15) == 0) == Plus) return apply_seed(E, m, i);
-    return extend_pen(E, m, qs & 0x7FFFu, sd_db(m, i), Plus);
+    return extend_pen(E, m, qs & 0x7FFFu, m.sd_db[i], Plus);
 }
 
 // State2::ExtendBoth1Pair4/5, search2m4.cpp:189-208, search2m5.cpp:134-156
@@ -2041,12 +2021,12 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairSta
     for (int t = 0; t < max(NF, NR); ++t) {
         if (t < NF && !seed_dead(F, t)) {
             const int nR = min(t, NR);
-            const uint32_t dbf = sd_db(F, t);
+            const uint32_t dbf = F.sd_db[t];
             const bool Plusf = (F.sd_qs[t] >> 15) == 0;
             bool gone = false;
             for (int base = 0; base < nR && !gone; base += 32) {
                 const int i = base + E.lane;
-                int64_t d = (int64_t)dbf - (int64_t)((i < nR) ? sd_db(R, i) : 0u);
+                int64_t d = (int64_t)dbf - (int64_t)((i < nR) ? R.sd_db[i] : 0u);
                 if (d < 0) d = -d;
                 uint32_t bal = __ballot_sync(FULL, (i < nR) && (d + QL2 <= MAX_TL));
                 while (bal) {
@@ -2060,13 +2040,13 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairSta
         }
         if (t < NR) {
             const int nF = min(t + 1, NF);
-            const uint32_t dbr = sd_db(R, t);
+            const uint32_t dbr = R.sd_db[t];
             const bool Plusr = (R.sd_qs[t] >> 15) == 0;
             for (int base = 0; base < nF; base += 32) {
                 const int i = base + E.lane;
                 bool ok = false;
                 if (i < nF) {
-                    int64_t d = (int64_t)sd_db(F, i) - (int64_t)dbr;
+                    int64_t d = (int64_t)F.sd_db[i] - (int64_t)dbr;
                     if (d < 0) d = -d;
                     const bool own = ((F.sd_qs[i] >> 15) == 0) == !Plusr;
                     ok = (d + QL2 <= MAX_TL) && !(own && seed_dead(F, i));
@@ -2157,8 +2137,8 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
 // Per-mate shared-memory footprint: read view (+ the seed lists of the first pass).
 __host__ __device__ inline size_t mate_smem_bytes(uint32_t qcap, uint32_t seqcap, bool seeds) {
     size_t n = 2 * (size_t)seqcap + kReadViewBytes;   // bytes fwd+rc, packed strands, bad bits
-    //            s_pos + s_ext           sd_qs              sd_dead                              s_tally
-    if (seeds) n += 2 * (size_t)qcap * 8 + 2 * (size_t)qcap * 2 + ((2 * (size_t)qcap + 31) / 32) * 4 + 2 * (size_t)qcap;
+    //            sd_db + sd_ext          sd_qs              sd_dead
+    if (seeds) n += 2 * (size_t)qcap * 8 + 2 * (size_t)qcap * 2 + ((2 * (size_t)qcap + 31) / 32) * 4;
     return (n + 15) & ~(size_t)15;
 }
 
@@ -2181,50 +2161,55 @@ __host__ __device__ inline size_t smem_per_warp(const DevBatch &b, const SmemPla
 // Stage one read: bytes, reverse complement, packed strands in shared memory; probe results stay in global.
 __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b, const DevProbe &pr, uint32_t r, uint8_t *sm,
                                        MateScratch *g, bool seeds) {
-    const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
+    const uint32_t off = __ldg(b.offs + r), L = __ldg(b.offs + r + 1) - off;
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(sm);
     uint32_t *s_bad = reinterpret_cast<uint32_t *>(sm + 2 * kPkWords * 8);
     uint8_t *p8 = sm + kReadViewBytes;
-    const size_t base = (size_t)r * 2 * b.qcap;
-    m.sd_dead = nullptr;
+    m.sd_db = m.sd_ext = m.sd_dead = nullptr;
     m.sd_qs = nullptr;
-    m.s_tally = nullptr;
-    m.s_pos = m.s_ext = nullptr;
     if (seeds) {
-        // the probe rows of the read ([2][qcap] tally / pos / ext): 8-byte loads, all in flight together with the
-        // loads of the read view below (every address is a multiple of 8: qcap is a multiple of 32)
-        uint64_t *d_pos = reinterpret_cast<uint64_t *>(p8);
+        m.sd_db = reinterpret_cast<uint32_t *>(p8);
         p8 += 2 * (size_t)b.qcap * 4;
-        uint64_t *d_ext = reinterpret_cast<uint64_t *>(p8);
+        m.sd_ext = reinterpret_cast<uint32_t *>(p8);
         p8 += 2 * (size_t)b.qcap * 4;
         m.sd_dead = reinterpret_cast<uint32_t *>(p8);
         p8 += ((2 * (size_t)b.qcap + 31) / 32) * 4;
         m.sd_qs = reinterpret_cast<uint16_t *>(p8);
         p8 += 2 * (size_t)b.qcap * 2;
-        uint64_t *d_tally = reinterpret_cast<uint64_t *>(p8);
-        p8 += 2 * (size_t)b.qcap;
-        const uint64_t *g_pos = reinterpret_cast<const uint64_t *>(pr.pos + base);
-        const uint64_t *g_ext = reinterpret_cast<const uint64_t *>(pr.ext + base);
-        const uint64_t *g_tally = reinterpret_cast<const uint64_t *>(pr.tally + base);
-        for (uint32_t i = E.lane; i < b.qcap; i += 32) {
-            d_pos[i] = __ldg(g_pos + i);
-            d_ext[i] = __ldg(g_ext + i);
-        }
-        for (uint32_t i = E.lane; i < b.qcap / 4; i += 32) d_tally[i] = __ldg(g_tally + i);
-        m.s_pos = reinterpret_cast<const uint32_t *>(d_pos);
-        m.s_ext = reinterpret_cast<const uint32_t *>(d_ext);
-        m.s_tally = reinterpret_cast<const uint8_t *>(d_tally);
     }
     uint8_t *s_q = p8, *s_rc = p8 + b.seqcap;
-    {   // the probe kernel's staged read: packed strands + bad bits + flags + reverse complement; forward bytes as given
+    {   // the probe kernel's staged read: packed strands + bad bits + flags + reverse complement; forward bytes as given.
+        // Every global load is issued before the first shared store (the stores would otherwise fence the loads of the
+        // next piece behind them: three dependent round trips to HBM instead of one after the offsets).
+        static_assert(kReadViewBytes / 4 <= 64 && kMaxLen / 4 <= 64, "two rounds of 32 lanes per piece");
         const uint32_t *vw = reinterpret_cast<const uint32_t *>(pr.view + (size_t)r * pr.view_stride);
-        uint32_t *dst32 = reinterpret_cast<uint32_t *>(sm);
-        for (uint32_t i = E.lane; i < kReadViewBytes / 4; i += 32) dst32[i] = __ldg(vw + i);
+        const uint32_t lane = (uint32_t)E.lane, nrc = b.seqcap / 4;
+        const uint32_t v0 = __ldg(vw + lane);
+        const uint32_t v1 = (lane + 32 < kReadViewBytes / 4) ? __ldg(vw + lane + 32) : 0u;
         const uint32_t fl = __ldg(vw + kReadViewBytes / 4);
+        const uint32_t c0 = (lane < nrc) ? __ldg(vw + kViewHdr / 4 + lane) : 0u;
+        const uint32_t c1 = (lane + 32 < nrc) ? __ldg(vw + kViewHdr / 4 + lane + 32) : 0u;
+        // forward bytes: aligned words covering [off, off + L) (the batch buffer is padded), bytes placed below
+        const uint32_t sk = off & 3u, nws = (sk + L + 3) >> 2;   // <= 65 words
+        const uint32_t *sw32 = reinterpret_cast<const uint32_t *>(b.seqs + (off - sk));
+        uint32_t w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = (lane + 32 * k < nws) ? __ldg(sw32 + lane + 32 * k) : 0u;
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(sm);
+        dst32[lane] = v0;
+        if (lane + 32 < kReadViewBytes / 4) dst32[lane + 32] = v1;
         uint32_t *rc32 = reinterpret_cast<uint32_t *>(s_rc);
-        for (uint32_t i = E.lane; i < b.seqcap / 4; i += 32) rc32[i] = __ldg(vw + kViewHdr / 4 + i);
-        const uint8_t *src = b.seqs + off;
-        for (uint32_t i = E.lane; i < L; i += 32) s_q[i] = src[i];
+        if (lane < nrc) rc32[lane] = c0;
+        if (lane + 32 < nrc) rc32[lane + 32] = c1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t p0 = 4 * (lane + 32 * k);   // byte position of the word in the aligned stream
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t p = p0 + t - sk;        // position in the read (wraps below zero for the skipped bytes)
+                if (p < L) s_q[p] = (uint8_t)(w[k] >> (8 * t));
+            }
+        }
         m.rv.q = s_q;
         m.rv.rc = s_rc;
         m.rv.pk = s_pk;
@@ -2234,6 +2219,7 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
         m.rv.hasbad = (fl & 2u) != 0;
         __syncwarp();
     }
+    const size_t base = (size_t)r * 2 * b.qcap;
     m.q = s_q;
     m.rc = s_rc;
     m.tally = pr.tally + base;
@@ -2314,10 +2300,8 @@ __device__ __forceinline__ void bare_mate(const Env &E, Mate &m, const DevBatch 
     const uint32_t L = b.offs[r + 1] - b.offs[r];
     m.q = m.rc = nullptr;
     m.tally = nullptr; m.pos = nullptr; m.ext = nullptr;
-    m.sd_dead = nullptr;
+    m.sd_db = m.sd_ext = m.sd_dead = nullptr;
     m.sd_qs = nullptr;
-    m.s_tally = nullptr;
-    m.s_pos = m.s_ext = nullptr;
     m.nSeeds = 0;
     m.g = &sv->s;
     m.QL = L;

@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/smi.txt 
 cp urmap_b200/liburmb.so $OUT/liburmb_saved.so
 for name in "$@"; do
   cp urmap_b200/variants/liburmb_$name.so urmap_b200/liburmb.so
-  timeout 400 python tools/step_sweep.py --var URMB_FLAGS --values 0,64 --steps 9 > $OUT/steps_$name.log 2>&1
+  timeout 400 python tools/step_sweep.py --var URMB_FLAGS --values ${VALUES:-0,64} --steps 9 > $OUT/steps_$name.log 2>&1
   echo "== $name"; grep "ms/step" $OUT/steps_$name.log
 done
 cp $OUT/liburmb_saved.so urmap_b200/liburmb.so

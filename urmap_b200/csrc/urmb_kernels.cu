@@ -2244,26 +2244,31 @@ __device__ __noinline__ void save_mate(const Env &E, Mate &m, MateSave *dst) {
         m.MaxPenalty = E.P.MAXPEN;   // search1pepend.cpp:15
         if (done) m.Mapq = calc_mapq6(m);
     }
-    const MateScratch *g = m.g;
-    MateScratch *d = &dst->s;
-    for (int i = E.lane; i < m.HitCount; i += 32) {
-        d->hit_pos[i] = g->hit_pos[i];
-        d->hit_score[i] = g->hit_score[i];
-        d->hit_plus[i] = g->hit_plus[i];
-        d->hit_nruns[i] = g->hit_nruns[i];
-        d->hit_roff[i] = g->hit_roff[i];
+    // scratch -> pool never overlap: with __restrict__ the loads of a whole round are issued before its stores
+    const MateScratch *__restrict__ g = m.g;
+    MateScratch *__restrict__ d = &dst->s;
+    for (int i0 = 0; i0 < max(m.HitCount, m.HSPCount); i0 += 32) {
+        const int i = i0 + E.lane;
+        const bool a = i < m.HitCount, c = i < m.HSPCount;
+        uint32_t hp = 0, hd = 0;
+        int16_t hs = 0, xs = 0;
+        uint16_t hr = 0, xq = 0, xl = 0;
+        uint8_t hl = 0, hn = 0, xf = 0;
+        if (a) { hp = g->hit_pos[i]; hs = g->hit_score[i]; hl = g->hit_plus[i]; hn = g->hit_nruns[i]; hr = g->hit_roff[i]; }
+        if (c) { hd = g->hsp_dbstart[i]; xq = g->hsp_qstart[i]; xl = g->hsp_len[i]; xs = g->hsp_score[i]; xf = g->hsp_flags[i]; }
+        if (a) { d->hit_pos[i] = hp; d->hit_score[i] = hs; d->hit_plus[i] = hl; d->hit_nruns[i] = hn; d->hit_roff[i] = hr; }
+        if (c) { d->hsp_dbstart[i] = hd; d->hsp_qstart[i] = xq; d->hsp_len[i] = xl; d->hsp_score[i] = xs; d->hsp_flags[i] = xf; }
     }
     for (int i = E.lane; i < m.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
-    for (int i = E.lane; i < m.HSPCount; i += 32) {
-        d->hsp_dbstart[i] = g->hsp_dbstart[i];
-        d->hsp_qstart[i] = g->hsp_qstart[i];
-        d->hsp_len[i] = g->hsp_len[i];
-        d->hsp_score[i] = g->hsp_score[i];
-        d->hsp_flags[i] = g->hsp_flags[i];
-    }
     if (!done)
-        for (int s = 0; s < 2; ++s)
-            for (int i = E.lane; i < m.nPend[s]; i += 32) d->pend[s][i] = g->pend[s][i];
+        for (int i0 = 0; i0 < max(m.nPend[0], m.nPend[1]); i0 += 32) {
+            const int i = i0 + E.lane;
+            uint8_t p0 = 0, p1 = 0;
+            if (i < m.nPend[0]) p0 = g->pend[0][i];
+            if (i < m.nPend[1]) p1 = g->pend[1][i];
+            if (i < m.nPend[0]) d->pend[0][i] = p0;
+            if (i < m.nPend[1]) d->pend[1][i] = p1;
+        }
     if (E.lane == 0) {
         MateHdr h;
         h.HitCount = m.HitCount; h.HSPCount = m.HSPCount; h.Top = m.Top; h.MaxPenalty = m.MaxPenalty;
@@ -2506,7 +2511,7 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
 #define URMB_LB_ROWS 6
 #endif
 #ifndef URMB_LB_ALIGN
-#define URMB_LB_ALIGN 5
+#define URMB_LB_ALIGN 6
 #endif
 __global__ void __launch_bounds__(128, URMB_LB_PAIR) seed_kernel_se(const __grid_constant__ KArgs A) { search_body<0>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se3(const __grid_constant__ KArgs A) { stage_body<3>(A); }

@@ -444,7 +444,13 @@ __host__ __device__ inline size_t probe_smem_per_warp(uint32_t qcap, uint32_t se
     //     read view + bytes                  c_pos                 c_qs
     return ((kReadViewBytes + 2 * (size_t)seqcap + 2 * (size_t)qcap * 4 + 2 * (size_t)qcap * 2) + 15) & ~(size_t)15;
 }
-__global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr) {
+#ifndef URMB_PROBE_BATCH
+#define URMB_PROBE_BATCH 8
+#endif
+#ifndef URMB_PROBE_LB
+#define URMB_PROBE_LB 3
+#endif
+__global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr) {
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     uint8_t *sw = smem + (size_t)warp * probe_smem_per_warp(b.qcap, b.seqcap);
@@ -470,51 +476,50 @@ __global__ void __launch_bounds__(256) probe_kernel(DevIndex ix, DevParams P, De
         const uint32_t QWC = (L >= W) ? L - W + 1 : 0;
         const size_t base = (size_t)r * 2 * b.qcap;
         uint32_t nc = 0;
-        // Slot records of four rounds of 32 k-mers are gathered together (eight loads per lane in flight) before the
-        // first one is looked at: the candidate list needs a ballot per round, which would otherwise put one trip to
+        // Slot records of URMB_PROBE_BATCH rounds of 32 k-mers are gathered together (two loads per round and lane in
+        // flight) before the first one is looked at: the candidate list needs a ballot per round, which would otherwise put one trip to
         // HBM between consecutive rounds.
-        for (uint32_t s = 0; s < 2; ++s) {
-            for (uint32_t q0 = 0; q0 < b.qcap; q0 += 128) {
-                uint32_t w0[4], w1[4], shp = 0, okm = 0;
+        const uint32_t rps = b.qcap / 32, nrounds = 2 * rps;   // rounds of 32 k-mers: the plus strand, then the minus strand
+        for (uint32_t r0 = 0; r0 < nrounds; r0 += URMB_PROBE_BATCH) {
+            uint32_t w0[URMB_PROBE_BATCH], w1[URMB_PROBE_BATCH], shp = 0, okm = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t q = q0 + 32 * k + lane;
-                    w0[k] = w1[k] = 0;
-                    if (q < QWC) {
-                        const uint64_t slot = slot_of(ix, rv, (int)s, q);
-                        if (slot != ~0ull) {
-                            const uint64_t a = 5ull * slot;   // record at byte offset 5*slot: two aligned words cover it
-                            const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blob + (a & ~3ull));
-                            w0[k] = __ldg(w);
-                            w1[k] = __ldg(w + 1);
-                            shp |= (uint32_t)(a & 3ull) << (2 * k);
-                            okm |= 1u << k;
-                        }
+            for (int k = 0; k < URMB_PROBE_BATCH; ++k) {
+                const uint32_t rr = r0 + k, s = rr >= rps, q = (rr - s * rps) * 32 + lane;
+                w0[k] = w1[k] = 0;
+                if (rr < nrounds && q < QWC) {
+                    const uint64_t slot = slot_of(ix, rv, (int)s, q);
+                    if (slot != ~0ull) {
+                        const uint64_t a = 5ull * slot;   // record at byte offset 5*slot: two aligned words cover it
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blob + (a & ~3ull));
+                        w0[k] = __ldg(w);
+                        w1[k] = __ldg(w + 1);
+                        shp |= (uint32_t)(a & 3ull) << (2 * k);
+                        okm |= 1u << k;
                     }
                 }
+            }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (q0 + 32 * k >= b.qcap) break;
-                    const uint32_t q = q0 + 32 * k + lane;
-                    uint32_t tally = T_FREE, pos = POS_INVALID_WORD;
-                    if ((okm >> k) & 1u) {
-                        const uint64_t v = (((uint64_t)w1[k] << 32) | w0[k]) >> (((shp >> (2 * k)) & 3u) * 8u);
-                        tally = (uint32_t)v & 0xFFu;
-                        pos = (uint32_t)(v >> 8);
-                    }
-                    const bool cand = tally == T_BOTH1;
-                    const uint32_t bal = __ballot_sync(FULL, cand);
-                    if (cand) {
-                        const uint32_t i = nc + __popc(bal & lt);
-                        c_pos[i] = pos;
-                        c_qs[i] = (uint16_t)(q | (s << 15));
-                    } else {
-                        pr.ext[base + s * b.qcap + q] = EXT_NONE;
-                    }
-                    nc += __popc(bal);
-                    pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
-                    pr.pos[base + s * b.qcap + q] = pos;
+            for (int k = 0; k < URMB_PROBE_BATCH; ++k) {
+                const uint32_t rr = r0 + k, s = rr >= rps, q = (rr - s * rps) * 32 + lane;
+                if (rr >= nrounds) break;
+                uint32_t tally = T_FREE, pos = POS_INVALID_WORD;
+                if ((okm >> k) & 1u) {
+                    const uint64_t v = (((uint64_t)w1[k] << 32) | w0[k]) >> (((shp >> (2 * k)) & 3u) * 8u);
+                    tally = (uint32_t)v & 0xFFu;
+                    pos = (uint32_t)(v >> 8);
                 }
+                const bool cand = tally == T_BOTH1;
+                const uint32_t bal = __ballot_sync(FULL, cand);
+                if (cand) {
+                    const uint32_t i = nc + __popc(bal & lt);
+                    c_pos[i] = pos;
+                    c_qs[i] = (uint16_t)(q | (s << 15));
+                } else {
+                    pr.ext[base + s * b.qcap + q] = EXT_NONE;
+                }
+                nc += __popc(bal);
+                pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
+                pr.pos[base + s * b.qcap + q] = pos;
             }
         }
         __syncwarp();

@@ -298,9 +298,9 @@ __device__ __noinline__ uint32_t pure_ext_bytes(const uint8_t *Qs, const uint8_t
 // The mismatch flags of a candidate window, 16 bases per 32-bit word: base t of half-word h (read position 16 h + t) at
 // bit 30 - 2 t.  NH = compiled number of half-words (10 covers reads up to 160 bases with half the code of 16: the
 // search kernels are instruction-fetch sensitive).  Returns false when the window touches a non-ACGT genome byte.
-template <int NH>
+template <int NH, bool NZ>
 __device__ __forceinline__ bool ext_flags(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus, uint32_t DBLo,
-                                          int nw, int nh, int QL, uint32_t *mm) {
+                                          int nw, int nh, int QL, uint32_t *mm, uint32_t &nz) {
     constexpr int NW = NH / 2 + 1;   // 64-bit genome words that can be touched
     const uint64_t *g = ix.seq2 + (DBLo >> 5);
     const uint32_t sh = 2 * (DBLo & 31);
@@ -339,20 +339,29 @@ __device__ __forceinline__ bool ext_flags(const DevIndex &ix, const DevParams &P
         mm[j] = d;
     }
     if (QL & 15) mm[nh - 1] &= 0xFFFFFFFFu << (32 - 2 * (QL & 15));
+    nz = 0;   // bit j: half-word j holds a mismatch (the NZ walks jump over clean half-words without touching mm)
+    if (NZ) {
+#pragma unroll
+        for (int j = 0; j < NH; ++j) nz |= (uint32_t)(mm[j] != 0) << j;
+    }
     return true;
 }
 
-__device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus,
-                                          uint32_t SeedPosQ, uint32_t SeedPosDB, bool LeftCountsPen, int PenBound) {
+// NZ: the walks skip runs of clean half-words through a bit mask.  It pays where most candidates are true ones (the
+// probe kernel: -1.0 ms per 2 M reads) and costs where most are hash collisions that stop after a few mismatches (the
+// row stages: +1.4 ms), so each kernel instantiates the form that suits it (profiles/r02n).
+template <bool NZ>
+__device__ __noinline__ uint32_t pure_ext_t(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus,
+                                            uint32_t SeedPosQ, uint32_t SeedPosDB, bool LeftCountsPen, int PenBound) {
     if (SeedPosDB < SeedPosQ) return EXT_NONE;   // extendpen.cpp:11
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
     const int QL = (int)rv.QL, W = (int)ix.word_len, MM = P.MM, XD = P.XDROP;
     const int nw = (QL + 31) >> 5;   // <= 8 packed 64-bit words
     const int nh = (QL + 15) >> 4;   // <= 16 half-words of 16 bases
     const int maxmis = min(PenBound / -MM, 126);   // nmis > maxmis  <=>  nmis * -MM > PenBound
-    uint32_t mm[16];
+    uint32_t mm[16], nz = 0;
     bool slow = rv.slow;
-    if (!slow) slow = (nh <= 10) ? !ext_flags<10>(ix, P, rv, Plus, DBLo, nw, nh, QL, mm) : !ext_flags<16>(ix, P, rv, Plus, DBLo, nw, nh, QL, mm);
+    if (!slow) slow = (nh <= 10) ? !ext_flags<10, NZ>(ix, P, rv, Plus, DBLo, nw, nh, QL, mm, nz) : !ext_flags<16, NZ>(ix, P, rv, Plus, DBLo, nw, nh, QL, mm, nz);
     if (slow) return pure_ext_bytes(Plus ? rv.q : rv.rc, ix.seq + DBLo, QL, W, MM, XD, SeedPosQ, LeftCountsPen);
 
     // Both walks are single loops whose iterations either step to the next half-word or consume one mismatch, so that
@@ -367,8 +376,12 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
         if (h < nh) w = mm[h] & (0xFFFFFFFFu >> (2 * (p & 15)));
         bool stop = false;
         for (;;) {
-            if (w == 0) {
-                if (++h >= nh) break;
+            if (w == 0) {   // next half-word (NZ: with a mismatch) to the right
+                if (NZ) {
+                    const uint32_t rem = (h < 31) ? nz & (0xFFFFFFFEu << h) : 0u;
+                    if (!rem) break;
+                    h = __ffs(rem) - 1;
+                } else if (++h >= nh) break;
                 w = mm[h];
                 continue;
             }
@@ -402,8 +415,12 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
         if (h >= 0) w = mm[h] & (0xFFFFFFFFu << (30 - 2 * (p & 15)));
         bool stop = false;
         for (;;) {
-            if (w == 0) {
-                if (--h < 0) break;
+            if (w == 0) {   // next half-word (NZ: with a mismatch) to the left
+                if (NZ) {
+                    const uint32_t rem = (h > 0) ? nz & ((1u << h) - 1u) : 0u;
+                    if (!rem) break;
+                    h = 31 - __clz(rem);
+                } else if (--h < 0) break;
                 w = mm[h];
                 continue;
             }
@@ -430,6 +447,11 @@ __device__ __noinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P
     }
     if (nmis > maxmis) return ext_pack(0, 1, 0, 127);
     return ext_pack(Best, Start, End, nmis);
+}
+
+__device__ __forceinline__ uint32_t pure_ext(const DevIndex &ix, const DevParams &P, const ReadView &rv, bool Plus,
+                                             uint32_t SeedPosQ, uint32_t SeedPosDB, bool LeftCountsPen, int PenBound) {
+    return pure_ext_t<false>(ix, P, rv, Plus, SeedPosQ, SeedPosDB, LeftCountsPen, PenBound);
 }
 
 // =====================================================================================
@@ -525,7 +547,7 @@ __global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_kernel(DevIndex ix, 
         __syncwarp();
         for (uint32_t i = lane; i < nc; i += 32) {
             const uint32_t qs = c_qs[i], q = qs & 0x7FFFu, s = qs >> 15;
-            pr.ext[base + s * b.qcap + q] = pure_ext(ix, P, rv, s == 0, q, c_pos[i], true, P.MAXPEN);
+            pr.ext[base + s * b.qcap + q] = pure_ext_t<true>(ix, P, rv, s == 0, q, c_pos[i], true, P.MAXPEN);
         }
         __syncwarp();
     }

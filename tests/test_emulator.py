@@ -134,3 +134,44 @@ def test_emulated_second_pair_matches_reference_tabbedout(oracle, golden_oix, go
     labels = [want[i].split("\t")[0] for i in sel]
     got = _tab_lines(hix.contigs, labels, np.diff(o1), np.diff(o2), res[:n], res[n:], second[:n], second[n:])
     assert got == [want[i] for i in sel]
+
+
+def test_emulated_repeat_rich_rows(oracle, built_lib, tmp_path):
+    """Repeat-rich genome (35 % repeats, tandem runs): most k-mers of a read own a non-BOTH1 slot, so the pending-row
+    stages (plus and minus lists gathered together, rows <= 2 now / longer rows deferred, search1pepend.cpp:53-110 and
+    search1m6.cpp:149-245) and the seed lists built from the probe rows carry the search.  Index from the drop-in's own
+    host builder (byte-identical to the reference's, tests/test_cli.py)."""
+    import subprocess
+    import emu_py
+    from urmap_b200 import synth
+    g = synth.make_genome(300_000, n_contigs=2, seed=77, repeat_frac=0.35, n_runs=[(0, 0.3, 300)], tandem=6)
+    fa, ufi = str(tmp_path / "rr.fa"), str(tmp_path / "rr.ufi")
+    g.write_fasta(fa)
+    cli = os.path.join(ROOT, "urmap_b200", "bin", "urmap_b200")
+    r = subprocess.run([cli, "-make_ufi", fa, "-output", ufi, "-quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ix = oracle.Index(ufi)
+    try:
+        reads, names = synth.sim_se(g, 120, 150, 0.03, 0.003, seed=3)
+        fq = str(tmp_path / "se.fq")
+        synth.write_fastq(fq, reads, names)
+        b = oracle.ReadBatch.from_fastq(fq)
+        for method in (6, 7):
+            ro, uo = oracle.map_se(ix, b, method=method)
+            re_, ue, cnt = emu_py.emu_map(ix, oracle.RESULT_DTYPE, b.seqs, b.offs, b.n, False, method=method)
+            assert cnt[1] == 0
+            _same(ro, uo, re_, ue)
+        r1, r2, names = synth.sim_pe(g, 100, 150, 0.03, 0.003, seed=13)
+        f1, f2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+        synth.write_fastq(f1, r1, names, b"/1")
+        synth.write_fastq(f2, r2, names, b"/2")
+        b1, b2 = oracle.ReadBatch.from_fastq(f1), oracle.ReadBatch.from_fastq(f2)
+        o1, o2, uo, st = oracle.map_pe(ix, b1, b2, pe_method=4, want_stats=True)
+        seqs = np.concatenate([b1.seqs, b2.seqs])
+        offs = np.concatenate([b1.offs, b2.offs[1:] + b1.offs[-1]]).astype(np.uint32)
+        re_, ue, cnt = emu_py.emu_map(ix, oracle.RESULT_DTYPE, seqs, offs, b1.n, True, pe_method=4)
+        assert cnt[1] == 0
+        assert st["row_calls"] > 20 * st["reads"] and st["row_hops"] > st["row_calls"]   # the case is what it claims to be
+        _same(np.concatenate([o1, o2]), uo, re_, ue)
+    finally:
+        ix.close()

@@ -2561,7 +2561,7 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
 #define URMB_LB_PAIR 5
 #endif
 #ifndef URMB_LB_ROWS
-#define URMB_LB_ROWS 6
+#define URMB_LB_ROWS 7
 #endif
 #ifndef URMB_LB_ALIGN
 #define URMB_LB_ALIGN 7

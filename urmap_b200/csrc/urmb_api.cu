@@ -206,7 +206,7 @@ static DevParams make_params(const urmb_params &p) {  // State1::SetMethod, stat
     P.pe_method = (p.pe_method == 5) ? 5 : 4;
     if (p.band_radius >= 0) P.R = (uint32_t)p.band_radius;
     else if (p.pe_method == 5) P.R = 4;   // map2.cpp:17-21
-    P.flags = 0;       // bit3: 168-register variant of the search kernel (3 blocks/SM)
+    P.flags = 0;       // URMB_FLAGS: see DevParams::flags
     if (const char *f = getenv("URMB_FLAGS")) P.flags = (uint32_t)strtoul(f, nullptr, 0);
     return P;
 }

@@ -33,7 +33,7 @@ struct DevParams {  // State1::SetMethod constants, state1.cpp:147-183
     int MM, GO, GE, MIN_HSP_PCT, TERM3_PCT, XDROP, MAXPEN, XP1, XP3, XP4;
     uint32_t R;
     int pe_method;
-    uint32_t flags;   // tuning switches (URMB_FLAGS): bit0 BOTH1 alive table, bit1 row prefilter, bit2 lazy table
+    uint32_t flags;   // tuning switches (URMB_FLAGS): bit 5 = do not consult the coarse exception bitmap (seqc)
 };
 
 struct DevBatch {

@@ -29,8 +29,8 @@ extern "C" {
 #define URMB_E_IO (-2)        /* file error / bad UFI magic */
 #define URMB_E_CUDA (-3)      /* CUDA runtime error */
 #define URMB_E_NOMEM (-4)
-#define URMB_E_OVERFLOW (-5)  /* a per-read capacity (hits, HSPs, path runs, runs pool) was exceeded */
-#define URMB_E_UNSUPPORTED (-6) /* read longer than URMB_MAX_READ_LEN, word length > 32, ... */
+#define URMB_E_OVERFLOW (-5)  /* the caller's runs buffer is too small (urmb_map_se / urmb_map_pe) */
+#define URMB_E_UNSUPPORTED (-6) /* word length > 32, batch of more than 4 GB of bases, ... */
 #define URMB_E_NODEVICE (-7)  /* no CUDA device: there is NO CPU fallback */
 
 #define URMB_SLOTS 3
@@ -67,7 +67,8 @@ typedef struct urmb_result {
     int16_t best;       /* m_BestScore */
     int16_t second;     /* m_SecondBestScore */
     uint8_t mapq;       /* m_Mapq */
-    uint8_t flags;      /* bit0 plus strand, bit1 has top hit, bit7 capacity overflow */
+    uint8_t flags;      /* bit0 plus strand, bit1 has top hit, bit6 not searched (read or mate longer than
+                           URMB_MAX_READ_LEN), bit7 capacity overflow */
     uint8_t hit_count;
     uint8_t hsp_count;
 } urmb_result;
@@ -104,8 +105,9 @@ typedef struct urmb_index_desc {
 } urmb_index_desc;
 
 /* Kernel timings of the last launch on a slot (CUDA events on the launching streams). */
-#define URMB_KCLASSES 7 /* 0 probe, 1 seed pairing (PE) / seeds (SE), 2 first HSP alignment, 3 rows, 4 final HSP
-                           alignment, 5 pair finishing, 6 mate rescue */
+#define URMB_KCLASSES 12 /* 0 probe, 1 seed pairing (PE) / seeds (SE), 2 first HSP alignment, 3 rows (short rows), 4 final
+                            HSP alignment, 5 pair finishing, 6 mate rescue: window scan, 7 deferred long rows, 8 mate rescue:
+                            full-window DP, 9 mate rescue: pair finishing, 10-11 reserved */
 typedef struct urmb_timing {
     float probe_ms;  /* slot-probe / gather kernel */
     float search_ms; /* all search kernels on the compute stream (seed pairing, alignment, rows, finishing) */
@@ -147,6 +149,15 @@ int urmb_map_pe(urmb_ctx *c, const urmb_batch *r1, const urmb_batch *r2, urmb_re
 int urmb_submit(urmb_ctx *c, int slot, const urmb_batch *r1, const urmb_batch *r2);
 int urmb_wait(urmb_ctx *c, int slot, const urmb_result **res1, const urmb_result **res2,
               const uint16_t **runs, uint32_t *runs_used);
+/* Reads whose search exceeded a per-read capacity of the kernels (256 hits, 256 HSPs, 64 path runs per alignment; the
+ * reference grows these lists without bound, state1.cpp:190) are still reported, with bit 7 set in urmb_result.flags, and
+ * counted here: *last = such reads in the batch urmb_wait last returned for this slot, *total = over all batches of the
+ * context.  Their records may differ from the reference's; it is not an error of the batch. */
+int urmb_overflow_count(urmb_ctx *c, int slot, uint32_t *last, uint64_t *total);
+/* Reads longer than URMB_MAX_READ_LEN are not searched (the reference maps reads up to 4096 bases, xdpmem.h:6): they and
+ * their mates are reported unmapped with bit 6 set in urmb_result.flags; every other read of the batch is mapped as usual.
+ * Counts as for urmb_overflow_count. */
+int urmb_unsupported_count(urmb_ctx *c, int slot, uint32_t *last, uint64_t *total);
 /* After urmb_wait on a paired-end slot of a context created with want_second: the second hits of mate 1 / mate 2. */
 int urmb_second_hits(urmb_ctx *c, int slot, const urmb_second **s1, const urmb_second **s2);
 /* Finer-grained steps (bench.py uses them to time the kernels with inputs resident in HBM). */

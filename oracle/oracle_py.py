@@ -22,7 +22,8 @@ RESULT_DTYPE = np.dtype([
 assert RESULT_DTYPE.itemsize == 20
 
 STATS_FIELDS = ["reads", "probes", "row_calls", "row_hops", "extend_calls", "compare_bytes", "slot_hashes",
-                "dp_calls", "dp_cells", "scan_calls", "tb_poison_reads", "compare_bytes_rows"]
+                "dp_calls", "dp_cells", "scan_calls", "tb_poison_reads", "compare_bytes_rows", "row_hops_long",
+                "compare_bytes_rows_long", "dp_cells_scan"]
 
 
 class Params(C.Structure):

@@ -388,6 +388,7 @@ struct S1 {
         SetSlotsVec(RC.data(), L, SlotsM.data());
     }
 
+    bool LongPhase = false;   // statistics only: inside phase 5 / pending round 2 (second visit of rows longer than 2)
     // UFIndex::GetRow_Blob, ufindex.cpp:883-943
     unsigned GetRow_Blob(uint64 Slot, const byte *ptrBlob, uint32 *Pv) {
         if (st) st->row_calls++;
@@ -400,7 +401,7 @@ struct S1 {
             if (K > 0) {
                 T = GetTally(Slot2);
                 Pos = GetPos(Slot2);
-                if (st) st->row_hops++;
+                if (st) { st->row_hops++; if (LongPhase) st->row_hops_long++; }
             }
             Pv[K++] = Pos;
             if (K == ix.MaxIx) return K;
@@ -411,7 +412,7 @@ struct S1 {
                 uint64 SlotA = (Slot2 + StepA) % ix.SlotCount;
                 Slot2 = (SlotA + StepB) % ix.SlotCount;
                 Pv[K - 1] = GetPos(SlotA);
-                if (st) st->row_hops++;
+                if (st) { st->row_hops++; if (LongPhase) st->row_hops_long++; }
             } else {
                 byte Next = T & T_NEXT_MASK;
                 Slot2 = (Slot2 + Next) % ix.SlotCount;
@@ -496,6 +497,7 @@ struct S1 {
         const uint64 c0 = st ? st->compare_bytes : 0;
         int r = ExtendPen(SeedPosQ, SeedPosDB, Plus);
         if (st) st->compare_bytes_rows += st->compare_bytes - c0;
+        if (st && LongPhase) st->compare_bytes_rows_long += st->compare_bytes - c0;
         InRows = false;
         return r;
     }
@@ -736,6 +738,7 @@ struct S1 {
             }
         }
         if (BestScore >= MinScorePhase3) { Mapq = CalcMAPQ6(); return; }
+        LongPhase = true;
         for (int strand = 0; strand < 2; ++strand) {  // phase 5
             const bool Plus = (strand == 0);
             const byte *Bv = (Plus ? BlobP : BlobM).data();
@@ -745,6 +748,7 @@ struct S1 {
                 for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], Plus);
             }
         }
+        LongPhase = false;
         if (BestScore >= MinScorePhase4) { Mapq = CalcMAPQ6(); return; }
         for (unsigned i = 0; i < HSPCount; ++i) AlignHSP(i);  // phase 6
         Mapq = CalcMAPQ6();
@@ -877,6 +881,7 @@ struct S1 {
             if (RowLength > 2) { PendM[nM2++] = (byte)QPos; continue; }
             for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], false);
         }
+        LongPhase = true;
         for (unsigned i = 0; i < nP2; ++i) {
             unsigned QPos = PendP[i];
             unsigned RowLength = GetRow_Blob(SlotsP[QPos], BlobP.data() + 5 * QPos, PosVec.data());
@@ -887,6 +892,7 @@ struct S1 {
             unsigned RowLength = GetRow_Blob(SlotsM[QPos], BlobM.data() + 5 * QPos, PosVec.data());
             for (unsigned r = 0; r < RowLength; ++r) ExtendPenRow(QPos, PosVec[r], false);
         }
+        LongPhase = false;
         int B = std::max(BestScore, BestHSPScore) - 8;
         for (unsigned i = 0; i < HSPCount; ++i) {
             if (HSPs[i].score < B) continue;
@@ -933,7 +939,9 @@ struct S1 {
         std::vector<byte> Win(DBSegLength);
         for (unsigned i = 0; i < DBSegLength; ++i) Win[i] = ix.T((uint64)DBPos + i);
         std::string Path;
+        const uint64 cells0 = st ? st->dp_cells : 0;
         float Score = Viterbi(P, Seq(Plus), QL, Win.data(), DBSegLength, true, true, Path, st);
+        if (st) st->dp_cells_scan += st->dp_cells - cells0;
         if (Score >= QL / 3.0) {
             unsigned LeftICount = TrimLeftIs(Path);
             TrimRightIs(Path);
@@ -1160,6 +1168,8 @@ void AddStats(uo_stats *dst, const uo_stats &s) {
     dst->dp_calls += s.dp_calls; dst->dp_cells += s.dp_cells; dst->scan_calls += s.scan_calls;
     dst->tb_poison_reads += s.tb_poison_reads;
     dst->compare_bytes_rows += s.compare_bytes_rows;
+    dst->row_hops_long += s.row_hops_long; dst->compare_bytes_rows_long += s.compare_bytes_rows_long;
+    dst->dp_cells_scan += s.dp_cells_scan;
 }
 
 // ---- CIGAR (cigar.cpp:4-41, 141-199; state1.cpp:717-734) --------------------------------

@@ -54,6 +54,9 @@ typedef struct uo_stats {
     uint64_t scan_calls;
     uint64_t tb_poison_reads; /* traceback reads of cells the current call never wrote */
     uint64_t compare_bytes_rows; /* part of C spent on positions that came out of GetRow_Blob */
+    uint64_t row_hops_long;      /* part of H spent on the second visit of rows longer than 2 (phase 5 / pending round 2) */
+    uint64_t compare_bytes_rows_long; /* part of compare_bytes_rows spent there */
+    uint64_t dp_cells_scan;      /* part of dp_cells spent in State1::Scan's full-window Viterbi (mate rescue) */
 } uo_stats;
 
 uo_index *uo_index_open(const char *ufi_path);   /* mmap, ufindexio.cpp:60-115 */

@@ -109,8 +109,11 @@ def _fastq_records(path):
     lines = data.split(b"\n")
     if lines and lines[-1] == b"":
         lines.pop()
+    n_all = len(lines)
     while lines and lines[-1] == b"":
         lines.pop()
+    if len(lines) % 4 and len(lines) + 4 - len(lines) % 4 <= n_all:   # empty sequence / quality lines of the last record
+        lines += [b""] * (4 - len(lines) % 4)
     assert len(lines) % 4 == 0
     return [(lines[i][1:], lines[i + 1], lines[i + 3]) for i in range(0, len(lines), 4)]
 
@@ -121,7 +124,8 @@ def _dump(cli, fq, out, extra=()):
     return [tuple(l.split(b"\t")) for l in open(out, "rb").read().split(b"\n")[:-1]]
 
 
-@pytest.mark.parametrize("variant", ["lf", "crlf", "no_final_lf", "trailing_blank", "gz", "ragged", "one"])
+@pytest.mark.parametrize("variant", ["lf", "crlf", "no_final_lf", "trailing_blank", "gz", "ragged", "one", "empty_last",
+                                     "empty_last_blank"])
 def test_fastq_reader_matches_plain_parse(cli, golden_dir, tmp_path, variant):
     src = open(os.path.join(golden_dir, "se.fq"), "rb").read()
     fq = tmp_path / "in.fq"
@@ -136,6 +140,10 @@ def test_fastq_reader_matches_plain_parse(cli, golden_dir, tmp_path, variant):
         src = b"".join(b"@%s extra words\n%s\n+anything\n%s\n" % (l, s[:i % 151], q[:i % 151]) for i, (l, s, q) in enumerate(recs))
     elif variant == "one":
         src = b"@only\nACGT\n+\nIIII"
+    elif variant == "empty_last":   # a last record with empty sequence and quality lines is a record (fastqseqsource.cpp:9-116)
+        src = src + b"@r\n\n+\n\n"
+    elif variant == "empty_last_blank":
+        src = src + b"@r\n\n+\n\n\n\n"
     if variant == "gz":
         fq = tmp_path / "in.fq.gz"
         with gzip.open(fq, "wb") as g:
@@ -162,6 +170,7 @@ def test_fastq_reader_pairs_and_errors(cli, golden_dir, tmp_path):
     good = b"@a\nACGT\n+\nIIII\n"
     for bad, msg in ((good + b"b\nACGT\n+\nIIII\n", "expected '@'"),
                      (good + b"@b\nACGT\n+\nIII\n", "4 bases, 3 quals"),
+                     (good + b"@b x\nACGT\n+\nIII\n", "file %s label b x" % (tmp_path / "bad.fq")),
                      (good + b"@b\nAC-T\n+\nIIII\n", "Invalid sequence letter '-'"),
                      (good + b"@b\nAC\x01T\n+\nIIII\n", "Non-printing byte 0x01"),
                      (good + b"\n" + good, "Empty line nr 5"),

@@ -149,10 +149,21 @@ def test_ragged_and_edge_reads(eng, oracle, mid_env):
     res, runs = ctx.map_se(b.seqs, b.offs)
     ro, uo = oracle.map_se(oix, b, threads=4)
     assert_same(ro, uo, res, runs)
-    too_long = np.full(300, ord("A"), dtype=np.uint8)
-    with pytest.raises(eng.UrmbError) as e:
-        ctx.map_se(too_long, np.array([0, 300], dtype=np.uint32))
-    assert e.value.code == -6
+    # reads longer than URMB_MAX_READ_LEN are handled per read: reported unmapped with flag bit 6, the rest of the batch
+    # is mapped exactly as without them (single-end and paired: the mate of an over-long read is not searched either)
+    L0 = int(offs[40])
+    long_read = g.asc[1000:1300].copy()
+    mixed = np.concatenate([b.seqs[:L0], long_read, b.seqs[L0:]])
+    moffs = np.concatenate([offs[:41], np.array(offs[40:]) + 300]).astype(np.uint32)
+    r2_, u2_ = ctx.map_se(mixed, moffs)
+    assert r2_[40]["flags"] == 0x40 and r2_[40]["db_pos"] == 0xFFFFFFFF and r2_[40]["mapq"] == 0
+    assert canon(np.delete(r2_, 40), u2_) == canon(res, runs)
+    assert ctx.unsupported_count() == (1, 1) and ctx.overflow_count()[1] == 0
+    pr1, pr2, pu = ctx.map_pe(mixed, moffs, np.concatenate([b.seqs[:L0], b.seqs[:50], b.seqs[L0:]]),
+                              np.concatenate([offs[:41], np.array(offs[40:]) + 50]).astype(np.uint32))
+    assert pr1[40]["flags"] == 0x40 and pr2[40]["flags"] == 0x40 and ctx.unsupported_count() == (2, 3)
+    q1, q2, qu = ctx.map_pe(b.seqs, b.offs, b.seqs, b.offs)
+    assert canon(np.delete(pr1, 40), pu) == canon(q1, qu) and canon(np.delete(pr2, 40), pu) == canon(q2, qu)
     ctx.close()
 
 

@@ -1,0 +1,76 @@
+#!/bin/bash
+# One GPU-box visit of round 2.  Usage (under gpurun): bash tools/gpu_round2.sh <tag> [step ...]
+#   tests      pytest -m gpu
+#   smoke      __graft_entry__.smoke()
+#   tiny       bench.py on a 20 Mb genome with every leg (checks the plumbing in a minute)
+#   bench      the default bench line (all configurations, reference binary, CLI)
+#   benchq     kernels only (no CPU legs, no other configurations)
+#   benchref   the reference arm
+#   launches   ncu launch list of a short bench run (every kernel)
+#   ncufull    one `ncu --set full` capture of every kernel class of one step (CSV exports made on the box)
+#   sanitize   compute-sanitizer memcheck + racecheck on the golden sets
+#   ab         per-kernel step times of the current build (tools/step_sweep.py)
+TAG=${1:-run}; shift
+WHAT=${*:-tests bench}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/smi.txt 2>&1
+KREGEX='probe_kernel|seed_kernel|pair_kernel|align_kernel|rows_kernel|rows_long_kernel|finish_kernel|rescue'
+for w in $WHAT; do
+case $w in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+  tail -5 $OUT/pytest_gpu.log ;;
+smoke)
+  timeout 600 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log ;;
+tiny)
+  timeout 900 python bench.py --genome-len 20000000 --pairs-per-step 20000 --config-units-scale 0.02 --steps 3 --cpu-sample-pairs 20000 \
+      > $OUT/bench_tiny.json 2> $OUT/bench_tiny.log; echo "tiny exit $?"
+  tail -c 1500 $OUT/bench_tiny.log; head -c 600 $OUT/bench_tiny.json; echo ;;
+bench)
+  timeout 1700 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.log; echo "bench exit $?"
+  tail -c 3000 $OUT/bench.log; head -c 1200 $OUT/bench.json; echo ;;
+benchq)
+  timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-configs > $OUT/benchq.json 2> $OUT/benchq.log; echo "benchq exit $?"
+  tail -c 800 $OUT/benchq.log ;;
+benchcfg)
+  timeout 1200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/benchcfg.json 2> $OUT/benchcfg.log; echo "benchcfg exit $?"
+  grep -E "config|main workload" $OUT/benchcfg.log ;;
+benchref)
+  timeout 1500 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_ref.json 2> $OUT/bench_ref.log; echo "benchref exit $?"
+  tail -c 1000 $OUT/bench_ref.log; cat $OUT/bench_ref.json ;;
+launches)
+  # launch list of the same command (short): per-launch durations, cold-cache and serialised
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$KREGEX" -c 400 --csv \
+      --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs > $OUT/ncu_launch_bench.log 2>&1
+  echo "ncu launches exit $?"
+  python tools/launch_summary.py $OUT/launches.csv > $OUT/launch_summary.txt 2>&1; cat $OUT/launch_summary.txt ;;
+ncufull)
+  # 250 k pairs per step = one chunk: every step launches each kernel class once, in a fixed order; skip the warm-up
+  # steps and capture one launch of every class (finish_kernel is excluded: 0.3 ms)
+  NK=${NCU_KERNELS:-'probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue'}
+  NSKIP=${NCU_SKIP:-24}
+  NCOUNT=${NCU_COUNT:-8}
+  timeout 1700 ncu --set full --clock-control none --import-source on -k regex:"$NK" -s $NSKIP -c $NCOUNT -f -o $OUT/full \
+      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs --pairs-per-step 250000 > $OUT/ncu_full.log 2>&1
+  echo "ncu full exit $?"
+  ncu -i $OUT/full.ncu-rep --page raw --csv > $OUT/full_raw.csv 2>/dev/null
+  ncu -i $OUT/full.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null | gzip -9 > $OUT/full_src.csv.gz
+  ls -la $OUT/full.ncu-rep
+  if [ $(stat -c %s $OUT/full.ncu-rep) -gt 45000000 ]; then rm -f $OUT/full.ncu-rep; echo "report dropped (too large), CSV exports kept"; fi ;;
+sanitize)
+  timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_memcheck_smoke.log 2>&1
+  echo "memcheck smoke exit $?"; tail -4 $OUT/sanitizer_memcheck_smoke.log
+  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "golden" \
+      > $OUT/sanitizer_memcheck_golden.log 2>&1
+  echo "memcheck golden exit $?"; tail -4 $OUT/sanitizer_memcheck_golden.log
+  timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_racecheck_smoke.log 2>&1
+  echo "racecheck smoke exit $?"; tail -4 $OUT/sanitizer_racecheck_smoke.log
+  timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "golden" \
+      > $OUT/sanitizer_racecheck_golden.log 2>&1
+  echo "racecheck golden exit $?"; tail -4 $OUT/sanitizer_racecheck_golden.log ;;
+ab)
+  timeout 900 python tools/step_sweep.py > $OUT/step_sweep.log 2>&1; echo "step_sweep exit $?"; tail -12 $OUT/step_sweep.log ;;
+esac
+done
+ls -la $OUT

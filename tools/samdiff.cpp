@@ -1,7 +1,8 @@
 // samdiff a.sam b.sam -- order-independent record comparison of two SAM files (header lines: @SQ compared in order,
 // @PG ignored).  Every record line is reduced to a 128-bit hash; the two sorted hash multisets are merged.
-// Prints one JSON object.  Used by tools/cli_scale.py to compare the drop-in's SAM file with the reference's at the
-// full BASELINE size (20 M records), where a Python dict comparison would need tens of GB.
+// Prints one JSON object.  Used by tools/cli_scale.py and bench.py to compare the drop-in's SAM file with the reference's
+// at the full BASELINE size (20 M records), where a Python dict comparison would need tens of GB.  Records whose QNAME
+// has the form <group>.<rest> are also counted per group ("groups": bench.py maps several workloads in one run).
 #include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -11,11 +12,26 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
-struct H { uint64_t a, b; bool operator<(const H &o) const { return a != o.a ? a < o.a : b < o.b; } bool operator==(const H &o) const { return a == o.a && b == o.b; } };
+struct H { uint64_t a, b; uint32_t g; bool operator<(const H &o) const { return a != o.a ? a < o.a : b < o.b; } bool operator==(const H &o) const { return a == o.a && b == o.b; } };
+
+static std::mutex g_mu;
+static std::vector<std::string> g_groups{std::string()};   // group names in order of first appearance; [0] = "" (no group);
+                                                           // at most 16 groups are told apart, the rest counts under ""
+static uint32_t group_of(const char *p, size_t n) {   // QNAME up to the first '.', "" when there is none
+    size_t k = 0;
+    while (k < n && p[k] != '\t' && p[k] != '.') ++k;
+    std::string name = (k < n && p[k] == '.') ? std::string(p, k) : std::string();
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t i = 0; i < g_groups.size(); ++i) if (g_groups[i] == name) return (uint32_t)i;
+    if (g_groups.size() >= 16) return 0;
+    g_groups.push_back(name);
+    return (uint32_t)g_groups.size() - 1;
+}
 
 static inline uint64_t mix(uint64_t h) { h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33; return h; }
 
@@ -33,7 +49,7 @@ static H hash_line(const char *p, size_t n) {
     memcpy(&w, p + i, n - i);
     a = mix(a ^ w ^ 0xabcdefull);
     b = mix(b + w);
-    return H{a, b};
+    return H{a, b, 0};
 }
 
 struct File {
@@ -71,10 +87,22 @@ static bool load(const char *path, File &f) {
             if (t > 0) { while (lo < f.n && f.p[lo - 1] != '\n') ++lo; }
             if (t + 1 < nt) { while (hi < f.n && f.p[hi - 1] != '\n') ++hi; } else hi = f.n;
             std::vector<H> v;
+            uint32_t cur = 0;
+            size_t curlen = (size_t)-1;   // length of the current group's name (records of a group are contiguous)
+            const char *curp = nullptr;
             while (lo < hi) {
                 const char *e = (const char *)memchr(f.p + lo, '\n', f.n - lo);
                 size_t len = e ? (size_t)(e - (f.p + lo)) : f.n - lo;
-                if (len) v.push_back(hash_line(f.p + lo, len));
+                if (len) {
+                    H h = hash_line(f.p + lo, len);
+                    const char *q = f.p + lo;
+                    size_t k = 0;
+                    while (k < len && q[k] != '\t' && q[k] != '.') ++k;
+                    const size_t gl = (k < len && q[k] == '.') ? k : 0;
+                    if (curlen != gl || (gl && memcmp(curp, q, gl) != 0)) { cur = group_of(q, len); curlen = gl; curp = q; }
+                    h.g = cur;
+                    v.push_back(h);
+                }
                 lo += len + 1;
             }
             parts[t].swap(v);
@@ -90,13 +118,20 @@ int main(int argc, char **argv) {
     File a, b;
     if (!load(argv[1], a) || !load(argv[2], b)) { fprintf(stderr, "cannot read input\n"); return 2; }
     size_t i = 0, j = 0, same = 0;
+    std::vector<size_t> ga(g_groups.size(), 0), gb(g_groups.size(), 0), gs(g_groups.size(), 0);
+    for (auto &h : a.recs) ++ga[h.g];
+    for (auto &h : b.recs) ++gb[h.g];
     while (i < a.recs.size() && j < b.recs.size()) {
-        if (a.recs[i] == b.recs[j]) { ++same; ++i; ++j; }
+        if (a.recs[i] == b.recs[j]) { ++same; ++gs[a.recs[i].g]; ++i; ++j; }
         else if (a.recs[i] < b.recs[j]) ++i;
         else ++j;
     }
-    printf("{\"records_a\": %zu, \"records_b\": %zu, \"identical\": %zu, \"pct\": %.6f, \"header_equal\": %s}\n", a.recs.size(),
+    printf("{\"records_a\": %zu, \"records_b\": %zu, \"identical\": %zu, \"pct\": %.6f, \"header_equal\": %s, \"groups\": {", a.recs.size(),
            b.recs.size(), same, a.recs.empty() ? 0.0 : 100.0 * same / std::max(a.recs.size(), b.recs.size()),
            a.sq == b.sq ? "true" : "false");
+    for (size_t g = 0; g < g_groups.size(); ++g)
+        printf("%s\"%s\": {\"records_a\": %zu, \"records_b\": %zu, \"identical\": %zu, \"pct\": %.6f}", g ? ", " : "", g_groups[g].c_str(),
+               ga[g], gb[g], gs[g], std::max(ga[g], gb[g]) ? 100.0 * gs[g] / std::max(ga[g], gb[g]) : 0.0);
+    printf("}}\n");
     return 0;
 }

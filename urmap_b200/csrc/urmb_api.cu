@@ -80,6 +80,9 @@ extern "C" int urmb_index_load_host(const char *path, urmb_index_host **out) {
     }
     ok = ok && (u32() == 0x55464932u);  // 'UFI2'
     h->blob = m + o;
+    // header sanity before any size arithmetic (a corrupt slot count must not wrap 5 * slot_count)
+    ok = ok && h->word_length >= 1 && h->word_length <= 32 && h->max_ix >= 1 && h->slot_count >= 2 &&
+         o <= h->map_len && h->slot_count <= (h->map_len - o) / 5;
     if (ok && need(5 * (size_t)h->slot_count)) o += 5 * (size_t)h->slot_count;
     ok = ok && (u32() == 0x55464933u);  // 'UFI3'
     h->seq = m + o;
@@ -155,6 +158,8 @@ struct Slot {
     DevBatch batch{};
     size_t seq_bytes = 0;
     bool staged = false, launched = false, downloaded = false;
+    bool counted = false;             // the batch's overflow / too-long reads went into the context totals
+    std::vector<uint32_t> too_long;   // reads of the staged batch that were not searched (longer than URMB_MAX_READ_LEN, or their mate is)
 };
 
 struct urmb_ctx {
@@ -183,6 +188,8 @@ struct urmb_ctx {
     uint32_t chunk_pairs = 524288; // URMB_CHUNK_PAIRS (step time at 1 M pairs: 92.9 / 86.0 / 82.5 / 82.1 ms for 128k / 256k / 512k / 1M)
     Slot slots[URMB_SLOTS];
     uint64_t launches = 0;
+    uint64_t overflow_total = 0;   // reads that exceeded a per-read capacity, over all finished batches
+    uint64_t unsupported_total = 0; // reads not searched because they (or their mates) are longer than URMB_MAX_READ_LEN
     std::string err;
 };
 
@@ -537,32 +544,56 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     Slot &s = c->slots[si];
     const uint32_t n = r1->n, nreads = r2 ? 2 * n : n;
     const size_t b1 = n ? r1->offs[n] - r1->offs[0] : 0, b2 = (r2 && n) ? r2->offs[n] - r2->offs[0] : 0;
-    const size_t nbytes = b1 + b2;
+    size_t nbytes = b1 + b2;
     if (nbytes >= 0xFFFFFFF0ull) return fail(c, URMB_E_UNSUPPORTED, "batch larger than 4 GB of bases");
     // previous use of this slot must have drained
     CK(cudaStreamSynchronize(s.copy));
-    const bool direct = n > 0 && !getenv("URMB_NO_DIRECT_H2D") && is_pinned_host(r1->seqs) && (!r2 || is_pinned_host(r2->seqs));
+    bool direct = n > 0 && !getenv("URMB_NO_DIRECT_H2D") && is_pinned_host(r1->seqs) && (!r2 || is_pinned_host(r2->seqs));
     if (!direct && (rc = grow_host(c, s.h_seqs, s.h_seqs_cap, nbytes + 64))) return rc;
     if ((rc = grow_host(c, s.h_offs, s.h_offs_cap, (size_t)nreads + 1))) return rc;
     if ((rc = grow_dev(c, s.d_seqs, s.d_seqs_cap, nbytes + 64))) return rc;
     if ((rc = grow_dev(c, s.d_offs, s.d_offs_cap, (size_t)nreads + 1))) return rc;
     uint32_t maxlen = 0;
+    s.too_long.clear();
     if (n) {
+        for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r1->offs[i + 1] - r1->offs[i]);
+        if (r2) for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r2->offs[i + 1] - r2->offs[i]);
+    }
+    if (maxlen > (uint32_t)kMaxLen) {
+        // Reads longer than URMB_MAX_READ_LEN are handled per read, not per batch: they (and their mates) go to the
+        // device as empty reads, come back unmapped with bit 6 of urmb_result.flags set, and are counted
+        // (urmb_unsupported_count).  The rest of the batch is mapped as usual.  The bases are staged read by read.
+        direct = false;
+        if ((rc = grow_host(c, s.h_seqs, s.h_seqs_cap, nbytes + 64))) return rc;
+        size_t o = 0;
+        maxlen = 0;
+        for (int mate = 0; mate < (r2 ? 2 : 1); ++mate) {
+            const urmb_batch *rb = mate ? r2 : r1;
+            const urmb_batch *ob = mate ? r1 : r2;   // the other mate (null for single-end)
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint32_t L = rb->offs[i + 1] - rb->offs[i];
+                const bool skip = L > (uint32_t)kMaxLen || (ob && ob->offs[i + 1] - ob->offs[i] > (uint32_t)kMaxLen);
+                s.h_offs[(size_t)mate * n + i] = (uint32_t)o;
+                if (skip) { s.too_long.push_back(mate * n + i); continue; }
+                memcpy(s.h_seqs + o, rb->seqs + rb->offs[i], L);
+                o += L;
+                maxlen = std::max(maxlen, L);
+            }
+        }
+        s.h_offs[nreads] = (uint32_t)o;
+        nbytes = o;
+    } else if (n) {
         if (!direct) memcpy(s.h_seqs, r1->seqs + r1->offs[0], b1);
         const uint32_t o0 = r1->offs[0];
         for (uint32_t i = 0; i <= n; ++i) s.h_offs[i] = r1->offs[i] - o0;
-        for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r1->offs[i + 1] - r1->offs[i]);
         if (r2) {
             if (!direct) memcpy(s.h_seqs + b1, r2->seqs + r2->offs[0], b2);
             const uint32_t p0 = r2->offs[0];
             for (uint32_t i = 0; i <= n; ++i) s.h_offs[n + i] = (uint32_t)b1 + (r2->offs[i] - p0);
-            for (uint32_t i = 0; i < n; ++i) maxlen = std::max(maxlen, r2->offs[i + 1] - r2->offs[i]);
         }
     } else {
         s.h_offs[0] = 0;
     }
-    if (maxlen > (uint32_t)kMaxLen)
-        return fail(c, URMB_E_UNSUPPORTED, "read longer than URMB_MAX_READ_LEN (256) in batch");
     const uint32_t W = c->ix.word_len;
     const uint32_t qwc = maxlen >= W ? maxlen - W + 1 : 1;
     DevBatch &b = s.batch;
@@ -622,6 +653,7 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     s.staged = true;
     s.launched = false;
     s.downloaded = false;
+    s.counted = false;
     return URMB_OK;
 }
 
@@ -792,12 +824,24 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
     if (res2) *res2 = s.batch.paired ? s.h_res + s.batch.n_units : nullptr;
     if (runs) *runs = s.h_runs;
     if (runs_used) *runs_used = used;
-    if (s.h_counters[1] != 0) {
-        char msg[160];
-        snprintf(msg, sizeof msg, "%u reads exceeded a per-read capacity (hits %d, HSPs %d, path runs %d)",
-                 s.h_counters[1], kHitCap, kHspCap, kRunCap);
-        return fail(c, URMB_E_OVERFLOW, msg);
-    }
+    for (uint32_t r : s.too_long) s.h_res[r].flags |= 0x40;   // unmapped because the read (or its mate) is too long
+    if (!s.counted) { c->unsupported_total += s.too_long.size(); c->overflow_total += s.h_counters[CT_OVERFLOW]; s.counted = true; }
+    // Reads that exceeded a per-read capacity carry bit 7 in urmb_result.flags and are counted (urmb_overflow_count): the
+    // batch itself is valid, so this is not an error (the reference grows its lists without bound, state1.cpp:190).
+    return URMB_OK;
+}
+
+extern "C" int urmb_unsupported_count(urmb_ctx *c, int si, uint32_t *last, uint64_t *total) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    if (last) *last = (uint32_t)c->slots[si].too_long.size();
+    if (total) *total = c->unsupported_total;
+    return URMB_OK;
+}
+
+extern "C" int urmb_overflow_count(urmb_ctx *c, int si, uint32_t *last, uint64_t *total) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    if (last) *last = c->slots[si].h_counters ? c->slots[si].h_counters[CT_OVERFLOW] : 0;
+    if (total) *total = c->overflow_total;
     return URMB_OK;
 }
 
@@ -852,7 +896,7 @@ extern "C" int urmb_map_se(urmb_ctx *c, const urmb_batch *in, urmb_result *out, 
     const uint16_t *rr;
     uint32_t used = 0;
     rc = urmb_wait(c, 0, &r1, nullptr, &rr, &used);
-    if (rc && rc != URMB_E_OVERFLOW) return rc;
+    if (rc) return rc;
     copy_out(c, in->n, r1, out);
     if (runs_used) *runs_used = used;
     if (used > runs_cap) return fail(c, URMB_E_OVERFLOW, "caller's runs buffer too small");
@@ -869,7 +913,7 @@ extern "C" int urmb_map_pe(urmb_ctx *c, const urmb_batch *r1, const urmb_batch *
     const uint16_t *rr;
     uint32_t used = 0;
     rc = urmb_wait(c, 0, &a, &b, &rr, &used);
-    if (rc && rc != URMB_E_OVERFLOW) return rc;
+    if (rc) return rc;
     copy_out(c, r1->n, a, out1);
     copy_out(c, r1->n, b, out2);
     if (runs_used) *runs_used = used;

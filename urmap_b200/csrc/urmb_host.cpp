@@ -384,8 +384,12 @@ class FastqReader {  // FASTQSeqSource::GetNextLo, fastqseqsource.cpp:9-116
             want = want + want / 2 + (1 << 20);
         }
         size_t lines = nl_.size();
-        if (eof)   // empty lines are allowed at the end of the file only
+        if (eof) {   // empty lines are allowed at the end of the file only ...
+            const size_t all = lines;
             while (lines > 0 && LineLen(lines - 1) == 0) --lines;
+            // ... but the empty sequence / quality lines of a last record ("@r", "", "+", "") belong to it
+            if (lines % 4 != 0 && lines + (4 - lines % 4) <= all) lines += 4 - lines % 4;
+        }
         uint32_t nrec = (uint32_t)std::min<size_t>(lines / 4, max_reads);
         // an empty line where a record should start: fine if nothing but empty lines follows, fatal otherwise
         const uint32_t cand = (uint32_t)std::min<size_t>((lines + 3) / 4, max_reads);
@@ -627,7 +631,8 @@ class FastqReader {  // FASTQSeqSource::GetNextLo, fastqseqsource.cpp:9-116
             const unsigned ln = line_base_ + 4 * first.rec;
             if (first.kind == 1) Die("Bad line %u in FASTQ file '%s': expected '@'", ln + 1, path_.c_str());
             if (first.kind == 2)
-                Die("Bad FASTQ record: %u bases, %u quals line %u file %s", first.a, first.b, ln + 4, path_.c_str());
+                Die("Bad FASTQ record: %u bases, %u quals line %u file %s label %.*s", first.a, first.b, ln + 4, path_.c_str(),
+                    (int)b.lablen[first.rec], (const char *)b.Label(first.rec));
             const uint8_t *s = b.Seq(first.rec);
             for (unsigned i = 0; i < b.Len(first.rec); ++i)
                 if (!isalpha(s[i])) {
@@ -876,9 +881,20 @@ static void FormatSE(const Contigs &C, const HostBatch &b, const urmb_result *re
     }
 }
 
+// sam_active: -samout was given.  State2::Output2 (output2.cpp:10-16) runs OutputSAM2 -> OutputTab2 -> UpdateHitStats, and only
+// OutputSAM2 (when a SAM file is open) calls SetMappedPos, which clears m_TopHit of a mate that overhangs its contig
+// (SetSAM_Unmapped then zeroes m_Mapq): the tabbed line and the hit statistics see that cleared state.  Without -samout they
+// see the raw search result.
 static void FormatPE(const Contigs &C, const HostBatch &b1, const HostBatch &b2, const urmb_result *r1,
                      const urmb_result *r2, const uint16_t *runs, uint32_t lo, uint32_t hi, unsigned minq, OutBuf &o,
-                     HitCounters &hc) {
+                     HitCounters &hc, bool sam_active) {
+    if (!sam_active) {
+        for (uint32_t i = lo; i < hi; ++i) {
+            UpdateHitStats(hc, (r1[i].flags & 2) != 0, r1[i].mapq, minq);
+            UpdateHitStats(hc, (r2[i].flags & 2) != 0, r2[i].mapq, minq);
+        }
+        return;
+    }
     for (uint32_t i = lo; i < hi; ++i) {  // State2::SetSAM2, output2.cpp:71-132
         const unsigned L1 = b1.Len(i), L2 = b2.Len(i);
         Mapped m1 = SetMappedPos(C, r1[i], L1), m2 = SetMappedPos(C, r2[i], L2);
@@ -965,19 +981,23 @@ static unsigned TabTemplateLength(const TabHit &h1, const TabHit &h2, unsigned L
 }
 
 static void FormatTab2(const Contigs &C, const HostBatch &b1, const HostBatch &b2, const urmb_result *r1, const urmb_result *r2,
-                       const urmb_second *s1, const urmb_second *s2, uint32_t lo, uint32_t hi, OutBuf &o) {
+                       const urmb_second *s1, const urmb_second *s2, uint32_t lo, uint32_t hi, OutBuf &o, bool sam_active) {
     for (uint32_t i = lo; i < hi; ++i) {
-        const TabHit t1{(r1[i].flags & 2) != 0, r1[i].db_pos, (r1[i].flags & 1) != 0, r1[i].score};
-        const TabHit t2{(r2[i].flags & 2) != 0, r2[i].db_pos, (r2[i].flags & 1) != 0, r2[i].score};
+        // after OutputSAM2 a mate whose top hit overhangs its contig has no top hit and MAPQ 0 (see FormatPE)
+        const bool has1 = sam_active ? SetMappedPos(C, r1[i], b1.Len(i)).idx >= 0 : (r1[i].flags & 2) != 0;
+        const bool has2 = sam_active ? SetMappedPos(C, r2[i], b2.Len(i)).idx >= 0 : (r2[i].flags & 2) != 0;
+        const unsigned mq1 = (sam_active && !has1) ? 0u : r1[i].mapq, mq2 = (sam_active && !has2) ? 0u : r2[i].mapq;
+        const TabHit t1{has1, r1[i].db_pos, (r1[i].flags & 1) != 0, r1[i].score};
+        const TabHit t2{has2, r2[i].db_pos, (r2[i].flags & 1) != 0, r2[i].score};
         const TabHit u1{(s1[i].flags & 2) != 0, s1[i].db_pos, (s1[i].flags & 1) != 0, s1[i].score};
         const TabHit u2{(s2[i].flags & 2) != 0, s2[i].db_pos, (s2[i].flags & 1) != 0, s2[i].score};
         AppendQName(o, b1.Label(i), b1.lablen[i]);   // State1::GetPairLabel, state1.cpp:762-778
         o.push_back('\t');
         TabPairPos(C, o, t1, t2);
         o.push_back('\t');
-        put_u(o, r1[i].mapq);
+        put_u(o, mq1);
         o.push_back(',');
-        put_u(o, r2[i].mapq);
+        put_u(o, mq2);
         o.push_back('\t');
         if (u1.has) TabPairPos(C, o, u1, u2); else o.push_back('*');
         if (t1.has && t2.has && u1.has && u2.has) {   // State2::GetInfoStr
@@ -1252,11 +1272,11 @@ static int CmdMap(const Opts &o, bool paired) {
                 hcs[t] = HitCounters();
                 uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
                 out.reserve(SamTextEstimate(*job->b1, lo, hi) + (paired ? SamTextEstimate(*job->b2, lo, hi) : 0));
-                if (paired) FormatPE(C, *job->b1, *job->b2, r1, r2, runs, lo, hi, o.minq, out, hcs[t]);
+                if (paired) FormatPE(C, *job->b1, *job->b2, r1, r2, runs, lo, hi, o.minq, out, hcs[t], sink.active());
                 else FormatSE(C, *job->b1, r1, runs, lo, hi, o.minq, out, hcs[t]);
                 if (want_tab) {
                     ts->tab[t].clear();
-                    FormatTab2(C, *job->b1, *job->b2, r1, r2, job->second.data(), job->second.data() + n, lo, hi, ts->tab[t]);
+                    FormatTab2(C, *job->b1, *job->b2, r1, r2, job->second.data(), job->second.data() + n, lo, hi, ts->tab[t], sink.active());
                 }
             });
             for (int t = 0; t < nthreads; ++t) {
@@ -1361,6 +1381,24 @@ static int CmdMap(const Opts &o, bool paired) {
     Progress("%16s  Mapped Q>=%u (%.1f%%)\n", Commas(total.accept).c_str(), o.minq, pct(total.accept));
     Progress("%16s  Mapped Q< %u (%.1f%%)\n", Commas(total.reject).c_str(), o.minq, pct(total.reject));
     Progress("%16s  Unmapped (%.1f%%)\n\n", Commas(total.nohit).c_str(), pct(total.nohit));
+    uint64_t overflowed = 0;
+    for (auto c : ctxs) {
+        uint64_t t = 0;
+        urmb_overflow_count(c, 0, nullptr, &t);
+        overflowed += t;
+    }
+    uint64_t too_long = 0;
+    for (auto c : ctxs) {
+        uint64_t t = 0;
+        urmb_unsupported_count(c, 0, nullptr, &t);
+        too_long += t;
+    }
+    if (too_long)
+        Progress("\nWARNING: %llu read(s) longer than %d bases (or mates of such reads) were not searched and are reported "
+                 "unmapped\n\n", (unsigned long long)too_long, URMB_MAX_READ_LEN);
+    if (overflowed)
+        Progress("\nWARNING: %llu read(s) exceeded a per-read capacity of the GPU search (hit / HSP / path lists); their records "
+                 "are reported but may differ from urmap's\n\n", (unsigned long long)overflowed);
     if (g_log) fclose(g_log);
     fflush(nullptr);
     if (!getenv("URMB_TEARDOWN")) _exit(0);   // the output is complete: leave the 70 GB of mappings and device memory to the OS
@@ -1734,7 +1772,7 @@ static int CmdSamBench(const Opts &o) {
                 outs[t].clear();
                 uint32_t lo = (uint32_t)((uint64_t)n1 * t / nt), hi = (uint32_t)((uint64_t)n1 * (t + 1) / nt);
                 outs[t].reserve(SamTextEstimate(a, lo, hi) + (rd2 ? SamTextEstimate(b, lo, hi) : 0));
-                if (rd2) FormatPE(C, a, b, res.data(), res.data() + n1, nullptr, lo, hi, 10, outs[t], hcs[t]);
+                if (rd2) FormatPE(C, a, b, res.data(), res.data() + n1, nullptr, lo, hi, 10, outs[t], hcs[t], true);
                 else FormatSE(C, a, res.data(), nullptr, lo, hi, 10, outs[t], hcs[t]);
             });
             fprintf(stderr, "  rep %d: %.3fs\n", rep, now_s() - r0);
@@ -1744,7 +1782,7 @@ static int CmdSamBench(const Opts &o) {
             outs[t].clear();
             uint32_t lo = (uint32_t)((uint64_t)n1 * t / nt), hi = (uint32_t)((uint64_t)n1 * (t + 1) / nt);
             outs[t].reserve(SamTextEstimate(a, lo, hi) + (rd2 ? SamTextEstimate(b, lo, hi) : 0));
-            if (rd2) FormatPE(C, a, b, res.data(), res.data() + n1, nullptr, lo, hi, 10, outs[t], hcs[t]);
+            if (rd2) FormatPE(C, a, b, res.data(), res.data() + n1, nullptr, lo, hi, 10, outs[t], hcs[t], true);
             else FormatSE(C, a, res.data(), nullptr, lo, hi, 10, outs[t], hcs[t]);
         });
         double t2 = now_s();

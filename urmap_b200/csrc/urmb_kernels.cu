@@ -2666,7 +2666,7 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
             URMB_TRY(launch_one(seed_kernel_se, 1, tr, A, SmemPlan{1, 1, 0}, cnt, R, stream, sm_count, warps_used));
             URMB_TRY(launch_one(align_kernel_se3, 2, tr, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
             URMB_TRY(launch_one(rows_kernel_se, 3, tr, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
-            URMB_TRY(launch_one(rows_long_kernel_se, 3, tr, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
+            URMB_TRY(launch_one(rows_long_kernel_se, 7, tr, A, SmemPlan{1, 0, 0}, cnt, R, stream, sm_count, nullptr));
             URMB_TRY(launch_one(align_kernel_se6, 4, tr, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
             n += 5;
         }
@@ -2684,7 +2684,7 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
         URMB_TRY(launch_one(pair_kernel, 1, tr, A, SmemPlan{2, 1, 0}, cnt, R, stream, sm_count, warps_used));
         URMB_TRY(launch_one(align_kernel_a, 2, tr, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
         URMB_TRY(launch_one(rows_kernel, 3, tr, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
-        URMB_TRY(launch_one(rows_long_kernel, 3, tr, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
+        URMB_TRY(launch_one(rows_long_kernel, 7, tr, A, SmemPlan{1, 0, 0}, 2 * cnt, R, stream, sm_count, nullptr));
         URMB_TRY(launch_one(align_kernel_c, 4, tr, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
         URMB_TRY(launch_one(finish_kernel, 5, tr, A, SmemPlan{0, 0, 0}, cnt, R, stream, sm_count, nullptr));
         n += 6;

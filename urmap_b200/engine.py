@@ -60,10 +60,11 @@ class Contig(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("probe_ms", C.c_float), ("search_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("rescue_ms", C.c_float), ("kernel_ms", C.c_float * 7), ("kernel_launches", C.c_uint32 * 7)]
+                ("rescue_ms", C.c_float), ("kernel_ms", C.c_float * 12), ("kernel_launches", C.c_uint32 * 12)]
 
 
-KERNEL_CLASSES = ("probe", "pair", "align_a", "rows", "align_c", "finish", "rescue")
+KERNEL_CLASSES = ("probe", "pair", "align_a", "rows", "align_c", "finish", "rescue", "rows_long", "rescue_dp",
+                  "rescue_finish", "k10", "k11")
 
 
 EXPORTS = [
@@ -72,7 +73,8 @@ EXPORTS = [
     "urmb_index_device_desc", "urmb_map_se", "urmb_map_pe", "urmb_submit", "urmb_wait", "urmb_upload",
     "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
     "urmb_build_index_device", "urmb_build_last_error", "urmb_peak_gather", "urmb_peak_alu",
-    "urmb_host_alloc", "urmb_host_free", "urmb_reserve", "urmb_second_hits",
+    "urmb_host_alloc", "urmb_host_free", "urmb_reserve", "urmb_second_hits", "urmb_overflow_count",
+    "urmb_unsupported_count",
 ]
 
 _lib = None
@@ -115,6 +117,8 @@ def lib():
         L.urmb_peak_alu.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_double)]
         L.urmb_reserve.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
         L.urmb_second_hits.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+        L.urmb_overflow_count.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.urmb_unsupported_count.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.urmb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
         L.urmb_host_free.argtypes = [vp]
         L.urmb_host_free.restype = None
@@ -295,6 +299,18 @@ class Context:
         ms = C.c_float()
         _check(lib().urmb_mark_elapsed(self.c, C.byref(ms)), self.c)
         return float(ms.value)
+
+    def overflow_count(self, slot=0):
+        """(reads of the slot's last batch, reads over all batches) that exceeded a per-read capacity (flags bit 7)."""
+        last, total = C.c_uint32(), C.c_uint64()
+        _check(lib().urmb_overflow_count(self.c, slot, C.byref(last), C.byref(total)), self.c)
+        return int(last.value), int(total.value)
+
+    def unsupported_count(self, slot=0):
+        """(reads of the slot's last batch, reads over all batches) not searched: longer than URMB_MAX_READ_LEN (flags bit 6)."""
+        last, total = C.c_uint32(), C.c_uint64()
+        _check(lib().urmb_unsupported_count(self.c, slot, C.byref(last), C.byref(total)), self.c)
+        return int(last.value), int(total.value)
 
     def launch_count(self):
         return int(lib().urmb_launch_count(self.c))

@@ -31,8 +31,76 @@ def contig_layout(total_len, n_contigs=24, human_ratios=True):
     return names, lens, offsets, o  # o = SeqDataSize
 
 
-def make_seqdata(total_len, device, seed=12345, n_contigs=24, human_ratios=True, repeat_frac=0.10, n_runs=3):
-    """Returns (seqdata uint8 tensor [SeqDataSize + pad] upper-case ASCII with '-' pads, names, lens, offsets)."""
+def _g_to_seq(pos, lens, offsets):
+    """Positions in the pad-free concatenation of the contigs -> sequence-data offsets (PADGAP between contigs)."""
+    starts = np.concatenate([[0], np.cumsum(np.asarray(lens, dtype=np.int64))])[:-1]
+    ci = np.searchsorted(starts, pos, side="right") - 1
+    return np.asarray(offsets, dtype=np.int64)[ci] + (pos - starts[ci])
+
+
+def _inject_segdups(g, G, frac, rng, gen, device):
+    """Segmental duplications (BASELINE.json configs[4]): a 5-100 kb source segment copied to 1-5 other places, each copy
+    with 0.5-5 % substitutions, half of the copies reverse-complemented.  Returns [(start, length)] of every copy and
+    source in pad-free coordinates."""
+    regions, covered, target = [], 0, int(frac * G)
+    while covered < target:
+        L = int(min(rng.integers(5_000, 100_001), max(1000, G // 64)))
+        K = int(rng.integers(1, 6))
+        src = int(rng.integers(0, G - L))
+        seg = g[src:src + L].clone()
+        regions.append((src, L))
+        for _ in range(K):
+            dst = int(rng.integers(0, G - L))
+            c = seg
+            if rng.random() < 0.5:
+                c = (3 - seg).flip(0)
+            m = torch.rand(L, device=device, generator=gen) < float(rng.uniform(0.005, 0.05))
+            shift = torch.randint(1, 4, (L,), dtype=torch.uint8, device=device, generator=gen)
+            g[dst:dst + L] = torch.where(m, (c + shift) & 3, c)
+            regions.append((dst, L))
+            covered += L
+    return regions
+
+
+def _inject_tandems(g, G, frac, rng, gen, device):
+    """Tandem repeats (BASELINE.json configs[4]): arrays of a 2-60 bp unit, 200-5000 bp long, 0-10 % substitutions per
+    array; all arrays are written by one scatter (non-overlapping by construction)."""
+    target = int(frac * G)
+    if target <= 0:
+        return []
+    n = max(1, target // 2600)
+    T = rng.integers(200, 5001, size=n).astype(np.int64)
+    U = rng.integers(2, 61, size=n).astype(np.int64)
+    pos = np.sort(rng.integers(0, G - 5001, size=n)).astype(np.int64)
+    keep = np.ones(n, dtype=bool)
+    last_end = -1
+    for i in range(n):
+        if pos[i] < last_end:
+            keep[i] = False
+        else:
+            last_end = pos[i] + T[i]
+    T, U, pos = T[keep], U[keep], pos[keep]
+    n = len(T)
+    ustart = np.concatenate([[0], np.cumsum(U)])[:-1]
+    units = torch.randint(0, 4, (int(U.sum()),), dtype=torch.uint8, device=device, generator=gen)
+    Tt = torch.as_tensor(T, device=device)
+    rid = torch.repeat_interleave(torch.arange(n, device=device), Tt)
+    first = torch.as_tensor(np.concatenate([[0], np.cumsum(T)])[:-1], device=device)
+    j = torch.arange(int(T.sum()), device=device) - first[rid]
+    val = units[torch.as_tensor(ustart, device=device)[rid] + j % torch.as_tensor(U, device=device)[rid]]
+    div = torch.as_tensor(rng.uniform(0.0, 0.10, size=n), device=device, dtype=torch.float32)[rid]
+    m = torch.rand(val.shape, device=device, generator=gen) < div
+    shift = torch.randint(1, 4, val.shape, dtype=torch.uint8, device=device, generator=gen)
+    g[torch.as_tensor(pos, device=device)[rid] + j] = torch.where(m, (val + shift) & 3, val)
+    return list(zip(pos.tolist(), T.tolist()))
+
+
+def make_seqdata(total_len, device, seed=12345, n_contigs=24, human_ratios=True, repeat_frac=0.10, n_runs=3,
+                 segdup_frac=0.0, tandem_frac=0.0, regions_out=None):
+    """Returns (seqdata uint8 tensor [SeqDataSize + pad] upper-case ASCII with '-' pads, names, lens, offsets).
+    segdup_frac / tandem_frac add segmental duplications and tandem repeats (the repeat-rich reference of
+    BASELINE.json configs[4]); regions_out (a list) receives (sequence-data offset, length) of every such region so that
+    reads can be drawn from them (sim_se / sim_pe `regions`).  With both at 0 the genome is the one earlier rounds used."""
     names, lens, offsets, sds = contig_layout(total_len, n_contigs, human_ratios)
     G = int(total_len)
     gen = torch.Generator(device=device)
@@ -64,6 +132,14 @@ def make_seqdata(total_len, device, seed=12345, n_contigs=24, human_ratios=True,
         g[idx.reshape(-1)] = copies.reshape(-1)
         covered += L * K
         del idx, copies, m, shift
+    regions = []
+    if segdup_frac > 0:
+        regions += _inject_segdups(g, G, segdup_frac, rng, gen, device)
+    if tandem_frac > 0:
+        regions += _inject_tandems(g, G, tandem_frac, rng, gen, device)
+    if regions_out is not None and regions:
+        r = np.asarray(regions, dtype=np.int64)
+        regions_out.extend(zip(_g_to_seq(r[:, 0], lens, offsets).tolist(), r[:, 1].tolist()))
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
     seq = torch.empty(sds + 4096, dtype=torch.uint8, device=device)
     seq[sds:] = 0
@@ -130,8 +206,30 @@ def _mutate(frag, sub, indel, read_len, gen):
     return torch.where(ins_mask, ins_bases, out).contiguous()
 
 
+def _pick(m, span, lens_t, offs_t, w, gen, device, regions, enrich):
+    """Fragment starts (sequence-data offsets) of m fragments of `span` bases: uniform over the genome, except that a
+    fraction `enrich` starts inside (or up to span/2 before) one of `regions` [(offset, length)] chosen by length."""
+    ci = torch.multinomial(w / w.sum(), m, replacement=True, generator=gen)
+    p = (torch.rand(m, device=device, generator=gen, dtype=torch.float64) * (lens_t[ci] - span)).long()
+    g0 = offs_t[ci] + p
+    if regions is not None and enrich > 0:
+        rs, rl = regions
+        ri = torch.multinomial(rl.double() / rl.double().sum(), m, replacement=True, generator=gen)
+        q = rs[ri] + (torch.rand(m, device=device, generator=gen, dtype=torch.float64) * rl[ri].double()).long() - span // 2
+        cq = torch.clamp(torch.searchsorted(offs_t, q, right=True) - 1, 0, len(lens_t) - 1)
+        q = torch.minimum(torch.maximum(q, offs_t[cq]), offs_t[cq] + lens_t[cq] - span)
+        use = torch.rand(m, device=device, generator=gen) < enrich
+        g0 = torch.where(use, q, g0)
+    return g0
+
+
+def regions_tensor(regions, device):
+    r = torch.as_tensor(np.asarray(regions, dtype=np.int64), device=device)
+    return r[:, 0].contiguous(), r[:, 1].contiguous()
+
+
 def sim_pe(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, seed=778, pad=40, ins_mean=400,
-           ins_sd=50, ins_lo=200, ins_hi=800, chunk=1 << 18, return_truth=False):
+           ins_sd=50, ins_lo=200, ins_hi=800, chunk=1 << 18, return_truth=False, regions=None, enrich=0.0):
     """FR pairs (which mate is forward is randomised). Returns (r1, r2) uint8 tensors [n, read_len] on device; with
     return_truth also (pos1, pos2, plus1): the sequence-data offset each mate was drawn from (start of its alignment
     on the plus strand, up to the read's own indels) and whether mate 1 is the forward one."""
@@ -147,12 +245,15 @@ def sim_pe(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, s
     t1, t2, tf = [], [], []
     for c0 in range(0, n, chunk):
         m = min(chunk, n - c0)
-        ci = torch.multinomial(w / w.sum(), m, replacement=True, generator=gen)
         ins = torch.clamp(torch.normal(float(ins_mean), float(ins_sd), (m,), device=device, generator=gen),
                           max(ins_lo, L), ins_hi).long()
-        maxp = lens_t[ci] - (ins_hi + pad)
-        p = (torch.rand(m, device=device, generator=gen, dtype=torch.float64) * maxp).long()
-        g0 = offs_t[ci] + p
+        if regions is None:   # the draw order of earlier rounds (same reads for the same seed)
+            ci = torch.multinomial(w / w.sum(), m, replacement=True, generator=gen)
+            maxp = lens_t[ci] - (ins_hi + pad)
+            p = (torch.rand(m, device=device, generator=gen, dtype=torch.float64) * maxp).long()
+            g0 = offs_t[ci] + p
+        else:
+            g0 = _pick(m, ins_hi + pad, lens_t, offs_t, w, gen, device, regions, enrich)
         left = seq[g0[:, None] + ar]
         right = seq[(g0 + ins - L)[:, None] + ar]
         a = _mutate(left, sub, indel, read_len, gen)
@@ -170,7 +271,8 @@ def sim_pe(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, s
     return torch.cat(o1).contiguous(), torch.cat(o2).contiguous()
 
 
-def sim_se(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, seed=777, pad=40, chunk=1 << 18):
+def sim_se(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, seed=777, pad=40, chunk=1 << 18,
+           regions=None, enrich=0.0):
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     L = read_len + pad
@@ -182,9 +284,7 @@ def sim_se(seq, lens, offsets, n, device, read_len=150, sub=0.01, indel=0.001, s
     out = []
     for c0 in range(0, n, chunk):
         m = min(chunk, n - c0)
-        ci = torch.multinomial(w / w.sum(), m, replacement=True, generator=gen)
-        p = (torch.rand(m, device=device, generator=gen, dtype=torch.float64) * (lens_t[ci] - L)).long()
-        g0 = offs_t[ci] + p
+        g0 = _pick(m, L, lens_t, offs_t, w, gen, device, regions, enrich)
         frag = seq[g0[:, None] + ar]
         minus = torch.rand(m, device=device, generator=gen) < 0.5
         frag = torch.where(minus[:, None], comp[frag.flip(1).long()], frag)

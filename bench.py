@@ -444,8 +444,9 @@ KCLASS = {
     "probe": ("probe_kernel", "gather"), "pair": ("pair_kernel | seed_kernel_se", "state"),
     "align_a": ("align_kernel_a | align_kernel_se3", "dp"), "rows": ("rows_kernel | rows_kernel_se", "gather"),
     "rows_long": ("rows_long_kernel | rows_long_kernel_se", "gather"), "align_c": ("align_kernel_c | align_kernel_se6", "dp"),
-    "finish": ("finish_kernel", "state"), "rescue": ("rescue_scan_kernel", "gather"), "rescue_dp": ("rescue_dp_kernel", "dp"),
-    "rescue_finish": ("rescue_finish_kernel", "state"),
+    "finish": ("finish_kernel", "state"), "rescue": ("rescue_scan_kernel | rescue_last_kernel", "gather"),
+    "rescue_dp": ("rescue_dp_kernel", "dp"),
+    "rescue_legacy": ("rescue_kernel", "state"),
 }
 
 

@@ -173,7 +173,14 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     memset(ct, 0, sizeof ct);
     std::vector<uint32_t> todo(n_units + 1), rescue(n_units + 1);
     if (g_emu_second) memset(g_emu_second, 0, sizeof(urmb_second) * nreads);
-    DevOut o{res, runs, runs_cap, ct, todo.data(), rescue.data(), paired ? g_emu_second : nullptr};
+    // a tiny rescue pool: the first pairs that need mate rescue continue from their saved states (rescue rounds), the
+    // others take the legacy kernel -- both paths are exercised
+    uint32_t rcap = 6;
+    if (const char *f = getenv("URMB_EMU_RESCUE_CAP")) rcap = (uint32_t)strtoul(f, nullptr, 0);
+    RescueSave *rpool = rcap ? (RescueSave *)malloc(sizeof(RescueSave) * rcap) : nullptr;
+    if (rpool) memset(rpool, 0xEE, sizeof(RescueSave) * rcap);
+    std::vector<uint32_t> rq0(rcap + 1), rq1(rcap + 1);
+    DevOut o{res, runs, runs_cap, ct, todo.data(), rescue.data(), paired ? g_emu_second : nullptr, rpool, rcap, {rq0.data(), rq1.data()}};
     const int nw = 4;
     WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch) * nw);
     memset(ws, 0xEE, sizeof(WarpScratch) * nw);
@@ -188,6 +195,7 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     if (nk >= 0) nk = launch_rescue(ix, P, b, pr, o, R, nullptr, 1, nullptr);
     free(ws);
     free(pool);
+    free(rpool);
     memcpy(counters, ct, 32);
     return nk < 0 ? nk : 0;
 }

@@ -62,6 +62,36 @@ def test_emulated_pe(oracle, golden_oix, golden_dir, pe_method):
     _same(np.concatenate([r1, r2]), uo, re_, ue)
 
 
+@pytest.mark.parametrize("cap", [0, 1000])
+def test_emulated_rescue_rounds(oracle, golden_oix, golden_dir, cap, monkeypatch):
+    """Mate rescue continued from the saved states in rounds of (window scans, full-window DPs) against the legacy
+    kernel that searches the pair again from scratch (rescue pool capacity 0): both equal the oracle."""
+    import emu_py
+    monkeypatch.setenv("URMB_EMU_RESCUE_CAP", str(cap))
+    b1 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_1.fq"))
+    b2 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_2.fq"))
+    sel = np.r_[255:270, 390:430]   # 5 % reads and damaged-mate pairs
+
+    def take(b):
+        s = np.concatenate([b.seqs[b.offs[i]:b.offs[i + 1]] for i in sel])
+        o = np.concatenate([[0], np.cumsum([b.offs[i + 1] - b.offs[i] for i in sel])]).astype(np.uint32)
+        return s, o
+
+    s1, o1 = take(b1)
+    s2, o2 = take(b2)
+    r1, r2, uo, st = oracle.map_pe(golden_oix, oracle.ReadBatch(s1, o1), oracle.ReadBatch(s2, o2), want_stats=True)
+    assert st["scan_calls"] > 20 and st["dp_cells_scan"] > 0
+    seqs = np.concatenate([s1, s2])
+    offs = np.concatenate([o1, o2[1:] + o1[-1]]).astype(np.uint32)
+    re_, ue, cnt = emu_py.emu_map(golden_oix, oracle.RESULT_DTYPE, seqs, offs, len(sel), True)
+    assert cnt[1] == 0 and cnt[2] > 20              # no overflow; pairs that needed mate rescue
+    if cap:
+        assert cnt[5] == 0 and cnt[6] > 10          # nothing left to the legacy kernel; DPs run by the rounds
+    else:
+        assert cnt[5] == cnt[2] and cnt[6] == 0
+    _same(np.concatenate([r1, r2]), uo, re_, ue)
+
+
 def _tab_lines(contigs, labels, L1, L2, r1, r2, s1, s2):
     """State2::OutputTab2 (outputtab2.cpp:6-119) restated in Python over result records (test helper)."""
     def chrpos(pos):

@@ -185,6 +185,15 @@ struct urmb_ctx {
     int n_rescue_warps = 0;
     MateSave *pool = nullptr;      // saved mate states of one chunk of the paired-end second pass (2 per pair)
     size_t pool_pairs = 0;
+    // Rescue pools: saved states of the pairs that need mate rescue, two so that the rescue rounds of batch k (side stream)
+    // and the finish kernels of batch k + 1 (compute stream) never share one; work lists of the rounds beside them.
+    RescueSave *rpool[2] = {nullptr, nullptr};
+    uint32_t *rq[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    size_t rescue_cap = 0;
+    cudaEvent_t ev_rpool[2] = {nullptr, nullptr};   // end of the last rescue that used the pool
+    bool rpool_used[2] = {false, false};
+    int rparity = 0;
+    bool rescue_legacy = false;    // URMB_RESCUE_LEGACY: no rescue pool, every rescued pair is searched again from scratch
     uint32_t chunk_pairs = 524288; // URMB_CHUNK_PAIRS (step time at 1 M pairs: 92.9 / 86.0 / 82.5 / 82.1 ms for 128k / 256k / 512k / 1M)
     Slot slots[URMB_SLOTS];
     uint64_t launches = 0;
@@ -249,11 +258,13 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     CK(cudaStreamCreateWithPriority(&c->compute, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&c->rescue, cudaStreamNonBlocking, prio_lo));
     for (auto &ev : c->ev_mark) CK(cudaEventCreate(&ev));
+    for (auto &ev : c->ev_rpool) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char *f = getenv("URMB_RESCUE_LEGACY")) c->rescue_legacy = atoi(f) != 0;
     CK(cudaEventCreateWithFlags(&c->ev_rescue_tail, cudaEventDisableTiming));
     c->n_scratch_warps = max_search_warps(c->sm_count);
     // The rescue kernel is a queue of few, long work items that runs beside the next batch: a small persistent grid
     // (one block per SM) takes few registers away from the main kernels and still drains the queue in time.
-    c->n_rescue_warps = c->sm_count * 4;
+    c->n_rescue_warps = c->sm_count * 12;
     if (const char *f = getenv("URMB_RESCUE_WARPS")) c->n_rescue_warps = std::max(4, atoi(f) & ~3);
     if (const char *f = getenv("URMB_RESCUE_INLINE")) c->rescue_inline = atoi(f) != 0;
     CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps));
@@ -291,6 +302,12 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     cudaFree(c->rescue_scratch);
     cudaFree(c->scratch);
     cudaFree(c->pool);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->rpool[k]);
+        cudaFree(c->rq[k][0]);
+        cudaFree(c->rq[k][1]);
+        if (c->ev_rpool[k]) cudaEventDestroy(c->ev_rpool[k]);
+    }
     cudaFree(c->own_blob);
     cudaFree(c->own_seq);
     cudaFree(c->seq2);
@@ -485,6 +502,28 @@ static int check_batch(urmb_ctx *c, const urmb_batch *b) {
 // Sizes every slot (and the pool of saved mate states) for batches of n_units reads / pairs of up to max_read_len bases,
 // so that the first batches do not pay for the allocations.  Touches only the slots and the pool: the CLI calls it from
 // a helper thread while urmb_index_broadcast is still copying the index.
+// Rescue pools for paired-end batches of n pairs: one pair in eight (at least 4096, at most 131072 entries of 21.6 kB);
+// pairs beyond that take the legacy kernel.
+static int size_rescue_pools(urmb_ctx *c, size_t n) {
+    if (c->rescue_legacy || c->P.pe_method == 5) return URMB_OK;
+    const size_t want = std::min<size_t>(std::max<size_t>(n / 8, 4096), 131072);
+    if (want <= c->rescue_cap) return URMB_OK;
+    CK(cudaStreamSynchronize(c->compute));
+    CK(cudaStreamSynchronize(c->rescue));
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->rpool[k]); cudaFree(c->rq[k][0]); cudaFree(c->rq[k][1]);
+        c->rpool[k] = nullptr; c->rq[k][0] = c->rq[k][1] = nullptr;
+    }
+    c->rescue_cap = 0;
+    for (int k = 0; k < 2; ++k) {
+        CK(cudaMalloc(&c->rpool[k], sizeof(RescueSave) * want));
+        CK(cudaMalloc(&c->rq[k][0], sizeof(uint32_t) * (want + 1)));
+        CK(cudaMalloc(&c->rq[k][1], sizeof(uint32_t) * (want + 1)));
+    }
+    c->rescue_cap = want;
+    return URMB_OK;
+}
+
 extern "C" int urmb_reserve(urmb_ctx *c, uint32_t n_units, uint32_t max_read_len, int paired, uint32_t word_length) {
     if (!c || n_units == 0 || max_read_len == 0 || max_read_len > (uint32_t)kMaxLen || word_length < 8 || word_length > 32)
         return URMB_E_ARG;
@@ -527,6 +566,7 @@ extern "C" int urmb_reserve(urmb_ctx *c, uint32_t n_units, uint32_t max_read_len
         CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
         c->pool_pairs = want;
     }
+    if (paired && (rc = size_rescue_pools(c, n))) return rc;
     return URMB_OK;
 }
 
@@ -632,6 +672,7 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
             CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
             c->pool_pairs = want;
         }
+        if (r2 && (rc = size_rescue_pools(c, n))) return rc;
     }
     if ((rc = grow_host(c, s.h_res, s.h_res_cap, (size_t)nreads + 1))) return rc;
     if (c->params.want_second && r2) {
@@ -697,7 +738,14 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         DevProbe pr{s.d_tally, s.d_pos, s.d_ext, s.d_view, view_stride_for(s.batch.seqcap)};
         urmb_second *second = (c->params.want_second && s.batch.paired) ? s.d_second : nullptr;
         if (second) CK(cudaMemsetAsync(second, 0, (size_t)s.batch.n_reads * sizeof(urmb_second), c->compute));
-        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue, second};
+        // this launch's rescue pool: the other one may still be in use by the rescue rounds of the previous launch
+        const int rp = c->rparity;
+        c->rparity ^= 1;
+        const bool use_pool = s.batch.paired && c->rescue_cap && c->rpool[rp];
+        if (use_pool && c->rpool_used[rp]) CK(cudaStreamWaitEvent(c->compute, c->ev_rpool[rp], 0));
+        DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue, second,
+                 use_pool ? c->rpool[rp] : nullptr, use_pool ? (uint32_t)c->rescue_cap : 0u,
+                 {use_pool ? c->rq[rp][0] : nullptr, use_pool ? c->rq[rp][1] : nullptr}};
         SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
         TraceCtx tc{&s, c->compute, cudaSuccess};
@@ -720,6 +768,10 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         e = launch_rescue(c->ix, P, s.batch, pr, o, c->rescue_inline ? R : RR, rs, c->sm_count, &tr);
         if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, c->compute));
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("rescue launch: ") + cudaGetErrorString((cudaError_t)-e));
+        if (use_pool) {
+            CK(cudaEventRecord(c->ev_rpool[rp], rs));
+            c->rpool_used[rp] = true;
+        }
         if (tc.err != cudaSuccess) return fail(c, URMB_E_CUDA, std::string("event record: ") + cudaGetErrorString(tc.err));
         c->launches += (uint64_t)e;
         rescued = e > 0;
@@ -819,7 +871,7 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
     }
     CK(cudaEventRecord(s.ev_d2h, s.copy));
     CK(cudaStreamSynchronize(s.copy));
-    if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u rescued, %u path runs\n", si, s.batch.n_units, s.h_counters[CT_TODO_TOTAL], s.h_counters[CT_RESCUE], used);
+    if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u rescued (%u by the legacy kernel, %u full-window DPs), %u path runs\n", si, s.batch.n_units, s.h_counters[CT_TODO_TOTAL], s.h_counters[CT_RESCUE], s.h_counters[CT_RESCUE_LEGACY], s.h_counters[CT_RESCUE_DPS], used);
     if (res1) *res1 = s.h_res;
     if (res2) *res2 = s.batch.paired ? s.h_res + s.batch.n_units : nullptr;
     if (runs) *runs = s.h_runs;
@@ -873,7 +925,7 @@ extern "C" int urmb_timing_last(urmb_ctx *c, int si, urmb_timing *t) {
             t->kernel_launches[k] += 1;
         }
     }
-    t->rescue_ms = t->kernel_ms[6];
+    t->rescue_ms = t->kernel_ms[6] + t->kernel_ms[8] + t->kernel_ms[9];
     if (cudaEventQuery(s.ev_h2d) == cudaSuccess) cudaEventElapsedTime(&t->h2d_ms, s.ev_h2d0, s.ev_h2d);
     if (cudaEventQuery(s.ev_d2h) == cudaSuccess && cudaEventQuery(s.ev_k2) == cudaSuccess)
         cudaEventElapsedTime(&t->d2h_ms, s.ev_k2, s.ev_d2h);

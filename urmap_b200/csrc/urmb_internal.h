@@ -58,27 +58,39 @@ inline uint32_t view_stride_for(uint32_t seqcap) { return kViewHdr + seqcap; }
 
 // Device counters of one batch slot (u32 each).  CT_RUNS / CT_OVERFLOW / CT_*_TOTAL live for the whole batch; the
 // others are per chunk and are zeroed by the launcher between chunks.
+constexpr int kRescueRounds = 6;   // suspend-at-DP rounds of the mate rescue; a last round finishes the stragglers in place
 enum {
     CT_RUNS = 0,        // path runs used in DevOut::runs
     CT_OVERFLOW = 1,    // reads that exceeded a per-read capacity
-    CT_RESCUE = 2,      // pairs queued for the mate-rescue kernel (whole batch)
-    CT_RESCUE_HEAD = 3, // work-queue head of the mate-rescue kernel
+    CT_RESCUE = 2,      // pairs that need mate rescue (whole batch): the first rescue_cap of them own an entry of the rescue pool
+    CT_RESCUE_HEAD = 3, // work-queue head of the legacy (search from scratch) mate-rescue kernel
     CT_TODO_TOTAL = 4,  // pairs that went through the staged second pass (whole batch, statistics)
+    CT_RESCUE_LEGACY = 5, // pairs queued for the legacy mate-rescue kernel (rescue pool full)
+    CT_RESCUE_DPS = 6,  // full-window DPs run by the rescue rounds (statistics)
     CT_CHUNK0 = 8,      // first per-chunk counter
     CT_HEAD = 8,        // work-queue head of the first-pass kernel
     CT_TODO = 9,        // pairs of this chunk saved for the staged second pass
     CT_STAGE_A = 10, CT_STAGE_B = 11, CT_STAGE_C = 12, CT_FINISH = 13, CT_STAGE_B2 = 14,   // work-queue heads of the stage kernels
-    CT_COUNT = 16
+    // mate-rescue rounds (whole batch): round r scans the pairs of list r (round 0: every pool entry) and appends the
+    // ones that stop at a full-window DP to list r + 1; the DP kernel of round r works through list r + 1
+    CT_RQ_COUNT = 16,                           // [kRescueRounds + 2] entries of list r
+    CT_RQ_SCAN = CT_RQ_COUNT + kRescueRounds + 2,   // [kRescueRounds + 2] work-queue heads of the scan kernels
+    CT_RQ_DP = CT_RQ_SCAN + kRescueRounds + 2,      // [kRescueRounds + 2] work-queue heads of the DP kernels
+    CT_COUNT = CT_RQ_DP + kRescueRounds + 2
 };
 
+struct RescueSave;
 struct DevOut {
     urmb_result *res;      // [n_reads]
     uint16_t *runs;        // pool
     uint32_t runs_cap;
     uint32_t *counters;    // [CT_COUNT]
     uint32_t *todo;        // [chunk pairs] pairs of the current chunk saved for the staged second pass
-    uint32_t *rescue;      // [n_units] pairs that need mate rescue (State2::ScanPair)
+    uint32_t *rescue;      // [n_units] pairs for the legacy mate-rescue kernel (State2::ScanPair from scratch)
     urmb_second *second;   // [n_reads] or null: State2's second pair (m_SecondHit, search2.cpp:49-56), zero-filled per launch
+    RescueSave *rpool;     // [rescue_cap] saved states of the pairs that need mate rescue (null: legacy kernel only)
+    uint32_t rescue_cap;
+    uint32_t *rq[2];       // [rescue_cap] each: work lists of the rescue rounds (pool entry indexes), ping-pong
 };
 
 constexpr int kRunPool = 2048;  // path runs of all hits of one mate
@@ -111,6 +123,29 @@ struct MateHdr {
 struct MateSave {
     MateHdr h;
     MateScratch s;
+};
+
+// Mate rescue (State2::ScanPair, state2.cpp:87-137) continues from the saved states of the pair.  A pair whose next step
+// is a full-window Viterbi (State1::Scan, scan.cpp:27) stops there: the DP is a pure function of (read strand, window), so
+// it is queued for a kernel that runs all pending DPs of the batch side by side, and the pair resumes in the next round.
+struct RescuePos {
+    int32_t state;            // 0 fresh, 1 stopped at a DP (request below; the result is filled in by the DP kernel)
+    int32_t loop, h;          // position in ScanPair's two loops (h = next hit index)
+    int32_t hcF, hcR;         // hit counts at entry
+    int32_t dovF, dovR;       // DoVit of the two loops (Mapq >= 10 at entry)
+    uint32_t dp_pos, dp_len;  // window of the requested DP
+    int32_t dp_plus, dp_mate; // strand of the scanned mate; which mate is scanned (0 = forward read, 1 = reverse read)
+};
+struct RescueHdr {
+    uint32_t unit;            // pair index in the batch
+    RescuePos p;
+    float dp_score;
+    int32_t dp_nrev, dp_ovf;
+    uint16_t dp_runs[kRunCap + 8];   // reversed RLE path of the DP
+};
+struct RescueSave {
+    MateSave m[2];
+    RescueHdr h;
 };
 
 struct WarpScratch {

@@ -1874,20 +1874,22 @@ __device__ __noinline__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, ui
     }
 }
 
-// State1::Scan, scan.cpp:14-39
-__device__ __noinline__ void scan_mate(const Env &E, Mate &m, uint32_t DBPos, uint32_t DBSegLength, bool Plus,
-                                       bool DoVit) {
+// State1::Scan, scan.cpp:14-39, in three pieces so that the full-window Viterbi can run elsewhere:
+//   scan_mate_pre  : ScanSlots under the raised penalty bound; true when the DP has to run (no hit found, DoVit)
+//   (the DP)       : viterbi_warp<true>(strand of the mate, window), a pure function of its arguments
+//   scan_mate_post : the hit of a good enough DP (path trimmed as TrimLeftIs / TrimRightIs do)
+__device__ __noinline__ bool scan_mate_pre(const Env &E, Mate &m, uint32_t DBPos, uint32_t DBSegLength, bool Plus, bool DoVit) {
     const int SavedMaxPenalty = m.MaxPenalty;
     const int SavedHitCount = m.HitCount;
     m.MaxPenalty = 130;
     scan_slots(E, m, DBPos, DBSegLength, Plus);
     m.MaxPenalty = SavedMaxPenalty;
-    if (m.HitCount > SavedHitCount) return;
-    if (!DoVit) return;
-    int nrev = 0, ovf = 0;
-    float Score = viterbi_warp<true>(E, mate_seq(m, Plus), m.QL, E.ix.seq + DBPos, DBSegLength, true, true, nrev, ovf);
+    if (m.HitCount > SavedHitCount) return false;
+    return DoVit;
+}
+__device__ __noinline__ void scan_mate_post(const Env &E, Mate &m, uint32_t DBPos, bool Plus, float Score, const uint16_t *rev,
+                                            int nrev, int ovf) {
     if ((double)Score >= (double)m.QL / 3.0) {
-        const uint16_t *rev = E.ws->runs_a;
         uint16_t *path = E.ws->runs_p;
         int np = 0;
         uint32_t LeftICount = 0;
@@ -1902,6 +1904,13 @@ __device__ __noinline__ void scan_mate(const Env &E, Mate &m, uint32_t DBPos, ui
         if (ovf) m.overflow = 1;
         add_hit(E, m, DBPos + LeftICount, Plus, (int)Score, path, np);
     }
+}
+__device__ __noinline__ void scan_mate(const Env &E, Mate &m, uint32_t DBPos, uint32_t DBSegLength, bool Plus,
+                                       bool DoVit) {
+    if (!scan_mate_pre(E, m, DBPos, DBSegLength, Plus, DoVit)) return;
+    int nrev = 0, ovf = 0;
+    float Score = viterbi_warp<true>(E, mate_seq(m, Plus), m.QL, E.ix.seq + DBPos, DBSegLength, true, true, nrev, ovf);
+    scan_mate_post(E, m, DBPos, Plus, Score, E.ws->runs_a, nrev, ovf);
 }
 
 struct PairState {
@@ -1979,6 +1988,43 @@ __device__ __noinline__ void scan_pair(const Env &E, Mate &F, Mate &R) {
         if (R.g->hit_plus[h]) scan_mate(E, F, DBPos, kScanSeg, false, DoVitR);
         else if (DBPos >= (uint32_t)kScanSeg) scan_mate(E, F, DBPos - kScanSeg, kScanSeg + 2 * QLx, true, DoVitR);
     }
+}
+
+// State2::ScanPair as a resumable walk (see RescueHdr).  h holds the position; returns true when both loops are through,
+// false when the walk stopped at a full-window DP whose request is then in h (INLINE: the DP runs here, never stops).
+template <bool INLINE>
+__device__ __noinline__ bool scan_pair_resume(const Env &E, Mate &F, Mate &R, RescuePos &h) {
+    const uint32_t QLx = F.QL;
+    for (; h.loop < 2; ++h.loop, h.h = 0) {
+        Mate &src = h.loop ? R : F;
+        Mate &dst = h.loop ? F : R;
+        const int n = h.loop ? h.hcR : h.hcF;
+        const bool DoVit = (h.loop ? h.dovR : h.dovF) != 0;
+        while (h.h < n) {
+            const int k = h.h++;
+            if ((int)src.g->hit_score[k] < src.Second) continue;
+            const uint32_t DBPos = src.g->hit_pos[k];
+            uint32_t pos, len;
+            bool plus;
+            if (src.g->hit_plus[k]) { pos = DBPos; len = kScanSeg; plus = false; }
+            else if (DBPos >= (uint32_t)kScanSeg) { pos = DBPos - kScanSeg; len = kScanSeg + 2 * QLx; plus = true; }
+            else continue;
+            if (!scan_mate_pre(E, dst, pos, len, plus, DoVit)) continue;
+            if (INLINE) {
+                int nrev = 0, ovf = 0;
+                const float Score = viterbi_warp<true>(E, mate_seq(dst, plus), dst.QL, E.ix.seq + pos, len, true, true, nrev, ovf);
+                scan_mate_post(E, dst, pos, plus, Score, E.ws->runs_a, nrev, ovf);
+            } else {
+                h.state = 1;
+                h.dp_pos = pos;
+                h.dp_len = len;
+                h.dp_plus = plus ? 1 : 0;
+                h.dp_mate = h.loop ? 0 : 1;
+                return false;
+            }
+        }
+    }
+    return true;
 }
 
 // State2::AdjustTopHitsAndMapqs, search2.cpp:8-57
@@ -2368,6 +2414,27 @@ __device__ __forceinline__ void bare_mate(const Env &E, Mate &m, const DevBatch 
     hdr_to_mate(sv->h, m);
 }
 
+// Saved mate -> rescue pool: hit list with its path runs, HSP list, scalars (the pending lists are spent by then).
+__device__ __noinline__ void copy_save(const Env &E, const MateSave *__restrict__ src, MateSave *__restrict__ dst) {
+    const MateHdr h = src->h;
+    const MateScratch *__restrict__ g = &src->s;
+    MateScratch *__restrict__ d = &dst->s;
+    for (int i0 = 0; i0 < max(h.HitCount, h.HSPCount); i0 += 32) {
+        const int i = i0 + E.lane;
+        if (i < h.HitCount) {
+            d->hit_pos[i] = g->hit_pos[i]; d->hit_score[i] = g->hit_score[i]; d->hit_plus[i] = g->hit_plus[i];
+            d->hit_nruns[i] = g->hit_nruns[i]; d->hit_roff[i] = g->hit_roff[i];
+        }
+        if (i < h.HSPCount) {
+            d->hsp_dbstart[i] = g->hsp_dbstart[i]; d->hsp_qstart[i] = g->hsp_qstart[i]; d->hsp_len[i] = g->hsp_len[i];
+            d->hsp_score[i] = g->hsp_score[i]; d->hsp_flags[i] = g->hsp_flags[i];
+        }
+    }
+    for (int i = E.lane; i < h.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
+    if (E.lane == 0) dst->h = h;
+    __syncwarp();
+}
+
 __device__ __forceinline__ void make_env(Env &E, const DevIndex &ix, const DevParams &P, const DevBatch &b,
                                          WarpScratch *scratch, const SmemPlan &pl, uint8_t *sw, int gw, int lane) {
     E.ix = ix;
@@ -2409,7 +2476,7 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
     const size_t msz = mate_smem_bytes(b.qcap, b.seqcap, true);
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
-    const uint32_t n_work = (MODE == 2) ? o.counters[CT_RESCUE] : A.unit_count;
+    const uint32_t n_work = (MODE == 2) ? o.counters[CT_RESCUE_LEGACY] : A.unit_count;
 
     for (;;) {
         uint32_t u = 0;
@@ -2544,7 +2611,23 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
             PairState ps;
             find_pairs(E, F, R, ps);
             if (ps.PairCount == 0) {   // State2::ScanPair needed (search2m4.cpp:179-183)
-                if (lane == 0) A.o.rescue[atomicAdd(&A.o.counters[CT_RESCUE], 1u)] = u;
+                // the pair's saved states move to the rescue pool (this chunk's pool is about to be reused); when that
+                // is full the pair is searched again from scratch by the legacy kernel
+                uint32_t e = 0;
+                if (lane == 0) e = atomicAdd(&A.o.counters[CT_RESCUE], 1u);
+                e = __shfl_sync(FULL, e, 0);
+                if (A.o.rpool && e < A.o.rescue_cap) {
+                    RescueSave *rs = A.o.rpool + e;
+                    copy_save(E, A.pool + 2 * (size_t)t, &rs->m[0]);
+                    copy_save(E, A.pool + 2 * (size_t)t + 1, &rs->m[1]);
+                    if (lane == 0) {
+                        rs->h.unit = u;
+                        rs->h.p.state = 0;
+                    }
+                } else if (lane == 0) {
+                    A.o.rescue[atomicAdd(&A.o.counters[CT_RESCUE_LEGACY], 1u)] = u;
+                }
+                __syncwarp();
                 continue;
             }
             adjust_pair(F, R, ps);
@@ -2552,6 +2635,110 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
         }
         write_result(E, F, A.o, u);
         write_result(E, R, A.o, b.n_units + u);
+        __syncwarp();
+    }
+}
+
+// Mate-rescue round `round`, one warp per pair of the round's list: State2::ScanPair continued from the saved states in the
+// rescue pool (search2m4.cpp:179-186).  A pair that reaches a full-window DP is appended to the next list and stops
+// (INLINE, the last round: the DP runs here); a pair that gets through both loops is finished: FindPairs,
+// AdjustTopHitsAndMapqs, result records.
+template <bool INLINE>
+__device__ __forceinline__ void rescue_scan_body(const KArgs &A, int round) {
+    URMB_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpb + warp;
+    uint8_t *sw = smem + (size_t)warp * A.spw;
+    const DevBatch &b = A.b;
+    const DevOut &o = A.o;
+    const SmemPlan pl{2u, 0u, 1u};
+    const size_t msz = mate_smem_bytes(b.qcap, b.seqcap, false);
+    Env E;
+    make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
+    const uint32_t n_work = round == 0 ? min(o.counters[CT_RESCUE], o.rescue_cap) : o.counters[CT_RQ_COUNT + round];
+    const uint32_t *list = o.rq[round & 1];
+    uint32_t *next = o.rq[(round + 1) & 1];
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&o.counters[CT_RQ_SCAN + round], 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_work) break;
+        const uint32_t e = round == 0 ? k : list[k];
+        RescueSave *rs = o.rpool + e;
+        RescuePos h = rs->h.p;
+        const uint32_t u = rs->h.unit;
+        Mate F, R;
+        load_mate(E, F, b, A.pr, u, sw, &rs->m[0].s, false);
+        load_mate(E, R, b, A.pr, b.n_units + u, sw + msz, &rs->m[1].s, false);
+        hdr_to_mate(rs->m[0].h, F);
+        hdr_to_mate(rs->m[1].h, R);
+        if (h.state == 0) {   // State2::ScanPair entry, state2.cpp:87-98
+            h.loop = 0;
+            h.h = 0;
+            h.hcF = F.HitCount;
+            h.hcR = R.HitCount;
+            h.dovF = ((int)F.Mapq >= 10) ? 1 : 0;
+            h.dovR = ((int)R.Mapq >= 10) ? 1 : 0;
+        } else {              // the DP this pair stopped at has been run
+            Mate &dst = h.dp_mate ? R : F;
+            scan_mate_post(E, dst, h.dp_pos, h.dp_plus != 0, rs->h.dp_score, rs->h.dp_runs, rs->h.dp_nrev, rs->h.dp_ovf);
+        }
+        h.state = 0;
+        if (scan_pair_resume<INLINE>(E, F, R, h)) {
+            PairState ps;
+            find_pairs(E, F, R, ps);
+            adjust_pair(F, R, ps);
+            write_second(E, F, R, ps, o.second, u, b.n_units);
+            write_result(E, F, o, u);
+            write_result(E, R, o, b.n_units + u);
+        } else {
+            mate_to_hdr(E, F, &rs->m[0], false);
+            mate_to_hdr(E, R, &rs->m[1], false);
+            if (lane == 0) {
+                rs->h.p = h;
+                next[atomicAdd(&o.counters[CT_RQ_COUNT + round + 1], 1u)] = e;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// The full-window DPs of the pairs round `round` stopped at (list round + 1), one warp per DP: State1::Viterbi over the
+// whole scan window (scan.cpp:27), result (score, reversed RLE path) left in the pair's RescueHdr.
+__device__ __forceinline__ void rescue_dp_body(const KArgs &A, int round) {
+    URMB_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpb + warp;
+    uint8_t *sw = smem + (size_t)warp * A.spw;
+    const DevBatch &b = A.b;
+    const DevOut &o = A.o;
+    const SmemPlan pl{1u, 0u, 0u};
+    Env E;
+    make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
+    const uint32_t n_work = o.counters[CT_RQ_COUNT + round + 1];
+    const uint32_t *list = o.rq[(round + 1) & 1];
+    if (gw == 0 && lane == 0) atomicAdd(&o.counters[CT_RESCUE_DPS], n_work);
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&o.counters[CT_RQ_DP + round + 1], 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_work) break;
+        RescueSave *rs = o.rpool + list[k];
+        const uint32_t u = rs->h.unit;
+        const uint32_t pos = rs->h.p.dp_pos, len = rs->h.p.dp_len;
+        const bool plus = rs->h.p.dp_plus != 0;
+        const int mate = rs->h.p.dp_mate;
+        Mate m;
+        load_mate(E, m, b, A.pr, mate ? b.n_units + u : u, sw, &rs->m[mate].s, false);
+        int nrev = 0, ovf = 0;
+        const float Score = viterbi_warp<true>(E, mate_seq(m, plus), m.QL, E.ix.seq + pos, len, true, true, nrev, ovf);
+        __syncwarp();
+        for (int i = lane; i < nrev; i += 32) rs->h.dp_runs[i] = E.ws->runs_a[i];
+        if (lane == 0) {
+            rs->h.dp_score = Score;
+            rs->h.dp_nrev = nrev;
+            rs->h.dp_ovf = ovf;
+        }
         __syncwarp();
     }
 }
@@ -2578,6 +2765,9 @@ __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_kernel(const __grid_co
 __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_long_kernel(const __grid_constant__ KArgs A) { stage_body<6>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_c(const __grid_constant__ KArgs A) { stage_body<2>(A); }
 __global__ void __launch_bounds__(128, 4) finish_kernel(const __grid_constant__ KArgs A) { finish_body(A); }
+__global__ void __launch_bounds__(128, 5) rescue_scan_kernel(const __grid_constant__ KArgs A, int round) { rescue_scan_body<false>(A, round); }
+__global__ void __launch_bounds__(128, 4) rescue_last_kernel(const __grid_constant__ KArgs A, int round) { rescue_scan_body<true>(A, round); }
+__global__ void __launch_bounds__(128, 6) rescue_dp_kernel(const __grid_constant__ KArgs A, int round) { rescue_dp_body(A, round); }
 
 // =====================================================================================
 // host-side launchers
@@ -2607,9 +2797,9 @@ int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, cons
 }
 
 // Persistent grid: SMs x resident blocks (bounded by the per-warp scratch), work claimed by atomicAdd.
-template <class K>
+template <class K, class... X>
 static int launch_one(K kern, int klass, const LaunchTrace *tr, KArgs &A, const SmemPlan &pl, uint32_t max_items,
-                      const SearchRes &R, void *stream, int sm_count, int *warps_used) {
+                      const SearchRes &R, void *stream, int sm_count, int *warps_used, X... extra) {
     const int wpb = 4;
     A.spw = (uint32_t)smem_per_warp(A.b, pl);
     const size_t smem = (size_t)A.spw * wpb;
@@ -2624,7 +2814,7 @@ static int launch_one(K kern, int klass, const LaunchTrace *tr, KArgs &A, const 
     if (blocks < 1) blocks = 1;
     if (warps_used) *warps_used = blocks * wpb;
     if (tr) tr->mark(tr->user, klass, 0);
-    URMB_LAUNCH(kern, blocks, wpb * 32, smem, stream, A);
+    URMB_LAUNCH(kern, blocks, wpb * 32, smem, stream, A, extra...);
     if (tr) tr->mark(tr->user, klass, 1);
     return (int)cudaGetLastError();
 }
@@ -2692,13 +2882,26 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     return n;
 }
 
+// Mate rescue of the pairs finish_kernel found without a pair of hits: kRescueRounds rounds of
+// (rescue_scan_kernel, rescue_dp_kernel) over the rescue pool, a last round that finishes the stragglers in place, and the
+// legacy kernel (complete search from scratch) for the pairs that did not fit into the pool.
 int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
                   const SearchRes &R, void *stream, int sm_count, const LaunchTrace *tr) {
     if (!b.paired || P.pe_method == 5) return 0;
     KArgs A = make_kargs(ix, P, b, pr, o, R);
-    int e;
-    URMB_TRY(launch_one(rescue_kernel, 6, tr, A, SmemPlan{2, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
-    return 1;
+    int e, n = 0;
+    if (o.rpool && o.rescue_cap) {
+        const uint32_t cap = b.n_units < o.rescue_cap ? b.n_units : o.rescue_cap;
+        for (int r = 0; r < kRescueRounds; ++r) {
+            URMB_TRY(launch_one(rescue_scan_kernel, 6, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, r));
+            URMB_TRY(launch_one(rescue_dp_kernel, 8, tr, A, SmemPlan{1, 0, 0}, cap, R, stream, sm_count, nullptr, r));
+        }
+        URMB_TRY(launch_one(rescue_last_kernel, 6, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, (int)kRescueRounds));
+        n += 2 * kRescueRounds + 1;
+    }
+    URMB_TRY(launch_one(rescue_kernel, 9, tr, A, SmemPlan{2, 1, 1}, o.rpool ? (b.n_units < (uint32_t)(4 * sm_count) ? b.n_units : (uint32_t)(4 * sm_count)) : b.n_units,
+                        R, stream, sm_count, nullptr));
+    return n + 1;
 #undef URMB_TRY
 }
 

@@ -312,9 +312,9 @@ class ReferenceRunner:
                 "sam": sam, "reference_summary": own}
 
 
-def samdiff(a, b):
+def samdiff(a, b, unmatched=None):
     exe = os.path.join(ROOT, "urmap_b200", "bin", "samdiff")
-    p = subprocess.run([exe, a, b], capture_output=True, text=True)
+    p = subprocess.run([exe, a, b] + ([unmatched] if unmatched else []), capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"samdiff failed: {p.stderr[-200:]!r}")
     return json.loads(p.stdout)
@@ -383,7 +383,7 @@ def samdiff_prefix(ref_sam, cli_sam):
                 break
             g.write(ln)
             k += 1
-    d = samdiff(ref_sam, cut)
+    d = samdiff(ref_sam, cut, os.environ.get("URMB_BENCH_UNMATCHED") and os.environ["URMB_BENCH_UNMATCHED"] + "_main.txt")
     os.unlink(cut)
     return {"records": d["records_a"], "identical": d["identical"], "header_equal": d["header_equal"], "pct": d["pct"],
             "cli_records_compared": d["records_b"]}
@@ -444,7 +444,7 @@ KCLASS = {
     "probe": ("probe_kernel", "gather"), "pair": ("pair_kernel | seed_kernel_se", "state"),
     "align_a": ("align_kernel_a | align_kernel_se3", "dp"), "rows": ("rows_kernel | rows_kernel_se", "gather"),
     "rows_long": ("rows_long_kernel | rows_long_kernel_se", "gather"), "align_c": ("align_kernel_c | align_kernel_se6", "dp"),
-    "finish": ("finish_kernel", "state"), "rescue": ("rescue_scan_kernel | rescue_last_kernel", "gather"),
+    "finish": ("finish_kernel", "state"), "rescue": ("rescue_scan_kernel", "gather"), "rescue_last": ("rescue_last_kernel", "dp"),
     "rescue_dp": ("rescue_dp_kernel", "dp"),
     "rescue_legacy": ("rescue_kernel", "state"),
 }
@@ -850,7 +850,8 @@ def main():
                             n_reads += nu * (2 if kind_paired else 1)
                         rr = ref.run(px, kind_paired, n_reads, px + "_ref.sam", "configs " + ",".join(keys))
                         rc = run_cli_once(px, kind_paired, ufi_path, px + "_cli.sam", threads)
-                        d = samdiff(px + "_ref.sam", px + "_cli.sam")
+                        d = samdiff(px + "_ref.sam", px + "_cli.sam", os.environ.get("URMB_BENCH_UNMATCHED") and
+                                    os.environ["URMB_BENCH_UNMATCHED"] + ("_pe" if kind_paired else "_se") + ".txt")
                         for key in keys:
                             g = d["groups"].get(key, {})
                             configs[key]["sam_identity"] = {"records": g.get("records_a", 0), "identical": g.get("identical", 0),

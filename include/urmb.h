@@ -108,7 +108,8 @@ typedef struct urmb_index_desc {
 #define URMB_KCLASSES 12 /* 0 probe, 1 seed pairing (PE) / seeds (SE), 2 first HSP alignment, 3 rows (short rows), 4 final
                             HSP alignment, 5 pair finishing, 6 mate rescue: window scans continued from the saved pair states,
                             7 deferred long rows, 8 mate rescue: full-window DPs, 9 mate rescue: legacy kernel (pairs beyond
-                            the rescue pool, searched again from scratch), 10-11 reserved */
+                            the rescue pool, searched again from scratch), 10 mate rescue: last round (stragglers finished in
+                            place), 11 reserved */
 typedef struct urmb_timing {
     float probe_ms;  /* slot-probe / gather kernel */
     float search_ms; /* all search kernels on the compute stream (seed pairing, alignment, rows, finishing) */

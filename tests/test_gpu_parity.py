@@ -246,6 +246,34 @@ def test_chunk_size_invariance(eng, oracle, mid_env):
         ctx.close()
 
 
+def test_big_capacity_rerun_and_legacy_rescue(eng, oracle, mid_env):
+    """Reads that overflow a per-mate capacity are mapped again by the kernels compiled with big capacities (urmb_big.cu):
+    forced here for every third unit, the results must not change (SE and PE, path runs and second hits included).
+    The legacy mate-rescue kernel (no rescue pool) must agree with the rescue rounds as well."""
+    g, oix, hix = mid_env
+    r1, r2, _ = synth.sim_pe(g, 5000, 150, 0.04, 0.006, seed=21)
+    r2 = r2.copy()
+    r2[::20, :75] = r1[::20, :75]   # damaged mates: mate rescue
+    b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
+    o1, o2, uo = oracle.map_pe(oix, b1, b2, threads=os.cpu_count())
+    s1, us = oracle.map_se(oix, b1, threads=os.cpu_count())
+    for env in ({"URMB_FORCE_RERUN": "3"}, {"URMB_RESCUE_LEGACY": "1"}):
+        ctx = _ctx_with_env(eng, hix, env, want_second=True)
+        g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+        assert_same(np.concatenate([o1, o2]), uo, np.concatenate([g1, g2]), ug)
+        sec = [x.copy() for x in ctx.second_hits(0, b1.n)]
+        x1, ux = ctx.map_se(b1.seqs, b1.offs)
+        assert_same(s1, us, x1, ux)
+        assert ctx.overflow_count()[1] == 0
+        ctx.close()
+        ref = eng.Context(0, want_second=True)
+        ref.set_index(hix)
+        ref.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+        rs = ref.second_hits(0, b1.n)
+        assert (sec[0] == rs[0]).all() and (sec[1] == rs[1]).all()
+        ref.close()
+
+
 def test_human_scale_properties(eng):
     """BASELINE.json's full-size index (3.1 Gb reference, 27 GB table, built on the GPU) with properties that need no
     oracle: reads map back to where they were drawn from, results are idempotent, independent of the chunk size and of

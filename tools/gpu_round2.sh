@@ -28,14 +28,14 @@ tiny)
       > $OUT/bench_tiny.json 2> $OUT/bench_tiny.log; echo "tiny exit $?"
   tail -c 1500 $OUT/bench_tiny.log; head -c 600 $OUT/bench_tiny.json; echo ;;
 bench)
-  timeout 1700 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.log; echo "bench exit $?"
+  URMB_BENCH_UNMATCHED=$OUT/unmatched timeout 1700 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.log; echo "bench exit $?"
   tail -c 3000 $OUT/bench.log; head -c 1200 $OUT/bench.json; echo ;;
 benchq)
   timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-configs > $OUT/benchq.json 2> $OUT/benchq.log; echo "benchq exit $?"
   tail -c 800 $OUT/benchq.log ;;
 benchcfg)
-  timeout 1200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/benchcfg.json 2> $OUT/benchcfg.log; echo "benchcfg exit $?"
-  grep -E "config|main workload" $OUT/benchcfg.log ;;
+  URMB_DEBUG=${BENCH_DEBUG:-} timeout 1200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline $BENCHCFG_ARGS > $OUT/benchcfg.json 2> $OUT/benchcfg.log; echo "benchcfg exit $?"
+  grep -E "config|main workload" $OUT/benchcfg.log; grep "rescue rounds" $OUT/benchcfg.log | sort | uniq -c | sort -rn | head -12 ;;
 benchref)
   timeout 1500 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_ref.json 2> $OUT/bench_ref.log; echo "benchref exit $?"
   tail -c 1000 $OUT/bench_ref.log; cat $OUT/bench_ref.json ;;

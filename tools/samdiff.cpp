@@ -17,7 +17,7 @@
 #include <thread>
 #include <vector>
 
-struct H { uint64_t a, b; uint32_t g; bool operator<(const H &o) const { return a != o.a ? a < o.a : b < o.b; } bool operator==(const H &o) const { return a == o.a && b == o.b; } };
+struct H { uint64_t a, b; uint32_t g; uint32_t len; uint64_t off; bool operator<(const H &o) const { return a != o.a ? a < o.a : b < o.b; } bool operator==(const H &o) const { return a == o.a && b == o.b; } };
 
 static std::mutex g_mu;
 static std::vector<std::string> g_groups{std::string()};   // group names in order of first appearance; [0] = "" (no group);
@@ -49,7 +49,7 @@ static H hash_line(const char *p, size_t n) {
     memcpy(&w, p + i, n - i);
     a = mix(a ^ w ^ 0xabcdefull);
     b = mix(b + w);
-    return H{a, b, 0};
+    return H{a, b, 0, 0, 0};
 }
 
 struct File {
@@ -101,6 +101,8 @@ static bool load(const char *path, File &f) {
                     const size_t gl = (k < len && q[k] == '.') ? k : 0;
                     if (curlen != gl || (gl && memcmp(curp, q, gl) != 0)) { cur = group_of(q, len); curlen = gl; curp = q; }
                     h.g = cur;
+                    h.len = (uint32_t)len;
+                    h.off = (uint64_t)lo;
                     v.push_back(h);
                 }
                 lo += len + 1;
@@ -114,7 +116,14 @@ static bool load(const char *path, File &f) {
 }
 
 int main(int argc, char **argv) {
-    if (argc != 3) { fprintf(stderr, "usage: samdiff a.sam b.sam\n"); return 2; }
+    if (argc != 3 && argc != 4) { fprintf(stderr, "usage: samdiff a.sam b.sam [file for up to 400 unmatched records]\n"); return 2; }
+    FILE *fd = argc == 4 ? fopen(argv[3], "w") : nullptr;
+    size_t shown = 0;
+    auto show = [&](const File &f, const H &h, char tag) {
+        if (!fd || shown >= 400) return;
+        ++shown;
+        fprintf(fd, "%c\t%.*s\n", tag, (int)std::min<uint32_t>(h.len, 120), f.p + h.off);   // up to the CIGAR; not the bases
+    };
     File a, b;
     if (!load(argv[1], a) || !load(argv[2], b)) { fprintf(stderr, "cannot read input\n"); return 2; }
     size_t i = 0, j = 0, same = 0;
@@ -123,9 +132,12 @@ int main(int argc, char **argv) {
     for (auto &h : b.recs) ++gb[h.g];
     while (i < a.recs.size() && j < b.recs.size()) {
         if (a.recs[i] == b.recs[j]) { ++same; ++gs[a.recs[i].g]; ++i; ++j; }
-        else if (a.recs[i] < b.recs[j]) ++i;
-        else ++j;
+        else if (a.recs[i] < b.recs[j]) { show(a, a.recs[i], 'a'); ++i; }
+        else { show(b, b.recs[j], 'b'); ++j; }
     }
+    for (; i < a.recs.size(); ++i) show(a, a.recs[i], 'a');
+    for (; j < b.recs.size(); ++j) show(b, b.recs[j], 'b');
+    if (fd) fclose(fd);
     printf("{\"records_a\": %zu, \"records_b\": %zu, \"identical\": %zu, \"pct\": %.6f, \"header_equal\": %s, \"groups\": {", a.recs.size(),
            b.recs.size(), same, a.recs.empty() ? 0.0 : 100.0 * same / std::max(a.recs.size(), b.recs.size()),
            a.sq == b.sq ? "true" : "false");

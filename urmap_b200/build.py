@@ -18,7 +18,7 @@ def _stale(target, sources):
 def build_engine(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> urmap_b200/liburmb.so (+ bin/urmap_b200)."""
     out = None if verbose else subprocess.DEVNULL
-    args = ["make", "-C", CSRC]
+    args = ["make", "-j4", "-C", CSRC]
     if force:
         args.append("-B")
     subprocess.check_call(args, stdout=out)

@@ -22,6 +22,12 @@
 
 using namespace urmb;
 
+// urmb_big.cu: the same kernels with per-mate capacities no read can exceed (reads that overflowed the fast build)
+extern "C" size_t urmb_big_scratch_bytes();
+extern "C" size_t urmb_big_save_bytes();
+extern "C" int urmb_big_map(const void *ix, const void *P, const void *batch, const void *probe, const void *out, void *scratch,
+                            int n_scratch_warps, void *pool, uint32_t pool_pairs, void *stream, int sm_count);
+
 static std::string g_last_error;
 static std::mutex g_err_mu;
 
@@ -193,6 +199,23 @@ struct urmb_ctx {
     cudaEvent_t ev_rpool[2] = {nullptr, nullptr};   // end of the last rescue that used the pool
     bool rpool_used[2] = {false, false};
     int rparity = 0;
+    // Resources of the big-capacity rerun (urmb_big.cu), allocated when a batch first needs them
+    struct Big {
+        static constexpr uint32_t kUnits = 1024;   // units per rerun piece
+        static constexpr int kWarps = 256;         // per-warp scratch entries (bounds the grids)
+        cudaStream_t stream = nullptr;
+        uint8_t *d_seqs = nullptr, *d_tally = nullptr, *d_view = nullptr;
+        uint32_t *d_offs = nullptr, *d_pos = nullptr, *d_ext = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_rescue = nullptr;
+        urmb_result *d_res = nullptr, *h_res = nullptr;
+        urmb_second *d_second = nullptr, *h_second = nullptr;
+        uint16_t *d_runs = nullptr, *h_runs = nullptr;
+        uint32_t *h_counters = nullptr, *h_offs = nullptr;
+        void *scratch = nullptr, *pool = nullptr;
+        size_t seq_cap = 0, probe_cap = 0, view_cap = 0, runs_cap = 0;
+        bool ready = false;
+    } big;
+    uint64_t rerun_total = 0;      // reads mapped again by the big-capacity build
+    uint32_t force_rerun = 0;      // URMB_FORCE_RERUN=N (tests): every N-th unit is mapped again by the big-capacity build
     bool rescue_legacy = false;    // URMB_RESCUE_LEGACY: no rescue pool, every rescued pair is searched again from scratch
     uint32_t chunk_pairs = 524288; // URMB_CHUNK_PAIRS (step time at 1 M pairs: 92.9 / 86.0 / 82.5 / 82.1 ms for 128k / 256k / 512k / 1M)
     Slot slots[URMB_SLOTS];
@@ -260,6 +283,7 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     for (auto &ev : c->ev_mark) CK(cudaEventCreate(&ev));
     for (auto &ev : c->ev_rpool) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *f = getenv("URMB_RESCUE_LEGACY")) c->rescue_legacy = atoi(f) != 0;
+    if (const char *f = getenv("URMB_FORCE_RERUN")) c->force_rerun = (uint32_t)std::max(0, atoi(f));
     CK(cudaEventCreateWithFlags(&c->ev_rescue_tail, cudaEventDisableTiming));
     c->n_scratch_warps = max_search_warps(c->sm_count);
     // The rescue kernel is a queue of few, long work items that runs beside the next batch: a small persistent grid
@@ -302,6 +326,14 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     cudaFree(c->rescue_scratch);
     cudaFree(c->scratch);
     cudaFree(c->pool);
+    {
+        urmb_ctx::Big &g = c->big;
+        if (g.stream) cudaStreamDestroy(g.stream);
+        cudaFree(g.d_seqs); cudaFree(g.d_tally); cudaFree(g.d_view); cudaFree(g.d_offs); cudaFree(g.d_pos); cudaFree(g.d_ext);
+        cudaFree(g.d_counters); cudaFree(g.d_todo); cudaFree(g.d_rescue); cudaFree(g.d_res); cudaFree(g.d_second); cudaFree(g.d_runs);
+        cudaFree(g.scratch); cudaFree(g.pool);
+        cudaFreeHost(g.h_res); cudaFreeHost(g.h_second); cudaFreeHost(g.h_runs); cudaFreeHost(g.h_counters); cudaFreeHost(g.h_offs);
+    }
     for (int k = 0; k < 2; ++k) {
         cudaFree(c->rpool[k]);
         cudaFree(c->rq[k][0]);
@@ -844,6 +876,113 @@ extern "C" int urmb_submit(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
     return urmb_download(c, si);
 }
 
+// Reads whose search overflowed a per-mate capacity of the fast build (urmb_result.flags bit 7) are mapped again, still on
+// the GPU, by the same kernels compiled with capacities no read can exceed (urmb_big.cu); their records, path runs and second
+// hits replace the overflowed ones.  Runs on its own stream (the other slots' batches keep flowing); pieces of 1024 units.
+static int rerun_overflowed(urmb_ctx *c, Slot &s, uint32_t &used) {
+    const uint32_t n = s.batch.n_units, nreads = s.batch.n_reads;
+    const bool paired = s.batch.paired != 0;
+    std::vector<uint32_t> sel;
+    for (uint32_t u = 0; u < n; ++u)
+        if ((s.h_res[u].flags & 0x80) || (paired && (s.h_res[n + u].flags & 0x80))) sel.push_back(u);
+    if (sel.empty()) return URMB_OK;
+    urmb_ctx::Big &g = c->big;
+    const uint32_t KU = urmb_ctx::Big::kUnits, KR = 2 * KU;
+    const bool second = c->params.want_second && paired;
+    if (!g.ready) {
+        CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        CK(cudaMalloc(&g.d_offs, (KR + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&g.d_counters, CT_COUNT * sizeof(uint32_t)));
+        CK(cudaMalloc(&g.d_todo, (KU + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&g.d_rescue, (KU + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&g.d_res, (KR + 1) * sizeof(urmb_result)));
+        CK(cudaMalloc(&g.d_second, (KR + 1) * sizeof(urmb_second)));
+        g.runs_cap = (size_t)KR * 512 + 4096;
+        CK(cudaMalloc(&g.d_runs, g.runs_cap * sizeof(uint16_t)));
+        CK(cudaMalloc(&g.scratch, urmb_big_scratch_bytes() * (size_t)urmb_ctx::Big::kWarps));
+        CK(cudaMalloc(&g.pool, urmb_big_save_bytes() * 2 * 256));
+        CK(cudaHostAlloc(&g.h_res, (KR + 1) * sizeof(urmb_result), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&g.h_second, (KR + 1) * sizeof(urmb_second), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&g.h_runs, g.runs_cap * sizeof(uint16_t), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&g.h_counters, CT_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&g.h_offs, (KR + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+        g.ready = true;
+    }
+    int rc;
+    const size_t seq_need = (size_t)KR * s.batch.seqcap + 64, probe_need = (size_t)KR * 2 * s.batch.qcap;
+    const size_t view_need = (size_t)KR * view_stride_for(s.batch.seqcap) + 64;
+    if ((rc = grow_dev(c, g.d_seqs, g.seq_cap, seq_need))) return rc;
+    if ((rc = grow_dev(c, g.d_view, g.view_cap, view_need))) return rc;
+    if (probe_need > g.probe_cap) {
+        cudaFree(g.d_tally); cudaFree(g.d_pos); cudaFree(g.d_ext);
+        g.d_tally = nullptr; g.d_pos = nullptr; g.d_ext = nullptr;
+        g.probe_cap = 0;
+        CK(cudaMalloc(&g.d_tally, probe_need));
+        CK(cudaMalloc(&g.d_pos, probe_need * 4));
+        CK(cudaMalloc(&g.d_ext, probe_need * 4));
+        g.probe_cap = probe_need;
+    }
+    uint32_t still = 0;
+    for (size_t p0 = 0; p0 < sel.size(); p0 += KU) {
+        const uint32_t m = (uint32_t)std::min<size_t>(KU, sel.size() - p0), sub = paired ? 2 * m : m;
+        uint32_t o = 0;
+        for (uint32_t j = 0; j < sub; ++j) {   // sub-batch read j: mate 1 of unit sel[p0 + j], then the mates 2
+            const uint32_t k = (j < m) ? sel[p0 + j] : n + sel[p0 + j - m];
+            const uint32_t len = s.h_offs[k + 1] - s.h_offs[k];
+            g.h_offs[j] = o;
+            if (len) CK(cudaMemcpyAsync(g.d_seqs + o, s.d_seqs + s.h_offs[k], len, cudaMemcpyDeviceToDevice, g.stream));
+            o += len;
+        }
+        g.h_offs[sub] = o;
+        CK(cudaMemcpyAsync(g.d_offs, g.h_offs, (sub + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemsetAsync(g.d_counters, 0, CT_COUNT * sizeof(uint32_t), g.stream));
+        if (second) CK(cudaMemsetAsync(g.d_second, 0, (size_t)sub * sizeof(urmb_second), g.stream));
+        DevBatch b = s.batch;
+        b.seqs = g.d_seqs;
+        b.offs = g.d_offs;
+        b.n_reads = sub;
+        b.n_units = m;
+        DevProbe pr{g.d_tally, g.d_pos, g.d_ext, g.d_view, view_stride_for(b.seqcap)};
+        DevOut out{g.d_res, g.d_runs, (uint32_t)g.runs_cap, g.d_counters, g.d_todo, g.d_rescue, second ? g.d_second : nullptr,
+                   nullptr, 0u, {nullptr, nullptr}};
+        const int e = urmb_big_map(&c->ix, &c->P, &b, &pr, &out, g.scratch, urmb_ctx::Big::kWarps, g.pool, 256, g.stream, c->sm_count);
+        if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun: ") + cudaGetErrorString((cudaError_t)-e));
+        c->launches += (uint64_t)e;
+        CK(cudaMemcpyAsync(g.h_counters, g.d_counters, CT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaMemcpyAsync(g.h_res, g.d_res, (size_t)sub * sizeof(urmb_result), cudaMemcpyDeviceToHost, g.stream));
+        if (second) CK(cudaMemcpyAsync(g.h_second, g.d_second, (size_t)sub * sizeof(urmb_second), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        const uint32_t bused = std::min<uint32_t>(g.h_counters[CT_RUNS], (uint32_t)g.runs_cap);
+        if (bused) {
+            CK(cudaMemcpyAsync(g.h_runs, g.d_runs, (size_t)bused * 2, cudaMemcpyDeviceToHost, g.stream));
+            CK(cudaStreamSynchronize(g.stream));
+            if ((size_t)used + bused > s.h_runs_cap) {   // grow the slot's host run pool, keeping its contents
+                uint16_t *nr = nullptr;
+                const size_t ncap = ((size_t)used + bused) * 2 + 4096;
+                CK(cudaHostAlloc(&nr, ncap * sizeof(uint16_t), cudaHostAllocDefault));
+                if (used) memcpy(nr, s.h_runs, (size_t)used * 2);
+                cudaFreeHost(s.h_runs);
+                s.h_runs = nr;
+                s.h_runs_cap = ncap;
+            }
+            memcpy(s.h_runs + used, g.h_runs, (size_t)bused * 2);
+        }
+        for (uint32_t j = 0; j < sub; ++j) {
+            const uint32_t k = (j < m) ? sel[p0 + j] : n + sel[p0 + j - m];
+            urmb_result r = g.h_res[j];
+            if (r.path_runs) r.path_off += used;
+            if (r.flags & 0x80) ++still;
+            s.h_res[k] = r;
+            if (second) s.h_second[k] = g.h_second[j];
+        }
+        used += bused;
+        c->rerun_total += sub;
+    }
+    s.h_counters[CT_OVERFLOW] = still;
+    (void)nreads;
+    return URMB_OK;
+}
+
 extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const urmb_result **res2, const uint16_t **runs,
                          uint32_t *runs_used) {
     if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
@@ -871,7 +1010,22 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
     }
     CK(cudaEventRecord(s.ev_d2h, s.copy));
     CK(cudaStreamSynchronize(s.copy));
+    if (c->force_rerun && !s.counted) {   // test hook: every force_rerun-th unit takes the big-capacity path as well
+        for (uint32_t u = 0; u < s.batch.n_units; u += c->force_rerun) s.h_res[u].flags |= 0x80;
+        s.h_counters[CT_OVERFLOW] += (s.batch.n_units + c->force_rerun - 1) / c->force_rerun;
+    }
+    if (s.h_counters[CT_OVERFLOW] != 0 && !s.counted && !getenv("URMB_NO_RERUN")) {
+        const uint32_t before = s.h_counters[CT_OVERFLOW];
+        int rc = rerun_overflowed(c, s, used);
+        if (rc) return rc;
+        if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u read(s) over a per-mate capacity mapped again by the big-capacity build, %u still over\n", si, before, s.h_counters[CT_OVERFLOW]);
+    }
     if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u rescued (%u by the legacy kernel, %u full-window DPs), %u path runs\n", si, s.batch.n_units, s.h_counters[CT_TODO_TOTAL], s.h_counters[CT_RESCUE], s.h_counters[CT_RESCUE_LEGACY], s.h_counters[CT_RESCUE_DPS], used);
+    if (getenv("URMB_DEBUG") && s.batch.paired) {
+        fprintf(stderr, "[urmb] slot %d: rescue rounds, pairs stopped at a full-window DP:", si);
+        for (int r = 1; r <= kRescueRounds + 1; ++r) fprintf(stderr, " %u", s.h_counters[CT_RQ_COUNT + r]);
+        fprintf(stderr, "\n");
+    }
     if (res1) *res1 = s.h_res;
     if (res2) *res2 = s.batch.paired ? s.h_res + s.batch.n_units : nullptr;
     if (runs) *runs = s.h_runs;
@@ -925,7 +1079,7 @@ extern "C" int urmb_timing_last(urmb_ctx *c, int si, urmb_timing *t) {
             t->kernel_launches[k] += 1;
         }
     }
-    t->rescue_ms = t->kernel_ms[6] + t->kernel_ms[8] + t->kernel_ms[9];
+    t->rescue_ms = t->kernel_ms[6] + t->kernel_ms[8] + t->kernel_ms[9] + t->kernel_ms[10];
     if (cudaEventQuery(s.ev_h2d) == cudaSuccess) cudaEventElapsedTime(&t->h2d_ms, s.ev_h2d0, s.ev_h2d);
     if (cudaEventQuery(s.ev_d2h) == cudaSuccess && cudaEventQuery(s.ev_k2) == cudaSuccess)
         cudaEventElapsedTime(&t->d2h_ms, s.ev_k2, s.ev_d2h);

@@ -4,11 +4,26 @@
 
 #include "../../include/urmb.h"
 
-namespace urmb {
+// The kernels are compiled twice: namespace urmb with the capacities every read normally fits into, and namespace urmb_big
+// (urmb_big.cu, -DURMB_BIG) with capacities no read of up to URMB_MAX_READ_LEN bases can exceed (2 strands x 233 k-mers x
+// MaxIx 32 positions = 14 912 candidates, each at most one hit or one HSP): the reads that overflow the first are mapped
+// again by the second (urmb_wait), so that results do not depend on a capacity (the reference's lists grow, state1.cpp:190).
+#ifndef URMB_NS
+#define URMB_NS urmb
+#endif
+namespace URMB_NS {
 
+#ifdef URMB_BIG
+constexpr int kHitCap = 16384;
+constexpr int kHspCap = 16384;
+constexpr int kRunCap = 192;
+constexpr int kRunPool = 32768;
+#else
 constexpr int kHitCap = 256;    // hits kept per mate (reference grows without bound, state1.cpp:190)
 constexpr int kHspCap = 256;    // HSPs kept per mate
 constexpr int kRunCap = 64;     // RLE runs per stored path
+constexpr int kRunPool = 2048;  // path runs of all hits of one mate
+#endif
 constexpr int kMaxLen = URMB_MAX_READ_LEN;
 constexpr int kScanSeg = 1024;  // SCAN_DB_SEG_LENGTH, state2.cpp:91
 constexpr int kBigCols = kScanSeg + 2 * kMaxLen + 8;   // widest mate-rescue window (+1 column)
@@ -92,8 +107,6 @@ struct DevOut {
     uint32_t rescue_cap;
     uint32_t *rq[2];       // [rescue_cap] each: work lists of the rescue rounds (pool entry indexes), ping-pong
 };
-
-constexpr int kRunPool = 2048;  // path runs of all hits of one mate
 
 struct MateScratch {
     uint32_t hit_pos[kHitCap];
@@ -192,4 +205,4 @@ size_t packed_words(size_t n_bytes);
 size_t coarse_words(size_t n_bytes);
 int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint32_t *seqx, uint32_t *seqc, void *stream);
 
-}  // namespace urmb
+}  // namespace URMB_NS

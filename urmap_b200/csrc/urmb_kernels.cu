@@ -24,7 +24,7 @@
 
 #include "urmb_internal.h"
 
-namespace urmb {
+namespace URMB_NS {
 
 #define FULL 0xffffffffu
 
@@ -2896,7 +2896,7 @@ int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
             URMB_TRY(launch_one(rescue_scan_kernel, 6, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, r));
             URMB_TRY(launch_one(rescue_dp_kernel, 8, tr, A, SmemPlan{1, 0, 0}, cap, R, stream, sm_count, nullptr, r));
         }
-        URMB_TRY(launch_one(rescue_last_kernel, 6, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, (int)kRescueRounds));
+        URMB_TRY(launch_one(rescue_last_kernel, 10, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, (int)kRescueRounds));
         n += 2 * kRescueRounds + 1;
     }
     URMB_TRY(launch_one(rescue_kernel, 9, tr, A, SmemPlan{2, 1, 1}, o.rpool ? (b.n_units < (uint32_t)(4 * sm_count) ? b.n_units : (uint32_t)(4 * sm_count)) : b.n_units,
@@ -2905,4 +2905,4 @@ int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
 #undef URMB_TRY
 }
 
-}  // namespace urmb
+}  // namespace URMB_NS

@@ -64,7 +64,7 @@ class Timing(C.Structure):
 
 
 KERNEL_CLASSES = ("probe", "pair", "align_a", "rows", "align_c", "finish", "rescue", "rows_long", "rescue_dp",
-                  "rescue_legacy", "k10", "k11")
+                  "rescue_legacy", "rescue_last", "k11")
 
 
 EXPORTS = [

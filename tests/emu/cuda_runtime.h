@@ -41,7 +41,7 @@ template <class F> inline int cudaFuncSetAttribute(F, int, int) { return 0; }
 template <class F> inline int cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return 0; }
 
 namespace emu {
-enum Kind { K_NONE, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_BALLOT, K_ANY, K_SYNC };
+enum Kind { K_NONE, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_BALLOT, K_ANY, K_SYNC };
 uint64_t collective(Kind kind, uint64_t value, int arg, int site);
 uint8_t *smem_base();
 void launch(const std::function<void()> &body, int grid, int block, size_t smem);
@@ -65,18 +65,23 @@ template <class T> inline T emu_shfl_up(T v, unsigned delta, int line) {
 template <class T> inline T emu_shfl_down(T v, unsigned delta, int line) {
     return emu_unbits<T>(emu::collective(emu::K_SHFL_DOWN, emu_bits(v), (int)delta, line));
 }
+template <class T> inline T emu_shfl_xor(T v, int mask, int line) {
+    return emu_unbits<T>(emu::collective(emu::K_SHFL_XOR, emu_bits(v), mask, line));
+}
 inline unsigned emu_ballot(int pred, int line) { return (unsigned)emu::collective(emu::K_BALLOT, pred ? 1 : 0, 0, line); }
 inline int emu_any(int pred, int line) { return (int)emu::collective(emu::K_ANY, pred ? 1 : 0, 0, line); }
 inline void emu_syncwarp(int line) { emu::collective(emu::K_SYNC, 0, 0, line); }
 #define __shfl_sync(m, v, l) emu_shfl((v), (l), __LINE__)
 #define __shfl_up_sync(m, v, d) emu_shfl_up((v), (d), __LINE__)
 #define __shfl_down_sync(m, v, d) emu_shfl_down((v), (d), __LINE__)
+#define __shfl_xor_sync(m, v, d) emu_shfl_xor((v), (d), __LINE__)
 #define __ballot_sync(m, p) emu_ballot((p), __LINE__)
 #define __any_sync(m, p) emu_any((p), __LINE__)
 #define __syncwarp() emu_syncwarp(__LINE__)
 
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 inline unsigned atomicSub(unsigned *p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
 inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
 inline void __syncthreads() {}

@@ -87,6 +87,7 @@ static void run_warp(int warp) {
                 case K_SHFL: L.result = g_lanes[L.arg & 31].value; break;
                 case K_SHFL_UP: L.result = (l - L.arg >= 0) ? g_lanes[l - L.arg].value : L.value; break;
                 case K_SHFL_DOWN: L.result = (l + L.arg < 32) ? g_lanes[l + L.arg].value : L.value; break;
+                case K_SHFL_XOR: L.result = g_lanes[(l ^ L.arg) & 31].value; break;
                 case K_BALLOT: L.result = bal; break;
                 case K_ANY: L.result = bal != 0; break;
                 default: L.result = 0; break;

@@ -182,8 +182,10 @@ struct urmb_ctx {
     cudaStream_t compute = nullptr;
     cudaStream_t rescue = nullptr;            // low-priority side stream of the mate-rescue kernel
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
-    cudaEvent_t ev_rescue_tail = nullptr;     // last event recorded on the rescue stream
-    bool rescue_used = false;
+    cudaStream_t rescue2 = nullptr;           // second side stream: consecutive launches alternate, so that the rescue rounds
+                                              // of a batch never queue behind the (occasionally long) tail of the batch before
+    cudaEvent_t ev_rescue_tail[2] = {nullptr, nullptr};   // last event recorded on each rescue stream
+    bool rescue_used[2] = {false, false};
     bool rescue_inline = false;               // URMB_RESCUE_INLINE: run the rescue kernel on the compute stream
     WarpScratch *scratch = nullptr;
     int n_scratch_warps = 0;
@@ -280,18 +282,19 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->compute, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&c->rescue, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&c->rescue2, cudaStreamNonBlocking, prio_lo));
     for (auto &ev : c->ev_mark) CK(cudaEventCreate(&ev));
     for (auto &ev : c->ev_rpool) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *f = getenv("URMB_RESCUE_LEGACY")) c->rescue_legacy = atoi(f) != 0;
     if (const char *f = getenv("URMB_FORCE_RERUN")) c->force_rerun = (uint32_t)std::max(0, atoi(f));
-    CK(cudaEventCreateWithFlags(&c->ev_rescue_tail, cudaEventDisableTiming));
+    for (auto &ev : c->ev_rescue_tail) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     c->n_scratch_warps = max_search_warps(c->sm_count);
     // The rescue kernel is a queue of few, long work items that runs beside the next batch: a small persistent grid
     // (one block per SM) takes few registers away from the main kernels and still drains the queue in time.
     c->n_rescue_warps = c->sm_count * 12;
     if (const char *f = getenv("URMB_RESCUE_WARPS")) c->n_rescue_warps = std::max(4, atoi(f) & ~3);
     if (const char *f = getenv("URMB_RESCUE_INLINE")) c->rescue_inline = atoi(f) != 0;
-    CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps));
+    CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps * 2));   // one set per side stream
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
     for (auto &s : c->slots) {
@@ -321,8 +324,9 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     for (auto &s : c->slots) free_slot(s);
     if (c->compute) cudaStreamDestroy(c->compute);
     if (c->rescue) cudaStreamDestroy(c->rescue);
+    if (c->rescue2) cudaStreamDestroy(c->rescue2);
     for (auto ev : c->ev_mark) if (ev) cudaEventDestroy(ev);
-    if (c->ev_rescue_tail) cudaEventDestroy(c->ev_rescue_tail);
+    for (auto ev : c->ev_rescue_tail) if (ev) cudaEventDestroy(ev);
     cudaFree(c->rescue_scratch);
     cudaFree(c->scratch);
     cudaFree(c->pool);
@@ -542,6 +546,7 @@ static int size_rescue_pools(urmb_ctx *c, size_t n) {
     if (want <= c->rescue_cap) return URMB_OK;
     CK(cudaStreamSynchronize(c->compute));
     CK(cudaStreamSynchronize(c->rescue));
+    CK(cudaStreamSynchronize(c->rescue2));
     for (int k = 0; k < 2; ++k) {
         cudaFree(c->rpool[k]); cudaFree(c->rq[k][0]); cudaFree(c->rq[k][1]);
         c->rpool[k] = nullptr; c->rq[k][0] = c->rq[k][1] = nullptr;
@@ -760,6 +765,8 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     Slot &s = c->slots[si];
     if (!s.staged) return fail(c, URMB_E_ARG, "slot not staged");
     CK(cudaSetDevice(c->device));
+    const int side_ix = c->rparity;            // side stream and rescue pool of this launch (both alternate)
+    cudaStream_t side = side_ix ? c->rescue2 : c->rescue;
     CK(cudaStreamWaitEvent(c->compute, s.ev_h2d, 0));
     if (s.launched) CK(cudaStreamWaitEvent(c->compute, s.ev_rescue, 0));   // an earlier launch of this very slot
     CK(cudaMemsetAsync(s.d_counters, 0, CT_COUNT * sizeof(uint32_t), c->compute));
@@ -793,8 +800,8 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         CK(cudaEventRecord(s.ev_k2, c->compute));
         // Mate rescue: few, long work items.  It runs on the low-priority side stream so that its tail overlaps the
         // kernels of the next batch instead of idling the GPU.
-        SearchRes RR{c->rescue_scratch, c->n_rescue_warps, nullptr, 0};
-        cudaStream_t rs = c->rescue_inline ? c->compute : c->rescue;
+        SearchRes RR{c->rescue_scratch + (size_t)side_ix * c->n_rescue_warps, c->n_rescue_warps, nullptr, 0};
+        cudaStream_t rs = c->rescue_inline ? c->compute : side;
         CK(cudaStreamWaitEvent(rs, s.ev_k2, 0));
         tc.stream = rs;
         e = launch_rescue(c->ix, P, s.batch, pr, o, c->rescue_inline ? R : RR, rs, c->sm_count, &tr);
@@ -811,10 +818,10 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         CK(cudaEventRecord(s.ev_k1, c->compute));
         CK(cudaEventRecord(s.ev_k2, c->compute));
     }
-    if (!rescued) CK(cudaStreamWaitEvent(c->rescue, s.ev_k2, 0));
-    CK(cudaEventRecord(s.ev_rescue, c->rescue));
-    CK(cudaEventRecord(c->ev_rescue_tail, c->rescue));
-    c->rescue_used = true;
+    if (!rescued) CK(cudaStreamWaitEvent(side, s.ev_k2, 0));
+    CK(cudaEventRecord(s.ev_rescue, side));
+    CK(cudaEventRecord(c->ev_rescue_tail[side_ix], side));
+    c->rescue_used[side_ix] = true;
     s.launched = true;
     s.downloaded = false;
     return URMB_OK;
@@ -823,7 +830,8 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
 extern "C" int urmb_mark(urmb_ctx *c, int which) {
     if (!c || which < 0 || which > 1) return URMB_E_ARG;
     CK(cudaSetDevice(c->device));
-    if (c->rescue_used) CK(cudaStreamWaitEvent(c->compute, c->ev_rescue_tail, 0));
+    for (int k = 0; k < 2; ++k)
+        if (c->rescue_used[k]) CK(cudaStreamWaitEvent(c->compute, c->ev_rescue_tail[k], 0));
     CK(cudaEventRecord(c->ev_mark[which], c->compute));
     return URMB_OK;
 }
@@ -1024,6 +1032,16 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
     if (getenv("URMB_DEBUG") && s.batch.paired) {
         fprintf(stderr, "[urmb] slot %d: rescue rounds, pairs stopped at a full-window DP:", si);
         for (int r = 1; r <= kRescueRounds + 1; ++r) fprintf(stderr, " %u", s.h_counters[CT_RQ_COUNT + r]);
+        fprintf(stderr, "; pairs by scan windows (<=4, <=16, <=64, <=256, more): %u %u %u %u %u; longest pair %.2f Mticks (%u windows, round %u)\n",
+                s.h_counters[CT_DBG_WIN], s.h_counters[CT_DBG_WIN + 1], s.h_counters[CT_DBG_WIN + 2], s.h_counters[CT_DBG_WIN + 3],
+                s.h_counters[CT_DBG_WIN + 4], s.h_counters[CT_DBG_MAXT] * 1024.0 / 1e6, s.h_counters[CT_DBG_MAXW] & 0xFFFFFFu,
+                s.h_counters[CT_DBG_MAXW] >> 24);
+        fprintf(stderr, "[urmb] slot %d: launches of the last step (class:ms):", si);
+        for (size_t i = 0; i < s.nkev; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s.kev[2 * i], s.kev[2 * i + 1]) == cudaSuccess) fprintf(stderr, " %d:%.2f", s.kclass[i], ms);
+        }
+        cudaGetLastError();
         fprintf(stderr, "\n");
     }
     if (res1) *res1 = s.h_res;

@@ -91,7 +91,12 @@ enum {
     CT_RQ_COUNT = 16,                           // [kRescueRounds + 2] entries of list r
     CT_RQ_SCAN = CT_RQ_COUNT + kRescueRounds + 2,   // [kRescueRounds + 2] work-queue heads of the scan kernels
     CT_RQ_DP = CT_RQ_SCAN + kRescueRounds + 2,      // [kRescueRounds + 2] work-queue heads of the DP kernels
-    CT_COUNT = CT_RQ_DP + kRescueRounds + 2
+    // statistics of the mate rescue (URMB_DEBUG): pairs by number of scan windows at entry (<= 4, <= 16, <= 64, <= 256, more),
+    // longest time one pair spent in a scan kernel (clock64 ticks >> 10) and its number of windows
+    CT_DBG_WIN = CT_RQ_DP + kRescueRounds + 2,      // [5]
+    CT_DBG_MAXT = CT_DBG_WIN + 5,
+    CT_DBG_MAXW = CT_DBG_MAXT + 1,
+    CT_COUNT = CT_DBG_MAXW + 1
 };
 
 struct RescueSave;

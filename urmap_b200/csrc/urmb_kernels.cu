@@ -2672,6 +2672,10 @@ __device__ __forceinline__ void rescue_scan_body(const KArgs &A, int round) {
         load_mate(E, R, b, A.pr, b.n_units + u, sw + msz, &rs->m[1].s, false);
         hdr_to_mate(rs->m[0].h, F);
         hdr_to_mate(rs->m[1].h, R);
+#ifndef URMB_EMU
+        const long long t_in = clock64();
+#endif
+        int nwin = 0;
         if (h.state == 0) {   // State2::ScanPair entry, state2.cpp:87-98
             h.loop = 0;
             h.h = 0;
@@ -2679,6 +2683,11 @@ __device__ __forceinline__ void rescue_scan_body(const KArgs &A, int round) {
             h.hcR = R.HitCount;
             h.dovF = ((int)F.Mapq >= 10) ? 1 : 0;
             h.dovR = ((int)R.Mapq >= 10) ? 1 : 0;
+            // scan windows this pair starts with (statistics; the second loop's bound can still rise)
+            for (int k = lane; k < max(F.HitCount, R.HitCount); k += 32)
+                nwin += (k < F.HitCount && (int)F.g->hit_score[k] >= F.Second) + (k < R.HitCount && (int)R.g->hit_score[k] >= R.Second);
+            for (int d = 16; d; d >>= 1) nwin += __shfl_xor_sync(FULL, nwin, d);
+            if (lane == 0) atomicAdd(&o.counters[CT_DBG_WIN + (nwin <= 4 ? 0 : nwin <= 16 ? 1 : nwin <= 64 ? 2 : nwin <= 256 ? 3 : 4)], 1u);
         } else {              // the DP this pair stopped at has been run
             Mate &dst = h.dp_mate ? R : F;
             scan_mate_post(E, dst, h.dp_pos, h.dp_plus != 0, rs->h.dp_score, rs->h.dp_runs, rs->h.dp_nrev, rs->h.dp_ovf);
@@ -2699,6 +2708,12 @@ __device__ __forceinline__ void rescue_scan_body(const KArgs &A, int round) {
                 next[atomicAdd(&o.counters[CT_RQ_COUNT + round + 1], 1u)] = e;
             }
         }
+#ifndef URMB_EMU
+        if (lane == 0) {
+            const uint32_t dt = (uint32_t)((clock64() - t_in) >> 10);
+            if (atomicMax(&o.counters[CT_DBG_MAXT], dt) < dt) o.counters[CT_DBG_MAXW] = (uint32_t)nwin | ((uint32_t)round << 24);
+        }
+#endif
         __syncwarp();
     }
 }

@@ -201,6 +201,42 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     return nk < 0 ? nk : 0;
 }
 
+// One flank DP (State1::Viterbi through flank_viterbi: band across the lanes when it fits) under emulation: score and the
+// forward path string ("M", "D", "I" as in the reference).  B must stay readable for 64 bytes past LB.
+static void emu_dp_kernel(Env E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB, bool Left, bool Right, float *score,
+                          int *nrev, int *ovf) {
+    URMB_DYN_SMEM(smem);
+    E.lane = (int)(threadIdx.x & 31);
+    E.s_win = smem;
+    E.s_tb = smem + kMaxLen + 64;
+    for (uint32_t k = E.lane; k < LB; k += 32) E.s_win[k] = B[k];
+    __syncwarp();
+    int n = 0, o = 0;
+    const float sc = flank_viterbi(E, A, LA, 0, LB, Left, Right, n, o);
+    if (E.lane == 0) { *score = sc; *nrev = n; *ovf = o; }
+}
+extern "C" float emu_flank_dp(const urmb_params *p, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB, int left, int right,
+                              char *path /* LA + LB + 1 */, int *ovf) {
+    static WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch));
+    Env E;
+    E.P = emu_make_params(*p);
+    E.ix = DevIndex{};
+    E.ix.seq = B;   // viterbi_warp<true> reads the window from ix.seq + TLo (TLo = 0)
+    E.ws = ws;
+    E.tb_rows = kMaxLen + 2;
+    E.tb_stride = 4 * E.P.R + 6;
+    float sc = 0;
+    int nrev = 0, o = 0;
+    const size_t smem = (size_t)kMaxLen + 64 + (size_t)E.tb_rows * 32 + E.tb_rows + 66 + 64;
+    emu::launch([&]() { emu_dp_kernel(E, A, LA, B, LB, left != 0, right != 0, &sc, &nrev, &o); }, 1, 32, smem);
+    size_t k = 0;
+    for (int r = nrev - 1; r >= 0; --r)
+        for (uint32_t t = 0; t < (uint32_t)(ws->runs_a[r] >> 2); ++t) path[k++] = "MDI"[ws->runs_a[r] & 3];
+    path[k] = 0;
+    if (ovf) *ovf = o;
+    return sc;
+}
+
 // Device index builder under emulation (scan passes done on the host: they use __syncthreads).
 extern "C" int emu_build_index(const uint8_t *seq, uint64_t seq_size, uint64_t slot_count, uint32_t word_len,
                                uint32_t max_ix, uint8_t *blob /* 5*slot_count+16 */, uint64_t *stats) {

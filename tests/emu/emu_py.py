@@ -69,3 +69,18 @@ def emu_build_index(seq: np.ndarray, slot_count: int, word_len: int = 24, max_ix
                            C.c_uint32(max_ix), blob.ctypes.data_as(vp), stats.ctypes.data_as(vp))
     assert rc == 0
     return blob[:5 * slot_count], stats
+
+
+def emu_flank_dp(A: bytes, B: bytes, left: bool, right: bool, method=6, band_radius=-1):
+    """One flank DP of the kernels (flank_viterbi) under emulation: (score, path string, overflowed)."""
+    L = lib()
+    L.emu_flank_dp.restype = C.c_float
+    p = Params(method, 4, band_radius, 10, 0)
+    a = np.frombuffer(A, dtype=np.uint8).copy()
+    b = np.concatenate([np.frombuffer(B, dtype=np.uint8), np.zeros(64, dtype=np.uint8)])
+    buf = C.create_string_buffer(len(A) + len(B) + 8)
+    ovf = C.c_int(0)
+    vp = C.c_void_p
+    sc = L.emu_flank_dp(C.byref(p), a.ctypes.data_as(vp), C.c_uint32(len(A)), b.ctypes.data_as(vp), C.c_uint32(len(B)),
+                        C.c_int(int(left)), C.c_int(int(right)), buf, C.byref(ovf))
+    return float(sc), buf.value.decode(), bool(ovf.value)

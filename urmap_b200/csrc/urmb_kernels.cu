@@ -1062,6 +1062,7 @@ __device__ __noinline__ float viterbi_warp(const Env &E, const uint8_t *A, uint3
 // Rows are sequential (LA <= 126 steps of ~100 instructions) and no lane idles in a wavefront ramp.
 // Trace bits: one byte per lane per row (two nibbles) in shared memory, TB[i][LB] and row LA kept separately,
 // TB[i][Startj-1] = IM (viterbi.cpp:119) answered on the fly.
+#ifdef URMB_BAND_F32
 __device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB,
                                            bool Left, bool Right, int &n_rev, int &ovf) {
     const int lane = E.lane;
@@ -1233,6 +1234,205 @@ __device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint3
     runs_append(rev, n_rev, curop, curlen, kRunCap, ovf, lane);
     return Score;
 }
+#else
+// Integer form (default).  Every finite value of the reference's fp32 DP is a small integer, and MINUS_INFINITY only ever
+// loses a comparison against a finite value, so 32-bit integers with NEG = -2^28 give the same scores and -- on every cell
+// a traceback can visit, where at least one operand of each comparison is finite -- the same trace bits (two "minus
+// infinities" compare differently here than in fp32, where NEG + k == NEG, but such cells are unreachable).  Against the
+// fp32 form: no special cases for column 0 (row 0 is seeded through the previous-row registers), the Drow[LB] column is
+// only computed on the rows whose band reaches it, the scan needs no lane predicate, and the traceback walks whole runs
+// (32 cells of a diagonal / column / row per step) instead of one cell at a time.
+__device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB,
+                                           bool Left, bool Right, int &n_rev, int &ovf) {
+    const int lane = E.lane;
+    uint16_t *rev = E.ws->runs_a;
+    n_rev = 0;
+    constexpr int NEG = -(1 << 28);
+    const int GO = E.P.GO, GE = E.P.GE, MMs = E.P.MM;
+    uint32_t dlo = min(LA, LB), dhi = max(LA, LB);
+    if (dlo > E.P.R) dlo -= E.P.R; else dlo = 1;
+    dhi += E.P.R;
+    if (dhi > LA + LB - 1) dhi = LA + LB - 1;
+    const int BW = (int)(dhi - dlo) + 1;
+    uint8_t *tb = E.s_tb;
+    uint8_t *collb = tb + (size_t)E.tb_rows * 32;
+    uint8_t *rowla = collb + E.tb_rows;
+    const int c0 = 2 * lane, c1 = c0 + 1;
+    // previous row at my coordinates; M0 of cell (0, 0) is 0 (viterbi.cpp:106-116): column 0 of row 0 has coordinate LA - dlo
+    const int cz = (int)LA - (int)dlo;
+    int pM0 = (c0 == cz) ? 0 : NEG, pM1 = (c1 == cz) ? 0 : NEG, pD0 = NEG, pD1 = NEG;
+    int DLB = NEG;                                                 // Drow[LB]
+#pragma unroll 1
+    for (uint32_t i = 0; i < LA; ++i) {
+        const int j0 = (int)dlo + (int)i - (int)LA;
+        const int ja = j0 + c0, jb = ja + 1;
+        const bool ina = c0 < BW && ja >= 0 && ja < (int)LB, inb = c1 < BW && jb >= 0 && jb < (int)LB;
+        const int a = (int)A[i];
+        const bool free0 = Left && i == 0;
+        const int openA = free0 ? 0 : GO, nextA = free0 ? 0 : -GE;   // nextA = -extA >= 0
+        int upDb = __shfl_down_sync(FULL, pD0, 1);
+        if (lane == 31) upDb = NEG;
+        const int upDa = pD1;
+        // Drow[LB] (viterbi.cpp:187-200): M0 after the row loop is the previous row's M at column Endj-1; before the band
+        // reaches column LB both operands are minus infinity and the reference's ">=" sets the bit
+        {
+            const int e = (int)LB - j0;   // previous-row coordinate of column Endj-1 when the band is clipped at LB
+            uint8_t t = TB_MD;
+            if (e >= 0 && e < BW) {       // uniform
+                const int t0 = __shfl_sync(FULL, pM0, e >> 1), t1 = __shfl_sync(FULL, pM1, e >> 1);
+                const int md = ((e & 1) ? t1 : t0) + GO;
+                DLB += GE;
+                t = 0;
+                if (md >= DLB) { DLB = md; t = TB_MD; }
+            }
+            if (lane == 0) collb[i] = t;
+        }
+        // I chain: prefix max of V over the band
+        const int Va = ina ? (pM0 + openA) + c0 * nextA : NEG;
+        const int Vb = inb ? (pM1 + openA) + c1 * nextA : NEG;
+        int inc = max(Va, Vb);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) inc = max(inc, __shfl_up_sync(FULL, inc, d));   // lanes below d get their own value back
+        int Ua = __shfl_up_sync(FULL, inc, 1);   // U_{c0-1}
+        if (lane == 0) Ua = NEG;
+        const int Ub = max(Ua, Va);              // U_{c1-1}
+        const int Ia = Ua - (c0 - 1) * nextA, Ib = Ub - (c1 - 1) * nextA;
+        int Ma = NEG, Mb = NEG, Da = NEG, Db = NEG;
+        uint32_t bits = 0;
+        if (ina) {
+            uint32_t t = 0;
+            int xM = pM0;
+            if (upDa > xM) { xM = upDa; t = TB_DM; }
+            if (Ia > xM) { xM = Ia; t = TB_IM; }
+            Ma = xM + ((a == (int)B[ja]) ? 1 : MMs);
+            const bool freeB = (ja == 0) && Left;
+            const int md = pM0 + (freeB ? 0 : GO);
+            int d = upDa + (freeB ? 0 : GE);
+            if (md >= d) { d = md; t |= TB_MD; }
+            Da = d;
+            if (Va >= Ua) t |= TB_MI;
+            bits = t;
+        }
+        if (inb) {
+            uint32_t t = 0;
+            int xM = pM1;
+            if (upDb > xM) { xM = upDb; t = TB_DM; }
+            if (Ib > xM) { xM = Ib; t = TB_IM; }
+            Mb = xM + ((a == (int)B[jb]) ? 1 : MMs);
+            const bool freeB = (jb == 0) && Left;   // column 0 is the first cell of its row (OpenB / ExtB, viterbi.cpp:102-103)
+            const int md = pM1 + (freeB ? 0 : GO);
+            int d = upDb + (freeB ? 0 : GE);
+            if (md >= d) { d = md; t |= TB_MD; }
+            Db = d;
+            if (Vb >= Ub) t |= TB_MI;
+            bits |= t << 4;
+        }
+        tb[i * 32 + lane] = (uint8_t)bits;
+        pM0 = Ma; pM1 = Mb; pD0 = Da; pD1 = Db;
+    }
+    // last row of DPI, viterbi.cpp:207-236 (strict >): chain over M(LA-1, j-1), j in [Startj, LB)
+    const int j0f = (int)dlo - 1;   // column of coordinate 0 in row LA-1
+    int I1;
+    {
+        const int gop = Right ? 0 : GO, ngex = Right ? 0 : -GE;
+        const int ja = j0f + c0, jb = ja + 1;
+        const bool ina = c0 < BW && ja >= 0 && ja < (int)LB, inb = c1 < BW && jb >= 0 && jb < (int)LB;
+        int Mla = __shfl_up_sync(FULL, pM1, 1);   // M at coordinate c0-1
+        if (lane == 0) Mla = NEG;
+        const int Mlb = pM0;
+        const int Va = ina ? (Mla + gop) + c0 * ngex : NEG;
+        const int Vb = inb ? (Mlb + gop) + c1 * ngex : NEG;
+        int inc = max(Va, Vb);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) inc = max(inc, __shfl_up_sync(FULL, inc, d));
+        int Ua = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) Ua = NEG;
+        const int Ub = max(Ua, Va);
+        rowla[c0] = (ina && Va > Ua) ? TB_MI : 0;
+        rowla[c1] = (inb && Vb > Ub) ? TB_MI : 0;
+        const int tot = __shfl_sync(FULL, inc, 31);
+        I1 = tot - ((int)LB - 1 - j0f) * ngex;
+    }
+    __syncwarp();
+    int Score;
+    {
+        const int cf = (int)LB - 1 - j0f;   // coordinate of column LB-1 in the last row
+        const int t0 = __shfl_sync(FULL, pM0, (cf >> 1) & 31), t1 = __shfl_sync(FULL, pM1, (cf >> 1) & 31);
+        Score = (cf >= 0 && cf < BW) ? ((cf & 1) ? t1 : t0) : NEG;
+    }
+    int State = 0;  // 0 M, 1 D, 2 I
+    if (DLB > Score) { Score = DLB; State = 1; }
+    if (I1 > Score) { Score = I1; State = 2; }
+
+    // traceback, tracebackbitmem.cpp:22-73.  The reference emits the state, then (unless a coordinate it needs is 0) reads
+    // the trace bits of the cell it leaves and moves; here lane k looks at the cell k steps ahead along the current
+    // direction, so a whole run of one state is emitted per iteration.  Everything stays uniform across the lanes.
+    auto get = [&](int i, int j) -> uint32_t {
+        if (i == (int)LA) {
+            const int c = j - j0f;
+            return (c >= 0 && c < BW) ? rowla[c] : 0u;
+        }
+        if (j == (int)LB) return collb[i];
+        const int jz = (int)dlo + i - (int)LA;
+        const int c = j - jz;
+        if (c == -1) return (jz > 0) ? (uint32_t)TB_IM : 0u;   // TB[i][Startj-1] = IM, viterbi.cpp:119
+        if (c < 0 || c >= BW) return 0u;
+        return ((uint32_t)tb[i * 32 + (c >> 1)] >> ((c & 1) * 4)) & 0xFu;
+    };
+    int ti = (int)LA, tj = (int)LB;
+    uint32_t curop = (uint32_t)State, curlen = 0;
+#pragma unroll 1
+    for (;;) {
+        // position of lane k: k steps further along the run of State
+        const int pi = ti - ((State == 2) ? 0 : lane), pj = tj - ((State == 1) ? 0 : lane);
+        // 1 = the walk ends here without emitting, 2 = emits and ends, 3 = emits, changes state and moves, 0 = emits and moves
+        uint32_t kind, nstate = (uint32_t)State;
+        if (pi <= 0 && pj <= 0) kind = (pi == 0 && pj == 0) ? 1u : 4u;           // 4: beyond the end of the walk
+        else if (pi < 0 || pj < 0) kind = 4u;
+        else if (State == 0) {
+            if (pi == 0 || pj == 0) kind = 2u;
+            else {
+                const uint32_t t = get(pi - 1, pj - 1);
+                nstate = (t & TB_DM) ? 1u : ((t & TB_IM) ? 2u : 0u);
+                kind = nstate != 0u ? 3u : 0u;
+            }
+        } else if (State == 1) {
+            if (pi == 0) kind = 2u;
+            else {
+                const uint32_t t = get(pi - 1, pj);
+                nstate = (t & TB_MD) ? 0u : 1u;
+                kind = nstate != 1u ? 3u : 0u;
+            }
+        } else {
+            if (pj == 0) kind = 2u;
+            else {
+                const uint32_t t = get(pi, pj - 1);
+                nstate = (t & TB_MI) ? 0u : 2u;
+                kind = nstate != 2u ? 3u : 0u;
+            }
+        }
+        const uint32_t stop = __ballot_sync(FULL, kind != 0u);
+        const int f = stop ? __ffs(stop) - 1 : 32;                 // first lane at which the run ends
+        const uint32_t fk = __shfl_sync(FULL, kind, f & 31), fs = __shfl_sync(FULL, nstate, f & 31);
+        const uint32_t emitted = (f == 32) ? 32u : (uint32_t)f + ((fk == 1u) ? 0u : 1u);
+        if (emitted) {
+            if ((uint32_t)State == curop) curlen += emitted;
+            else {
+                runs_append(rev, n_rev, curop, curlen, kRunCap, ovf, lane);
+                curop = (uint32_t)State;
+                curlen = emitted;
+            }
+        }
+        if (f < 32 && fk != 3u) break;                             // the walk is over (kinds 1 and 2; 4 cannot come first)
+        const int steps = (f == 32) ? 32 : f + 1;
+        if (State != 2) ti -= steps;
+        if (State != 1) tj -= steps;
+        if (f < 32) State = (int)fs;
+    }
+    runs_append(rev, n_rev, curop, curlen, kRunCap, ovf, lane);
+    return Score <= NEG / 2 ? NEG_INF : (float)Score;
+}
+#endif
 
 // Flank DP dispatch: bands up to 64 wide (always true for LB = LA + 2R (+1), R <= 12) run with the band across the
 // lanes and trace bits in shared memory; anything else (never seen from AlignHSP) takes the row-block kernel.

@@ -1434,6 +1434,222 @@ __device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint3
 }
 #endif
 
+// Full-window DP of the mate rescue (State1::Scan, scan.cpp:27: State1::Viterbi of the whole read against a window of
+// 1024 (+ 2 QL) bases, Left = Right = true in the reference's call).  Same recurrence and traceback as viterbi_warp (32-row
+// blocks swept as an anti-diagonal wavefront, lane = row), rebuilt around the memory system:
+//   * 32-bit integers instead of fp32 (see viterbi_band for why scores and reachable trace bits are the same);
+//   * the window is staged in shared memory once (it was one global load per cell);
+//   * trace bits are packed, eight 4-bit cells per word, word index [row block][step / 8][lane]: one coalesced 128-byte
+//     store per eight steps instead of 32 scattered byte stores per step (one 32-byte sector each);
+//   * the previous block's last row (M, D) is fetched 32 columns at a time by the whole warp and handed to lane 0 through
+//     shuffles (it was a dependent global load per step);
+//   * the last-row insert chain is a max-plus prefix scan, 32 columns per step;
+//   * the traceback walks whole runs (32 cells per step) as viterbi_band does.
+// A: read strand (shared).  Bg: window in global memory.  Leaves the path REVERSED as RLE runs in E.ws->runs_a.
+struct FullTB {
+    const uint32_t *w;      // packed trace words
+    const uint8_t *rowla;   // row LA (last-row insert chain), one byte per column
+    uint32_t wpl;           // words per lane and row block
+    uint32_t LA, LB, dlo, dhi;
+    uint32_t SjL;           // Startj of the last row
+};
+__device__ __forceinline__ uint32_t full_tb_get(const FullTB &T, int i, int j) {
+    if (i == (int)T.LA) return (j >= (int)T.SjL && j < (int)T.LB) ? (uint32_t)T.rowla[j] : 0u;
+    uint32_t Sj, Ej;
+    range_j(T.LA, T.LB, T.dlo, T.dhi, (uint32_t)i, Sj, Ej);
+    const bool edge = (j == (int)T.LB);
+    if (edge && Ej < T.LB) return TB_MD;                       // -inf >= -inf in the reference (viterbi.cpp:194)
+    if (!edge) {
+        if (j + 1 == (int)Sj) return TB_IM;                    // TB[i][Startj-1] = IM, viterbi.cpp:119
+        if (j < (int)Sj || j >= (int)Ej) return 0u;
+    }
+    const uint32_t i0 = (uint32_t)i & ~31u, l = (uint32_t)i & 31u;
+    uint32_t jb, te;
+    range_j(T.LA, T.LB, T.dlo, T.dhi, i0, jb, te);
+    const uint32_t st = (uint32_t)j - jb + l;
+    return (T.w[((size_t)(i0 >> 5) * T.wpl + (st >> 3)) * 32 + l] >> (4 * (st & 7))) & 0xFu;
+}
+
+__device__ __noinline__ float viterbi_full(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *Bg, uint32_t LB, bool Left,
+                                           bool Right, int &n_rev, int &ovf) {
+    const int lane = E.lane;
+    uint16_t *rev = E.ws->runs_a;
+    n_rev = 0;
+    if (LA == 0 || LB == 0) return viterbi_warp<true>(E, A, LA, Bg, LB, Left, Right, n_rev, ovf);   // degenerate (never from Scan)
+    constexpr int NEG = -(1 << 28);
+    const int GO = E.P.GO, GE = E.P.GE, MMs = E.P.MM;
+    uint32_t dlo = min(LA, LB), dhi = max(LA, LB);
+    if (dlo > E.P.R) dlo -= E.P.R; else dlo = 1;
+    dhi += E.P.R;
+    if (dhi > LA + LB - 1) dhi = LA + LB - 1;
+    // the window in shared memory when the flank-DP trace area is large enough for it, else read from global memory
+    const uint8_t *B = Bg;
+    if ((size_t)E.tb_rows * 32 >= (size_t)LB + 4) {
+        uint8_t *sb = E.s_tb;
+        for (uint32_t k = lane; k < LB; k += 32) sb[k] = __ldg(Bg + k);
+        B = sb;
+        __syncwarp();
+    }
+    int *rowM = reinterpret_cast<int *>(E.ws->rowM), *rowD = reinterpret_cast<int *>(E.ws->rowD);
+    uint32_t *tbw = reinterpret_cast<uint32_t *>(E.ws->tb);
+    const uint32_t wpl = (LB + 1 + 32 + 7) / 8 + 1;   // steps of a block <= LB + 1 + 31
+    uint8_t *rowla = E.ws->tb + (size_t)((LA + 31) / 32) * wpl * 32 * 4;
+    for (uint32_t i0 = 0; i0 < LA; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool rowact = i < LA;
+        uint32_t Sj = 0, Ej = 0;
+        if (rowact) range_j(LA, LB, dlo, dhi, i, Sj, Ej);
+        uint32_t jbase, tmpE;
+        range_j(LA, LB, dlo, dhi, i0, jbase, tmpE);
+        const uint32_t ilast = min(i0 + 31, LA - 1);
+        uint32_t lS, lE;
+        range_j(LA, LB, dlo, dhi, ilast, lS, lE);
+        const uint32_t lastcol = (lE == LB) ? LB : lE - 1;  // includes the virtual column LB
+        const int nsteps = (int)(lastcol - jbase) + (int)(ilast - i0) + 1;
+        uint32_t pS = 0, pE = 0;
+        if (i0 > 0) range_j(LA, LB, dlo, dhi, i0 - 1, pS, pE);
+        const int a = rowact ? (int)A[i] : 0x100;
+        int outM = NEG, outD = NEG, Mdiag = NEG, I0 = NEG;
+        const int openA = (Left && i == 0) ? 0 : GO, extA = (Left && i == 0) ? 0 : GE;
+        const bool lastrow = rowact && (i == ilast);
+        uint32_t *wrow = tbw + (size_t)(i0 >> 5) * wpl * 32 + lane;
+        uint32_t acc = 0;
+        int cM = NEG, cD = NEG;   // previous block's last row, 32 columns at a time (lane t: column jbase + s0 + t)
+#pragma unroll 1
+        for (int s = 0; s < nsteps; ++s) {
+            if ((s & 31) == 0 && i0 > 0) {
+                const uint32_t jj = jbase + (uint32_t)s + (uint32_t)lane;
+                const bool inprev = (jj >= pS && jj < pE);
+                cM = inprev ? rowM[jj] : NEG;
+                cD = (inprev || (jj == LB && pE == LB)) ? rowD[jj] : NEG;
+            }
+            int upM = __shfl_up_sync(FULL, outM, 1), upD = __shfl_up_sync(FULL, outD, 1);
+            const int bM = __shfl_sync(FULL, cM, s & 31), bD = __shfl_sync(FULL, cD, s & 31);
+            if (lane == 0) { upM = bM; upD = bD; }
+            const int js = (int)jbase + s - lane;
+            const uint32_t j = (uint32_t)js;
+            const bool incol = rowact && js >= (int)Sj && js < (int)Ej;
+            const bool vcol = rowact && j == LB && Ej == LB && js >= 0;
+            int myM = NEG, myD = NEG;
+            uint32_t bits = 0;
+            if (incol) {
+                const int M0 = (j == 0) ? ((i == 0) ? 0 : NEG) : Mdiag;
+                const int bch = (int)B[j];
+                int xM = M0;
+                if (upD > xM) { xM = upD; bits = TB_DM; }
+                if (I0 > xM) { xM = I0; bits = TB_IM; }
+                myM = xM + ((a == bch) ? 1 : MMs);
+                const bool freeB = (j == 0) && Left;
+                const int md = M0 + (freeB ? 0 : GO);
+                int d = upD + (freeB ? 0 : GE);
+                if (md >= d) { d = md; bits |= TB_MD; }
+                myD = d;
+                const int mi = M0 + openA;
+                I0 += extA;
+                if (mi >= I0) { I0 = mi; bits |= TB_MI; }
+            } else if (vcol) {  // viterbi.cpp:187-200, end of Drow[]
+                const int md = Mdiag + GO;
+                int d = upD + GE;
+                if (md >= d) { d = md; bits = TB_MD; }
+                myD = d;
+            }
+            acc |= bits << (4 * (s & 7));
+            if ((s & 7) == 7) {
+                wrow[(size_t)(s >> 3) * 32] = acc;
+                acc = 0;
+            }
+            Mdiag = upM;
+            outM = myM;
+            outD = myD;
+            if (lastrow) {
+                if (incol) { rowM[j] = myM; rowD[j] = myD; }
+                else if (vcol) rowD[j] = myD;
+            }
+        }
+        if (nsteps & 7) wrow[(size_t)((nsteps - 1) >> 3) * 32] = acc;
+        __syncwarp();
+    }
+
+    // last row of DPI, viterbi.cpp:207-236 (strict >): I1 = max-plus chain over M(LA-1, j-1), j in [Startj, LB)
+    uint32_t SjL, EjL;
+    range_j(LA, LB, dlo, dhi, LA - 1, SjL, EjL);
+    const int gop = Right ? 0 : GO, ngex = Right ? 0 : -GE;
+    int Ucarry = NEG;   // running max of V_c = (M(LA-1, j-1) + gop) + c * ngex over c = j - SjL
+    for (uint32_t c0 = 0; SjL + c0 < EjL; c0 += 32) {
+        const uint32_t c = c0 + lane, j = SjL + c;
+        const bool in = j < EjL;
+        const int mp = (in && j > SjL) ? rowM[j - 1] : NEG;   // Mrow[Startj-1] = -inf, viterbi.cpp:212
+        const int V = in ? (mp + gop) + (int)c * ngex : NEG;
+        int inc = V;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) inc = max(inc, __shfl_up_sync(FULL, inc, d));
+        int Uprev = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) Uprev = NEG;
+        Uprev = max(Uprev, Ucarry);
+        if (in) rowla[j] = (V > Uprev) ? TB_MI : 0;
+        Ucarry = max(Ucarry, __shfl_sync(FULL, inc, 31));
+    }
+    const int I1 = (EjL > SjL) ? Ucarry - (int)(EjL - 1 - SjL) * ngex : NEG;
+    __syncwarp();
+    int Score = rowM[LB - 1];
+    int State = 0;  // 0 M, 1 D, 2 I
+    const int FinalD = rowD[LB];
+    if (FinalD > Score) { Score = FinalD; State = 1; }
+    if (I1 > Score) { Score = I1; State = 2; }
+
+    FullTB T{tbw, rowla, wpl, LA, LB, dlo, dhi, SjL};
+    int ti = (int)LA, tj = (int)LB;
+    uint32_t curop = (uint32_t)State, curlen = 0;
+#pragma unroll 1
+    for (;;) {   // run-wise traceback, see viterbi_band
+        const int pi = ti - ((State == 2) ? 0 : lane), pj = tj - ((State == 1) ? 0 : lane);
+        uint32_t kind, nstate = (uint32_t)State;
+        if (pi <= 0 && pj <= 0) kind = (pi == 0 && pj == 0) ? 1u : 4u;
+        else if (pi < 0 || pj < 0) kind = 4u;
+        else if (State == 0) {
+            if (pi == 0 || pj == 0) kind = 2u;
+            else {
+                const uint32_t t = full_tb_get(T, pi - 1, pj - 1);
+                nstate = (t & TB_DM) ? 1u : ((t & TB_IM) ? 2u : 0u);
+                kind = nstate != 0u ? 3u : 0u;
+            }
+        } else if (State == 1) {
+            if (pi == 0) kind = 2u;
+            else {
+                const uint32_t t = full_tb_get(T, pi - 1, pj);
+                nstate = (t & TB_MD) ? 0u : 1u;
+                kind = nstate != 1u ? 3u : 0u;
+            }
+        } else {
+            if (pj == 0) kind = 2u;
+            else {
+                const uint32_t t = full_tb_get(T, pi, pj - 1);
+                nstate = (t & TB_MI) ? 0u : 2u;
+                kind = nstate != 2u ? 3u : 0u;
+            }
+        }
+        const uint32_t stop = __ballot_sync(FULL, kind != 0u);
+        const int f = stop ? __ffs(stop) - 1 : 32;
+        const uint32_t fk = __shfl_sync(FULL, kind, f & 31), fs = __shfl_sync(FULL, nstate, f & 31);
+        const uint32_t emitted = (f == 32) ? 32u : (uint32_t)f + ((fk == 1u) ? 0u : 1u);
+        if (emitted) {
+            if ((uint32_t)State == curop) curlen += emitted;
+            else {
+                runs_append(rev, n_rev, curop, curlen, kRunCap, ovf, lane);
+                curop = (uint32_t)State;
+                curlen = emitted;
+            }
+        }
+        if (f < 32 && fk != 3u) break;
+        const int steps = (f == 32) ? 32 : f + 1;
+        if (State != 2) ti -= steps;
+        if (State != 1) tj -= steps;
+        if (f < 32) State = (int)fs;
+    }
+    runs_append(rev, n_rev, curop, curlen, kRunCap, ovf, lane);
+    return Score <= NEG / 2 ? NEG_INF : (float)Score;
+}
+
 // Flank DP dispatch: bands up to 64 wide (always true for LB = LA + 2R (+1), R <= 12) run with the band across the
 // lanes and trace bits in shared memory; anything else (never seen from AlignHSP) takes the row-block kernel.
 __device__ __noinline__ float flank_viterbi(const Env &E, const uint8_t *A, uint32_t LA, uint32_t TLo, uint32_t LB, bool Left,
@@ -1501,6 +1717,11 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
     }
     runs_append(path, np, 0, HSPLength, pcap, ovf, E.lane);
     const uint32_t RightQLo = StartPosQ + HSPLength;
+    // The start of the alignment is known once the left flank is done.  AddHitX (state1.cpp:508-551) drops a hit whose
+    // 64-base bucket is taken before it looks at anything else, and nothing below has another effect, so the right-flank
+    // DP of such a hit is skipped: same result (-1, no change of state), about half of the DP work of the candidates that
+    // sit on a locus already found (tandem repeats in a scan window produce hundreds of them).
+    if (RightQLo < QL && overlaps_hit(E, m, CombinedTLo)) return -1;
     if (RightQLo < QL) {
         const uint32_t RightQL = QL - RightQLo;
         const uint32_t RightTLo = StartPosDB + HSPLength;
@@ -2076,7 +2297,7 @@ __device__ __noinline__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, ui
 
 // State1::Scan, scan.cpp:14-39, in three pieces so that the full-window Viterbi can run elsewhere:
 //   scan_mate_pre  : ScanSlots under the raised penalty bound; true when the DP has to run (no hit found, DoVit)
-//   (the DP)       : viterbi_warp<true>(strand of the mate, window), a pure function of its arguments
+//   (the DP)       : viterbi_full(strand of the mate, window), a pure function of its arguments
 //   scan_mate_post : the hit of a good enough DP (path trimmed as TrimLeftIs / TrimRightIs do)
 __device__ __noinline__ bool scan_mate_pre(const Env &E, Mate &m, uint32_t DBPos, uint32_t DBSegLength, bool Plus, bool DoVit) {
     const int SavedMaxPenalty = m.MaxPenalty;
@@ -2109,7 +2330,7 @@ __device__ __noinline__ void scan_mate(const Env &E, Mate &m, uint32_t DBPos, ui
                                        bool DoVit) {
     if (!scan_mate_pre(E, m, DBPos, DBSegLength, Plus, DoVit)) return;
     int nrev = 0, ovf = 0;
-    float Score = viterbi_warp<true>(E, mate_seq(m, Plus), m.QL, E.ix.seq + DBPos, DBSegLength, true, true, nrev, ovf);
+    float Score = viterbi_full(E, mate_seq(m, Plus), m.QL, E.ix.seq + DBPos, DBSegLength, true, true, nrev, ovf);
     scan_mate_post(E, m, DBPos, Plus, Score, E.ws->runs_a, nrev, ovf);
 }
 
@@ -2212,7 +2433,7 @@ __device__ __noinline__ bool scan_pair_resume(const Env &E, Mate &F, Mate &R, Re
             if (!scan_mate_pre(E, dst, pos, len, plus, DoVit)) continue;
             if (INLINE) {
                 int nrev = 0, ovf = 0;
-                const float Score = viterbi_warp<true>(E, mate_seq(dst, plus), dst.QL, E.ix.seq + pos, len, true, true, nrev, ovf);
+                const float Score = viterbi_full(E, mate_seq(dst, plus), dst.QL, E.ix.seq + pos, len, true, true, nrev, ovf);
                 scan_mate_post(E, dst, pos, plus, Score, E.ws->runs_a, nrev, ovf);
             } else {
                 h.state = 1;
@@ -2927,7 +3148,7 @@ __device__ __forceinline__ void rescue_dp_body(const KArgs &A, int round) {
     uint8_t *sw = smem + (size_t)warp * A.spw;
     const DevBatch &b = A.b;
     const DevOut &o = A.o;
-    const SmemPlan pl{1u, 0u, 0u};
+    const SmemPlan pl{1u, 0u, 1u};   // the flank-DP trace area holds the window
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
     const uint32_t n_work = o.counters[CT_RQ_COUNT + round + 1];
@@ -2946,7 +3167,7 @@ __device__ __forceinline__ void rescue_dp_body(const KArgs &A, int round) {
         Mate m;
         load_mate(E, m, b, A.pr, mate ? b.n_units + u : u, sw, &rs->m[mate].s, false);
         int nrev = 0, ovf = 0;
-        const float Score = viterbi_warp<true>(E, mate_seq(m, plus), m.QL, E.ix.seq + pos, len, true, true, nrev, ovf);
+        const float Score = viterbi_full(E, mate_seq(m, plus), m.QL, E.ix.seq + pos, len, true, true, nrev, ovf);
         __syncwarp();
         for (int i = lane; i < nrev; i += 32) rs->h.dp_runs[i] = E.ws->runs_a[i];
         if (lane == 0) {
@@ -3109,7 +3330,7 @@ int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
         const uint32_t cap = b.n_units < o.rescue_cap ? b.n_units : o.rescue_cap;
         for (int r = 0; r < kRescueRounds; ++r) {
             URMB_TRY(launch_one(rescue_scan_kernel, 6, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, r));
-            URMB_TRY(launch_one(rescue_dp_kernel, 8, tr, A, SmemPlan{1, 0, 0}, cap, R, stream, sm_count, nullptr, r));
+            URMB_TRY(launch_one(rescue_dp_kernel, 8, tr, A, SmemPlan{1, 0, 1}, cap, R, stream, sm_count, nullptr, r));
         }
         URMB_TRY(launch_one(rescue_last_kernel, 10, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, (int)kRescueRounds));
         n += 2 * kRescueRounds + 1;

@@ -898,7 +898,9 @@ static int rerun_overflowed(urmb_ctx *c, Slot &s, uint32_t &used) {
     const uint32_t KU = urmb_ctx::Big::kUnits, KR = 2 * KU;
     const bool second = c->params.want_second && paired;
     if (!g.ready) {
-        CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        int plo = 0, phi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+        CK(cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, phi));   // its few blocks go first when an SM frees up
         CK(cudaMalloc(&g.d_offs, (KR + 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&g.d_counters, CT_COUNT * sizeof(uint32_t)));
         CK(cudaMalloc(&g.d_todo, (KU + 1) * sizeof(uint32_t)));
@@ -1026,7 +1028,7 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
         const uint32_t before = s.h_counters[CT_OVERFLOW];
         int rc = rerun_overflowed(c, s, used);
         if (rc) return rc;
-        if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u read(s) over a per-mate capacity mapped again by the big-capacity build, %u still over\n", si, before, s.h_counters[CT_OVERFLOW]);
+        if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u read(s) over a per-mate capacity (hits %u, path runs %u, run pool %u, HSPs %u, path assembly %u) mapped again by the big-capacity build, %u still over\n", si, before, s.h_counters[CT_DBG_OVF], s.h_counters[CT_DBG_OVF + 1], s.h_counters[CT_DBG_OVF + 2], s.h_counters[CT_DBG_OVF + 3], s.h_counters[CT_DBG_OVF + 4], s.h_counters[CT_OVERFLOW]);
     }
     if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u rescued (%u by the legacy kernel, %u full-window DPs), %u path runs\n", si, s.batch.n_units, s.h_counters[CT_TODO_TOTAL], s.h_counters[CT_RESCUE], s.h_counters[CT_RESCUE_LEGACY], s.h_counters[CT_RESCUE_DPS], used);
     if (getenv("URMB_DEBUG") && s.batch.paired) {

@@ -11,7 +11,7 @@
 extern "C" size_t urmb_big_scratch_bytes() { return sizeof(urmb_big::WarpScratch); }
 extern "C" size_t urmb_big_save_bytes() { return sizeof(urmb_big::MateSave); }
 
-// Probe + search + mate rescue (legacy kernel: no rescue pool) of one small batch on `stream`.
+// Probe kernel + one kernel that searches every unit from scratch (launch_search_monolithic) on `stream`.
 // ix / P / batch / probe / out point to the namespace-urmb structures of the same names; scratch holds n_scratch_warps
 // x urmb_big_scratch_bytes(), pool 2 x pool_pairs x urmb_big_save_bytes().  Returns kernels launched or a negative cudaError.
 extern "C" int urmb_big_map(const void *ix_, const void *P_, const void *batch_, const void *probe_, const void *out_,
@@ -28,9 +28,7 @@ extern "C" int urmb_big_map(const void *ix_, const void *P_, const void *batch_,
     SearchRes R{reinterpret_cast<WarpScratch *>(scratch), n_scratch_warps, reinterpret_cast<MateSave *>(pool), pool_pairs};
     int e = launch_probe(ix, P, b, pr, stream, sm_count);
     if (e) return -e;
-    int n = launch_search(ix, P, b, pr, o, R, stream, sm_count, nullptr, nullptr);
+    const int n = launch_search_monolithic(ix, P, b, pr, o, R, stream, sm_count);
     if (n < 0) return n;
-    const int m = launch_rescue(ix, P, b, pr, o, R, stream, sm_count, nullptr);
-    if (m < 0) return m;
-    return 1 + n + m;
+    return 1 + n;
 }

@@ -96,7 +96,8 @@ enum {
     CT_DBG_WIN = CT_RQ_DP + kRescueRounds + 2,      // [5]
     CT_DBG_MAXT = CT_DBG_WIN + 5,
     CT_DBG_MAXW = CT_DBG_MAXT + 1,
-    CT_COUNT = CT_DBG_MAXW + 1
+    CT_DBG_OVF = CT_DBG_MAXW + 1,                   // [5] reads over a capacity, by capacity (hits, path runs, run pool, HSPs, path assembly)
+    CT_COUNT = CT_DBG_OVF + 5
 };
 
 struct RescueSave;
@@ -203,6 +204,8 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
 // touches the batch's own buffers and R.scratch).  Returns the number of kernels launched or a negative cudaError.
 int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
                   const SearchRes &R, void *stream, int sm_count, const LaunchTrace *tr);
+int launch_search_monolithic(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                             const SearchRes &R, void *stream, int sm_count);
 int max_search_warps(int sm_count);
 // n_bytes = seq_data_size + URMB_SEQ_PAD; seq2 holds n_bytes/32+2 words, seqx n_bytes/32+2 words
 size_t packed_words(size_t n_bytes);

@@ -652,9 +652,9 @@ __device__ __noinline__ int add_hit(const Env &E, Mate &m, uint32_t StartPosDB, 
     int MaxPen = Pen - 2 * E.P.MM;
     if (MaxPen < m.MaxPenalty) m.MaxPenalty = MaxPen;
     int idx = m.HitCount;
-    if (idx >= kHitCap) { m.overflow = 1; return -1; }
-    if (nruns > kRunCap) { m.overflow = 1; nruns = kRunCap; }
-    if (m.nRuns + nruns > kRunPool) { m.overflow = 1; nruns = 0; }
+    if (idx >= kHitCap) { m.overflow |= 1; return -1; }
+    if (nruns > kRunCap) { m.overflow |= 2; nruns = kRunCap; }
+    if (m.nRuns + nruns > kRunPool) { m.overflow |= 4; nruns = 0; }
     if (E.lane == 0) {
         m.g->hit_pos[idx] = StartPosDB;
         m.g->hit_score[idx] = (int16_t)Score;
@@ -700,7 +700,7 @@ __device__ __noinline__ void add_hsp(const Env &E, Mate &m, uint32_t qs, uint32_
         if (Score > (int)m.g->hsp_score[k]) hsp_store(E, m, k, qs, dbs, Plus, len, Score);
         return;
     }
-    if (m.HSPCount >= kHspCap) { m.overflow = 1; return; }
+    if (m.HSPCount >= kHspCap) { m.overflow |= 8; return; }
     hsp_store(E, m, m.HSPCount, qs, dbs, Plus, len, Score);
     ++m.HSPCount;
     if (Score > m.BestHSP) m.BestHSP = Score;
@@ -713,7 +713,7 @@ __device__ __noinline__ int add_hsp_scan(const Env &E, Mate &m, uint32_t qs, uin
         if (Score > (int)m.g->hsp_score[k]) hsp_store(E, m, k, qs, dbs, Plus, len, Score);
         return k;
     }
-    if (m.HSPCount >= kHspCap) { m.overflow = 1; return -1; }
+    if (m.HSPCount >= kHspCap) { m.overflow |= 8; return -1; }
     k = m.HSPCount++;
     hsp_store(E, m, k, qs, dbs, Plus, len, Score);
     if (Score > m.BestHSP) m.BestHSP = Score;
@@ -1755,7 +1755,7 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
         TotalPen += (int)RightQL - RightScore;
         if (TotalPen > m.MaxPenalty) return -1;
     }
-    if (ovf) m.overflow = 1;
+    if (ovf) m.overflow |= 16;
     return add_hit(E, m, CombinedTLo, Plus, TotalScore, path, np);
 }
 
@@ -2322,7 +2322,7 @@ __device__ __noinline__ void scan_mate_post(const Env &E, Mate &m, uint32_t DBPo
         uint32_t keep1 = (last == 0 && (rev[0] & 3u) == 2u) ? 1 : 0;
         if (keep1) runs_append(path, np, 2, 1, 3 * kRunCap, ovf, E.lane);
         else for (int k = last; k >= first; --k) runs_append(path, np, rev[k] & 3u, rev[k] >> 2, 3 * kRunCap, ovf, E.lane);
-        if (ovf) m.overflow = 1;
+        if (ovf) m.overflow |= 16;
         add_hit(E, m, DBPos + LeftICount, Plus, (int)Score, path, np);
     }
 }
@@ -2650,7 +2650,11 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
     }
     if (E.lane == 0) {
         o.res[r] = res;
-        if (res.flags & 0x80) atomicAdd(&o.counters[CT_OVERFLOW], 1u);
+        if (res.flags & 0x80) {
+            atomicAdd(&o.counters[CT_OVERFLOW], 1u);
+            for (int k = 0; k < 5; ++k)   // which capacity: hits, runs of a path, run pool, HSPs, path assembly (statistics)
+                if (m.overflow >> k & 1) atomicAdd(&o.counters[CT_DBG_OVF + k], 1u);
+        }
     }
 }
 
@@ -2881,6 +2885,8 @@ struct KArgs {   // one parameter block for every search kernel
     uint32_t spw;                     // shared bytes per warp
 };
 
+// MODE 3 (single-end, complete search in one kernel: the big-capacity rerun of urmb_big.cu, where a handful of reads must
+// not cost a dozen dependent launches).
 // MODE 0 (single-end, first pass): every read of the chunk, phases 1-2; reads that need more are saved to the pool.
 // MODE 1 (paired, first pass): every pair of the chunk, the part
 // every pair goes through; pairs that need more are saved to the pool.  MODE 2 (paired, mate rescue): complete search
@@ -2893,7 +2899,7 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
     uint8_t *sw = smem + (size_t)warp * A.spw;
     const DevBatch &b = A.b;
     const DevOut &o = A.o;
-    const SmemPlan pl{b.paired ? 2u : 1u, 1u, MODE == 2 ? 1u : 0u};
+    const SmemPlan pl{b.paired ? 2u : 1u, 1u, MODE >= 2 ? 1u : 0u};
     const size_t msz = mate_smem_bytes(b.qcap, b.seqcap, true);
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
@@ -2905,7 +2911,13 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
         u = __shfl_sync(FULL, u, 0);
         if (u >= n_work) break;
         u = (MODE == 2) ? o.rescue[u] : A.unit_base + u;
-        if (MODE == 0) {
+        if (MODE == 3) {   // single-end, the whole of Search_Lo in one kernel (search1m6.cpp:35-277)
+            Mate m;
+            load_mate(E, m, b, A.pr, u, sw, &E.ws->m[0], true);
+            reset_search(E, m);
+            if (!se_phase12(E, m) && !se_phase3(E, m) && !se_phase45(E, m)) se_phase6(E, m);
+            write_result(E, m, o, u);
+        } else if (MODE == 0) {
             Mate m;
             load_mate(E, m, b, A.pr, u, sw, &E.ws->m[0], true);
             reset_search(E, m);   // State1::Search, search1.cpp:7-24
@@ -3196,6 +3208,11 @@ __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_long_kernel_se(const _
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se6(const __grid_constant__ KArgs A) { stage_body<5>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_PAIR) pair_kernel(const __grid_constant__ KArgs A) { search_body<1>(A); }
 __global__ void __launch_bounds__(128, 4) rescue_kernel(const __grid_constant__ KArgs A) { search_body<2>(A); }
+__global__ void __launch_bounds__(128, 4) se_full_kernel(const __grid_constant__ KArgs A) { search_body<3>(A); }
+__global__ void identity_list_kernel(uint32_t *list, uint32_t n, uint32_t *count) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) list[i] = i;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count = n;
+}
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_a(const __grid_constant__ KArgs A) { stage_body<0>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_kernel(const __grid_constant__ KArgs A) { stage_body<1>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_long_kernel(const __grid_constant__ KArgs A) { stage_body<6>(A); }
@@ -3318,11 +3335,30 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     return n;
 }
 
+// Every unit of the batch searched from scratch by ONE kernel (after the probe kernel): se_full_kernel, or for pairs the
+// legacy mate-rescue kernel over a list of all pairs.  Two launches instead of a dozen: the big-capacity rerun of a few reads.
+int launch_search_monolithic(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                             const SearchRes &R, void *stream, int sm_count) {
+    KArgs A = make_kargs(ix, P, b, pr, o, R);
+    int e;
+#define URMB_TRY(call) do { e = (call); if (e) return -e; } while (0)
+    if (!b.paired) {
+        URMB_TRY(launch_one(se_full_kernel, 1, nullptr, A, SmemPlan{1, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
+        return 1;
+    }
+    URMB_LAUNCH(identity_list_kernel, 1, 256, 0, stream, o.rescue, b.n_units, o.counters + CT_RESCUE_LEGACY);
+    URMB_TRY((int)cudaGetLastError());
+    URMB_TRY(launch_one(rescue_kernel, 9, nullptr, A, SmemPlan{2, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
+    return 2;
+#undef URMB_TRY
+}
+
 // Mate rescue of the pairs finish_kernel found without a pair of hits: kRescueRounds rounds of
 // (rescue_scan_kernel, rescue_dp_kernel) over the rescue pool, a last round that finishes the stragglers in place, and the
 // legacy kernel (complete search from scratch) for the pairs that did not fit into the pool.
 int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
                   const SearchRes &R, void *stream, int sm_count, const LaunchTrace *tr) {
+#define URMB_TRY(call) do { e = (call); if (e) return -e; } while (0)
     if (!b.paired || P.pe_method == 5) return 0;
     KArgs A = make_kargs(ix, P, b, pr, o, R);
     int e, n = 0;

@@ -247,8 +247,10 @@ def test_chunk_size_invariance(eng, oracle, mid_env):
 
 
 def test_big_capacity_rerun_and_legacy_rescue(eng, oracle, mid_env):
-    """Reads that overflow a per-mate capacity are mapped again by the kernels compiled with big capacities (urmb_big.cu):
-    forced here for every third unit, the results must not change (SE and PE, path runs and second hits included).
+    """Reads that overflow a per-mate capacity are mapped again by the kernels compiled with big capacities (urmb_big.cu),
+    in stream behind the mate rescue (URMB_FLAGS bit 8 forces it for every fifth read) or, for what is left, from the host
+    in urmb_wait (URMB_FORCE_RERUN forces it for every third unit): the results must not change (SE and PE, path runs and
+    second hits included).
     The legacy mate-rescue kernel (no rescue pool) must agree with the rescue rounds as well."""
     g, oix, hix = mid_env
     r1, r2, _ = synth.sim_pe(g, 5000, 150, 0.04, 0.006, seed=21)
@@ -257,7 +259,8 @@ def test_big_capacity_rerun_and_legacy_rescue(eng, oracle, mid_env):
     b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
     o1, o2, uo = oracle.map_pe(oix, b1, b2, threads=os.cpu_count())
     s1, us = oracle.map_se(oix, b1, threads=os.cpu_count())
-    for env in ({"URMB_FORCE_RERUN": "3"}, {"URMB_RESCUE_LEGACY": "1"}):
+    for env in ({"URMB_FORCE_RERUN": "3"}, {"URMB_FLAGS": "256"}, {"URMB_FLAGS": "256", "URMB_RESCUE_INLINE": "1"},
+                {"URMB_RESCUE_LEGACY": "1"}):
         ctx = _ctx_with_env(eng, hix, env, want_second=True)
         g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
         assert_same(np.concatenate([o1, o2]), uo, np.concatenate([g1, g2]), ug)

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 #include <string>
@@ -25,8 +26,13 @@ using namespace urmb;
 // urmb_big.cu: the same kernels with per-mate capacities no read can exceed (reads that overflowed the fast build)
 extern "C" size_t urmb_big_scratch_bytes();
 extern "C" size_t urmb_big_save_bytes();
+extern "C" int urmb_big_rerun_listed(const void *ix, const void *P, const void *batch, const void *probe, const void *out, void *scratch,
+                                     int n_scratch_warps, void *stream, int sm_count);
 extern "C" int urmb_big_map(const void *ix, const void *P, const void *batch, const void *probe, const void *out, void *scratch,
                             int n_scratch_warps, void *pool, uint32_t pool_pairs, void *stream, int sm_count);
+
+static constexpr uint32_t kOvfCap = 4096;    // reads per batch the in-stream big-capacity rerun takes (more: host path in urmb_wait)
+static constexpr int kBigWarps = 256;        // per-warp scratch entries of the big-capacity kernels, per side stream
 
 static std::string g_last_error;
 static std::mutex g_err_mu;
@@ -161,6 +167,7 @@ struct Slot {
     uint32_t *d_counters = nullptr;
     uint32_t *d_todo = nullptr; size_t d_todo_cap = 0;
     uint32_t *d_rescue = nullptr; size_t d_rescue_cap = 0;
+    uint32_t *d_ovf = nullptr;                // reads over a per-mate capacity (kOvfCap entries), see DevOut::ovf_list
     DevBatch batch{};
     size_t seq_bytes = 0;
     bool staged = false, launched = false, downloaded = false;
@@ -216,6 +223,7 @@ struct urmb_ctx {
         size_t seq_cap = 0, probe_cap = 0, view_cap = 0, runs_cap = 0;
         bool ready = false;
     } big;
+    void *big_scratch = nullptr;   // 2 x kBigWarps x urmb_big_scratch_bytes(): in-stream rerun, one set per side stream
     uint64_t rerun_total = 0;      // reads mapped again by the big-capacity build
     uint32_t force_rerun = 0;      // URMB_FORCE_RERUN=N (tests): every N-th unit is mapped again by the big-capacity build
     bool rescue_legacy = false;    // URMB_RESCUE_LEGACY: no rescue pool, every rescued pair is searched again from scratch
@@ -297,10 +305,12 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps * 2));   // one set per side stream
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
+    if (!getenv("URMB_NO_RERUN")) CK(cudaMalloc(&c->big_scratch, urmb_big_scratch_bytes() * (size_t)kBigWarps * 2));
     for (auto &s : c->slots) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h, &s.ev_rescue}) CK(cudaEventCreate(ev));
         CK(cudaMalloc(&s.d_counters, CT_COUNT * sizeof(uint32_t)));
+        CK(cudaMalloc(&s.d_ovf, kOvfCap * sizeof(uint32_t)));
         CK(cudaHostAlloc(&s.h_counters, CT_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
     }
     *out = c;
@@ -314,7 +324,7 @@ static void free_slot(Slot &s) {
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
     cudaFree(s.d_seqs); cudaFree(s.d_offs); cudaFree(s.d_tally); cudaFree(s.d_pos); cudaFree(s.d_ext); cudaFree(s.d_view);
     cudaFree(s.d_second); cudaFreeHost(s.h_second);
-    cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo); cudaFree(s.d_rescue);
+    cudaFree(s.d_res); cudaFree(s.d_runs); cudaFree(s.d_counters); cudaFree(s.d_todo); cudaFree(s.d_rescue); cudaFree(s.d_ovf);
 }
 
 extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
@@ -330,6 +340,7 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     cudaFree(c->rescue_scratch);
     cudaFree(c->scratch);
     cudaFree(c->pool);
+    cudaFree(c->big_scratch);
     {
         urmb_ctx::Big &g = c->big;
         if (g.stream) cudaStreamDestroy(g.stream);
@@ -784,7 +795,8 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         if (use_pool && c->rpool_used[rp]) CK(cudaStreamWaitEvent(c->compute, c->ev_rpool[rp], 0));
         DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue, second,
                  use_pool ? c->rpool[rp] : nullptr, use_pool ? (uint32_t)c->rescue_cap : 0u,
-                 {use_pool ? c->rq[rp][0] : nullptr, use_pool ? c->rq[rp][1] : nullptr}};
+                 {use_pool ? c->rq[rp][0] : nullptr, use_pool ? c->rq[rp][1] : nullptr},
+                 c->big_scratch ? s.d_ovf : nullptr, c->big_scratch ? kOvfCap : 0u};
         SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
         TraceCtx tc{&s, c->compute, cudaSuccess};
@@ -811,9 +823,19 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
             CK(cudaEventRecord(c->ev_rpool[rp], rs));
             c->rpool_used[rp] = true;
         }
-        if (tc.err != cudaSuccess) return fail(c, URMB_E_CUDA, std::string("event record: ") + cudaGetErrorString(tc.err));
         c->launches += (uint64_t)e;
-        rescued = e > 0;
+        if (c->big_scratch) {
+            // reads over a per-mate capacity of the fast kernels are searched again by the big-capacity build, queued
+            // behind the mate rescue on the same stream (rs already waits for the search kernels)
+            e = urmb_big_rerun_listed(&c->ix, &P, &s.batch, &pr, &o, (uint8_t *)c->big_scratch + (size_t)side_ix * kBigWarps * urmb_big_scratch_bytes(),
+                                      kBigWarps, rs, c->sm_count);
+            if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun launch: ") + cudaGetErrorString((cudaError_t)-e));
+            c->launches += (uint64_t)e;
+            if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, c->compute));
+        }
+        if (tc.err != cudaSuccess) return fail(c, URMB_E_CUDA, std::string("event record: ") + cudaGetErrorString(tc.err));
+        rescued = true;   // the side stream has work of this batch (or, inline, waits for the re-recorded ev_k2 below)
+        if (c->rescue_inline) rescued = false;
     } else {
         CK(cudaEventRecord(s.ev_k1, c->compute));
         CK(cudaEventRecord(s.ev_k2, c->compute));
@@ -933,6 +955,8 @@ static int rerun_overflowed(urmb_ctx *c, Slot &s, uint32_t &used) {
         g.probe_cap = probe_need;
     }
     uint32_t still = 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    uint32_t hs[5] = {0, 0, 0, 0, 0};
     for (size_t p0 = 0; p0 < sel.size(); p0 += KU) {
         const uint32_t m = (uint32_t)std::min<size_t>(KU, sel.size() - p0), sub = paired ? 2 * m : m;
         uint32_t o = 0;
@@ -954,7 +978,7 @@ static int rerun_overflowed(urmb_ctx *c, Slot &s, uint32_t &used) {
         b.n_units = m;
         DevProbe pr{g.d_tally, g.d_pos, g.d_ext, g.d_view, view_stride_for(b.seqcap)};
         DevOut out{g.d_res, g.d_runs, (uint32_t)g.runs_cap, g.d_counters, g.d_todo, g.d_rescue, second ? g.d_second : nullptr,
-                   nullptr, 0u, {nullptr, nullptr}};
+                   nullptr, 0u, {nullptr, nullptr}, nullptr, 0u};
         const int e = urmb_big_map(&c->ix, &c->P, &b, &pr, &out, g.scratch, urmb_ctx::Big::kWarps, g.pool, 256, g.stream, c->sm_count);
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun: ") + cudaGetErrorString((cudaError_t)-e));
         c->launches += (uint64_t)e;
@@ -987,7 +1011,12 @@ static int rerun_overflowed(urmb_ctx *c, Slot &s, uint32_t &used) {
         }
         used += bused;
         c->rerun_total += sub;
+        for (int k = 0; k < 4; ++k) hs[k] += g.h_counters[CT_DBG_HSPS + k];
+        hs[4] = std::max(hs[4], g.h_counters[CT_DBG_MAXHSP]);
     }
+    if (getenv("URMB_DEBUG"))
+        fprintf(stderr, "[urmb] big-capacity rerun of %zu unit(s): %.2f ms on the host; reads by HSP count (<=256, <=512, <=1024, more): %u %u %u %u, max %u\n",
+                sel.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), hs[0], hs[1], hs[2], hs[3], hs[4]);
     s.h_counters[CT_OVERFLOW] = still;
     (void)nreads;
     return URMB_OK;

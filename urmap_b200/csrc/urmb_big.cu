@@ -32,3 +32,20 @@ extern "C" int urmb_big_map(const void *ix_, const void *P_, const void *batch_,
     if (n < 0) return n;
     return 1 + n;
 }
+
+// The reads the fast build recorded in out->ovf_list searched again, in place, by the big-capacity kernels: queued on
+// `stream` behind the batch's mate rescue, no host round trip.  scratch: n_scratch_warps x urmb_big_scratch_bytes().
+extern "C" int urmb_big_rerun_listed(const void *ix_, const void *P_, const void *batch_, const void *probe_, const void *out_,
+                                     void *scratch, int n_scratch_warps, void *stream, int sm_count) {
+    using namespace urmb_big;
+    const DevIndex &ix = *reinterpret_cast<const DevIndex *>(ix_);
+    const DevParams &P = *reinterpret_cast<const DevParams *>(P_);
+    const DevBatch &b = *reinterpret_cast<const DevBatch *>(batch_);
+    const DevProbe &pr = *reinterpret_cast<const DevProbe *>(probe_);
+    DevOut o = *reinterpret_cast<const DevOut *>(out_);
+    o.rpool = nullptr;
+    o.rescue_cap = 0;
+    o.rq[0] = o.rq[1] = nullptr;
+    SearchRes R{reinterpret_cast<WarpScratch *>(scratch), n_scratch_warps, nullptr, 0};
+    return launch_overflow_rerun(ix, P, b, pr, o, R, stream, sm_count);
+}

@@ -48,7 +48,8 @@ struct DevParams {  // State1::SetMethod constants, state1.cpp:147-183
     int MM, GO, GE, MIN_HSP_PCT, TERM3_PCT, XDROP, MAXPEN, XP1, XP3, XP4;
     uint32_t R;
     int pe_method;
-    uint32_t flags;   // tuning switches (URMB_FLAGS): bit 5 = do not consult the coarse exception bitmap (seqc)
+    uint32_t flags;   // tuning switches (URMB_FLAGS): bit 5 = do not consult the coarse exception bitmap (seqc); bit 8 = test hook:
+                      // every fifth read is treated as over a capacity (exercises the in-stream big-capacity rerun)
 };
 
 struct DevBatch {
@@ -82,6 +83,7 @@ enum {
     CT_TODO_TOTAL = 4,  // pairs that went through the staged second pass (whole batch, statistics)
     CT_RESCUE_LEGACY = 5, // pairs queued for the legacy mate-rescue kernel (rescue pool full)
     CT_RESCUE_DPS = 6,  // full-window DPs run by the rescue rounds (statistics)
+    CT_OVF_LIST = 7,    // entries of DevOut::ovf_list
     CT_CHUNK0 = 8,      // first per-chunk counter
     CT_HEAD = 8,        // work-queue head of the first-pass kernel
     CT_TODO = 9,        // pairs of this chunk saved for the staged second pass
@@ -97,7 +99,9 @@ enum {
     CT_DBG_MAXT = CT_DBG_WIN + 5,
     CT_DBG_MAXW = CT_DBG_MAXT + 1,
     CT_DBG_OVF = CT_DBG_MAXW + 1,                   // [5] reads over a capacity, by capacity (hits, path runs, run pool, HSPs, path assembly)
-    CT_COUNT = CT_DBG_OVF + 5
+    CT_DBG_HSPS = CT_DBG_OVF + 5,                   // [4] reads by final HSP count: <= 256, <= 512, <= 1024, more (statistics of the big-capacity rerun)
+    CT_DBG_MAXHSP = CT_DBG_HSPS + 4,
+    CT_COUNT = CT_DBG_MAXHSP + 1
 };
 
 struct RescueSave;
@@ -112,6 +116,8 @@ struct DevOut {
     RescueSave *rpool;     // [rescue_cap] saved states of the pairs that need mate rescue (null: legacy kernel only)
     uint32_t rescue_cap;
     uint32_t *rq[2];       // [rescue_cap] each: work lists of the rescue rounds (pool entry indexes), ping-pong
+    uint32_t *ovf_list;    // [ovf_cap] reads whose search went over a per-mate capacity (null: not recorded); the big-capacity
+    uint32_t ovf_cap;      //           build searches them again at the end of the batch (urmb_big.cu)
 };
 
 struct MateScratch {
@@ -206,6 +212,8 @@ int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
                   const SearchRes &R, void *stream, int sm_count, const LaunchTrace *tr);
 int launch_search_monolithic(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
                              const SearchRes &R, void *stream, int sm_count);
+int launch_overflow_rerun(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                          const SearchRes &R, void *stream, int sm_count);
 int max_search_warps(int sm_count);
 // n_bytes = seq_data_size + URMB_SEQ_PAD; seq2 holds n_bytes/32+2 words, seqx n_bytes/32+2 words
 size_t packed_words(size_t n_bytes);

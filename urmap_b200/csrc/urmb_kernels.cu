@@ -2648,10 +2648,23 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
             }
         }
     }
+#ifndef URMB_BIG
+    if ((E.P.flags & 256u) && r % 5 == 0) res.flags |= 0x80;   // test hook (URMB_FLAGS bit 8): every fifth read takes the in-stream big-capacity rerun
+#endif
     if (E.lane == 0) {
         o.res[r] = res;
+#ifdef URMB_BIG
+        atomicAdd(&o.counters[CT_DBG_HSPS + (m.HSPCount <= 256 ? 0 : m.HSPCount <= 512 ? 1 : m.HSPCount <= 1024 ? 2 : 3)], 1u);
+        atomicMax(&o.counters[CT_DBG_MAXHSP], (uint32_t)m.HSPCount);
+#endif
         if (res.flags & 0x80) {
             atomicAdd(&o.counters[CT_OVERFLOW], 1u);
+#ifndef URMB_BIG
+            if (o.ovf_list) {
+                const uint32_t k = atomicAdd(&o.counters[CT_OVF_LIST], 1u);
+                if (k < o.ovf_cap) o.ovf_list[k] = r;
+            }
+#endif
             for (int k = 0; k < 5; ++k)   // which capacity: hits, runs of a path, run pool, HSPs, path assembly (statistics)
                 if (m.overflow >> k & 1) atomicAdd(&o.counters[CT_DBG_OVF + k], 1u);
         }
@@ -2903,14 +2916,15 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
     const size_t msz = mate_smem_bytes(b.qcap, b.seqcap, true);
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
-    const uint32_t n_work = (MODE == 2) ? o.counters[CT_RESCUE_LEGACY] : A.unit_count;
+    const bool listed = (MODE == 2) || (MODE == 3 && A.unit_count == 0xFFFFFFFFu);   // units come from the list o.rescue
+    const uint32_t n_work = listed ? o.counters[CT_RESCUE_LEGACY] : A.unit_count;
 
     for (;;) {
         uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(&o.counters[MODE == 2 ? CT_RESCUE_HEAD : CT_HEAD], 1u);
+        if (lane == 0) u = atomicAdd(&o.counters[listed ? CT_RESCUE_HEAD : CT_HEAD], 1u);
         u = __shfl_sync(FULL, u, 0);
         if (u >= n_work) break;
-        u = (MODE == 2) ? o.rescue[u] : A.unit_base + u;
+        u = listed ? o.rescue[u] : A.unit_base + u;
         if (MODE == 3) {   // single-end, the whole of Search_Lo in one kernel (search1m6.cpp:35-277)
             Mate m;
             load_mate(E, m, b, A.pr, u, sw, &E.ws->m[0], true);
@@ -3349,6 +3363,49 @@ int launch_search_monolithic(const DevIndex &ix, const DevParams &P, const DevBa
     URMB_LAUNCH(identity_list_kernel, 1, 256, 0, stream, o.rescue, b.n_units, o.counters + CT_RESCUE_LEGACY);
     URMB_TRY((int)cudaGetLastError());
     URMB_TRY(launch_one(rescue_kernel, 9, nullptr, A, SmemPlan{2, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
+    return 2;
+#undef URMB_TRY
+}
+
+// The reads recorded in o.ovf_list (over a per-mate capacity of the fast build) as a duplicate-free list of units in
+// o.rescue, ready for a listed launch of rescue_kernel / se_full_kernel; the overflow counter starts again from zero (the
+// rerun counts what is still over).  One block; the list is short.
+__global__ void __launch_bounds__(256) overflow_list_kernel(DevOut o, uint32_t n_units, int paired) {
+    const uint32_t n = min(o.counters[CT_OVF_LIST], o.ovf_cap);
+    __shared__ uint32_t cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t r = o.ovf_list[i], u = (paired && r >= n_units) ? r - n_units : r;
+        bool first = true;
+        for (uint32_t j = 0; j < n && first; ++j) {
+            const uint32_t rj = o.ovf_list[j], uj = (paired && rj >= n_units) ? rj - n_units : rj;
+            if (uj == u && (rj < r)) first = false;   // the smaller read index of a unit stands for it
+        }
+        if (first) o.rescue[atomicAdd(&cnt, 1u)] = u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        o.counters[CT_RESCUE_LEGACY] = cnt;
+        o.counters[CT_RESCUE_HEAD] = 0;
+        if (o.counters[CT_OVF_LIST] <= o.ovf_cap) o.counters[CT_OVERFLOW] = 0;   // else: the host finds the rest by their flags
+    }
+}
+
+// The listed units searched again from scratch by one kernel (big-capacity build: urmb_big.cu calls this after the mate
+// rescue of the batch, on the same stream).  Results, path runs and second hits are written in place.
+int launch_overflow_rerun(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
+                          const SearchRes &R, void *stream, int sm_count) {
+    if (!o.ovf_list || !o.ovf_cap) return 0;
+    KArgs A = make_kargs(ix, P, b, pr, o, R);
+    A.unit_count = 0xFFFFFFFFu;   // listed launch
+    int e;
+#define URMB_TRY(call) do { e = (call); if (e) return -e; } while (0)
+    URMB_LAUNCH(overflow_list_kernel, 1, 256, 0, stream, o, b.n_units, b.paired);
+    URMB_TRY((int)cudaGetLastError());
+    const uint32_t items = b.n_units < o.ovf_cap ? b.n_units : o.ovf_cap;
+    if (b.paired) URMB_TRY(launch_one(rescue_kernel, 11, nullptr, A, SmemPlan{2, 1, 1}, items, R, stream, sm_count, nullptr));
+    else URMB_TRY(launch_one(se_full_kernel, 11, nullptr, A, SmemPlan{1, 1, 1}, items, R, stream, sm_count, nullptr));
     return 2;
 #undef URMB_TRY
 }

@@ -240,3 +240,32 @@ def test_cli_tabbedout_repeat_rich_vs_reference(cli, oracle, tmp_path):
     assert sum(1 for l in want if l and l.split(b"\t")[3] != b"*") > 100   # the case is exercised
     diff = [(a, b) for a, b in zip(want, got) if a != b]
     assert len(want) == len(got) and not diff, diff[:5]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["pe", "se"])
+def test_cli_two_gpus(cli, golden_dir, tmp_path, mode):
+    """`-gpus 2` (SURVEY.md §8e through the drop-in itself): the index goes to GPU 0 over PCIe and on to GPU 1 over NVLink,
+    batches alternate between the GPUs; the SAM file equals the golden one record for record, in input order."""
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = tmp_path / "o.sam"
+    if mode == "pe":
+        args = ["-map2", os.path.join(golden_dir, "pe_1.fq"), "-reverse", os.path.join(golden_dir, "pe_2.fq")]
+        want, n = "pe.sam", 860
+    else:
+        args = ["-map", os.path.join(golden_dir, "se.fq")]
+        want, n = "se.sam", 580
+    r = run([cli] + args + ["-ufi", os.path.join(golden_dir, "ref.ufi"), "-samout", str(out), "-gpus", "2", "-batch", "37", "-threads", "4"])
+    assert r.returncode == 0, r.stderr
+    assert "2 GPU" in r.stderr
+    c = synth.compare_sam(os.path.join(golden_dir, want), str(out))
+    assert c["identical"] == c["total"] == n and c["header_equal"]
+    one = tmp_path / "one.sam"
+    r = run([cli] + args + ["-ufi", os.path.join(golden_dir, "ref.ufi"), "-samout", str(one), "-batch", "37", "-threads", "4"])
+    assert r.returncode == 0, r.stderr
+    strip = lambda p: [l for l in open(p, "rb").read().split(b"\n") if not l.startswith(b"@PG")]
+    assert strip(out) == strip(one)   # same records in the same order

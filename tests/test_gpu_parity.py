@@ -246,6 +246,35 @@ def test_chunk_size_invariance(eng, oracle, mid_env):
         ctx.close()
 
 
+def test_dense_index_long_links(eng, oracle, tmp_path):
+    """Mapping parity on an index full of long links (tallies 125 / 253, ufindex.cpp:256-300, 905-926): the reference
+    binary builds the 2 Mb repeat-rich genome at load factor 0.95 (tens of thousands of long-link records); single-end
+    (rows of both row kernels walk them) and paired-end results equal the oracle's on the same index."""
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available to build the index")
+    g = synth.make_genome(2_000_000, n_contigs=4, seed=77, repeat_frac=0.10, n_runs=[(2, 0.3, 1500)], tandem=20, segdup=4)
+    fa, ufi = str(tmp_path / "ref.fa"), str(tmp_path / "dense.ufi")
+    g.write_fasta(fa)
+    oracle.run_reference(["-make_ufi", fa, "-output", ufi, "-load_factor", "0.95"])
+    oix, hix = oracle.Index(ufi), eng.HostIndex(ufi)
+    tallies = oix.blob()[0::5]
+    assert int(((tallies == 125) | (tallies == 253)).sum()) > 10000
+    ctx = eng.Context(0)
+    ctx.set_index(hix)
+    reads, _ = synth.sim_se(g, 20000, 150, 0.02, 0.002, seed=31)
+    b = oracle.ReadBatch.from_arrays(reads)
+    res, runs = ctx.map_se(b.seqs, b.offs)
+    ro, uo, st = oracle.map_se(oix, b, threads=os.cpu_count(), want_stats=True)
+    assert st["row_hops"] > 100000
+    assert_same(ro, uo, res, runs)
+    r1, r2, _ = synth.sim_pe(g, 10000, 150, 0.02, 0.002, seed=32)
+    b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
+    g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+    o1, o2, uo2 = oracle.map_pe(oix, b1, b2, threads=os.cpu_count())
+    assert_same(np.concatenate([o1, o2]), uo2, np.concatenate([g1, g2]), ug)
+    ctx.close()
+
+
 def test_big_capacity_rerun_and_legacy_rescue(eng, oracle, mid_env):
     """Reads that overflow a per-mate capacity are mapped again by the kernels compiled with big capacities (urmb_big.cu),
     in stream behind the mate rescue (URMB_FLAGS bit 8 forces it for every fifth read) or, for what is left, from the host

@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=10_000_000)
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--gpus-list", default="", help="comma list of GPU counts: strong scaling of the same files through `-gpus G`")
     ap.add_argument("--no-reference", action="store_true")
     ap.add_argument("--tabbedout", action="store_true", help="also write and compare -tabbedout files")
     ap.add_argument("--write-threads", default="", help="comma list of URMB_WRITE_THREADS values to try (SAM file in /dev/shm)")
@@ -49,7 +50,7 @@ def main():
     device = torch.device("cuda", 0)
     torch.cuda.set_device(device)
     args = argparse.Namespace(genome_len=3_100_000_000, pairs_per_step=1_000_000, read_len=150, sub=0.01, indel=0.001,
-                              single_end=False)
+                              single_end=False, segdup_frac=0.03, tandem_frac=0.01)
     meta, seq, blob = bench.build_workload(args, 0, 1, device)
     os.makedirs(a.workdir, exist_ok=True)
     ufi = os.path.join(a.workdir, "ref.ufi")
@@ -88,9 +89,9 @@ def main():
     out = {"pairs": a.pairs, "reads": 2 * a.pairs, "host_threads": threads, "gpus": a.gpus,
            "workload": "3.1 Gb synthetic reference (24 contigs, 10% repeats), 2x150 bp, 1% subs + 0.1% indels"}
 
-    def cli(sam, batch=None, tab=None, **env):
+    def cli(sam, batch=None, tab=None, gpus=None, **env):
         c = [exe, "-map2", prefix + "_1.fq", "-reverse", prefix + "_2.fq", "-ufi", ufi, "-samout", sam, "-threads",
-             str(threads), "-gpus", str(a.gpus)] + (["-batch", str(batch)] if batch else []) + (["-tabbedout", tab] if tab else [])
+             str(threads), "-gpus", str(gpus or a.gpus)] + (["-batch", str(batch)] if batch else []) + (["-tabbedout", tab] if tab else [])
         t0 = time.time()
         p = subprocess.run(c, capture_output=True, env=dict(os.environ, URMB_PROFILE="1", **env))
         wall = time.time() - t0
@@ -107,6 +108,16 @@ def main():
     if a.tabbedout:
         out["urmap_b200_with_tabbedout"] = cli(os.path.join(a.workdir, "urmb.sam"), tab=os.path.join(a.workdir, "urmb.tab"))
     out["urmap_b200_to_dev_null"] = cli("/dev/null")
+    # strong scaling through the drop-in: the same FASTQ files with -gpus G (index replicated over NVLink, batches dealt
+    # round-robin); the stage that bounds each run is visible in its host profile (reader / gpu wait / formatter / writer)
+    ngpu = torch.cuda.device_count()
+    for G in [int(x) for x in a.gpus_list.split(",") if x]:
+        if G > ngpu:
+            continue
+        out[f"gpus_{G}_to_dev_null"] = cli("/dev/null", gpus=G)
+        out[f"gpus_{G}_to_file"] = cli(os.path.join(a.workdir, "urmb2.sam"), gpus=G)
+        d = subprocess.run([samdiff, os.path.join(a.workdir, "urmb.sam"), os.path.join(a.workdir, "urmb2.sam")], capture_output=True, text=True)
+        out[f"gpus_{G}_same_sam_as_1_gpu"] = json.loads(d.stdout).get("pct") if d.returncode == 0 else None
     for wt in [int(x) for x in a.write_threads.split(",") if x]:
         out[f"to_file_write_threads_{wt}"] = cli(os.path.join(a.workdir, "urmb2.sam"), URMB_WRITE_THREADS=str(wt))
     for bsz in [int(x) for x in a.batches.split(",") if x]:

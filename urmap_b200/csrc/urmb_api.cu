@@ -416,20 +416,30 @@ extern "C" int urmb_index_device_desc(const urmb_ctx *c, urmb_index_desc *out) {
     return URMB_OK;
 }
 
-// Chunked H2D through two pinned staging buffers (the 30 GB human-scale file is never pinned whole).
-// Host (mapped file) -> device through two page-locked staging buffers; the staging copy, which also takes the page
-// faults of the mapping, is what bounds the load, so several threads share each chunk.
-static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n) {
+// Host (mapped file) -> device(s) through two page-locked staging buffers; the staging copy, which also takes the page
+// faults of the mapping, is what bounds the load, so several threads share each chunk.  With more than one destination
+// the chunk goes to the first GPU over PCIe and from there to every other GPU over NVLink (peer copies on the other GPUs'
+// streams, all in flight together: through NVSwitch each runs at full link rate), pipelined chunk by chunk behind the
+// upload -- the index reaches all GPUs in the time one GPU needs.
+struct Fanout {
+    int n = 0;
+    urmb_ctx **ctxs = nullptr;
+    std::vector<void *> dst;            // destination base per GPU
+    std::vector<cudaStream_t> streams;  // [1..n): copy streams of the peers
+};
+static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n, const Fanout *fan = nullptr) {
     const size_t CH = 128u << 20;
     unsigned nt = std::thread::hardware_concurrency();
     nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt);
     if (getenv("URMB_LOAD_THREADS")) nt = (unsigned)std::max(1, atoi(getenv("URMB_LOAD_THREADS")));
     uint8_t *stage[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
-    CK(cudaHostAlloc(&stage[0], CH, cudaHostAllocDefault));
-    CK(cudaHostAlloc(&stage[1], CH, cudaHostAllocDefault));
-    CK(cudaEventCreate(&ev[0]));
-    CK(cudaEventCreate(&ev[1]));
+    cudaEvent_t ev[2], evc;
+    CK(cudaSetDevice(c->device));
+    CK(cudaHostAlloc(&stage[0], CH, cudaHostAllocPortable));
+    CK(cudaHostAlloc(&stage[1], CH, cudaHostAllocPortable));
+    CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&evc, cudaEventDisableTiming));
     int k = 0;
     std::vector<std::thread> th;
     for (size_t o = 0; o < n; o += CH, k ^= 1) {
@@ -445,64 +455,81 @@ static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n) {
         for (auto &x : th) x.join();
         CK(cudaMemcpyAsync((uint8_t *)dst + o, stage[k], m, cudaMemcpyHostToDevice, c->compute));
         CK(cudaEventRecord(ev[k], c->compute));
+        if (fan && fan->n > 1) {   // the chunk that just landed on GPU 0 goes on to the peers
+            CK(cudaEventRecord(evc, c->compute));
+            for (int g = 1; g < fan->n; ++g) {
+                CK(cudaStreamWaitEvent(fan->streams[g], evc, 0));
+                CK(cudaMemcpyPeerAsync((uint8_t *)fan->dst[g] + o, fan->ctxs[g]->device, (uint8_t *)dst + o, c->device, m, fan->streams[g]));
+            }
+        }
     }
     CK(cudaStreamSynchronize(c->compute));
+    if (fan) for (int g = 1; g < fan->n; ++g) CK(cudaStreamSynchronize(fan->streams[g]));
     cudaFreeHost(stage[0]);
     cudaFreeHost(stage[1]);
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
+    cudaEventDestroy(evc);
     return URMB_OK;
 }
 
 extern "C" int urmb_index_upload(urmb_ctx *c, const urmb_index_host *h) {
-    if (!c || !h) return URMB_E_ARG;
-    CK(cudaSetDevice(c->device));
-    cudaFree(c->own_blob);
-    cudaFree(c->own_seq);
-    c->own_blob = c->own_seq = nullptr;
-    const size_t nb = 5 * (size_t)h->slot_count, ns = h->seq_data_size;
-    CK(cudaMalloc(&c->own_blob, nb + URMB_BLOB_PAD));
-    CK(cudaMalloc(&c->own_seq, ns + URMB_SEQ_PAD));
-    CK(cudaMemset((uint8_t *)c->own_blob + nb, 0, URMB_BLOB_PAD));
-    CK(cudaMemset((uint8_t *)c->own_seq + ns, 0, URMB_SEQ_PAD));
-    int rc = upload_region(c, c->own_blob, h->blob, nb);
-    if (rc) return rc;
-    rc = upload_region(c, c->own_seq, h->seq, ns);
-    if (rc) return rc;
-    urmb_index_desc d;
-    urmb_index_info(h, &d, nullptr);
-    d.d_blob = c->own_blob;
-    d.d_seq = c->own_seq;
-    return set_index(c, &d);
+    urmb_ctx *one[1] = {c};
+    return urmb_index_broadcast(one, 1, h);
 }
 
-// One process, n GPUs: upload to ctx 0, then device-to-device copies (NVLink when peers are enabled).
-// The one-process-per-GPU path (bench.py) instead broadcasts with NCCL and calls urmb_index_attach.
+// UFIndex::FromFile for n GPUs of one process (state1.cpp:185 SetUFI on every worker): buffers on every GPU, one pass
+// over the file (upload_region with the NVLink fan-out), derived data built on each GPU.  The one-process-per-GPU path
+// (bench.py) instead broadcasts with NCCL and calls urmb_index_attach.
 extern "C" int urmb_index_broadcast(urmb_ctx **ctxs, int n, const urmb_index_host *h) {
     if (!ctxs || n < 1 || !h) return URMB_E_ARG;
-    int rc = urmb_index_upload(ctxs[0], h);
-    if (rc) return rc;
-    const size_t nb = 5 * (size_t)h->slot_count + URMB_BLOB_PAD, ns = (size_t)h->seq_data_size + URMB_SEQ_PAD;
-    for (int i = 1; i < n; ++i) {
-        urmb_ctx *c = ctxs[i];
-        CK(cudaSetDevice(c->device));
-        int can = 0;
-        cudaDeviceCanAccessPeer(&can, c->device, ctxs[0]->device);
-        if (can) cudaDeviceEnablePeerAccess(ctxs[0]->device, 0);
-        cudaGetLastError();
-        cudaFree(c->own_blob);
-        cudaFree(c->own_seq);
-        CK(cudaMalloc(&c->own_blob, nb));
-        CK(cudaMalloc(&c->own_seq, ns));
-        CK(cudaMemcpyPeer(c->own_blob, c->device, ctxs[0]->own_blob, ctxs[0]->device, nb));
-        CK(cudaMemcpyPeer(c->own_seq, c->device, ctxs[0]->own_seq, ctxs[0]->device, ns));
-        urmb_index_desc d;
-        urmb_index_info(h, &d, nullptr);
-        d.d_blob = c->own_blob;
-        d.d_seq = c->own_seq;
-        rc = set_index(c, &d);
-        if (rc) return rc;
+    for (int i = 0; i < n; ++i) if (!ctxs[i]) return URMB_E_ARG;
+    urmb_ctx *c = ctxs[0];
+    const size_t nb = 5 * (size_t)h->slot_count, ns = h->seq_data_size;
+    Fanout fb, fs;
+    fb.n = fs.n = n;
+    fb.ctxs = fs.ctxs = ctxs;
+    fb.dst.assign(n, nullptr); fs.dst.assign(n, nullptr);
+    fb.streams.assign(n, nullptr); fs.streams.assign(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        urmb_ctx *d = ctxs[i];
+        {   // errors below are reported against the context they belong to
+            urmb_ctx *c = d;
+            CK(cudaSetDevice(d->device));
+            cudaFree(d->own_blob);
+            cudaFree(d->own_seq);
+            d->own_blob = d->own_seq = nullptr;
+            CK(cudaMalloc(&d->own_blob, nb + URMB_BLOB_PAD));
+            CK(cudaMalloc(&d->own_seq, ns + URMB_SEQ_PAD));
+            CK(cudaMemset((uint8_t *)d->own_blob + nb, 0, URMB_BLOB_PAD));
+            CK(cudaMemset((uint8_t *)d->own_seq + ns, 0, URMB_SEQ_PAD));
+            if (i > 0) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, d->device, ctxs[0]->device);
+                if (can) cudaDeviceEnablePeerAccess(ctxs[0]->device, 0);   // peer copies then go GPU to GPU over NVLink
+                cudaGetLastError();
+            }
+        }
+        fb.dst[i] = d->own_blob;
+        fs.dst[i] = d->own_seq;
+        fb.streams[i] = fs.streams[i] = d->slots[0].copy;
     }
+    int rc = upload_region(c, c->own_blob, h->blob, nb, &fb);
+    if (rc) return rc;
+    rc = upload_region(c, c->own_seq, h->seq, ns, &fs);
+    if (rc) return rc;
+    std::vector<int> rcs(n, 0);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i)   // derived data (2-bit genome, exception bits) on every GPU at once
+        th.emplace_back([&, i]() {
+            urmb_index_desc d;
+            urmb_index_info(h, &d, nullptr);
+            d.d_blob = ctxs[i]->own_blob;
+            d.d_seq = ctxs[i]->own_seq;
+            rcs[i] = set_index(ctxs[i], &d);
+        });
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n; ++i) if (rcs[i]) return rcs[i];
     return URMB_OK;
 }
 

@@ -33,7 +33,7 @@ extern "C" {
 #define URMB_E_UNSUPPORTED (-6) /* word length > 32, batch of more than 4 GB of bases, ... */
 #define URMB_E_NODEVICE (-7)  /* no CUDA device: there is NO CPU fallback */
 
-#define URMB_SLOTS 3
+#define URMB_SLOTS 8
 #define URMB_MAX_READ_LEN 256
 
 typedef struct urmb_index_host urmb_index_host; /* parsed UFI file in (pinned) host memory */

@@ -168,6 +168,14 @@ struct Slot {
     uint32_t *d_todo = nullptr; size_t d_todo_cap = 0;
     uint32_t *d_rescue = nullptr; size_t d_rescue_cap = 0;
     uint32_t *d_ovf = nullptr;                // reads over a per-mate capacity (kOvfCap entries), see DevOut::ovf_list
+    // Mate rescue and big-capacity rerun of this slot's batch run on the slot's own low-priority side stream with their own
+    // pool and scratch: the (occasionally long) tail of one batch then delays nothing but that batch's results.
+    cudaStream_t side = nullptr;
+    RescueSave *rpool = nullptr;              // saved states of the pairs that need mate rescue
+    uint32_t *rq[2] = {nullptr, nullptr};     // work lists of the rescue rounds
+    size_t rescue_cap = 0;
+    WarpScratch *rescue_scratch = nullptr;    // n_rescue_warps entries
+    void *big_scratch = nullptr;              // kBigWarps x urmb_big_scratch_bytes()
     DevBatch batch{};
     size_t seq_bytes = 0;
     bool staged = false, launched = false, downloaded = false;
@@ -189,25 +197,12 @@ struct urmb_ctx {
     cudaStream_t compute = nullptr;
     cudaStream_t rescue = nullptr;            // low-priority side stream of the mate-rescue kernel
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
-    cudaStream_t rescue2 = nullptr;           // second side stream: consecutive launches alternate, so that the rescue rounds
-                                              // of a batch never queue behind the (occasionally long) tail of the batch before
-    cudaEvent_t ev_rescue_tail[2] = {nullptr, nullptr};   // last event recorded on each rescue stream
-    bool rescue_used[2] = {false, false};
     bool rescue_inline = false;               // URMB_RESCUE_INLINE: run the rescue kernel on the compute stream
     WarpScratch *scratch = nullptr;
     int n_scratch_warps = 0;
-    WarpScratch *rescue_scratch = nullptr;
     int n_rescue_warps = 0;
     MateSave *pool = nullptr;      // saved mate states of one chunk of the paired-end second pass (2 per pair)
     size_t pool_pairs = 0;
-    // Rescue pools: saved states of the pairs that need mate rescue, two so that the rescue rounds of batch k (side stream)
-    // and the finish kernels of batch k + 1 (compute stream) never share one; work lists of the rounds beside them.
-    RescueSave *rpool[2] = {nullptr, nullptr};
-    uint32_t *rq[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    size_t rescue_cap = 0;
-    cudaEvent_t ev_rpool[2] = {nullptr, nullptr};   // end of the last rescue that used the pool
-    bool rpool_used[2] = {false, false};
-    int rparity = 0;
     // Resources of the big-capacity rerun (urmb_big.cu), allocated when a batch first needs them
     struct Big {
         static constexpr uint32_t kUnits = 1024;   // units per rerun piece
@@ -223,7 +218,8 @@ struct urmb_ctx {
         size_t seq_cap = 0, probe_cap = 0, view_cap = 0, runs_cap = 0;
         bool ready = false;
     } big;
-    void *big_scratch = nullptr;   // 2 x kBigWarps x urmb_big_scratch_bytes(): in-stream rerun, one set per side stream
+    int prio_lo = 0;
+    bool no_rerun = false;         // URMB_NO_RERUN
     uint64_t rerun_total = 0;      // reads mapped again by the big-capacity build
     uint32_t force_rerun = 0;      // URMB_FORCE_RERUN=N (tests): every N-th unit is mapped again by the big-capacity build
     bool rescue_legacy = false;    // URMB_RESCUE_LEGACY: no rescue pool, every rescued pair is searched again from scratch
@@ -290,24 +286,22 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->compute, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&c->rescue, cudaStreamNonBlocking, prio_lo));
-    CK(cudaStreamCreateWithPriority(&c->rescue2, cudaStreamNonBlocking, prio_lo));
+    c->prio_lo = prio_lo;
     for (auto &ev : c->ev_mark) CK(cudaEventCreate(&ev));
-    for (auto &ev : c->ev_rpool) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *f = getenv("URMB_RESCUE_LEGACY")) c->rescue_legacy = atoi(f) != 0;
     if (const char *f = getenv("URMB_FORCE_RERUN")) c->force_rerun = (uint32_t)std::max(0, atoi(f));
-    for (auto &ev : c->ev_rescue_tail) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     c->n_scratch_warps = max_search_warps(c->sm_count);
     // The rescue kernel is a queue of few, long work items that runs beside the next batch: a small persistent grid
     // (one block per SM) takes few registers away from the main kernels and still drains the queue in time.
     c->n_rescue_warps = c->sm_count * 12;
     if (const char *f = getenv("URMB_RESCUE_WARPS")) c->n_rescue_warps = std::max(4, atoi(f) & ~3);
     if (const char *f = getenv("URMB_RESCUE_INLINE")) c->rescue_inline = atoi(f) != 0;
-    CK(cudaMalloc(&c->rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps * 2));   // one set per side stream
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
-    if (!getenv("URMB_NO_RERUN")) CK(cudaMalloc(&c->big_scratch, urmb_big_scratch_bytes() * (size_t)kBigWarps * 2));
+    c->no_rerun = getenv("URMB_NO_RERUN") != nullptr;
     for (auto &s : c->slots) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, prio_lo));
         for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h, &s.ev_rescue}) CK(cudaEventCreate(ev));
         CK(cudaMalloc(&s.d_counters, CT_COUNT * sizeof(uint32_t)));
         CK(cudaMalloc(&s.d_ovf, kOvfCap * sizeof(uint32_t)));
@@ -319,6 +313,8 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
 
 static void free_slot(Slot &s) {
     if (s.copy) cudaStreamDestroy(s.copy);
+    if (s.side) cudaStreamDestroy(s.side);
+    cudaFree(s.rpool); cudaFree(s.rq[0]); cudaFree(s.rq[1]); cudaFree(s.rescue_scratch); cudaFree(s.big_scratch);
     for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h, s.ev_rescue}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s.kev) cudaEventDestroy(ev);
     cudaFreeHost(s.h_seqs); cudaFreeHost(s.h_offs); cudaFreeHost(s.h_res); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_counters);
@@ -334,13 +330,9 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     for (auto &s : c->slots) free_slot(s);
     if (c->compute) cudaStreamDestroy(c->compute);
     if (c->rescue) cudaStreamDestroy(c->rescue);
-    if (c->rescue2) cudaStreamDestroy(c->rescue2);
     for (auto ev : c->ev_mark) if (ev) cudaEventDestroy(ev);
-    for (auto ev : c->ev_rescue_tail) if (ev) cudaEventDestroy(ev);
-    cudaFree(c->rescue_scratch);
     cudaFree(c->scratch);
     cudaFree(c->pool);
-    cudaFree(c->big_scratch);
     {
         urmb_ctx::Big &g = c->big;
         if (g.stream) cudaStreamDestroy(g.stream);
@@ -348,12 +340,6 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
         cudaFree(g.d_counters); cudaFree(g.d_todo); cudaFree(g.d_rescue); cudaFree(g.d_res); cudaFree(g.d_second); cudaFree(g.d_runs);
         cudaFree(g.scratch); cudaFree(g.pool);
         cudaFreeHost(g.h_res); cudaFreeHost(g.h_second); cudaFreeHost(g.h_runs); cudaFreeHost(g.h_counters); cudaFreeHost(g.h_offs);
-    }
-    for (int k = 0; k < 2; ++k) {
-        cudaFree(c->rpool[k]);
-        cudaFree(c->rq[k][0]);
-        cudaFree(c->rq[k][1]);
-        if (c->ev_rpool[k]) cudaEventDestroy(c->ev_rpool[k]);
     }
     cudaFree(c->own_blob);
     cudaFree(c->own_seq);
@@ -576,26 +562,24 @@ static int check_batch(urmb_ctx *c, const urmb_batch *b) {
 // Sizes every slot (and the pool of saved mate states) for batches of n_units reads / pairs of up to max_read_len bases,
 // so that the first batches do not pay for the allocations.  Touches only the slots and the pool: the CLI calls it from
 // a helper thread while urmb_index_broadcast is still copying the index.
-// Rescue pools for paired-end batches of n pairs: one pair in eight (at least 4096, at most 131072 entries of 21.6 kB);
-// pairs beyond that take the legacy kernel.
-static int size_rescue_pools(urmb_ctx *c, size_t n) {
-    if (c->rescue_legacy || c->P.pe_method == 5) return URMB_OK;
+// Side-stream resources of a slot for batches of n units: scratch of the rescue / rerun kernels, and for paired-end
+// batches the rescue pool: one pair in eight (at least 4096, at most 131072 entries of 21.6 kB); pairs beyond that take
+// the legacy kernel.
+static int size_side_resources(urmb_ctx *c, Slot &s, size_t n, bool paired) {
+    if (!s.big_scratch && !c->no_rerun) CK(cudaMalloc(&s.big_scratch, urmb_big_scratch_bytes() * (size_t)kBigWarps));
+    if (!paired || c->P.pe_method == 5) return URMB_OK;
+    if (!s.rescue_scratch) CK(cudaMalloc(&s.rescue_scratch, sizeof(WarpScratch) * (size_t)c->n_rescue_warps));
+    if (c->rescue_legacy) return URMB_OK;
     const size_t want = std::min<size_t>(std::max<size_t>(n / 8, 4096), 131072);
-    if (want <= c->rescue_cap) return URMB_OK;
-    CK(cudaStreamSynchronize(c->compute));
-    CK(cudaStreamSynchronize(c->rescue));
-    CK(cudaStreamSynchronize(c->rescue2));
-    for (int k = 0; k < 2; ++k) {
-        cudaFree(c->rpool[k]); cudaFree(c->rq[k][0]); cudaFree(c->rq[k][1]);
-        c->rpool[k] = nullptr; c->rq[k][0] = c->rq[k][1] = nullptr;
-    }
-    c->rescue_cap = 0;
-    for (int k = 0; k < 2; ++k) {
-        CK(cudaMalloc(&c->rpool[k], sizeof(RescueSave) * want));
-        CK(cudaMalloc(&c->rq[k][0], sizeof(uint32_t) * (want + 1)));
-        CK(cudaMalloc(&c->rq[k][1], sizeof(uint32_t) * (want + 1)));
-    }
-    c->rescue_cap = want;
+    if (want <= s.rescue_cap) return URMB_OK;
+    CK(cudaStreamSynchronize(s.side));
+    cudaFree(s.rpool); cudaFree(s.rq[0]); cudaFree(s.rq[1]);
+    s.rpool = nullptr; s.rq[0] = s.rq[1] = nullptr;
+    s.rescue_cap = 0;
+    CK(cudaMalloc(&s.rpool, sizeof(RescueSave) * want));
+    CK(cudaMalloc(&s.rq[0], sizeof(uint32_t) * (want + 1)));
+    CK(cudaMalloc(&s.rq[1], sizeof(uint32_t) * (want + 1)));
+    s.rescue_cap = want;
     return URMB_OK;
 }
 
@@ -641,7 +625,8 @@ extern "C" int urmb_reserve(urmb_ctx *c, uint32_t n_units, uint32_t max_read_len
         CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
         c->pool_pairs = want;
     }
-    if (paired && (rc = size_rescue_pools(c, n))) return rc;
+    for (auto &s : c->slots)
+        if ((rc = size_side_resources(c, s, n, paired != 0))) return rc;
     return URMB_OK;
 }
 
@@ -747,8 +732,8 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
             CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
             c->pool_pairs = want;
         }
-        if (r2 && (rc = size_rescue_pools(c, n))) return rc;
     }
+    if ((rc = size_side_resources(c, s, n, r2 != nullptr))) return rc;
     if ((rc = grow_host(c, s.h_res, s.h_res_cap, (size_t)nreads + 1))) return rc;
     if (c->params.want_second && r2) {
         if ((rc = grow_dev(c, s.d_second, s.d_second_cap, (size_t)nreads + 1))) return rc;
@@ -803,8 +788,7 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     Slot &s = c->slots[si];
     if (!s.staged) return fail(c, URMB_E_ARG, "slot not staged");
     CK(cudaSetDevice(c->device));
-    const int side_ix = c->rparity;            // side stream and rescue pool of this launch (both alternate)
-    cudaStream_t side = side_ix ? c->rescue2 : c->rescue;
+    cudaStream_t side = s.side;
     CK(cudaStreamWaitEvent(c->compute, s.ev_h2d, 0));
     if (s.launched) CK(cudaStreamWaitEvent(c->compute, s.ev_rescue, 0));   // an earlier launch of this very slot
     CK(cudaMemsetAsync(s.d_counters, 0, CT_COUNT * sizeof(uint32_t), c->compute));
@@ -815,15 +799,11 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         DevProbe pr{s.d_tally, s.d_pos, s.d_ext, s.d_view, view_stride_for(s.batch.seqcap)};
         urmb_second *second = (c->params.want_second && s.batch.paired) ? s.d_second : nullptr;
         if (second) CK(cudaMemsetAsync(second, 0, (size_t)s.batch.n_reads * sizeof(urmb_second), c->compute));
-        // this launch's rescue pool: the other one may still be in use by the rescue rounds of the previous launch
-        const int rp = c->rparity;
-        c->rparity ^= 1;
-        const bool use_pool = s.batch.paired && c->rescue_cap && c->rpool[rp];
-        if (use_pool && c->rpool_used[rp]) CK(cudaStreamWaitEvent(c->compute, c->ev_rpool[rp], 0));
+        const bool use_pool = s.batch.paired && s.rescue_cap && s.rpool;
         DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue, second,
-                 use_pool ? c->rpool[rp] : nullptr, use_pool ? (uint32_t)c->rescue_cap : 0u,
-                 {use_pool ? c->rq[rp][0] : nullptr, use_pool ? c->rq[rp][1] : nullptr},
-                 c->big_scratch ? s.d_ovf : nullptr, c->big_scratch ? kOvfCap : 0u};
+                 use_pool ? s.rpool : nullptr, use_pool ? (uint32_t)s.rescue_cap : 0u,
+                 {use_pool ? s.rq[0] : nullptr, use_pool ? s.rq[1] : nullptr},
+                 s.big_scratch ? s.d_ovf : nullptr, s.big_scratch ? kOvfCap : 0u};
         SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
         TraceCtx tc{&s, c->compute, cudaSuccess};
@@ -839,22 +819,18 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         CK(cudaEventRecord(s.ev_k2, c->compute));
         // Mate rescue: few, long work items.  It runs on the low-priority side stream so that its tail overlaps the
         // kernels of the next batch instead of idling the GPU.
-        SearchRes RR{c->rescue_scratch + (size_t)side_ix * c->n_rescue_warps, c->n_rescue_warps, nullptr, 0};
+        SearchRes RR{s.rescue_scratch, c->n_rescue_warps, nullptr, 0};
         cudaStream_t rs = c->rescue_inline ? c->compute : side;
         CK(cudaStreamWaitEvent(rs, s.ev_k2, 0));
         tc.stream = rs;
         e = launch_rescue(c->ix, P, s.batch, pr, o, c->rescue_inline ? R : RR, rs, c->sm_count, &tr);
         if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, c->compute));
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("rescue launch: ") + cudaGetErrorString((cudaError_t)-e));
-        if (use_pool) {
-            CK(cudaEventRecord(c->ev_rpool[rp], rs));
-            c->rpool_used[rp] = true;
-        }
         c->launches += (uint64_t)e;
-        if (c->big_scratch) {
+        if (s.big_scratch) {
             // reads over a per-mate capacity of the fast kernels are searched again by the big-capacity build, queued
             // behind the mate rescue on the same stream (rs already waits for the search kernels)
-            e = urmb_big_rerun_listed(&c->ix, &P, &s.batch, &pr, &o, (uint8_t *)c->big_scratch + (size_t)side_ix * kBigWarps * urmb_big_scratch_bytes(),
+            e = urmb_big_rerun_listed(&c->ix, &P, &s.batch, &pr, &o, s.big_scratch,
                                       kBigWarps, rs, c->sm_count);
             if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun launch: ") + cudaGetErrorString((cudaError_t)-e));
             c->launches += (uint64_t)e;
@@ -869,8 +845,6 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     }
     if (!rescued) CK(cudaStreamWaitEvent(side, s.ev_k2, 0));
     CK(cudaEventRecord(s.ev_rescue, side));
-    CK(cudaEventRecord(c->ev_rescue_tail[side_ix], side));
-    c->rescue_used[side_ix] = true;
     s.launched = true;
     s.downloaded = false;
     return URMB_OK;
@@ -879,8 +853,8 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
 extern "C" int urmb_mark(urmb_ctx *c, int which) {
     if (!c || which < 0 || which > 1) return URMB_E_ARG;
     CK(cudaSetDevice(c->device));
-    for (int k = 0; k < 2; ++k)
-        if (c->rescue_used[k]) CK(cudaStreamWaitEvent(c->compute, c->ev_rescue_tail[k], 0));
+    for (auto &s : c->slots)   // a mark comes after the side-stream work of every batch launched so far
+        if (s.launched) CK(cudaStreamWaitEvent(c->compute, s.ev_rescue, 0));
     CK(cudaEventRecord(c->ev_mark[which], c->compute));
     return URMB_OK;
 }

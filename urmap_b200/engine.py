@@ -19,7 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liburmb.so")
 
-URMB_SLOTS = 3
+URMB_SLOTS = 8
 URMB_SEQ_PAD = 4096
 URMB_BLOB_PAD = 16
 URMB_E_OVERFLOW = -5

@@ -181,7 +181,7 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     RescueSave *rpool = rcap ? (RescueSave *)malloc(sizeof(RescueSave) * rcap) : nullptr;
     if (rpool) memset(rpool, 0xEE, sizeof(RescueSave) * rcap);
     std::vector<uint32_t> rq0(rcap + 1), rq1(rcap + 1);
-    DevOut o{res, runs, runs_cap, ct, todo.data(), rescue.data(), paired ? g_emu_second : nullptr, rpool, rcap, {rq0.data(), rq1.data()}, nullptr, 0u};
+    DevOut o{res, runs, runs_cap, ct, todo.data(), rescue.data(), paired ? g_emu_second : nullptr, rpool, rcap, {rq0.data(), rq1.data()}, nullptr, 0u, nullptr};
     const int nw = 4;
     WarpScratch *ws = (WarpScratch *)malloc(sizeof(WarpScratch) * nw);
     memset(ws, 0xEE, sizeof(WarpScratch) * nw);

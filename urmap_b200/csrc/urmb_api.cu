@@ -168,6 +168,10 @@ struct Slot {
     uint32_t *d_todo = nullptr; size_t d_todo_cap = 0;
     uint32_t *d_rescue = nullptr; size_t d_rescue_cap = 0;
     uint32_t *d_ovf = nullptr;                // reads over a per-mate capacity (kOvfCap entries), see DevOut::ovf_list
+    uint32_t *d_ovf_units = nullptr;          // their units, work list of the rerun (DevOut::ovf_units)
+    cudaStream_t big = nullptr;               // high-priority stream of the big-capacity rerun (a handful of blocks that
+                                              // must get onto an SM while the persistent main kernels keep them all busy)
+    cudaEvent_t ev_big = nullptr, ev_side = nullptr;
     // Mate rescue and big-capacity rerun of this slot's batch run on the slot's own low-priority side stream with their own
     // pool and scratch: the (occasionally long) tail of one batch then delays nothing but that batch's results.
     cudaStream_t side = nullptr;
@@ -305,6 +309,10 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
         for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h, &s.ev_rescue}) CK(cudaEventCreate(ev));
         CK(cudaMalloc(&s.d_counters, CT_COUNT * sizeof(uint32_t)));
         CK(cudaMalloc(&s.d_ovf, kOvfCap * sizeof(uint32_t)));
+        CK(cudaMalloc(&s.d_ovf_units, kOvfCap * sizeof(uint32_t)));
+        CK(cudaStreamCreateWithPriority(&s.big, cudaStreamNonBlocking, prio_hi));
+        CK(cudaEventCreateWithFlags(&s.ev_big, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_side, cudaEventDisableTiming));
         CK(cudaHostAlloc(&s.h_counters, CT_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
     }
     *out = c;
@@ -314,6 +322,10 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
 static void free_slot(Slot &s) {
     if (s.copy) cudaStreamDestroy(s.copy);
     if (s.side) cudaStreamDestroy(s.side);
+    if (s.big) cudaStreamDestroy(s.big);
+    if (s.ev_big) cudaEventDestroy(s.ev_big);
+    if (s.ev_side) cudaEventDestroy(s.ev_side);
+    cudaFree(s.d_ovf_units);
     cudaFree(s.rpool); cudaFree(s.rq[0]); cudaFree(s.rq[1]); cudaFree(s.rescue_scratch); cudaFree(s.big_scratch);
     for (cudaEvent_t ev : {s.ev_h2d0, s.ev_h2d, s.ev_k0, s.ev_k1, s.ev_k2, s.ev_d2h, s.ev_rescue}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s.kev) cudaEventDestroy(ev);
@@ -803,7 +815,7 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue, second,
                  use_pool ? s.rpool : nullptr, use_pool ? (uint32_t)s.rescue_cap : 0u,
                  {use_pool ? s.rq[0] : nullptr, use_pool ? s.rq[1] : nullptr},
-                 s.big_scratch ? s.d_ovf : nullptr, s.big_scratch ? kOvfCap : 0u};
+                 s.big_scratch ? s.d_ovf : nullptr, s.big_scratch ? kOvfCap : 0u, s.big_scratch ? s.d_ovf_units : nullptr};
         SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
         TraceCtx tc{&s, c->compute, cudaSuccess};
@@ -828,13 +840,27 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("rescue launch: ") + cudaGetErrorString((cudaError_t)-e));
         c->launches += (uint64_t)e;
         if (s.big_scratch) {
-            // reads over a per-mate capacity of the fast kernels are searched again by the big-capacity build, queued
-            // behind the mate rescue on the same stream (rs already waits for the search kernels)
-            e = urmb_big_rerun_listed(&c->ix, &P, &s.batch, &pr, &o, s.big_scratch,
-                                      kBigWarps, rs, c->sm_count);
-            if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun launch: ") + cudaGetErrorString((cudaError_t)-e));
-            c->launches += (uint64_t)e;
+            // Reads over a per-mate capacity of the fast kernels are searched again by the big-capacity build on the slot's
+            // high-priority stream: a first pass as soon as the search kernels are done (beside the mate rescue), a second
+            // one after the mate rescue for the reads it added to the list (usually none).
+            cudaStream_t bs = c->rescue_inline ? c->compute : s.big;
+            for (int pass = 0; pass < 2; ++pass) {
+                if (!c->rescue_inline) {
+                    if (pass == 0) CK(cudaStreamWaitEvent(bs, s.ev_k2, 0));
+                    else {
+                        CK(cudaEventRecord(s.ev_side, rs));
+                        CK(cudaStreamWaitEvent(bs, s.ev_side, 0));
+                    }
+                } else if (pass == 0) continue;   // inline: everything is on one stream, one pass at the end is enough
+                e = urmb_big_rerun_listed(&c->ix, &P, &s.batch, &pr, &o, s.big_scratch, kBigWarps, bs, c->sm_count);
+                if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun launch: ") + cudaGetErrorString((cudaError_t)-e));
+                c->launches += (uint64_t)e;
+            }
             if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, c->compute));
+            else {   // the batch is done when both streams are
+                CK(cudaEventRecord(s.ev_big, bs));
+                CK(cudaStreamWaitEvent(rs, s.ev_big, 0));
+            }
         }
         if (tc.err != cudaSuccess) return fail(c, URMB_E_CUDA, std::string("event record: ") + cudaGetErrorString(tc.err));
         rescued = true;   // the side stream has work of this batch (or, inline, waits for the re-recorded ev_k2 below)
@@ -979,7 +1005,7 @@ static int rerun_overflowed(urmb_ctx *c, Slot &s, uint32_t &used) {
         b.n_units = m;
         DevProbe pr{g.d_tally, g.d_pos, g.d_ext, g.d_view, view_stride_for(b.seqcap)};
         DevOut out{g.d_res, g.d_runs, (uint32_t)g.runs_cap, g.d_counters, g.d_todo, g.d_rescue, second ? g.d_second : nullptr,
-                   nullptr, 0u, {nullptr, nullptr}, nullptr, 0u};
+                   nullptr, 0u, {nullptr, nullptr}, nullptr, 0u, g.d_rescue};
         const int e = urmb_big_map(&c->ix, &c->P, &b, &pr, &out, g.scratch, urmb_ctx::Big::kWarps, g.pool, 256, g.stream, c->sm_count);
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun: ") + cudaGetErrorString((cudaError_t)-e));
         c->launches += (uint64_t)e;

@@ -83,11 +83,12 @@ enum {
     CT_TODO_TOTAL = 4,  // pairs that went through the staged second pass (whole batch, statistics)
     CT_RESCUE_LEGACY = 5, // pairs queued for the legacy mate-rescue kernel (rescue pool full)
     CT_RESCUE_DPS = 6,  // full-window DPs run by the rescue rounds (statistics)
-    CT_OVF_LIST = 7,    // entries of DevOut::ovf_list
+    CT_OVF_LIST = 7,    // entries of DevOut::ovf_list (reads over a capacity, appended by the fast kernels)
     CT_CHUNK0 = 8,      // first per-chunk counter
     CT_HEAD = 8,        // work-queue head of the first-pass kernel
     CT_TODO = 9,        // pairs of this chunk saved for the staged second pass
     CT_STAGE_A = 10, CT_STAGE_B = 11, CT_STAGE_C = 12, CT_FINISH = 13, CT_STAGE_B2 = 14,   // work-queue heads of the stage kernels
+    CT_CHUNK_END = 16,  // [CT_CHUNK0, CT_CHUNK_END) are zeroed by the launcher between chunks
     // mate-rescue rounds (whole batch): round r scans the pairs of list r (round 0: every pool entry) and appends the
     // ones that stop at a full-window DP to list r + 1; the DP kernel of round r works through list r + 1
     CT_RQ_COUNT = 16,                           // [kRescueRounds + 2] entries of list r
@@ -99,7 +100,13 @@ enum {
     CT_DBG_MAXT = CT_DBG_WIN + 5,
     CT_DBG_MAXW = CT_DBG_MAXT + 1,
     CT_DBG_OVF = CT_DBG_MAXW + 1,                   // [5] reads over a capacity, by capacity (hits, path runs, run pool, HSPs, path assembly)
-    CT_DBG_HSPS = CT_DBG_OVF + 5,                   // [4] reads by final HSP count: <= 256, <= 512, <= 1024, more (statistics of the big-capacity rerun)
+    // big-capacity rerun (urmb_big.cu): ovf_list entries already turned into units, units listed so far, first unit and
+    // work-queue head of the current pass
+    CT_OVF_DONE = CT_DBG_OVF + 5,
+    CT_OVF_UNITS = CT_OVF_DONE + 1,
+    CT_OVF_BASE = CT_OVF_UNITS + 1,
+    CT_OVF_HEAD = CT_OVF_BASE + 1,
+    CT_DBG_HSPS = CT_OVF_HEAD + 1,                   // [4] reads by final HSP count: <= 256, <= 512, <= 1024, more (statistics of the big-capacity rerun)
     CT_DBG_MAXHSP = CT_DBG_HSPS + 4,
     CT_COUNT = CT_DBG_MAXHSP + 1
 };
@@ -117,7 +124,8 @@ struct DevOut {
     uint32_t rescue_cap;
     uint32_t *rq[2];       // [rescue_cap] each: work lists of the rescue rounds (pool entry indexes), ping-pong
     uint32_t *ovf_list;    // [ovf_cap] reads whose search went over a per-mate capacity (null: not recorded); the big-capacity
-    uint32_t ovf_cap;      //           build searches them again at the end of the batch (urmb_big.cu)
+    uint32_t ovf_cap;      //           build searches them again (urmb_big.cu)
+    uint32_t *ovf_units;   // [ovf_cap] the units (reads / pairs) of ovf_list without duplicates: work list of the rerun kernels
 };
 
 struct MateScratch {

@@ -2916,15 +2916,26 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
     const size_t msz = mate_smem_bytes(b.qcap, b.seqcap, true);
     Env E;
     make_env(E, A.ix, A.P, b, A.scratch, pl, sw, gw, lane);
-    const bool listed = (MODE == 2) || (MODE == 3 && A.unit_count == 0xFFFFFFFFu);   // units come from the list o.rescue
+    // units from a list: the pairs finish_kernel left to the legacy mate rescue (o.rescue), or -- big-capacity build -- the
+    // units of the current rerun pass (o.ovf_units from CT_OVF_BASE on)
+    const bool listed = (MODE == 2) || (MODE == 3 && A.unit_count == 0xFFFFFFFFu);
+#ifdef URMB_BIG
+    const uint32_t lbase = o.counters[CT_OVF_BASE];
+    const uint32_t n_work = listed ? o.counters[CT_OVF_UNITS] - lbase : A.unit_count;
+    const uint32_t *ulist = o.ovf_units + lbase;
+    constexpr int kListHead = CT_OVF_HEAD;
+#else
     const uint32_t n_work = listed ? o.counters[CT_RESCUE_LEGACY] : A.unit_count;
+    const uint32_t *ulist = o.rescue;
+    constexpr int kListHead = CT_RESCUE_HEAD;
+#endif
 
     for (;;) {
         uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(&o.counters[listed ? CT_RESCUE_HEAD : CT_HEAD], 1u);
+        if (lane == 0) u = atomicAdd(&o.counters[listed ? kListHead : CT_HEAD], 1u);
         u = __shfl_sync(FULL, u, 0);
         if (u >= n_work) break;
-        u = listed ? o.rescue[u] : A.unit_base + u;
+        u = listed ? ulist[u] : A.unit_base + u;
         if (MODE == 3) {   // single-end, the whole of Search_Lo in one kernel (search1m6.cpp:35-277)
             Mate m;
             load_mate(E, m, b, A.pr, u, sw, &E.ws->m[0], true);
@@ -3223,9 +3234,14 @@ __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se6(const __g
 __global__ void __launch_bounds__(128, URMB_LB_PAIR) pair_kernel(const __grid_constant__ KArgs A) { search_body<1>(A); }
 __global__ void __launch_bounds__(128, 4) rescue_kernel(const __grid_constant__ KArgs A) { search_body<2>(A); }
 __global__ void __launch_bounds__(128, 4) se_full_kernel(const __grid_constant__ KArgs A) { search_body<3>(A); }
-__global__ void identity_list_kernel(uint32_t *list, uint32_t n, uint32_t *count) {
+__global__ void identity_list_kernel(uint32_t *list, uint32_t n, uint32_t *counters) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) list[i] = i;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *count = n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counters[CT_OVF_UNITS] = n;
+        counters[CT_OVF_BASE] = 0;
+        counters[CT_OVF_HEAD] = 0;
+        counters[CT_RESCUE_LEGACY] = n;   // (the fast build's listed mode)
+    }
 }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_a(const __grid_constant__ KArgs A) { stage_body<0>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ROWS) rows_kernel(const __grid_constant__ KArgs A) { stage_body<1>(A); }
@@ -3316,9 +3332,9 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
             A.unit_base = u0;
             A.unit_count = cnt;
 #ifndef URMB_EMU
-            URMB_TRY((int)cudaMemsetAsync(o.counters + CT_CHUNK0, 0, (CT_COUNT - CT_CHUNK0) * sizeof(uint32_t), (cudaStream_t)stream));
+            URMB_TRY((int)cudaMemsetAsync(o.counters + CT_CHUNK0, 0, (CT_CHUNK_END - CT_CHUNK0) * sizeof(uint32_t), (cudaStream_t)stream));
 #else
-            for (int i = CT_CHUNK0; i < CT_COUNT; ++i) o.counters[i] = 0;
+            for (int i = CT_CHUNK0; i < CT_CHUNK_END; ++i) o.counters[i] = 0;
 #endif
             URMB_TRY(launch_one(seed_kernel_se, 1, tr, A, SmemPlan{1, 1, 0}, cnt, R, stream, sm_count, warps_used));
             URMB_TRY(launch_one(align_kernel_se3, 2, tr, A, SmemPlan{1, 0, 1}, cnt, R, stream, sm_count, nullptr));
@@ -3334,9 +3350,9 @@ int launch_search(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
         A.unit_base = u0;
         A.unit_count = cnt;
 #ifndef URMB_EMU
-        URMB_TRY((int)cudaMemsetAsync(o.counters + CT_CHUNK0, 0, (CT_COUNT - CT_CHUNK0) * sizeof(uint32_t), (cudaStream_t)stream));
+        URMB_TRY((int)cudaMemsetAsync(o.counters + CT_CHUNK0, 0, (CT_CHUNK_END - CT_CHUNK0) * sizeof(uint32_t), (cudaStream_t)stream));
 #else
-        for (int i = CT_CHUNK0; i < CT_COUNT; ++i) o.counters[i] = 0;
+        for (int i = CT_CHUNK0; i < CT_CHUNK_END; ++i) o.counters[i] = 0;
 #endif
         URMB_TRY(launch_one(pair_kernel, 1, tr, A, SmemPlan{2, 1, 0}, cnt, R, stream, sm_count, warps_used));
         URMB_TRY(launch_one(align_kernel_a, 2, tr, A, SmemPlan{1, 0, 1}, 2 * cnt, R, stream, sm_count, nullptr));
@@ -3360,7 +3376,7 @@ int launch_search_monolithic(const DevIndex &ix, const DevParams &P, const DevBa
         URMB_TRY(launch_one(se_full_kernel, 1, nullptr, A, SmemPlan{1, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
         return 1;
     }
-    URMB_LAUNCH(identity_list_kernel, 1, 256, 0, stream, o.rescue, b.n_units, o.counters + CT_RESCUE_LEGACY);
+    URMB_LAUNCH(identity_list_kernel, 1, 256, 0, stream, o.ovf_units ? o.ovf_units : o.rescue, b.n_units, o.counters);
     URMB_TRY((int)cudaGetLastError());
     URMB_TRY(launch_one(rescue_kernel, 9, nullptr, A, SmemPlan{2, 1, 1}, b.n_units, R, stream, sm_count, nullptr));
     return 2;
@@ -3371,24 +3387,31 @@ int launch_search_monolithic(const DevIndex &ix, const DevParams &P, const DevBa
 // o.rescue, ready for a listed launch of rescue_kernel / se_full_kernel; the overflow counter starts again from zero (the
 // rerun counts what is still over).  One block; the list is short.
 __global__ void __launch_bounds__(256) overflow_list_kernel(DevOut o, uint32_t n_units, int paired) {
+    // entries [start, n) of ovf_list are new since the last pass: their units (the smaller read index of a pair stands
+    // for it; both mates of a pair are always written by the same kernel, hence listed in the same pass) become the
+    // units [CT_OVF_BASE, CT_OVF_UNITS) of this pass; the reads leave the overflow count (the rerun counts what stays over)
+    const uint32_t start = o.counters[CT_OVF_DONE];
     const uint32_t n = min(o.counters[CT_OVF_LIST], o.ovf_cap);
+    const uint32_t base = o.counters[CT_OVF_UNITS];
     __shared__ uint32_t cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    for (uint32_t i = start + threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t r = o.ovf_list[i], u = (paired && r >= n_units) ? r - n_units : r;
         bool first = true;
-        for (uint32_t j = 0; j < n && first; ++j) {
+        for (uint32_t j = start; j < n && first; ++j) {
             const uint32_t rj = o.ovf_list[j], uj = (paired && rj >= n_units) ? rj - n_units : rj;
-            if (uj == u && (rj < r)) first = false;   // the smaller read index of a unit stands for it
+            if (uj == u && (rj < r)) first = false;
         }
-        if (first) o.rescue[atomicAdd(&cnt, 1u)] = u;
+        if (first) o.ovf_units[base + atomicAdd(&cnt, 1u)] = u;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        o.counters[CT_RESCUE_LEGACY] = cnt;
-        o.counters[CT_RESCUE_HEAD] = 0;
-        if (o.counters[CT_OVF_LIST] <= o.ovf_cap) o.counters[CT_OVERFLOW] = 0;   // else: the host finds the rest by their flags
+        o.counters[CT_OVF_BASE] = base;
+        o.counters[CT_OVF_UNITS] = base + cnt;
+        o.counters[CT_OVF_HEAD] = 0;
+        o.counters[CT_OVF_DONE] = n;
+        if (n > start) atomicSub(&o.counters[CT_OVERFLOW], n - start);
     }
 }
 
@@ -3396,7 +3419,7 @@ __global__ void __launch_bounds__(256) overflow_list_kernel(DevOut o, uint32_t n
 // rescue of the batch, on the same stream).  Results, path runs and second hits are written in place.
 int launch_overflow_rerun(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, const DevOut &o,
                           const SearchRes &R, void *stream, int sm_count) {
-    if (!o.ovf_list || !o.ovf_cap) return 0;
+    if (!o.ovf_list || !o.ovf_units || !o.ovf_cap) return 0;
     KArgs A = make_kargs(ix, P, b, pr, o, R);
     A.unit_count = 0xFFFFFFFFu;   // listed launch
     int e;

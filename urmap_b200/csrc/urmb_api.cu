@@ -199,6 +199,15 @@ struct urmb_ctx {
     uint32_t *seqx = nullptr;
     uint32_t *seqc = nullptr;
     cudaStream_t compute = nullptr;
+    // Second compute lane (URMB_LANES=2; off by default): consecutive launches alternate between two streams, each with its
+    // own per-warp scratch and pool of saved mate states, so that the kernels of two batches can interleave.  Measured:
+    // the persistent grids leave no room for each other, 26.6 M against 29.1 M reads/s on the paired-end workload
+    // (profiles/r03p), so one lane stays the default.
+    cudaStream_t compute2 = nullptr;
+    WarpScratch *scratch2 = nullptr;
+    MateSave *pool2 = nullptr;
+    cudaEvent_t ev_lane = nullptr;
+    int lanes = 1, lane_next = 0;
     cudaStream_t rescue = nullptr;            // low-priority side stream of the mate-rescue kernel
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
     bool rescue_inline = false;               // URMB_RESCUE_INLINE: run the rescue kernel on the compute stream
@@ -289,6 +298,9 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->compute, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->compute2, cudaStreamNonBlocking, prio_hi));
+    CK(cudaEventCreateWithFlags(&c->ev_lane, cudaEventDisableTiming));
+    if (const char *f = getenv("URMB_LANES")) c->lanes = atoi(f) == 2 ? 2 : 1;
     CK(cudaStreamCreateWithPriority(&c->rescue, cudaStreamNonBlocking, prio_lo));
     c->prio_lo = prio_lo;
     for (auto &ev : c->ev_mark) CK(cudaEventCreate(&ev));
@@ -302,6 +314,7 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     if (const char *f = getenv("URMB_RESCUE_INLINE")) c->rescue_inline = atoi(f) != 0;
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
     CK(cudaMalloc(&c->scratch, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
+    if (c->lanes == 2) CK(cudaMalloc(&c->scratch2, sizeof(WarpScratch) * (size_t)c->n_scratch_warps));
     c->no_rerun = getenv("URMB_NO_RERUN") != nullptr;
     for (auto &s : c->slots) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
@@ -341,6 +354,10 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &s : c->slots) free_slot(s);
     if (c->compute) cudaStreamDestroy(c->compute);
+    if (c->compute2) cudaStreamDestroy(c->compute2);
+    if (c->ev_lane) cudaEventDestroy(c->ev_lane);
+    cudaFree(c->scratch2);
+    cudaFree(c->pool2);
     if (c->rescue) cudaStreamDestroy(c->rescue);
     for (auto ev : c->ev_mark) if (ev) cudaEventDestroy(ev);
     cudaFree(c->scratch);
@@ -631,10 +648,13 @@ extern "C" int urmb_reserve(urmb_ctx *c, uint32_t n_units, uint32_t max_read_len
     const size_t want = std::min<size_t>(std::max<size_t>(units, 1), c->chunk_pairs);
     if (want > c->pool_pairs) {
         CK(cudaStreamSynchronize(c->compute));
+        CK(cudaStreamSynchronize(c->compute2));
         cudaFree(c->pool);
-        c->pool = nullptr;
+        cudaFree(c->pool2);
+        c->pool = c->pool2 = nullptr;
         c->pool_pairs = 0;
         CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
+        if (c->lanes == 2) CK(cudaMalloc(&c->pool2, sizeof(MateSave) * 2 * want));
         c->pool_pairs = want;
     }
     for (auto &s : c->slots)
@@ -738,10 +758,13 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
         const size_t want = std::min<size_t>(std::max<size_t>(units, 1), c->chunk_pairs);
         if (want > c->pool_pairs) {
             CK(cudaStreamSynchronize(c->compute));
+            CK(cudaStreamSynchronize(c->compute2));
             cudaFree(c->pool);
-            c->pool = nullptr;
+            cudaFree(c->pool2);
+            c->pool = c->pool2 = nullptr;
             c->pool_pairs = 0;
             CK(cudaMalloc(&c->pool, sizeof(MateSave) * 2 * want));
+            if (c->lanes == 2) CK(cudaMalloc(&c->pool2, sizeof(MateSave) * 2 * want));
             c->pool_pairs = want;
         }
     }
@@ -801,49 +824,52 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     if (!s.staged) return fail(c, URMB_E_ARG, "slot not staged");
     CK(cudaSetDevice(c->device));
     cudaStream_t side = s.side;
-    CK(cudaStreamWaitEvent(c->compute, s.ev_h2d, 0));
-    if (s.launched) CK(cudaStreamWaitEvent(c->compute, s.ev_rescue, 0));   // an earlier launch of this very slot
-    CK(cudaMemsetAsync(s.d_counters, 0, CT_COUNT * sizeof(uint32_t), c->compute));
-    CK(cudaEventRecord(s.ev_k0, c->compute));
+    const int lane = (c->lanes == 2 && !c->rescue_inline) ? c->lane_next : 0;   // compute lane of this launch
+    if (c->lanes == 2) c->lane_next ^= 1;
+    cudaStream_t cs = lane ? c->compute2 : c->compute;
+    CK(cudaStreamWaitEvent(cs, s.ev_h2d, 0));
+    if (s.launched) CK(cudaStreamWaitEvent(cs, s.ev_rescue, 0));   // an earlier launch of this very slot
+    CK(cudaMemsetAsync(s.d_counters, 0, CT_COUNT * sizeof(uint32_t), cs));
+    CK(cudaEventRecord(s.ev_k0, cs));
     s.nkev = 0;
     bool rescued = false;
     if (s.batch.n_reads) {
         DevProbe pr{s.d_tally, s.d_pos, s.d_ext, s.d_view, view_stride_for(s.batch.seqcap)};
         urmb_second *second = (c->params.want_second && s.batch.paired) ? s.d_second : nullptr;
-        if (second) CK(cudaMemsetAsync(second, 0, (size_t)s.batch.n_reads * sizeof(urmb_second), c->compute));
+        if (second) CK(cudaMemsetAsync(second, 0, (size_t)s.batch.n_reads * sizeof(urmb_second), cs));
         const bool use_pool = s.batch.paired && s.rescue_cap && s.rpool;
         DevOut o{s.d_res, s.d_runs, (uint32_t)std::min<size_t>(s.d_runs_cap, 0xFFFFFFFFu), s.d_counters, s.d_todo, s.d_rescue, second,
                  use_pool ? s.rpool : nullptr, use_pool ? (uint32_t)s.rescue_cap : 0u,
                  {use_pool ? s.rq[0] : nullptr, use_pool ? s.rq[1] : nullptr},
                  s.big_scratch ? s.d_ovf : nullptr, s.big_scratch ? kOvfCap : 0u, s.big_scratch ? s.d_ovf_units : nullptr};
-        SearchRes R{c->scratch, c->n_scratch_warps, c->pool, (uint32_t)c->pool_pairs};
+        SearchRes R{lane ? c->scratch2 : c->scratch, c->n_scratch_warps, lane ? c->pool2 : c->pool, (uint32_t)c->pool_pairs};
         DevParams P = c->P;
-        TraceCtx tc{&s, c->compute, cudaSuccess};
+        TraceCtx tc{&s, cs, cudaSuccess};
         LaunchTrace tr{trace_mark, &tc};
         trace_mark(&tc, 0, 0);
-        int e = launch_probe(c->ix, P, s.batch, pr, c->compute, c->sm_count);
+        int e = launch_probe(c->ix, P, s.batch, pr, cs, c->sm_count);
         trace_mark(&tc, 0, 1);
         if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
-        CK(cudaEventRecord(s.ev_k1, c->compute));
-        e = launch_search(c->ix, P, s.batch, pr, o, R, c->compute, c->sm_count, nullptr, &tr);
+        CK(cudaEventRecord(s.ev_k1, cs));
+        e = launch_search(c->ix, P, s.batch, pr, o, R, cs, c->sm_count, nullptr, &tr);
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("search launch: ") + cudaGetErrorString((cudaError_t)-e));
         c->launches += 1 + (uint64_t)e;
-        CK(cudaEventRecord(s.ev_k2, c->compute));
+        CK(cudaEventRecord(s.ev_k2, cs));
         // Mate rescue: few, long work items.  It runs on the low-priority side stream so that its tail overlaps the
         // kernels of the next batch instead of idling the GPU.
         SearchRes RR{s.rescue_scratch, c->n_rescue_warps, nullptr, 0};
-        cudaStream_t rs = c->rescue_inline ? c->compute : side;
+        cudaStream_t rs = c->rescue_inline ? cs : side;
         CK(cudaStreamWaitEvent(rs, s.ev_k2, 0));
         tc.stream = rs;
         e = launch_rescue(c->ix, P, s.batch, pr, o, c->rescue_inline ? R : RR, rs, c->sm_count, &tr);
-        if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, c->compute));
+        if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, cs));
         if (e < 0) return fail(c, URMB_E_CUDA, std::string("rescue launch: ") + cudaGetErrorString((cudaError_t)-e));
         c->launches += (uint64_t)e;
         if (s.big_scratch) {
             // Reads over a per-mate capacity of the fast kernels are searched again by the big-capacity build on the slot's
             // high-priority stream: a first pass as soon as the search kernels are done (beside the mate rescue), a second
             // one after the mate rescue for the reads it added to the list (usually none).
-            cudaStream_t bs = c->rescue_inline ? c->compute : s.big;
+            cudaStream_t bs = c->rescue_inline ? cs : s.big;
             for (int pass = 0; pass < 2; ++pass) {
                 if (!c->rescue_inline) {
                     if (pass == 0) CK(cudaStreamWaitEvent(bs, s.ev_k2, 0));
@@ -856,7 +882,7 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
                 if (e < 0) return fail(c, URMB_E_CUDA, std::string("big-capacity rerun launch: ") + cudaGetErrorString((cudaError_t)-e));
                 c->launches += (uint64_t)e;
             }
-            if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, c->compute));
+            if (c->rescue_inline) CK(cudaEventRecord(s.ev_k2, cs));
             else {   // the batch is done when both streams are
                 CK(cudaEventRecord(s.ev_big, bs));
                 CK(cudaStreamWaitEvent(rs, s.ev_big, 0));
@@ -866,8 +892,8 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         rescued = true;   // the side stream has work of this batch (or, inline, waits for the re-recorded ev_k2 below)
         if (c->rescue_inline) rescued = false;
     } else {
-        CK(cudaEventRecord(s.ev_k1, c->compute));
-        CK(cudaEventRecord(s.ev_k2, c->compute));
+        CK(cudaEventRecord(s.ev_k1, cs));
+        CK(cudaEventRecord(s.ev_k2, cs));
     }
     if (!rescued) CK(cudaStreamWaitEvent(side, s.ev_k2, 0));
     CK(cudaEventRecord(s.ev_rescue, side));
@@ -881,7 +907,10 @@ extern "C" int urmb_mark(urmb_ctx *c, int which) {
     CK(cudaSetDevice(c->device));
     for (auto &s : c->slots)   // a mark comes after the side-stream work of every batch launched so far
         if (s.launched) CK(cudaStreamWaitEvent(c->compute, s.ev_rescue, 0));
+    CK(cudaEventRecord(c->ev_lane, c->compute2));   // ... and after the second compute lane; which then waits for the mark
+    CK(cudaStreamWaitEvent(c->compute, c->ev_lane, 0));
     CK(cudaEventRecord(c->ev_mark[which], c->compute));
+    CK(cudaStreamWaitEvent(c->compute2, c->ev_mark[which], 0));
     return URMB_OK;
 }
 

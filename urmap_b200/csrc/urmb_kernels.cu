@@ -3224,7 +3224,7 @@ __device__ __forceinline__ void rescue_dp_body(const KArgs &A, int round) {
 #define URMB_LB_ROWS 7
 #endif
 #ifndef URMB_LB_ALIGN
-#define URMB_LB_ALIGN 7
+#define URMB_LB_ALIGN 6
 #endif
 __global__ void __launch_bounds__(128, URMB_LB_PAIR) seed_kernel_se(const __grid_constant__ KArgs A) { search_body<0>(A); }
 __global__ void __launch_bounds__(128, URMB_LB_ALIGN) align_kernel_se3(const __grid_constant__ KArgs A) { stage_body<3>(A); }

@@ -86,6 +86,7 @@ inline unsigned atomicSub(unsigned *p, unsigned v) { unsigned o = *p; *p = o - v
 inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
 inline void __syncthreads() {}
 #define __shared__ static
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }

@@ -2164,11 +2164,14 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
     bool have_prev = false;
     uint32_t prev_diag = 0;
     const uint32_t lt = (1u << E.lane) - 1u;
+    // (27 k) % QWC without a division per visit: 27 k < 2^13 and QWC < 2^8, so floor(n / QWC) = (n * ceil(2^32 / QWC)) >> 32 exactly
+    const uint32_t qrec = QWC ? (uint32_t)((0x100000000ull + QWC - 1) / QWC) : 0u;
     for (uint32_t v0 = 0; v0 < 2 * QWC; v0 += 32) {
         const uint32_t v = v0 + E.lane, k = v >> 1;
         const int sgn = (int)(v & 1u);
         const bool valid = k < QWC;
-        const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0;
+        const uint32_t n27 = k * PRIME_STRIDE;
+        const uint32_t QPos = valid ? n27 - __umulhi(n27, qrec) * QWC : 0;
         const uint32_t T = valid ? m_tally(m, sgn, QPos) : 0u;
         const uint32_t Pz = valid ? m_pos(m, sgn, QPos) : 0u;
         const bool mine = (T & T_MY_BIT) != 0;          // invalid words carry T_FREE

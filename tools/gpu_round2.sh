@@ -10,6 +10,7 @@
 #   ncufull    one `ncu --set full` capture of every kernel class of one step (CSV exports made on the box)
 #   sanitize   compute-sanitizer memcheck + racecheck on the golden sets
 #   ab         per-kernel step times of the current build (tools/step_sweep.py)
+#   cliscale   BASELINE's full size through the drop-in next to the reference binary (tools/cli_scale.py, 10 M pairs)
 TAG=${1:-run}; shift
 WHAT=${*:-tests bench}
 OUT=gpurun_out/$TAG
@@ -48,8 +49,10 @@ launches)
 ncufull)
   # 250 k pairs per step = one chunk: every step launches each kernel class once, in a fixed order; skip the warm-up
   # steps and capture one launch of every class (finish_kernel is excluded: 0.3 ms)
-  NK=${NCU_KERNELS:-'probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue'}
-  NSKIP=${NCU_SKIP:-24}
+  # per step and in launch order: probe, pair, align_a, rows, rows_long, align_c, then six rounds of (rescue_scan, rescue_dp):
+  # 18 matching launches; three warm-up steps are skipped, then the six main kernels and the first rescue round are captured
+  NK=${NCU_KERNELS:-'probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue_scan_kernel|rescue_dp_kernel'}
+  NSKIP=${NCU_SKIP:-54}
   NCOUNT=${NCU_COUNT:-8}
   timeout 1700 ncu --set full --clock-control none --import-source on -k regex:"$NK" -s $NSKIP -c $NCOUNT -f -o $OUT/full \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs --pairs-per-step 250000 > $OUT/ncu_full.log 2>&1
@@ -61,14 +64,17 @@ ncufull)
 sanitize)
   timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_memcheck_smoke.log 2>&1
   echo "memcheck smoke exit $?"; tail -4 $OUT/sanitizer_memcheck_smoke.log
-  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "golden" \
+  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "golden or big_capacity or dense_index" \
       > $OUT/sanitizer_memcheck_golden.log 2>&1
   echo "memcheck golden exit $?"; tail -4 $OUT/sanitizer_memcheck_golden.log
-  timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_racecheck_smoke.log 2>&1
+  URMB_FLAGS=256 timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_racecheck_smoke.log 2>&1
   echo "racecheck smoke exit $?"; tail -4 $OUT/sanitizer_racecheck_smoke.log
   timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "golden" \
       > $OUT/sanitizer_racecheck_golden.log 2>&1
   echo "racecheck golden exit $?"; tail -4 $OUT/sanitizer_racecheck_golden.log ;;
+cliscale)
+  timeout 1700 python tools/cli_scale.py --pairs ${CLI_PAIRS:-10000000} --tabbedout > $OUT/cli_scale.json 2> $OUT/cli_scale.log; echo "cli_scale exit $?"
+  tail -3 $OUT/cli_scale.log; head -c 1500 $OUT/cli_scale.json; echo ;;
 ab)
   timeout 900 python tools/step_sweep.py > $OUT/step_sweep.log 2>&1; echo "step_sweep exit $?"; tail -12 $OUT/step_sweep.log ;;
 esac

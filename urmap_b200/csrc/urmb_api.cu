@@ -236,7 +236,7 @@ struct urmb_ctx {
     uint64_t rerun_total = 0;      // reads mapped again by the big-capacity build
     uint32_t force_rerun = 0;      // URMB_FORCE_RERUN=N (tests): every N-th unit is mapped again by the big-capacity build
     bool rescue_legacy = false;    // URMB_RESCUE_LEGACY: no rescue pool, every rescued pair is searched again from scratch
-    uint32_t chunk_pairs = 524288; // URMB_CHUNK_PAIRS (step time at 1 M pairs: 92.9 / 86.0 / 82.5 / 82.1 ms for 128k / 256k / 512k / 1M)
+    uint32_t chunk_pairs = 1048576; // URMB_CHUNK_PAIRS (step time at 1 M pairs: 65.5 / 61.0 / 60.3 ms for 256k / 512k / 1M, profiles/r03s)
     Slot slots[URMB_SLOTS];
     uint64_t launches = 0;
     uint64_t overflow_total = 0;   // reads that exceeded a per-read capacity, over all finished batches

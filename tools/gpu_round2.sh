@@ -54,13 +54,14 @@ ncufull)
   NK=${NCU_KERNELS:-'probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue_scan_kernel|rescue_dp_kernel'}
   NSKIP=${NCU_SKIP:-54}
   NCOUNT=${NCU_COUNT:-8}
-  timeout 1700 ncu --set full --clock-control none --import-source on -k regex:"$NK" -s $NSKIP -c $NCOUNT -f -o $OUT/full \
-      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs --pairs-per-step 250000 > $OUT/ncu_full.log 2>&1
+  timeout 1700 ncu --set full --clock-control none --import-source on -k regex:"$NK" -s $NSKIP -c $NCOUNT -f -o $OUT/${NCU_OUT:-full} \
+      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs --pairs-per-step ${NCU_PAIRS:-250000} $NCU_BENCH_ARGS > $OUT/ncu_full.log 2>&1
   echo "ncu full exit $?"
-  ncu -i $OUT/full.ncu-rep --page raw --csv > $OUT/full_raw.csv 2>/dev/null
-  ncu -i $OUT/full.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null | gzip -9 > $OUT/full_src.csv.gz
-  ls -la $OUT/full.ncu-rep
-  if [ $(stat -c %s $OUT/full.ncu-rep) -gt 45000000 ]; then rm -f $OUT/full.ncu-rep; echo "report dropped (too large), CSV exports kept"; fi ;;
+  F=${NCU_OUT:-full}
+  ncu -i $OUT/$F.ncu-rep --page raw --csv > $OUT/${F}_raw.csv 2>/dev/null
+  ncu -i $OUT/$F.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null | gzip -9 > $OUT/${F}_src.csv.gz
+  ls -la $OUT/$F.ncu-rep
+  rm -f $OUT/$F.ncu-rep ;;   # the CSV exports are what is read afterwards; the report itself would eat the 64 MiB return budget
 sanitize)
   timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_memcheck_smoke.log 2>&1
   echo "memcheck smoke exit $?"; tail -4 $OUT/sanitizer_memcheck_smoke.log

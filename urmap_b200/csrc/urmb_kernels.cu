@@ -768,6 +768,7 @@ __device__ __forceinline__ bool seed_dead(const Mate &m, int i) { return (m.sd_d
 // a no-op from the start.
 __device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m, bool fetch_db) {
     __syncwarp();
+#pragma unroll 1
     for (int base = 0; base < m.nSeeds; base += 32) {
         const int i = base + E.lane;
         uint32_t x = EXT_NONE;
@@ -789,6 +790,7 @@ __device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m, bool fetch_d
 // OverlapsHit (state1.cpp:230, strand ignored), every seed over the new penalty bound fails the bound.
 __device__ __noinline__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo) {
     const uint32_t key = HitDBLo >> 6;
+#pragma unroll 1
     for (int base = 0; base < m.nSeeds; base += 32) {
         const int i = base + E.lane;
         bool d = false;
@@ -1886,6 +1888,7 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
     uint16_t *flat = reinterpret_cast<uint16_t *>(E.ws->tb + 2 * CAP);   // [2 * CAP] entry | which << 15
     const uint32_t lt = (1u << E.lane) - 1u;
     int total = 0;
+#pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += 32) {   // pass 1
         const int i = i0 + E.lane;
         const bool valid = i < n;
@@ -1911,6 +1914,7 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
         total += __popc(b1);
     }
     __syncwarp();
+#pragma unroll 1
     for (int f0 = 0; f0 < total; f0 += 32) {   // pass 2
         const int f = f0 + E.lane;
         if (f < total) {
@@ -1921,6 +1925,7 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
         }
     }
     __syncwarp();
+#pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += 32) {   // pass 3; a block of 32 entries may straddle the two lists
         const int i = i0 + E.lane;
         const bool valid = i < n;
@@ -1991,6 +1996,7 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_
     uint32_t *fpos = reinterpret_cast<uint32_t *>(E.ws->rowD);    // flat candidate positions (<= 1024)
     uint8_t *fq = E.ws->tb;                                       // flat candidate QPos
     const int n = n0 + n1;   // the plus list, then the minus list (one may be empty)
+#pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + E.lane;
         const bool valid = i < n;
@@ -2013,6 +2019,7 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_
             fq[off + k] = (uint8_t)QPos;
         }
         __syncwarp();
+#pragma unroll 1
         for (uint32_t f0 = 0; f0 < total; f0 += 32) {
             const uint32_t f = f0 + E.lane;
             uint32_t x = EXT_NONE, q = 0, pz = 0;
@@ -2063,6 +2070,7 @@ __device__ __noinline__ bool se_phase12(const Env &E, Mate &m) {
     const uint32_t n1 = (QWC + W - 1) / W;          // phase-1 QPos count
     const uint32_t nvis = 2 * QWC;
     m.nSeeds = 0;
+#pragma unroll 1
     for (uint32_t v0 = 0; v0 < nvis; v0 += 32) {
         const uint32_t v = v0 + E.lane;
         uint32_t q = 0;
@@ -2108,10 +2116,12 @@ __device__ __noinline__ bool se_phase4(const Env &E, Mate &m) {
     const int QL = (int)m.QL;
     const uint32_t QWC = m.QWC;
     int nls[2];
+#pragma unroll 1
     for (int s = 0; s < 2; ++s) {
         // the owned non-BOTH1 slots of this strand in QPos order (search1m6.cpp:170-203), then rows <= 2 / deferral
         uint8_t *lst = m.g->todo[s];
         int nl = 0;
+#pragma unroll 1
         for (uint32_t q0 = 0; q0 < QWC; q0 += 32) {
             const uint32_t q = q0 + E.lane;
             const uint32_t T = (q < QWC) ? m_tally(m, s, q) : 0;
@@ -2166,6 +2176,7 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
     const uint32_t lt = (1u << E.lane) - 1u;
     // (27 k) % QWC without a division per visit: 27 k < 2^13 and QWC < 2^8, so floor(n / QWC) = (n * ceil(2^32 / QWC)) >> 32 exactly
     const uint32_t qrec = QWC ? (uint32_t)((0x100000000ull + QWC - 1) / QWC) : 0u;
+#pragma unroll 1
     for (uint32_t v0 = 0; v0 < 2 * QWC; v0 += 32) {
         const uint32_t v = v0 + E.lane, k = v >> 1;
         const int sgn = (int)(v & 1u);
@@ -2541,6 +2552,7 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairSta
     //       once it is known to return <= 0 without side effects the remaining partners are no-ops;
     //   (b) R seed t against F seeds [0, min(t+1, NF)): partners whose own-strand memo is dead are no-ops.
     const int NF = F.nSeeds, NR = R.nSeeds;
+#pragma unroll 1
     for (int t = 0; t < max(NF, NR); ++t) {
         if (t < NF && !seed_dead(F, t)) {
             const int nR = min(t, NR);

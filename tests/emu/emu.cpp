@@ -206,15 +206,15 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
 static void emu_dp_kernel(Env E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB, bool Left, bool Right, float *score,
                           int *nrev, int *ovf) {
     URMB_DYN_SMEM(smem);
-    E.lane = (int)(threadIdx.x & 31);
+    E.lane_ = (int)(threadIdx.x & 31);
     E.s_win = smem;
     E.s_tb = smem + kMaxLen + 64;
-    for (uint32_t k = E.lane; k < LB && k < (uint32_t)kMaxLen + 64; k += 32) E.s_win[k] = B[k];
+    for (uint32_t k = E.lane_; k < LB && k < (uint32_t)kMaxLen + 64; k += 32) E.s_win[k] = B[k];
     __syncwarp();
     int n = 0, o = 0;
     const float sc = (LB > 512) ? (getenv("EMU_OLD_FULL") ? viterbi_warp<true>(E, A, LA, B, LB, Left, Right, n, o) : viterbi_full(E, A, LA, B, LB, Left, Right, n, o))
                                 : flank_viterbi(E, A, LA, 0, LB, Left, Right, n, o);
-    if (E.lane == 0) { *score = sc; *nrev = n; *ovf = o; }
+    if (E.lane_ == 0) { *score = sc; *nrev = n; *ovf = o; }
 }
 extern "C" float emu_flank_dp(const urmb_params *p, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB, int left, int right,
                               char *path /* LA + LB + 1 */, int *ovf) {

@@ -27,6 +27,9 @@
 namespace URMB_NS {
 
 #define FULL 0xffffffffu
+// lane of the calling thread: from the special register, not from Env (every out-of-line function would otherwise start
+// with a load of Env::lane from local memory)
+#define URMB_LANE ((int)(threadIdx.x & 31u))
 
 // Kernel launch / dynamic shared memory spelled through macros so that tests/emu can compile this very
 // file as plain C++ (a lock-step warp emulator used for debugging only; never part of the product).
@@ -564,7 +567,7 @@ struct Env {
     uint8_t *s_win;     // flank-DP genome window (shared)
     uint32_t tb_stride;
     uint32_t tb_rows;
-    int lane;
+    int lane_;          // (kept for the emulator harness; the kernels read the lane from threadIdx: no load from the stack)
 };
 
 struct Mate {
@@ -616,7 +619,7 @@ __device__ __noinline__ void runs_append(uint16_t *runs, int &n, uint32_t op, ui
 __device__ bool overlaps_hit(const Env &E, const Mate &m, uint32_t DBStartPos) {  // state1.cpp:230 (strand ignored)
     const uint32_t key = DBStartPos >> 6;
     for (int base = 0; base < m.HitCount; base += 32) {
-        int h = base + E.lane;
+        int h = base + URMB_LANE;
         bool f = (h < m.HitCount) && ((m.g->hit_pos[h] >> 6) == key);
         if (__any_sync(FULL, f)) return true;
     }
@@ -635,7 +638,7 @@ __device__ __forceinline__ bool overlaps_hit_lane(const Mate &m, uint32_t DBStar
 __device__ int overlaps_hsp(const Env &E, const Mate &m, uint32_t StartPosQ, uint32_t StartPosDB) {  // state1.cpp:241
     const int64_t diag = (int64_t)StartPosDB - (int64_t)StartPosQ;
     for (int base = 0; base < m.HSPCount; base += 32) {
-        int h = base + E.lane;
+        int h = base + URMB_LANE;
         bool f = (h < m.HSPCount) && ((int64_t)m.g->hsp_dbstart[h] - (int64_t)m.g->hsp_qstart[h] == diag);
         uint32_t bal = __ballot_sync(FULL, f);
         if (bal) return base + __ffs(bal) - 1;
@@ -655,14 +658,14 @@ __device__ __noinline__ int add_hit(const Env &E, Mate &m, uint32_t StartPosDB, 
     if (idx >= kHitCap) { m.overflow |= 1; return -1; }
     if (nruns > kRunCap) { m.overflow |= 2; nruns = kRunCap; }
     if (m.nRuns + nruns > kRunPool) { m.overflow |= 4; nruns = 0; }
-    if (E.lane == 0) {
+    if (URMB_LANE == 0) {
         m.g->hit_pos[idx] = StartPosDB;
         m.g->hit_score[idx] = (int16_t)Score;
         m.g->hit_plus[idx] = Plus ? 1 : 0;
         m.g->hit_nruns[idx] = (uint8_t)nruns;
         m.g->hit_roff[idx] = (uint16_t)m.nRuns;
     }
-    for (int i = E.lane; i < nruns; i += 32) m.g->runs_pool[m.nRuns + i] = runs[i];
+    for (int i = URMB_LANE; i < nruns; i += 32) m.g->runs_pool[m.nRuns + i] = runs[i];
     __syncwarp();
     if (Score > m.Best) {
         m.Second = m.Best;
@@ -682,7 +685,7 @@ __device__ __noinline__ int add_hit(const Env &E, Mate &m, uint32_t StartPosDB, 
 __device__ __forceinline__ void hsp_store(const Env &E, Mate &m, int k, uint32_t qs, uint32_t dbs, bool Plus,
                                           uint32_t len, int Score) {
     __syncwarp();   // callers read the old record before it is replaced
-    if (E.lane == 0) {
+    if (URMB_LANE == 0) {
         m.g->hsp_qstart[k] = (uint16_t)qs;
         m.g->hsp_dbstart[k] = dbs;
         m.g->hsp_len[k] = (uint16_t)len;
@@ -770,7 +773,7 @@ __device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m, bool fetch_d
     __syncwarp();
 #pragma unroll 1
     for (int base = 0; base < m.nSeeds; base += 32) {
-        const int i = base + E.lane;
+        const int i = base + URMB_LANE;
         uint32_t x = EXT_NONE;
         if (i < m.nSeeds) {
             const uint32_t qs = m.sd_qs[i];
@@ -781,7 +784,7 @@ __device__ __noinline__ void seeds_init_dead(const Env &E, Mate &m, bool fetch_d
         }
         const bool d = (i >= m.nSeeds) || ext_is_noop(E, x, (int)m.QL, m.MaxPenalty);
         const uint32_t w = __ballot_sync(FULL, d);
-        if (E.lane == 0) m.sd_dead[base >> 5] = w;
+        if (URMB_LANE == 0) m.sd_dead[base >> 5] = w;
     }
     __syncwarp();
 }
@@ -792,14 +795,14 @@ __device__ __noinline__ void seeds_kill(const Env &E, Mate &m, uint32_t HitDBLo)
     const uint32_t key = HitDBLo >> 6;
 #pragma unroll 1
     for (int base = 0; base < m.nSeeds; base += 32) {
-        const int i = base + E.lane;
+        const int i = base + URMB_LANE;
         bool d = false;
         if (i < m.nSeeds) {
             const uint32_t x = m.sd_ext[i];
             d = (((m.sd_db[i] - (m.sd_qs[i] & 0x7FFFu)) >> 6) == key) || (ext_nmis(x) * -E.P.MM > m.MaxPenalty);
         }
         const uint32_t w = __ballot_sync(FULL, d);
-        if (E.lane == 0 && w) m.sd_dead[base >> 5] |= w;
+        if (URMB_LANE == 0 && w) m.sd_dead[base >> 5] |= w;
     }
     __syncwarp();
 }
@@ -813,7 +816,7 @@ __device__ __noinline__ int apply_seed(const Env &E, Mate &m, int i) {
     __syncwarp();
     if (stored) seeds_kill(E, m, db - (qs & 0x7FFFu));
     else if (r <= 0) {
-        if (E.lane == 0) m.sd_dead[i >> 5] |= 1u << (i & 31);
+        if (URMB_LANE == 0) m.sd_dead[i >> 5] |= 1u << (i & 31);
         __syncwarp();
     }
     return r;
@@ -879,7 +882,7 @@ struct TBStore {
 template <bool BIG>
 __device__ __noinline__ float viterbi_warp(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB,
                                            bool Left, bool Right, int &n_rev, int &ovf) {
-    const int lane = E.lane;
+    const int lane = URMB_LANE;
     uint16_t *rev = E.ws->runs_a;
     n_rev = 0;
     const float GO = (float)E.P.GO, GE = (float)E.P.GE, MMs = (float)E.P.MM;
@@ -1067,7 +1070,7 @@ __device__ __noinline__ float viterbi_warp(const Env &E, const uint8_t *A, uint3
 #ifdef URMB_BAND_F32
 __device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB,
                                            bool Left, bool Right, int &n_rev, int &ovf) {
-    const int lane = E.lane;
+    const int lane = URMB_LANE;
     uint16_t *rev = E.ws->runs_a;
     n_rev = 0;
     const float GO = (float)E.P.GO, GE = (float)E.P.GE, MMs = (float)E.P.MM;
@@ -1246,7 +1249,7 @@ __device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint3
 // (32 cells of a diagonal / column / row per step) instead of one cell at a time.
 __device__ __noinline__ float viterbi_band(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *B, uint32_t LB,
                                            bool Left, bool Right, int &n_rev, int &ovf) {
-    const int lane = E.lane;
+    const int lane = URMB_LANE;
     uint16_t *rev = E.ws->runs_a;
     n_rev = 0;
     constexpr int NEG = -(1 << 28);
@@ -1474,7 +1477,7 @@ __device__ __forceinline__ uint32_t full_tb_get(const FullTB &T, int i, int j) {
 
 __device__ __noinline__ float viterbi_full(const Env &E, const uint8_t *A, uint32_t LA, const uint8_t *Bg, uint32_t LB, bool Left,
                                            bool Right, int &n_rev, int &ovf) {
-    const int lane = E.lane;
+    const int lane = URMB_LANE;
     uint16_t *rev = E.ws->runs_a;
     n_rev = 0;
     if (LA == 0 || LB == 0) return viterbi_warp<true>(E, A, LA, Bg, LB, Left, Right, n_rev, ovf);   // degenerate (never from Scan)
@@ -1670,7 +1673,7 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
     const uint8_t fl = m.g->hsp_flags[HSPIndex];
     if (fl & 2) return -1;
     __syncwarp();   // all lanes have read the flags
-    if (E.lane == 0) m.g->hsp_flags[HSPIndex] = fl | 2;
+    if (URMB_LANE == 0) m.g->hsp_flags[HSPIndex] = fl | 2;
     __syncwarp();
     const uint32_t StartPosQ = m.g->hsp_qstart[HSPIndex], StartPosDB = m.g->hsp_dbstart[HSPIndex];
     const uint32_t HSPLength = m.g->hsp_len[HSPIndex];
@@ -1693,7 +1696,7 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
         if (LeftTL >= LeftTHi) return -1;
         const uint32_t LeftTLo = LeftTHi - LeftTL + 1;
         bool dash = false;
-        for (uint32_t k = E.lane; k < LeftTL; k += 32) {
+        for (uint32_t k = URMB_LANE; k < LeftTL; k += 32) {
             uint8_t c = __ldg(E.ix.seq + LeftTLo + k);
             E.s_win[k] = c;
             dash |= (c == '-');
@@ -1709,7 +1712,7 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
             LeftICount = rev[nrev - 1] >> 2;
             --nrev;
         }
-        for (int k = nrev - 1; k >= 0; --k) runs_append(path, np, rev[k] & 3u, rev[k] >> 2, pcap, ovf, E.lane);
+        for (int k = nrev - 1; k >= 0; --k) runs_append(path, np, rev[k] & 3u, rev[k] >> 2, pcap, ovf, URMB_LANE);
         CombinedTLo = LeftTLo + LeftICount;
         const int AllGapScore = E.P.GO + ((int)LeftQL - 1) * E.P.GE;
         if (AllGapScore > LeftScore) LeftScore = AllGapScore;
@@ -1717,7 +1720,7 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
         TotalPen += (int)LeftQL - LeftScore;
         if (TotalPen > m.MaxPenalty) return -1;
     }
-    runs_append(path, np, 0, HSPLength, pcap, ovf, E.lane);
+    runs_append(path, np, 0, HSPLength, pcap, ovf, URMB_LANE);
     const uint32_t RightQLo = StartPosQ + HSPLength;
     // The start of the alignment is known once the left flank is done.  AddHitX (state1.cpp:508-551) drops a hit whose
     // 64-base bucket is taken before it looks at anything else, and nothing below has another effect, so the right-flank
@@ -1732,7 +1735,7 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
         if (RightTHi < RightTLo) return -1;
         const uint32_t RightTL = RightTHi - RightTLo + 1;
         bool dash = false;
-        for (uint32_t k = E.lane; k < RightTL; k += 32) {
+        for (uint32_t k = URMB_LANE; k < RightTL; k += 32) {
             uint8_t c = __ldg(E.ix.seq + RightTLo + k);
             E.s_win[k] = c;
             dash |= (c == '-');
@@ -1749,8 +1752,8 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
             if (nrev == 1) keepI = 1;  // whole path is I's: one survives
             first = 1;
         }
-        for (int k = nrev - 1; k >= first; --k) runs_append(path, np, rev[k] & 3u, rev[k] >> 2, pcap, ovf, E.lane);
-        if (keepI) runs_append(path, np, 2, 1, pcap, ovf, E.lane);
+        for (int k = nrev - 1; k >= first; --k) runs_append(path, np, rev[k] & 3u, rev[k] >> 2, pcap, ovf, URMB_LANE);
+        if (keepI) runs_append(path, np, 2, 1, pcap, ovf, URMB_LANE);
         const int AllGapScore = E.P.GO + ((int)RightQL - 1) * E.P.GE;
         if (AllGapScore > RightScore) RightScore = AllGapScore;
         TotalScore += RightScore;
@@ -1806,7 +1809,7 @@ __device__ __noinline__ uint32_t get_row(const Env &E, uint64_t Slot, uint32_t T
     const uint64_t SC = E.ix.slot_count;
     for (;;) {
         if (K > 0) load_blob_s(E.ix.blob, Slot2, T, Pos);
-        if ((uint32_t)E.lane == K) mypos = Pos;
+        if ((uint32_t)URMB_LANE == K) mypos = Pos;
         ++K;
         if (K == E.ix.max_ix) return K;
         if (T == T_PLUS1 || T == T_BOTH1) return 1;
@@ -1817,7 +1820,7 @@ __device__ __noinline__ uint32_t get_row(const Env &E, uint64_t Slot, uint32_t T
             Slot2 = add_mod(SlotA, StepB, SC);
             uint32_t ta, pa;
             load_blob_s(E.ix.blob, SlotA, ta, pa);
-            if ((uint32_t)E.lane == K - 1) mypos = pa;
+            if ((uint32_t)URMB_LANE == K - 1) mypos = pa;
         } else {
             Slot2 = add_mod(Slot2, T & T_NEXT_MASK, SC);
         }
@@ -1886,11 +1889,11 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
     uint32_t *hx1 = hx0 + CAP;
     uint8_t *hq = E.ws->tb, *hn = E.ws->tb + CAP;               // [CAP] QPos, row length (3 = longer than 2)
     uint16_t *flat = reinterpret_cast<uint16_t *>(E.ws->tb + 2 * CAP);   // [2 * CAP] entry | which << 15
-    const uint32_t lt = (1u << E.lane) - 1u;
+    const uint32_t lt = (1u << URMB_LANE) - 1u;
     int total = 0;
 #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += 32) {   // pass 1
-        const int i = i0 + E.lane;
+        const int i = i0 + URMB_LANE;
         const bool valid = i < n;
         const int s = (i < n0) ? 0 : 1;
         const uint32_t QPos = valid ? (s ? list1[i - n0] : list0[i]) : 0u;
@@ -1916,7 +1919,7 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
     __syncwarp();
 #pragma unroll 1
     for (int f0 = 0; f0 < total; f0 += 32) {   // pass 2
-        const int f = f0 + E.lane;
+        const int f = f0 + URMB_LANE;
         if (f < total) {
             const uint32_t e = flat[f], i = e & 0x7FFFu;
             const uint32_t pz = (e & 0x8000u) ? hp1[i] : hp0[i];
@@ -1927,7 +1930,7 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
     __syncwarp();
 #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += 32) {   // pass 3; a block of 32 entries may straddle the two lists
-        const int i = i0 + E.lane;
+        const int i = i0 + URMB_LANE;
         const bool valid = i < n;
         const uint32_t QPos = valid ? hq[i] : 0u, rn = valid ? hn[i] : 0u;
         const uint32_t p0 = valid ? hp0[i] : 0u, p1 = valid ? hp1[i] : 0u;
@@ -1943,10 +1946,10 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
             const bool plus = i0 + b < n0;
             if (big >> b & 1u) {
                 if (plus) {
-                    if (E.lane == 0) def0[nd0] = (uint8_t)qb;
+                    if (URMB_LANE == 0) def0[nd0] = (uint8_t)qb;
                     ++nd0;
                 } else {
-                    if (E.lane == 0) def1[nd1] = (uint8_t)qb;
+                    if (URMB_LANE == 0) def1[nd1] = (uint8_t)qb;
                     ++nd1;
                 }
                 continue;
@@ -1998,16 +2001,16 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_
     const int n = n0 + n1;   // the plus list, then the minus list (one may be empty)
 #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + E.lane;
+        const int i = i0 + URMB_LANE;
         const bool valid = i < n;
         const int s = (i < n0) ? 0 : 1;
         const uint32_t QPos = valid ? (s ? list1[i - n0] : list0[i]) : 0u;
         uint32_t len = 0;
-        if (valid) len = row_walk_lane(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), stage + 32 * E.lane);
+        if (valid) len = row_walk_lane(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), stage + 32 * URMB_LANE);
         uint32_t off = len;   // exclusive prefix sum over lanes
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(FULL, off, d);
-            if (E.lane >= d) off += t;
+            if (URMB_LANE >= d) off += t;
         }
         const uint32_t total = __shfl_sync(FULL, off, 31);
         off -= len;
@@ -2015,13 +2018,13 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_
         const int lp = min(max(n0 - i0, 0), 32);   // lanes [0, lp) hold plus rows
         const uint32_t nplus = (lp >= 32) ? total : __shfl_sync(FULL, off, lp);
         for (uint32_t k = 0; k < len; ++k) {
-            fpos[off + k] = stage[32 * E.lane + k];
+            fpos[off + k] = stage[32 * URMB_LANE + k];
             fq[off + k] = (uint8_t)QPos;
         }
         __syncwarp();
 #pragma unroll 1
         for (uint32_t f0 = 0; f0 < total; f0 += 32) {
-            const uint32_t f = f0 + E.lane;
+            const uint32_t f = f0 + URMB_LANE;
             uint32_t x = EXT_NONE, q = 0, pz = 0;
             if (f < total) {
                 q = fq[f];
@@ -2072,7 +2075,7 @@ __device__ __noinline__ bool se_phase12(const Env &E, Mate &m) {
     m.nSeeds = 0;
 #pragma unroll 1
     for (uint32_t v0 = 0; v0 < nvis; v0 += 32) {
-        const uint32_t v = v0 + E.lane;
+        const uint32_t v = v0 + URMB_LANE;
         uint32_t q = 0;
         const int sgn = (int)(v & 1u);
         if (v < 2 * n1) q = (v >> 1) * W;
@@ -2082,7 +2085,7 @@ __device__ __noinline__ bool se_phase12(const Env &E, Mate &m) {
         }
         const bool c = (v < nvis) && (q < QWC) && (m_tally(m, sgn, q) == T_BOTH1);
         const uint32_t bal = __ballot_sync(FULL, c);
-        if (c) m.sd_qs[m.nSeeds + __popc(bal & ((1u << E.lane) - 1u))] = (uint16_t)(q | ((uint32_t)sgn << 15));
+        if (c) m.sd_qs[m.nSeeds + __popc(bal & ((1u << URMB_LANE) - 1u))] = (uint16_t)(q | ((uint32_t)sgn << 15));
         m.nSeeds += __popc(bal);
     }
     seeds_init_dead(E, m, true);
@@ -2123,11 +2126,11 @@ __device__ __noinline__ bool se_phase4(const Env &E, Mate &m) {
         int nl = 0;
 #pragma unroll 1
         for (uint32_t q0 = 0; q0 < QWC; q0 += 32) {
-            const uint32_t q = q0 + E.lane;
+            const uint32_t q = q0 + URMB_LANE;
             const uint32_t T = (q < QWC) ? m_tally(m, s, q) : 0;
             const bool cand = (T != T_FREE && T != T_BOTH1 && (T & T_MY_BIT));
             const uint32_t bal = __ballot_sync(FULL, cand);
-            if (cand) lst[nl + __popc(bal & ((1u << E.lane) - 1u))] = (uint8_t)q;
+            if (cand) lst[nl + __popc(bal & ((1u << URMB_LANE) - 1u))] = (uint8_t)q;
             nl += __popc(bal);
         }
         nls[s] = nl;
@@ -2173,12 +2176,12 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
     m.nPend[0] = m.nPend[1] = 0;
     bool have_prev = false;
     uint32_t prev_diag = 0;
-    const uint32_t lt = (1u << E.lane) - 1u;
+    const uint32_t lt = (1u << URMB_LANE) - 1u;
     // (27 k) % QWC without a division per visit: 27 k < 2^13 and QWC < 2^8, so floor(n / QWC) = (n * ceil(2^32 / QWC)) >> 32 exactly
     const uint32_t qrec = QWC ? (uint32_t)((0x100000000ull + QWC - 1) / QWC) : 0u;
 #pragma unroll 1
     for (uint32_t v0 = 0; v0 < 2 * QWC; v0 += 32) {
-        const uint32_t v = v0 + E.lane, k = v >> 1;
+        const uint32_t v = v0 + URMB_LANE, k = v >> 1;
         const int sgn = (int)(v & 1u);
         const bool valid = k < QWC;
         const uint32_t n27 = k * PRIME_STRIDE;
@@ -2195,7 +2198,7 @@ __device__ __noinline__ void build_seeds_pe(const Env &E, Mate &m) {
         const uint32_t pdiag = below ? pd : prev_diag;
         const bool ret = b1 && (!hasp || diag != pdiag);
         const uint32_t retmask = __ballot_sync(FULL, ret);
-        const bool plus_ret = sgn && ((retmask >> ((E.lane - 1) & 31)) & 1u);
+        const bool plus_ret = sgn && ((retmask >> ((URMB_LANE - 1) & 31)) & 1u);
         const bool pend = sgn ? (plus_ret ? (b1 && !ret) : (mine && !b1)) : (mine && !b1);
         const uint32_t pp = __ballot_sync(FULL, pend && !sgn), pm = __ballot_sync(FULL, pend && sgn);
         if (ret) {
@@ -2282,7 +2285,7 @@ __device__ __noinline__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, ui
     if (DBSegLength < W) return;
     const uint32_t nwords = DBSegLength - W + 1;
     for (uint32_t p0 = 0; p0 < nwords; p0 += 32) {
-        uint32_t p = p0 + E.lane;   // window word start
+        uint32_t p = p0 + URMB_LANE;   // window word start
         uint32_t hitmask = 0;
         if (p < nwords) {
             uint64_t word = 0;
@@ -2334,8 +2337,8 @@ __device__ __noinline__ void scan_mate_post(const Env &E, Mate &m, uint32_t DBPo
         // TrimRightIs on the already left-trimmed path: index 0 is never removed
         if (last >= 0 && (rev[0] & 3u) == 2u) first = (last == 0) ? 0 : 1;
         uint32_t keep1 = (last == 0 && (rev[0] & 3u) == 2u) ? 1 : 0;
-        if (keep1) runs_append(path, np, 2, 1, 3 * kRunCap, ovf, E.lane);
-        else for (int k = last; k >= first; --k) runs_append(path, np, rev[k] & 3u, rev[k] >> 2, 3 * kRunCap, ovf, E.lane);
+        if (keep1) runs_append(path, np, 2, 1, 3 * kRunCap, ovf, URMB_LANE);
+        else for (int k = last; k >= first; --k) runs_append(path, np, rev[k] & 3u, rev[k] >> 2, 3 * kRunCap, ovf, URMB_LANE);
         if (ovf) m.overflow |= 16;
         add_hit(E, m, DBPos + LeftICount, Plus, (int)Score, path, np);
     }
@@ -2369,7 +2372,7 @@ __device__ __noinline__ void find_pairs(const Env &E, const Mate &F, const Mate 
         const int64_t PosF = F.g->hit_pos[hf];
         const int PlusF = F.g->hit_plus[hf];
         for (int base = 0; base < R.HitCount; base += 32) {
-            int hr = base + E.lane;
+            int hr = base + URMB_LANE;
             bool ok = false;
             int ScoreR = 0;
             if (hr < R.HitCount) {
@@ -2488,7 +2491,7 @@ __device__ __noinline__ void adjust_pair(Mate &F, Mate &R, const PairState &ps) 
 // that never reach AdjustTopHitsAndMapqs with a second pair keep "no second hit".
 __device__ __forceinline__ void write_second(const Env &E, const Mate &F, const Mate &R, const PairState &ps, urmb_second *out,
                                              uint32_t u, uint32_t n_units) {
-    if (!out || ps.PairCount == 0 || ps.SecF < 0 || E.lane != 0) return;
+    if (!out || ps.PairCount == 0 || ps.SecF < 0 || URMB_LANE != 0) return;
     urmb_second a, b;
     a.db_pos = F.g->hit_pos[ps.SecF];
     a.score = F.g->hit_score[ps.SecF];
@@ -2560,7 +2563,7 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairSta
             const bool Plusf = (F.sd_qs[t] >> 15) == 0;
             bool gone = false;
             for (int base = 0; base < nR && !gone; base += 32) {
-                const int i = base + E.lane;
+                const int i = base + URMB_LANE;
                 int64_t d = (int64_t)dbf - (int64_t)((i < nR) ? R.sd_db[i] : 0u);
                 if (d < 0) d = -d;
                 uint32_t bal = __ballot_sync(FULL, (i < nR) && (d + QL2 <= MAX_TL));
@@ -2578,7 +2581,7 @@ __device__ __noinline__ bool search_pair(const Env &E, Mate &F, Mate &R, PairSta
             const uint32_t dbr = R.sd_db[t];
             const bool Plusr = (R.sd_qs[t] >> 15) == 0;
             for (int base = 0; base < nF; base += 32) {
-                const int i = base + E.lane;
+                const int i = base + URMB_LANE;
                 bool ok = false;
                 if (i < nF) {
                     int64_t d = (int64_t)F.sd_db[i] - (int64_t)dbr;
@@ -2651,11 +2654,11 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
         const uint32_t n = m.g->hit_nruns[t];
         if (n) {
             uint32_t off = 0;
-            if (E.lane == 0) off = atomicAdd(&o.counters[CT_RUNS], n);
+            if (URMB_LANE == 0) off = atomicAdd(&o.counters[CT_RUNS], n);
             off = __shfl_sync(FULL, off, 0);
             if (off + n <= o.runs_cap) {
                 const uint16_t *src = m.g->runs_pool + m.g->hit_roff[t];
-                for (uint32_t k = E.lane; k < n; k += 32) o.runs[off + k] = src[k];
+                for (uint32_t k = URMB_LANE; k < n; k += 32) o.runs[off + k] = src[k];
                 res.path_off = off;
                 res.path_runs = (uint16_t)n;
             } else {
@@ -2666,7 +2669,7 @@ __device__ __noinline__ void write_result(const Env &E, const Mate &m, const Dev
 #ifndef URMB_BIG
     if ((E.P.flags & 256u) && r % 5 == 0) res.flags |= 0x80;   // test hook (URMB_FLAGS bit 8): every fifth read takes the in-stream big-capacity rerun
 #endif
-    if (E.lane == 0) {
+    if (URMB_LANE == 0) {
         o.res[r] = res;
 #ifdef URMB_BIG
         atomicAdd(&o.counters[CT_DBG_HSPS + (m.HSPCount <= 256 ? 0 : m.HSPCount <= 512 ? 1 : m.HSPCount <= 1024 ? 2 : 3)], 1u);
@@ -2735,7 +2738,7 @@ __device__ __noinline__ void load_mate(const Env &E, Mate &m, const DevBatch &b,
         // next piece behind them: three dependent round trips to HBM instead of one after the offsets).
         static_assert(kReadViewBytes / 4 <= 64 && kMaxLen / 4 <= 64, "two rounds of 32 lanes per piece");
         const uint32_t *vw = reinterpret_cast<const uint32_t *>(pr.view + (size_t)r * pr.view_stride);
-        const uint32_t lane = (uint32_t)E.lane, nrc = b.seqcap / 4;
+        const uint32_t lane = (uint32_t)URMB_LANE, nrc = b.seqcap / 4;
         const uint32_t v0 = __ldg(vw + lane);
         const uint32_t v1 = (lane + 32 < kReadViewBytes / 4) ? __ldg(vw + lane + 32) : 0u;
         const uint32_t fl = __ldg(vw + kReadViewBytes / 4);
@@ -2800,7 +2803,7 @@ __device__ __noinline__ void save_mate(const Env &E, Mate &m, MateSave *dst) {
     const MateScratch *__restrict__ g = m.g;
     MateScratch *__restrict__ d = &dst->s;
     for (int i0 = 0; i0 < max(m.HitCount, m.HSPCount); i0 += 32) {
-        const int i = i0 + E.lane;
+        const int i = i0 + URMB_LANE;
         const bool a = i < m.HitCount, c = i < m.HSPCount;
         uint32_t hp = 0, hd = 0;
         int16_t hs = 0, xs = 0;
@@ -2811,17 +2814,17 @@ __device__ __noinline__ void save_mate(const Env &E, Mate &m, MateSave *dst) {
         if (a) { d->hit_pos[i] = hp; d->hit_score[i] = hs; d->hit_plus[i] = hl; d->hit_nruns[i] = hn; d->hit_roff[i] = hr; }
         if (c) { d->hsp_dbstart[i] = hd; d->hsp_qstart[i] = xq; d->hsp_len[i] = xl; d->hsp_score[i] = xs; d->hsp_flags[i] = xf; }
     }
-    for (int i = E.lane; i < m.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
+    for (int i = URMB_LANE; i < m.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
     if (!done)
         for (int i0 = 0; i0 < max(m.nPend[0], m.nPend[1]); i0 += 32) {
-            const int i = i0 + E.lane;
+            const int i = i0 + URMB_LANE;
             uint8_t p0 = 0, p1 = 0;
             if (i < m.nPend[0]) p0 = g->pend[0][i];
             if (i < m.nPend[1]) p1 = g->pend[1][i];
             if (i < m.nPend[0]) d->pend[0][i] = p0;
             if (i < m.nPend[1]) d->pend[1][i] = p1;
         }
-    if (E.lane == 0) {
+    if (URMB_LANE == 0) {
         MateHdr h;
         h.HitCount = m.HitCount; h.HSPCount = m.HSPCount; h.Top = m.Top; h.MaxPenalty = m.MaxPenalty;
         h.Best = m.Best; h.Second = m.Second; h.BestHSP = m.BestHSP; h.nRuns = m.nRuns;
@@ -2841,7 +2844,7 @@ __device__ __forceinline__ void hdr_to_mate(const MateHdr &h, Mate &m) {
 }
 __device__ __forceinline__ void mate_to_hdr(const Env &E, const Mate &m, MateSave *sv, bool done) {
     __syncwarp();
-    if (E.lane == 0) {
+    if (URMB_LANE == 0) {
         MateHdr h;
         h.HitCount = m.HitCount; h.HSPCount = m.HSPCount; h.Top = m.Top; h.MaxPenalty = m.MaxPenalty;
         h.Best = m.Best; h.Second = m.Second; h.BestHSP = m.BestHSP; h.nRuns = m.nRuns;
@@ -2873,7 +2876,7 @@ __device__ __noinline__ void copy_save(const Env &E, const MateSave *__restrict_
     const MateScratch *__restrict__ g = &src->s;
     MateScratch *__restrict__ d = &dst->s;
     for (int i0 = 0; i0 < max(h.HitCount, h.HSPCount); i0 += 32) {
-        const int i = i0 + E.lane;
+        const int i = i0 + URMB_LANE;
         if (i < h.HitCount) {
             d->hit_pos[i] = g->hit_pos[i]; d->hit_score[i] = g->hit_score[i]; d->hit_plus[i] = g->hit_plus[i];
             d->hit_nruns[i] = g->hit_nruns[i]; d->hit_roff[i] = g->hit_roff[i];
@@ -2883,8 +2886,8 @@ __device__ __noinline__ void copy_save(const Env &E, const MateSave *__restrict_
             d->hsp_score[i] = g->hsp_score[i]; d->hsp_flags[i] = g->hsp_flags[i];
         }
     }
-    for (int i = E.lane; i < h.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
-    if (E.lane == 0) dst->h = h;
+    for (int i = URMB_LANE; i < h.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
+    if (URMB_LANE == 0) dst->h = h;
     __syncwarp();
 }
 
@@ -2898,7 +2901,7 @@ __device__ __forceinline__ void make_env(Env &E, const DevIndex &ix, const DevPa
     E.s_tb = p8 + b.seqcap + 64;
     E.tb_stride = 4 * P.R + 6;
     E.tb_rows = pl.dp ? b.seqcap + 2 : 0;
-    E.lane = lane;
+    E.lane_ = lane;
 }
 
 struct KArgs {   // one parameter block for every search kernel
@@ -3068,7 +3071,7 @@ __device__ __forceinline__ void finish_body(const KArgs &A) {
     E.ws = A.scratch + gw;
     E.s_win = E.s_tb = nullptr;
     E.tb_stride = E.tb_rows = 0;
-    E.lane = lane;
+    E.lane_ = lane;
     const uint32_t n_work = A.o.counters[CT_TODO];
     if (gw == 0 && lane == 0) atomicAdd(&A.o.counters[CT_TODO_TOTAL], n_work);
     for (;;) {

@@ -128,6 +128,8 @@ static DevParams emu_make_params(const urmb_params &p) {  // same table as urmb_
 
 // Optional output of State2's second pair (-tabbedout): set before emu_map, n_reads entries, zero-filled here.
 static urmb_second *g_emu_second = nullptr;
+static uint32_t g_emu_first_look = 0;   // pairs the probe kernel's first look finished in the last emu_map call
+extern "C" uint32_t emu_first_look() { return g_emu_first_look; }
 extern "C" void emu_set_second(urmb_second *p) { g_emu_second = p; }
 
 // seqs/offs: n_reads+1 offsets; for paired input read n_units+i is the mate of read i.
@@ -169,7 +171,8 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     std::vector<uint32_t> pos((size_t)nreads * 2 * b.qcap);
     std::vector<uint32_t> ext((size_t)nreads * 2 * b.qcap);
     std::vector<uint8_t> view((size_t)nreads * view_stride_for(b.seqcap) + 64, 0xCD);
-    DevProbe pr{tally.data(), pos.data(), ext.data(), view.data(), view_stride_for(b.seqcap)};
+    std::vector<uint8_t> done(n_units + 1, 0xCD);
+    DevProbe pr{tally.data(), pos.data(), ext.data(), view.data(), view_stride_for(b.seqcap), paired ? done.data() : nullptr};
     uint32_t ct[CT_COUNT];
     memset(ct, 0, sizeof ct);
     std::vector<uint32_t> todo(n_units + 1), rescue(n_units + 1);
@@ -191,13 +194,14 @@ extern "C" int emu_map(const uint8_t *blob, const uint8_t *seq_padded, uint32_t 
     MateSave *pool = (MateSave *)malloc(sizeof(MateSave) * 2 * chunk);
     memset(pool, 0xEE, sizeof(MateSave) * 2 * chunk);
     SearchRes R{ws, nw, pool, chunk};
-    launch_probe(ix, P, b, pr, nullptr, 1);
+    launch_probe(ix, P, b, pr, nullptr, 1, &o);
     int nk = launch_search(ix, P, b, pr, o, R, nullptr, 1, nullptr, nullptr);
     if (nk >= 0) nk = launch_rescue(ix, P, b, pr, o, R, nullptr, 1, nullptr);
     free(ws);
     free(pool);
     free(rpool);
     memcpy(counters, ct, 32);
+    g_emu_first_look = ct[CT_FIRST_LOOK];
     return nk < 0 ? nk : 0;
 }
 

@@ -636,7 +636,7 @@ extern "C" int urmb_reserve(urmb_ctx *c, uint32_t n_units, uint32_t max_read_len
             CK(cudaMalloc(&s.d_ext, probe_need * 4));
             s.d_probe_cap = probe_need;
         }
-        if ((rc = grow_dev(c, s.d_view, s.d_view_cap, nreads * view_stride_for(seqcap) + 64))) return rc;
+        if ((rc = grow_dev(c, s.d_view, s.d_view_cap, nreads * view_stride_for(seqcap) + 64 + n))) return rc;   // + the pairs' first-look flags
         if ((rc = grow_dev(c, s.d_res, s.d_res_cap, nreads + 1))) return rc;
         if ((rc = grow_dev(c, s.d_todo, s.d_todo_cap, n + 1))) return rc;
         if ((rc = grow_dev(c, s.d_rescue, s.d_rescue_cap, n + 1))) return rc;
@@ -748,7 +748,7 @@ extern "C" int urmb_upload(urmb_ctx *c, int si, const urmb_batch *r1, const urmb
         CK(cudaMalloc(&s.d_ext, ncap * 4));
         s.d_probe_cap = ncap;
     }
-    if ((rc = grow_dev(c, s.d_view, s.d_view_cap, (size_t)nreads * view_stride_for(b.seqcap) + 64))) return rc;
+    if ((rc = grow_dev(c, s.d_view, s.d_view_cap, (size_t)nreads * view_stride_for(b.seqcap) + 64 + n))) return rc;   // + the pairs' first-look flags
     if ((rc = grow_dev(c, s.d_res, s.d_res_cap, (size_t)nreads + 1))) return rc;
     if ((rc = grow_dev(c, s.d_todo, s.d_todo_cap, (size_t)n + 1))) return rc;
     if ((rc = grow_dev(c, s.d_rescue, s.d_rescue_cap, (size_t)n + 1))) return rc;
@@ -834,7 +834,8 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
     s.nkev = 0;
     bool rescued = false;
     if (s.batch.n_reads) {
-        DevProbe pr{s.d_tally, s.d_pos, s.d_ext, s.d_view, view_stride_for(s.batch.seqcap)};
+        DevProbe pr{s.d_tally, s.d_pos, s.d_ext, s.d_view, view_stride_for(s.batch.seqcap),
+                    s.batch.paired ? s.d_view + (size_t)s.batch.n_reads * view_stride_for(s.batch.seqcap) + 64 : nullptr};
         urmb_second *second = (c->params.want_second && s.batch.paired) ? s.d_second : nullptr;
         if (second) CK(cudaMemsetAsync(second, 0, (size_t)s.batch.n_reads * sizeof(urmb_second), cs));
         const bool use_pool = s.batch.paired && s.rescue_cap && s.rpool;
@@ -847,7 +848,7 @@ extern "C" int urmb_launch(urmb_ctx *c, int si) {
         TraceCtx tc{&s, cs, cudaSuccess};
         LaunchTrace tr{trace_mark, &tc};
         trace_mark(&tc, 0, 0);
-        int e = launch_probe(c->ix, P, s.batch, pr, cs, c->sm_count);
+        int e = launch_probe(c->ix, P, s.batch, pr, cs, c->sm_count, &o);
         trace_mark(&tc, 0, 1);
         if (e) return fail(c, URMB_E_CUDA, std::string("probe launch: ") + cudaGetErrorString((cudaError_t)e));
         CK(cudaEventRecord(s.ev_k1, cs));
@@ -1115,7 +1116,7 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
         if (rc) return rc;
         if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u read(s) over a per-mate capacity (hits %u, path runs %u, run pool %u, HSPs %u, path assembly %u) mapped again by the big-capacity build, %u still over\n", si, before, s.h_counters[CT_DBG_OVF], s.h_counters[CT_DBG_OVF + 1], s.h_counters[CT_DBG_OVF + 2], s.h_counters[CT_DBG_OVF + 3], s.h_counters[CT_DBG_OVF + 4], s.h_counters[CT_OVERFLOW]);
     }
-    if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u in the second pass, %u rescued (%u by the legacy kernel, %u full-window DPs), %u path runs\n", si, s.batch.n_units, s.h_counters[CT_TODO_TOTAL], s.h_counters[CT_RESCUE], s.h_counters[CT_RESCUE_LEGACY], s.h_counters[CT_RESCUE_DPS], used);
+    if (getenv("URMB_DEBUG")) fprintf(stderr, "[urmb] slot %d: %u units, %u finished by the first look, %u in the second pass, %u rescued (%u by the legacy kernel, %u full-window DPs), %u path runs\n", si, s.batch.n_units, s.h_counters[CT_FIRST_LOOK], s.h_counters[CT_TODO_TOTAL], s.h_counters[CT_RESCUE], s.h_counters[CT_RESCUE_LEGACY], s.h_counters[CT_RESCUE_DPS], used);
     if (getenv("URMB_DEBUG") && s.batch.paired) {
         fprintf(stderr, "[urmb] slot %d: rescue rounds, pairs stopped at a full-window DP:", si);
         for (int r = 1; r <= kRescueRounds + 1; ++r) fprintf(stderr, " %u", s.h_counters[CT_RQ_COUNT + r]);

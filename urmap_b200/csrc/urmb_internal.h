@@ -49,7 +49,8 @@ struct DevParams {  // State1::SetMethod constants, state1.cpp:147-183
     uint32_t R;
     int pe_method;
     uint32_t flags;   // tuning switches (URMB_FLAGS): bit 5 = do not consult the coarse exception bitmap (seqc); bit 8 = test hook:
-                      // every fifth read is treated as over a capacity (exercises the in-stream big-capacity rerun)
+                      // every fifth read is treated as over a capacity (exercises the in-stream big-capacity rerun);
+                      // bit 9 = no first look in the probe kernel (paired input)
 };
 
 struct DevBatch {
@@ -68,6 +69,8 @@ struct DevProbe {   // output of the probe+extend kernel, [n_reads][2 strands][q
     uint32_t *ext;     // BOTH1 slots: packed state-independent result of the gapless extension (EXT_NONE otherwise)
     uint8_t *view;     // [n_reads][view_stride] staged read: packed strands, invalid-letter bits, flags, reverse complement
     uint32_t view_stride;
+    uint8_t *done;     // [n_units] or null.  Paired input: 1 = the pair left State2::Search4/5 inside the seed loop on the probe
+                       // kernel's first look (result records written there; no probe rows, no staged read exist for it)
 };
 constexpr uint32_t kViewHdr = 224;   // packed strands (144) + bad bits (72) + flags (4) + pad; then seqcap bytes of rc
 inline uint32_t view_stride_for(uint32_t seqcap) { return kViewHdr + seqcap; }
@@ -108,7 +111,8 @@ enum {
     CT_OVF_HEAD = CT_OVF_BASE + 1,
     CT_DBG_HSPS = CT_OVF_HEAD + 1,                   // [4] reads by final HSP count: <= 256, <= 512, <= 1024, more (statistics of the big-capacity rerun)
     CT_DBG_MAXHSP = CT_DBG_HSPS + 4,
-    CT_COUNT = CT_DBG_MAXHSP + 1
+    CT_FIRST_LOOK = CT_DBG_MAXHSP + 1,               // pairs finished by the probe kernel's first look (statistics)
+    CT_COUNT = CT_FIRST_LOOK + 1
 };
 
 struct RescueSave;
@@ -198,7 +202,9 @@ struct LaunchCfg {
 };
 
 // implemented in urmb_kernels.cu
-int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count);
+// o: result records and counters for the first look of paired input (null, or pr.done null: every read is probed in full)
+int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count,
+                 const struct DevOut *o = nullptr);
 // Per-context resources of the search kernels: per-warp scratch and the pool of saved mate states (2 per pair of a chunk).
 struct SearchRes {
     WarpScratch *scratch;

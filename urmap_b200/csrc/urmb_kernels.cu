@@ -475,6 +475,78 @@ __host__ __device__ inline size_t probe_smem_per_warp(uint32_t qcap, uint32_t se
 #ifndef URMB_PROBE_LB
 #define URMB_PROBE_LB 3
 #endif
+// The complete probe of one staged read: every k-mer of both strands, then the pure extension of every BOTH1 candidate.
+// vsrc = the read's staged view in shared memory (packed strands + invalid-letter bits), copied out for the search kernels.
+__device__ __forceinline__ void probe_read(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, uint32_t r,
+                                           const ReadView &rv, const uint8_t *vsrc, const uint8_t *s_rc, uint32_t *c_pos,
+                                           uint16_t *c_qs, int lane) {
+    const uint32_t W = ix.word_len, L = rv.QL;
+    const uint32_t lt = (1u << lane) - 1u;
+    {   // the staged read is kept for the search kernels (they would otherwise redo stage_read up to four times)
+        uint32_t *vw = reinterpret_cast<uint32_t *>(pr.view + (size_t)r * pr.view_stride);
+        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(vsrc);
+        for (uint32_t i = lane; i < kReadViewBytes / 4; i += 32) vw[i] = src32[i];
+        if (lane == 0) vw[kReadViewBytes / 4] = (rv.slow ? 1u : 0u) | (rv.hasbad ? 2u : 0u);
+        const uint32_t *rc32 = reinterpret_cast<const uint32_t *>(s_rc);
+        for (uint32_t i = lane; i < b.seqcap / 4; i += 32) vw[kViewHdr / 4 + i] = rc32[i];
+    }
+    const uint32_t QWC = (L >= W) ? L - W + 1 : 0;
+    const size_t base = (size_t)r * 2 * b.qcap;
+    uint32_t nc = 0;
+    // Slot records of URMB_PROBE_BATCH rounds of 32 k-mers are gathered together (two loads per round and lane in
+    // flight) before the first one is looked at: the candidate list needs a ballot per round, which would otherwise put one trip to
+    // HBM between consecutive rounds.
+    const uint32_t rps = b.qcap / 32, nrounds = 2 * rps;   // rounds of 32 k-mers: the plus strand, then the minus strand
+    for (uint32_t r0 = 0; r0 < nrounds; r0 += URMB_PROBE_BATCH) {
+        uint32_t w0[URMB_PROBE_BATCH], w1[URMB_PROBE_BATCH], shp = 0, okm = 0;
+#pragma unroll
+        for (int k = 0; k < URMB_PROBE_BATCH; ++k) {
+            const uint32_t rr = r0 + k, s = rr >= rps, q = (rr - s * rps) * 32 + lane;
+            w0[k] = w1[k] = 0;
+            if (rr < nrounds && q < QWC) {
+                const uint64_t slot = slot_of(ix, rv, (int)s, q);
+                if (slot != ~0ull) {
+                    const uint64_t a = 5ull * slot;   // record at byte offset 5*slot: two aligned words cover it
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blob + (a & ~3ull));
+                    w0[k] = __ldg(w);
+                    w1[k] = __ldg(w + 1);
+                    shp |= (uint32_t)(a & 3ull) << (2 * k);
+                    okm |= 1u << k;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < URMB_PROBE_BATCH; ++k) {
+            const uint32_t rr = r0 + k, s = rr >= rps, q = (rr - s * rps) * 32 + lane;
+            if (rr >= nrounds) break;
+            uint32_t tally = T_FREE, pos = POS_INVALID_WORD;
+            if ((okm >> k) & 1u) {
+                const uint64_t v = (((uint64_t)w1[k] << 32) | w0[k]) >> (((shp >> (2 * k)) & 3u) * 8u);
+                tally = (uint32_t)v & 0xFFu;
+                pos = (uint32_t)(v >> 8);
+            }
+            const bool cand = tally == T_BOTH1;
+            const uint32_t bal = __ballot_sync(FULL, cand);
+            if (cand) {
+                const uint32_t i = nc + __popc(bal & lt);
+                c_pos[i] = pos;
+                c_qs[i] = (uint16_t)(q | (s << 15));
+            } else {
+                pr.ext[base + s * b.qcap + q] = EXT_NONE;
+            }
+            nc += __popc(bal);
+            pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
+            pr.pos[base + s * b.qcap + q] = pos;
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < nc; i += 32) {
+        const uint32_t qs = c_qs[i], q = qs & 0x7FFFu, s = qs >> 15;
+        pr.ext[base + s * b.qcap + q] = pure_ext_t<true>(ix, P, rv, s == 0, q, c_pos[i], true, P.MAXPEN);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr) {
     URMB_DYN_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -484,76 +556,194 @@ __global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_kernel(DevIndex ix, 
     uint32_t *c_pos = reinterpret_cast<uint32_t *>(sw + kReadViewBytes);
     uint16_t *c_qs = reinterpret_cast<uint16_t *>(c_pos + 2 * b.qcap);
     uint8_t *s_q = reinterpret_cast<uint8_t *>(c_qs + 2 * b.qcap), *s_rc = s_q + b.seqcap;
-    const uint32_t W = ix.word_len;
-    const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t r = blockIdx.x * wpb + warp; r < b.n_reads; r += gridDim.x * wpb) {
         const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
         ReadView rv;
         stage_read(lane, b.seqs + off, L, b.seqcap, s_q, s_rc, s_pk, s_bad, rv);
-        {   // the staged read is kept for the search kernels (they would otherwise redo stage_read up to four times)
-            uint32_t *vw = reinterpret_cast<uint32_t *>(pr.view + (size_t)r * pr.view_stride);
-            const uint32_t *src32 = reinterpret_cast<const uint32_t *>(sw);
-            for (uint32_t i = lane; i < kReadViewBytes / 4; i += 32) vw[i] = src32[i];
-            if (lane == 0) vw[kReadViewBytes / 4] = (rv.slow ? 1u : 0u) | (rv.hasbad ? 2u : 0u);
-            const uint32_t *rc32 = reinterpret_cast<const uint32_t *>(s_rc);
-            for (uint32_t i = lane; i < b.seqcap / 4; i += 32) vw[kViewHdr / 4 + i] = rc32[i];
-        }
-        const uint32_t QWC = (L >= W) ? L - W + 1 : 0;
-        const size_t base = (size_t)r * 2 * b.qcap;
-        uint32_t nc = 0;
-        // Slot records of URMB_PROBE_BATCH rounds of 32 k-mers are gathered together (two loads per round and lane in
-        // flight) before the first one is looked at: the candidate list needs a ballot per round, which would otherwise put one trip to
-        // HBM between consecutive rounds.
-        const uint32_t rps = b.qcap / 32, nrounds = 2 * rps;   // rounds of 32 k-mers: the plus strand, then the minus strand
-        for (uint32_t r0 = 0; r0 < nrounds; r0 += URMB_PROBE_BATCH) {
-            uint32_t w0[URMB_PROBE_BATCH], w1[URMB_PROBE_BATCH], shp = 0, okm = 0;
-#pragma unroll
-            for (int k = 0; k < URMB_PROBE_BATCH; ++k) {
-                const uint32_t rr = r0 + k, s = rr >= rps, q = (rr - s * rps) * 32 + lane;
-                w0[k] = w1[k] = 0;
-                if (rr < nrounds && q < QWC) {
-                    const uint64_t slot = slot_of(ix, rv, (int)s, q);
-                    if (slot != ~0ull) {
-                        const uint64_t a = 5ull * slot;   // record at byte offset 5*slot: two aligned words cover it
-                        const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blob + (a & ~3ull));
-                        w0[k] = __ldg(w);
-                        w1[k] = __ldg(w + 1);
-                        shp |= (uint32_t)(a & 3ull) << (2 * k);
-                        okm |= 1u << k;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < URMB_PROBE_BATCH; ++k) {
-                const uint32_t rr = r0 + k, s = rr >= rps, q = (rr - s * rps) * 32 + lane;
-                if (rr >= nrounds) break;
-                uint32_t tally = T_FREE, pos = POS_INVALID_WORD;
-                if ((okm >> k) & 1u) {
-                    const uint64_t v = (((uint64_t)w1[k] << 32) | w0[k]) >> (((shp >> (2 * k)) & 3u) * 8u);
-                    tally = (uint32_t)v & 0xFFu;
-                    pos = (uint32_t)(v >> 8);
-                }
-                const bool cand = tally == T_BOTH1;
-                const uint32_t bal = __ballot_sync(FULL, cand);
-                if (cand) {
-                    const uint32_t i = nc + __popc(bal & lt);
-                    c_pos[i] = pos;
-                    c_qs[i] = (uint16_t)(q | (s << 15));
-                } else {
-                    pr.ext[base + s * b.qcap + q] = EXT_NONE;
-                }
-                nc += __popc(bal);
-                pr.tally[base + s * b.qcap + q] = (uint8_t)tally;
-                pr.pos[base + s * b.qcap + q] = pos;
-            }
-        }
-        __syncwarp();
-        for (uint32_t i = lane; i < nc; i += 32) {
-            const uint32_t qs = c_qs[i], q = qs & 0x7FFFu, s = qs >> 15;
-            pr.ext[base + s * b.qcap + q] = pure_ext_t<true>(ix, P, rv, s == 0, q, c_pos[i], true, P.MAXPEN);
-        }
-        __syncwarp();
+        probe_read(ix, P, b, pr, r, rv, sw, s_rc, c_pos, c_qs, lane);
     }
+}
+
+// ---- first look (paired input) -----------------------------------------------------------
+// 42 % of the pairs of a typical run leave State2::Search4/5 inside the seed loop (search2m4.cpp:79-142): the first BOTH1
+// seed of each mate lies on the true diagonal, both gapless extensions span the whole read and the scores add up to
+// QLf + QLr - 15 or more.  The reference has then touched a handful of slots, not 2 x 2 x 127.  The first look replays the
+// seed loop over the first kLookK steps of both seed iterators (k < 8: both strands of both mates = 32 slot probes, one per
+// lane) for as long as that is a pure function of those probes:
+//   * the iterator of either mate returns, within the first 16 visits, exactly the BOTH1 visits whose diagonal differs
+//     from the previous BOTH1 visit (getseed.cpp:9-138, as build_seeds_pe);
+//   * inside the loop seeds are only extended by ExtendBoth1Pair4/5, i.e. for seed pairs within the template length, and on
+//     untouched search states ExtendPen is the pure function pure_ext_t computes: a call that returns <= 0 without adding a
+//     hit or an HSP changes nothing, so the replay may go on; the first call that does add something either completes the
+//     exit (both full length, sum >= the bound: MAPQ 40/40, one hit per mate -- the result is written here) or ends the
+//     replay;
+//   * the replay also ends when it would need a seed beyond the probed visits, or an extension on the strand that is not
+//     the seed's own (search2m4.cpp:122 passes !Plusr for the forward mate).
+// A pair whose replay ends that way takes the complete path as before (the 32 records are L2 hits then), so the first look
+// only has to be sound, never complete.
+constexpr int kLookK = 8;   // seed-iterator steps of the first look: 2 mates x 2 strands x kLookK = one probe per lane
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+    for (int i = 0; i < n; ++i) m &= m - 1;
+    return __ffs(m) - 1;
+}
+__device__ __forceinline__ bool ext_is_noop_p(const DevParams &P, uint32_t x, int QL, int MaxPenalty) {
+    if (x == EXT_NONE) return true;
+    if (ext_nmis(x) * -P.MM > MaxPenalty) return true;
+    if (ext_start(x) == 0 && ext_end(x) == QL - 1) return false;
+    const int MinHSPScore = (P.MIN_HSP_PCT * QL) / 100;   // == int(PCT*QL/100.0), extendpen.cpp:22
+    return ext_best(x) < MinHSPScore;
+}
+__device__ __noinline__ bool pair_first_look(const DevIndex &ix, const DevParams &P, const ReadView &rvF, const ReadView &rvR,
+                                             urmb_result *resF, urmb_result *resR) {
+    const int lane = URMB_LANE;
+    const uint32_t W = ix.word_len;
+    if (rvF.QL < W || rvR.QL < W) return false;
+    const int QLf = (int)rvF.QL, QLr = (int)rvR.QL, QL2 = (QLf + QLr) / 2;
+    // lane = mate << 4 | visit, visit v = 2 k + strand as the iterators go (plus, then minus at every k)
+    static_assert(4 * kLookK == 32, "one probe per lane");
+    const int mate = lane >> 4, v = lane & 15, sgn = v & 1;
+    const uint32_t k = (uint32_t)v >> 1;
+    const ReadView &rv = mate ? rvR : rvF;
+    const int QL = (int)rv.QL;
+    const uint32_t QWC = rv.QL - W + 1;
+    const bool valid = k < QWC;
+    const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0u;
+    uint32_t tally = T_FREE, pos = 0;
+    if (valid) {
+        const uint64_t slot = slot_of(ix, rv, sgn, QPos);
+        if (slot != ~0ull) load_blob<false>(ix.blob, slot, tally, pos);
+    }
+    const bool b1 = tally == T_BOTH1;
+    const uint32_t diag = pos - QPos;
+    const uint32_t half = mate ? 0xFFFF0000u : 0x0000FFFFu, lt = (1u << lane) - 1u;
+    const uint32_t b1mask = __ballot_sync(FULL, b1);
+    const uint32_t below = b1mask & lt & half;
+    const uint32_t pd = __shfl_sync(FULL, diag, below ? 31 - __clz(below) : 0);
+    const bool ret = b1 && (!below || diag != pd);
+    const uint32_t retmask = __ballot_sync(FULL, ret);
+    const uint32_t retF = retmask & 0xFFFFu, retR = retmask >> 16;
+    const int nF = __popc(retF), nR = __popc(retR);
+    if (nF == 0 || nR == 0) return false;
+    // seeds of the other mate within the template length of this one (bit j: visit j of the other mate)
+    uint32_t partners = 0;
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+        const int src = ((mate ^ 1) << 4) | j;
+        const uint32_t op = __shfl_sync(FULL, pos, src);
+        int64_t d = (int64_t)pos - (int64_t)op;
+        if (d < 0) d = -d;
+        if (((retmask >> src) & 1u) && d + QL2 <= MAX_TL) partners |= 1u << j;
+    }
+    if (!ret) partners = 0;
+    if (!__any_sync(FULL, partners != 0)) return false;
+    // ExtendPen of a seed on its own strand against an untouched search state: 0 = returns <= 0 and changes nothing,
+    // 1 = full-length hit stored (returns its score), 2 = anything else (an HSP is saved; a hit below AddHitX's floor)
+    int cls = 0, score = 0;
+    if (partners) {
+        const uint32_t x = pure_ext_t<true>(ix, P, rv, sgn == 0, QPos, pos, true, P.MAXPEN);
+        if (!ext_is_noop_p(P, x, QL, P.MAXPEN)) {
+            score = ext_best(x);
+            cls = (ext_start(x) == 0 && ext_end(x) == QL - 1 && score >= 10) ? 1 : 2;
+        }
+    }
+    const int Term = QLf + QLr + 5 * P.MM;
+    int exF = -1, exR = -1;
+#pragma unroll 1
+    for (int t = 0; t < 16; ++t) {
+        if (t >= nF) return false;   // the next seed lies beyond the probed visits
+        const int fl = nth_set_bit(retF, t), rl = (t < nR) ? 16 + nth_set_bit(retR, t) : 32;
+        {   // F seed t against the R seeds recorded so far (search2m4.cpp:81-109): ExtendPen(F seed) comes first in every call
+            const uint32_t pm = __shfl_sync(FULL, partners, fl) & retR & (uint32_t)((1ull << (rl - 16)) - 1ull);
+            if (pm) {
+                const int cf = __shfl_sync(FULL, cls, fl);
+                if (cf == 2) return false;
+                if (cf == 1) {
+                    const int r0 = 16 + __ffs(pm) - 1;
+                    // the R seed is extended on the strand opposite to F's: only its own strand's extension is at hand
+                    if (((r0 ^ fl) & 1) == 0) return false;
+                    if (__shfl_sync(FULL, cls, r0) != 1) return false;
+                    if (__shfl_sync(FULL, score, fl) + __shfl_sync(FULL, score, r0) < Term) return false;
+                    exF = fl; exR = r0;
+                    break;
+                }
+            }
+        }
+        if (t >= nR) return false;
+        {   // R seed t against the F seeds recorded so far, F seed t included (search2m4.cpp:110-137): the F seed is extended
+            // on the strand opposite to R's
+            uint32_t pm = __shfl_sync(FULL, partners, rl) & retF & ((2u << fl) - 1u);
+            while (pm) {
+                const int f0 = __ffs(pm) - 1;
+                pm &= pm - 1;
+                if (((f0 ^ rl) & 1) == 0) return false;
+                const int cf = __shfl_sync(FULL, cls, f0);
+                if (cf == 0) continue;
+                if (cf == 2) return false;
+                if (__shfl_sync(FULL, cls, rl) != 1) return false;
+                if (__shfl_sync(FULL, score, f0) + __shfl_sync(FULL, score, rl) < Term) return false;
+                exF = f0; exR = rl;
+                break;
+            }
+            if (exF >= 0) break;
+        }
+    }
+    if (exF < 0) return false;
+    if (lane == exF || lane == exR) {   // one stored hit, m_BestScore = its score, m_SecondBestScore 0, MAPQ 40 (search2m4.cpp:203-205)
+        urmb_result res;
+        res.db_pos = diag;
+        res.path_off = 0;
+        res.path_runs = 0;
+        res.score = (int16_t)score;
+        res.best = (int16_t)score;
+        res.second = 0;
+        res.mapq = 40;
+        res.flags = (uint8_t)((sgn == 0 ? 1 : 0) | 2);
+        res.hit_count = 1;
+        res.hsp_count = 0;
+        *(mate ? resR : resF) = res;
+    }
+    return true;
+}
+
+__host__ __device__ inline size_t probe_pair_smem_per_warp(uint32_t qcap, uint32_t seqcap) {
+    //     two read views + bytes                        c_pos                 c_qs
+    return (2 * (kReadViewBytes + 2 * (size_t)seqcap) + 2 * (size_t)qcap * 4 + 2 * (size_t)qcap * 2 + 15) & ~(size_t)15;
+}
+// Paired input: one warp per pair -- stage both mates, first look, and the complete probe of both mates when that does not
+// finish the pair.
+__global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_pair_kernel(DevIndex ix, DevParams P, DevBatch b, DevProbe pr, urmb_result *res,
+                                                                        uint32_t *counters) {
+    URMB_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint8_t *sw = smem + (size_t)warp * probe_pair_smem_per_warp(b.qcap, b.seqcap);
+    const size_t msz = kReadViewBytes + 2 * (size_t)b.seqcap;   // per mate: packed strands, invalid-letter bits, bytes, reverse complement
+    uint32_t *c_pos = reinterpret_cast<uint32_t *>(sw + 2 * msz);
+    uint16_t *c_qs = reinterpret_cast<uint16_t *>(c_pos + 2 * b.qcap);
+    uint32_t nlook = 0;
+    for (uint32_t u = blockIdx.x * wpb + warp; u < b.n_units; u += gridDim.x * wpb) {
+        ReadView rv[2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const uint32_t r = m ? b.n_units + u : u;
+            const uint32_t off = b.offs[r], L = b.offs[r + 1] - off;
+            uint8_t *a = sw + m * msz;
+            stage_read(lane, b.seqs + off, L, b.seqcap, a + kReadViewBytes, a + kReadViewBytes + b.seqcap, reinterpret_cast<uint64_t *>(a),
+                       reinterpret_cast<uint32_t *>(a + 2 * kPkWords * 8), rv[m]);
+        }
+        const bool fin = pair_first_look(ix, P, rv[0], rv[1], res + u, res + b.n_units + u) && !(P.flags & 1024u);   // bit 10: measure-only
+        if (lane == 0) pr.done[u] = fin ? 1 : 0;
+        if (fin) {
+            ++nlook;
+            __syncwarp();
+            continue;
+        }
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m) {
+            const uint8_t *a = sw + m * msz;
+            probe_read(ix, P, b, pr, m ? b.n_units + u : u, rv[m], a, a + kReadViewBytes + b.seqcap, c_pos, c_qs, lane);
+        }
+    }
+    if (lane == 0 && nlook) atomicAdd(&counters[CT_FIRST_LOOK], nlook);
 }
 
 // =====================================================================================
@@ -2954,6 +3144,7 @@ __device__ __forceinline__ void search_body(const KArgs &A) {
         u = __shfl_sync(FULL, u, 0);
         if (u >= n_work) break;
         u = listed ? ulist[u] : A.unit_base + u;
+        if (MODE == 1 && A.pr.done && A.pr.done[u]) continue;   // finished by the probe kernel's first look
         if (MODE == 3) {   // single-end, the whole of Search_Lo in one kernel (search1m6.cpp:35-277)
             Mate m;
             load_mate(E, m, b, A.pr, u, sw, &E.ws->m[0], true);
@@ -3286,14 +3477,34 @@ int launch_pack_genome(const uint8_t *seq, size_t n_bytes, uint64_t *seq2, uint3
     return (int)cudaGetLastError();
 }
 
-int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count) {
+int launch_probe(const DevIndex &ix, const DevParams &P, const DevBatch &b, const DevProbe &pr, void *stream, int sm_count,
+                 const DevOut *o) {
     const int threads = 256;
+    if (b.paired && pr.done && o && !(P.flags & (256u | 512u))) {   // one warp per pair, with the first look
+        const size_t smem = (size_t)(threads / 32) * probe_pair_smem_per_warp(b.qcap, b.seqcap);
+        cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        int blocks = (int)((b.n_units + 7) / 8);
+        if (blocks > sm_count * 16) blocks = sm_count * 16;
+        if (blocks < 1) blocks = 1;
+        URMB_LAUNCH(probe_pair_kernel, blocks, threads, smem, stream, ix, P, b, pr, o->res, o->counters);
+        return (int)cudaGetLastError();
+    }
+    DevProbe q = pr;
+    q.done = nullptr;
+    if (b.paired && pr.done) {   // no first look: no pair is finished here
+#ifndef URMB_EMU
+        const cudaError_t me = cudaMemsetAsync(pr.done, 0, b.n_units, (cudaStream_t)stream);
+        if (me != cudaSuccess) return (int)me;
+#else
+        memset(pr.done, 0, b.n_units);
+#endif
+    }
     const size_t smem = (size_t)(threads / 32) * probe_smem_per_warp(b.qcap, b.seqcap);
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int blocks = (int)((b.n_reads + 7) / 8);
     if (blocks > sm_count * 16) blocks = sm_count * 16;
     if (blocks < 1) blocks = 1;
-    URMB_LAUNCH(probe_kernel, blocks, threads, smem, stream, ix, P, b, pr);
+    URMB_LAUNCH(probe_kernel, blocks, threads, smem, stream, ix, P, b, q);
     return (int)cudaGetLastError();
 }
 

@@ -626,13 +626,14 @@ __device__ __noinline__ bool pair_first_look(const DevIndex &ix, const DevParams
     if (nF == 0 || nR == 0) return false;
     // seeds of the other mate within the template length of this one (bit j: visit j of the other mate)
     uint32_t partners = 0;
+    if (QL2 > MAX_TL) return false;
+    const uint32_t maxd = (uint32_t)(MAX_TL - QL2);   // |DBPosf - DBPosr| + QL2 <= MAX_TL
 #pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
-        const int src = ((mate ^ 1) << 4) | j;
+    for (uint32_t rm = retmask; rm; rm &= rm - 1) {   // every seed of either mate (a handful)
+        const int src = __ffs(rm) - 1;
         const uint32_t op = __shfl_sync(FULL, pos, src);
-        int64_t d = (int64_t)pos - (int64_t)op;
-        if (d < 0) d = -d;
-        if (((retmask >> src) & 1u) && d + QL2 <= MAX_TL) partners |= 1u << j;
+        const uint32_t d = pos > op ? pos - op : op - pos;
+        if (((src ^ lane) & 16) && d <= maxd) partners |= 1u << (src & 15);
     }
     if (!ret) partners = 0;
     if (!__any_sync(FULL, partners != 0)) return false;
@@ -730,7 +731,8 @@ __global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_pair_kernel(DevIndex
             stage_read(lane, b.seqs + off, L, b.seqcap, a + kReadViewBytes, a + kReadViewBytes + b.seqcap, reinterpret_cast<uint64_t *>(a),
                        reinterpret_cast<uint32_t *>(a + 2 * kPkWords * 8), rv[m]);
         }
-        const bool fin = pair_first_look(ix, P, rv[0], rv[1], res + u, res + b.n_units + u) && !(P.flags & 1024u);   // bit 10: measure-only
+        // bits 10 / 11 (measurements): the first look is computed but not used / not computed
+        const bool fin = !(P.flags & 2048u) && pair_first_look(ix, P, rv[0], rv[1], res + u, res + b.n_units + u) && !(P.flags & 1024u);
         if (lane == 0) pr.done[u] = fin ? 1 : 0;
         if (fin) {
             ++nlook;
@@ -740,7 +742,17 @@ __global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_pair_kernel(DevIndex
 #pragma unroll 1
         for (int m = 0; m < 2; ++m) {
             const uint8_t *a = sw + m * msz;
-            probe_read(ix, P, b, pr, m ? b.n_units + u : u, rv[m], a, a + kReadViewBytes + b.seqcap, c_pos, c_qs, lane);
+            // the view of this mate by value: rv[] was handed to functions by reference and lives in local memory, and the
+            // probe's inner loops consult the view for every k-mer
+            ReadView v;
+            v.q = a + kReadViewBytes;
+            v.rc = a + kReadViewBytes + b.seqcap;
+            v.pk = reinterpret_cast<const uint64_t *>(a);
+            v.bad = reinterpret_cast<const uint32_t *>(a + 2 * kPkWords * 8);
+            v.QL = m ? rv[1].QL : rv[0].QL;
+            v.slow = m ? rv[1].slow : rv[0].slow;
+            v.hasbad = m ? rv[1].hasbad : rv[0].hasbad;
+            probe_read(ix, P, b, pr, m ? b.n_units + u : u, v, a, v.rc, c_pos, c_qs, lane);
         }
     }
     if (lane == 0 && nlook) atomicAdd(&counters[CT_FIRST_LOOK], nlook);

@@ -35,6 +35,7 @@ extern "C" {
 
 #define URMB_SLOTS 8
 #define URMB_MAX_READ_LEN 256
+#define URMB_MAX_IX 1024 /* largest MaxIx of an index (-maxix, ufindexio.cpp:135-136; the reference's default is 32) */
 
 typedef struct urmb_index_host urmb_index_host; /* parsed UFI file in (pinned) host memory */
 typedef struct urmb_ctx urmb_ctx;               /* per-GPU context */
@@ -160,6 +161,10 @@ int urmb_overflow_count(urmb_ctx *c, int slot, uint32_t *last, uint64_t *total);
  * their mates are reported unmapped with bit 6 set in urmb_result.flags; every other read of the batch is mapped as usual.
  * Counts as for urmb_overflow_count. */
 int urmb_unsupported_count(urmb_ctx *c, int slot, uint32_t *last, uint64_t *total);
+/* Pairs that left State2::Search4/5 inside its seed loop (search2m4.cpp:79-142: MAPQ 40/40 exit) on the probe kernel's first
+ * look at the first 8 steps of both seed iterators, and therefore skipped the complete probe and the search kernels
+ * (statistics; counts as for urmb_overflow_count). */
+int urmb_first_look_count(urmb_ctx *c, int slot, uint32_t *last, uint64_t *total);
 /* After urmb_wait on a paired-end slot of a context created with want_second: the second hits of mate 1 / mate 2. */
 int urmb_second_hits(urmb_ctx *c, int slot, const urmb_second **s1, const urmb_second **s2);
 /* Finer-grained steps (bench.py uses them to time the kernels with inputs resident in HBM). */

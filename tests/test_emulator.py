@@ -205,3 +205,45 @@ def test_emulated_repeat_rich_rows(oracle, built_lib, tmp_path):
         _same(np.concatenate([o1, o2]), uo, re_, ue)
     finally:
         ix.close()
+
+
+def test_emulated_maxix_above_32(oracle, built_lib, tmp_path):
+    """An index built with -maxix 100 (ufindexio.cpp:135-136): rows of 33 .. 100 positions (tandem arrays) go through the
+    deferred-row stage with a row stride of MaxIx instead of 32."""
+    import subprocess
+    import emu_py
+    from urmap_b200 import synth
+    g = synth.make_genome(300_000, n_contigs=2, seed=78, repeat_frac=0.35, n_runs=[(0, 0.3, 300)], tandem=12)
+    fa, ufi, ufi32 = str(tmp_path / "m.fa"), str(tmp_path / "m.ufi"), str(tmp_path / "m32.ufi")
+    g.write_fasta(fa)
+    cli = os.path.join(ROOT, "urmap_b200", "bin", "urmap_b200")
+    for out, extra in ((ufi, ["-maxix", "100"]), (ufi32, [])):
+        r = subprocess.run([cli, "-make_ufi", fa, "-output", out, "-quiet"] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    ix, ix32 = oracle.Index(ufi), oracle.Index(ufi32)
+    try:
+        assert ix.max_ix == 100
+        reads, names = synth.sim_se(g, 150, 150, 0.02, 0.002, seed=5)
+        fq = str(tmp_path / "se.fq")
+        synth.write_fastq(fq, reads, names)
+        b = oracle.ReadBatch.from_fastq(fq)
+        ro, uo, st = oracle.map_se(ix, b, want_stats=True)
+        _, _, st32 = oracle.map_se(ix32, b, want_stats=True)
+        assert st["row_hops"] > st32["row_hops"]   # lists the default index leaves out are walked here
+        re_, ue, cnt = emu_py.emu_map(ix, oracle.RESULT_DTYPE, b.seqs, b.offs, b.n, False)
+        assert cnt[1] == 0
+        _same(ro, uo, re_, ue)
+        r1, r2, names = synth.sim_pe(g, 60, 150, 0.02, 0.002, seed=15)
+        f1, f2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+        synth.write_fastq(f1, r1, names, b"/1")
+        synth.write_fastq(f2, r2, names, b"/2")
+        b1, b2 = oracle.ReadBatch.from_fastq(f1), oracle.ReadBatch.from_fastq(f2)
+        o1, o2, uo = oracle.map_pe(ix, b1, b2)
+        seqs = np.concatenate([b1.seqs, b2.seqs])
+        offs = np.concatenate([b1.offs, b2.offs[1:] + b1.offs[-1]]).astype(np.uint32)
+        re_, ue, cnt = emu_py.emu_map(ix, oracle.RESULT_DTYPE, seqs, offs, b1.n, True)
+        assert cnt[1] == 0
+        _same(np.concatenate([o1, o2]), uo, re_, ue)
+    finally:
+        ix.close()
+        ix32.close()

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import have_gpu
+from conftest import ROOT, have_gpu
 from urmap_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -272,6 +272,74 @@ def test_dense_index_long_links(eng, oracle, tmp_path):
     g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
     o1, o2, uo2 = oracle.map_pe(oix, b1, b2, threads=os.cpu_count())
     assert_same(np.concatenate([o1, o2]), uo2, np.concatenate([g1, g2]), ug)
+    ctx.close()
+
+
+def test_maxix_above_32(eng, oracle, tmp_path):
+    """An index built with -maxix 100 (ufindexio.cpp:135-136) by the drop-in's GPU builder: byte-identical to the reference's,
+    and rows of 33 .. 100 positions (tandem arrays) are mapped as the oracle maps them, single-end and paired."""
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available to build the index")
+    import subprocess
+    g = synth.make_genome(1_000_000, n_contigs=3, seed=78, repeat_frac=0.30, n_runs=[(0, 0.3, 300)], tandem=40)
+    fa, ufi, mine = str(tmp_path / "m.fa"), str(tmp_path / "m.ufi"), str(tmp_path / "mine.ufi")
+    g.write_fasta(fa)
+    oracle.run_reference(["-make_ufi", fa, "-output", ufi, "-maxix", "100"])
+    cli = os.path.join(ROOT, "urmap_b200", "bin", "urmap_b200")
+    r = subprocess.run([cli, "-make_ufi", fa, "-output", mine, "-maxix", "100", "-gpu_build", "-quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(mine, "rb").read() == open(ufi, "rb").read()
+    oix, hix = oracle.Index(ufi), eng.HostIndex(mine)
+    assert oix.max_ix == 100
+    ctx = eng.Context(0)
+    ctx.set_index(hix)
+    reads, _ = synth.sim_se(g, 20000, 150, 0.02, 0.002, seed=31)
+    b = oracle.ReadBatch.from_arrays(reads)
+    res, runs = ctx.map_se(b.seqs, b.offs)
+    ro, uo, st = oracle.map_se(oix, b, threads=os.cpu_count(), want_stats=True)
+    assert st["row_hops_long"] > 20 * b.n
+    assert_same(ro, uo, res, runs)
+    r1, r2, _ = synth.sim_pe(g, 10000, 250, 0.02, 0.002, seed=32)
+    b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
+    g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+    o1, o2, uo2 = oracle.map_pe(oix, b1, b2, threads=os.cpu_count())
+    assert_same(np.concatenate([o1, o2]), uo2, np.concatenate([g1, g2]), ug)
+    ctx.close()
+
+
+def test_first_look(eng, oracle, mid_env):
+    """The probe kernel's first look (paired input): the pairs it finishes -- the seed-loop exit of Search4/5,
+    search2m4.cpp:79-142, 203-205 -- carry the oracle's records, a third of clean pairs take it, and switching it off
+    (URMB_FLAGS bit 9) changes nothing.  Also -map2 -veryfast (Search5), 250-base reads and reads shorter than a word."""
+    g, oix, hix = mid_env
+    for rl, sub, indel, pm in ((150, 0.01, 0.001, 4), (150, 0.01, 0.001, 5), (250, 0.005, 0.0005, 4), (100, 0.0, 0.0, 4)):
+        r1, r2, _ = synth.sim_pe(g, 8000, rl, sub, indel, seed=41 + rl)
+        b1, b2 = oracle.ReadBatch.from_arrays(r1), oracle.ReadBatch.from_arrays(r2)
+        o1, o2, uo = oracle.map_pe(oix, b1, b2, pe_method=pm, band_radius=4 if pm == 5 else -1, threads=os.cpu_count())
+        got = []
+        for env in ({}, {"URMB_FLAGS": "512"}):
+            ctx = _ctx_with_env(eng, hix, env, pe_method=pm, band_radius=4 if pm == 5 else -1)
+            g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+            assert_same(np.concatenate([o1, o2]), uo, np.concatenate([g1, g2]), ug)
+            got.append(ctx.first_look_count()[0])
+            ctx.close()
+        assert got[1] == 0 and got[0] > 0.2 * b1.n, got
+    # ragged pairs: a mate shorter than a word, an empty mate, invalid letters -- never finished by the first look wrongly
+    r1, r2, _ = synth.sim_pe(g, 64, 150, 0.0, 0.0, seed=5)
+    rows1 = [bytes(r) for r in r1]
+    rows2 = [bytes(r) for r in r2]
+    rows1[0], rows2[1], rows1[2], rows2[3] = rows1[0][:20], b"", rows1[2][:30], b"N" * 150
+    rows1[4] = rows1[4][:70] + b"N" + rows1[4][71:]
+    rows2[5] = rows2[5].lower()
+    def batch(rows):
+        return oracle.ReadBatch(np.frombuffer(b"".join(rows), dtype=np.uint8), np.concatenate([[0], np.cumsum([len(x) for x in rows])]).astype(np.uint32))
+
+    b1, b2 = batch(rows1), batch(rows2)
+    o1, o2, uo = oracle.map_pe(oix, b1, b2, threads=2)
+    ctx = eng.Context(0)
+    ctx.set_index(hix)
+    g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
+    assert_same(np.concatenate([o1, o2]), uo, np.concatenate([g1, g2]), ug)
     ctx.close()
 
 

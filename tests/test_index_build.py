@@ -41,6 +41,7 @@ def test_emulated_builder_matches_reference(oracle, golden_oix, golden_dir, tmp_
 
 
 @pytest.mark.parametrize("extra,long_links", [([], False), (["-veryfast"], False), (["-maxix", "5", "-wordlength", "20"], False),
+                                              (["-maxix", "100"], True),
                                               (["-load_factor", "0.8"], True), (["-load_factor", "0.95"], True)])
 def test_emulated_builder_options(oracle, tmp_path, extra, long_links):
     """Repeat-rich 400 kb genome under the reference's index options: byte-identical, including the dense tables in which

@@ -240,6 +240,7 @@ struct urmb_ctx {
     Slot slots[URMB_SLOTS];
     uint64_t launches = 0;
     uint64_t overflow_total = 0;   // reads that exceeded a per-read capacity, over all finished batches
+    uint64_t first_look_total = 0;   // pairs finished by the probe kernel's first look
     uint64_t unsupported_total = 0; // reads not searched because they (or their mates) are longer than URMB_MAX_READ_LEN
     std::string err;
 };
@@ -380,7 +381,7 @@ extern "C" void urmb_ctx_destroy(urmb_ctx *c) {
 
 static int set_index(urmb_ctx *c, const urmb_index_desc *d) {
     if (d->word_length < 8 || d->word_length > 32) return fail(c, URMB_E_UNSUPPORTED, "word length must be in [8,32]");
-    if (d->max_ix < 1 || d->max_ix > 32) return fail(c, URMB_E_UNSUPPORTED, "max_ix must be in [1,32]");
+    if (d->max_ix < 1 || d->max_ix > URMB_MAX_IX) return fail(c, URMB_E_UNSUPPORTED, "max_ix must be in [1,1024]");
     if (d->slot_count < 2 || d->slot_count >= (1ull << 62)) return fail(c, URMB_E_ARG, "bad slot count");
     c->ix.blob = (const uint8_t *)d->d_blob;
     c->ix.seq = (const uint8_t *)d->d_seq;
@@ -1137,7 +1138,7 @@ extern "C" int urmb_wait(urmb_ctx *c, int si, const urmb_result **res1, const ur
     if (runs) *runs = s.h_runs;
     if (runs_used) *runs_used = used;
     for (uint32_t r : s.too_long) s.h_res[r].flags |= 0x40;   // unmapped because the read (or its mate) is too long
-    if (!s.counted) { c->unsupported_total += s.too_long.size(); c->overflow_total += s.h_counters[CT_OVERFLOW]; s.counted = true; }
+    if (!s.counted) { c->unsupported_total += s.too_long.size(); c->overflow_total += s.h_counters[CT_OVERFLOW]; c->first_look_total += s.h_counters[CT_FIRST_LOOK]; s.counted = true; }
     // Reads that exceeded a per-read capacity carry bit 7 in urmb_result.flags and are counted (urmb_overflow_count): the
     // batch itself is valid, so this is not an error (the reference grows its lists without bound, state1.cpp:190).
     return URMB_OK;
@@ -1154,6 +1155,13 @@ extern "C" int urmb_overflow_count(urmb_ctx *c, int si, uint32_t *last, uint64_t
     if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
     if (last) *last = c->slots[si].h_counters ? c->slots[si].h_counters[CT_OVERFLOW] : 0;
     if (total) *total = c->overflow_total;
+    return URMB_OK;
+}
+
+extern "C" int urmb_first_look_count(urmb_ctx *c, int si, uint32_t *last, uint64_t *total) {
+    if (!c || si < 0 || si >= URMB_SLOTS) return URMB_E_ARG;
+    if (last) *last = c->slots[si].h_counters ? c->slots[si].h_counters[CT_FIRST_LOOK] : 0;
+    if (total) *total = c->first_look_total;
     return URMB_OK;
 }
 

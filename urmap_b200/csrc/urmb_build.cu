@@ -17,7 +17,7 @@
 //   count  : saturating 8-bit counts per slot for plus- and minus-strand k-mers (CAS on packed bytes)
 //   scan   : exclusive prefix sum of list lengths over indexed slots -> pool offsets (two-level)
 //   scatter: positions of indexed k-mers -> pool[base[slot] + ticket]
-//   heads  : per indexed slot: sort its <=32 positions (genome order), write the head record
+//   heads  : per indexed slot: sort its <= MaxIx positions (genome order), write the head record
 //   carry  : q(s) by a two-level max-plus scan -> bitmap of segment borders (q(s) == 0)
 //   segment: one thread per segment replays UpdateSlot (ufindex.cpp:194-322) for its overflow elements in genome order
 //   repair : segments that need a long link, replayed with the segments they spill into
@@ -244,16 +244,29 @@ __global__ void build_heads_kernel(BuildArgs a) {
     if (s >= a.slot_count) return;
     const uint32_t n = list_len(a, s);
     if (n == 0) return;
-    uint32_t pos[32];
     const uint64_t b = a.base[s];
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t v = a.pool[b + i];
-        int j = (int)i - 1;
-        while (j >= 0 && pos[j] > v) { pos[j + 1] = pos[j]; --j; }
-        pos[j + 1] = v;
+    uint32_t first;
+    if (n <= 32) {
+        uint32_t pos[32];
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t v = a.pool[b + i];
+            int j = (int)i - 1;
+            while (j >= 0 && pos[j] > v) { pos[j + 1] = pos[j]; --j; }
+            pos[j + 1] = v;
+        }
+        for (uint32_t i = 0; i < n; ++i) a.pool[b + i] = pos[i];
+        first = pos[0];
+    } else {   // -maxix above 32: sorted in place
+        uint32_t *pos = a.pool + b;
+        for (uint32_t i = 1; i < n; ++i) {
+            const uint32_t v = pos[i];
+            int j = (int)i - 1;
+            while (j >= 0 && pos[j] > v) { pos[j + 1] = pos[j]; --j; }
+            pos[j + 1] = v;
+        }
+        first = pos[0];
     }
-    for (uint32_t i = 0; i < n; ++i) a.pool[b + i] = pos[i];
-    put_rec(a.blob, s, (n == 1 && cnt_get(a.cntM, s) == 0) ? BT_BOTH1 : BT_PLUS1, pos[0]);
+    put_rec(a.blob, s, (n == 1 && cnt_get(a.cntM, s) == 0) ? BT_BOTH1 : BT_PLUS1, first);
     atomicSub(a.fill + (s >> 2), 1u << ((uint32_t)(s & 3) * 8));
 }
 
@@ -542,8 +555,9 @@ extern "C" const char *urmb_build_last_error() { return g_build_err.c_str(); }
 // stats[2] = microseconds.
 extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size, uint64_t slot_count,
                                        uint32_t word_length, uint32_t max_ix, void *d_blob, uint64_t *stats) {
-    if (!d_seq || !d_blob || slot_count < 2 || word_length < 8 || word_length > 32 || max_ix < 1 || max_ix > 32)
-        return URMB_E_ARG;
+    // the slot counts saturate at 255 as the reference's (ufindex.cpp:338-408): lists of up to 254 positions are exact here
+    if (!d_seq || !d_blob || slot_count < 2 || word_length < 8 || word_length > 32 || max_ix < 1) return URMB_E_ARG;
+    if (max_ix > 254) { g_build_err = "-maxix above 254 (saturated slot counts)"; return URMB_E_UNSUPPORTED; }
     BuildArgs a{};
     a.seq = (const uint8_t *)d_seq;
     a.seq_size = seq_data_size;

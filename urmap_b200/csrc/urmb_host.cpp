@@ -1646,7 +1646,7 @@ static int CmdMakeUfi(const Opts &o) {  // cmd_make_ufi, ufindexio.cpp:117-179
     if (o.gpu_build) {
         B.Blob.resize(5 * B.SlotCount);
         const int rc = urmb_host_gpu_build(B.Seq.data(), B.Seq.size(), B.SlotCount, B.W, B.MaxIx, B.Blob.data());
-        if (rc == URMB_E_OVERFLOW) {   // a list would have to be truncated (TruncateSlot): exact on the host only
+        if (rc == URMB_E_OVERFLOW || rc == URMB_E_UNSUPPORTED) {   // a list would have to be truncated (TruncateSlot), -maxix above 254: exact on the host only
             Progress("GPU index build: %s; building on the host instead\n", urmb_build_last_error());
             std::vector<uint8_t>().swap(B.Blob);
             B.MakeIndex();

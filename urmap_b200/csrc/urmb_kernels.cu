@@ -2165,7 +2165,7 @@ __device__ __noinline__ void rows_short_round(const Env &E, Mate &m, const uint8
     __syncwarp();
 }
 
-// Lane-local GetRow_Blob (ufindex.cpp:883-943): the whole row into out[0..31]; returns the row length.
+// Lane-local GetRow_Blob (ufindex.cpp:883-943): the whole row into out[0 .. MaxIx); returns the row length.
 __device__ uint32_t row_walk_lane(const Env &E, uint64_t Slot, uint32_t Tally, uint32_t Pos0, uint32_t *out) {
     uint32_t T = Tally;
     if ((T & T_MY_BIT) == 0) return 0;
@@ -2200,6 +2200,13 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_
     uint32_t *stage = reinterpret_cast<uint32_t *>(E.ws->rowM);   // [32 rows][32 positions]
     uint32_t *fpos = reinterpret_cast<uint32_t *>(E.ws->rowD);    // flat candidate positions (<= 1024)
     uint8_t *fq = E.ws->tb;                                       // flat candidate QPos
+    const uint32_t mx = E.ix.max_ix > 32u ? E.ix.max_ix : 32u;    // row stride
+    if (mx > 32u) {   // an index built with -maxix above 32 (ufindexio.cpp:135-136): the three arrays in the trace-bit area
+        static_assert((size_t)kBigRows * kBigCols >= (size_t)32 * URMB_MAX_IX * 9, "trace-bit area holds the rows of -maxix URMB_MAX_IX");
+        stage = reinterpret_cast<uint32_t *>(E.ws->tb);
+        fpos = stage + 32u * mx;
+        fq = reinterpret_cast<uint8_t *>(fpos + 32u * mx);
+    }
     const int n = n0 + n1;   // the plus list, then the minus list (one may be empty)
 #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -2208,7 +2215,7 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_
         const int s = (i < n0) ? 0 : 1;
         const uint32_t QPos = valid ? (s ? list1[i - n0] : list0[i]) : 0u;
         uint32_t len = 0;
-        if (valid) len = row_walk_lane(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), stage + 32 * URMB_LANE);
+        if (valid) len = row_walk_lane(E, m_slot(E, m, s, QPos), m_tally(m, s, QPos), m_pos(m, s, QPos), stage + mx * URMB_LANE);
         uint32_t off = len;   // exclusive prefix sum over lanes
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(FULL, off, d);
@@ -2220,7 +2227,7 @@ __device__ __noinline__ void rows_long_batch(const Env &E, Mate &m, const uint8_
         const int lp = min(max(n0 - i0, 0), 32);   // lanes [0, lp) hold plus rows
         const uint32_t nplus = (lp >= 32) ? total : __shfl_sync(FULL, off, lp);
         for (uint32_t k = 0; k < len; ++k) {
-            fpos[off + k] = stage[32 * URMB_LANE + k];
+            fpos[off + k] = stage[mx * URMB_LANE + k];
             fq[off + k] = (uint8_t)QPos;
         }
         __syncwarp();

@@ -74,7 +74,7 @@ EXPORTS = [
     "urmb_launch", "urmb_download", "urmb_timing_last", "urmb_launch_count", "urmb_mark", "urmb_mark_elapsed",
     "urmb_build_index_device", "urmb_build_last_error", "urmb_peak_gather", "urmb_peak_alu",
     "urmb_host_alloc", "urmb_host_free", "urmb_reserve", "urmb_second_hits", "urmb_overflow_count",
-    "urmb_unsupported_count",
+    "urmb_unsupported_count", "urmb_first_look_count",
 ]
 
 _lib = None
@@ -118,6 +118,7 @@ def lib():
         L.urmb_reserve.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
         L.urmb_second_hits.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
         L.urmb_overflow_count.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.urmb_first_look_count.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.urmb_unsupported_count.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.urmb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
         L.urmb_host_free.argtypes = [vp]
@@ -310,6 +311,12 @@ class Context:
         """(reads of the slot's last batch, reads over all batches) not searched: longer than URMB_MAX_READ_LEN (flags bit 6)."""
         last, total = C.c_uint32(), C.c_uint64()
         _check(lib().urmb_unsupported_count(self.c, slot, C.byref(last), C.byref(total)), self.c)
+        return int(last.value), int(total.value)
+
+    def first_look_count(self, slot=0):
+        """(pairs of the slot's last batch, pairs over all batches) finished by the probe kernel's first look."""
+        last, total = C.c_uint32(), C.c_uint64()
+        _check(lib().urmb_first_look_count(self.c, slot, C.byref(last), C.byref(total)), self.c)
         return int(last.value), int(total.value)
 
     def launch_count(self):

@@ -504,7 +504,11 @@ __device__ __forceinline__ void probe_read(const DevIndex &ix, const DevParams &
             const uint32_t rr = r0 + k, s = rr >= rps, q = (rr - s * rps) * 32 + lane;
             w0[k] = w1[k] = 0;
             if (rr < nrounds && q < QWC) {
+#ifdef URMB_PROBE_SLOT_CALL
+                const uint64_t slot = slot_of_s(ix, rv, (int)s, q);
+#else
                 const uint64_t slot = slot_of(ix, rv, (int)s, q);
+#endif
                 if (slot != ~0ull) {
                     const uint64_t a = 5ull * slot;   // record at byte offset 5*slot: two aligned words cover it
                     const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blob + (a & ~3ull));
@@ -583,6 +587,7 @@ __global__ void __launch_bounds__(256, URMB_PROBE_LB) probe_kernel(DevIndex ix, 
 // only has to be sound, never complete.
 constexpr int kLookK = 8;   // seed-iterator steps of the first look: 2 mates x 2 strands x kLookK = one probe per lane
 __device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+#pragma unroll 1
     for (int i = 0; i < n; ++i) m &= m - 1;
     return __ffs(m) - 1;
 }
@@ -609,9 +614,9 @@ __device__ __noinline__ bool pair_first_look(const DevIndex &ix, const DevParams
     const bool valid = k < QWC;
     const uint32_t QPos = valid ? (k * PRIME_STRIDE) % QWC : 0u;
     uint32_t tally = T_FREE, pos = 0;
-    if (valid) {
-        const uint64_t slot = slot_of(ix, rv, sgn, QPos);
-        if (slot != ~0ull) load_blob<false>(ix.blob, slot, tally, pos);
+    if (valid) {   // out-of-line forms: the probe kernels are instruction-fetch sensitive (profiles/r05i)
+        const uint64_t slot = slot_of_s(ix, rv, sgn, QPos);
+        if (slot != ~0ull) load_blob_s(ix.blob, slot, tally, pos);
     }
     const bool b1 = tally == T_BOTH1;
     const uint32_t diag = pos - QPos;

@@ -441,7 +441,7 @@ SURVEY_WORK = {"probes": 157.0, "row_hops": 50.0, "row_hops_long": 25.0, "compar
 # kernel class -> (kernel name(s), kind); kind "gather": HBM random gathers, "dp": dynamic programming, "state": replay of
 # the order-dependent bookkeeping over data the gather kernels produced
 KCLASS = {
-    "probe": ("probe_kernel", "gather"), "pair": ("pair_kernel | seed_kernel_se", "state"),
+    "probe": ("probe_pair_kernel | probe_kernel", "gather"), "pair": ("pair_kernel | seed_kernel_se", "state"),
     "align_a": ("align_kernel_a | align_kernel_se3", "dp"), "rows": ("rows_kernel | rows_kernel_se", "gather"),
     "rows_long": ("rows_long_kernel | rows_long_kernel_se", "gather"), "align_c": ("align_kernel_c | align_kernel_se6", "dp"),
     "finish": ("finish_kernel", "state"), "rescue": ("rescue_scan_kernel", "gather"), "rescue_last": ("rescue_last_kernel", "dp"),
@@ -493,7 +493,10 @@ def time_steps(ctx, batches, paired, steps, warmup, D, device):
     for s in range(min(NSLOTS, steps)):   # drain (results are not looked at here)
         ctx.download(s)
         ctx.wait(s, B, paired)
-    return {"dev_ms": dev_ms, "wall_ms": 1e3 * t_wall, "gpu_launches": gpu_launches, "kernel_ms": kms, "kernel_launches": klaunch}
+    # pairs the probe kernel's first look finished (seed-loop exit of Search4/5) in the last batch of slot 0
+    first_look = ctx.first_look_count(0)[0] / float(B) if paired else 0.0
+    return {"dev_ms": dev_ms, "wall_ms": 1e3 * t_wall, "gpu_launches": gpu_launches, "kernel_ms": kms, "kernel_launches": klaunch,
+            "first_look_frac": first_look}
 
 
 def time_e2e(ctx, batches, paired, steps, D, device):
@@ -518,7 +521,7 @@ def time_e2e(ctx, batches, paired, steps, D, device):
     return time.perf_counter() - t0, d2h
 
 
-def rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traffic):
+def rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traffic, first_look=0.0):
     """One object per kernel class that ran: share of the step, average launch duration, and the roofline that bounds it
     (HBM bytes for the gather kernels, int32 ALU ops for the DP kernels)."""
     peak = peaks.get("hbm_gbs")
@@ -555,10 +558,13 @@ def rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traf
         out[cls] = o
     roof_gather, roof_alu = None, None
     if micro:
-        acc = 2.0 * qwc * reads_per_step / max(kms.get("probe", 0.0) / 1e3, 1e-9) / 1e9
+        # slot probes the kernel makes per read: every k-mer of both strands, except for the pairs its first look finishes
+        # (16 probes per read there, which the other pairs make on top)
+        apr = 2.0 * qwc * (1.0 - first_look) + (16.0 if rpu == 2 and first_look > 0 else 0.0)
+        acc = apr * reads_per_step / max(kms.get("probe", 0.0) / 1e3, 1e-9) / 1e9
         pk = micro["gather_4B"]["gaccess_per_s"]
-        roof_gather = {"kernel": "probe_kernel", "bound": "hbm random sector gather", "achieved": acc, "peak": pk,
-                       "unit": "G accesses/s", "frac": acc / pk, "accesses_per_read": 2 * qwc,
+        roof_gather = {"kernel": "probe_pair_kernel | probe_kernel", "bound": "hbm random sector gather", "achieved": acc, "peak": pk,
+                       "unit": "G accesses/s", "frac": acc / pk, "accesses_per_read": apr,
                        "peak_source": "urmb_peak_gather: random 4-byte reads at 32-byte-aligned addresses over the blob",
                        "peak_16B_gaccess_per_s": micro["gather_16B"]["gaccess_per_s"]}
         dp_classes = [c for c in ("align_a", "align_c", "rescue_dp") if c in kms]
@@ -785,7 +791,8 @@ def main():
                     "value": r_ * units * args.config_steps / (t["dev_ms"] / 1e3), "unit": "reads/s",
                     "ms_per_step": t["dev_ms"] / args.config_steps,
                     "e2e": {"value": r_ * units * args.config_steps / te, "unit": "reads/s"},
-                    "kernel_ms_per_step": t["kernel_ms"], "kernel_launches_per_step": t["kernel_launches"]}
+                    "kernel_ms_per_step": t["kernel_ms"], "kernel_launches_per_step": t["kernel_launches"],
+                    "first_look_frac": t["first_look_frac"]}
                 cfg_batches[ec["key"]] = bt[0]
                 log(f"config {ec['key']}: {configs[ec['key']]['value'] / 1e6:.2f} M reads/s kernels "
                     f"({t['dev_ms'] / args.config_steps:.1f} ms per {r_ * units} reads; set-up {time.time() - t0:.1f}s); "
@@ -896,7 +903,8 @@ def main():
         reads_per_step = rpu * B
         traffic = load_json(os.path.join("profiles", "ncu_traffic.json"))   # dram bytes per pair from ncu --set full
         W = meta["word_length"]
-        per_kernel, roof_gather, roof_alu = rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traffic)
+        per_kernel, roof_gather, roof_alu = rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traffic,
+                                                      tv["first_look_frac"])
         # `roofline` = the largest kernel class of the step over ALL classes (the side-stream rescue kernels included)
         dominant = max(per_kernel, key=lambda c: per_kernel[c]["ms_per_step"])
         for key, c in configs.items():
@@ -917,6 +925,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_per_step,
                     "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": 1e3 * t_e2e_max / args.steps},
             "gpu_launches": tv["gpu_launches"],
+            "first_look_frac": tv["first_look_frac"],   # pairs finished by the probe kernel's first look (seed-loop exit, search2m4.cpp:79-142)
             "clocks": clocks,
             "roofline": dict(per_kernel[dominant], kernel_class=dominant),
             "roofline_probe": per_kernel.get("probe"),

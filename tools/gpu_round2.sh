@@ -16,7 +16,7 @@ WHAT=${*:-tests bench}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/smi.txt 2>&1
-KREGEX='probe_kernel|seed_kernel|pair_kernel|align_kernel|rows_kernel|rows_long_kernel|finish_kernel|rescue'
+KREGEX='probe_pair_kernel|probe_kernel|seed_kernel|pair_kernel|align_kernel|rows_kernel|rows_long_kernel|finish_kernel|rescue'
 for w in $WHAT; do
 case $w in
 tests)
@@ -51,7 +51,7 @@ ncufull)
   # steps and capture one launch of every class (finish_kernel is excluded: 0.3 ms)
   # per step and in launch order: probe, pair, align_a, rows, rows_long, align_c, then six rounds of (rescue_scan, rescue_dp):
   # 18 matching launches; three warm-up steps are skipped, then the six main kernels and the first rescue round are captured
-  NK=${NCU_KERNELS:-'probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue_scan_kernel|rescue_dp_kernel'}
+  NK=${NCU_KERNELS:-'probe_pair_kernel|probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue_scan_kernel|rescue_dp_kernel'}
   NSKIP=${NCU_SKIP:-54}
   NCOUNT=${NCU_COUNT:-8}
   timeout 1700 ncu --set full --clock-control none --import-source on -k regex:"$NK" -s $NSKIP -c $NCOUNT -f -o $OUT/${NCU_OUT:-full} \

@@ -275,6 +275,7 @@ extern "C" const char *urmb_last_error(const urmb_ctx *c) {
     return g_last_error.c_str();
 }
 
+static int ctx_init(urmb_ctx *c, int device);
 extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out) {
     if (!out) return URMB_E_ARG;
     *out = nullptr;
@@ -292,6 +293,16 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
     if (c->params.method != 7) c->params.method = 6;
     c->P = make_params(c->params);
     if (c->P.R > 12) { delete c; set_global_error("band radius > 12 unsupported"); return URMB_E_UNSUPPORTED; }
+    const int rc = ctx_init(c, device);
+    if (rc != URMB_OK) {   // the message is in the global error; streams, events and buffers created so far are released
+        urmb_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return URMB_OK;
+}
+
+static int ctx_init(urmb_ctx *c, int device) {
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -329,7 +340,6 @@ extern "C" int urmb_ctx_create(int device, const urmb_params *p, urmb_ctx **out)
         CK(cudaEventCreateWithFlags(&s.ev_side, cudaEventDisableTiming));
         CK(cudaHostAlloc(&s.h_counters, CT_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
     }
-    *out = c;
     return URMB_OK;
 }
 
@@ -449,7 +459,16 @@ static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n, c
     nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt);
     if (getenv("URMB_LOAD_THREADS")) nt = (unsigned)std::max(1, atoi(getenv("URMB_LOAD_THREADS")));
     uint8_t *stage[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2], evc;
+    cudaEvent_t ev[2] = {nullptr, nullptr}, evc = nullptr;
+    struct Release {   // every early return below releases the staging buffers and events
+        uint8_t **stage; cudaEvent_t *ev, *evc;
+        ~Release() {
+            cudaFreeHost(stage[0]); cudaFreeHost(stage[1]);
+            if (ev[0]) cudaEventDestroy(ev[0]);
+            if (ev[1]) cudaEventDestroy(ev[1]);
+            if (*evc) cudaEventDestroy(*evc);
+        }
+    } release{stage, ev, &evc};
     CK(cudaSetDevice(c->device));
     CK(cudaHostAlloc(&stage[0], CH, cudaHostAllocPortable));
     CK(cudaHostAlloc(&stage[1], CH, cudaHostAllocPortable));
@@ -481,11 +500,6 @@ static int upload_region(urmb_ctx *c, void *dst, const uint8_t *src, size_t n, c
     }
     CK(cudaStreamSynchronize(c->compute));
     if (fan) for (int g = 1; g < fan->n; ++g) CK(cudaStreamSynchronize(fan->streams[g]));
-    cudaFreeHost(stage[0]);
-    cudaFreeHost(stage[1]);
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
-    cudaEventDestroy(evc);
     return URMB_OK;
 }
 
@@ -1180,6 +1194,7 @@ extern "C" int urmb_timing_last(urmb_ctx *c, int si, urmb_timing *t) {
     Slot &s = c->slots[si];
     memset(t, 0, sizeof *t);
     if (!s.launched) return fail(c, URMB_E_ARG, "slot not launched");
+    CK(cudaSetDevice(c->device));   // a process that drives several contexts may have another device current
     CK(cudaEventSynchronize(s.ev_k2));
     CK(cudaEventSynchronize(s.ev_rescue));
     cudaEventElapsedTime(&t->probe_ms, s.ev_k0, s.ev_k1);

@@ -53,7 +53,8 @@ struct BuildArgs {
     uint8_t *qzero;         // bit s: q(s) == 0, nothing is carried from slot s to slot s+1 (segment border)
     int64_t *blockA, *blockB;   // per scan block: composite f(q) = max(A, q + B) of its slots
     int64_t *blockQ;        // q entering each scan block
-    uint32_t *errors;       // [0] segments handed to the repair pass, [1] pool overflow, [2] truncated lists / repair gave up
+    uint32_t *errors;       // [0] segments handed to the repair pass, [1] pool overflow, [2] truncated lists / repair gave up,
+                            // [3] segments beyond the capacity of the repair list (the blob is then not valid either)
     uint64_t *flagged;      // start slots of the segments handed to the repair pass
     uint32_t flagged_cap;
 };
@@ -369,7 +370,7 @@ __device__ __forceinline__ uint64_t next_slot(const BuildArgs &a, uint64_t s) { 
 __device__ __forceinline__ void flag_segment(const BuildArgs &a, uint64_t s) {
     const uint32_t i = atomicAdd(a.errors, 1u);
     if (i < a.flagged_cap) a.flagged[i] = s;
-    else atomicAdd(a.errors + 2, 1u);
+    else atomicAdd(a.errors + 3, 1u);   // flag buffer full: not a truncation -- its own count and message
 }
 
 // segment: thread s owns the segment that starts at s when s has overflow elements and nothing is carried into s.
@@ -588,7 +589,7 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
     BCK(cudaMalloc(&a.blockB, (nblocks + 1) * 8));
     BCK(cudaMalloc(&a.blockQ, (nblocks + 1) * 8));
     BCK(cudaMalloc(&a.errors, 16));
-    a.flagged_cap = 1u << 16;
+    a.flagged_cap = 1u << 18;   // appended in nearly increasing slot order, so the repair pass's insertion sort stays cheap
     BCK(cudaMalloc(&a.flagged, (size_t)a.flagged_cap * 8));
     BCK(cudaMemset(a.cntP, 0, cwords * 4));
     BCK(cudaMemset(a.cntM, 0, cwords * 4));
@@ -626,6 +627,11 @@ extern "C" int urmb_build_index_device(const void *d_seq, uint64_t seq_data_size
     cudaFree(a.qzero); cudaFree(a.blockA); cudaFree(a.blockB); cudaFree(a.blockQ); cudaFree(a.errors); cudaFree(a.flagged); cudaFree(a.pool);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (herr[1]) { g_build_err = "pool overflow (internal error)"; return URMB_E_OVERFLOW; }
+    if (herr[3]) {   // a very dense table (one segment in ten needs the sequential repair pass at load factor 0.95)
+        g_build_err = std::to_string(a.flagged_cap + herr[3]) + " segments need the sequential repair pass (more than its list of " +
+                      std::to_string(a.flagged_cap) + " holds: dense table)";
+        return URMB_E_OVERFLOW;
+    }
     return URMB_OK;
 fail:
     cudaFree(a.cntP); cudaFree(a.cntM); cudaFree(a.fill); cudaFree(a.base); cudaFree(a.blocksum);

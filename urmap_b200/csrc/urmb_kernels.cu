@@ -1972,10 +1972,11 @@ __device__ __noinline__ int align_hsp(const Env &E, Mate &m, int HSPIndex) {
 }
 
 // State1::ExtendScan, extendscan.cpp:51-187 (returns hit index or -1). Uniform arguments.
-__device__ __noinline__ int extend_scan(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus) {
-    if (SeedPosDB < SeedPosQ) return -1;
+// The order-dependent half of ExtendScan from the packed pure result x (pure_ext with LeftCountsPen = false: the left walk
+// adds no penalty, quirk 5; EXT_NONE when the diagonal starts before the genome).
+__device__ __noinline__ int extend_scan_apply(const Env &E, Mate &m, uint32_t SeedPosQ, uint32_t SeedPosDB, bool Plus, uint32_t x) {
+    if (x == EXT_NONE) return -1;
     const uint32_t DBLo = SeedPosDB - SeedPosQ;
-    const uint32_t x = pure_ext(E.ix, E.P, m.rv, Plus, SeedPosQ, SeedPosDB, false, m.MaxPenalty);   // left walk adds no penalty (quirk 5)
     if (ext_nmis(x) * -E.P.MM > m.MaxPenalty) return -1;
     const int Best = ext_best(x), Start = ext_start(x), End = ext_end(x);
     const int MinHSPScore = (int)E.ix.word_len * 2;
@@ -2498,16 +2499,34 @@ __device__ __noinline__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, ui
     const uint8_t *T = E.ix.seq + DBLo;
     if (DBSegLength < W) return;
     const uint32_t nwords = DBSegLength - W + 1;
+    // The window's k-mers come from the 2-bit packed genome (two 64-bit loads and a funnel shift instead of W byte loads
+    // and letter tests) unless the window touches a byte that is not exactly ACGT (coarse exception bitmap): then the
+    // bytes decide, letter by letter, as g_CharToLetterNucleo does (scanslots.cpp:27-45).
+    bool bytes = true;   // some byte of the window is not exactly ACGT (or the bitmap is switched off)
+    if (!(E.P.flags & 32u)) {
+        bytes = false;
+        for (uint32_t cb = DBLo >> kCoarseShift; cb <= (DBLo + DBSegLength - 1) >> kCoarseShift; ++cb)
+            bytes = bytes || ((__ldg(E.ix.seqc + (cb >> 5)) >> (cb & 31)) & 1u);
+    }
+    const uint32_t wshift = 64 - 2 * W;
     for (uint32_t p0 = 0; p0 < nwords; p0 += 32) {
         uint32_t p = p0 + URMB_LANE;   // window word start
         uint32_t hitmask = 0;
         if (p < nwords) {
             uint64_t word = 0;
             uint32_t bad = 0;
-            for (uint32_t t = 0; t < W; ++t) {
-                uint32_t l = letter_of(__ldg(T + p + t));
-                bad |= l & 0x80u;
-                word = (word << 2) | (l & 3u);
+            if (bytes) {
+                for (uint32_t t = 0; t < W; ++t) {
+                    uint32_t l = letter_of(__ldg(T + p + t));
+                    bad |= l & 0x80u;
+                    word = (word << 2) | (l & 3u);
+                }
+            } else {
+                const uint32_t g = DBLo + p, off = 2 * (g & 31u);
+                const uint64_t *pw = E.ix.seq2 + (g >> 5);
+                const uint64_t a = __ldg(pw), b = __ldg(pw + 1);
+                const uint64_t hi = off ? ((a << off) | (b >> (64 - off))) : a;
+                word = hi >> wshift;
             }
             if (!bad) {
                 uint64_t slot = mod_slots(murmur64(word & E.ix.shift_mask), E.ix.slot_count, E.ix.magic);
@@ -2516,12 +2535,26 @@ __device__ __noinline__ void scan_slots(const Env &E, Mate &m, uint32_t DBLo, ui
             }
         }
         uint32_t any = __ballot_sync(FULL, hitmask != 0);
+        if (!any) continue;
+        // The pure halves of this round's ExtendScan calls, one match per lane (a tandem-repeat window matches at every
+        // period: the uniform form computed one extension per call on all 32 lanes).  The penalty bound only falls while
+        // the window is scanned, so the bound of now is valid for every call of the round.
+        uint32_t xs[SCANK];
+#pragma unroll
+        for (uint32_t k = 0; k < SCANK; ++k) {
+            xs[k] = EXT_NONE;
+            const bool mine = (hitmask >> k) & 1u;
+            if (__any_sync(FULL, mine) && mine) xs[k] = pure_ext(E.ix, E.P, m.rv, Plus, qpos[k], DBLo + p, false, m.MaxPenalty);
+        }
         while (any) {
             int bit = __ffs(any) - 1;
             any &= any - 1;
             uint32_t hm = __shfl_sync(FULL, hitmask, bit);
-            for (uint32_t k = 0; k < SCANK; ++k)
-                if (hm >> k & 1u) extend_scan(E, m, qpos[k], DBLo + p0 + bit, Plus);
+#pragma unroll
+            for (uint32_t k = 0; k < SCANK; ++k) {
+                const uint32_t x = __shfl_sync(FULL, xs[k], bit);
+                if (hm >> k & 1u) extend_scan_apply(E, m, qpos[k], DBLo + p0 + bit, Plus, x);
+            }
         }
     }
 }

@@ -450,7 +450,7 @@ KCLASS = {
 }
 
 
-NSLOTS = 6   # batch slots the bench keeps in flight (the context has 8): the side-stream work of a batch -- mate rescue,
+NSLOTS = int(os.environ.get("URMB_BENCH_SLOTS", "6"))   # batch slots the bench keeps in flight (the context has 8): the side-stream work of a batch -- mate rescue,
              # big-capacity rerun of the few reads over a capacity, occasionally 100+ ms for one heavy pair -- then has
              # five steps to finish before its slot is needed again
 
@@ -508,17 +508,32 @@ def time_e2e(ctx, batches, paired, steps, D, device):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     d2h = 0
+    trace = [] if os.environ.get("URMB_E2E_TRACE") else None   # host seconds spent in every wait / submit call
     for k in range(steps):
         if k >= NSLOTS:
+            ta = time.perf_counter()
             r1, r2, runs = ctx.wait(k % NSLOTS, B, paired)
+            if trace is not None:
+                trace.append(("wait", k - NSLOTS, time.perf_counter() - ta))
             d2h += r1.nbytes + (r2.nbytes if r2 is not None else 0) + runs.nbytes + 16
         _, _, a1, a2, offs = batches[k % nb]
+        ta = time.perf_counter()
         ctx.submit(k % NSLOTS, a1, offs, a2, offs if paired else None)
+        if trace is not None:
+            trace.append(("submit", k, time.perf_counter() - ta))
     for k in range(max(0, steps - NSLOTS), steps):
+        ta = time.perf_counter()
         r1, r2, runs = ctx.wait(k % NSLOTS, B, paired)
+        if trace is not None:
+            trace.append(("wait", k, time.perf_counter() - ta))
         d2h += r1.nbytes + (r2.nbytes if r2 is not None else 0) + runs.nbytes + 16
     torch.cuda.synchronize()
-    return time.perf_counter() - t0, d2h
+    t1 = time.perf_counter() - t0
+    if trace is not None:
+        log("e2e trace (ms): " + " ".join(f"{w}{k}={1e3 * t:.1f}" for w, k, t in trace))
+        tm = ctx.timing((steps - 1) % NSLOTS)
+        log(f"e2e last batch: h2d {tm['h2d_ms']:.2f} ms, d2h {tm['d2h_ms']:.2f} ms (copy engine time of one batch)")
+    return t1, d2h
 
 
 def rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traffic, first_look=0.0):

@@ -123,6 +123,8 @@ static DevParams emu_make_params(const urmb_params &p) {  // same table as urmb_
     else if (p.pe_method == 5) P.R = 4;
     P.flags = 0;
     if (const char *f = getenv("URMB_FLAGS")) P.flags = (uint32_t)strtoul(f, nullptr, 0);
+    P.rescue_rounds = 0;
+    if (const char *f = getenv("URMB_RESCUE_ROUNDS")) P.rescue_rounds = std::min(std::max(atoi(f), 0), (int)kRescueRounds);
     return P;
 }
 

@@ -62,12 +62,14 @@ def test_emulated_pe(oracle, golden_oix, golden_dir, pe_method):
     _same(np.concatenate([r1, r2]), uo, re_, ue)
 
 
-@pytest.mark.parametrize("cap", [0, 1000])
-def test_emulated_rescue_rounds(oracle, golden_oix, golden_dir, cap, monkeypatch):
-    """Mate rescue continued from the saved states in rounds of (window scans, full-window DPs) against the legacy
-    kernel that searches the pair again from scratch (rescue pool capacity 0): both equal the oracle."""
+@pytest.mark.parametrize("cap,rounds", [(0, 0), (1000, 0), (1000, 2), (1000, 6)])
+def test_emulated_rescue_rounds(oracle, golden_oix, golden_dir, cap, rounds, monkeypatch):
+    """Mate rescue continued from the saved states -- in place (the default), or in rounds of (window scans, batched
+    full-window DPs) with a last round for the stragglers (URMB_RESCUE_ROUNDS) -- against the legacy kernel that searches the
+    pair again from scratch (rescue pool capacity 0): all equal the oracle."""
     import emu_py
     monkeypatch.setenv("URMB_EMU_RESCUE_CAP", str(cap))
+    monkeypatch.setenv("URMB_RESCUE_ROUNDS", str(rounds))
     b1 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_1.fq"))
     b2 = oracle.ReadBatch.from_fastq(os.path.join(golden_dir, "pe_2.fq"))
     sel = np.r_[255:270, 390:430]   # 5 % reads and damaged-mate pairs
@@ -86,7 +88,8 @@ def test_emulated_rescue_rounds(oracle, golden_oix, golden_dir, cap, monkeypatch
     re_, ue, cnt = emu_py.emu_map(golden_oix, oracle.RESULT_DTYPE, seqs, offs, len(sel), True)
     assert cnt[1] == 0 and cnt[2] > 20              # no overflow; pairs that needed mate rescue
     if cap:
-        assert cnt[5] == 0 and cnt[6] > 10          # nothing left to the legacy kernel; DPs run by the rounds
+        assert cnt[5] == 0                          # nothing left to the legacy kernel
+        assert (cnt[6] > 10) == (rounds > 0)        # DPs run by the rounds' DP kernel (in place otherwise)
     else:
         assert cnt[5] == cnt[2] and cnt[6] == 0
     _same(np.concatenate([r1, r2]), uo, re_, ue)

@@ -348,7 +348,8 @@ def test_big_capacity_rerun_and_legacy_rescue(eng, oracle, mid_env):
     in stream behind the mate rescue (URMB_FLAGS bit 8 forces it for every fifth read) or, for what is left, from the host
     in urmb_wait (URMB_FORCE_RERUN forces it for every third unit): the results must not change (SE and PE, path runs and
     second hits included).
-    The legacy mate-rescue kernel (no rescue pool) must agree with the rescue rounds as well."""
+    The legacy mate-rescue kernel (no rescue pool) and the rescue in rounds of window scans and batched full-window DPs
+    (URMB_RESCUE_ROUNDS; the default runs the DPs in place) must agree as well."""
     g, oix, hix = mid_env
     r1, r2, _ = synth.sim_pe(g, 5000, 150, 0.04, 0.006, seed=21)
     r2 = r2.copy()
@@ -357,7 +358,7 @@ def test_big_capacity_rerun_and_legacy_rescue(eng, oracle, mid_env):
     o1, o2, uo = oracle.map_pe(oix, b1, b2, threads=os.cpu_count())
     s1, us = oracle.map_se(oix, b1, threads=os.cpu_count())
     for env in ({"URMB_FORCE_RERUN": "3"}, {"URMB_FLAGS": "256"}, {"URMB_FLAGS": "256", "URMB_RESCUE_INLINE": "1"},
-                {"URMB_RESCUE_LEGACY": "1"}):
+                {"URMB_RESCUE_LEGACY": "1"}, {"URMB_RESCUE_ROUNDS": "2"}, {"URMB_RESCUE_ROUNDS": "6"}):
         ctx = _ctx_with_env(eng, hix, env, want_second=True)
         g1, g2, ug = ctx.map_pe(b1.seqs, b1.offs, b2.seqs, b2.offs)
         assert_same(np.concatenate([o1, o2]), uo, np.concatenate([g1, g2]), ug)

@@ -10,6 +10,7 @@
 #   ncufull    one `ncu --set full` capture of every kernel class of one step (CSV exports made on the box)
 #   sanitize   compute-sanitizer memcheck + racecheck on the golden sets
 #   ab         per-kernel step times of the current build (tools/step_sweep.py)
+#   tmpfs      threads filling a fresh file in /dev/shm (the ceiling of the SAM sink on this box)
 #   cliscale   BASELINE's full size through the drop-in next to the reference binary (tools/cli_scale.py, 10 M pairs)
 TAG=${1:-run}; shift
 WHAT=${*:-tests bench}
@@ -76,6 +77,11 @@ sanitize)
 cliscale)
   timeout 1700 python tools/cli_scale.py --pairs ${CLI_PAIRS:-10000000} --tabbedout > $OUT/cli_scale.json 2> $OUT/cli_scale.log; echo "cli_scale exit $?"
   tail -3 $OUT/cli_scale.log; head -c 1500 $OUT/cli_scale.json; echo ;;
+tmpfs)
+  # what the SAM sink can reach on this box: threads filling a fresh 4 GiB file in /dev/shm (tools/tmpfs_write_bench.cpp)
+  g++ -O2 -pthread -o /tmp/tmpfs_write_bench tools/tmpfs_write_bench.cpp
+  for m in 0 2 1 3; do for t in 1 4 8 16; do /tmp/tmpfs_write_bench /dev/shm/urmb_wbtest $m $t 4; done; done > $OUT/tmpfs_write_bench.log 2>&1
+  cat $OUT/tmpfs_write_bench.log ;;
 ab)
   timeout 900 python tools/step_sweep.py > $OUT/step_sweep.log 2>&1; echo "step_sweep exit $?"; tail -12 $OUT/step_sweep.log ;;
 esac

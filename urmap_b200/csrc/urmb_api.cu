@@ -267,6 +267,8 @@ static DevParams make_params(const urmb_params &p) {  // State1::SetMethod, stat
     else if (p.pe_method == 5) P.R = 4;   // map2.cpp:17-21
     P.flags = 0;       // URMB_FLAGS: see DevParams::flags
     if (const char *f = getenv("URMB_FLAGS")) P.flags = (uint32_t)strtoul(f, nullptr, 0);
+    P.rescue_rounds = 0;
+    if (const char *f = getenv("URMB_RESCUE_ROUNDS")) P.rescue_rounds = std::min(std::max(atoi(f), 0), (int)kRescueRounds);
     return P;
 }
 
@@ -321,7 +323,7 @@ static int ctx_init(urmb_ctx *c, int device) {
     c->n_scratch_warps = max_search_warps(c->sm_count);
     // The rescue kernel is a queue of few, long work items that runs beside the next batch: a small persistent grid
     // (one block per SM) takes few registers away from the main kernels and still drains the queue in time.
-    c->n_rescue_warps = c->sm_count * 12;
+    c->n_rescue_warps = c->sm_count * 16;   // four resident blocks of the last-round kernel per SM (profiles/r06h)
     if (const char *f = getenv("URMB_RESCUE_WARPS")) c->n_rescue_warps = std::max(4, atoi(f) & ~3);
     if (const char *f = getenv("URMB_RESCUE_INLINE")) c->rescue_inline = atoi(f) != 0;
     if (const char *f = getenv("URMB_CHUNK_PAIRS")) c->chunk_pairs = (uint32_t)std::max(1ul, strtoul(f, nullptr, 0));
@@ -330,7 +332,7 @@ static int ctx_init(urmb_ctx *c, int device) {
     c->no_rerun = getenv("URMB_NO_RERUN") != nullptr;
     for (auto &s : c->slots) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, prio_lo));
+        CK(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, getenv("URMB_RESCUE_PRIO_HI") ? prio_hi : prio_lo));
         for (cudaEvent_t *ev : {&s.ev_h2d0, &s.ev_h2d, &s.ev_k0, &s.ev_k1, &s.ev_k2, &s.ev_d2h, &s.ev_rescue}) CK(cudaEventCreate(ev));
         CK(cudaMalloc(&s.d_counters, CT_COUNT * sizeof(uint32_t)));
         CK(cudaMalloc(&s.d_ovf, kOvfCap * sizeof(uint32_t)));

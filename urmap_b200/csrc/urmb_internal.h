@@ -51,6 +51,9 @@ struct DevParams {  // State1::SetMethod constants, state1.cpp:147-183
     uint32_t flags;   // tuning switches (URMB_FLAGS): bit 5 = do not consult the coarse exception bitmap (seqc); bit 8 = test hook:
                       // every fifth read is treated as over a capacity (exercises the in-stream big-capacity rerun);
                       // bit 9 = no first look in the probe kernel (paired input)
+    int rescue_rounds; // mate rescue: rounds of (window scans, batched full-window DPs) before the last round that runs the DPs in
+                       // place.  0 by default (URMB_RESCUE_ROUNDS): every kernel of the chain has to wait for room on SMs the
+                       // main kernels of the following batches fill, so a short chain finishes a batch sooner (profiles/r06g)
 };
 
 struct DevBatch {
@@ -77,7 +80,8 @@ inline uint32_t view_stride_for(uint32_t seqcap) { return kViewHdr + seqcap; }
 
 // Device counters of one batch slot (u32 each).  CT_RUNS / CT_OVERFLOW / CT_*_TOTAL live for the whole batch; the
 // others are per chunk and are zeroed by the launcher between chunks.
-constexpr int kRescueRounds = 6;   // suspend-at-DP rounds of the mate rescue; a last round finishes the stragglers in place
+constexpr int kRescueRounds = 6;   // most suspend-at-DP rounds of the mate rescue (DevParams::rescue_rounds of them run; a last round
+                                   // finishes what is left in place)
 enum {
     CT_RUNS = 0,        // path runs used in DevOut::runs
     CT_OVERFLOW = 1,    // reads that exceeded a per-read capacity

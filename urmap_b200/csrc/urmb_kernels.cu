@@ -3730,12 +3730,13 @@ int launch_rescue(const DevIndex &ix, const DevParams &P, const DevBatch &b, con
     int e, n = 0;
     if (o.rpool && o.rescue_cap) {
         const uint32_t cap = b.n_units < o.rescue_cap ? b.n_units : o.rescue_cap;
-        for (int r = 0; r < kRescueRounds; ++r) {
+        const int rounds = P.rescue_rounds < 0 ? 0 : (P.rescue_rounds > kRescueRounds ? (int)kRescueRounds : P.rescue_rounds);
+        for (int r = 0; r < rounds; ++r) {
             URMB_TRY(launch_one(rescue_scan_kernel, 6, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, r));
             URMB_TRY(launch_one(rescue_dp_kernel, 8, tr, A, SmemPlan{1, 0, 1}, cap, R, stream, sm_count, nullptr, r));
         }
-        URMB_TRY(launch_one(rescue_last_kernel, 10, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, (int)kRescueRounds));
-        n += 2 * kRescueRounds + 1;
+        URMB_TRY(launch_one(rescue_last_kernel, 10, tr, A, SmemPlan{2, 0, 1}, cap, R, stream, sm_count, nullptr, rounds));
+        n += 2 * rounds + 1;
     }
     URMB_TRY(launch_one(rescue_kernel, 9, tr, A, SmemPlan{2, 1, 1}, o.rpool ? (b.n_units < (uint32_t)(4 * sm_count) ? b.n_units : (uint32_t)(4 * sm_count)) : b.n_units,
                         R, stream, sm_count, nullptr));

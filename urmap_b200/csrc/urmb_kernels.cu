@@ -470,7 +470,7 @@ __host__ __device__ inline size_t probe_smem_per_warp(uint32_t qcap, uint32_t se
     return ((kReadViewBytes + 2 * (size_t)seqcap + 2 * (size_t)qcap * 4 + 2 * (size_t)qcap * 2) + 15) & ~(size_t)15;
 }
 #ifndef URMB_PROBE_BATCH
-#define URMB_PROBE_BATCH 8
+#define URMB_PROBE_BATCH 4   // with the first look compiled in, 8 rounds unrolled cost more in instruction fetch than they hide (profiles/r06j)
 #endif
 #ifndef URMB_PROBE_LB
 #define URMB_PROBE_LB 3

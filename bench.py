@@ -555,6 +555,9 @@ def rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traf
         "align_c": (0.5 * dp_flank / 25.0 + RL, "genome windows of the flank DPs (cells / band width) + the read; DP kernel: see roofline_dp_alu"),
         "rescue": (algo.get("scan_calls", 0.0) * 1100.0, "scanned window bytes (1024 + 2 QL per scan)"),
         "rescue_dp": (algo.get("dp_cells_scan", 0.0) / max(RL, 1), "window bytes of the full-window DPs; DP kernel: see roofline_dp_alu"),
+        # the in-place mate rescue (URMB_RESCUE_ROUNDS=0, the default): window scans and full-window DPs in one kernel
+        "rescue_last": (algo.get("scan_calls", 0.0) * 1100.0 + algo.get("dp_cells_scan", 0.0) / max(RL, 1),
+                        "scanned window bytes (1024 + 2 QL per scan) + window bytes of the full-window DPs (run in place by the pair's warp)"),
     }
     out = {}
     for cls, ms in kms.items():
@@ -582,14 +585,18 @@ def rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traf
                        "unit": "G accesses/s", "frac": acc / pk, "accesses_per_read": apr,
                        "peak_source": "urmb_peak_gather: random 4-byte reads at 32-byte-aligned addresses over the blob",
                        "peak_16B_gaccess_per_s": micro["gather_16B"]["gaccess_per_s"]}
-        dp_classes = [c for c in ("align_a", "align_c", "rescue_dp") if c in kms]
-        if "rescue_dp" not in kms and "rescue" in kms:
-            dp_classes.append("rescue")   # a build whose rescue kernel does scan + DP in one kernel
-        align_ms = sum(kms[c] for c in dp_classes)
+        dp_classes = [c for c in ("align_a", "align_c", "rescue_dp") if c in kms and kms[c] > 0]
         cells = algo.get("dp_cells", 0.0) * reads_per_step
+        if "rescue_dp" not in dp_classes:
+            # the full-window DPs of the mate rescue run inside the in-place rescue kernel, whose time is mostly window scans:
+            # their cells are left out and the figure is that of the flank DPs alone
+            cells -= algo.get("dp_cells_scan", 0.0) * reads_per_step
+        align_ms = sum(kms[c] for c in dp_classes)
         if cells and align_ms > 0:
             ach = 16.0 * cells / (align_ms / 1e3) / 1e12
-            roof_alu = {"kernels": " + ".join(KCLASS[c][0] for c in dp_classes), "bound": "int32 alu",
+            roof_alu = {"kernels": " + ".join(KCLASS[c][0] for c in dp_classes),
+                        "cells": "flank DPs and batched rescue DPs" if "rescue_dp" in dp_classes else "flank DPs (rescue DPs run in place in rescue_last_kernel: not counted)",
+                        "bound": "int32 alu",
                         "achieved": ach, "peak": micro["alu"]["tops_per_s"], "unit": "Tops/s",
                         "frac": ach / micro["alu"]["tops_per_s"], "dp_cells_per_s": cells / (align_ms / 1e3),
                         "ops_per_cell": 16, "kernel_ms": align_ms,

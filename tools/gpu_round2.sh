@@ -30,7 +30,7 @@ tiny)
       > $OUT/bench_tiny.json 2> $OUT/bench_tiny.log; echo "tiny exit $?"
   tail -c 1500 $OUT/bench_tiny.log; head -c 600 $OUT/bench_tiny.json; echo ;;
 bench)
-  URMB_BENCH_UNMATCHED=$OUT/unmatched timeout 1700 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.log; echo "bench exit $?"
+  URMB_BENCH_UNMATCHED=$OUT/unmatched timeout 1700 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.log; echo "bench exit $?"
   tail -c 3000 $OUT/bench.log; head -c 1200 $OUT/bench.json; echo ;;
 benchq)
   timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-configs > $OUT/benchq.json 2> $OUT/benchq.log; echo "benchq exit $?"
@@ -50,11 +50,12 @@ launches)
 ncufull)
   # 250 k pairs per step = one chunk: every step launches each kernel class once, in a fixed order; skip the warm-up
   # steps and capture one launch of every class (finish_kernel is excluded: 0.3 ms)
-  # per step and in launch order: probe, pair, align_a, rows, rows_long, align_c, then six rounds of (rescue_scan, rescue_dp):
-  # 18 matching launches; three warm-up steps are skipped, then the six main kernels and the first rescue round are captured
-  NK=${NCU_KERNELS:-'probe_pair_kernel|probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue_scan_kernel|rescue_dp_kernel'}
-  NSKIP=${NCU_SKIP:-54}
-  NCOUNT=${NCU_COUNT:-8}
+  # per step and in launch order: probe_pair, pair, align_a, rows, rows_long, align_c, rescue_last (the in-place mate rescue):
+  # 7 matching launches; three warm-up steps and the first timed step are skipped, then one launch of every class is captured
+  # (URMB_RESCUE_ROUNDS=r adds r x (rescue_scan, rescue_dp) per step: set NCU_SKIP / NCU_COUNT accordingly)
+  NK=${NCU_KERNELS:-'probe_pair_kernel|probe_kernel|pair_kernel|align_kernel_a|align_kernel_c|rows_kernel|rows_long_kernel|rescue_last_kernel|rescue_scan_kernel|rescue_dp_kernel'}
+  NSKIP=${NCU_SKIP:-28}
+  NCOUNT=${NCU_COUNT:-7}
   timeout 1700 ncu --set full --clock-control none --import-source on -k regex:"$NK" -s $NSKIP -c $NCOUNT -f -o $OUT/${NCU_OUT:-full} \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs --pairs-per-step ${NCU_PAIRS:-250000} $NCU_BENCH_ARGS > $OUT/ncu_full.log 2>&1
   echo "ncu full exit $?"
@@ -66,7 +67,7 @@ ncufull)
 sanitize)
   timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_memcheck_smoke.log 2>&1
   echo "memcheck smoke exit $?"; tail -4 $OUT/sanitizer_memcheck_smoke.log
-  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "golden or big_capacity or dense_index" \
+  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -k "golden or big_capacity or dense_index or first_look or maxix" \
       > $OUT/sanitizer_memcheck_golden.log 2>&1
   echo "memcheck golden exit $?"; tail -4 $OUT/sanitizer_memcheck_golden.log
   URMB_FLAGS=256 timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python __graft_entry__.py smoke > $OUT/sanitizer_racecheck_smoke.log 2>&1

@@ -26,6 +26,6 @@ for r in rows:
         func = r[1] if len(r) > 1 else None
     elif r and r[0] == "Line No":
         cur = [r]
-    elif cur is not None and r and r[0].isdigit():
-        cur.append(r)
+    elif cur is not None and r and (r[0].isdigit() or (len(r) > 2 and r[2].startswith("0x"))):
+        cur.append(r)   # a source line, or one of the SASS instructions listed under it
 flush()

@@ -3049,6 +3049,7 @@ __device__ __noinline__ void save_mate(const Env &E, Mate &m, MateSave *dst) {
     // scratch -> pool never overlap: with __restrict__ the loads of a whole round are issued before its stores
     const MateScratch *__restrict__ g = m.g;
     MateScratch *__restrict__ d = &dst->s;
+#pragma unroll 1
     for (int i0 = 0; i0 < max(m.HitCount, m.HSPCount); i0 += 32) {
         const int i = i0 + URMB_LANE;
         const bool a = i < m.HitCount, c = i < m.HSPCount;
@@ -3061,8 +3062,10 @@ __device__ __noinline__ void save_mate(const Env &E, Mate &m, MateSave *dst) {
         if (a) { d->hit_pos[i] = hp; d->hit_score[i] = hs; d->hit_plus[i] = hl; d->hit_nruns[i] = hn; d->hit_roff[i] = hr; }
         if (c) { d->hsp_dbstart[i] = hd; d->hsp_qstart[i] = xq; d->hsp_len[i] = xl; d->hsp_score[i] = xs; d->hsp_flags[i] = xf; }
     }
+#pragma unroll 1
     for (int i = URMB_LANE; i < m.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
     if (!done)
+#pragma unroll 1
         for (int i0 = 0; i0 < max(m.nPend[0], m.nPend[1]); i0 += 32) {
             const int i = i0 + URMB_LANE;
             uint8_t p0 = 0, p1 = 0;
@@ -3122,6 +3125,7 @@ __device__ __noinline__ void copy_save(const Env &E, const MateSave *__restrict_
     const MateHdr h = src->h;
     const MateScratch *__restrict__ g = &src->s;
     MateScratch *__restrict__ d = &dst->s;
+#pragma unroll 1
     for (int i0 = 0; i0 < max(h.HitCount, h.HSPCount); i0 += 32) {
         const int i = i0 + URMB_LANE;
         if (i < h.HitCount) {
@@ -3133,6 +3137,7 @@ __device__ __noinline__ void copy_save(const Env &E, const MateSave *__restrict_
             d->hsp_score[i] = g->hsp_score[i]; d->hsp_flags[i] = g->hsp_flags[i];
         }
     }
+#pragma unroll 1
     for (int i = URMB_LANE; i < h.nRuns; i += 32) d->runs_pool[i] = g->runs_pool[i];
     if (URMB_LANE == 0) dst->h = h;
     __syncwarp();

@@ -269,3 +269,42 @@ def test_cli_two_gpus(cli, golden_dir, tmp_path, mode):
     assert r.returncode == 0, r.stderr
     strip = lambda p: [l for l in open(p, "rb").read().split(b"\n") if not l.startswith(b"@PG")]
     assert strip(out) == strip(one)   # same records in the same order
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("contigs", [1, 3])
+def test_cli_config1_gate(cli, oracle, tmp_path, contigs):
+    """BASELINE.json configs[0] at its stated size: 5 000 000 bp of iid uniform ACGT (one contig, and the three-contig variant
+    that exercises the contig padding and SetMappedPos), 100 000 x 150 bp single-end reads with 1 % substitutions and 0.1 %
+    indels -- and the same number of read pairs.  The drop-in builds the index on the GPU (byte-identical to the reference's
+    file) and maps from FASTQ files; the reference binary (-threads 1: input order) writes the expected SAM files."""
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available")
+    g = synth.make_genome(5_000_000, n_contigs=contigs, seed=12345)
+    fa, ufi, mine = str(tmp_path / "ref.fa"), str(tmp_path / "ref.ufi"), str(tmp_path / "mine.ufi")
+    g.write_fasta(fa)
+    oracle.run_reference(["-make_ufi", fa, "-output", ufi])
+    r = run([cli, "-make_ufi", fa, "-output", mine, "-gpu_build", "-quiet"])
+    assert r.returncode == 0, r.stderr
+    assert open(mine, "rb").read() == open(ufi, "rb").read()
+    reads, names = synth.sim_se(g, 100_000, 150, 0.01, 0.001, seed=777)
+    fq = str(tmp_path / "se.fq")
+    synth.write_fastq(fq, reads, names)
+    want, got = str(tmp_path / "ref_se.sam"), str(tmp_path / "se.sam")
+    oracle.run_reference(["-map", fq, "-ufi", ufi, "-samout", want, "-threads", "1"])
+    r = run([cli, "-map", fq, "-ufi", mine, "-samout", got, "-quiet"])
+    assert r.returncode == 0, r.stderr
+    c = synth.compare_sam(want, got)
+    assert c["identical"] == c["total"] == 100_000 and c["header_equal"], c["diffs"][:5]
+    r1, r2, names = synth.sim_pe(g, 100_000, 150, 0.01, 0.001, seed=778)
+    f1, f2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+    synth.write_fastq(f1, r1, names, b"/1")
+    synth.write_fastq(f2, r2, names, b"/2")
+    want, got = str(tmp_path / "ref_pe.sam"), str(tmp_path / "pe.sam")
+    oracle.run_reference(["-map2", f1, "-reverse", f2, "-ufi", ufi, "-samout", want, "-threads", "1"])
+    r = run([cli, "-map2", f1, "-reverse", f2, "-ufi", mine, "-samout", got, "-quiet"])
+    assert r.returncode == 0, r.stderr
+    c = synth.compare_sam(want, got)
+    assert c["identical"] == c["total"] == 200_000 and c["header_equal"], c["diffs"][:5]

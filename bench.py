@@ -969,6 +969,7 @@ def main():
     ctx.close()
     if args.workdir.startswith("/dev/shm") and rank == 0 and not os.environ.get("URMB_KEEP_BENCH_DIR"):
         shutil.rmtree(args.workdir, ignore_errors=True)
+    D.finalize()
     return 0
 
 

@@ -77,3 +77,13 @@ def sum_over_ranks(x: float, device) -> float:
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def finalize():
+    """Tear the process group down at the end of a run (NCCL warns about leaked resources otherwise)."""
+    if dist.is_initialized():
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass

@@ -308,3 +308,59 @@ def test_cli_config1_gate(cli, oracle, tmp_path, contigs):
     assert r.returncode == 0, r.stderr
     c = synth.compare_sam(want, got)
     assert c["identical"] == c["total"] == 200_000 and c["header_equal"], c["diffs"][:5]
+
+
+@pytest.mark.gpu
+def test_cli_contig_end_overhang(cli, oracle, tmp_path):
+    """Pairs with a mate hanging 1 - 10 bases over either end of a contig: State1::SetMappedPos (state1.cpp:129-145) clears
+    the top hit of such a mate, and OutputTab2 sees that cleared state only when a SAM file is written first
+    (output2.cpp:10-16): the -tabbedout file differs with and without -samout.  Both forms, and the SAM file, equal the
+    reference binary's."""
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available")
+    import numpy as np
+    g = synth.make_genome(600_000, n_contigs=3, seed=99)
+    fa, ufi = str(tmp_path / "ref.fa"), str(tmp_path / "ref.ufi")
+    g.write_fasta(fa)
+    oracle.run_reference(["-make_ufi", fa, "-output", ufi])
+    rng = np.random.default_rng(5)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    rc = lambda x: comp[x[::-1]]
+    r1, r2, names = [], [], []
+    for c in range(3):
+        off, L = int(g.offs[c]), int(g.lens[c])
+        for hang in range(1, 11):
+            for side in (0, 1):
+                if c == 2 and side == 0:
+                    continue   # past the end of the LAST contig the reference compares against bytes beyond its sequence buffer
+                               # (extendpen.cpp:29-52 has no bound): undefined there, zero padding here
+                tail = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=hang)
+                if side == 0:   # right end of the contig: the reverse mate hangs over
+                    a, b = g.asc[off + L - 450: off + L - 300].copy(), rc(np.concatenate([g.asc[off + L - (150 - hang): off + L], tail]))
+                else:           # left end: the forward mate starts before the contig
+                    a, b = np.concatenate([tail, g.asc[off: off + 150 - hang]]), rc(g.asc[off + 300: off + 450].copy())
+                if len(names) % 2:
+                    a, b = b, a
+                r1.append(a)
+                r2.append(b)
+                names.append(b"ov%d_c%d_h%d_s%d" % (len(names), c, hang, side))
+    f1, f2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+    synth.write_fastq(f1, np.array(r1), names, b"/1")
+    synth.write_fastq(f2, np.array(r2), names, b"/2")
+    args = ["-map2", f1, "-reverse", f2, "-ufi", ufi]
+    p = lambda n: str(tmp_path / n)
+    oracle.run_reference(args + ["-threads", "1", "-samout", p("ref.sam"), "-tabbedout", p("ref_a.tab")])
+    oracle.run_reference(args + ["-threads", "1", "-tabbedout", p("ref_b.tab")])
+    assert open(p("ref_a.tab"), "rb").read() != open(p("ref_b.tab"), "rb").read()   # the case is what it claims to be
+    r = run([cli] + args + ["-samout", p("o.sam"), "-tabbedout", p("o_a.tab"), "-batch", "16", "-quiet"])
+    assert r.returncode == 0, r.stderr
+    r = run([cli] + args + ["-tabbedout", p("o_b.tab"), "-batch", "16", "-quiet"])
+    assert r.returncode == 0, r.stderr
+    assert open(p("o_a.tab"), "rb").read() == open(p("ref_a.tab"), "rb").read()
+    assert open(p("o_b.tab"), "rb").read() == open(p("ref_b.tab"), "rb").read()
+    c = synth.compare_sam(p("ref.sam"), p("o.sam"))
+    assert c["identical"] == c["total"] == 2 * len(names) and c["header_equal"], c["diffs"][:5]

@@ -147,9 +147,20 @@ def main():
                                capture_output=True, text=True)
             out["sam_identity_vs_reference"] = json.loads(d.stdout) if d.returncode == 0 else {"error": d.stderr[-300:]}
             if a.tabbedout:
-                d = subprocess.run([samdiff, os.path.join(a.workdir, "ref.tab"), os.path.join(a.workdir, "urmb.tab")],
+                um = os.path.join(a.workdir, "unmatched_tab.txt")
+                d = subprocess.run([samdiff, os.path.join(a.workdir, "ref.tab"), os.path.join(a.workdir, "urmb.tab"), um],
                                    capture_output=True, text=True)
                 out["tabbedout_identity_vs_reference"] = json.loads(d.stdout) if d.returncode == 0 else {"error": d.stderr[-300:]}
+                if os.path.exists(um) and os.path.getsize(um):   # the lines only one of the two files has (and their SAM records)
+                    lines = open(um).read().split("\n")[:40]
+                    out["tabbedout_unmatched"] = lines
+                    names = {l.split("\t")[1] if l[:2] in ("a\t", "b\t") else l.split("\t")[0] for l in lines if l}
+                    recs = []
+                    for fn in ("ref.sam", "urmb.sam"):
+                        g = subprocess.run(["grep", "-m", "8", "-F", "-f", "/dev/stdin", os.path.join(a.workdir, fn)],
+                                           input="\n".join(n for n in names if n), capture_output=True, text=True)
+                        recs.append(g.stdout.split("\n")[:8])
+                    out["tabbedout_unmatched_sam"] = recs
     print(json.dumps(out))
     shutil.rmtree(a.workdir, ignore_errors=True)
 

@@ -2735,19 +2735,25 @@ __device__ __noinline__ void adjust_pair(Mate &F, Mate &R, const PairState &ps) 
 // ExtendPen of seed i of mate m on strand Plus: through the memo when Plus is the seed's own strand, otherwise
 // (search2m4.cpp:94-95,122 extend a stored seed on the strand dictated by the OTHER mate's seed) computed here.
 // m_SecondHit of both mates (search2.cpp:49-56) for -tabbedout; the array is zero-filled before every launch, so pairs
-// that never reach AdjustTopHitsAndMapqs with a second pair keep "no second hit".
+// that never reach AdjustTopHitsAndMapqs keep "no second hit".  A pair that does reach it without a second pair is written
+// as such: the big-capacity rerun searches a pair again whose first search -- over truncated lists -- may have left one
+// (seen once in 10 M pairs: a tandem-repeat pair, profiles/r07i).
 __device__ __forceinline__ void write_second(const Env &E, const Mate &F, const Mate &R, const PairState &ps, urmb_second *out,
                                              uint32_t u, uint32_t n_units) {
-    if (!out || ps.PairCount == 0 || ps.SecF < 0 || URMB_LANE != 0) return;
+    if (!out || URMB_LANE != 0) return;
     urmb_second a, b;
-    a.db_pos = F.g->hit_pos[ps.SecF];
-    a.score = F.g->hit_score[ps.SecF];
-    a.flags = (uint8_t)(2u | (F.g->hit_plus[ps.SecF] ? 1u : 0u));
-    a.pad = 0;
-    b.db_pos = R.g->hit_pos[ps.SecR];
-    b.score = R.g->hit_score[ps.SecR];
-    b.flags = (uint8_t)(2u | (R.g->hit_plus[ps.SecR] ? 1u : 0u));
-    b.pad = 0;
+    a.db_pos = b.db_pos = 0;
+    a.score = b.score = 0;
+    a.flags = b.flags = 0;
+    a.pad = b.pad = 0;
+    if (ps.PairCount != 0 && ps.SecF >= 0) {
+        a.db_pos = F.g->hit_pos[ps.SecF];
+        a.score = F.g->hit_score[ps.SecF];
+        a.flags = (uint8_t)(2u | (F.g->hit_plus[ps.SecF] ? 1u : 0u));
+        b.db_pos = R.g->hit_pos[ps.SecR];
+        b.score = R.g->hit_score[ps.SecR];
+        b.flags = (uint8_t)(2u | (R.g->hit_plus[ps.SecR] ? 1u : 0u));
+    }
     out[u] = a;
     out[n_units + u] = b;
 }

@@ -265,9 +265,9 @@ class ReferenceRunner:
     def available(self):
         return os.path.exists(self.bin)
 
-    def cmd(self, prefix, paired, sam):
+    def cmd(self, prefix, paired, sam, tab=None):
         c = ["-map2", prefix + "_1.fq", "-reverse", prefix + "_2.fq"] if paired else ["-map", prefix + "_1.fq"]
-        return [self.bin] + c + ["-ufi", self.ufi, "-samout", sam, "-threads", str(self.threads)]
+        return [self.bin] + c + ["-ufi", self.ufi, "-samout", sam, "-threads", str(self.threads)] + (["-tabbedout", tab] if tab else [])
 
     def _run(self, c, what):
         # The reference has no error channel but its exit status, and its multi-threaded mapper occasionally dies with
@@ -293,9 +293,9 @@ class ReferenceRunner:
             self.t_load, _ = self._run(self.cmd(tiny, paired, tiny + ".sam"), "index-load (4 reads)")
         return self.t_load
 
-    def run(self, prefix, paired, n_reads, sam, what="sample"):
+    def run(self, prefix, paired, n_reads, sam, what="sample", tab=None):
         t_load = self.load_seconds(prefix, paired)
-        t_run, text = self._run(self.cmd(prefix, paired, sam), what)
+        t_run, text = self._run(self.cmd(prefix, paired, sam, tab), what)
         dt = max(t_run - t_load, 1e-3)
         own = {}
         m = re.search(r"(\d+)\s+Seconds to load index", text)
@@ -320,13 +320,13 @@ def samdiff(a, b, unmatched=None):
     return json.loads(p.stdout)
 
 
-def run_cli_once(prefix, paired, ufi_path, sam, threads, **env):
-    """`urmap_b200 -map/-map2 ... -samout` (FASTQ files in, SAM file out); returns its stage times."""
+def run_cli_once(prefix, paired, ufi_path, sam, threads, tab=None, **env):
+    """`urmap_b200 -map/-map2 ... -samout [-tabbedout]` (FASTQ files in, SAM file out); returns its stage times."""
     exe = os.path.join(ROOT, "urmap_b200", "bin", "urmap_b200")
     c = ["-map2", prefix + "_1.fq", "-reverse", prefix + "_2.fq"] if paired else ["-map", prefix + "_1.fq"]
     t0 = time.time()
-    p = subprocess.run([exe] + c + ["-ufi", ufi_path, "-samout", sam, "-threads", str(threads)], capture_output=True,
-                       env=dict(os.environ, URMB_PROFILE="1", **env))
+    p = subprocess.run([exe] + c + ["-ufi", ufi_path, "-samout", sam, "-threads", str(threads)] + (["-tabbedout", tab] if tab else []),
+                       capture_output=True, env=dict(os.environ, URMB_PROFILE="1", **env))
     wall = time.time() - t0
     err = p.stderr.decode(errors="replace")
     if p.returncode != 0:
@@ -883,15 +883,23 @@ def main():
                             nu = len(offs) - 1
                             write_fastq_pair(px, a1, a2, nu, ec["read_len"], label=key + ".", mode="wb" if i == 0 else "ab")
                             n_reads += nu * (2 if kind_paired else 1)
-                        rr = ref.run(px, kind_paired, n_reads, px + "_ref.sam", "configs " + ",".join(keys))
-                        rc = run_cli_once(px, kind_paired, ufi_path, px + "_cli.sam", threads)
+                        # paired: the -tabbedout files (second pairs of FindPairs, outputtab2.cpp:85-119) are compared as well
+                        rtab, ctab = (px + "_ref.tab", px + "_cli.tab") if kind_paired else (None, None)
+                        rr = ref.run(px, kind_paired, n_reads, px + "_ref.sam", "configs " + ",".join(keys), tab=rtab)
+                        rc = run_cli_once(px, kind_paired, ufi_path, px + "_cli.sam", threads, tab=ctab)
                         d = samdiff(px + "_ref.sam", px + "_cli.sam", os.environ.get("URMB_BENCH_UNMATCHED") and
                                     os.environ["URMB_BENCH_UNMATCHED"] + ("_pe" if kind_paired else "_se") + ".txt")
+                        dt_ = samdiff(rtab, ctab, os.environ.get("URMB_BENCH_UNMATCHED") and
+                                      os.environ["URMB_BENCH_UNMATCHED"] + "_pe_tab.txt") if kind_paired else None
                         for key in keys:
                             g = d["groups"].get(key, {})
                             configs[key]["sam_identity"] = {"records": g.get("records_a", 0), "identical": g.get("identical", 0),
                                                             "pct": g.get("pct", 0.0), "cli_records": g.get("records_b", 0),
                                                             "header_equal": d["header_equal"]}
+                            if dt_:
+                                gt = dt_["groups"].get(key, {})
+                                configs[key]["tabbedout_identity"] = {"lines": gt.get("records_a", 0), "identical": gt.get("identical", 0),
+                                                                      "pct": gt.get("pct", 0.0), "cli_lines": gt.get("records_b", 0)}
                         for key in keys:
                             configs[key]["combined_run"] = {
                                 "configs": keys, "reads": n_reads,
@@ -901,7 +909,9 @@ def main():
                                 "cli_warnings": rc["warnings"]}
                         log(f"configs {keys}: SAM identity {[configs[k]['sam_identity']['pct'] for k in keys]}; reference "
                             f"{rr['reads_per_s'] / 1e6:.3f} M reads/s, CLI {n_reads / rc['seconds_in_mapper'] / 1e6:.2f} M reads/s")
-                        for sfx in ("_1.fq", "_2.fq", "_ref.sam", "_cli.sam"):
+                        if dt_:
+                            log(f"configs {keys}: -tabbedout identity {[configs[k]['tabbedout_identity']['pct'] for k in keys]}")
+                        for sfx in ("_1.fq", "_2.fq", "_ref.sam", "_cli.sam", "_ref.tab", "_cli.tab"):
                             if os.path.exists(px + sfx):
                                 os.unlink(px + sfx)
                     except Exception as e:

@@ -56,6 +56,13 @@ def emu_map(oix, res_dtype, seqs, offs, n_units, paired, method=6, pe_method=4, 
     return res, runs, counters
 
 
+def emu_first_look() -> int:
+    """Pairs the probe kernel's first look finished in the last emu_map call."""
+    L = lib()
+    L.emu_first_look.restype = C.c_uint32
+    return int(L.emu_first_look())
+
+
 def emu_build_index(seq: np.ndarray, slot_count: int, word_len: int = 24, max_ix: int = 32):
     """Runs the device index-builder kernels under emulation; returns (blob uint8[5*slot_count], stats)."""
     L = lib()

@@ -250,3 +250,40 @@ def test_emulated_maxix_above_32(oracle, built_lib, tmp_path):
     finally:
         ix.close()
         ix32.close()
+
+
+@pytest.mark.parametrize("pe_method", [4, 5])
+def test_emulated_first_look(oracle, built_lib, tmp_path, pe_method, monkeypatch):
+    """The probe kernel's first look at paired input (the seed-loop exit of Search4/5, search2m4.cpp:79-142, replayed over the
+    first eight iterator steps): a good part of clean pairs ends there with the oracle's records; switched off
+    (URMB_FLAGS bit 9) nothing ends there and nothing changes."""
+    import subprocess
+    import emu_py
+    from urmap_b200 import synth
+    g = synth.make_genome(1_000_000, n_contigs=2, seed=12, repeat_frac=0.10)
+    fa, ufi = str(tmp_path / "g.fa"), str(tmp_path / "g.ufi")
+    g.write_fasta(fa)
+    cli = os.path.join(ROOT, "urmap_b200", "bin", "urmap_b200")
+    r = subprocess.run([cli, "-make_ufi", fa, "-output", ufi, "-quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ix = oracle.Index(ufi)
+    try:
+        r1, r2, names = synth.sim_pe(g, 500, 150, 0.01, 0.001, seed=13)
+        f1, f2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+        synth.write_fastq(f1, r1, names, b"/1")
+        synth.write_fastq(f2, r2, names, b"/2")
+        b1, b2 = oracle.ReadBatch.from_fastq(f1), oracle.ReadBatch.from_fastq(f2)
+        br = 4 if pe_method == 5 else -1
+        o1, o2, uo = oracle.map_pe(ix, b1, b2, pe_method=pe_method, band_radius=br)
+        seqs = np.concatenate([b1.seqs, b2.seqs])
+        offs = np.concatenate([b1.offs, b2.offs[1:] + b1.offs[-1]]).astype(np.uint32)
+        looks = []
+        for flags in ("0", "512"):
+            monkeypatch.setenv("URMB_FLAGS", flags)
+            re_, ue, cnt = emu_py.emu_map(ix, oracle.RESULT_DTYPE, seqs, offs, b1.n, True, pe_method=pe_method, band_radius=br)
+            assert cnt[1] == 0
+            _same(np.concatenate([o1, o2]), uo, re_, ue)
+            looks.append(emu_py.emu_first_look())
+        assert looks[1] == 0 and looks[0] > 0.2 * b1.n, looks
+    finally:
+        ix.close()

@@ -937,8 +937,15 @@ def main():
         W = meta["word_length"]
         per_kernel, roof_gather, roof_alu = rooflines(kms, klaunch, algo, reads_per_step, rpu, RL, W, peaks, micro, traffic,
                                                       tv["first_look_frac"])
-        # `roofline` = the largest kernel class of the step over ALL classes (the side-stream rescue kernels included)
-        dominant = max(per_kernel, key=lambda c: per_kernel[c]["ms_per_step"])
+        # `roofline` = the largest kernel class on the step's critical path (the kernels of the compute stream, whose durations
+        # add up to the step); the mate-rescue classes run beside the following batches on the slots' side streams -- their
+        # launch durations are those of kernels waiting for room on busy SMs -- and the largest of them is reported as
+        # `roofline_side_stream`.  `per_kernel` has every class.
+        SIDE = ("rescue", "rescue_dp", "rescue_last", "rescue_legacy")
+        main_classes = [c for c in per_kernel if c not in SIDE] or list(per_kernel)
+        dominant = max(main_classes, key=lambda c: per_kernel[c]["ms_per_step"])
+        side_classes = [c for c in per_kernel if c in SIDE and "frac" in per_kernel[c]]
+        side_dom = max(side_classes, key=lambda c: per_kernel[c]["ms_per_step"]) if side_classes else None
         for key, c in configs.items():
             if "kernel_ms_per_step" in c:
                 ec = next(e for e in EXTRA_CONFIGS if e["key"] == key)
@@ -946,7 +953,7 @@ def main():
                 a = a if isinstance(a, dict) and "bytes" in a else dict(SURVEY_WORK)
                 pk, _, ra = rooflines(c["kernel_ms_per_step"], c["kernel_launches_per_step"], a, c["reads_per_step"],
                                       2 if ec["paired"] else 1, ec["read_len"], W, peaks, micro, {})
-                dom = max(pk, key=lambda k: pk[k]["ms_per_step"])
+                dom = max([k for k in pk if k not in SIDE] or list(pk), key=lambda k: pk[k]["ms_per_step"])
                 c["roofline"] = dict(pk[dom], kernel_class=dom)
                 c["roofline_dp_alu"] = ra
         line = {
@@ -960,6 +967,7 @@ def main():
             "first_look_frac": tv["first_look_frac"],   # pairs finished by the probe kernel's first look (seed-loop exit, search2m4.cpp:79-142)
             "clocks": clocks,
             "roofline": dict(per_kernel[dominant], kernel_class=dominant),
+            "roofline_side_stream": dict(per_kernel[side_dom], kernel_class=side_dom) if side_dom else None,
             "roofline_probe": per_kernel.get("probe"),
             "roofline_probe_gather": roof_gather,
             "roofline_dp_alu": roof_alu,

@@ -364,3 +364,41 @@ def test_cli_contig_end_overhang(cli, oracle, tmp_path):
     assert open(p("o_b.tab"), "rb").read() == open(p("ref_b.tab"), "rb").read()
     c = synth.compare_sam(p("ref.sam"), p("o.sam"))
     assert c["identical"] == c["total"] == 2 * len(names) and c["header_equal"], c["diffs"][:5]
+
+
+def test_ufi_validate(cli, oracle, golden_dir, tmp_path):
+    """-ufi_validate and -make_ufi ... -validate (cmd_ufi_validate ufistats.cpp:141-146, UFIndex::Validate ufindex.cpp:611-658):
+    silent success on consistent tables -- the golden one and a dense one full of long links -- and the reference's fatal
+    "WordToSlot != Slot" on a table with one stored position moved (the reference binary judges the same file the same way)."""
+    import struct
+    golden = os.path.join(golden_dir, "ref.ufi")
+    r = run([cli, "-ufi_validate", golden, "-quiet"])
+    assert r.returncode == 0, r.stderr
+    dense = str(tmp_path / "dense.ufi")
+    r = run([cli, "-make_ufi", os.path.join(golden_dir, "ref.fa"), "-output", dense, "-load_factor", "0.95", "-validate", "-quiet"])
+    assert r.returncode == 0, r.stderr
+    raw = open(dense, "rb").read()
+    hdr = raw.index(struct.pack("<I", 0x55464932)) + 4
+    slots = struct.unpack_from("<Q", raw, 16)[0]
+    tallies = raw[hdr:hdr + 5 * slots:5]
+    assert tallies.count(bytes([125])) > 100   # long links are there
+    r = run([cli, "-ufi_validate", dense, "-quiet", "-threads", "3"])
+    assert r.returncode == 0, r.stderr
+    # move the position stored in the first BOTH1 slot by one base: its 24-mer no longer hashes to the slot
+    raw = bytearray(open(golden, "rb").read())
+    hdr = raw.index(struct.pack("<I", 0x55464932)) + 4
+    slots = struct.unpack_from("<Q", raw, 16)[0]
+    s = next(i for i in range(slots) if raw[hdr + 5 * i] == 255)
+    pos = struct.unpack_from("<I", raw, hdr + 5 * s + 1)[0]
+    struct.pack_into("<I", raw, hdr + 5 * s + 1, pos + 1)
+    bad = str(tmp_path / "bad.ufi")
+    open(bad, "wb").write(raw)
+    r = run([cli, "-ufi_validate", bad])
+    assert r.returncode == 1 and "---Fatal error---" in r.stderr and "WordToSlot != Slot" in r.stderr
+    if os.path.exists(oracle.REF_BIN):
+        import subprocess
+        for path, ok in ((golden, True), (dense, True), (bad, False)):
+            p = subprocess.run([oracle.REF_BIN, "-ufi_validate", path, "-quiet"], capture_output=True, text=True)
+            assert (p.returncode == 0) == ok
+            if not ok:
+                assert "WordToSlot != Slot" in p.stderr

@@ -6,6 +6,7 @@
 //   urmap_b200 -map reads.fq[.gz] -ufi ref.ufi -samout out.sam [-threads N] [-veryfast] [-gpus G] [-batch N]
 //   urmap_b200 -map2 R1.fq -reverse R2.fq -ufi ref.ufi -samout out.sam [-tabbedout out.tab] [-threads N] [-veryfast] [-minq 10]
 //   urmap_b200 -ufi_info ref.ufi
+//   urmap_b200 -ufi_validate ref.ufi          (also: -make_ufi ... -validate)
 //
 // Reference behaviour restated here (file:line under /root/reference/src):
 //   option spellings / errors   cmdline.cpp:148-269, myopts.h, getcmd.cpp:6-26, myutils.cpp:915-960
@@ -92,10 +93,10 @@ static double now_s() {
 // options
 // ------------------------------------------------------------------------------------------------
 struct Opts {
-    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots, ufi_info, fastq_dump, sam_bench, tabbedout;
+    std::string make_ufi, map, map2, reverse, ufi, samout, output, log, slots, ufi_info, ufi_validate, fastq_dump, sam_bench, tabbedout;
     unsigned threads = 0, wordlength = 24, maxix = 32, minq = 10, gpus = 1, batch = 262144;
     double load_factor = 0.6;
-    bool veryfast = false, quiet = false, gpu_build = false, version = false;
+    bool veryfast = false, quiet = false, gpu_build = false, version = false, validate = false;
     bool set_maxix = false, set_wordlength = false, set_threads = false;
 };
 
@@ -119,6 +120,8 @@ static Opts ParseCmdLine(int argc, char **argv) {
         else if (name == "map2") o.map2 = val();
         else if (name == "reverse") o.reverse = val();
         else if (name == "ufi_info") o.ufi_info = val();
+        else if (name == "ufi_validate") o.ufi_validate = val();
+        else if (name == "validate") o.validate = true;
         else if (name == "fastq_dump") o.fastq_dump = val();
         else if (name == "sam_bench") o.sam_bench = val();
         else if (name == "ufi") o.ufi = val();
@@ -141,7 +144,7 @@ static Opts ParseCmdLine(int argc, char **argv) {
         else bad("Unknown option " + name);
     }
     int ncmd = (!o.make_ufi.empty()) + (!o.map.empty()) + (!o.map2.empty()) + (o.version ? 1 : 0) + (!o.ufi_info.empty()) +
-               (!o.fastq_dump.empty()) + (!o.sam_bench.empty());
+               (!o.ufi_validate.empty()) + (!o.fastq_dump.empty()) + (!o.sam_bench.empty());
     if (ncmd == 0) bad("No command specified");       // getcmd.cpp:6-11
     if (ncmd > 1) bad("Two commands specified");
     return o;
@@ -1622,6 +1625,8 @@ struct UfiBuilder {
 };
 
 extern "C" int urmb_host_gpu_build(const uint8_t *seq, uint64_t n, uint64_t slots, uint32_t W, uint32_t maxix, uint8_t *blob);
+static std::string ValidateTable(const uint8_t *Blob, const uint8_t *Seq, uint64_t SlotCount, uint32_t SeqDataSize, uint32_t W,
+                                 uint32_t MaxIx, int nthreads);
 
 static int CmdMakeUfi(const Opts &o) {  // cmd_make_ufi, ufindexio.cpp:117-179
     UfiBuilder B;
@@ -1660,7 +1665,102 @@ static int CmdMakeUfi(const Opts &o) {  // cmd_make_ufi, ufindexio.cpp:117-179
         B.MakeIndex();
         Progress("Index built in %.1f s\n%u slots truncated\n", now_s() - t0, B.Truncated);
     }
+    if (o.validate) {   // ufindexio.cpp:171-172
+        Progress("Validate\n");
+        const int nthreads = o.set_threads ? (int)std::max(1u, o.threads) : std::max(1, std::min((int)std::thread::hardware_concurrency(), 32));
+        const std::string err = ValidateTable(B.Blob.data(), B.Seq.data(), B.SlotCount, (uint32_t)B.Seq.size(), B.W, B.MaxIx, nthreads);
+        if (!err.empty()) Die("%s", err.c_str());
+    }
     B.ToFile(o.output);
+    return 0;
+}
+
+// UFIndex::Validate / ValidateSlot / GetRow_Validate (ufindex.cpp:611-658, 834-882): every position stored in the list of every
+// owned slot must hash back to that slot.  The reference walks the table on one thread and dies at the first failure with
+// "WordToSlot != Slot" (its asserts on the list structure die with their own text); here the slot range is split over the
+// host threads and the failure at the lowest slot is reported -- the same one.  Returns "" when the table is consistent.
+static std::string ValidateTable(const uint8_t *Blob, const uint8_t *Seq, uint64_t SlotCount, uint32_t SeqDataSize, uint32_t W,
+                                 uint32_t MaxIx, int nthreads) {
+    auto tally = [&](uint64_t s) { return Blob[5 * s]; };
+    auto pos = [&](uint64_t s) { uint32_t v; memcpy(&v, Blob + 5 * s + 1, 4); return v; };
+    uint64_t bad_slot = UINT64_MAX;
+    std::string bad_msg;
+    std::mutex mu;
+    auto fail = [&](uint64_t s, const char *msg) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (s < bad_slot) { bad_slot = s; bad_msg = msg; }
+    };
+    const uint64_t piece = (SlotCount + (uint64_t)nthreads * 64 - 1) / ((uint64_t)nthreads * 64);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int64_t chunk = 0; chunk < (int64_t)nthreads * 64; ++chunk) {
+        std::vector<uint32_t> PosVec(MaxIx);
+        const uint64_t lo = (uint64_t)chunk * piece, hi = std::min(SlotCount, lo + piece);
+        for (uint64_t Slot = lo; Slot < hi; ++Slot) {
+            if (Slot > bad_slot) break;   // a failure at a lower slot is already known
+            uint8_t T = tally(Slot);
+            if ((T & 128) == 0) continue;   // TallyOther: not the head of a list
+            uint64_t Slot2 = Slot;
+            uint32_t K = 0;
+            const char *err = nullptr;
+            for (;;) {   // GetRow_Validate
+                T = tally(Slot2);
+                const uint32_t P = pos(Slot2);
+                PosVec[K++] = P;
+                if (T == 254 || T == 255) break;        // PLUS1 / BOTH1: a single entry
+                if (K == MaxIx) break;
+                if ((Slot2 == Slot) != ((T & 128) != 0)) { err = "list element with the wrong owner bit"; break; }   // asserta(TallyMine / TallyOther)
+                if (T == 127) break;                    // END
+                if (T == 253 || T == 125) {             // long link: the position is parked in slot + StepA
+                    const uint64_t SlotA = (Slot2 + (P & 0xffffu)) % SlotCount;
+                    Slot2 = (SlotA + (P >> 16)) % SlotCount;
+                    PosVec[K - 1] = pos(SlotA);
+                    if (tally(SlotA) != 125) { err = "long link without its parking slot"; break; }   // asserta(TA == TALLY_NEXT_LONG_OTHER)
+                } else {
+                    const uint32_t Next = T & 127u;
+                    if (Next == 0 || Next > 124) { err = "bad link step"; break; }
+                    Slot2 = (Slot2 + Next) % SlotCount;
+                }
+            }
+            if (err) { fail(Slot, err); break; }
+            for (uint32_t k = 0; k < K && !err; ++k) {   // ValidateSlot
+                const uint32_t P = PosVec[k];
+                if (P >= SeqDataSize || (uint64_t)P + W > SeqDataSize) { err = "position beyond the sequence data"; break; }
+                uint64_t Word = 0;
+                bool valid = true;
+                for (uint32_t i = 0; i < W; ++i) {   // GetWord, ufindex.cpp:68-81
+                    const uint8_t c = Seq[P + i] & 0xDF;
+                    const uint32_t l = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : (c == 'T' || c == 'U') ? 3 : 4;
+                    if (l > 3) { valid = false; break; }
+                    Word = (Word << 2) | l;
+                }
+                if (!valid) Word = UINT64_MAX;
+                uint64_t h = Word;   // WordToSlot, ufindex.h:50-65
+                h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;
+                if (h % SlotCount != Slot) err = "WordToSlot != Slot";
+            }
+            if (err) { fail(Slot, err); break; }
+        }
+    }
+    if (bad_slot == UINT64_MAX) return std::string();
+    char t[160];
+    snprintf(t, sizeof t, "%s (slot 0x%llx)", bad_msg.c_str(), (unsigned long long)bad_slot);
+    return bad_msg == "WordToSlot != Slot" ? bad_msg : std::string(t);
+}
+
+// cmd_ufi_validate, ufistats.cpp:141-146
+static int CmdUfiValidate(const Opts &o) {
+    urmb_index_host *h = nullptr;
+    Progress("Reading index %s\n", o.ufi_validate.c_str());
+    if (urmb_index_load_host(o.ufi_validate.c_str(), &h) != 0) Die("%s", urmb_last_error(nullptr));
+    urmb_index_desc d;
+    uint32_t nc = 0;
+    if (urmb_index_info(h, &d, &nc) != 0) Die("%s", urmb_last_error(nullptr));
+    const int nthreads = o.set_threads ? (int)std::max(1u, o.threads) : std::max(1, std::min((int)std::thread::hardware_concurrency(), 32));
+    Progress("Validate\n");
+    const std::string err = ValidateTable((const uint8_t *)d.d_blob, (const uint8_t *)d.d_seq, d.slot_count, d.seq_data_size,
+                                          d.word_length, d.max_ix, nthreads);
+    urmb_index_free_host(h);
+    if (!err.empty()) Die("%s", err.c_str());
     return 0;
 }
 
@@ -1807,6 +1907,7 @@ int main(int argc, char **argv) {
     if (o.version) { printf("urmap_b200 v%s (B200-native drop-in for urmap -map/-map2)\n", URMB_VERSION); return 0; }
     if (!o.make_ufi.empty()) return CmdMakeUfi(o);
     if (!o.ufi_info.empty()) return CmdUfiInfo(o);
+    if (!o.ufi_validate.empty()) return CmdUfiValidate(o);
     if (!o.fastq_dump.empty()) return CmdFastqDump(o);
     if (!o.sam_bench.empty()) return CmdSamBench(o);
     if (!o.map.empty()) return CmdMap(o, false);

@@ -402,3 +402,15 @@ def test_ufi_validate(cli, oracle, golden_dir, tmp_path):
             assert (p.returncode == 0) == ok
             if not ok:
                 assert "WordToSlot != Slot" in p.stderr
+
+
+def test_args_file(cli, golden_dir, tmp_path):
+    """`file: args.txt` on the command line stands for the fields of that file, '#' starts a comment (cmdline.cpp:40-56,162-179)."""
+    args = tmp_path / "args.txt"
+    out = tmp_path / "o.ufi"
+    args.write_text("-make_ufi %s   # the reference\n\n  -output %s\n-quiet\n" % (os.path.join(golden_dir, "ref.fa"), out))
+    r = run([cli, "file:", str(args)])
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "ref.ufi"), "rb").read()
+    r = run([cli, "-ufi_info", "file:", str(args)])   # "-ufi_info -make_ufi ...": two commands
+    assert r.returncode == 1 and "Invalid command line" in r.stderr

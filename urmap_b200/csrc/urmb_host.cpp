@@ -102,11 +102,49 @@ struct Opts {
 
 static Opts ParseCmdLine(int argc, char **argv) {
     Opts o;
-    for (int i = 0; i < argc; ++i) g_argv.push_back(argv[i]);
     auto bad = [&](const std::string &why) {
         fprintf(stderr, "\nInvalid command line\n%s\n\n", why.c_str());  // cmdline.cpp:28-38
         exit(1);
     };
+    // "file: args.txt" anywhere on the command line is replaced by the white-space separated fields of that file, '#' starts
+    // a comment (cmdline.cpp:40-56,162-179)
+    std::vector<std::string> args;
+    for (int i = 0; i < argc;) {
+        if (std::string(argv[i]) == "file:" && i + 1 < argc) {
+            FILE *f = fopen(argv[i + 1], "rb");
+            if (!f) Die("Cannot open %s", argv[i + 1]);
+            std::string line;
+            int c;
+            auto flush = [&]() {
+                const size_t h = line.find('#');
+                if (h != std::string::npos) line.resize(h);
+                size_t k = 0;
+                while (k < line.size()) {
+                    while (k < line.size() && isspace((unsigned char)line[k])) ++k;
+                    size_t e = k;
+                    while (e < line.size() && !isspace((unsigned char)line[e])) ++e;
+                    if (e > k) args.push_back(line.substr(k, e - k));
+                    k = e;
+                }
+                line.clear();
+            };
+            while ((c = fgetc(f)) != EOF) {
+                if (c == '\n') flush();
+                else if (c != '\r') line.push_back((char)c);
+            }
+            flush();
+            fclose(f);
+            i += 2;
+        } else {
+            args.push_back(argv[i]);
+            i += 1;
+        }
+    }
+    g_argv = args;
+    argc = (int)args.size();
+    std::vector<char *> argp;
+    for (auto &a : args) argp.push_back(const_cast<char *>(a.c_str()));
+    argv = argp.data();
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a.size() < 2 || a[0] != '-') bad("Expected -option_name, got '" + a + "'");

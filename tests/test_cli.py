@@ -72,6 +72,7 @@ def test_cli_sam_matches_golden(cli, golden_dir, tmp_path, name, args):
     r = run([cli] + args + ["-ufi", os.path.join(golden_dir, "ref.ufi"), "-samout", str(out), "-threads", "4", "-batch", "97"])
     assert r.returncode == 0, r.stderr
     assert "Reads/sec" in r.stderr and "Mapped Q>=10" in r.stderr
+    assert _unused(r.stderr) == []
     a = open(os.path.join(golden_dir, name), "rb").read().split(b"\n")
     b = open(out, "rb").read().split(b"\n")
     strip = lambda ls: [l for l in ls if not l.startswith(b"@PG")]
@@ -414,3 +415,32 @@ def test_args_file(cli, golden_dir, tmp_path):
     assert open(out, "rb").read() == open(os.path.join(golden_dir, "ref.ufi"), "rb").read()
     r = run([cli, "-ufi_info", "file:", str(args)])   # "-ufi_info -make_ufi ...": two commands
     assert r.returncode == 1 and "Invalid command line" in r.stderr
+
+
+def _unused(stderr):
+    return [l.split("Option -")[1].split()[0] for l in stderr.splitlines() if "WARNING: Option -" in l and "not used" in l]
+
+
+@pytest.mark.parametrize("cmd", ["make_ufi", "ufi_info", "ufi_validate"])
+def test_unused_option_warnings(cli, oracle, golden_dir, tmp_path, cmd):
+    """CheckUsedOpts (cmdline.cpp:13-26): an option that was given but that the command never looks at is named in a warning
+    after the command has run, in the order of myopts.h -- the same names in the same order as the reference binary prints
+    (this program uses -threads for -ufi_validate, the one deliberate difference)."""
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("reference binary not available")
+    import subprocess
+    g = golden_dir
+    base = {"make_ufi": ["-make_ufi", os.path.join(g, "ref.fa"), "-output", str(tmp_path / "o.ufi")],
+            "ufi_info": ["-ufi_info", os.path.join(g, "ref.ufi")],
+            "ufi_validate": ["-ufi_validate", os.path.join(g, "ref.ufi")]}[cmd]
+    extras = ["-veryfast", "-minq", "7", "-reverse", os.path.join(g, "pe_2.fq"), "-threads", "2", "-maxix", "32", "-validate",
+              "-load_factor", "0.6", "-wordlength", "24", "-ufi", os.path.join(g, "ref.ufi"), "-samout", str(tmp_path / "x.sam")]
+    if cmd == "make_ufi":
+        extras = [e for e in extras if e not in ("-maxix", "32", "-wordlength", "24", "-load_factor", "0.6", "-validate")] + ["-validate"]
+    ref = subprocess.run([oracle.REF_BIN] + base + extras, capture_output=True, text=True)
+    mine = run([cli] + base + extras)
+    assert ref.returncode == 0 and mine.returncode == 0, (ref.stderr[-300:], mine.stderr[-300:])
+    want = _unused(ref.stderr)
+    if cmd == "ufi_validate":
+        want = [w for w in want if w != "threads"]
+    assert _unused(mine.stderr) == want and len(want) >= 3

@@ -98,6 +98,7 @@ struct Opts {
     double load_factor = 0.6;
     bool veryfast = false, quiet = false, gpu_build = false, version = false, validate = false;
     bool set_maxix = false, set_wordlength = false, set_threads = false;
+    std::vector<std::string> given;   // every option name on the command line (CheckUsedOpts, cmdline.cpp:13-26)
 };
 
 static Opts ParseCmdLine(int argc, char **argv) {
@@ -149,6 +150,7 @@ static Opts ParseCmdLine(int argc, char **argv) {
         std::string a = argv[i];
         if (a.size() < 2 || a[0] != '-') bad("Expected -option_name, got '" + a + "'");
         std::string name = a.substr(a[1] == '-' ? 2 : 1);
+        o.given.push_back(name);
         auto val = [&]() -> std::string {
             if (i + 1 >= argc) bad("Missing value for option -" + name);
             return std::string(argv[++i]);
@@ -1937,17 +1939,42 @@ static int CmdSamBench(const Opts &o) {
     return 0;
 }
 
+// CheckUsedOpts (cmdline.cpp:13-26, urmap_main.cpp:37): after a command that ends normally every option that was given but
+// never looked at gets "WARNING: Option -x not used", in the order of myopts.h.  Which options a command looks at was taken
+// from the reference binary itself, one extra option at a time; the output files, -log and -quiet count as used everywhere
+// (main opens them), and so do this program's own options (-gpus, -batch, -gpu_build; -threads with -ufi_validate).
+static void WarnUnusedOpts(const Opts &o, const char *cmd) {
+    static const char *order[] = {"slots", "ufi", "reverse", "threads", "wordlength", "minq", "maxix", "load_factor", "validate", "veryfast"};
+    const std::string c = cmd;
+    auto used = [&](const std::string &n) {
+        if (c == "make_ufi") return n == "slots" || n == "wordlength" || n == "maxix" || n == "load_factor" || n == "validate" || n == "veryfast";
+        if (c == "map") return n == "ufi" || n == "threads" || n == "veryfast";
+        if (c == "map2") return n == "ufi" || n == "reverse" || n == "threads" || n == "minq" || n == "veryfast";
+        if (c == "ufi_validate") return n == "threads";
+        return false;   // ufi_info
+    };
+    for (const char *n : order)
+        if (std::find(o.given.begin(), o.given.end(), n) != o.given.end() && !used(n)) {
+            fprintf(stderr, "\nWARNING: Option -%s not used\n\n", n);   // Warning_, myutils.cpp:965-982
+            if (g_log) fprintf(g_log, "\nWARNING: Option -%s not used\n", n);
+        }
+}
+
 int main(int argc, char **argv) {
     InitAlpha();
     Opts o = ParseCmdLine(argc, argv);
     g_quiet = o.quiet;
     if (!o.log.empty()) g_log = fopen(o.log.c_str(), "w");
     if (o.version) { printf("urmap_b200 v%s (B200-native drop-in for urmap -map/-map2)\n", URMB_VERSION); return 0; }
-    if (!o.make_ufi.empty()) return CmdMakeUfi(o);
-    if (!o.ufi_info.empty()) return CmdUfiInfo(o);
-    if (!o.ufi_validate.empty()) return CmdUfiValidate(o);
-    if (!o.fastq_dump.empty()) return CmdFastqDump(o);
-    if (!o.sam_bench.empty()) return CmdSamBench(o);
-    if (!o.map.empty()) return CmdMap(o, false);
-    return CmdMap(o, true);
+    int rc;
+    const char *cmd = nullptr;
+    if (!o.make_ufi.empty()) { rc = CmdMakeUfi(o); cmd = "make_ufi"; }
+    else if (!o.ufi_info.empty()) { rc = CmdUfiInfo(o); cmd = "ufi_info"; }
+    else if (!o.ufi_validate.empty()) { rc = CmdUfiValidate(o); cmd = "ufi_validate"; }
+    else if (!o.fastq_dump.empty()) rc = CmdFastqDump(o);
+    else if (!o.sam_bench.empty()) rc = CmdSamBench(o);
+    else if (!o.map.empty()) { rc = CmdMap(o, false); cmd = "map"; }
+    else { rc = CmdMap(o, true); cmd = "map2"; }
+    if (rc == 0 && cmd) WarnUnusedOpts(o, cmd);
+    return rc;
 }

@@ -444,3 +444,23 @@ def test_unused_option_warnings(cli, oracle, golden_dir, tmp_path, cmd):
     if cmd == "ufi_validate":
         want = [w for w in want if w != "threads"]
     assert _unused(mine.stderr) == want and len(want) >= 3
+
+
+@pytest.mark.gpu
+def test_cli_unused_options_map(cli, golden_dir, tmp_path):
+    """-map looks at neither -minq nor -load_factor, -map2 looks at -minq (probed on the reference binary): the warnings come
+    after the run, in the order of myopts.h; the log file ends with the reference's Finished / Elapsed time / Max memory lines."""
+    if not have_gpu():
+        pytest.skip("no CUDA device")
+    ufi = os.path.join(golden_dir, "ref.ufi")
+    log = tmp_path / "run.log"
+    r = run([cli, "-map", os.path.join(golden_dir, "se.fq"), "-ufi", ufi, "-samout", str(tmp_path / "a.sam"), "-load_factor", "0.6",
+             "-minq", "7", "-log", str(log)])
+    assert r.returncode == 0, r.stderr
+    assert _unused(r.stderr) == ["minq", "load_factor"]
+    text = log.read_text()
+    assert "Started " in text and "Finished " in text and "Elapsed time " in text and "Option -minq not used" in text
+    r = run([cli, "-map2", os.path.join(golden_dir, "pe_1.fq"), "-reverse", os.path.join(golden_dir, "pe_2.fq"), "-ufi", ufi,
+             "-samout", str(tmp_path / "b.sam"), "-minq", "7", "-maxix", "32"])
+    assert r.returncode == 0, r.stderr
+    assert _unused(r.stderr) == ["maxix"]

@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -1197,6 +1198,44 @@ class SamSink {
 // The host pipeline, one thread per stage, every stage internally parallel or cheap:
 //   reader (block FASTQ parse, rpool) -> main (urmb_submit / urmb_wait: the only thread that talks to the C ABI)
 //   -> formatter (SAM text, fpool) -> writer (write(2) in record order)
+static std::string MemBytesToStr(double Bytes);
+// CheckUsedOpts (cmdline.cpp:13-26, urmap_main.cpp:37): after a command that ends normally every option that was given but
+// never looked at gets "WARNING: Option -x not used", in the order of myopts.h.  Which options a command looks at was taken
+// from the reference binary itself, one extra option at a time; the output files, -log and -quiet count as used everywhere
+// (main opens them), and so do this program's own options (-gpus, -batch, -gpu_build; -threads with -ufi_validate).
+static void WarnUnusedOpts(const Opts &o, const char *cmd) {
+    static const char *order[] = {"slots", "ufi", "reverse", "threads", "wordlength", "minq", "maxix", "load_factor", "validate", "veryfast"};
+    const std::string c = cmd;
+    auto used = [&](const std::string &n) {
+        if (c == "make_ufi") return n == "slots" || n == "wordlength" || n == "maxix" || n == "load_factor" || n == "validate" || n == "veryfast";
+        if (c == "map") return n == "ufi" || n == "threads" || n == "veryfast";
+        if (c == "map2") return n == "ufi" || n == "reverse" || n == "threads" || n == "minq" || n == "veryfast";
+        if (c == "ufi_validate") return n == "threads";
+        return false;   // ufi_info
+    };
+    for (const char *n : order)
+        if (std::find(o.given.begin(), o.given.end(), n) != o.given.end() && !used(n)) {
+            fprintf(stderr, "\nWARNING: Option -%s not used\n\n", n);   // Warning_, myutils.cpp:965-982
+            if (g_log) fprintf(g_log, "\nWARNING: Option -%s not used\n", n);
+        }
+}
+
+static time_t g_started = 0;
+// What urmap_main.cpp:36-39 does after a command that ended normally: unused-option warnings, then elapsed time and memory
+// into the log file.
+static void FinishRun(const Opts &o, const char *cmd) {
+    WarnUnusedOpts(o, cmd);
+    if (g_log) {   // LogElapsedTimeAndRAM, myutils.cpp
+        const time_t t_done = time(nullptr);
+        const long secs = (long)(t_done - g_started);
+        struct rusage ru;
+        getrusage(RUSAGE_SELF, &ru);
+        fprintf(g_log, "\nFinished %sElapsed time %02ld:%02ld\nMax memory %s\n", ctime(&t_done), secs / 60, secs % 60,
+                MemBytesToStr((double)ru.ru_maxrss * 1024.0).c_str());
+        fflush(g_log);
+    }
+}
+
 static int CmdMap(const Opts &o, bool paired) {
     if (o.ufi.empty()) Die("-ufi required");
     if (paired && o.reverse.empty()) Die("-reverse required");  // map2.cpp:42
@@ -1442,7 +1481,8 @@ static int CmdMap(const Opts &o, bool paired) {
     if (overflowed)
         Progress("\nWARNING: %llu read(s) exceeded a per-read capacity of the GPU search (hit / HSP / path lists); their records "
                  "are reported but may differ from urmap's\n\n", (unsigned long long)overflowed);
-    if (g_log) fclose(g_log);
+    FinishRun(o, paired ? "map2" : "map");
+    if (g_log) { fclose(g_log); g_log = nullptr; }
     fflush(nullptr);
     if (!getenv("URMB_TEARDOWN")) _exit(0);   // the output is complete: leave the 70 GB of mappings and device memory to the OS
     for (auto c : ctxs) urmb_ctx_destroy(c);
@@ -1939,32 +1979,19 @@ static int CmdSamBench(const Opts &o) {
     return 0;
 }
 
-// CheckUsedOpts (cmdline.cpp:13-26, urmap_main.cpp:37): after a command that ends normally every option that was given but
-// never looked at gets "WARNING: Option -x not used", in the order of myopts.h.  Which options a command looks at was taken
-// from the reference binary itself, one extra option at a time; the output files, -log and -quiet count as used everywhere
-// (main opens them), and so do this program's own options (-gpus, -batch, -gpu_build; -threads with -ufi_validate).
-static void WarnUnusedOpts(const Opts &o, const char *cmd) {
-    static const char *order[] = {"slots", "ufi", "reverse", "threads", "wordlength", "minq", "maxix", "load_factor", "validate", "veryfast"};
-    const std::string c = cmd;
-    auto used = [&](const std::string &n) {
-        if (c == "make_ufi") return n == "slots" || n == "wordlength" || n == "maxix" || n == "load_factor" || n == "validate" || n == "veryfast";
-        if (c == "map") return n == "ufi" || n == "threads" || n == "veryfast";
-        if (c == "map2") return n == "ufi" || n == "reverse" || n == "threads" || n == "minq" || n == "veryfast";
-        if (c == "ufi_validate") return n == "threads";
-        return false;   // ufi_info
-    };
-    for (const char *n : order)
-        if (std::find(o.given.begin(), o.given.end(), n) != o.given.end() && !used(n)) {
-            fprintf(stderr, "\nWARNING: Option -%s not used\n\n", n);   // Warning_, myutils.cpp:965-982
-            if (g_log) fprintf(g_log, "\nWARNING: Option -%s not used\n", n);
-        }
-}
-
 int main(int argc, char **argv) {
     InitAlpha();
     Opts o = ParseCmdLine(argc, argv);
     g_quiet = o.quiet;
     if (!o.log.empty()) g_log = fopen(o.log.c_str(), "w");
+    g_started = time(nullptr);
+    const time_t t_started = g_started;
+    if (g_log) {   // LogProgramInfoAndCmdLine, myutils.cpp: program, command line, start time
+        fprintf(g_log, "\nurmap_b200 v%s\n", URMB_VERSION);
+        for (auto &a : g_argv) fprintf(g_log, "%s ", a.c_str());
+        fprintf(g_log, "\nStarted %s", ctime(&t_started));
+        fflush(g_log);
+    }
     if (o.version) { printf("urmap_b200 v%s (B200-native drop-in for urmap -map/-map2)\n", URMB_VERSION); return 0; }
     int rc;
     const char *cmd = nullptr;
@@ -1975,6 +2002,6 @@ int main(int argc, char **argv) {
     else if (!o.sam_bench.empty()) rc = CmdSamBench(o);
     else if (!o.map.empty()) { rc = CmdMap(o, false); cmd = "map"; }
     else { rc = CmdMap(o, true); cmd = "map2"; }
-    if (rc == 0 && cmd) WarnUnusedOpts(o, cmd);
+    if (rc == 0 && cmd && std::string(cmd) != "map" && std::string(cmd) != "map2") FinishRun(o, cmd);   // CmdMap finishes its own run
     return rc;
 }

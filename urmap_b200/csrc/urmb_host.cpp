@@ -1457,6 +1457,7 @@ static int CmdMap(const Opts &o, bool paired) {
                 "%.3fs, gpu wait %.3fs, result copy %.3fs), formatter %.3fs, writer %.3fs; mapper total %.3fs\n",
                 (unsigned long long)k, t_loaded - t_start, t_read, t_qwait, t_submit, t_gpuwait, t_copy, t_format, t_write, secs);
     auto pct = [&](uint64_t x) { return total.query ? 100.0 * x / total.query : 0.0; };
+    if (g_log) fprintf(g_log, "@rps=%.1f\n", secs > 0 ? total.query / secs : 0.0);   // state1.cpp:608
     Progress("\n%16.1f  Seconds to load index\n%16.1f  Seconds in mapper\n", t_loaded - t_start, secs);  // state1.cpp:593-632
     Progress("%16s  Reads (%llu)\n", Commas(total.query).c_str(), (unsigned long long)total.query);
     Progress("%16.0f  Reads/sec. (%d GPUs, %d host threads)\n", secs > 0 ? total.query / secs : 0.0, ngpu, nthreads);
